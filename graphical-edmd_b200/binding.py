@@ -1,0 +1,234 @@
+"""ctypes mirror of include/edmd_cuda.h (the drop-in C ABI).
+
+Nothing here computes anything: every method forwards to libedmd_cuda.so and
+raises EdmdError when the library reports a failure.  If the library is missing
+the import of this module still works but ``load_library`` raises -- there is
+no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libedmd_cuda.so"
+
+MODE_NORMAL, MODE_GROW = 0, 1
+EV_CELLCROSS, EV_COLLISION = 0, 1
+EINVAL, ESTATE, EOVERLAP, ECELL, ENOMEM = 1, 2, 3, 4, 5
+BENCH_SWEEP, BENCH_FREEFLY, BENCH_BOOP, BENCH_PCF = 0, 1, 2, 3
+
+# every symbol include/edmd_cuda.h declares
+SYMBOLS = [
+    "edmd_cuda_create", "edmd_cuda_destroy", "edmd_cuda_last_error",
+    "edmd_cuda_get_box", "edmd_cuda_launch_count", "edmd_cuda_upload",
+    "edmd_cuda_upload_aos", "edmd_cuda_predict_all", "edmd_cuda_predict_device",
+    "edmd_cuda_fetch_predictions", "edmd_cuda_set_growth", "edmd_cuda_free_fly",
+    "edmd_cuda_download_state", "edmd_cuda_pcf", "edmd_cuda_boop_cutoff",
+    "edmd_cuda_bench",
+]
+
+
+class Box(C.Structure):
+    _fields_ = [("n", C.c_int32), ("nxcells", C.c_int32), ("nycells", C.c_int32),
+                ("lx", C.c_double), ("ly", C.c_double), ("half_lx", C.c_double),
+                ("half_ly", C.c_double), ("cellx_size", C.c_double),
+                ("celly_size", C.c_double), ("cellx_fac", C.c_double),
+                ("celly_fac", C.c_double), ("dt_paul", C.c_double)]
+
+
+class EdmdError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"edmd_cuda error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path: os.PathLike | None = None) -> C.CDLL:
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise FileNotFoundError(
+            f"{p} not built -- run `make cuda` (or __graft_entry__.build()); "
+            "there is no CPU fallback for the hot path")
+    lib = C.CDLL(str(p))
+    dp, ip, u8p = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    vp = C.c_void_p
+    lib.edmd_cuda_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
+    lib.edmd_cuda_destroy.argtypes = [vp]
+    lib.edmd_cuda_destroy.restype = None
+    lib.edmd_cuda_last_error.argtypes = [vp]
+    lib.edmd_cuda_last_error.restype = C.c_char_p
+    lib.edmd_cuda_get_box.argtypes = [vp, C.POINTER(Box)]
+    lib.edmd_cuda_launch_count.argtypes = [vp]
+    lib.edmd_cuda_launch_count.restype = C.c_uint64
+    lib.edmd_cuda_upload.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_double]
+    lib.edmd_cuda_upload_aos.argtypes = [vp, vp] + [C.c_size_t] * 7 + [C.c_double]
+    lib.edmd_cuda_predict_all.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    lib.edmd_cuda_predict_device.argtypes = [vp, C.c_int]
+    lib.edmd_cuda_fetch_predictions.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.edmd_cuda_set_growth.argtypes = [vp, vp]
+    lib.edmd_cuda_free_fly.argtypes = [vp, C.c_int, C.c_double]
+    lib.edmd_cuda_download_state.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.edmd_cuda_pcf.argtypes = [vp, C.c_double, C.c_double, vp, vp, C.POINTER(C.c_int)]
+    lib.edmd_cuda_boop_cutoff.argtypes = [vp, C.c_double, vp, vp, vp, vp, vp, vp]
+    lib.edmd_cuda_bench.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double,
+                                    C.c_int, C.c_int, C.c_size_t, vp, vp]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int:
+            pass
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, n):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    assert a.shape == (n,), (a.shape, n)
+    return a
+
+
+class EdmdCuda:
+    """One context = one GPU + one particle system (edmd_cuda_create)."""
+
+    def __init__(self, n: int, lx: float, ly: float, device: int = 0):
+        self.lib = load_library()
+        self.n = int(n)
+        h = C.c_void_p()
+        rc = self.lib.edmd_cuda_create(device, self.n, lx, ly, C.byref(h))
+        self._h = h
+        if rc != 0:
+            msg = self.lib.edmd_cuda_last_error(h).decode() if h else "create failed"
+            if h:
+                self.lib.edmd_cuda_destroy(h)
+            self._h = None
+            raise EdmdError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.edmd_cuda_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, allow=()):
+        if rc != 0 and rc not in allow:
+            raise EdmdError(rc, self.lib.edmd_cuda_last_error(self._h).decode())
+        return rc
+
+    @property
+    def box(self) -> Box:
+        b = Box()
+        self._check(self.lib.edmd_cuda_get_box(self._h, C.byref(b)))
+        return b
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.edmd_cuda_launch_count(self._h))
+
+    def upload(self, x, y, vx, vy, rad, cell_xy=None, t=0.0):
+        n = self.n
+        arrs = [_f64(a, n) for a in (x, y, vx, vy, rad)]
+        cells = None
+        if cell_xy is not None:
+            cells = np.ascontiguousarray(cell_xy, dtype=np.int32).reshape(-1)
+            assert cells.size == 2 * n
+        self._check(self.lib.edmd_cuda_upload(self._h, *[_ptr(a) for a in arrs], _ptr(cells), float(t)))
+
+    def upload_aos(self, records: np.ndarray, t=0.0, with_cells=True):
+        """records: structured array with fields x,y,vx,vy,rad[,cell (2 x i4)]."""
+        rec = np.ascontiguousarray(records)
+        off = {k: rec.dtype.fields[k][1] for k in ("x", "y", "vx", "vy", "rad")}
+        off_cell = rec.dtype.fields["cell"][1] if with_cells else C.c_size_t(-1).value
+        self._check(self.lib.edmd_cuda_upload_aos(
+            self._h, _ptr(rec), rec.dtype.itemsize, off["x"], off["y"], off["vx"],
+            off["vy"], off["rad"], off_cell, float(t)))
+
+    def _out(self):
+        n = self.n
+        return (np.empty(n, np.float64), np.empty(n, np.uint8), np.empty(n, np.float64),
+                np.empty(n, np.int32), np.empty(n, np.uint8), np.full(2, -7, np.int32))
+
+    def predict_all(self, mode=MODE_NORMAL, vr=None, allow_overlap=False):
+        tc, d, tl, p, ct, ov = self._out()
+        vr_a = None if vr is None else _f64(vr, self.n)
+        rc = self._check(self.lib.edmd_cuda_predict_all(
+            self._h, mode, _ptr(vr_a), _ptr(tc), _ptr(d), _ptr(tl), _ptr(p), _ptr(ct), _ptr(ov)),
+            allow=(EOVERLAP,) if allow_overlap else ())
+        return dict(t_cross=tc, dir=d, t_coll=tl, partner=p, ctype=ct, overlap=ov, rc=rc)
+
+    def set_growth(self, vr):
+        vr_a = _f64(vr, self.n)
+        self._check(self.lib.edmd_cuda_set_growth(self._h, _ptr(vr_a)))
+
+    def predict_device(self, mode=MODE_NORMAL):
+        self._check(self.lib.edmd_cuda_predict_device(self._h, mode))
+
+    def fetch_predictions(self, allow_overlap=False):
+        tc, d, tl, p, ct, ov = self._out()
+        rc = self._check(self.lib.edmd_cuda_fetch_predictions(
+            self._h, _ptr(tc), _ptr(d), _ptr(tl), _ptr(p), _ptr(ct), _ptr(ov)),
+            allow=(EOVERLAP,) if allow_overlap else ())
+        return dict(t_cross=tc, dir=d, t_coll=tl, partner=p, ctype=ct, overlap=ov, rc=rc)
+
+    def free_fly(self, t_new, mode=MODE_NORMAL):
+        self._check(self.lib.edmd_cuda_free_fly(self._h, mode, float(t_new)))
+
+    def download_state(self):
+        n = self.n
+        out = [np.empty(n, np.float64) for _ in range(5)]
+        self._check(self.lib.edmd_cuda_download_state(self._h, *[_ptr(a) for a in out]))
+        return dict(zip(("x", "y", "vx", "vy", "rad"), out))
+
+    def pcf_num_bins(self, dr, max_r) -> int:
+        nb = C.c_int(0)
+        self._check(self.lib.edmd_cuda_pcf(self._h, dr, max_r, None, None, C.byref(nb)))
+        return nb.value
+
+    def pcf(self, dr, max_r):
+        nb = self.pcf_num_bins(dr, max_r)
+        counts = np.zeros(max(nb, 1), np.uint64)
+        g = np.zeros(max(nb, 1), np.float64)
+        nbc = C.c_int(0)
+        self._check(self.lib.edmd_cuda_pcf(self._h, dr, max_r, _ptr(counts), _ptr(g), C.byref(nbc)))
+        return dict(num_bins=nb, counts=counts[:nb], g_r=g[:nb],
+                    r=(np.arange(nb) + 0.5) * dr)
+
+    def boop_cutoff(self, r_c=2.5):
+        n = self.n
+        q5, q6, q7, arg = (np.empty(n, np.float64) for _ in range(4))
+        nb = np.empty(n, np.int32)
+        mean = C.c_double(0.0)
+        self._check(self.lib.edmd_cuda_boop_cutoff(
+            self._h, r_c, _ptr(q5), _ptr(q6), _ptr(q7), _ptr(arg), _ptr(nb), C.addressof(mean)))
+        return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, mean_q6=mean.value)
+
+    def bench(self, what, mode=MODE_NORMAL, dr=0.0, max_r=0.0, warmup=3, iters=10,
+              flush_bytes=0):
+        tot = np.zeros(iters, np.float32)
+        main = np.zeros(iters, np.float32)
+        self._check(self.lib.edmd_cuda_bench(self._h, what, mode, dr, max_r, warmup, iters,
+                                             flush_bytes, _ptr(tot), _ptr(main)))
+        return tot, main

@@ -1,0 +1,270 @@
+// analysis.cu -- per-frame structure analysis.
+//
+//   K4 boop_cutoff : computeBOOPCutoff, src/boop.c:61-107
+//   K3 pcf_hist    : calculate_pcf,     src/pcf.c:16-75
+//
+// Parity-critical arithmetic (the r2 < r_c^2 neighbour test, the pair
+// distance and its bin) uses explicit unfused __d*_rn operations in the
+// reference's order so that neighbour counts and histogram counts are
+// integers identical to the reference's.
+#include "edmd_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ double min_image(double d, double half, double len)
+{
+    if (d >= half) return __dsub_rn(d, len);
+    if (d < -half) return __dadd_rn(d, len);
+    return d;
+}
+
+__device__ __forceinline__ int wrap_cell(int a, int n)
+{
+    if (a < 0) return a + n;
+    if (a >= n) return a - n;
+    return a;
+}
+
+// ------------------------------------------------------------------ K4 ----
+// One thread per particle in cell order; same 3x3 traversal as the sweep (and
+// the same truncation the reference has: cells are ~2.0 wide, r_c = 2.5, so
+// neighbours two cells away are never seen -- reproduced on purpose).
+// e^{ik theta} = ((dx + i dy)/r)^k by complex powers instead of atan2 + cexp;
+// agrees with libm to a few ulp (gate: 1e-10).
+constexpr int kBoopThreads = 128;
+
+__global__ void __launch_bounds__(kBoopThreads)
+k_boop(int n, edmd_dev_box b, double rc2, const double4 *__restrict__ sxv,
+       const int32_t *__restrict__ sid, const int32_t *__restrict__ scid,
+       const int32_t *__restrict__ start, double *__restrict__ q5,
+       double *__restrict__ q6, double *__restrict__ q7,
+       double *__restrict__ q6arg, int32_t *__restrict__ nbr)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const double4 p1 = sxv[s];
+    const int id = sid[s];
+    const int c = scid[s];
+    const int Y = c / b.nx;
+    const int X = c - Y * b.nx;
+    double s5r = 0, s5i = 0, s6r = 0, s6i = 0, s7r = 0, s7i = 0;
+    int nb = 0;
+    const bool interior = (X >= 1) && (X + 1 < b.nx);
+#pragma unroll 1
+    for (int j = -1; j <= 1; j++) {
+        const int rowbase = wrap_cell(Y + j, b.ny) * b.nx;
+        const int nseg = interior ? 1 : 3;
+#pragma unroll 1
+        for (int k = 0; k < nseg; k++) {
+            int lo, hi;
+            if (interior) {
+                lo = start[rowbase + X - 1];
+                hi = start[rowbase + X + 2];
+            } else {
+                int cc = rowbase + wrap_cell(X + k - 1, b.nx);
+                lo = start[cc];
+                hi = start[cc + 1];
+            }
+#pragma unroll 1
+            for (int p = lo; p < hi; p++) {
+                if (p == s) continue;  // `p2->num != p1->num`
+                const double4 p2 = sxv[p];
+                double dx = min_image(__dsub_rn(p2.x, p1.x), b.half_lx, b.lx);
+                double dy = min_image(__dsub_rn(p2.y, p1.y), b.half_ly, b.ly);
+                double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (r2 < rc2) {
+                    nb++;
+                    double zr, zi;
+                    if (r2 > 0) {
+                        double inv = rsqrt(r2);
+                        zr = dx * inv;
+                        zi = dy * inv;
+                    } else {  // atan2(0,0) = 0 in the reference
+                        zr = 1.0;
+                        zi = 0.0;
+                    }
+                    double z2r = zr * zr - zi * zi, z2i = 2.0 * zr * zi;
+                    double z4r = z2r * z2r - z2i * z2i, z4i = 2.0 * z2r * z2i;
+                    double z5r = z4r * zr - z4i * zi, z5i = z4r * zi + z4i * zr;
+                    double z6r = z4r * z2r - z4i * z2i, z6i = z4r * z2i + z4i * z2r;
+                    double z7r = z6r * zr - z6i * zi, z7i = z6r * zi + z6i * zr;
+                    s5r += z5r; s5i += z5i;
+                    s6r += z6r; s6i += z6i;
+                    s7r += z7r; s7i += z7i;
+                }
+            }
+        }
+    }
+    nbr[id] = nb;
+    if (nb > 0) {
+        double dn = (double)nb;
+        q5[id] = hypot(s5r, s5i) / dn;
+        q6[id] = hypot(s6r, s6i) / dn;
+        q7[id] = hypot(s7r, s7i) / dn;
+        q6arg[id] = atan2(s6i, s6r);
+    } else {
+        q5[id] = 0.0;
+        q6[id] = 0.0;
+        q7[id] = 0.0;
+        q6arg[id] = 0.0;
+    }
+}
+
+// deterministic two-stage sum: fixed block partials, then one block in order
+constexpr int kRedThreads = 256;
+
+__global__ void __launch_bounds__(kRedThreads)
+k_sum_partial(int n, const double *__restrict__ v, double *__restrict__ partial)
+{
+    __shared__ double sh[kRedThreads];
+    double acc = 0;
+    for (int i = blockIdx.x * kRedThreads + threadIdx.x; i < n;
+         i += gridDim.x * kRedThreads)
+        acc += v[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = kRedThreads / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+k_sum_final(int m, const double *__restrict__ partial, double scale,
+            double *__restrict__ out)
+{
+    __shared__ double sh[kRedThreads];
+    double acc = 0;
+    for (int i = threadIdx.x; i < m; i += kRedThreads) acc += partial[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = kRedThreads / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0] * scale;
+}
+
+// ------------------------------------------------------------------ K3 ----
+// All unordered pairs i < j (src/pcf.c:39-54).  Particles are cut into tiles
+// of kTile; a CTA walks tile pairs (a <= b) from a persistent work list, keeps
+// tile b in shared memory (broadcast reads) and one particle of tile a per
+// thread in registers, and bins into a per-CTA shared u32 histogram that is
+// merged into the global u64 histogram once at the end.  FP64-pipe bound
+// (positions fit in L2; HBM traffic is negligible).
+constexpr int kPcfThreads = 256;
+constexpr int kTile = 256;
+
+__global__ void __launch_bounds__(kPcfThreads)
+k_pcf(int n, edmd_dev_box b, double bin_width, double max_r, int num_bins,
+      const double4 *__restrict__ xv, unsigned long long *__restrict__ counts,
+      int use_smem_hist)
+{
+    extern __shared__ unsigned char smem_raw[];
+    double2 *tile = reinterpret_cast<double2 *>(smem_raw);
+    unsigned int *hist = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(double2));
+    if (use_smem_hist) {
+        for (int k = threadIdx.x; k < num_bins; k += kPcfThreads) hist[k] = 0;
+    }
+    const int nt = (n + kTile - 1) / kTile;
+    const long long npairs = (long long)nt * (nt + 1) / 2;
+    for (long long w = blockIdx.x; w < npairs; w += gridDim.x) {
+        // unrank w -> (ta, tb) with ta <= tb, row-major over the upper triangle
+        // row ta starts at ta*nt - ta*(ta-1)/2
+        double fn = (double)nt + 0.5;
+        long long ta = (long long)(fn - sqrt(fn * fn - 2.0 * (double)w));
+        while (ta * nt - ta * (ta - 1) / 2 > w) ta--;
+        while ((ta + 1) * nt - (ta + 1) * ta / 2 <= w) ta++;
+        long long tb = ta + (w - (ta * nt - ta * (ta - 1) / 2));
+        __syncthreads();
+        {
+            int jj = (int)tb * kTile + threadIdx.x;
+            if (jj < n) {
+                double4 q = xv[jj];
+                tile[threadIdx.x] = make_double2(q.x, q.y);
+            }
+        }
+        __syncthreads();
+        const int i = (int)ta * kTile + threadIdx.x;
+        if (i < n) {
+            const double4 pi = xv[i];
+            const int jbase = (int)tb * kTile;
+            const int jcount = min(kTile, n - jbase);
+            const int jstart = (ta == tb) ? threadIdx.x + 1 : 0;
+            for (int jj = jstart; jj < jcount; jj++) {
+                double2 pj = tile[jj];
+                double dx = min_image(__dsub_rn(pj.x, pi.x), b.half_lx, b.lx);
+                double dy = min_image(__dsub_rn(pj.y, pi.y), b.half_ly, b.ly);
+                double r = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                if (r < max_r) {
+                    int bin = (int)__ddiv_rn(r, bin_width);
+                    if (bin < num_bins) {
+                        if (use_smem_hist) atomicAdd(&hist[bin], 1u);
+                        else atomicAdd(&counts[bin], 1ull);
+                    }
+                }
+            }
+        }
+    }
+    if (use_smem_hist) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < num_bins; k += kPcfThreads) {
+            unsigned int v = hist[k];
+            if (v) atomicAdd(&counts[k], (unsigned long long)v);
+        }
+    }
+}
+
+}  // namespace
+
+int edmd_launch_boop(edmd_ctx *c, double r_c)
+{
+    int n = c->n;
+    if (n == 0) return 0;
+    int blocks = (n + kBoopThreads - 1) / kBoopThreads;
+    double rc2 = r_c * r_c;  // `r_c*r_c`, a single rounded product
+    size_t N = (size_t)n;
+    k_boop<<<blocks, kBoopThreads, 0, c->stream>>>(
+        n, c->dbox, rc2, c->sxv, c->sid, c->scid, c->cell_start, c->boop,
+        c->boop + N, c->boop + 2 * N, c->boop + 3 * N, c->boop_nb);
+    return 1;
+}
+
+int edmd_launch_mean(edmd_ctx *c, const double *v, int n, double *out_dev)
+{
+    int blocks = c->red_cap;
+    k_sum_partial<<<blocks, kRedThreads, 0, c->stream>>>(n, v, c->red_partial);
+    k_sum_final<<<1, kRedThreads, 0, c->stream>>>(blocks, c->red_partial,
+                                                  n > 0 ? 1.0 / (double)n : 0.0,
+                                                  out_dev);
+    return 2;
+}
+
+int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins)
+{
+    int n = c->n;
+    if (n < 2 || num_bins <= 0) return 0;
+    size_t tile_bytes = kTile * sizeof(double2);
+    size_t hist_bytes = (size_t)num_bins * sizeof(unsigned int);
+    int use_smem = (tile_bytes + hist_bytes) <= 200 * 1024;
+    size_t smem = tile_bytes + (use_smem ? hist_bytes : 0);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_pcf, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024);
+        attr_set = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf, kPcfThreads, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long nt = (n + kTile - 1) / kTile;
+    long long npairs = nt * (nt + 1) / 2;
+    long long grid = (long long)sms * per_sm;
+    if (grid > npairs) grid = npairs;
+    k_pcf<<<(int)grid, kPcfThreads, smem, c->stream>>>(
+        n, c->dbox, dr, max_r, num_bins, c->xv, c->pcf_counts, use_smem);
+    return 1;
+}

@@ -1,0 +1,583 @@
+// edmd_cuda.cu -- the C ABI of include/edmd_cuda.h: context lifetime, host
+// <-> device transfers, and the call sequences K0 -> K1 / K2 / K3 / K4.
+// No CPU fallback anywhere: every entry point needs a live CUDA context.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "edmd_internal.cuh"
+
+int edmd_scan_tiles_for(int nc);
+
+namespace {
+
+constexpr size_t kBounce = 8u << 20;  // per half of the pinned bounce buffer
+
+int fail_cuda(edmd_ctx *c, cudaError_t e, const char *what)
+{
+    if (c) snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
+    return -(int)e - 1000;
+}
+
+int fail(edmd_ctx *c, int code, const char *msg)
+{
+    if (c) snprintf(c->err, sizeof(c->err), "%s", msg);
+    return code;
+}
+
+#define CU(call)                                            \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return fail_cuda(c, e__, #call); \
+    } while (0)
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// host -> device.  Pinned sources go straight to the copy engine; pageable
+// sources are bounced through the context's pinned buffer in two alternating
+// halves so the CPU memcpy of chunk k+1 overlaps the DMA of chunk k.
+int h2d(edmd_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return 0;
+    if (is_pinned(src)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        return 0;
+    }
+    char *pin = (char *)c->h_pin;
+    size_t off = 0;
+    int half = 0;
+    while (off < bytes) {
+        size_t m = bytes - off < kBounce ? bytes - off : kBounce;
+        CU(cudaEventSynchronize(c->ev[half]));
+        memcpy(pin + half * kBounce, (const char *)src + off, m);
+        CU(cudaMemcpyAsync((char *)dst + off, pin + half * kBounce, m,
+                           cudaMemcpyHostToDevice, c->stream));
+        CU(cudaEventRecord(c->ev[half], c->stream));
+        off += m;
+        half ^= 1;
+    }
+    return 0;
+}
+
+// device -> host, same scheme in the other direction.
+int d2h(edmd_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return 0;
+    if (is_pinned(dst)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return 0;
+    }
+    char *pin = (char *)c->h_pin;
+    size_t off = 0, done = 0;
+    int half = 0;
+    size_t pend_off[2] = {0, 0}, pend_len[2] = {0, 0};
+    while (off < bytes || done < bytes) {
+        if (pend_len[half]) {
+            CU(cudaEventSynchronize(c->ev[half]));
+            memcpy((char *)dst + pend_off[half], pin + half * kBounce, pend_len[half]);
+            done += pend_len[half];
+            pend_len[half] = 0;
+        }
+        if (off < bytes) {
+            size_t m = bytes - off < kBounce ? bytes - off : kBounce;
+            CU(cudaMemcpyAsync(pin + half * kBounce, (const char *)src + off, m,
+                               cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaEventRecord(c->ev[half], c->stream));
+            pend_off[half] = off;
+            pend_len[half] = m;
+            off += m;
+        }
+        half ^= 1;
+    }
+    return 0;
+}
+
+template <typename T>
+int dev_alloc(edmd_ctx *c, T **p, size_t count)
+{
+    if (count == 0) count = 1;
+    CU(cudaMalloc((void **)p, count * sizeof(T)));
+    return 0;
+}
+
+// boxConstantHelper, src/EDMD.c:679-715 (addWell == 0)
+void box_init(edmd_box *b, int n, double lx, double ly)
+{
+    b->n = n;
+    b->lx = lx;
+    b->ly = ly;
+    b->half_lx = lx / 2;
+    b->half_ly = ly / 2;
+    b->nycells = (int)(b->half_ly);
+    b->nxcells = (int)(b->half_lx);
+    b->cellx_size = lx / b->nxcells;
+    b->celly_size = ly / b->nycells;
+    b->cellx_fac = 1 / b->cellx_size;
+    b->celly_fac = 1 / b->celly_size;
+    b->dt_paul = 5.0 / (double)n;
+}
+
+int check_flags(edmd_ctx *c)
+{
+    int32_t f = 0;
+    CU(cudaMemcpyAsync(&f, c->flags, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (f & 1) {
+        CU(cudaMemsetAsync(c->flags, 0, sizeof(int32_t), c->stream));
+        c->have_state = false;
+        return fail(c, EDMD_ECELL, "a particle's cell id lies outside the cell grid");
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
+{
+    if (!out) return EDMD_EINVAL;
+    *out = nullptr;
+    if (n < 0 || n >= (1 << 30) || !(lx >= 2.0) || !(ly >= 2.0)) return EDMD_EINVAL;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return -(int)(e ? e : cudaErrorNoDevice) - 1000;
+    if (device < 0 || device >= ndev) return EDMD_EINVAL;
+    edmd_ctx *c = new (std::nothrow) edmd_ctx();
+    if (!c) return EDMD_ENOMEM;
+    memset(c, 0, sizeof(*c));
+    *out = c;  // returned even on failure so last_error() is readable
+    c->device = device;
+    c->n = n;
+    box_init(&c->box, n > 0 ? n : 1, lx, ly);
+    c->box.n = n;
+    long long nc = (long long)c->box.nxcells * c->box.nycells;
+    if (nc <= 0 || nc >= (1ll << 31) - 8) return fail(c, EDMD_EINVAL, "cell grid too large");
+    c->dbox.n = n;
+    c->dbox.nx = c->box.nxcells;
+    c->dbox.ny = c->box.nycells;
+    c->dbox.nc = (int)nc;
+    c->dbox.lx = lx;
+    c->dbox.ly = ly;
+    c->dbox.half_lx = c->box.half_lx;
+    c->dbox.half_ly = c->box.half_ly;
+    c->dbox.csx = c->box.cellx_size;
+    c->dbox.csy = c->box.celly_size;
+    c->dbox.fx = c->box.cellx_fac;
+    c->dbox.fy = c->box.celly_fac;
+
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; k++) CU(cudaEventCreateWithFlags(&c->ev[k], cudaEventDisableTiming));
+    size_t N = (size_t)n;
+    int r;
+    if ((r = dev_alloc(c, &c->in_soa, 5 * N))) return r;
+    if ((r = dev_alloc(c, &c->in_cell, 2 * N))) return r;
+    c->h_pin_bytes = 2 * kBounce;
+    CU(cudaHostAlloc(&c->h_pin, c->h_pin_bytes, cudaHostAllocDefault));
+    if ((r = dev_alloc(c, &c->xv, N))) return r;
+    if ((r = dev_alloc(c, &c->rad, N))) return r;
+    if ((r = dev_alloc(c, &c->vr, N))) return r;
+    if ((r = dev_alloc(c, &c->cid, N))) return r;
+    if ((r = dev_alloc(c, &c->cell_cnt, (size_t)nc + 8))) return r;
+    if ((r = dev_alloc(c, &c->cell_start, (size_t)nc + 8))) return r;
+    if ((r = dev_alloc(c, &c->slot_id, N))) return r;
+    c->scan_tiles = edmd_scan_tiles_for((int)nc);
+    for (int k = 0; k < 2; k++) {
+        if ((r = dev_alloc(c, &c->scan_state[k], (size_t)c->scan_tiles))) return r;
+        CU(cudaMemsetAsync(c->scan_state[k], 0, c->scan_tiles * sizeof(uint32_t), c->stream));
+    }
+    if ((r = dev_alloc(c, &c->scan_ticket, 2))) return r;
+    CU(cudaMemsetAsync(c->scan_ticket, 0, 2 * sizeof(int32_t), c->stream));
+    CU(cudaMemsetAsync(c->cell_cnt, 0, ((size_t)nc + 8) * sizeof(int32_t), c->stream));
+    if ((r = dev_alloc(c, &c->sxv, N))) return r;
+    if ((r = dev_alloc(c, &c->srad, N))) return r;
+    if ((r = dev_alloc(c, &c->svr, N))) return r;
+    if ((r = dev_alloc(c, &c->sid, N))) return r;
+    if ((r = dev_alloc(c, &c->scid, N))) return r;
+    if ((r = dev_alloc(c, &c->t_cross, N))) return r;
+    if ((r = dev_alloc(c, &c->t_coll, N))) return r;
+    if ((r = dev_alloc(c, &c->partner, N))) return r;
+    if ((r = dev_alloc(c, &c->dir, N))) return r;
+    if ((r = dev_alloc(c, &c->ctype, N))) return r;
+    if ((r = dev_alloc(c, &c->overlap_key, 1))) return r;
+    if ((r = dev_alloc(c, &c->flags, 4))) return r;
+    CU(cudaMemsetAsync(c->flags, 0, 4 * sizeof(int32_t), c->stream));
+    if ((r = dev_alloc(c, &c->boop, 4 * N))) return r;
+    if ((r = dev_alloc(c, &c->boop_nb, N))) return r;
+    c->red_cap = 296;
+    if ((r = dev_alloc(c, &c->red_partial, (size_t)c->red_cap + 8))) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void edmd_cuda_destroy(edmd_ctx *c)
+{
+    if (!c) return;
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->cell_cnt,
+                   c->cell_start, c->slot_id, c->scan_state[0], c->scan_state[1],
+                   c->scan_ticket, c->sxv, c->srad, c->svr, c->sid, c->scid,
+                   c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
+                   c->overlap_key, c->flags, c->pcf_counts, c->boop, c->boop_nb,
+                   c->red_partial, c->flush_buf};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    for (int k = 0; k < 4; k++)
+        if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *edmd_cuda_last_error(const edmd_ctx *c) { return c ? c->err : "null context"; }
+
+int edmd_cuda_get_box(const edmd_ctx *c, edmd_box *out)
+{
+    if (!c || !out) return EDMD_EINVAL;
+    *out = c->box;
+    return 0;
+}
+
+uint64_t edmd_cuda_launch_count(const edmd_ctx *c) { return c ? c->launches : 0; }
+
+int edmd_cuda_upload(edmd_ctx *c, const double *x, const double *y, const double *vx,
+                     const double *vy, const double *rad, const int32_t *cell_xy,
+                     double t)
+{
+    if (!c) return EDMD_EINVAL;
+    if (c->n > 0 && (!x || !y || !vx || !vy || !rad)) return fail(c, EDMD_EINVAL, "null state array");
+    CU(cudaSetDevice(c->device));
+    size_t N = (size_t)c->n, B = N * sizeof(double);
+    int r;
+    if ((r = h2d(c, c->in_soa, x, B))) return r;
+    if ((r = h2d(c, c->in_soa + N, y, B))) return r;
+    if ((r = h2d(c, c->in_soa + 2 * N, vx, B))) return r;
+    if ((r = h2d(c, c->in_soa + 3 * N, vy, B))) return r;
+    if ((r = h2d(c, c->in_soa + 4 * N, rad, B))) return r;
+    if (cell_xy && (r = h2d(c, c->in_cell, cell_xy, 2 * N * sizeof(int32_t)))) return r;
+    c->launches += edmd_launch_pack(c, cell_xy != nullptr);
+    CU(cudaGetLastError());
+    c->t = t;
+    c->have_pred = false;
+    c->have_index = false;
+    if ((r = check_flags(c))) return r;
+    c->have_state = true;
+    return 0;
+}
+
+int edmd_cuda_upload_aos(edmd_ctx *c, const void *base, size_t stride, size_t off_x,
+                         size_t off_y, size_t off_vx, size_t off_vy, size_t off_rad,
+                         size_t off_cell, double t)
+{
+    if (!c) return EDMD_EINVAL;
+    if (c->n > 0 && !base) return fail(c, EDMD_EINVAL, "null record array");
+    // Host-side strided pack into SoA chunks, then the SoA path.  The reference's
+    // struct particle is 144 bytes of which 48 are used here; shipping the
+    // whole records would triple the PCIe traffic.
+    size_t N = (size_t)c->n;
+    std::vector<double> soa;
+    std::vector<int32_t> cells;
+    try {
+        soa.resize(5 * N + 1);
+        if (off_cell != (size_t)-1) cells.resize(2 * N + 1);
+    } catch (...) {
+        return fail(c, EDMD_ENOMEM, "host staging allocation failed");
+    }
+    const char *p = (const char *)base;
+    for (size_t i = 0; i < N; i++, p += stride) {
+        soa[i] = *(const double *)(p + off_x);
+        soa[N + i] = *(const double *)(p + off_y);
+        soa[2 * N + i] = *(const double *)(p + off_vx);
+        soa[3 * N + i] = *(const double *)(p + off_vy);
+        soa[4 * N + i] = *(const double *)(p + off_rad);
+        if (off_cell != (size_t)-1) {
+            const int32_t *cc = (const int32_t *)(p + off_cell);
+            cells[2 * i] = cc[0];
+            cells[2 * i + 1] = cc[1];
+        }
+    }
+    return edmd_cuda_upload(c, soa.data(), soa.data() + N, soa.data() + 2 * N,
+                            soa.data() + 3 * N, soa.data() + 4 * N,
+                            off_cell != (size_t)-1 ? cells.data() : nullptr, t);
+}
+
+int edmd_cuda_set_growth(edmd_ctx *c, const double *vr)
+{
+    if (!c || (c->n > 0 && !vr)) return EDMD_EINVAL;
+    CU(cudaSetDevice(c->device));
+    int r = h2d(c, c->vr, vr, (size_t)c->n * sizeof(double));
+    if (r) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_vr = true;
+    c->have_index = false;
+    return 0;
+}
+
+int edmd_cuda_predict_device(edmd_ctx *c, int mode)
+{
+    if (!c) return EDMD_EINVAL;
+    if (mode != EDMD_MODE_NORMAL && mode != EDMD_MODE_GROW) return fail(c, EDMD_EINVAL, "bad mode");
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "predict before upload");
+    if (mode == EDMD_MODE_GROW && !c->have_vr) return fail(c, EDMD_ESTATE, "GROW mode needs growth rates");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));
+    c->launches += edmd_launch_cell_index(c, mode);
+    c->launches += edmd_launch_predict(c, mode);
+    CU(cudaGetLastError());
+    c->have_index = true;
+    c->have_pred = true;
+    return 0;
+}
+
+int edmd_cuda_fetch_predictions(edmd_ctx *c, double *t_cross, uint8_t *dir, double *t_coll,
+                                int32_t *partner, uint8_t *ctype, int32_t *overlap_pair)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_pred) return fail(c, EDMD_ESTATE, "no device predictions to fetch");
+    CU(cudaSetDevice(c->device));
+    size_t N = (size_t)c->n;
+    int r;
+    if (t_cross && (r = d2h(c, t_cross, c->t_cross, N * sizeof(double)))) return r;
+    if (t_coll && (r = d2h(c, t_coll, c->t_coll, N * sizeof(double)))) return r;
+    if (partner && (r = d2h(c, partner, c->partner, N * sizeof(int32_t)))) return r;
+    if (dir && (r = d2h(c, dir, c->dir, N))) return r;
+    if (ctype && (r = d2h(c, ctype, c->ctype, N))) return r;
+    unsigned long long key = ~0ull;
+    CU(cudaMemcpyAsync(&key, c->overlap_key, sizeof(key), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (overlap_pair) {
+        overlap_pair[0] = key == ~0ull ? -1 : (int32_t)(key >> 32);
+        overlap_pair[1] = key == ~0ull ? -1 : (int32_t)(key & 0xffffffffu);
+    }
+    if (key != ~0ull) {
+        snprintf(c->err, sizeof(c->err), "overlap between particles %d and %d (c < -0.01)",
+                 (int)(key >> 32), (int)(key & 0xffffffffu));
+        return EDMD_EOVERLAP;
+    }
+    return 0;
+}
+
+int edmd_cuda_predict_all(edmd_ctx *c, int mode, const double *vr, double *t_cross,
+                          uint8_t *dir, double *t_coll, int32_t *partner, uint8_t *ctype,
+                          int32_t *overlap_pair)
+{
+    if (!c) return EDMD_EINVAL;
+    int r;
+    if (mode == EDMD_MODE_GROW) {
+        if (!vr) return fail(c, EDMD_EINVAL, "GROW mode needs vr");
+        if ((r = edmd_cuda_set_growth(c, vr))) return r;
+    }
+    if ((r = edmd_cuda_predict_device(c, mode))) return r;
+    return edmd_cuda_fetch_predictions(c, t_cross, dir, t_coll, partner, ctype, overlap_pair);
+}
+
+int edmd_cuda_free_fly(edmd_ctx *c, int mode, double t_new)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "free_fly before upload");
+    if (mode == EDMD_MODE_GROW && !c->have_vr) return fail(c, EDMD_ESTATE, "GROW mode needs growth rates");
+    CU(cudaSetDevice(c->device));
+    double dt = t_new - c->t;  // `double dt = t - p->t;` src/EDMD.c:4955
+    c->launches += edmd_launch_free_fly(c, mode, dt);
+    CU(cudaGetLastError());
+    c->t = t_new;
+    c->have_pred = false;
+    c->have_index = false;
+    return 0;
+}
+
+int edmd_cuda_download_state(edmd_ctx *c, double *x, double *y, double *vx, double *vy,
+                             double *rad)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "download before upload");
+    CU(cudaSetDevice(c->device));
+    size_t N = (size_t)c->n;
+    std::vector<double> tmp;
+    try {
+        tmp.resize(4 * N + 1);
+    } catch (...) {
+        return fail(c, EDMD_ENOMEM, "host staging allocation failed");
+    }
+    int r;
+    if ((r = d2h(c, tmp.data(), c->xv, 4 * N * sizeof(double)))) return r;
+    if (rad && (r = d2h(c, rad, c->rad, N * sizeof(double)))) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < N; i++) {
+        if (x) x[i] = tmp[4 * i];
+        if (y) y[i] = tmp[4 * i + 1];
+        if (vx) vx[i] = tmp[4 * i + 2];
+        if (vy) vy[i] = tmp[4 * i + 3];
+    }
+    return 0;
+}
+
+static int ensure_index(edmd_ctx *c)
+{
+    if (c->have_index) return 0;
+    c->launches += edmd_launch_cell_index(c, EDMD_MODE_NORMAL);
+    CU(cudaGetLastError());
+    c->have_index = true;
+    return 0;
+}
+
+int edmd_cuda_boop_cutoff(edmd_ctx *c, double r_c, double *q5, double *q6, double *q7,
+                          double *q6_arg, int32_t *neighbors, double *mean_q6)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "boop before upload");
+    CU(cudaSetDevice(c->device));
+    int r;
+    if ((r = ensure_index(c))) return r;
+    c->launches += edmd_launch_boop(c, r_c);
+    size_t N = (size_t)c->n, B = N * sizeof(double);
+    if (mean_q6) c->launches += edmd_launch_mean(c, c->boop + N, c->n, c->red_partial + c->red_cap);
+    CU(cudaGetLastError());
+    if (q5 && (r = d2h(c, q5, c->boop, B))) return r;
+    if (q6 && (r = d2h(c, q6, c->boop + N, B))) return r;
+    if (q7 && (r = d2h(c, q7, c->boop + 2 * N, B))) return r;
+    if (q6_arg && (r = d2h(c, q6_arg, c->boop + 3 * N, B))) return r;
+    if (neighbors && (r = d2h(c, neighbors, c->boop_nb, N * sizeof(int32_t)))) return r;
+    if (mean_q6)
+        CU(cudaMemcpyAsync(mean_q6, c->red_partial + c->red_cap, sizeof(double),
+                           cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int edmd_cuda_pcf(edmd_ctx *c, double dr, double max_r, uint64_t *counts, double *g_r,
+                  int *num_bins)
+{
+    if (!c || !num_bins) return EDMD_EINVAL;
+    if (!(dr > 0) || !(max_r >= 0)) return fail(c, EDMD_EINVAL, "bad dr / max_r");
+    double q = max_r / dr;
+    if (!(q < 1e8)) return fail(c, EDMD_EINVAL, "too many bins");
+    int nb = (int)q;  // `(int)(max_r / dr)` src/pcf.c:21
+    *num_bins = nb;
+    if (!counts) return 0;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "pcf before upload");
+    CU(cudaSetDevice(c->device));
+    if (nb > c->pcf_cap) {
+        if (c->pcf_counts) CU(cudaFree(c->pcf_counts));
+        c->pcf_counts = nullptr;
+        c->pcf_cap = 0;
+        int r = dev_alloc(c, &c->pcf_counts, (size_t)nb);
+        if (r) return r;
+        c->pcf_cap = nb;
+    }
+    if (nb > 0) {
+        CU(cudaMemsetAsync(c->pcf_counts, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
+        c->launches += edmd_launch_pcf(c, dr, max_r, nb);
+        CU(cudaGetLastError());
+        int r = d2h(c, counts, c->pcf_counts, (size_t)nb * sizeof(uint64_t));
+        if (r) return r;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (g_r) {
+        // normalisation, src/pcf.c:56-72 (host side: num_bins values)
+        double volume = c->box.lx * c->box.ly;
+        double density = c->n / volume;
+        for (int i = 0; i < nb; i++) {
+            double r = (i + 0.5) * dr;
+            double shell_volume = 2 * M_PI * r * dr;
+            double norm = shell_volume * density * c->n;
+            double g = 2.0 * (double)counts[i];
+            g_r[i] = norm > 0 ? g / norm : 0.0;
+        }
+    }
+    return 0;
+}
+
+int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, int warmup,
+                    int iters, size_t flush_bytes, float *ms_total, float *ms_main)
+{
+    if (!c || iters < 1 || warmup < 0) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "bench before upload");
+    if (mode == EDMD_MODE_GROW && !c->have_vr) return fail(c, EDMD_ESTATE, "GROW mode needs growth rates");
+    CU(cudaSetDevice(c->device));
+    if (flush_bytes > c->flush_cap) {
+        if (c->flush_buf) CU(cudaFree(c->flush_buf));
+        c->flush_buf = nullptr;
+        c->flush_cap = 0;
+        CU(cudaMalloc((void **)&c->flush_buf, flush_bytes));
+        c->flush_cap = flush_bytes;
+    }
+    int nb = 0;
+    if (what == EDMD_BENCH_PCF) {
+        int r = edmd_cuda_pcf(c, dr, max_r, nullptr, nullptr, &nb);
+        if (r) return r;
+        if (nb > c->pcf_cap) {
+            if (c->pcf_counts) CU(cudaFree(c->pcf_counts));
+            c->pcf_counts = nullptr;
+            c->pcf_cap = 0;
+            r = dev_alloc(c, &c->pcf_counts, (size_t)nb);
+            if (r) return r;
+            c->pcf_cap = nb;
+        }
+    }
+    if (what == EDMD_BENCH_BOOP) {
+        int r = ensure_index(c);
+        if (r) return r;
+    }
+    std::vector<cudaEvent_t> evs(3 * (size_t)iters);
+    for (auto &e : evs) CU(cudaEventCreate(&e));
+    const double t_keep = c->t;
+    for (int it = -warmup; it < iters; it++) {
+        if (flush_bytes) CU(cudaMemsetAsync(c->flush_buf, it & 0xff, flush_bytes, c->stream));
+        cudaEvent_t *e = it >= 0 ? &evs[3 * (size_t)it] : nullptr;
+        if (e) CU(cudaEventRecord(e[0], c->stream));
+        switch (what) {
+        case EDMD_BENCH_SWEEP:
+            CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));
+            c->launches += edmd_launch_cell_index(c, mode);
+            if (e) CU(cudaEventRecord(e[1], c->stream));
+            c->launches += edmd_launch_predict(c, mode);
+            c->have_index = true;
+            c->have_pred = true;
+            break;
+        case EDMD_BENCH_FREEFLY:
+            if (e) CU(cudaEventRecord(e[1], c->stream));
+            c->launches += edmd_launch_free_fly(c, mode, 0.0);  // dt = 0: state unchanged
+            break;
+        case EDMD_BENCH_BOOP:
+            if (e) CU(cudaEventRecord(e[1], c->stream));
+            c->launches += edmd_launch_boop(c, dr > 0 ? dr : 2.5);
+            break;
+        case EDMD_BENCH_PCF:
+            CU(cudaMemsetAsync(c->pcf_counts, 0, (size_t)(nb > 0 ? nb : 1) * sizeof(unsigned long long), c->stream));
+            if (e) CU(cudaEventRecord(e[1], c->stream));
+            c->launches += edmd_launch_pcf(c, dr, max_r, nb);
+            break;
+        default:
+            return fail(c, EDMD_EINVAL, "bad bench id");
+        }
+        if (e) CU(cudaEventRecord(e[2], c->stream));
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->t = t_keep;
+    for (int it = 0; it < iters; it++) {
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, evs[3 * (size_t)it], evs[3 * (size_t)it + 2]));
+        CU(cudaEventElapsedTime(&b, evs[3 * (size_t)it + 1], evs[3 * (size_t)it + 2]));
+        if (ms_total) ms_total[it] = a;
+        if (ms_main) ms_main[it] = b;
+    }
+    for (auto &e : evs) cudaEventDestroy(e);
+    return 0;
+}
+
+}  // extern "C"

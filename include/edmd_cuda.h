@@ -1,0 +1,178 @@
+/*
+ * edmd_cuda.h -- C ABI of the B200 (sm_100a) implementation of
+ * Graphical-EDMD's data-parallel hot path.
+ *
+ * The reference has no plugin/FFI layer.  Its seams for this path are the
+ * batch loops that call the per-particle function pointers
+ *     crossingEvent(int) / collisionEvent(int) / freeFly(particle*)
+ *                                   (src/EDMD.c:317-321)
+ * for ALL particles:
+ *     eventListInit   src/EDMD.c:2007-2012   (setup)
+ *     stopGrow        src/EDMD.c:4772-4779   (end of growth)
+ *     addNoise        src/EDMD.c:4909-4915   (every thermostat tick)
+ *     doUmbrella      src/EDMD.c:4519-4536   (umbrella roll-back)
+ *     takeAScreenshot src/EDMD.c:4659-4661   (free-fly re-sync)
+ * and the analysis signatures
+ *     calculate_pcf(particle*, N, dr, max_r, Lx, Ly)          src/pcf.h:33
+ *     computeBOOPCutoff(particle*, N, r_c, cellList, Nxcells) src/boop.h:13
+ * Each entry point below names the reference interface it replaces.
+ *
+ * Conventions: plain C types only; every function returns 0 on success, a
+ * negative value for a CUDA/runtime failure and a positive EDMD_E* value for a
+ * semantic error; edmd_cuda_last_error() gives the text.  A context is driven
+ * by one host thread (the reference is single-threaded).  Host buffers are
+ * caller-owned and may be pageable.  Nothing here ever calls exit().
+ * There is no CPU fallback: without a CUDA device create() fails.
+ */
+#ifndef EDMD_CUDA_H
+#define EDMD_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct edmd_ctx edmd_ctx;
+
+/* semantic error codes (positive) */
+#define EDMD_EINVAL 1    /* bad argument */
+#define EDMD_ESTATE 2    /* call out of order (e.g. predict before upload) */
+#define EDMD_EOVERLAP 3  /* predict found c < -0.01: reference would exit(3) */
+#define EDMD_ECELL 4     /* a cell id outside the grid */
+#define EDMD_ENOMEM 5
+
+/* prediction mode: which set of reference function pointers is emulated
+ * (src/EDMD.c:1977-1989) */
+#define EDMD_MODE_NORMAL 0 /* crossingEventNormal + collisionEventNormal */
+#define EDMD_MODE_GROW 1   /* crossingEventGrow   + collisionEventGrow   */
+
+/* enum event values the sweep emits (order of src/EDMD.h:19-34) */
+#define EDMD_EV_CELLCROSS 0
+#define EDMD_EV_COLLISION 1
+
+#define EDMD_NEVER 100000000000000000000000000.0 /* src/EDMD.h:8 */
+
+/* Box constants exactly as boxConstantHelper derives them, src/EDMD.c:679-715 */
+typedef struct {
+	int32_t n;
+	int32_t nxcells, nycells;
+	double lx, ly, half_lx, half_ly;
+	double cellx_size, celly_size;
+	double cellx_fac, celly_fac;
+	double dt_paul; /* PAUL_DT_SCALE / N, src/EDMD.c:712 */
+} edmd_box;
+
+/* ---- lifetime -------------------------------------------------------- */
+
+/* Replaces: constantInit's box set-up + boxConstantHelper (src/EDMD.c:679-715,
+ * 1150-1217), particles calloc (:1358) and cellList calloc (:1909).
+ * Allocates the device SoA store, the cell index and pinned staging. */
+int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out);
+void edmd_cuda_destroy(edmd_ctx *ctx);
+const char *edmd_cuda_last_error(const edmd_ctx *ctx);
+int edmd_cuda_get_box(const edmd_ctx *ctx, edmd_box *out);
+/* number of kernels this context has launched so far (bench accounting) */
+uint64_t edmd_cuda_launch_count(const edmd_ctx *ctx);
+
+/* ---- state upload ---------------------------------------------------- */
+
+/* Synchronous snapshot: every particle already advanced to time t (the state
+ * the reference has after its freeFly loop, src/EDMD.c:4838-4886, :4744).
+ * cell_xy (interleaved X,Y = particle.cell[0..1], src/EDMD.h:57) may be NULL:
+ * the device then computes (int)(x*cellxFac) like coordToCell (:2098-2107).
+ * Mid-run callers MUST pass the host's cell ids. */
+int edmd_cuda_upload(edmd_ctx *ctx, const double *x, const double *y,
+                     const double *vx, const double *vy, const double *rad,
+                     const int32_t *cell_xy, double t);
+
+/* Same, reading straight out of an array of records such as the reference's
+ * particles[] (struct particle, src/EDMD.h:42-64, 144-byte stride): byte
+ * offsets of the double fields x,y,vx,vy,rad and of int cell[2]
+ * (off_cell == (size_t)-1 => compute cells on the device). */
+int edmd_cuda_upload_aos(edmd_ctx *ctx, const void *base, size_t stride,
+                         size_t off_x, size_t off_y, size_t off_vx,
+                         size_t off_vy, size_t off_rad, size_t off_cell,
+                         double t);
+
+/* ---- the prediction sweep ------------------------------------------- */
+
+/* Replaces the loop bodies `crossingEvent(i); collisionEvent(i);` over all i
+ * (src/EDMD.c:2007-2012, 4772-4779, 4909-4915, 4530-4536).  Outputs are indexed
+ * by ORIGINAL particle id and carry what addCrossingEvent / addCollisionEvent
+ * (src/EDMD.c:2487-2496, 3286-3297) store into eventList[i] / eventList[N+i]:
+ *   t_cross[i]  absolute crossing time  (node.t)
+ *   dir[i]      1..4                    (node.j)
+ *   t_coll[i]   absolute collision time, t + 1e26 when no candidate
+ *   partner[i]  partner id, 0 when no candidate (the reference's default)
+ *   ctype[i]    EDMD_EV_COLLISION
+ * vr: growth rates, required for EDMD_MODE_GROW, ignored otherwise.
+ * overlap_pair[2] (nullable): first (i,j) in sweep order with c < -0.01, else
+ * -1,-1; the call then returns EDMD_EOVERLAP with all outputs still filled
+ * (the host mirrors the reference's exit(3), src/EDMD.c:2708-2717).
+ * Blocks until the results are in host memory. */
+int edmd_cuda_predict_all(edmd_ctx *ctx, int mode, const double *vr,
+                          double *t_cross, uint8_t *dir, double *t_coll,
+                          int32_t *partner, uint8_t *ctype,
+                          int32_t *overlap_pair);
+
+/* The two halves of predict_all for callers that keep state resident:
+ * run K0+K1 on the uploaded state (asynchronous, results stay in HBM) ... */
+int edmd_cuda_predict_device(edmd_ctx *ctx, int mode);
+/* ... and copy the last device results out (blocking). */
+int edmd_cuda_fetch_predictions(edmd_ctx *ctx, double *t_cross, uint8_t *dir,
+                                double *t_coll, int32_t *partner,
+                                uint8_t *ctype, int32_t *overlap_pair);
+int edmd_cuda_set_growth(edmd_ctx *ctx, const double *vr);
+
+/* ---- free flight ------------------------------------------------------ */
+
+/* Replaces `for i<N freeFly(particles+i)` (takeAScreenshot, src/EDMD.c:
+ * 4659-4661; freeFlyNormal :4954-4990 / freeFlyGrow :4992-5007) on the
+ * resident state: x += dt*vx, y += dt*vy (rad += dt*vr in GROW mode), one
+ * +-L wrap (PBCpostX/Y :5948-5959), t <- t_new.  Cell ids are NOT changed
+ * (in the reference only crossing events change them). */
+int edmd_cuda_free_fly(edmd_ctx *ctx, int mode, double t_new);
+int edmd_cuda_download_state(edmd_ctx *ctx, double *x, double *y, double *vx,
+                             double *vy, double *rad);
+
+/* ---- per-frame structure analysis ----------------------------------- */
+
+/* Replaces calculate_pcf (src/pcf.c:16-75; caller save_pcf, src/EDMD.c:
+ * 5636-5637 with dr = 0.1, max_r = min(Lx,Ly)/2).  counts[b] = number of
+ * UNORDERED pairs in bin b (the reference adds 2.0 per pair); g_r (nullable)
+ * gets the reference's normalisation (:56-72).  *num_bins = (int)(max_r/dr);
+ * counts/g_r must hold that many entries (query with counts == NULL). */
+int edmd_cuda_pcf(edmd_ctx *ctx, double dr, double max_r, uint64_t *counts,
+                  double *g_r, int *num_bins);
+
+/* Replaces computeBOOPCutoff (src/boop.c:61-107; callers saveTXT src/EDMD.c:
+ * 5057-5060 and saveThermo :5521-5536 with r_c = 2.5).  SoA mirror of
+ * boop_data (src/boop.h:6-10).  Like the reference it scans only the 3x3 cell
+ * block.  mean_q6 (nullable) = sum(q6)/N as saveThermo prints it. */
+int edmd_cuda_boop_cutoff(edmd_ctx *ctx, double r_c, double *q5, double *q6,
+                          double *q7, double *q6_arg, int32_t *neighbors,
+                          double *mean_q6);
+
+/* ---- measurement helpers (used by bench.py; timed with CUDA events on the
+ * context's own stream, inputs resident in HBM) ------------------------ */
+
+/* kernel ids for edmd_cuda_bench */
+#define EDMD_BENCH_SWEEP 0  /* K0 (cell index) + K1 (predict) */
+#define EDMD_BENCH_FREEFLY 1
+#define EDMD_BENCH_BOOP 2
+#define EDMD_BENCH_PCF 3    /* uses dr / max_r arguments */
+
+/* Runs `warmup` untimed and `iters` timed passes of the chosen device path,
+ * writing `flush_bytes` of scratch between passes (L2 flush, outside the timed
+ * events) when flush_bytes > 0.  ms_total[iters] = whole pass,
+ * ms_main[iters] = the dominant kernel alone (K1 for the sweep). */
+int edmd_cuda_bench(edmd_ctx *ctx, int what, int mode, double dr, double max_r,
+                    int warmup, int iters, size_t flush_bytes, float *ms_total,
+                    float *ms_main);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDMD_CUDA_H */

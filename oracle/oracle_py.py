@@ -1,0 +1,216 @@
+"""ctypes wrappers around the two CPU checkers -- TEST INFRASTRUCTURE ONLY.
+
+* ``Oracle``    -> oracle/liboracle.so      (our C restatement, edmd_oracle.c)
+* ``Reference`` -> oracle/_ref/libedmd_ref.so (the unmodified reference + ref_shim.c)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  The product never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_SO = HERE / "liboracle.so"
+REF_SO = HERE / "_ref" / "libedmd_ref.so"
+
+MODE_NORMAL, MODE_GROW = 0, 1
+
+
+def build(ref: bool = True) -> None:
+    """Compile liboracle.so (always) and _ref (only if /root/reference exists)."""
+    subprocess.run(["make", "-C", str(HERE), "liboracle.so"] + (["ref"] if ref else []),
+                   check=True, capture_output=True)
+
+
+class OBox(C.Structure):
+    _fields_ = [("n", C.c_int), ("nx", C.c_int), ("ny", C.c_int), ("lx", C.c_double),
+                ("ly", C.c_double), ("half_lx", C.c_double), ("half_ly", C.c_double),
+                ("csx", C.c_double), ("csy", C.c_double), ("fx", C.c_double), ("fy", C.c_double)]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Oracle:
+    def __init__(self):
+        if not ORACLE_SO.exists():
+            build(ref=False)
+        self.lib = lib = C.CDLL(str(ORACLE_SO))
+        vp = C.c_void_p
+        lib.oracle_box_init.argtypes = [C.POINTER(OBox), C.c_int, C.c_double, C.c_double]
+        lib.oracle_box_init.restype = None
+        lib.oracle_cells_from_coords.argtypes = [C.POINTER(OBox), C.c_int, vp, vp, vp]
+        lib.oracle_cells_from_coords.restype = None
+        lib.oracle_predict_all.argtypes = [C.POINTER(OBox), C.c_int, C.c_double] + [vp] * 7 + \
+            [C.c_int] + [vp] * 6
+        lib.oracle_free_fly.argtypes = [C.POINTER(OBox), C.c_int, C.c_int, C.c_double, vp,
+                                        C.c_double] + [vp] * 6
+        lib.oracle_free_fly.restype = None
+        lib.oracle_pcf.argtypes = [C.POINTER(OBox), C.c_int, vp, vp, C.c_double, C.c_double,
+                                   vp, vp, vp]
+        lib.oracle_pcf_num_bins.argtypes = [C.c_double, C.c_double]
+        lib.oracle_boop_cutoff.argtypes = [C.POINTER(OBox), C.c_int, vp, vp, vp, C.c_double] + [vp] * 5
+        lib.oracle_boop_cutoff.restype = None
+
+    def box(self, n, lx, ly) -> OBox:
+        b = OBox()
+        self.lib.oracle_box_init(C.byref(b), n, lx, ly)
+        return b
+
+    def cells(self, n, lx, ly, x, y):
+        b = self.box(n, lx, ly)
+        x, y = _f64(x), _f64(y)
+        out = np.empty(2 * n, np.int32)
+        self.lib.oracle_cells_from_coords(C.byref(b), n, _p(x), _p(y), _p(out))
+        return out
+
+    def predict_all(self, n, lx, ly, t, x, y, vx, vy, rad, vr=None, cell_xy=None,
+                    mode=MODE_NORMAL):
+        b = self.box(n, lx, ly)
+        x, y, vx, vy, rad, vr = map(_f64, (x, y, vx, vy, rad, vr))
+        cells = None if cell_xy is None else np.ascontiguousarray(cell_xy, np.int32).reshape(-1)
+        tc = np.empty(n, np.float64)
+        d = np.empty(n, np.uint8)
+        tl = np.empty(n, np.float64)
+        p = np.empty(n, np.int32)
+        ct = np.empty(n, np.uint8)
+        ov = np.full(2, -7, np.int32)
+        rc = self.lib.oracle_predict_all(C.byref(b), n, float(t), _p(x), _p(y), _p(vx), _p(vy),
+                                         _p(rad), _p(vr), _p(cells), mode, _p(tc), _p(d),
+                                         _p(tl), _p(p), _p(ct), _p(ov))
+        return dict(t_cross=tc, dir=d, t_coll=tl, partner=p, ctype=ct, overlap=ov, rc=rc)
+
+    def free_fly(self, n, lx, ly, t_old, t_new, x, y, vx, vy, rad=None, vr=None,
+                 mode=MODE_NORMAL, tp=None):
+        b = self.box(n, lx, ly)
+        x = _f64(x).copy()
+        y = _f64(y).copy()
+        rad = None if rad is None else _f64(rad).copy()
+        vx, vy, vr, tp = map(_f64, (vx, vy, vr, tp))
+        self.lib.oracle_free_fly(C.byref(b), n, mode, float(t_old), _p(tp), float(t_new),
+                                 _p(x), _p(y), _p(vx), _p(vy), _p(rad), _p(vr))
+        return dict(x=x, y=y, rad=rad)
+
+    def pcf(self, n, lx, ly, x, y, dr, max_r):
+        b = self.box(n, lx, ly)
+        x, y = _f64(x), _f64(y)
+        nb = self.lib.oracle_pcf_num_bins(dr, max_r)
+        counts = np.zeros(max(nb, 1), np.uint64)
+        g = np.zeros(max(nb, 1), np.float64)
+        r = np.zeros(max(nb, 1), np.float64)
+        self.lib.oracle_pcf(C.byref(b), n, _p(x), _p(y), dr, max_r, _p(counts), _p(g), _p(r))
+        return dict(num_bins=nb, counts=counts[:nb], g_r=g[:nb], r=r[:nb])
+
+    def boop_cutoff(self, n, lx, ly, x, y, r_c=2.5, cell_xy=None):
+        b = self.box(n, lx, ly)
+        x, y = _f64(x), _f64(y)
+        cells = None if cell_xy is None else np.ascontiguousarray(cell_xy, np.int32).reshape(-1)
+        q5, q6, q7, arg = (np.empty(n, np.float64) for _ in range(4))
+        nb = np.empty(n, np.int32)
+        self.lib.oracle_boop_cutoff(C.byref(b), n, _p(x), _p(y), _p(cells), r_c, _p(q5), _p(q6),
+                                    _p(q7), _p(arg), _p(nb))
+        return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb)
+
+
+class Reference:
+    """The unmodified reference behind ref_shim.c.  Holds global state: one
+    system at a time per process."""
+
+    @staticmethod
+    def available() -> bool:
+        return REF_SO.exists()
+
+    def __init__(self):
+        if not REF_SO.exists():
+            raise FileNotFoundError(f"{REF_SO} missing (built only where /root/reference exists)")
+        self.lib = lib = C.CDLL(str(REF_SO))
+        vp = C.c_void_p
+        lib.ref_setup.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double] + [vp] * 7
+        lib.ref_teardown.restype = None
+        lib.ref_get_box.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)] + [C.POINTER(C.c_double)] * 4
+        lib.ref_get_box.restype = None
+        lib.ref_get_cells.argtypes = [vp]
+        lib.ref_get_cells.restype = None
+        lib.ref_predict_first.argtypes = [C.c_int] + [vp] * 5
+        lib.ref_predict_first.restype = C.c_double
+        lib.ref_repredict.argtypes = [vp] * 5
+        lib.ref_repredict.restype = C.c_double
+        lib.ref_calendar_only.restype = C.c_double
+        lib.ref_free_fly.argtypes = [C.c_int, C.c_double, vp, vp, vp]
+        lib.ref_free_fly.restype = C.c_double
+        lib.ref_pcf.argtypes = [C.c_double, C.c_double, C.c_int, vp, vp, C.POINTER(C.c_int)]
+        lib.ref_pcf.restype = C.c_double
+        lib.ref_boop_cutoff.argtypes = [C.c_double] + [vp] * 5
+        lib.ref_boop_cutoff.restype = C.c_double
+        self.n = 0
+
+    def setup(self, n, lx, ly, t, x, y, vx, vy, rad, vr=None, cell_xy=None):
+        x, y, vx, vy, rad, vr = map(_f64, (x, y, vx, vy, rad, vr))
+        cells = None if cell_xy is None else np.ascontiguousarray(cell_xy, np.int32).reshape(-1)
+        rc = self.lib.ref_setup(n, lx, ly, float(t), _p(x), _p(y), _p(vx), _p(vy), _p(rad),
+                                _p(vr), _p(cells))
+        assert rc == 0
+        self.n = n
+
+    def teardown(self):
+        self.lib.ref_teardown()
+
+    def box(self):
+        nx, ny = C.c_int(), C.c_int()
+        d = [C.c_double() for _ in range(4)]
+        self.lib.ref_get_box(C.byref(nx), C.byref(ny), *[C.byref(v) for v in d])
+        return dict(nx=nx.value, ny=ny.value, csx=d[0].value, csy=d[1].value,
+                    fx=d[2].value, fy=d[3].value)
+
+    def cells(self):
+        out = np.empty(2 * self.n, np.int32)
+        self.lib.ref_get_cells(_p(out))
+        return out
+
+    def _outs(self):
+        n = self.n
+        return (np.empty(n, np.float64), np.empty(n, np.uint8), np.empty(n, np.float64),
+                np.empty(n, np.int32), np.empty(n, np.uint8))
+
+    def predict_first(self, grow=False):
+        tc, d, tl, p, ct = self._outs()
+        sec = self.lib.ref_predict_first(int(grow), _p(tc), _p(d), _p(tl), _p(p), _p(ct))
+        return dict(t_cross=tc, dir=d, t_coll=tl, partner=p, ctype=ct, seconds=sec)
+
+    def repredict(self):
+        tc, d, tl, p, ct = self._outs()
+        sec = self.lib.ref_repredict(_p(tc), _p(d), _p(tl), _p(p), _p(ct))
+        return dict(t_cross=tc, dir=d, t_coll=tl, partner=p, ctype=ct, seconds=sec)
+
+    def calendar_only(self) -> float:
+        return self.lib.ref_calendar_only()
+
+    def free_fly(self, t_new, grow=False):
+        x, y, rad = (np.empty(self.n, np.float64) for _ in range(3))
+        sec = self.lib.ref_free_fly(int(grow), float(t_new), _p(x), _p(y), _p(rad))
+        return dict(x=x, y=y, rad=rad, seconds=sec)
+
+    def pcf(self, dr, max_r, n_sub=0):
+        nb_guess = int(max_r / dr) + 2
+        g = np.zeros(nb_guess, np.float64)
+        r = np.zeros(nb_guess, np.float64)
+        nb = C.c_int(0)
+        sec = self.lib.ref_pcf(dr, max_r, n_sub, _p(g), _p(r), C.byref(nb))
+        return dict(num_bins=nb.value, g_r=g[:nb.value], r=r[:nb.value], seconds=sec)
+
+    def boop_cutoff(self, r_c=2.5):
+        n = self.n
+        q5, q6, q7, arg = (np.empty(n, np.float64) for _ in range(4))
+        nb = np.empty(n, np.int32)
+        sec = self.lib.ref_boop_cutoff(r_c, _p(q5), _p(q6), _p(q7), _p(arg), _p(nb))
+        return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, seconds=sec)

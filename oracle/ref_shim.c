@@ -1,0 +1,303 @@
+/*
+ * oracle/ref_shim.c -- TEST INFRASTRUCTURE, not product code.
+ *
+ * Thin driver around the UNMODIFIED reference (Syrocco/Graphical-EDMD).  The
+ * reference sources are not copied into this repository: this translation unit
+ * textually includes `EDMD.c` from the mounted reference tree at build time
+ * (oracle/Makefile passes -I<REF>/src), renaming its main(), exactly the unity
+ * build the reference's own Makefile does (Makefile:31,60).  The result is
+ * oracle/_ref/libedmd_ref.so (git-ignored, travels to the GPU box).
+ *
+ * Must be compiled as C (the unity TU relies on tentative definitions).
+ *
+ * Every ref_* entry point below fills the reference's globals from plain
+ * arrays, then runs the reference's own functions:
+ *   boxConstantHelper   src/EDMD.c:679
+ *   cellListInit        src/EDMD.c:1906
+ *   crossingEvent{Normal,Grow}, collisionEvent{Normal,Grow}
+ *                       src/EDMD.c:2343,2405,2829,3104
+ *   addNoise            src/EDMD.c:4828   (the recurring full re-predict)
+ *   freeFlyNormal/Grow  src/EDMD.c:4954,4992
+ *   calculate_pcf       src/pcf.c:16
+ *   computeBOOPCutoff   src/boop.c:61
+ */
+#define main edmd_reference_main
+#include "EDMD.c"
+#undef main
+
+#include <stdint.h>
+
+static int shim_live = 0;
+static int shim_total = 0;
+
+void ref_teardown(void)
+{
+	if (!shim_live)
+		return;
+	free(particles);
+	free(cellList);
+	if (eventList) {
+		for (int i = 0; i < shim_total; i++)
+			free(eventList[i]);
+		free(eventList);
+	}
+	free(eventPaul);
+	particles = NULL;
+	cellList = NULL;
+	eventList = NULL;
+	eventPaul = NULL;
+	shim_live = 0;
+}
+
+/* Load a synchronous snapshot.  cell_xy == NULL: cells come from the
+ * reference's cellListInit (coordToCell).  cell_xy != NULL: host-owned cell
+ * ids (interleaved X,Y) are linked in ascending particle order with the same
+ * head insertion addToCell does (src/EDMD.c:2071-2077).  vr may be NULL. */
+int ref_setup(int n, double lx, double ly, double t0,
+              const double *x, const double *y, const double *vx,
+              const double *vy, const double *rad, const double *vr_in,
+              const int *cell_xy)
+{
+	ref_teardown();
+	N = n;
+	Lx = lx;
+	Ly = ly;
+	t = t0;
+	boxConstantHelper();
+	particles = calloc(N, sizeof(particle));
+	if (!particles)
+		return -1;
+	for (int i = 0; i < N; i++) {
+		particle *p = particles + i;
+		p->num = i;
+		p->x = x[i];
+		p->y = y[i];
+		p->vx = vx[i];
+		p->vy = vy[i];
+		p->rad = rad[i];
+		p->vr = vr_in ? vr_in[i] : 0.0;
+		p->m = 1;
+		p->t = t0;
+		p->type = 1;
+		p->coll = 0;
+	}
+	if (!cell_xy) {
+		cellListInit();
+	} else {
+		cellList = calloc((size_t)Nxcells * Nycells, sizeof(particle *));
+		for (int i = 0; i < N; i++) {
+			particle *p = particles + i;
+			p->cell[0] = cell_xy[2 * i];
+			p->cell[1] = cell_xy[2 * i + 1];
+			p->prv = NULL;
+			p->nxt = cellList[p->cell[1] * Nxcells + p->cell[0]];
+			cellList[p->cell[1] * Nxcells + p->cell[0]] = p;
+			if (p->nxt)
+				p->nxt->prv = p;
+		}
+	}
+
+	/* calendar storage as in eventListInit (src/EDMD.c:1937-1953), without
+	 * scheduling the THERMO / SCREENSHOT / GROWSTOP bookkeeping events */
+	shim_total = 2 * N + suppSizeEvent;
+	eventList = calloc(shim_total, sizeof(node *));
+	eventPaul = calloc(paulListN + 1, sizeof(node *));
+	for (int i = 0; i < shim_total; i++)
+		eventList[i] = calloc(1, sizeof(node));
+	root = eventList[2 * N];
+	root->t = never + 1;
+	root->rgt = root->lft = root->top = NULL;
+	treeMin = NULL;
+	paulTime = t0;
+	actualPaulList = 0;
+	for (int i = 0; i < N; i++) {
+		eventList[i]->i = i;
+		eventList[N + i]->i = i;
+	}
+	shim_live = 1;
+	return 0;
+}
+
+static void shim_set_mode(int grow)
+{
+	if (grow) {
+		collisionEvent = &collisionEventGrow;
+		doTheCollision = &doTheCollisionGrow;
+		freeFly = &freeFlyGrow;
+		doTheWall = &doTheWallGrow;
+		crossingEvent = &crossingEventGrow;
+	} else {
+		collisionEvent = &collisionEventNormal;
+		doTheCollision = &doTheCollisionNormal;
+		freeFly = &freeFlyNormal;
+		doTheWall = &doTheWallNormal;
+		crossingEvent = &crossingEventNormal;
+	}
+}
+
+void ref_get_box(int *nx, int *ny, double *csx, double *csy, double *fx,
+                 double *fy)
+{
+	*nx = Nxcells;
+	*ny = Nycells;
+	*csx = cellxSize;
+	*csy = cellySize;
+	*fx = cellxFac;
+	*fy = cellyFac;
+}
+
+void ref_get_cells(int *cell_xy)
+{
+	for (int i = 0; i < N; i++) {
+		cell_xy[2 * i] = particles[i].cell[0];
+		cell_xy[2 * i + 1] = particles[i].cell[1];
+	}
+}
+
+static void shim_copy_out(double *t_cross, uint8_t *dir, double *t_coll,
+                          int32_t *partner, uint8_t *ctype)
+{
+	for (int i = 0; i < N; i++) {
+		if (t_cross)
+			t_cross[i] = eventList[i]->t;
+		if (dir)
+			dir[i] = (uint8_t)eventList[i]->j;
+		if (t_coll)
+			t_coll[i] = eventList[N + i]->t;
+		if (partner)
+			partner[i] = eventList[N + i]->j;
+		if (ctype)
+			ctype[i] = (uint8_t)eventList[N + i]->type;
+	}
+}
+
+static double shim_now(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+/* First sweep, the eventListInit loop (src/EDMD.c:2007-2012).  Must be the
+ * first predict after ref_setup (events are not in the calendar yet).
+ * Returns seconds spent in the loop. */
+double ref_predict_first(int grow, double *t_cross, uint8_t *dir,
+                         double *t_coll, int32_t *partner, uint8_t *ctype)
+{
+	shim_set_mode(grow);
+	double t0 = shim_now();
+	for (int i = 0; i < N; i++) {
+		crossingEvent(i);
+		collisionEvent(i);
+	}
+	double t1 = shim_now();
+	shim_copy_out(t_cross, dir, t_coll, partner, ctype);
+	return t1 - t0;
+}
+
+/* Recurring full re-predict: the reference's own thermostat tick addNoise()
+ * (src/EDMD.c:4828-4923).  In the CLI build `noise` is const 0, so the tick
+ * takes the velocity-rescale branch `v /= sqrt(E/N/T)` (:4899-4902); E and T
+ * are set so that factor is exactly 1 and the tick reduces to
+ * freeFly(dt=0) + coll++ + the remove/predict/insert sweep (:4909-4915).
+ * Requires a previous ref_predict_first.  Returns seconds. */
+double ref_repredict(double *t_cross, uint8_t *dir, double *t_coll,
+                     int32_t *partner, uint8_t *ctype)
+{
+	shim_set_mode(0);
+	T = 1.0;
+	E = (double)N;
+	double t0 = shim_now();
+	addNoise();
+	double t1 = shim_now();
+	removeEventFromQueue(eventList[2 * N + 2]); /* the re-armed NOISE event */
+	shim_copy_out(t_cross, dir, t_coll, partner, ctype);
+	return t1 - t0;
+}
+
+/* Calendar-only cost: remove + re-insert all 2N events unchanged
+ * (src/EDMD.c:2144-2221); the host residual after GPU offload. */
+double ref_calendar_only(void)
+{
+	double t0 = shim_now();
+	for (int j = 0; j < N; j++) {
+		removeEventFromQueue(eventList[j]);
+		addEventToQueue(eventList[j]);
+		removeEventFromQueue(eventList[N + j]);
+		addEventToQueue(eventList[N + j]);
+	}
+	return shim_now() - t0;
+}
+
+/* Batched free flight to t_new (takeAScreenshot loop, src/EDMD.c:4659-4661). */
+double ref_free_fly(int grow, double t_new, double *x, double *y, double *rad)
+{
+	shim_set_mode(grow);
+	t = t_new;
+	double t0 = shim_now();
+	for (int i = 0; i < N; i++)
+		freeFly(particles + i);
+	double t1 = shim_now();
+	for (int i = 0; i < N; i++) {
+		if (x)
+			x[i] = particles[i].x;
+		if (y)
+			y[i] = particles[i].y;
+		if (rad)
+			rad[i] = particles[i].rad;
+	}
+	return t1 - t0;
+}
+
+/* Per-particle local times for the asynchronous form (p->t != t). */
+void ref_set_particle_times(const double *tp)
+{
+	for (int i = 0; i < N; i++)
+		particles[i].t = tp[i];
+}
+
+/* calculate_pcf (src/pcf.c:16-75).  g_r / r hold at least (int)(max_r/dr)
+ * entries; first n_sub particles only when n_sub > 0 (bounded CPU sample with
+ * the same box, for timing).  Returns seconds. */
+double ref_pcf(double dr, double max_r, int n_sub, double *g_r, double *r,
+               int *num_bins)
+{
+	int n = (n_sub > 0 && n_sub < N) ? n_sub : N;
+	double t0 = shim_now();
+	pcf_data *d = calculate_pcf(particles, n, dr, max_r, Lx, Ly);
+	double t1 = shim_now();
+	*num_bins = d->num_bins;
+	for (int i = 0; i < d->num_bins; i++) {
+		if (g_r)
+			g_r[i] = d->g_r[i];
+		if (r)
+			r[i] = d->r[i];
+	}
+	free_pcf_data(d);
+	return t1 - t0;
+}
+
+/* computeBOOPCutoff (src/boop.c:61-107). */
+double ref_boop_cutoff(double r_c, double *q5, double *q6, double *q7,
+                       double *q6_arg, int32_t *neighbors)
+{
+	double t0 = shim_now();
+	boop_data *b = computeBOOPCutoff(particles, N, r_c, cellList, Nxcells);
+	double t1 = shim_now();
+	for (int i = 0; i < N; i++) {
+		if (q5)
+			q5[i] = b[i].q5;
+		if (q6)
+			q6[i] = b[i].q6;
+		if (q7)
+			q7[i] = b[i].q7;
+		if (q6_arg)
+			q6_arg[i] = b[i].q6_arg;
+		if (neighbors)
+			neighbors[i] = b[i].neighbors;
+	}
+	free(b);
+	return t1 - t0;
+}
+
+int ref_num_particles(void) { return N; }

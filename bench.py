@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full re-predict sweep (K0 cell index + K1 prediction) of the
+BASELINE.json workload `N=1000000 phi=0.70` (configs[2]) on synthetic
+non-overlapping disks.  `value` is particles/s with the state resident in HBM
+(L2 flushed between steps, CUDA events on the library's own stream); `e2e` is
+the same sweep through the public C ABI call pair edmd_cuda_upload +
+edmd_cuda_predict_all with pinned HOST buffers, copies inside the timed region.
+The per-frame analysis (psi6 + full-range g(r)) is reported under "analysis".
+
+`--impl reference` times the reference's own CPU implementation of the path
+(oracle/_ref = the unmodified reference's addNoise() re-predict loop; falls back
+to the oracle port when _ref is absent) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_PART = 1_000_000
+PHI = 0.70
+SEED = 12345
+BYTES_PER_PARTICLE = 62          # 40 B in (x,y,vx,vy,rad) + 22 B out
+L2_FLUSH_BYTES = 256 << 20       # > 126 MB L2
+METRIC = "full re-predict particles/s at N=1M"
+UNIT = "particles/s"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(cfg, repeats=3):
+    """The reference's own re-predict (addNoise loop) on one host core."""
+    from oracle.oracle_py import Oracle, Reference
+    n = cfg["n"]
+    if Reference.available():
+        ref = Reference()
+        ref.setup(n, cfg["lx"], cfg["ly"], 0.0, cfg["x"], cfg["y"], cfg["vx"], cfg["vy"], cfg["rad"])
+        ref.predict_first()
+        secs = [ref.repredict()["seconds"] for _ in range(repeats)]
+        cal = ref.calendar_only()
+        ref.teardown()
+        return {"value": n / min(secs), "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"{repeats} full re-predict sweeps (reference addNoise loop incl. calendar "
+                          f"remove/insert) of the same N={n} snapshot, best of {repeats}",
+                "seconds_per_sweep": min(secs), "calendar_only_seconds": cal}
+    orc = Oracle()
+    secs = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.predict_all(n, cfg["lx"], cfg["ly"], 0.0, cfg["x"], cfg["y"], cfg["vx"], cfg["vy"], cfg["rad"])
+        secs.append(time.perf_counter() - t0)
+    return {"value": n / min(secs), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{repeats} sweeps of the oracle port (no calendar) at N={n}, best",
+            "seconds_per_sweep": min(secs)}
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle_py import Oracle, Reference
+    n = cfg["n"]
+    steps, warm = args.steps, args.warmup
+    if Reference.available():
+        kind = "reference"
+        ref = Reference()
+        ref.setup(n, cfg["lx"], cfg["ly"], 0.0, cfg["x"], cfg["y"], cfg["vx"], cfg["vy"], cfg["rad"])
+        ref.predict_first()
+        for _ in range(warm):
+            ref.repredict()
+        secs = [ref.repredict()["seconds"] for _ in range(steps)]
+        ref.teardown()
+    else:
+        kind = "port"
+        orc = Oracle()
+        secs = []
+        for it in range(warm + steps):
+            t0 = time.perf_counter()
+            orc.predict_all(n, cfg["lx"], cfg["ly"], 0.0, cfg["x"], cfg["y"], cfg["vx"], cfg["vy"], cfg["rad"])
+            if it >= warm:
+                secs.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(secs))
+    val = n / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(cfg),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
+                         "sample": f"{steps} full re-predict sweeps of the N={n} snapshot "
+                                   "(single-threaded, as the reference ships)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(cfg):
+    return {"workload": f"N={cfg['n']} phi={PHI} monodisperse liquid-density jittered-lattice "
+                        "snapshot, shuffled ids, full re-predict sweep (BASELINE configs[2])",
+            "n_particles": cfg["n"], "phi": PHI, "seed": SEED,
+            "box": [cfg["lx"], cfg["ly"]],
+            "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset outside the timed events)"}
+
+
+def profile_traffic():
+    """dram bytes per launch of K1 from the committed ncu summary, if any."""
+    p = ROOT / "profiles" / "k1_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+
+    pkg = entry.load_package()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = cfg["n"]
+    steps, warm = args.steps, max(args.warmup, 3)
+    B = pkg.binding
+    ctx = pkg.EdmdCuda(n, cfg["lx"], cfg["ly"], device=local)
+
+    # pinned host buffers for the end-to-end leg
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    keep, host = [], {}
+    for k in ("x", "y", "vx", "vy", "rad"):
+        t, host[k] = pinned(cfg[k])
+        keep.append(t)
+    outs = {}
+    for k, dt in (("t_cross", np.float64), ("dir", np.uint8), ("t_coll", np.float64),
+                  ("partner", np.int32), ("ctype", np.uint8)):
+        t = torch.empty(n, dtype=getattr(torch, np.dtype(dt).name)).pin_memory()
+        keep.append(t)
+        outs[k] = t.numpy()
+    ov = np.zeros(2, np.int32)
+    lib, h = ctx.lib, ctx._h
+    P = B._ptr
+
+    def e2e_step():
+        rc = lib.edmd_cuda_upload(h, P(host["x"]), P(host["y"]), P(host["vx"]), P(host["vy"]),
+                                  P(host["rad"]), None, 0.0)
+        assert rc == 0, lib.edmd_cuda_last_error(h)
+        rc = lib.edmd_cuda_predict_all(h, B.MODE_NORMAL, None, P(outs["t_cross"]), P(outs["dir"]),
+                                       P(outs["t_coll"]), P(outs["partner"]), P(outs["ctype"]), P(ov))
+        assert rc == 0, lib.edmd_cuda_last_error(h)
+
+    ctx.upload(host["x"], host["y"], host["vx"], host["vy"], host["rad"], t=0.0)
+
+    # ---- device-resident sweep -------------------------------------------
+    barrier()
+    l0 = ctx.launches
+    with ClockSampler(local) as clk:
+        tot, main = ctx.bench(B.BENCH_SWEEP, warmup=warm, iters=steps, flush_bytes=L2_FLUSH_BYTES)
+        barrier()
+        launches_timed = (ctx.launches - l0) * steps // (steps + warm)
+        # ---- end to end through the C ABI, host buffers ------------------
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e2e_times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            e2e_step()
+            e2e_times.append(time.perf_counter() - t0)
+        barrier()
+    clocks = clk.summary()
+
+    ms_step = float(np.mean(tot))
+    ms_k1 = float(np.mean(main))
+    e2e_ms = float(np.mean(e2e_times)) * 1e3
+    if world > 1:
+        tt = torch.tensor([ms_step, ms_k1, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_step, ms_k1, e2e_ms = tt.tolist()
+
+    # ---- per-frame analysis (rank-local; reported, not the headline) -----
+    analysis = {}
+    if args.analysis != "none" and rank == 0:
+        bt, _ = ctx.bench(B.BENCH_BOOP, dr=2.5, warmup=3, iters=10, flush_bytes=L2_FLUSH_BYTES)
+        analysis["psi6_ms"] = float(np.mean(bt))
+        analysis["psi6_particles_per_s"] = n / (np.mean(bt) * 1e-3)
+        analysis["psi6_hbm_frac"] = 56.0 * n / (np.mean(bt) * 1e-3) / 1e9 / peaks()[0]
+        max_r_cut = 12.0
+        if args.analysis == "full":
+            max_r = min(cfg["lx"], cfg["ly"]) / 2
+            pt, _ = ctx.bench(B.BENCH_PCF, dr=0.1, max_r=max_r, warmup=0, iters=1)
+            pairs = n * (n - 1) / 2
+            analysis["gr_full_ms"] = float(pt[0])
+            analysis["gr_full_bins"] = int(max_r / 0.1)
+            analysis["gr_full_pairs_per_s"] = pairs / (pt[0] * 1e-3)
+            analysis["gr_full_fp64_tflops_9op"] = 9 * pairs / (pt[0] * 1e-3) / 1e12
+            analysis["frames_per_s_gr_full_plus_psi6"] = 1e3 / (pt[0] + np.mean(bt))
+        analysis["note"] = ("psi6 = computeBOOPCutoff r_c=2.5 (56 B/particle, HBM); g(r) full range = "
+                            "calculate_pcf dr=0.1 max_r=min(L)/2, all N(N-1)/2 pairs (FP64 pipe)")
+        del max_r_cut
+
+    cpu = cpu_baseline(cfg) if (rank == 0 and world == 1 and not args.no_cpu) else None
+
+    if rank == 0:
+        peak, how = peaks()
+        achieved = BYTES_PER_PARTICLE * n / (ms_k1 * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * n / (ms_step * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(cfg),
+            "clocks": clocks,
+            "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 40 * n, "d2h_bytes_per_step": 22 * n,
+                    "api": "edmd_cuda_upload + edmd_cuda_predict_all, pinned host buffers"},
+            "gpu_launches": int(launches_timed),
+            "roofline": {"bound": "hbm", "kernel": "k_predict (K1)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": how + " (burst copy)",
+                         "traffic": profile_traffic(),
+                         "ms_kernel": ms_k1, "bytes_per_particle": BYTES_PER_PARTICLE},
+            "analysis": analysis,
+        }
+        if world > 1:
+            line["config"]["parallelism"] = f"{world} independent replicas (slab path: see DESIGN.md)"
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--analysis", choices=["none", "psi6", "full"], default="full")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--n", type=int, default=N_PART)
+    args = ap.parse_args()
+
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    cfg = pkg.synth.lattice_config(args.n, PHI, SEED, shuffle=True)
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,75 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference
+(oracle/_ref/libedmd_ref.so, built from /root/reference by oracle/Makefile).
+
+Run in the build container (where /root/reference is mounted):
+    python tests/golden/make_golden.py
+The reference itself ships no tests or golden vectors;
+these files pin the oracle restatement -- and through it the CUDA path -- to
+outputs of the reference's own functions on fixed inputs.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as entry  # noqa: E402
+from oracle.oracle_py import Reference  # noqa: E402
+
+pkg = entry.load_package()
+ref = Reference()
+
+
+def sweep_case(name, cfg, t, grow=False, with_analysis=True, pcf_max_r=None):
+    n = cfg["n"]
+    ref.setup(n, cfg["lx"], cfg["ly"], t, cfg["x"], cfg["y"], cfg["vx"], cfg["vy"], cfg["rad"],
+              vr=cfg.get("vr"))
+    out = dict(n=n, lx=cfg["lx"], ly=cfg["ly"], t=t, grow=int(grow),
+               x=cfg["x"], y=cfg["y"], vx=cfg["vx"], vy=cfg["vy"], rad=cfg["rad"])
+    if grow:
+        out["vr"] = cfg["vr"]
+    box = ref.box()
+    out.update(nx=box["nx"], ny=box["ny"], csx=box["csx"], csy=box["csy"])
+    out["cells"] = ref.cells()
+    first = ref.predict_first(grow=grow)
+    for k in ("t_cross", "dir", "t_coll", "partner", "ctype"):
+        out["first_" + k] = first[k]
+    if not grow:
+        again = ref.repredict()  # the reference's own addNoise() tick
+        for k in ("t_cross", "dir", "t_coll", "partner", "ctype"):
+            out["re_" + k] = again[k]
+    if with_analysis and not grow:
+        b = ref.boop_cutoff(2.5)
+        for k in ("q5", "q6", "q7", "q6_arg", "neighbors"):
+            out["boop_" + k] = b[k]
+        max_r = pcf_max_r if pcf_max_r else min(cfg["lx"], cfg["ly"]) / 2
+        p = ref.pcf(0.1, max_r)
+        out["pcf_dr"] = 0.1
+        out["pcf_max_r"] = max_r
+        out["pcf_g"] = p["g_r"]
+        out["pcf_r"] = p["r"]
+    ff = ref.free_fly(t + 0.4375, grow=grow)
+    out["ff_t"] = t + 0.4375
+    out["ff_x"], out["ff_y"], out["ff_rad"] = ff["x"], ff["y"], ff["rad"]
+    np.savez_compressed(HERE / f"{name}.npz", **out)
+    print("wrote", name, "n =", n)
+
+
+# BASELINE config 1 flavour: N=2000, phi=0.7, 30 % small disks (reference CLI defaults)
+sweep_case("sweep_n2000_phi070_bidisperse",
+           pkg.synth.lattice_config(2000, 0.70, seed=1, small_fraction=0.3), t=0.0)
+# dense monodisperse, non-zero sweep time
+sweep_case("sweep_n3000_phi085_mono",
+           pkg.synth.lattice_config(3000, 0.85, seed=2), t=17.25)
+# lattice order (ids correlated with position), near liquid-hexatic density
+sweep_case("sweep_n2500_phi072_ordered",
+           pkg.synth.lattice_config(2500, 0.72, seed=3, shuffle=False), t=3.0)
+# growth mode (setup sweep)
+g = pkg.synth.growth_config(2000, 0.70, seed=4)
+rng = np.random.default_rng(4)
+g["vr"] = g["vr"] * (0.5 + rng.random(g["n"]))
+g["rad"] = g["rad"] * (0.7 + 0.3 * rng.random(g["n"]))
+sweep_case("sweep_n2000_grow", g, t=g["t"], grow=True)
+ref.teardown()

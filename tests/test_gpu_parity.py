@@ -1,0 +1,303 @@
+"""GPU parity tests: the CUDA path, called through the C ABI
+(include/edmd_cuda.h), against the oracle on the same seeded inputs and against
+the golden fixtures generated from the unmodified reference.
+
+Gates (BASELINE.json north_star): partner / dir / ctype bit-exact; event times
+bit-exact (bar: 1e-12 relative); g(r) integer pair counts exact (=> g within
+1e-10); psi6 within 1e-10, neighbour counts exact."""
+import numpy as np
+import pytest
+
+from helpers import (ANALYSIS_ATOL, GOLDEN_CASES, assert_boop_close, assert_events_equal,
+                     cfg_of, load_golden, pcf_counts_from_g)
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_sweep(pkg, c, *, t=None, cells=None, mode=0, allow_overlap=False):
+    t = c.get("t", 0.0) if t is None else t
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], cell_xy=cells, t=t)
+        return ctx.predict_all(mode=mode, vr=c.get("vr"), allow_overlap=allow_overlap)
+
+
+def oracle_sweep(oracle, c, *, t=None, cells=None, mode=0):
+    t = c.get("t", 0.0) if t is None else t
+    return oracle.predict_all(c["n"], c["lx"], c["ly"], t, c["x"], c["y"], c["vx"], c["vy"],
+                              c["rad"], vr=c.get("vr"), cell_xy=cells, mode=mode)
+
+
+# ---------------------------------------------------------------- golden ----
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_sweep_matches_reference_golden(pkg, name):
+    g = load_golden(name)
+    c = cfg_of(g)
+    grow = bool(g["grow"])
+    got = gpu_sweep(pkg, c, mode=int(grow))
+    assert tuple(got["overlap"]) == (-1, -1)
+    assert_events_equal(got, g, exact_times=not grow, prefix="first_")
+    if not grow:
+        assert_events_equal(got, g, exact_times=True, prefix="re_")
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_free_fly_matches_reference_golden(pkg, name):
+    g = load_golden(name)
+    c = cfg_of(g)
+    grow = bool(g["grow"])
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=c["t"])
+        if grow:
+            ctx.set_growth(c["vr"])
+        ctx.free_fly(float(g["ff_t"]), mode=int(grow))
+        s = ctx.download_state()
+    assert np.array_equal(s["x"], g["ff_x"])
+    assert np.array_equal(s["y"], g["ff_y"])
+    assert np.array_equal(s["rad"], g["ff_rad"])
+    assert np.array_equal(s["vx"], c["vx"]) and np.array_equal(s["vy"], c["vy"])
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN_CASES if "grow" not in n])
+def test_analysis_matches_reference_golden(pkg, name):
+    g = load_golden(name)
+    c = cfg_of(g)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=c["t"])
+        b = ctx.boop_cutoff(2.5)
+        p = ctx.pcf(float(g["pcf_dr"]), float(g["pcf_max_r"]))
+    assert_boop_close(b, g, prefix="boop_")
+    assert abs(b["mean_q6"] - g["boop_q6"].mean()) <= ANALYSIS_ATOL
+    assert p["num_bins"] == len(g["pcf_g"])
+    want = pcf_counts_from_g(g["pcf_g"], c["n"], c["lx"], c["ly"], float(g["pcf_dr"]))
+    assert np.array_equal(p["counts"], want)
+    assert np.abs(p["g_r"] - g["pcf_g"]).max() <= ANALYSIS_ATOL
+
+
+# ------------------------------------------------- oracle, BASELINE sizes ----
+SWEEP_CASES = [
+    # (N, phi, seed, small_fraction, shuffle)   BASELINE.json configs
+    (2000, 0.70, 1, 0.3, True),      # configs[0]: reference CLI defaults, bidisperse
+    (100000, 0.72, 2, 0.0, True),    # configs[1]
+    (1000000, 0.70, 3, 0.0, True),   # configs[2]
+    (1000000, 0.85, 1, 0.0, True),   # configs[4]
+    (1000000, 0.70, 2, 0.3, False),  # bidisperse, lattice order
+    (4000000, 0.70, 3, 0.0, True),   # configs[3] (whole system on one GPU)
+]
+
+
+@pytest.mark.parametrize("n,phi,seed,sf,shuffle", SWEEP_CASES)
+def test_sweep_matches_oracle(pkg, oracle, n, phi, seed, sf, shuffle):
+    c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf, shuffle=shuffle)
+    t = 12.5 * seed
+    got = gpu_sweep(pkg, c, t=t)
+    want = oracle_sweep(oracle, c, t=t)
+    assert want["rc"] == 0
+    assert_events_equal(got, want)
+    # size-independent properties
+    assert got["dir"].min() >= 1 and got["dir"].max() <= 4
+    assert (got["t_cross"] >= t).all() and (got["t_coll"] >= t).all()
+    has = got["t_coll"] < 1e25
+    i = np.nonzero(has)[0]
+    j = got["partner"][i]
+    mutual = got["t_coll"][j] == got["t_coll"][i]
+    assert np.array_equal(got["partner"][j[mutual]], i[mutual])
+    assert (got["partner"][~has] == 0).all()
+    assert (got["t_coll"][~has] == t + 1e26).all()
+
+
+def test_sweep_is_deterministic_and_reentrant(pkg):
+    c = pkg.synth.lattice_config(200000, 0.72, seed=5)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=1.0)
+        a = ctx.predict_all()
+        b = ctx.predict_all()      # idempotent on resident state
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=1.0)
+        d = ctx.predict_all()
+    for k in ("t_cross", "dir", "t_coll", "partner", "ctype"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], d[k])
+
+
+def test_growth_sweep_matches_oracle(pkg, oracle):
+    c = pkg.synth.growth_config(100000, 0.70, seed=7)
+    rng = np.random.default_rng(7)
+    c["vr"] = c["vr"] * (0.5 + rng.random(c["n"]))
+    c["rad"] = c["rad"] * (0.7 + 0.3 * rng.random(c["n"]))
+    got = gpu_sweep(pkg, c, mode=1)
+    want = oracle_sweep(oracle, c, mode=1)
+    assert_events_equal(got, want)   # same source order => bit-exact vs the restatement
+
+
+def test_host_cells_and_aos_upload(pkg, oracle):
+    """Mid-run form: the host supplies cell[2]; a few particles sit on the
+    'wrong' side of their boundary (as after a crossing event at the boundary)."""
+    c = pkg.synth.lattice_config(50000, 0.70, seed=8)
+    n = c["n"]
+    cells = oracle.cells(n, c["lx"], c["ly"], c["x"], c["y"]).reshape(n, 2).copy()
+    box = oracle.box(n, c["lx"], c["ly"])
+    # particles within 0.03 of their right-hand boundary are moved exactly onto it but
+    # keep the old cell (0.03 cannot create an overlap at this density)
+    edge = (cells[:, 0] + 1) * box.csx
+    idx = np.nonzero((edge - c["x"] < 0.03) & (cells[:, 0] + 1 < box.nx))[0]
+    assert idx.size > 100
+    c["x"] = c["x"].copy()
+    c["x"][idx] = edge[idx]
+    assert not np.array_equal(oracle.cells(n, c["lx"], c["ly"], c["x"], c["y"]).reshape(n, 2), cells)
+    want = oracle_sweep(oracle, c, t=2.0, cells=cells)
+    got = gpu_sweep(pkg, c, t=2.0, cells=cells)
+    assert_events_equal(got, want)
+    # the same through the array-of-records entry point (reference struct stride)
+    rec = np.zeros(n, dtype=np.dtype({
+        "names": ["rad", "x", "y", "vx", "vy", "cell"],
+        "formats": ["f8", "f8", "f8", "f8", "f8", ("i4", 2)],
+        "offsets": [0, 8, 16, 24, 32, 136], "itemsize": 144}))
+    for k in ("rad", "x", "y", "vx", "vy"):
+        rec[k] = c[k]
+    rec["cell"] = cells
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload_aos(rec, t=2.0, with_cells=True)
+        got2 = ctx.predict_all()
+    assert_events_equal(got2, want)
+
+
+# ------------------------------------------------------------ edge cases ----
+def test_empty_and_single_particle(pkg):
+    e = np.zeros(0)
+    with pkg.EdmdCuda(0, 10.0, 10.0) as ctx:
+        ctx.upload(e, e, e, e, e, t=0.0)
+        o = ctx.predict_all()
+        assert o["t_coll"].size == 0
+        assert ctx.pcf(0.1, 5.0)["counts"].sum() == 0
+    with pkg.EdmdCuda(1, 10.0, 10.0) as ctx:
+        ctx.upload(np.array([1.0]), np.array([1.0]), np.array([0.5]), np.array([-0.25]),
+                   np.array([1.0]), t=2.0)
+        o = ctx.predict_all()
+        assert o["partner"][0] == 0 and o["t_coll"][0] == 2.0 + 1e26 and o["ctype"][0] == 1
+        assert o["dir"][0] == 2 and o["t_cross"][0] == 2.0 + (2.0 - 1.0) / 0.5
+        b = ctx.boop_cutoff(2.5)
+        assert b["neighbors"][0] == 0 and b["q6"][0] == 0.0 and b["q6_arg"][0] == 0.0
+
+
+@pytest.mark.parametrize("lx,ly", [(2.5, 2.5), (4.5, 9.0), (5.0, 2.2), (6.1, 6.1), (7.9, 40.0)])
+def test_tiny_boxes_with_repeated_cells(pkg, oracle, lx, ly):
+    """nx or ny < 3: the reference's 3x3 scan visits the same cell more than
+    once (and psi6 double counts); the device must do the same."""
+    rng = np.random.default_rng(int(lx * 10 + ly))
+    n = max(2, int(lx * ly / 12))
+    x = rng.random(n) * lx
+    y = rng.random(n) * ly
+    vx = rng.standard_normal(n)
+    vy = rng.standard_normal(n)
+    rad = np.full(n, 0.05)   # tiny disks: no overlap worries
+    c = dict(n=n, lx=lx, ly=ly, x=x, y=y, vx=vx, vy=vy, rad=rad)
+    got = gpu_sweep(pkg, c, t=0.5)
+    want = oracle_sweep(oracle, c, t=0.5)
+    assert_events_equal(got, want)
+    with pkg.EdmdCuda(n, lx, ly) as ctx:
+        ctx.upload(x, y, vx, vy, rad, t=0.5)
+        b = ctx.boop_cutoff(2.5)
+    assert_boop_close(b, oracle.boop_cutoff(n, lx, ly, x, y, 2.5))
+
+
+def test_exact_ties_follow_reference_scan_order(pkg, oracle):
+    """Two candidates with identical pair times: the first in the reference's
+    scan order (rows, columns, then descending id inside a cell) wins."""
+    lx = ly = 20.0
+    # particle 0 at rest in the middle; mirrored partners approach with equal speed
+    x = np.array([11.0, 8.5, 13.5, 11.0, 11.0, 11.5])
+    y = np.array([11.0, 11.0, 11.0, 8.5, 13.5, 11.5])
+    vx = np.array([0.0, 1.0, -1.0, 0.0, 0.0, 0.0])
+    vy = np.array([0.0, 0.0, 0.0, 1.0, -1.0, 0.0])
+    rad = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 0.01])
+    for perm in (np.arange(6), np.array([5, 4, 3, 2, 1, 0]), np.array([2, 0, 4, 1, 5, 3])):
+        c = dict(n=6, lx=lx, ly=ly, x=x[perm], y=y[perm], vx=vx[perm], vy=vy[perm], rad=rad[perm])
+        got = gpu_sweep(pkg, c)
+        want = oracle_sweep(oracle, c)
+        assert_events_equal(got, want)
+
+
+def test_nan_candidates_lose(pkg, oracle):
+    """Identical velocities: b = 0, v2 = 0 => 0/0 = NaN, `dt > NaN` is false."""
+    lx = ly = 16.0
+    x = np.array([5.0, 7.5, 11.0]); y = np.array([5.0, 5.0, 5.5])
+    vx = np.array([0.25, 0.25, -1.0]); vy = np.array([0.5, 0.5, 0.0])
+    rad = np.ones(3)
+    c = dict(n=3, lx=lx, ly=ly, x=x, y=y, vx=vx, vy=vy, rad=rad)
+    got = gpu_sweep(pkg, c)
+    want = oracle_sweep(oracle, c)
+    assert_events_equal(got, want)
+    assert not np.isnan(got["t_coll"]).any()
+
+
+def test_overlap_is_reported_not_fatal(pkg, oracle):
+    c = pkg.synth.lattice_config(5000, 0.70, seed=9)
+    c["x"] = c["x"].copy(); c["y"] = c["y"].copy()
+    c["vx"] = c["vx"].copy(); c["vy"] = c["vy"].copy()
+    # drop particle 4000 onto particle 17 (approaching) and 4500 onto 99
+    for a, b in ((4000, 17), (4500, 99)):
+        c["x"][a] = c["x"][b] + 1.2 if c["x"][b] + 1.2 < c["lx"] else c["x"][b] - 1.2
+        c["y"][a] = c["y"][b]
+        s = np.sign(c["x"][a] - c["x"][b])
+        c["vx"][a], c["vx"][b] = -s, s
+        c["vy"][a] = c["vy"][b] = 0.0
+    want = oracle_sweep(oracle, c)
+    assert want["rc"] == 1
+    got = gpu_sweep(pkg, c, allow_overlap=True)
+    assert got["rc"] == pkg.binding.EOVERLAP
+    assert tuple(got["overlap"]) == tuple(want["overlap"])
+    assert_events_equal(got, want)   # outputs are still filled, like the oracle's
+
+
+def test_bad_cell_id_is_an_error(pkg):
+    c = pkg.synth.lattice_config(1000, 0.5, seed=10)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        x = c["x"].copy()
+        x[3] = c["lx"] * 1.5
+        with pytest.raises(pkg.EdmdError) as ei:
+            ctx.upload(x, c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        assert ei.value.code == pkg.binding.ECELL
+        with pytest.raises(pkg.EdmdError) as ei:
+            ctx.predict_all()
+        assert ei.value.code == pkg.binding.ESTATE
+
+
+# ------------------------------------------------------------- analysis ----
+@pytest.mark.parametrize("n,phi,seed,sf", [(100000, 0.72, 2, 0.0), (1000000, 0.70, 3, 0.0),
+                                           (1000000, 0.85, 1, 0.3)])
+def test_boop_matches_oracle(pkg, oracle, n, phi, seed, sf):
+    c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        b = ctx.boop_cutoff(2.5)
+    want = oracle.boop_cutoff(c["n"], c["lx"], c["ly"], c["x"], c["y"], 2.5)
+    assert_boop_close(b, want)
+    assert abs(b["mean_q6"] - want["q6"].mean()) <= ANALYSIS_ATOL
+    # the reference's truncation (3x3 cells of width ~2 with r_c = 2.5) is reproduced:
+    # at phi = 0.72 on a near-perfect lattice not every particle sees 6 neighbours
+    assert b["neighbors"].max() <= 8
+
+
+@pytest.mark.parametrize("n,phi,seed,dr,frac", [(30000, 0.70, 4, 0.1, 0.5), (50000, 0.72, 5, 0.1, 0.5),
+                                                (20000, 0.85, 6, 2.0, 0.5), (20000, 0.70, 7, 0.03, 0.1)])
+def test_pcf_counts_match_oracle(pkg, oracle, n, phi, seed, dr, frac):
+    c = pkg.synth.lattice_config(n, phi, seed)
+    max_r = min(c["lx"], c["ly"]) * frac
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        p = ctx.pcf(dr, max_r)
+    want = oracle.pcf(c["n"], c["lx"], c["ly"], c["x"], c["y"], dr, max_r)
+    assert p["num_bins"] == want["num_bins"]
+    assert np.array_equal(p["counts"], want["counts"])
+    assert np.abs(p["g_r"] - want["g_r"]).max() <= ANALYSIS_ATOL
+
+
+def test_pcf_counts_every_pair_once(pkg):
+    """Checksum at full size: with max_r beyond the half-diagonal every one of
+    the N(N-1)/2 pairs lands in exactly one bin."""
+    c = pkg.synth.lattice_config(300000, 0.70, seed=12)
+    n = c["n"]
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        p = ctx.pcf(0.1, 0.75 * max(c["lx"], c["ly"]))
+    assert int(p["counts"].sum()) == n * (n - 1) // 2
+    # hard disks: nothing below contact
+    assert p["counts"][: int(1.99 / 0.1)].sum() == 0

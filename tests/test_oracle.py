@@ -1,0 +1,112 @@
+"""CPU tests: the oracle restatement against the golden fixtures generated from
+the unmodified reference, against the live reference where oracle/_ref exists,
+and its own invariants."""
+import numpy as np
+import pytest
+
+from helpers import (GOLDEN_CASES, ANALYSIS_ATOL, assert_boop_close, assert_events_equal,
+                     cfg_of, load_golden, pcf_counts_from_g)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_sweep_matches_golden(oracle, name):
+    g = load_golden(name)
+    c = cfg_of(g)
+    grow = bool(g["grow"])
+    box = oracle.box(c["n"], c["lx"], c["ly"])
+    assert (box.nx, box.ny) == (int(g["nx"]), int(g["ny"]))
+    assert box.csx == float(g["csx"]) and box.csy == float(g["csy"])
+    cells = oracle.cells(c["n"], c["lx"], c["ly"], c["x"], c["y"])
+    assert np.array_equal(cells, g["cells"])
+    got = oracle.predict_all(c["n"], c["lx"], c["ly"], c["t"], c["x"], c["y"], c["vx"], c["vy"],
+                             c["rad"], vr=c.get("vr"), mode=int(grow))
+    assert got["rc"] == 0 and tuple(got["overlap"]) == (-1, -1)
+    # growth quadratic: the reference's -ffast-math build reassociates it (1e-15 rel)
+    assert_events_equal(got, g, exact_times=not grow, prefix="first_")
+    if not grow:
+        # the reference's own thermostat tick (addNoise) re-predicts identically
+        assert_events_equal(got, g, exact_times=True, prefix="re_")
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_free_fly_matches_golden(oracle, name):
+    g = load_golden(name)
+    c = cfg_of(g)
+    grow = bool(g["grow"])
+    got = oracle.free_fly(c["n"], c["lx"], c["ly"], c["t"], float(g["ff_t"]), c["x"], c["y"],
+                          c["vx"], c["vy"], rad=c["rad"], vr=c.get("vr"), mode=int(grow))
+    assert np.array_equal(got["x"], g["ff_x"])
+    assert np.array_equal(got["y"], g["ff_y"])
+    assert np.array_equal(got["rad"], g["ff_rad"])
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN_CASES if "grow" not in n])
+def test_oracle_analysis_matches_golden(oracle, name):
+    g = load_golden(name)
+    c = cfg_of(g)
+    b = oracle.boop_cutoff(c["n"], c["lx"], c["ly"], c["x"], c["y"], 2.5)
+    assert_boop_close(b, g, prefix="boop_")
+    p = oracle.pcf(c["n"], c["lx"], c["ly"], c["x"], c["y"], float(g["pcf_dr"]), float(g["pcf_max_r"]))
+    assert p["num_bins"] == len(g["pcf_g"])
+    assert np.abs(p["g_r"] - g["pcf_g"]).max() <= ANALYSIS_ATOL
+    want_counts = pcf_counts_from_g(g["pcf_g"], c["n"], c["lx"], c["ly"], float(g["pcf_dr"]))
+    assert np.array_equal(p["counts"], want_counts)
+
+
+def test_oracle_vs_live_reference(oracle, reference, pkg):
+    """Where the unmodified reference is built, re-pin on fresh seeds/sizes."""
+    for n, phi, seed, sf in [(5000, 0.70, 11, 0.3), (20000, 0.72, 12, 0.0), (20000, 0.85, 13, 0.0)]:
+        c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf)
+        t = 0.75 * seed
+        reference.setup(c["n"], c["lx"], c["ly"], t, c["x"], c["y"], c["vx"], c["vy"], c["rad"])
+        want = reference.predict_first()
+        got = oracle.predict_all(c["n"], c["lx"], c["ly"], t, c["x"], c["y"], c["vx"], c["vy"], c["rad"])
+        assert_events_equal(got, want)
+        assert_events_equal(got, reference.repredict())
+        assert_boop_close(oracle.boop_cutoff(c["n"], c["lx"], c["ly"], c["x"], c["y"], 2.5),
+                          reference.boop_cutoff(2.5))
+    reference.teardown()
+
+
+def test_oracle_host_cells_override(oracle, pkg):
+    """Host-owned cell ids win over coordinates: a particle one
+    ulp across its boundary keeps the host's cell."""
+    c = pkg.synth.lattice_config(400, 0.6, seed=5)
+    n = c["n"]
+    cells = oracle.cells(n, c["lx"], c["ly"], c["x"], c["y"])
+    a = oracle.predict_all(n, c["lx"], c["ly"], 0.0, c["x"], c["y"], c["vx"], c["vy"], c["rad"])
+    b = oracle.predict_all(n, c["lx"], c["ly"], 0.0, c["x"], c["y"], c["vx"], c["vy"], c["rad"],
+                           cell_xy=cells)
+    assert_events_equal(a, b)
+
+
+def test_oracle_symmetry_property(oracle, pkg):
+    """If i's earliest partner is j at time tau and j's minimum is also tau,
+    then j's partner is i (same pair time from both sides)."""
+    c = pkg.synth.lattice_config(5000, 0.72, seed=6)
+    o = oracle.predict_all(c["n"], c["lx"], c["ly"], 0.0, c["x"], c["y"], c["vx"], c["vy"], c["rad"])
+    has = o["t_coll"] < 1e25
+    i = np.nonzero(has)[0]
+    j = o["partner"][i]
+    mutual = o["t_coll"][j] == o["t_coll"][i]
+    assert np.array_equal(o["partner"][j[mutual]], i[mutual])
+    assert mutual.mean() > 0.3
+
+
+def test_oracle_overlap_flag(oracle):
+    lx = ly = 12.0
+    x = np.array([3.0, 4.2, 9.0]); y = np.array([3.0, 3.0, 9.0])
+    vx = np.array([1.0, -1.0, 0.3]); vy = np.array([0.0, 0.0, 0.1])
+    rad = np.ones(3)
+    o = oracle.predict_all(3, lx, ly, 0.0, x, y, vx, vy, rad)
+    assert o["rc"] == 1 and tuple(o["overlap"]) == (0, 1)
+
+
+def test_oracle_empty_and_single(oracle):
+    e = np.zeros(0)
+    o = oracle.predict_all(0, 10.0, 10.0, 0.0, e, e, e, e, e)
+    assert o["rc"] == 0 and o["t_coll"].size == 0
+    one = oracle.predict_all(1, 10.0, 10.0, 2.0, np.array([1.0]), np.array([1.0]),
+                             np.array([0.5]), np.array([-0.25]), np.array([1.0]))
+    assert one["partner"][0] == 0 and one["t_coll"][0] == 2.0 + 1e26
+    assert one["dir"][0] == 2 and one["t_cross"][0] == 2.0 + (2.0 - 1.0) / 0.5

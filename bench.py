@@ -271,7 +271,7 @@ def run_ours(args, cfg):
     if args.analysis != "none" and rank == 0:
         bt, _ = ctx.bench(B.BENCH_BOOP, dr=2.5, warmup=3, iters=10, flush_bytes=L2_FLUSH_BYTES)
         analysis["psi6_ms"] = float(np.mean(bt))
-        analysis["psi6_particles_per_s"] = n / (np.mean(bt) * 1e-3)
+        analysis["psi6_particles_per_s"] = float(n / (np.mean(bt) * 1e-3))
         analysis["psi6_hbm_frac"] = 56.0 * n / (np.mean(bt) * 1e-3) / 1e9 / peaks()[0]
         max_r_cut = 12.0
         if args.analysis == "full":
@@ -313,7 +313,7 @@ def run_ours(args, cfg):
             line["config"]["parallelism"] = f"{world} independent replicas (slab path: see DESIGN.md)"
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        print(json.dumps(line, default=float))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

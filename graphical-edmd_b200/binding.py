@@ -20,6 +20,8 @@ MODE_NORMAL, MODE_GROW = 0, 1
 EV_CELLCROSS, EV_COLLISION = 0, 1
 EINVAL, ESTATE, EOVERLAP, ECELL, ENOMEM = 1, 2, 3, 4, 5
 BENCH_SWEEP, BENCH_FREEFLY, BENCH_BOOP, BENCH_PCF = 0, 1, 2, 3
+OPT_FORCE_GENERIC = 1
+STAT_EXACT_RESCANS = 1
 
 # every symbol include/edmd_cuda.h declares
 SYMBOLS = [
@@ -28,7 +30,7 @@ SYMBOLS = [
     "edmd_cuda_upload_aos", "edmd_cuda_predict_all", "edmd_cuda_predict_device",
     "edmd_cuda_fetch_predictions", "edmd_cuda_set_growth", "edmd_cuda_free_fly",
     "edmd_cuda_download_state", "edmd_cuda_pcf", "edmd_cuda_boop_cutoff",
-    "edmd_cuda_bench",
+    "edmd_cuda_bench", "edmd_cuda_set_option", "edmd_cuda_get_stat",
 ]
 
 
@@ -81,6 +83,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_boop_cutoff.argtypes = [vp, C.c_double, vp, vp, vp, vp, vp, vp]
     lib.edmd_cuda_bench.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double,
                                     C.c_int, C.c_int, C.c_size_t, vp, vp]
+    lib.edmd_cuda_set_option.argtypes = [vp, C.c_int, C.c_int]
+    lib.edmd_cuda_get_stat.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:
@@ -147,6 +151,14 @@ class EdmdCuda:
     @property
     def launches(self) -> int:
         return int(self.lib.edmd_cuda_launch_count(self._h))
+
+    def set_option(self, option, value):
+        self._check(self.lib.edmd_cuda_set_option(self._h, option, int(value)))
+
+    def stat(self, which=STAT_EXACT_RESCANS) -> int:
+        v = C.c_uint64(0)
+        self._check(self.lib.edmd_cuda_get_stat(self._h, which, C.byref(v)))
+        return int(v.value)
 
     def upload(self, x, y, vx, vy, rad, cell_xy=None, t=0.0):
         n = self.n

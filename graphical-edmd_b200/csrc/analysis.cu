@@ -8,6 +8,9 @@
 // reference's order so that neighbour counts and histogram counts are
 // integers identical to the reference's.
 #include "edmd_internal.cuh"
+#include "tile.cuh"
+
+void edmd_tile_dims(const edmd_ctx *c, int *tx, int *ty);
 
 namespace {
 
@@ -26,87 +29,147 @@ __device__ __forceinline__ int wrap_cell(int a, int n)
 }
 
 // ------------------------------------------------------------------ K4 ----
-// One thread per particle in cell order; same 3x3 traversal as the sweep (and
-// the same truncation the reference has: cells are ~2.0 wide, r_c = 2.5, so
-// neighbours two cells away are never seen -- reproduced on purpose).
+// Same tile staging and 3x3 traversal as the sweep (and the same truncation
+// the reference has: cells are ~2.0 wide, r_c = 2.5, so neighbours two cells
+// away are never seen -- reproduced on purpose).
 // e^{ik theta} = ((dx + i dy)/r)^k by complex powers instead of atan2 + cexp;
 // agrees with libm to a few ulp (gate: 1e-10).
-constexpr int kBoopThreads = 128;
+struct BoopArgs {
+    int n;
+    edmd_dev_box b;
+    double rc2;
+    const double4 *sxv;
+    const double *srad;
+    const int32_t *sid;
+    const int32_t *scid;
+    const int32_t *start;
+    double *q5, *q6, *q7, *q6arg;
+    int32_t *nbr;
+    int tx, ty, tiles_x;
+};
 
-__global__ void __launch_bounds__(kBoopThreads)
-k_boop(int n, edmd_dev_box b, double rc2, const double4 *__restrict__ sxv,
-       const int32_t *__restrict__ sid, const int32_t *__restrict__ scid,
-       const int32_t *__restrict__ start, double *__restrict__ q5,
-       double *__restrict__ q6, double *__restrict__ q7,
-       double *__restrict__ q6arg, int32_t *__restrict__ nbr)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const double4 p1 = sxv[s];
-    const int id = sid[s];
-    const int c = scid[s];
-    const int Y = c / b.nx;
-    const int X = c - Y * b.nx;
+struct BoopAcc {
     double s5r = 0, s5i = 0, s6r = 0, s6i = 0, s7r = 0, s7i = 0;
     int nb = 0;
-    const bool interior = (X >= 1) && (X + 1 < b.nx);
+};
+
+template <bool WRAP>
+__device__ __forceinline__ void boop_pair(const edmd_dev_box &b, double rc2, const double4 &p1,
+                                          double x2, double y2, BoopAcc &acc)
+{
+    double dx = __dsub_rn(x2, p1.x);
+    double dy = __dsub_rn(y2, p1.y);
+    if (WRAP) {
+        dx = min_image(dx, b.half_lx, b.lx);
+        dy = min_image(dy, b.half_ly, b.ly);
+    }
+    const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    if (r2 < rc2) {
+        acc.nb++;
+        double zr = 1.0, zi = 0.0;  // atan2(0,0) = 0 in the reference
+        if (r2 > 0) {
+            const double inv = rsqrt(r2);
+            zr = dx * inv;
+            zi = dy * inv;
+        }
+        const double z2r = zr * zr - zi * zi, z2i = 2.0 * zr * zi;
+        const double z4r = z2r * z2r - z2i * z2i, z4i = 2.0 * z2r * z2i;
+        const double z5r = z4r * zr - z4i * zi, z5i = z4r * zi + z4i * zr;
+        const double z6r = z4r * z2r - z4i * z2i, z6i = z4r * z2i + z4i * z2r;
+        const double z7r = z6r * zr - z6i * zi, z7i = z6r * zi + z6i * zr;
+        acc.s5r += z5r; acc.s5i += z5i;
+        acc.s6r += z6r; acc.s6i += z6i;
+        acc.s7r += z7r; acc.s7i += z7i;
+    }
+}
+
+__device__ __forceinline__ void boop_emit(const BoopArgs &a, int id, const BoopAcc &acc)
+{
+    a.nbr[id] = acc.nb;
+    if (acc.nb > 0) {
+        const double dn = (double)acc.nb;
+        a.q5[id] = hypot(acc.s5r, acc.s5i) / dn;
+        a.q6[id] = hypot(acc.s6r, acc.s6i) / dn;
+        a.q7[id] = hypot(acc.s7r, acc.s7i) / dn;
+        a.q6arg[id] = atan2(acc.s6i, acc.s6r);
+    } else {
+        a.q5[id] = 0.0;
+        a.q6[id] = 0.0;
+        a.q7[id] = 0.0;
+        a.q6arg[id] = 0.0;
+    }
+}
+
+// one particle straight from the cell-ordered global arrays (overflow path)
+__device__ void boop_one_global(const BoopArgs &a, int s)
+{
+    const edmd_dev_box &b = a.b;
+    const double4 p1 = a.sxv[s];
+    const int c = a.scid[s];
+    const int Y = c / b.nx;
+    const int X = c - Y * b.nx;
+    BoopAcc acc;
 #pragma unroll 1
     for (int j = -1; j <= 1; j++) {
         const int rowbase = wrap_cell(Y + j, b.ny) * b.nx;
-        const int nseg = interior ? 1 : 3;
 #pragma unroll 1
-        for (int k = 0; k < nseg; k++) {
-            int lo, hi;
-            if (interior) {
-                lo = start[rowbase + X - 1];
-                hi = start[rowbase + X + 2];
-            } else {
-                int cc = rowbase + wrap_cell(X + k - 1, b.nx);
-                lo = start[cc];
-                hi = start[cc + 1];
-            }
+        for (int k = -1; k <= 1; k++) {
+            const int cc = rowbase + wrap_cell(X + k, b.nx);
+            const int lo = a.start[cc], hi = a.start[cc + 1];
 #pragma unroll 1
             for (int p = lo; p < hi; p++) {
                 if (p == s) continue;  // `p2->num != p1->num`
-                const double4 p2 = sxv[p];
-                double dx = min_image(__dsub_rn(p2.x, p1.x), b.half_lx, b.lx);
-                double dy = min_image(__dsub_rn(p2.y, p1.y), b.half_ly, b.ly);
-                double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                if (r2 < rc2) {
-                    nb++;
-                    double zr, zi;
-                    if (r2 > 0) {
-                        double inv = rsqrt(r2);
-                        zr = dx * inv;
-                        zi = dy * inv;
-                    } else {  // atan2(0,0) = 0 in the reference
-                        zr = 1.0;
-                        zi = 0.0;
-                    }
-                    double z2r = zr * zr - zi * zi, z2i = 2.0 * zr * zi;
-                    double z4r = z2r * z2r - z2i * z2i, z4i = 2.0 * z2r * z2i;
-                    double z5r = z4r * zr - z4i * zi, z5i = z4r * zi + z4i * zr;
-                    double z6r = z4r * z2r - z4i * z2i, z6i = z4r * z2i + z4i * z2r;
-                    double z7r = z6r * zr - z6i * zi, z7i = z6r * zi + z6i * zr;
-                    s5r += z5r; s5i += z5i;
-                    s6r += z6r; s6i += z6i;
-                    s7r += z7r; s7i += z7i;
-                }
+                const double4 p2 = a.sxv[p];
+                boop_pair<true>(b, a.rc2, p1, p2.x, p2.y, acc);
             }
         }
     }
-    nbr[id] = nb;
-    if (nb > 0) {
-        double dn = (double)nb;
-        q5[id] = hypot(s5r, s5i) / dn;
-        q6[id] = hypot(s6r, s6i) / dn;
-        q7[id] = hypot(s7r, s7i) / dn;
-        q6arg[id] = atan2(s6i, s6r);
-    } else {
-        q5[id] = 0.0;
-        q6[id] = 0.0;
-        q7[id] = 0.0;
-        q6arg[id] = 0.0;
+    boop_emit(a, a.sid[s], acc);
+}
+
+template <bool WRAP>
+__device__ __forceinline__ void boop_one_tile(const BoopArgs &a, const TileShared &s,
+                                              const TileInfo &ti, int r, int q)
+{
+    const edmd_dev_box &b = a.b;
+    const double4 p1 = s.xv[q];
+    const int Y = tile_wrap(ti.y0 - 1 + r, b.ny);
+    const int xl = (s.cell[q] - Y * b.nx) - ti.x0 + 1;
+    BoopAcc acc;
+#pragma unroll 1
+    for (int rr = r - 1; rr <= r + 1; rr++) {
+        const int lo = s.coff[rr][xl - 1];
+        const int hi = s.coff[rr][xl + 2];
+#pragma unroll 1
+        for (int p = lo; p < hi; p++) {
+            if (p == q) continue;
+            const double4 p2 = s.xv[p];
+            boop_pair<WRAP>(b, a.rc2, p1, p2.x, p2.y, acc);
+        }
+    }
+    boop_emit(a, s.id[q], acc);
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+k_boop_tile(const __grid_constant__ BoopArgs a)
+{
+    __shared__ TileShared s;
+    const TileInfo ti = tile_stage(s, a.b, a.tx, a.ty, a.tiles_x, a.sxv, a.srad, a.sid, a.scid, a.start);
+    const int own = s.own;
+    if (s.overflow) {
+        for (int k = threadIdx.x; k < own; k += kTileThreads) {
+            int r = 1;
+            while (k >= s.own_cum[r]) r++;
+            boop_one_global(a, s.seg_lo[r][1] + (k - s.own_cum[r - 1]));
+        }
+        return;
+    }
+    const bool fast = s.fast != 0;
+    for (int k = threadIdx.x; k < own; k += kTileThreads) {
+        int r, q;
+        tile_own(s, ti, k, r, q);
+        if (fast) boop_one_tile<false>(a, s, ti, r, q);
+        else boop_one_tile<true>(a, s, ti, r, q);
     }
 }
 
@@ -222,12 +285,25 @@ int edmd_launch_boop(edmd_ctx *c, double r_c)
 {
     int n = c->n;
     if (n == 0) return 0;
-    int blocks = (n + kBoopThreads - 1) / kBoopThreads;
-    double rc2 = r_c * r_c;  // `r_c*r_c`, a single rounded product
     size_t N = (size_t)n;
-    k_boop<<<blocks, kBoopThreads, 0, c->stream>>>(
-        n, c->dbox, rc2, c->sxv, c->sid, c->scid, c->cell_start, c->boop,
-        c->boop + N, c->boop + 2 * N, c->boop + 3 * N, c->boop_nb);
+    BoopArgs a;
+    a.n = n;
+    a.b = c->dbox;
+    a.rc2 = r_c * r_c;  // `r_c*r_c`, a single rounded product
+    a.sxv = c->sxv;
+    a.srad = c->srad;
+    a.sid = c->sid;
+    a.scid = c->scid;
+    a.start = c->cell_start;
+    a.q5 = c->boop;
+    a.q6 = c->boop + N;
+    a.q7 = c->boop + 2 * N;
+    a.q6arg = c->boop + 3 * N;
+    a.nbr = c->boop_nb;
+    edmd_tile_dims(c, &a.tx, &a.ty);
+    a.tiles_x = (c->dbox.nx + a.tx - 1) / a.tx;
+    int tiles_y = (c->dbox.ny + a.ty - 1) / a.ty;
+    k_boop_tile<<<a.tiles_x * tiles_y, kTileThreads, 0, c->stream>>>(a);
     return 1;
 }
 

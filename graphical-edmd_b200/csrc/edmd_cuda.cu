@@ -253,6 +253,28 @@ int edmd_cuda_get_box(const edmd_ctx *c, edmd_box *out)
 
 uint64_t edmd_cuda_launch_count(const edmd_ctx *c) { return c ? c->launches : 0; }
 
+int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
+{
+    if (!c) return EDMD_EINVAL;
+    if (option == EDMD_OPT_FORCE_GENERIC) {
+        c->force_generic = value != 0;
+        return 0;
+    }
+    return fail(c, EDMD_EINVAL, "unknown option");
+}
+
+int edmd_cuda_get_stat(edmd_ctx *c, int stat, uint64_t *value)
+{
+    if (!c || !value) return EDMD_EINVAL;
+    if (stat != EDMD_STAT_EXACT_RESCANS) return fail(c, EDMD_EINVAL, "unknown stat");
+    CU(cudaSetDevice(c->device));
+    uint32_t v = 0;
+    CU(cudaMemcpyAsync(&v, c->flags + 1, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *value = v;
+    return 0;
+}
+
 int edmd_cuda_upload(edmd_ctx *c, const double *x, const double *y, const double *vx,
                      const double *vy, const double *rad, const int32_t *cell_xy,
                      double t)

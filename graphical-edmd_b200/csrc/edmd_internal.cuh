@@ -44,6 +44,7 @@ struct edmd_ctx {
     cudaEvent_t ev[4];
     char err[512];
     uint64_t launches;
+    bool force_generic;  // EDMD_OPT_FORCE_GENERIC: global-memory exact kernel only
 
     bool have_state;     // upload done
     bool have_pred;      // device predictions valid

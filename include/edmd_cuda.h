@@ -76,6 +76,16 @@ int edmd_cuda_get_box(const edmd_ctx *ctx, edmd_box *out);
 /* number of kernels this context has launched so far (bench accounting) */
 uint64_t edmd_cuda_launch_count(const edmd_ctx *ctx);
 
+/* Options.  EDMD_OPT_FORCE_GENERIC = 1 runs the sweep with the plain
+ * global-memory kernel (the reference's loops as written) instead of the tiled
+ * two-phase kernel; results are identical, it exists for cross-checking. */
+#define EDMD_OPT_FORCE_GENERIC 1
+int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
+/* Counters: EDMD_STAT_EXACT_RESCANS = particles the tiled sweep had to resolve
+ * with the exact re-scan (near-ties, ill-conditioned pairs) since create. */
+#define EDMD_STAT_EXACT_RESCANS 1
+int edmd_cuda_get_stat(edmd_ctx *ctx, int stat, uint64_t *value);
+
 /* ---- state upload ---------------------------------------------------- */
 
 /* Synchronous snapshot: every particle already advanced to time t (the state

@@ -301,3 +301,42 @@ def test_pcf_counts_every_pair_once(pkg):
     assert int(p["counts"].sum()) == n * (n - 1) // 2
     # hard disks: nothing below contact
     assert p["counts"][: int(1.99 / 0.1)].sum() == 0
+
+
+# ------------------------------------------- tiled kernel vs generic kernel ----
+@pytest.mark.parametrize("n,phi,seed,sf", [(300000, 0.70, 21, 0.3), (300000, 0.85, 22, 0.0),
+                                           (50000, 0.30, 23, 0.0)])
+def test_tiled_and_generic_kernels_agree(pkg, n, phi, seed, sf):
+    """The two-phase tiled kernel and the plain exact kernel are two
+    implementations of the same function; the exact re-scan must be rare."""
+    c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=4.0)
+        a = ctx.predict_all()
+        rescans = ctx.stat(pkg.binding.STAT_EXACT_RESCANS)
+        ctx.set_option(pkg.binding.OPT_FORCE_GENERIC, 1)
+        b = ctx.predict_all()
+    for k in ("t_cross", "dir", "t_coll", "partner", "ctype"):
+        assert np.array_equal(a[k], b[k]), k
+    assert rescans < 0.02 * c["n"], rescans
+
+
+def test_dense_small_disks_overflow_the_tile_buffer(pkg, oracle):
+    """Many tiny disks per cell: more particles than a tile's staging buffer
+    holds, so CTAs take the global-memory path; results unchanged."""
+    rng = np.random.default_rng(31)
+    lx, ly = 64.0, 48.0
+    n = 40000          # ~52 per cell
+    x = rng.random(n) * lx
+    y = rng.random(n) * ly
+    vx = rng.standard_normal(n)
+    vy = rng.standard_normal(n)
+    rad = np.full(n, 1e-4)
+    c = dict(n=n, lx=lx, ly=ly, x=x, y=y, vx=vx, vy=vy, rad=rad)
+    got = gpu_sweep(pkg, c, t=0.25)
+    want = oracle_sweep(oracle, c, t=0.25)
+    assert_events_equal(got, want)
+    with pkg.EdmdCuda(n, lx, ly) as ctx:
+        ctx.upload(x, y, vx, vy, rad, t=0.25)
+        b = ctx.boop_cutoff(0.5)
+    assert_boop_close(b, oracle.boop_cutoff(n, lx, ly, x, y, 0.5))

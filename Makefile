@@ -20,7 +20,7 @@ all: cuda host oracle
 
 cuda: $(LIB)
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/edmd_internal.cuh $(CSRC)/tile.cuh include/edmd_cuda.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/edmd_internal.cuh $(CSRC)/rowstage.cuh include/edmd_cuda.h
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 $(LIB): $(CU_OBJS)

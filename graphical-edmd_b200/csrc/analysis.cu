@@ -8,9 +8,7 @@
 // reference's order so that neighbour counts and histogram counts are
 // integers identical to the reference's.
 #include "edmd_internal.cuh"
-#include "tile.cuh"
-
-void edmd_tile_dims(const edmd_ctx *c, int *tx, int *ty);
+#include "rowstage.cuh"
 
 namespace {
 
@@ -21,44 +19,38 @@ __device__ __forceinline__ double min_image(double d, double half, double len)
     return d;
 }
 
-__device__ __forceinline__ int wrap_cell(int a, int n)
-{
-    if (a < 0) return a + n;
-    if (a >= n) return a - n;
-    return a;
-}
 
 // ------------------------------------------------------------------ K4 ----
-// Same tile staging and 3x3 traversal as the sweep (and the same truncation
-// the reference has: cells are ~2.0 wide, r_c = 2.5, so neighbours two cells
-// away are never seen -- reproduced on purpose).
+// Same per-warp row staging and 3x3 traversal as the sweep (and the same
+// truncation the reference has: cells are ~2.0 wide, r_c = 2.5, so neighbours
+// two cells away are never seen -- reproduced on purpose).
 // e^{ik theta} = ((dx + i dy)/r)^k by complex powers instead of atan2 + cexp;
-// agrees with libm to a few ulp (gate: 1e-10).
+// agrees with libm to a few ulp (gate: 1e-10).  The six sums are accumulated
+// in 2^-48 fixed point: exact integer addition makes them independent of the
+// order in which a cell's particles are stored (error <= 8 * 2^-49 per sum).
 struct BoopArgs {
-    int n;
     edmd_dev_box b;
+    CellIndex g;
+    int max_chunks;
     double rc2;
-    const double4 *sxv;
-    const double *srad;
-    const int32_t *sid;
-    const int32_t *scid;
-    const int32_t *start;
     double *q5, *q6, *q7, *q6arg;
     int32_t *nbr;
-    int tx, ty, tiles_x;
 };
 
 struct BoopAcc {
-    double s5r = 0, s5i = 0, s6r = 0, s6i = 0, s7r = 0, s7i = 0;
+    long long s5r = 0, s5i = 0, s6r = 0, s6i = 0, s7r = 0, s7i = 0;
     int nb = 0;
 };
 
+constexpr double kFix = 281474976710656.0;        // 2^48
+constexpr double kUnfix = 1.0 / 281474976710656.0;
+
 template <bool WRAP>
-__device__ __forceinline__ void boop_pair(const edmd_dev_box &b, double rc2, const double4 &p1,
-                                          double x2, double y2, BoopAcc &acc)
+__device__ __forceinline__ void boop_pair(const edmd_dev_box &b, double rc2, const SRec &p1,
+                                          const SRec &p2, BoopAcc &acc)
 {
-    double dx = __dsub_rn(x2, p1.x);
-    double dy = __dsub_rn(y2, p1.y);
+    double dx = __dsub_rn(p2.x, p1.x);
+    double dy = __dsub_rn(p2.y, p1.y);
     if (WRAP) {
         dx = min_image(dx, b.half_lx, b.lx);
         dy = min_image(dy, b.half_ly, b.ly);
@@ -77,9 +69,9 @@ __device__ __forceinline__ void boop_pair(const edmd_dev_box &b, double rc2, con
         const double z5r = z4r * zr - z4i * zi, z5i = z4r * zi + z4i * zr;
         const double z6r = z4r * z2r - z4i * z2i, z6i = z4r * z2i + z4i * z2r;
         const double z7r = z6r * zr - z6i * zi, z7i = z6r * zi + z6i * zr;
-        acc.s5r += z5r; acc.s5i += z5i;
-        acc.s6r += z6r; acc.s6i += z6i;
-        acc.s7r += z7r; acc.s7i += z7i;
+        acc.s5r += __double2ll_rn(z5r * kFix); acc.s5i += __double2ll_rn(z5i * kFix);
+        acc.s6r += __double2ll_rn(z6r * kFix); acc.s6i += __double2ll_rn(z6i * kFix);
+        acc.s7r += __double2ll_rn(z7r * kFix); acc.s7i += __double2ll_rn(z7i * kFix);
     }
 }
 
@@ -88,10 +80,11 @@ __device__ __forceinline__ void boop_emit(const BoopArgs &a, int id, const BoopA
     a.nbr[id] = acc.nb;
     if (acc.nb > 0) {
         const double dn = (double)acc.nb;
-        a.q5[id] = hypot(acc.s5r, acc.s5i) / dn;
-        a.q6[id] = hypot(acc.s6r, acc.s6i) / dn;
-        a.q7[id] = hypot(acc.s7r, acc.s7i) / dn;
-        a.q6arg[id] = atan2(acc.s6i, acc.s6r);
+        const double s6r = (double)acc.s6r * kUnfix, s6i = (double)acc.s6i * kUnfix;
+        a.q5[id] = hypot((double)acc.s5r * kUnfix, (double)acc.s5i * kUnfix) / dn;
+        a.q6[id] = hypot(s6r, s6i) / dn;
+        a.q7[id] = hypot((double)acc.s7r * kUnfix, (double)acc.s7i * kUnfix) / dn;
+        a.q6arg[id] = atan2(s6i, s6r);
     } else {
         a.q5[id] = 0.0;
         a.q6[id] = 0.0;
@@ -100,77 +93,49 @@ __device__ __forceinline__ void boop_emit(const BoopArgs &a, int id, const BoopA
     }
 }
 
-// one particle straight from the cell-ordered global arrays (overflow path)
-__device__ void boop_one_global(const BoopArgs &a, int s)
-{
-    const edmd_dev_box &b = a.b;
-    const double4 p1 = a.sxv[s];
-    const int c = a.scid[s];
-    const int Y = c / b.nx;
-    const int X = c - Y * b.nx;
-    BoopAcc acc;
-#pragma unroll 1
-    for (int j = -1; j <= 1; j++) {
-        const int rowbase = wrap_cell(Y + j, b.ny) * b.nx;
-#pragma unroll 1
-        for (int k = -1; k <= 1; k++) {
-            const int cc = rowbase + wrap_cell(X + k, b.nx);
-            const int lo = a.start[cc], hi = a.start[cc + 1];
-#pragma unroll 1
-            for (int p = lo; p < hi; p++) {
-                if (p == s) continue;  // `p2->num != p1->num`
-                const double4 p2 = a.sxv[p];
-                boop_pair<true>(b, a.rc2, p1, p2.x, p2.y, acc);
-            }
-        }
-    }
-    boop_emit(a, a.sid[s], acc);
-}
-
 template <bool WRAP>
-__device__ __forceinline__ void boop_one_tile(const BoopArgs &a, const TileShared &s,
-                                              const TileInfo &ti, int r, int q)
+__device__ __forceinline__ void boop_range(const edmd_dev_box &b, double rc2, const SRec &p1,
+                                           const SRec *recs, int lo, int hi, BoopAcc &acc)
 {
-    const edmd_dev_box &b = a.b;
-    const double4 p1 = s.xv[q];
-    const int Y = tile_wrap(ti.y0 - 1 + r, b.ny);
-    const int xl = (s.cell[q] - Y * b.nx) - ti.x0 + 1;
-    BoopAcc acc;
 #pragma unroll 1
-    for (int rr = r - 1; rr <= r + 1; rr++) {
-        const int lo = s.coff[rr][xl - 1];
-        const int hi = s.coff[rr][xl + 2];
-#pragma unroll 1
-        for (int p = lo; p < hi; p++) {
-            if (p == q) continue;
-            const double4 p2 = s.xv[p];
-            boop_pair<WRAP>(b, a.rc2, p1, p2.x, p2.y, acc);
-        }
+    for (int p = lo; p < hi; p++) {
+        const SRec p2 = recs[p];
+        if (p2.id == p1.id) continue;  // `p2->num != p1->num`
+        boop_pair<WRAP>(b, rc2, p1, p2, acc);
     }
-    boop_emit(a, s.id[q], acc);
 }
 
-__global__ void __launch_bounds__(kTileThreads)
-k_boop_tile(const __grid_constant__ BoopArgs a)
+__global__ void __launch_bounds__(kStageThreads)
+k_boop_rows(const __grid_constant__ BoopArgs a)
 {
-    __shared__ TileShared s;
-    const TileInfo ti = tile_stage(s, a.b, a.tx, a.ty, a.tiles_x, a.sxv, a.srad, a.sid, a.scid, a.start);
-    const int own = s.own;
-    if (s.overflow) {
-        for (int k = threadIdx.x; k < own; k += kTileThreads) {
-            int r = 1;
-            while (k >= s.own_cum[r]) r++;
-            boop_one_global(a, s.seg_lo[r][1] + (k - s.own_cum[r - 1]));
-        }
+    __shared__ WarpStage stage[kStageWarps];
+    const int warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x * kStageWarps + warp;
+    if (chunk >= a.max_chunks) return;
+    RowLane rl;
+    const int st = row_stage(stage[warp], a.g, chunk, rl);
+    if (st == 0) return;
+    BoopAcc acc;
+    if (st == 2) {  // segments do not fit: straight from global memory
+        if (!rl.active) return;
+        const SRec p1 = a.g.srec[rl.s];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            boop_range<true>(a.b, a.rc2, p1, a.g.srec, rl.lo[j], rl.hi[j], acc);
+        boop_emit(a, p1.id, acc);
         return;
     }
-    const bool fast = s.fast != 0;
-    for (int k = threadIdx.x; k < own; k += kTileThreads) {
-        int r, q;
-        tile_own(s, ti, k, r, q);
-        if (fast) boop_one_tile<false>(a, s, ti, r, q);
-        else boop_one_tile<true>(a, s, ti, r, q);
+    const bool interior = !rl.active || (rl.pcx >= 2 && rl.pcx <= a.g.nx - 1);
+    const bool fast = (a.g.nx >= 12) && (a.g.ny >= 12) && (rl.Y >= 1) && (rl.Y <= a.g.ny - 2) &&
+                      (a.g.flags[kFlagInsane] == 0) && __all_sync(0xffffffffu, interior);
+    if (!rl.active) return;
+    const SRec p1 = stage[warp].rec[1][rl.self];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        if (fast) boop_range<false>(a.b, a.rc2, p1, stage[warp].rec[j], rl.lo[j], rl.hi[j], acc);
+        else boop_range<true>(a.b, a.rc2, p1, stage[warp].rec[j], rl.lo[j], rl.hi[j], acc);
     }
+    boop_emit(a, p1.id, acc);
 }
 
 // deterministic two-stage sum: fixed block partials, then one block in order
@@ -287,23 +252,17 @@ int edmd_launch_boop(edmd_ctx *c, double r_c)
     if (n == 0) return 0;
     size_t N = (size_t)n;
     BoopArgs a;
-    a.n = n;
     a.b = c->dbox;
+    a.g = edmd_cell_index(c);
+    a.max_chunks = edmd_chunks_bound(c);
     a.rc2 = r_c * r_c;  // `r_c*r_c`, a single rounded product
-    a.sxv = c->sxv;
-    a.srad = c->srad;
-    a.sid = c->sid;
-    a.scid = c->scid;
-    a.start = c->cell_start;
     a.q5 = c->boop;
     a.q6 = c->boop + N;
     a.q7 = c->boop + 2 * N;
     a.q6arg = c->boop + 3 * N;
     a.nbr = c->boop_nb;
-    edmd_tile_dims(c, &a.tx, &a.ty);
-    a.tiles_x = (c->dbox.nx + a.tx - 1) / a.tx;
-    int tiles_y = (c->dbox.ny + a.ty - 1) / a.ty;
-    k_boop_tile<<<a.tiles_x * tiles_y, kTileThreads, 0, c->stream>>>(a);
+    const int blocks = (a.max_chunks + kStageWarps - 1) / kStageWarps;
+    k_boop_rows<<<blocks, kStageThreads, 0, c->stream>>>(a);
     return 1;
 }
 

@@ -1,17 +1,22 @@
 // cell_index.cu -- K0: the reference's intrusive doubly linked cell list
 // (cellListInit / addToCell, src/EDMD.c:1906-1920, 2053-2078) rebuilt on the
-// device as a counting-sort cell index.
+// device as a counting sort over the padded cell grid described in
+// edmd_internal.cuh.
 //
-//   pack     : SoA upload staging -> resident records, cell id per particle
-//              (coordToCell, src/EDMD.c:2098-2107, or the host's cell[2])
-//   count    : histogram of cell ids
-//   scan     : single-pass decoupled look-back exclusive scan over the cells
-//   bucket   : particle ids into their cell's slot range (atomic cursor; the
-//              histogram is counted back down to zero = self-cleaning)
-//   gather   : rank-sort each cell's ids DESCENDING (the reference's list
-//              order) and gather the state into cell order
+//   pack     (upload)  SoA staging -> resident records; padded cell id per
+//                      particle (coordToCell, src/EDMD.c:2098-2107, or the
+//                      host's cell[2]); counts ghost entries; flags particles
+//                      that are not near the cell they are filed under
+//   count    histogram of cell ids; the atomic's return value is the
+//            particle's arrival rank inside its cell
+//   rowscan  one CTA per cell row: exclusive scan of the padded row (ghost
+//            cells take the count of the cell they mirror), row total, and the
+//            histogram is zeroed again (no memset between sweeps)
+//   rowbase  one CTA: scan of the row totals rounded up to 32; chunk -> row map
+//   scatter  every particle writes its 48-byte record (and its ghost copy when
+//            it sits in an edge cell) to row_base + off + rank
 //
-// Everything here is integer / data movement: HBM- and L2-bound.
+// Integer / data movement only: HBM- and L2-bound.
 #include "edmd_internal.cuh"
 
 namespace {
@@ -20,179 +25,186 @@ constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------ pack --
 __global__ void __launch_bounds__(kThreads)
-k_pack(int n, edmd_dev_box b, const double *__restrict__ soa,
+k_pack(int n, edmd_dev_box b, int ps, const double *__restrict__ soa,
        const int32_t *__restrict__ cell_xy, double4 *__restrict__ xv,
        double *__restrict__ rad, int32_t *__restrict__ cid,
        int32_t *__restrict__ flags)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    size_t N = (size_t)n;
-    double x = soa[i], y = soa[N + i];
-    xv[i] = make_double4(x, y, soa[2 * N + i], soa[3 * N + i]);
-    rad[i] = soa[4 * N + i];
-    int X, Y;
-    if (cell_xy) {
-        int2 c = reinterpret_cast<const int2 *>(cell_xy)[i];
-        X = c.x;
-        Y = c.y;
-    } else {
-        // coordToCell: multiply by the reciprocal, truncate toward zero
-        X = (int)__dmul_rn(x, b.fx);
-        Y = (int)__dmul_rn(y, b.fy);
+    int ghosts = 0, insane = 0;
+    if (i < n) {
+        size_t N = (size_t)n;
+        double x = soa[i], y = soa[N + i];
+        xv[i] = make_double4(x, y, soa[2 * N + i], soa[3 * N + i]);
+        rad[i] = soa[4 * N + i];
+        int X, Y;
+        if (cell_xy) {
+            int2 c = reinterpret_cast<const int2 *>(cell_xy)[i];
+            X = c.x;
+            Y = c.y;
+        } else {
+            // coordToCell: multiply by the reciprocal, truncate toward zero
+            X = (int)__dmul_rn(x, b.fx);
+            Y = (int)__dmul_rn(y, b.fy);
+        }
+        if (X < 0 || X >= b.nx || Y < 0 || Y >= b.ny) {
+            atomicOr(&flags[kFlagBadCell], 1);
+            X = min(max(X, 0), b.nx - 1);
+            Y = min(max(Y, 0), b.ny - 1);
+        }
+        cid[i] = Y * ps + X + 1;
+        ghosts = (X == 0) + (X == b.nx - 1);
+        // within one cell width of the filed cell?  (lets the sweep skip the
+        // minimum-image test away from the periodic edges)
+        insane = !(fabs(x - ((double)X + 0.5) * b.csx) <= 1.5 * b.csx) ||
+                 !(fabs(y - ((double)Y + 0.5) * b.csy) <= 1.5 * b.csy);
     }
-    if (X < 0 || X >= b.nx || Y < 0 || Y >= b.ny) {
-        atomicOr(flags, 1);
-        X = min(max(X, 0), b.nx - 1);
-        Y = min(max(Y, 0), b.ny - 1);
+    ghosts = __reduce_add_sync(0xffffffffu, ghosts);
+    insane = __reduce_add_sync(0xffffffffu, insane);
+    if ((threadIdx.x & 31) == 0) {
+        if (ghosts) atomicAdd(&flags[kFlagGhosts], ghosts);
+        if (insane) atomicAdd(&flags[kFlagInsane], insane);
     }
-    cid[i] = Y * b.nx + X;
 }
 
 // ----------------------------------------------------------------- count --
 __global__ void __launch_bounds__(kThreads)
-k_count(int n, const int32_t *__restrict__ cid, int32_t *__restrict__ cnt)
+k_count(int n, const int32_t *__restrict__ cid, int32_t *__restrict__ cnt,
+        int32_t *__restrict__ rank)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(&cnt[cid[i]], 1);
+    if (i < n) rank[i] = atomicAdd(&cnt[cid[i]], 1);
 }
 
-// ------------------------------------------------------------------ scan --
-// Exclusive scan of cnt[0..nc) into start[0..nc]; start[nc] = total.
-// Single pass, decoupled look-back.  Tile status word: 2 flag bits | 30 value
-// bits (N < 2^30).  Tiles take tickets from an atomic counter so a tile never
-// waits on one that has not started.  `state_next` / `ticket_next` belong to
-// the NEXT sweep and are cleared here (ping-pong) so no memset is needed.
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 16;
-constexpr int kScanTile = kScanThreads * kScanItems;
-constexpr uint32_t kFlagAgg = 1u << 30;
-constexpr uint32_t kFlagInc = 2u << 30;
-constexpr uint32_t kValMask = (1u << 30) - 1;
-
-__global__ void __launch_bounds__(kScanThreads)
-k_scan(int nc, const int32_t *__restrict__ cnt, int32_t *__restrict__ start,
-       uint32_t *state, int32_t *ticket, uint32_t *state_next,
-       int32_t *ticket_next, int tiles)
-{
-    __shared__ int s_tile;
-    __shared__ int s_warp[kScanThreads / 32];
-    __shared__ int s_prefix;
-    const int tid = threadIdx.x;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1);
-    __syncthreads();
-    const int tile = s_tile;
-
-    // clear next sweep's bookkeeping (one tile does it)
-    if (tile == 0) {
-        for (int k = tid; k < tiles; k += kScanThreads) state_next[k] = 0;
-        if (tid == 0) *ticket_next = 0;
-    }
-
-    const int base = tile * kScanTile + tid * kScanItems;
-    int v[kScanItems];
-    int sum = 0;
-#pragma unroll
-    for (int q = 0; q < kScanItems / 4; q++) {
-        int idx = base + 4 * q;
-        int4 w;
-        if (idx + 3 < nc) {
-            w = *reinterpret_cast<const int4 *>(cnt + idx);
-        } else {
-            w.x = idx < nc ? cnt[idx] : 0;
-            w.y = idx + 1 < nc ? cnt[idx + 1] : 0;
-            w.z = idx + 2 < nc ? cnt[idx + 2] : 0;
-            w.w = 0;
-        }
-        v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
-        sum += w.x + w.y + w.z + w.w;
-    }
-    // block exclusive scan of the per-thread sums
-    int incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int o = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((tid & 31) >= d) incl += o;
-    }
-    if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
-    __syncthreads();
-    if (tid < 32) {
-        int w = tid < kScanThreads / 32 ? s_warp[tid] : 0;
-        int wi = w;
-#pragma unroll
-        for (int d = 1; d < kScanThreads / 32; d <<= 1) {
-            int o = __shfl_up_sync(0xffffffffu, wi, d);
-            if (tid >= d) wi += o;
-        }
-        if (tid < kScanThreads / 32) s_warp[tid] = wi - w;  // exclusive
-        int total = __shfl_sync(0xffffffffu, wi, kScanThreads / 32 - 1);
-        if (tid == 0) {
-            volatile uint32_t *vs = state;
-            int prefix = 0;
-            if (tile == 0) {
-                vs[0] = kFlagInc | (uint32_t)total;
-            } else {
-                vs[tile] = kFlagAgg | (uint32_t)total;
-                __threadfence();
-                int p = tile - 1;
-                while (true) {
-                    uint32_t s = vs[p];
-                    if ((s >> 30) == 0) continue;  // predecessor not published yet
-                    prefix += (int)(s & kValMask);
-                    if (s & kFlagInc) break;
-                    p--;
-                }
-                vs[tile] = kFlagInc | (uint32_t)(prefix + total);
-            }
-            s_prefix = prefix;
-            if (tile == tiles - 1) start[nc] = prefix + total;
-        }
-    }
-    __syncthreads();
-    int run = s_prefix + s_warp[tid >> 5] + (incl - sum);
-#pragma unroll
-    for (int q = 0; q < kScanItems; q++) {
-        int idx = base + q;
-        if (idx < nc) start[idx] = run;
-        run += v[q];
-    }
-}
-
-// ---------------------------------------------------------------- bucket --
+// --------------------------------------------------------------- rowscan --
 __global__ void __launch_bounds__(kThreads)
-k_bucket(int n, const int32_t *__restrict__ cid, int32_t *__restrict__ cnt,
-         const int32_t *__restrict__ start, int32_t *__restrict__ slot_id)
+k_rowscan(int nx, int ps, int32_t *__restrict__ cnt, int32_t *__restrict__ off,
+          int32_t *__restrict__ row_total)
+{
+    __shared__ int s_warp[kThreads / 32];
+    __shared__ int s_carry;
+    const int Y = blockIdx.x;
+    const int tid = threadIdx.x;
+    int32_t *row = cnt + (size_t)Y * ps;
+    int32_t *orow = off + (size_t)Y * ps;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ps; base += kThreads) {
+        const int pcx = base + tid;
+        int v = 0;
+        if (pcx < ps) {
+            if (pcx == 0) v = row[nx];            // left ghost mirrors cell nx-1
+            else if (pcx <= nx) v = row[pcx];
+            else if (pcx == nx + 1) v = row[1];   // right ghost mirrors cell 0
+        }
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((tid & 31) >= d) incl += o;
+        }
+        if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+        __syncthreads();
+        int wbase = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++)
+            if (w < (tid >> 5)) wbase += s_warp[w];
+        const int carry = s_carry;
+        if (pcx < ps) orow[pcx] = carry + wbase + incl - v;
+        __syncthreads();
+        if (tid == kThreads - 1) s_carry = carry + wbase + incl;
+        __syncthreads();
+    }
+    if (tid == 0) row_total[Y] = s_carry;
+    // histogram back to zero for the next sweep
+    for (int pcx = 1 + tid; pcx <= nx; pcx += kThreads) row[pcx] = 0;
+}
+
+// --------------------------------------------------------------- rowbase --
+constexpr int kBaseThreads = 1024;
+
+__global__ void __launch_bounds__(kBaseThreads)
+k_rowbase(int ny, const int32_t *__restrict__ row_total, int32_t *__restrict__ row_base,
+          int32_t *__restrict__ chunk_row, int max_chunks)
+{
+    __shared__ int s_warp[kBaseThreads / 32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ny; base += kBaseThreads) {
+        const int Y = base + tid;
+        const int v = Y < ny ? ((row_total[Y] + 31) & ~31) : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((tid & 31) >= d) incl += o;
+        }
+        if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < (tid >> 5); w++) wbase += s_warp[w];
+        const int carry = s_carry;
+        const int excl = carry + wbase + incl - v;
+        if (Y < ny) {
+            row_base[Y] = excl;
+            for (int ch = excl >> 5; ch < ((excl + v) >> 5); ch++)
+                if (ch < max_chunks) chunk_row[ch] = Y;
+        }
+        __syncthreads();
+        if (tid == kBaseThreads - 1) s_carry = carry + wbase + incl;
+        __syncthreads();
+    }
+    const int total = s_carry;
+    if (tid == 0) row_base[ny] = total;
+    for (int ch = (total >> 5) + tid; ch < max_chunks; ch += kBaseThreads) chunk_row[ch] = -1;
+}
+
+// --------------------------------------------------------------- scatter --
+template <bool GROW>
+__global__ void __launch_bounds__(kThreads)
+k_scatter(int n, int nx, int ps, const int32_t *__restrict__ cid,
+          const int32_t *__restrict__ rank, const int32_t *__restrict__ off,
+          const int32_t *__restrict__ row_base, const double4 *__restrict__ xv,
+          const double *__restrict__ rad, const double *__restrict__ vr,
+          SRec *__restrict__ srec, double *__restrict__ svr)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int c = cid[i];
-    int r = atomicSub(&cnt[c], 1) - 1;  // counts back down to zero
-    slot_id[start[c] + r] = i;
-}
-
-// ---------------------------------------------------------------- gather --
-template <bool GROW>
-__global__ void __launch_bounds__(kThreads)
-k_gather(int n, const int32_t *__restrict__ slot_id,
-         const int32_t *__restrict__ cid, const int32_t *__restrict__ start,
-         const double4 *__restrict__ xv, const double *__restrict__ rad,
-         const double *__restrict__ vr, double4 *__restrict__ sxv,
-         double *__restrict__ srad, double *__restrict__ svr,
-         int32_t *__restrict__ sid, int32_t *__restrict__ scid)
-{
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    int id = slot_id[s];
-    int c = cid[id];
-    int lo = start[c], hi = start[c + 1];
-    int rank = 0;  // ids in this cell larger than mine come first
-    for (int p = lo; p < hi; p++) rank += (slot_id[p] > id);
-    int d = lo + rank;
-    sxv[d] = xv[id];
-    srad[d] = rad[id];
-    if (GROW) svr[d] = vr[id];
-    sid[d] = id;
-    scid[d] = c;
+    const int pc = cid[i];
+    const int Y = pc / ps;
+    const int pcx = pc - Y * ps;
+    const int rk = rank[i];
+    const int rb = row_base[Y];
+    const double4 p = xv[i];
+    SRec r;
+    r.x = p.x; r.y = p.y; r.vx = p.z; r.vy = p.w;
+    r.rad = rad[i];
+    r.id = i;
+    r.pc = pc;
+    const double g = GROW ? vr[i] : 0.0;
+    const uint4 *src = reinterpret_cast<const uint4 *>(&r);
+    {
+        const int d = rb + off[pc] + rk;
+        uint4 *dst = reinterpret_cast<uint4 *>(srec + d);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        if (GROW) svr[d] = g;
+    }
+    if (pcx == 1) {  // cell 0 is mirrored by the right ghost
+        r.pc = Y * ps + nx + 1;
+        const int d = rb + off[r.pc] + rk;
+        uint4 *dst = reinterpret_cast<uint4 *>(srec + d);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        if (GROW) svr[d] = g;
+    }
+    if (pcx == nx) {  // cell nx-1 is mirrored by the left ghost
+        r.pc = Y * ps;
+        const int d = rb + off[r.pc] + rk;
+        uint4 *dst = reinterpret_cast<uint4 *>(srec + d);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        if (GROW) svr[d] = g;
+    }
 }
 
 }  // namespace
@@ -202,42 +214,36 @@ int edmd_launch_pack(edmd_ctx *c, bool have_cells)
     int n = c->n;
     if (n == 0) return 0;
     k_pack<<<(n + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(
-        n, c->dbox, c->in_soa, have_cells ? c->in_cell : nullptr, c->xv, c->rad,
+        n, c->dbox, c->ps, c->in_soa, have_cells ? c->in_cell : nullptr, c->xv, c->rad,
         c->cid, c->flags);
     return 1;
 }
 
 int edmd_launch_cell_index(edmd_ctx *c, int mode)
 {
-    int n = c->n;
-    int nc = c->dbox.nc;
-    int blocks = (n + kThreads - 1) / kThreads;
-    int par = c->scan_parity;
+    const int n = c->n;
+    const int blocks = (n + kThreads - 1) / kThreads;
     int launched = 0;
     if (n > 0) {
-        k_count<<<blocks, kThreads, 0, c->stream>>>(n, c->cid, c->cell_cnt);
+        k_count<<<blocks, kThreads, 0, c->stream>>>(n, c->cid, c->cell_cnt, c->rank);
         launched++;
     }
-    k_scan<<<c->scan_tiles, kScanThreads, 0, c->stream>>>(
-        nc, c->cell_cnt, c->cell_start, c->scan_state[par],
-        c->scan_ticket + par, c->scan_state[par ^ 1], c->scan_ticket + (par ^ 1),
-        c->scan_tiles);
-    launched++;
-    c->scan_parity = par ^ 1;
+    k_rowscan<<<c->dbox.ny, kThreads, 0, c->stream>>>(c->dbox.nx, c->ps, c->cell_cnt, c->off,
+                                                     c->row_total);
+    k_rowbase<<<1, kBaseThreads, 0, c->stream>>>(c->dbox.ny, c->row_total, c->row_base,
+                                                 c->chunk_row, c->max_chunks);
+    launched += 2;
     if (n > 0) {
-        k_bucket<<<blocks, kThreads, 0, c->stream>>>(n, c->cid, c->cell_cnt,
-                                                     c->cell_start, c->slot_id);
         if (mode == EDMD_MODE_GROW)
-            k_gather<true><<<blocks, kThreads, 0, c->stream>>>(
-                n, c->slot_id, c->cid, c->cell_start, c->xv, c->rad, c->vr,
-                c->sxv, c->srad, c->svr, c->sid, c->scid);
+            k_scatter<true><<<blocks, kThreads, 0, c->stream>>>(
+                n, c->dbox.nx, c->ps, c->cid, c->rank, c->off, c->row_base, c->xv, c->rad,
+                c->vr, c->srec, c->svr);
         else
-            k_gather<false><<<blocks, kThreads, 0, c->stream>>>(
-                n, c->slot_id, c->cid, c->cell_start, c->xv, c->rad, c->vr,
-                c->sxv, c->srad, c->svr, c->sid, c->scid);
-        launched += 2;
+            k_scatter<false><<<blocks, kThreads, 0, c->stream>>>(
+                n, c->dbox.nx, c->ps, c->cid, c->rank, c->off, c->row_base, c->xv, c->rad,
+                c->vr, c->srec, c->svr);
+        launched++;
     }
+    c->index_has_vr = (mode == EDMD_MODE_GROW);
     return launched;
 }
-
-int edmd_scan_tiles_for(int nc) { return (nc + kScanTile - 1) / kScanTile; }

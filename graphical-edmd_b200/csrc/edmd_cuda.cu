@@ -11,8 +11,6 @@
 
 #include "edmd_internal.cuh"
 
-int edmd_scan_tiles_for(int nc);
-
 namespace {
 
 constexpr size_t kBounce = 8u << 20;  // per half of the pinned bounce buffer
@@ -131,11 +129,12 @@ void box_init(edmd_box *b, int n, double lx, double ly)
 
 int check_flags(edmd_ctx *c)
 {
-    int32_t f = 0;
-    CU(cudaMemcpyAsync(&f, c->flags, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
+    int32_t f[kFlagCount] = {0};
+    CU(cudaMemcpyAsync(f, c->flags, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (f & 1) {
-        CU(cudaMemsetAsync(c->flags, 0, sizeof(int32_t), c->stream));
+    c->nghost = f[kFlagGhosts];
+    if (f[kFlagBadCell] & 1) {
+        CU(cudaMemsetAsync(c->flags + kFlagBadCell, 0, sizeof(int32_t), c->stream));
         c->have_state = false;
         return fail(c, EDMD_ECELL, "a particle's cell id lies outside the cell grid");
     }
@@ -191,30 +190,31 @@ int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
     if ((r = dev_alloc(c, &c->rad, N))) return r;
     if ((r = dev_alloc(c, &c->vr, N))) return r;
     if ((r = dev_alloc(c, &c->cid, N))) return r;
-    if ((r = dev_alloc(c, &c->cell_cnt, (size_t)nc + 8))) return r;
-    if ((r = dev_alloc(c, &c->cell_start, (size_t)nc + 8))) return r;
-    if ((r = dev_alloc(c, &c->slot_id, N))) return r;
-    c->scan_tiles = edmd_scan_tiles_for((int)nc);
-    for (int k = 0; k < 2; k++) {
-        if ((r = dev_alloc(c, &c->scan_state[k], (size_t)c->scan_tiles))) return r;
-        CU(cudaMemsetAsync(c->scan_state[k], 0, c->scan_tiles * sizeof(uint32_t), c->stream));
-    }
-    if ((r = dev_alloc(c, &c->scan_ticket, 2))) return r;
-    CU(cudaMemsetAsync(c->scan_ticket, 0, 2 * sizeof(int32_t), c->stream));
-    CU(cudaMemsetAsync(c->cell_cnt, 0, ((size_t)nc + 8) * sizeof(int32_t), c->stream));
-    if ((r = dev_alloc(c, &c->sxv, N))) return r;
-    if ((r = dev_alloc(c, &c->srad, N))) return r;
-    if ((r = dev_alloc(c, &c->svr, N))) return r;
-    if ((r = dev_alloc(c, &c->sid, N))) return r;
-    if ((r = dev_alloc(c, &c->scid, N))) return r;
+    c->ps = c->dbox.nx + 3;
+    long long ncp = (long long)c->dbox.ny * c->ps;
+    if (ncp >= (1ll << 31) - 8) return fail(c, EDMD_EINVAL, "cell grid too large");
+    c->ncp = (int)ncp;
+    // every particle has at most one ghost copy (two when nx < 3); rows are padded to 32
+    c->cap = (size_t)(c->dbox.nx < 3 ? 3 : 2) * N + 32 * (size_t)c->dbox.ny + 64;
+    c->max_chunks = (int)((c->cap + 31) / 32);
+    if ((r = dev_alloc(c, &c->cell_cnt, (size_t)ncp + 8))) return r;
+    if ((r = dev_alloc(c, &c->off, (size_t)ncp + 8))) return r;
+    if ((r = dev_alloc(c, &c->rank, N))) return r;
+    if ((r = dev_alloc(c, &c->row_total, (size_t)c->dbox.ny + 8))) return r;
+    if ((r = dev_alloc(c, &c->row_base, (size_t)c->dbox.ny + 8))) return r;
+    if ((r = dev_alloc(c, &c->chunk_row, (size_t)c->max_chunks + 8))) return r;
+    CU(cudaMemsetAsync(c->cell_cnt, 0, ((size_t)ncp + 8) * sizeof(int32_t), c->stream));
+    if ((r = dev_alloc(c, &c->srec, c->cap + 32))) return r;
+    CU(cudaMemsetAsync(c->srec, 0, (c->cap + 32) * sizeof(SRec), c->stream));
+    if ((r = dev_alloc(c, &c->svr, c->cap + 32))) return r;
     if ((r = dev_alloc(c, &c->t_cross, N))) return r;
     if ((r = dev_alloc(c, &c->t_coll, N))) return r;
     if ((r = dev_alloc(c, &c->partner, N))) return r;
     if ((r = dev_alloc(c, &c->dir, N))) return r;
     if ((r = dev_alloc(c, &c->ctype, N))) return r;
     if ((r = dev_alloc(c, &c->overlap_key, 1))) return r;
-    if ((r = dev_alloc(c, &c->flags, 4))) return r;
-    CU(cudaMemsetAsync(c->flags, 0, 4 * sizeof(int32_t), c->stream));
+    if ((r = dev_alloc(c, &c->flags, kFlagCount))) return r;
+    CU(cudaMemsetAsync(c->flags, 0, kFlagCount * sizeof(int32_t), c->stream));
     if ((r = dev_alloc(c, &c->boop, 4 * N))) return r;
     if ((r = dev_alloc(c, &c->boop_nb, N))) return r;
     c->red_cap = 296;
@@ -228,8 +228,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->cell_cnt,
-                   c->cell_start, c->slot_id, c->scan_state[0], c->scan_state[1],
-                   c->scan_ticket, c->sxv, c->srad, c->svr, c->sid, c->scid,
+                   c->off, c->rank, c->row_total, c->row_base, c->chunk_row, c->srec, c->svr,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
                    c->overlap_key, c->flags, c->pcf_counts, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
@@ -269,7 +268,7 @@ int edmd_cuda_get_stat(edmd_ctx *c, int stat, uint64_t *value)
     if (stat != EDMD_STAT_EXACT_RESCANS) return fail(c, EDMD_EINVAL, "unknown stat");
     CU(cudaSetDevice(c->device));
     uint32_t v = 0;
-    CU(cudaMemcpyAsync(&v, c->flags + 1, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&v, c->flags + kFlagRescans, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *value = v;
     return 0;
@@ -290,6 +289,8 @@ int edmd_cuda_upload(edmd_ctx *c, const double *x, const double *y, const double
     if ((r = h2d(c, c->in_soa + 3 * N, vy, B))) return r;
     if ((r = h2d(c, c->in_soa + 4 * N, rad, B))) return r;
     if (cell_xy && (r = h2d(c, c->in_cell, cell_xy, 2 * N * sizeof(int32_t)))) return r;
+    CU(cudaMemsetAsync(c->flags + kFlagGhosts, 0, 2 * sizeof(int32_t), c->stream));
+    c->nghost = 0;
     c->launches += edmd_launch_pack(c, cell_xy != nullptr);
     CU(cudaGetLastError());
     c->t = t;
@@ -450,6 +451,7 @@ int edmd_cuda_download_state(edmd_ctx *c, double *x, double *y, double *vx, doub
 static int ensure_index(edmd_ctx *c)
 {
     if (c->have_index) return 0;
+    if (c->n == 0) { c->have_index = true; return 0; }
     c->launches += edmd_launch_cell_index(c, EDMD_MODE_NORMAL);
     CU(cudaGetLastError());
     c->have_index = true;

@@ -1,24 +1,34 @@
 // edmd_internal.cuh -- device-side data layout and kernel launchers shared by
 // the translation units of libedmd_cuda.so (sm_100a only).
 //
-// HBM layout (N particles, NC = nx*ny cells), all allocated once per context:
+// HBM layout (N particles, cell grid nx x ny), all allocated once per context:
 //
 //   resident state (original particle order, written by upload / free_fly)
 //     xv    double4[N]   (x, y, vx, vy)   one 32-byte sector per particle
 //     rad   double [N]
 //     vr    double [N]   growth rates (GROW mode only)
-//     cid   int32  [N]   row-major cell id Y*nx + X   (src/EDMD.c:2071)
+//     cid   int32  [N]   PADDED cell id  Y*PS + X + 1,  PS = nx + 3
 //
-//   cell index (rebuilt by every sweep, K0)
-//     cell_cnt   int32[NC]     histogram, self-cleaning (returns to zero)
-//     cell_start int32[NC+1]   exclusive scan; cell c owns [start[c], start[c+1])
-//     slot_id    int32[N]      particle ids bucketed by cell (arbitrary in-cell order)
-//     sxv/srad/svr/sid/scid    state gathered into cell order; inside a cell
-//                              the order is DESCENDING particle id, i.e. the
-//                              reference's linked-list order after
-//                              cellListInit (head insertion, src/EDMD.c:1906-1920,
-//                              2071-2072), so a plain strict-> running minimum
-//                              reproduces the reference's tie-breaking.
+//   cell index, rebuilt by every sweep (K0).  The reference's intrusive linked
+//   cell list (src/EDMD.c:1906-1920, 2053-2078) becomes a counting sort over a
+//   PADDED grid: every row of cells carries a left ghost cell (copy of cell
+//   nx-1), the nx real cells, a right ghost cell (copy of cell 0) and an empty
+//   sentinel.  With the ghosts the three cells X-1, X, X+1 the reference scans
+//   (PBCcellX, src/EDMD.c:2110-2116) are ALWAYS one contiguous run of the
+//   cell-ordered array, periodic edge included; with the sentinel, off[] of a
+//   row ends in the row total.  Rows start on 32-slot boundaries so a warp of
+//   the sweep never straddles two rows.
+//     cell_cnt  int32[ny*PS]    histogram (self-cleaning: zeroed by the row scan)
+//     rank      int32[N]        arrival rank of particle i inside its cell
+//     off       int32[ny*PS]    exclusive scan of the padded row (row-local)
+//     row_total int32[ny]       entries in the row (ghosts included)
+//     row_base  int32[ny+1]     first slot of each row (multiple of 32)
+//     chunk_row int32[cap/32]   row of every 32-slot chunk, -1 past the end
+//     srec      SRec [cap]      48-byte records in cell order (arbitrary order
+//                               inside a cell; consumers are order-independent
+//                               and break exact ties by the reference's rule:
+//                               descending particle id = its linked-list order)
+//     svr       double[cap]     growth rates in cell order (GROW only)
 //
 //   sweep outputs (original particle order)
 //     t_cross f64[N], t_coll f64[N], partner i32[N], dir u8[N], ctype u8[N]
@@ -35,6 +45,29 @@ struct edmd_dev_box {
     double csx, csy, fx, fy;
 };
 
+// one particle in cell order: exactly three 16-byte words
+struct __align__(16) SRec {
+    double x, y, vx, vy, rad;
+    int id;   // original particle id
+    int pc;   // padded cell id
+};
+static_assert(sizeof(SRec) == 48, "SRec must be 48 bytes");
+
+// everything a consumer of the cell index needs (kernel argument block)
+struct CellIndex {
+    int nx, ny, ps;           // ps = nx + 3
+    const int32_t *off;
+    const int32_t *row_total;
+    const int32_t *row_base;
+    const int32_t *chunk_row;
+    const SRec *srec;
+    const double *svr;
+    const int32_t *flags;     // [3] != 0: some particle is far from its filed cell
+};
+
+// device flag words
+enum { kFlagBadCell = 0, kFlagRescans = 1, kFlagGhosts = 2, kFlagInsane = 3, kFlagCount = 8 };
+
 struct edmd_ctx {
     int device;
     int n;
@@ -49,8 +82,10 @@ struct edmd_ctx {
     bool have_state;     // upload done
     bool have_pred;      // device predictions valid
     bool have_index;     // cell index matches resident state
+    bool index_has_vr;   // ... and carries growth rates
     bool have_vr;
     double t;            // time of the resident snapshot
+    int nghost;          // ghost entries of the current upload
 
     // upload staging (device SoA mirror of the host arrays)
     double *in_soa;      // 5*N doubles: x | y | vx | vy | rad
@@ -65,21 +100,20 @@ struct edmd_ctx {
     int32_t *cid;
 
     // cell index
-    int32_t *cell_cnt, *cell_start, *slot_id;
-    uint32_t *scan_state[2];   // decoupled look-back tile states, ping-pong
-    int32_t *scan_ticket;      // [2] dynamic tile counters, ping-pong
-    int scan_tiles;
-    int scan_parity;
-    double4 *sxv;
-    double *srad, *svr;
-    int32_t *sid, *scid;
+    int ps;              // padded row stride nx + 3
+    int ncp;             // ny * ps
+    size_t cap;          // slots in srec
+    int max_chunks;
+    int32_t *cell_cnt, *rank, *off, *row_total, *row_base, *chunk_row;
+    SRec *srec;
+    double *svr;
 
     // outputs
     double *t_cross, *t_coll;
     int32_t *partner;
     uint8_t *dir, *ctype;
     unsigned long long *overlap_key;  // min over (i<<32 | j), ~0ull = none
-    int32_t *flags;                   // [0] bad cell id seen
+    int32_t *flags;                   // kFlagCount words
 
     // analysis scratch
     unsigned long long *pcf_counts;   // capacity pcf_cap bins
@@ -91,6 +125,30 @@ struct edmd_ctx {
     char *flush_buf;                  // L2 flush scratch (bench only)
     size_t flush_cap;
 };
+
+inline CellIndex edmd_cell_index(const edmd_ctx *c)
+{
+    CellIndex g;
+    g.nx = c->dbox.nx;
+    g.ny = c->dbox.ny;
+    g.ps = c->ps;
+    g.off = c->off;
+    g.row_total = c->row_total;
+    g.row_base = c->row_base;
+    g.chunk_row = c->chunk_row;
+    g.srec = c->srec;
+    g.svr = c->svr;
+    g.flags = c->flags;
+    return g;
+}
+
+// number of 32-slot chunks the current index can occupy (host-side bound)
+inline int edmd_chunks_bound(const edmd_ctx *c)
+{
+    long long slots = (long long)c->n + c->nghost + 32ll * c->dbox.ny;
+    long long ch = (slots + 31) / 32;
+    return (int)(ch < c->max_chunks ? ch : c->max_chunks);
+}
 
 // ---- launchers (each returns the number of kernels it launched) ----------
 int edmd_launch_pack(edmd_ctx *c, bool have_cells);

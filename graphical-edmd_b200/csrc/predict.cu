@@ -1,7 +1,7 @@
-// predict.cu -- K1: the whole-system prediction sweep.
+// predict.cu -- K1: the whole-system prediction sweep, and K2: free flight.
 //
-// One thread per particle, in cell order.  For particle i this evaluates what
-// the reference's `crossingEvent(i); collisionEvent(i);` evaluate
+// For every particle i this evaluates what the reference's
+// `crossingEvent(i); collisionEvent(i);` evaluate
 //   crossingEventNormal / crossingEventGrow      src/EDMD.c:2405-2482, 2343-2403
 //   collisionEventNormal / collisionEventGrow    src/EDMD.c:2829-3102, 3104-3230
 //   collisionTimeNormal / collisionTimeGrow      src/EDMD.c:2661-2723, 2598-2659
@@ -10,36 +10,47 @@
 // and WITHOUT fused multiply-adds: every product and sum that the reference's
 // (FMA-less x86-64) build rounds separately is an explicit __dmul_rn /
 // __dadd_rn / __dsub_rn here; division and square root are IEEE
-// correctly-rounded on both sides.  That makes event times bit-identical, not
-// merely close.
+// correctly-rounded on both sides.  Event times are therefore bit-identical.
 //
-// Scan order = reference order: rows j = -1..1, columns k = -1..1, inside a
-// cell descending particle id (the cell index keeps that order), running
-// minimum with a strict `>`; NaN candidates lose; no candidate => partner 0 at
-// t + 1e26 (1e7 while growing).
+// Selection = the reference's running minimum with a strict `>` over rows
+// j = -1..1, columns k = -1..1 and, inside a cell, its linked list (descending
+// particle id after cellListInit).  A minimum does not depend on visiting
+// order except for exact ties, so records inside a cell may sit in any order;
+// exact ties are resolved explicitly by that rule (earlier cell wins, then the
+// larger id).  NaN candidates lose; no candidate => partner 0 at t + 1e26
+// (1e7 while growing).
 //
-// Two kernels:
-//   k_predict_tile  (NORMAL mode) -- a CTA stages a 2-D tile of cells + halo in
-//       shared memory (tile.cuh) with coalesced loads, then every thread scans
-//       its particle's 3x3 cells out of shared memory.  Candidate selection is
-//       two-phase: phase 1 computes b, |dv|^2, c, det EXACTLY (they decide the
-//       reference's `b > 0` / `det < 0` / overlap branches) and ranks the
-//       survivors by an APPROXIMATE time c / (sqrt~(det) - b) built from the
-//       MUFU rsqrt/rcp seeds (rel. error ~2^-20); phase 2 evaluates the
-//       reference's formula (-b - sqrt(det)) / v2 with IEEE sqrt and division
-//       for the winner only.  If any other survivor lies within 2^-13 relative
-//       of the winner, or anything looks ill-conditioned (non-positive or
-//       non-finite estimate, catastrophic cancellation in -b - sqrt(det)), the
-//       particle is re-done by the plain exact loop, so the result is always
-//       the reference's, bit for bit.
-//   k_predict_generic -- the plain exact loop straight from global memory;
-//       used for GROW mode (once per run) and as the overflow fallback.
+// k_predict_rows (NORMAL mode): one warp per 32-slot chunk, neighbours staged
+// in shared memory (rowstage.cuh).  Two-phase candidate selection: phase 1
+// computes b, |dv|^2, c, det EXACTLY (they decide the reference's `b > 0`,
+// `det < 0` and overlap branches) and ranks the survivors by an APPROXIMATE
+// time c / (sqrt~(det) - b) built from the MUFU rsqrt/rcp seeds (relative error
+// ~2^-20); phase 2 evaluates the reference's formula (-b - sqrt(det)) / v2 with
+// IEEE sqrt and division for the winner only.  If another survivor lies within
+// 2^-13 relative of the winner, or anything looks ill-conditioned (non-positive
+// or non-finite estimate, cancellation in -b - sqrt(det)), the particle is
+// re-done by the plain exact loop, so the result is always the reference's.
+//
+// k_predict_generic: the plain exact loop straight from global memory; used for
+// GROW mode (once per run), as the overflow path and for cross-checking.
 #include "edmd_internal.cuh"
-#include "tile.cuh"
+#include "rowstage.cuh"
 
 namespace {
 
-constexpr int kThreads = 128;
+struct SweepArgs {
+    edmd_dev_box b;
+    CellIndex g;
+    double t;
+    int max_chunks;
+    double *t_cross;
+    uint8_t *dir;
+    double *t_coll;
+    int32_t *partner;
+    uint8_t *ctype;
+    unsigned long long *overlap_key;
+    unsigned int *stats;  // particles resolved by the exact re-scan
+};
 
 __device__ __forceinline__ double min_image(double d, double half, double len)
 {
@@ -49,60 +60,65 @@ __device__ __forceinline__ double min_image(double d, double half, double len)
     return d;
 }
 
-__device__ __forceinline__ int wrap_cell(int a, int n)
+// exact b, |dv|^2, c and the two products of det, reference order
+// (collisionTimeNormal with lat2 == 0)
+template <bool WRAP>
+__device__ __forceinline__ void pair_terms(const edmd_dev_box &b, const SRec &p1, double four_r1,
+                                           const SRec &p2, double &bb, double &v2, double &c,
+                                           double &b2, double &vc)
 {
-    if (a < 0) return a + n;
-    if (a >= n) return a - n;
-    return a;
+    const double dvx = __dsub_rn(p2.vx, p1.vx);
+    const double dvy = __dsub_rn(p2.vy, p1.vy);
+    double dx = __dsub_rn(p2.x, p1.x);
+    double dy = __dsub_rn(p2.y, p1.y);
+    if (WRAP) {
+        dx = min_image(dx, b.half_lx, b.lx);
+        dy = min_image(dy, b.half_ly, b.ly);
+    }
+    bb = __dadd_rn(__dmul_rn(dx, dvx), __dmul_rn(dy, dvy));
+    v2 = __dadd_rn(__dmul_rn(dvx, dvx), __dmul_rn(dvy, dvy));
+    c = __dsub_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(four_r1, p2.rad));
+    b2 = __dmul_rn(bb, bb);
+    vc = __dmul_rn(v2, c);
 }
 
-// collisionTimeNormal, lat2 == 0.  Returns the candidate time (may be NaN).
-__device__ __forceinline__ double pair_time_normal(const edmd_dev_box &b,
-                                                   const double4 &p1, double r1,
-                                                   const double4 &p2, double r2,
-                                                   bool &overlap)
+// collisionTimeNormal: candidate time (NaN possible), sets overlap
+template <bool WRAP>
+__device__ __forceinline__ double pair_time_normal(const edmd_dev_box &b, const SRec &p1,
+                                                   double four_r1, const SRec &p2, bool &overlap)
 {
-    double dvx = __dsub_rn(p2.z, p1.z);
-    double dvy = __dsub_rn(p2.w, p1.w);
-    double dx = min_image(__dsub_rn(p2.x, p1.x), b.half_lx, b.lx);
-    double dy = min_image(__dsub_rn(p2.y, p1.y), b.half_ly, b.ly);
-    double bb = __dadd_rn(__dmul_rn(dx, dvx), __dmul_rn(dy, dvy));
+    double bb, v2, c, b2, vc;
+    pair_terms<WRAP>(b, p1, four_r1, p2, bb, v2, c, b2, vc);
     if (bb > 0) return EDMD_NEVER;
-    double v2 = __dadd_rn(__dmul_rn(dvx, dvx), __dmul_rn(dvy, dvy));
-    double c = __dsub_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)),
-                         __dmul_rn(__dmul_rn(4.0, r1), r2));
-    double det = __dsub_rn(__dmul_rn(bb, bb), __dmul_rn(v2, c));
+    const double det = __dsub_rn(b2, vc);
     if (c < -0.01) overlap = true;
     if (det < 0) return EDMD_NEVER;
     return __ddiv_rn(__dsub_rn(-bb, __dsqrt_rn(det)), v2);
 }
 
-// collisionTimeGrow, lat2 == 0.
-__device__ __forceinline__ double pair_time_grow(const edmd_dev_box &b,
-                                                 const double4 &p1, double r1,
-                                                 double vr1, const double4 &p2,
-                                                 double r2, double vr2,
-                                                 bool &overlap)
+// collisionTimeGrow, lat2 == 0
+__device__ __forceinline__ double pair_time_grow(const edmd_dev_box &b, const SRec &p1, double vr1,
+                                                 const SRec &p2, double vr2, bool &overlap)
 {
-    double dvx = __dsub_rn(p2.z, p1.z);
-    double dvy = __dsub_rn(p2.w, p1.w);
-    double dvr = __dadd_rn(vr1, vr2);
+    const double dvx = __dsub_rn(p2.vx, p1.vx);
+    const double dvy = __dsub_rn(p2.vy, p1.vy);
+    const double dvr = __dadd_rn(vr1, vr2);
     double dx = __dsub_rn(p2.x, p1.x);
     double dy = __dsub_rn(p2.y, p1.y);
-    double dr = __dsqrt_rn(__dmul_rn(__dmul_rn(4.0, r1), r2));
+    const double dr = __dsqrt_rn(__dmul_rn(__dmul_rn(4.0, p1.rad), p2.rad));
     dx = min_image(dx, b.half_lx, b.lx);
     dy = min_image(dy, b.half_ly, b.ly);
-    double bb = __dsub_rn(__dadd_rn(__dmul_rn(dx, dvx), __dmul_rn(dy, dvy)),
-                          __dmul_rn(dvr, dr));
-    double v2 = __dadd_rn(__dmul_rn(dvx, dvx), __dmul_rn(dvy, dvy));
-    double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-    double a = __dsub_rn(v2, __dmul_rn(dvr, dvr));
-    double gap = __dsub_rn(d2, __dmul_rn(dr, dr));
-    double det = __dsub_rn(__dmul_rn(bb, bb), __dmul_rn(a, gap));
+    const double bb = __dsub_rn(__dadd_rn(__dmul_rn(dx, dvx), __dmul_rn(dy, dvy)),
+                                __dmul_rn(dvr, dr));
+    const double v2 = __dadd_rn(__dmul_rn(dvx, dvx), __dmul_rn(dvy, dvy));
+    const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    const double a = __dsub_rn(v2, __dmul_rn(dvr, dvr));
+    const double gap = __dsub_rn(d2, __dmul_rn(dr, dr));
+    const double det = __dsub_rn(__dmul_rn(bb, bb), __dmul_rn(a, gap));
     if (det < 0) return EDMD_NEVER;
-    double sq = __dsqrt_rn(det);
-    double plus = __ddiv_rn(__dadd_rn(-bb, sq), a);
-    double minus = __ddiv_rn(__dsub_rn(-bb, sq), a);
+    const double sq = __dsqrt_rn(det);
+    const double plus = __ddiv_rn(__dadd_rn(-bb, sq), a);
+    const double minus = __ddiv_rn(__dsub_rn(-bb, sq), a);
     if (((minus > 0) && (plus > 0) && (minus < plus)) || ((minus > 0) && (plus < 0)))
         return minus;
     else if (((minus > 0) && (plus > 0.000000001) && (plus < minus)) ||
@@ -112,122 +128,116 @@ __device__ __forceinline__ double pair_time_grow(const edmd_dev_box &b,
     return EDMD_NEVER;
 }
 
-// Everything the sweep reads and writes (kernel argument block).
-struct SweepArgs {
-    int n;
-    edmd_dev_box b;
-    double t;
-    const double4 *sxv;
-    const double *srad;
-    const double *svr;
-    const int32_t *sid;
-    const int32_t *scid;
-    const int32_t *start;
-    double *t_cross;
-    uint8_t *dir;
-    double *t_coll;
-    int32_t *partner;
-    uint8_t *ctype;
-    unsigned long long *overlap_key;
-    unsigned int *stats;  // [0] particles resolved by the exact re-scan
-    int tx, ty, tiles_x;
-};
-
-// crossingEventNormal / crossingEventGrow for one particle, exact.
+// crossingEventNormal / crossingEventGrow, exact
 template <bool WRAP>
-__device__ __forceinline__ void crossing_exact(const edmd_dev_box &b, const double4 &p1, int X, int Y,
+__device__ __forceinline__ void crossing_exact(const edmd_dev_box &b, const SRec &p1, int X, int Y,
                                                double &dt, int &d)
 {
-    double ax = __dsub_rn(__dmul_rn((double)(p1.z < 0 ? X : 1 + X), b.csx), p1.x);
-    double ay = __dsub_rn(__dmul_rn((double)(p1.w < 0 ? Y : 1 + Y), b.csy), p1.y);
+    double ax = __dsub_rn(__dmul_rn((double)(p1.vx < 0 ? X : 1 + X), b.csx), p1.x);
+    double ay = __dsub_rn(__dmul_rn((double)(p1.vy < 0 ? Y : 1 + Y), b.csy), p1.y);
     if (WRAP) {
         ax = min_image(ax, b.half_lx, b.lx);
         ay = min_image(ay, b.half_ly, b.ly);
     }
-    const double tx = __ddiv_rn(ax, p1.z);
-    const double ty = __ddiv_rn(ay, p1.w);
+    const double tx = __ddiv_rn(ax, p1.vx);
+    const double ty = __ddiv_rn(ay, p1.vy);
     const bool takex = tx < ty;  // strict: ties go to y
     dt = takex ? tx : ty;
-    d = takex ? (p1.z < 0 ? 1 : 2) : (p1.w < 0 ? 3 : 4);
+    d = takex ? (p1.vx < 0 ? 1 : 2) : (p1.vy < 0 ? 3 : 4);
 }
 
-// One particle straight from the cell-ordered global arrays: the reference's
-// loops as written.  Used by k_predict_generic and as the tile overflow path.
-template <bool GROW>
-__device__ void predict_one_global(const SweepArgs &a, int s)
+// The reference's first-minimum-in-scan-order rule for a candidate that ties
+// the current best exactly: only a larger id in the SAME cell comes earlier.
+__device__ __forceinline__ bool tie_wins(const SRec &cand, int best_pc, int best_id)
 {
-    const edmd_dev_box &b = a.b;
-    const double4 p1 = a.sxv[s];
-    const double r1 = a.srad[s];
-    const double vr1 = GROW ? a.svr[s] : 0.0;
-    const int id = a.sid[s];
-    const int c = a.scid[s];
-    const int Y = c / b.nx;
-    const int X = c - Y * b.nx;
+    return cand.pc == best_pc && cand.id > best_id;
+}
 
-    double dtc;
-    int d;
-    crossing_exact<true>(b, p1, X, Y, dtc, d);
-    a.t_cross[id] = __dadd_rn(a.t, dtc);
-    a.dir[id] = (uint8_t)d;
-
-    double best = GROW ? 10000000.0 : EDMD_NEVER;
-    int best_slot = -1;
-    int first_overlap = -1;
-    const bool interior = (X >= 1) && (X + 1 < b.nx);
-#pragma unroll 1
-    for (int j = -1; j <= 1; j++) {
-        const int rowbase = wrap_cell(Y + j, b.ny) * b.nx;
-        const int nseg = interior ? 1 : 3;
-#pragma unroll 1
-        for (int k = 0; k < nseg; k++) {
-            int lo, hi;
-            if (interior) {
-                lo = a.start[rowbase + X - 1];
-                hi = a.start[rowbase + X + 2];
-            } else {
-                int cc = rowbase + wrap_cell(X + k - 1, b.nx);
-                lo = a.start[cc];
-                hi = a.start[cc + 1];
-            }
-#pragma unroll 1
-            for (int p = lo; p < hi; p++) {
-                if (p == s) continue;
-                const double4 p2 = a.sxv[p];
-                const double r2 = a.srad[p];
-                bool ov = false;
-                double dt;
-                if (GROW)
-                    dt = pair_time_grow(b, p1, r1, vr1, p2, r2, a.svr[p], ov);
-                else
-                    dt = pair_time_normal(b, p1, r1, p2, r2, ov);
-                if (ov && first_overlap < 0) first_overlap = p;
-                if (best > dt) {
-                    best = dt;
-                    best_slot = p;
-                }
-            }
-        }
-    }
+__device__ __forceinline__ void emit_collision(const SweepArgs &a, int id, double best, int best_id,
+                                               int ov_id)
+{
     a.t_coll[id] = __dadd_rn(a.t, best);
-    a.partner[id] = best_slot >= 0 ? a.sid[best_slot] : 0;
+    a.partner[id] = best_id >= 0 ? best_id : 0;
     a.ctype[id] = EDMD_EV_COLLISION;
-    if (first_overlap >= 0) {
-        unsigned long long key = ((unsigned long long)(uint32_t)id << 32) |
-                                 (uint32_t)a.sid[first_overlap];
+    if (ov_id >= 0) {
+        unsigned long long key = ((unsigned long long)(uint32_t)id << 32) | (uint32_t)ov_id;
         atomicMin(a.overlap_key, key);
     }
 }
 
+// Exact loop over candidate records [lo, hi) of one row (shared or global).
+template <bool GROW, bool WRAP>
+__device__ __forceinline__ void exact_scan_range(const edmd_dev_box &b, const SRec &p1, double four_r1,
+                                                 double vr1, const SRec *recs, const double *vrs,
+                                                 int lo, int hi, double &best, int &best_id,
+                                                 int &best_pc, int &ov_id, int &ov_pc)
+{
+#pragma unroll 1
+    for (int p = lo; p < hi; p++) {
+        const SRec p2 = recs[p];
+        if (p2.id == p1.id) continue;  // `p1 != p2` is identity (ghost copies included)
+        bool ov = false;
+        double dt;
+        if (GROW)
+            dt = pair_time_grow(b, p1, vr1, p2, vrs[p], ov);
+        else
+            dt = pair_time_normal<WRAP>(b, p1, four_r1, p2, ov);
+        if (ov && (ov_id < 0 || (p2.pc == ov_pc && p2.id > ov_id))) {
+            ov_id = p2.id;
+            ov_pc = p2.pc;
+        }
+        if (best > dt || (best == dt && best_id >= 0 && tie_wins(p2, best_pc, best_id))) {
+            best = dt;
+            best_id = p2.id;
+            best_pc = p2.pc;
+        }
+    }
+}
+
+// One particle straight from the global cell-ordered records.
 template <bool GROW>
-__global__ void __launch_bounds__(kThreads)
+__device__ void predict_one_global(const SweepArgs &a, int s, int Y, int pcx)
+{
+    const edmd_dev_box &b = a.b;
+    const CellIndex &g = a.g;
+    const SRec p1 = g.srec[s];
+    const double vr1 = GROW ? g.svr[s] : 0.0;
+    const double four_r1 = __dmul_rn(4.0, p1.rad);
+    double dtc;
+    int d;
+    crossing_exact<true>(b, p1, pcx - 1, Y, dtc, d);
+    a.t_cross[p1.id] = __dadd_rn(a.t, dtc);
+    a.dir[p1.id] = (uint8_t)d;
+
+    double best = GROW ? 10000000.0 : EDMD_NEVER;
+    int best_id = -1, best_pc = -1, ov_id = -1, ov_pc = -1;
+#pragma unroll 1
+    for (int j = 0; j < 3; j++) {
+        const int Yr = row_wrap(Y - 1 + j, g.ny);
+        const int rb = g.row_base[Yr];
+        const int32_t *o = g.off + (size_t)Yr * g.ps;
+        exact_scan_range<GROW, true>(b, p1, four_r1, vr1, g.srec, g.svr, rb + o[pcx - 1],
+                                     rb + o[pcx + 2], best, best_id, best_pc, ov_id, ov_pc);
+    }
+    emit_collision(a, p1.id, best, best_id, ov_id);
+}
+
+template <bool GROW>
+__global__ void __launch_bounds__(kStageThreads)
 k_predict_generic(const __grid_constant__ SweepArgs a)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < a.n) predict_one_global<GROW>(a, s);
+    const int chunk = s >> 5;
+    if (chunk >= a.max_chunks) return;
+    const int Y = a.g.chunk_row[chunk];
+    if (Y < 0) return;
+    if (s >= a.g.row_base[Y] + a.g.row_total[Y]) return;
+    const int pcx = a.g.srec[s].pc - Y * a.g.ps;
+    if (pcx < 1 || pcx > a.g.nx) return;  // ghost entry
+    predict_one_global<GROW>(a, s, Y, pcx);
 }
 
-// ---- tiled kernel ---------------------------------------------------------
+// ---- the staged two-phase kernel -------------------------------------------
 __device__ __forceinline__ double rsqrt_seed(double x)
 {
     double r;
@@ -242,7 +252,7 @@ __device__ __forceinline__ double rcp_seed(double x)
     return r;
 }
 
-// hi word of a positive normal finite double, else "suspicious"
+// hi word of anything but a positive, normal, finite double
 __device__ __forceinline__ bool hi_suspicious(int h)
 {
     return (unsigned)(h - 0x00100000) >= (unsigned)(0x7ff00000 - 0x00100000);
@@ -250,244 +260,177 @@ __device__ __forceinline__ bool hi_suspicious(int h)
 
 constexpr int kBandHi = 128;  // 128 * 2^-20 = 2^-13 relative
 
-// exact b, v2, c, det of the pair (shared index q -> p), reference order
 template <bool WRAP>
-__device__ __forceinline__ void pair_terms(const edmd_dev_box &b, const double4 &p1, double four_r1,
-                                           const double4 &p2, double r2, double &bb, double &v2,
-                                           double &c, double &b2, double &vc)
-{
-    const double dvx = __dsub_rn(p2.z, p1.z);
-    const double dvy = __dsub_rn(p2.w, p1.w);
-    double dx = __dsub_rn(p2.x, p1.x);
-    double dy = __dsub_rn(p2.y, p1.y);
-    if (WRAP) {
-        dx = min_image(dx, b.half_lx, b.lx);
-        dy = min_image(dy, b.half_ly, b.ly);
-    }
-    bb = __dadd_rn(__dmul_rn(dx, dvx), __dmul_rn(dy, dvy));
-    v2 = __dadd_rn(__dmul_rn(dvx, dvx), __dmul_rn(dvy, dvy));
-    c = __dsub_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(four_r1, r2));
-    b2 = __dmul_rn(bb, bb);
-    vc = __dmul_rn(v2, c);
-}
-
-template <bool WRAP>
-__device__ __forceinline__ void predict_one_tile(const SweepArgs &a, const TileShared &s,
-                                                 const TileInfo &ti, int r, int q)
+__device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const WarpStage &w,
+                                                   const RowLane &rl)
 {
     const edmd_dev_box &b = a.b;
-    const double4 p1 = s.xv[q];
-    const double r1 = s.rad[q];
-    const double four_r1 = __dmul_rn(4.0, r1);
-    const int id = s.id[q];
-    const int Y = tile_wrap(ti.y0 - 1 + r, b.ny);
-    const int X = s.cell[q] - Y * b.nx;
-    const int xl = X - ti.x0 + 1;
+    const SRec p1 = w.rec[1][rl.self];
+    const double four_r1 = __dmul_rn(4.0, p1.rad);
+    const int X = rl.pcx - 1, Y = rl.Y;
 
-    // ---- crossing: rank the two axes by seeds, divide once -----------------
+    // ---- crossing: rank the two axes by reciprocal seeds, divide once --------
     {
-        double ax = __dsub_rn(__dmul_rn((double)(p1.z < 0 ? X : 1 + X), b.csx), p1.x);
-        double ay = __dsub_rn(__dmul_rn((double)(p1.w < 0 ? Y : 1 + Y), b.csy), p1.y);
+        double ax = __dsub_rn(__dmul_rn((double)(p1.vx < 0 ? X : 1 + X), b.csx), p1.x);
+        double ay = __dsub_rn(__dmul_rn((double)(p1.vy < 0 ? Y : 1 + Y), b.csy), p1.y);
         if (WRAP) {
             ax = min_image(ax, b.half_lx, b.lx);
             ay = min_image(ay, b.half_ly, b.ly);
         }
-        const double qx = ax * rcp_seed(p1.z);
-        const double qy = ay * rcp_seed(p1.w);
+        const double qx = ax * rcp_seed(p1.vx);
+        const double qy = ay * rcp_seed(p1.vy);
         const int hx = __double2hiint(qx), hy = __double2hiint(qy);
+        bool takex;
         double dtc;
-        int d;
         if (hi_suspicious(hx) || hi_suspicious(hy) || abs(hx - hy) <= kBandHi) {
-            const double tx = __ddiv_rn(ax, p1.z);
-            const double ty = __ddiv_rn(ay, p1.w);
-            const bool takex = tx < ty;
+            const double tx = __ddiv_rn(ax, p1.vx);
+            const double ty = __ddiv_rn(ay, p1.vy);
+            takex = tx < ty;  // strict: ties go to y
             dtc = takex ? tx : ty;
-            d = takex ? (p1.z < 0 ? 1 : 2) : (p1.w < 0 ? 3 : 4);
         } else {
-            const bool takex = qx < qy;
-            dtc = __ddiv_rn(takex ? ax : ay, takex ? p1.z : p1.w);
-            d = takex ? (p1.z < 0 ? 1 : 2) : (p1.w < 0 ? 3 : 4);
+            takex = qx < qy;
+            dtc = __ddiv_rn(takex ? ax : ay, takex ? p1.vx : p1.vy);
         }
-        a.t_cross[id] = __dadd_rn(a.t, dtc);
-        a.dir[id] = (uint8_t)d;
+        a.t_cross[p1.id] = __dadd_rn(a.t, dtc);
+        a.dir[p1.id] = (uint8_t)(takex ? (p1.vx < 0 ? 1 : 2) : (p1.vy < 0 ? 3 : 4));
     }
 
-    // ---- collision, phase 1: exact filter + seed ranking --------------------
-    double m1 = EDMD_NEVER;
-    int hm = __double2hiint(EDMD_NEVER);
-    int ibest = -1;
-    int first_overlap = -1;
-    bool amb = false;
+    // ---- collision, phase 1: exact filter + seed ranking ---------------------
+    double m1 = EDMD_NEVER;   // smallest estimate so far; its hi word is the band centre
+    int jbest = 0, ibest = -1;
+    bool amb = false, ovany = false;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const SRec *row = w.rec[j];
 #pragma unroll 1
-    for (int rr = r - 1; rr <= r + 1; rr++) {
-        const int lo = s.coff[rr][xl - 1];
-        const int hi = s.coff[rr][xl + 2];
-#pragma unroll 1
-        for (int p = lo; p < hi; p++) {
-            const double4 p2 = s.xv[p];
-            const double r2 = s.rad[p];
+        for (int p = rl.lo[j]; p < rl.hi[j]; p++) {
+            const SRec p2 = row[p];
             double bb, v2, c, b2, vc;
-            pair_terms<WRAP>(b, p1, four_r1, p2, r2, bb, v2, c, b2, vc);
+            pair_terms<WRAP>(b, p1, four_r1, p2, bb, v2, c, b2, vc);
             const double det = __dsub_rn(b2, vc);
             // reference: `if (b > 0) never` ... overlap check ... `if (det < 0) never`
-            const bool approaching = !(bb > 0) && (p != q);
-            if (approaching && (c < -0.01) && first_overlap < 0) first_overlap = p;
+            const bool approaching = !(bb > 0) && (WRAP ? (p2.id != p1.id) : (j != 1 || p != rl.self));
+            ovany |= approaching && (c < -0.01);
             if (approaching && (det >= 0)) {
                 const double sq = det * rsqrt_seed(det);   // ~sqrt(det); NaN when det == 0
                 const double qd = c * rcp_seed(sq - bb);   // ~ c / (sqrt(det) - b)
                 const int hq = __double2hiint(qd);
-                amb |= hi_suspicious(hq) || (abs(hq - hm) <= kBandHi) ||
+                amb |= hi_suspicious(hq) || (abs(hq - __double2hiint(m1)) <= kBandHi) ||
                        (vc < 1e-10 * b2);                  // cancellation in -b - sqrt(det)
                 if (qd < m1) {
                     m1 = qd;
-                    hm = hq;
+                    jbest = j;
                     ibest = p;
                 }
             }
         }
     }
 
-    // ---- phase 2: the reference's formula for the winner --------------------
     double best = EDMD_NEVER;
-    int best_slot = -1;
-    if (!amb) {
+    int best_id = -1, best_pc = -1, ov_id = -1, ov_pc = -1;
+    if (!amb && !ovany) {
+        // ---- phase 2: the reference's formula for the winner -------------------
         if (ibest >= 0) {
+            const SRec p2 = w.rec[jbest][ibest];
             double bb, v2, c, b2, vc;
-            pair_terms<WRAP>(b, p1, four_r1, s.xv[ibest], s.rad[ibest], bb, v2, c, b2, vc);
-            const double det = __dsub_rn(b2, vc);
-            const double dt = __ddiv_rn(__dsub_rn(-bb, __dsqrt_rn(det)), v2);
+            pair_terms<WRAP>(b, p1, four_r1, p2, bb, v2, c, b2, vc);
+            const double dt = __ddiv_rn(__dsub_rn(-bb, __dsqrt_rn(__dsub_rn(b2, vc))), v2);
             if (best > dt) {
                 best = dt;
-                best_slot = ibest;
+                best_id = p2.id;
             }
         }
     } else {
-        // exact re-scan in reference order (strict >, first minimum wins)
-        atomicAdd(a.stats, 1u);
+        // ---- exact re-scan in reference order ---------------------------------
+        if (amb) atomicAdd(a.stats, 1u);
 #pragma unroll 1
-        for (int rr = r - 1; rr <= r + 1; rr++) {
-            const int lo = s.coff[rr][xl - 1];
-            const int hi = s.coff[rr][xl + 2];
-#pragma unroll 1
-            for (int p = lo; p < hi; p++) {
-                if (p == q) continue;
-                double bb, v2, c, b2, vc;
-                pair_terms<WRAP>(b, p1, four_r1, s.xv[p], s.rad[p], bb, v2, c, b2, vc);
-                if (bb > 0) continue;
-                const double det = __dsub_rn(b2, vc);
-                if (det < 0) continue;
-                const double dt = __ddiv_rn(__dsub_rn(-bb, __dsqrt_rn(det)), v2);
-                if (best > dt) {
-                    best = dt;
-                    best_slot = p;
-                }
-            }
-        }
+        for (int j = 0; j < 3; j++)
+            exact_scan_range<false, WRAP>(b, p1, four_r1, 0.0, w.rec[j], nullptr, rl.lo[j], rl.hi[j],
+                                          best, best_id, best_pc, ov_id, ov_pc);
     }
-    a.t_coll[id] = __dadd_rn(a.t, best);
-    a.partner[id] = best_slot >= 0 ? s.id[best_slot] : 0;
-    a.ctype[id] = EDMD_EV_COLLISION;
-    if (first_overlap >= 0) {
-        unsigned long long key = ((unsigned long long)(uint32_t)id << 32) |
-                                 (uint32_t)s.id[first_overlap];
-        atomicMin(a.overlap_key, key);
-    }
+    emit_collision(a, p1.id, best, best_id, ov_id);
 }
 
-__global__ void __launch_bounds__(kTileThreads)
-k_predict_tile(const __grid_constant__ SweepArgs a)
+__global__ void __launch_bounds__(kStageThreads)
+k_predict_rows(const __grid_constant__ SweepArgs a)
 {
-    __shared__ TileShared s;
-    const TileInfo ti = tile_stage(s, a.b, a.tx, a.ty, a.tiles_x, a.sxv, a.srad, a.sid, a.scid, a.start);
-    const int own = s.own;
-    if (s.overflow) {
-        // more particles than the staging buffer holds: global-memory path
-        for (int k = threadIdx.x; k < own; k += kTileThreads) {
-            int r = 1;
-            while (k >= s.own_cum[r]) r++;
-            predict_one_global<false>(a, s.seg_lo[r][1] + (k - s.own_cum[r - 1]));
-        }
+    __shared__ WarpStage stage[kStageWarps];
+    const int warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x * kStageWarps + warp;
+    if (chunk >= a.max_chunks) return;
+    RowLane rl;
+    const int st = row_stage(stage[warp], a.g, chunk, rl);
+    if (st == 0) return;
+    if (st == 2) {  // a segment does not fit the staging window
+        if (rl.active) predict_one_global<false>(a, rl.s, rl.Y, rl.pcx);
         return;
     }
-    const bool fast = s.fast != 0;
-    for (int k = threadIdx.x; k < own; k += kTileThreads) {
-        int r, q;
-        tile_own(s, ti, k, r, q);
-        if (fast) predict_one_tile<false>(a, s, ti, r, q);
-        else predict_one_tile<true>(a, s, ti, r, q);
-    }
+    // no periodic image can be involved: interior rows and columns, a grid at
+    // least 12 cells wide, and every particle within a cell width of its cell
+    const bool interior = !rl.active || (rl.pcx >= 2 && rl.pcx <= a.g.nx - 1);
+    const bool fast = (a.g.nx >= 12) && (a.g.ny >= 12) && (rl.Y >= 1) && (rl.Y <= a.g.ny - 2) &&
+                      (a.g.flags[kFlagInsane] == 0) && __all_sync(0xffffffffu, interior);
+    if (!rl.active) return;
+    if (fast) predict_one_staged<false>(a, stage[warp], rl);
+    else predict_one_staged<true>(a, stage[warp], rl);
 }
 
 // ---- K2: batched free flight (freeFlyNormal / freeFlyGrow) -----------------
 template <bool GROW>
 __global__ void __launch_bounds__(256)
-k_free_fly(int n, edmd_dev_box b, double dt, double4 *__restrict__ xv,
-           double *__restrict__ rad, const double *__restrict__ vr)
+k_free_fly(int n, edmd_dev_box b, int ps, double dt, double4 *__restrict__ xv,
+           double *__restrict__ rad, const double *__restrict__ vr,
+           const int32_t *__restrict__ cid, int32_t *__restrict__ flags)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double4 p = xv[i];
-    double x = __dadd_rn(p.x, __dmul_rn(dt, p.z));
-    double y = __dadd_rn(p.y, __dmul_rn(dt, p.w));
-    if (GROW) rad[i] = __dadd_rn(rad[i], __dmul_rn(dt, vr[i]));
-    // PBCpostX / PBCpostY: a single +-L
-    if (x < 0) x = __dadd_rn(x, b.lx);
-    else if (x >= b.lx) x = __dsub_rn(x, b.lx);
-    if (y < 0) y = __dadd_rn(y, b.ly);
-    else if (y >= b.ly) y = __dsub_rn(y, b.ly);
-    reinterpret_cast<double2 *>(xv)[2 * (size_t)i] = make_double2(x, y);
+    int insane = 0;
+    if (i < n) {
+        double4 p = xv[i];
+        double x = __dadd_rn(p.x, __dmul_rn(dt, p.z));
+        double y = __dadd_rn(p.y, __dmul_rn(dt, p.w));
+        if (GROW) rad[i] = __dadd_rn(rad[i], __dmul_rn(dt, vr[i]));
+        // PBCpostX / PBCpostY: a single +-L
+        if (x < 0) x = __dadd_rn(x, b.lx);
+        else if (x >= b.lx) x = __dsub_rn(x, b.lx);
+        if (y < 0) y = __dadd_rn(y, b.ly);
+        else if (y >= b.ly) y = __dsub_rn(y, b.ly);
+        reinterpret_cast<double2 *>(xv)[2 * (size_t)i] = make_double2(x, y);
+        // cells are host state and do not move with the particle: re-check that
+        // it is still near the cell it is filed under
+        const int pc = cid[i];
+        const int Y = pc / ps;
+        const int X = pc - Y * ps - 1;
+        insane = !(fabs(x - ((double)X + 0.5) * b.csx) <= 1.5 * b.csx) ||
+                 !(fabs(y - ((double)Y + 0.5) * b.csy) <= 1.5 * b.csy);
+    }
+    insane = __reduce_add_sync(0xffffffffu, insane);
+    if ((threadIdx.x & 31) == 0 && insane) atomicAdd(&flags[kFlagInsane], insane);
 }
 
 }  // namespace
 
-void edmd_tile_dims(const edmd_ctx *c, int *tx, int *ty)
-{
-    // aim at ~100 own particles per 128-thread CTA
-    double per_cell = c->dbox.nc > 0 ? (double)c->n / (double)c->dbox.nc : 1.0;
-    if (per_cell < 0.05) per_cell = 0.05;
-    int y = kTileMaxTY;
-    if (y > c->dbox.ny) y = c->dbox.ny;
-    int x = (int)(100.0 / (per_cell * y) + 0.5);
-    if (x < 2) x = 2;
-    if (x > kTileMaxTX) x = kTileMaxTX;
-    if (x > c->dbox.nx) x = c->dbox.nx;
-    *tx = x;
-    *ty = y;
-}
-
 int edmd_launch_predict(edmd_ctx *c, int mode)
 {
-    int n = c->n;
-    if (n == 0) return 0;
+    if (c->n == 0) return 0;
     SweepArgs a;
-    a.n = n;
     a.b = c->dbox;
+    a.g = edmd_cell_index(c);
     a.t = c->t;
-    a.sxv = c->sxv;
-    a.srad = c->srad;
-    a.svr = c->svr;
-    a.sid = c->sid;
-    a.scid = c->scid;
-    a.start = c->cell_start;
+    a.max_chunks = edmd_chunks_bound(c);
     a.t_cross = c->t_cross;
     a.dir = c->dir;
     a.t_coll = c->t_coll;
     a.partner = c->partner;
     a.ctype = c->ctype;
     a.overlap_key = c->overlap_key;
-    a.stats = reinterpret_cast<unsigned int *>(c->flags + 1);
-    edmd_tile_dims(c, &a.tx, &a.ty);
-    a.tiles_x = (c->dbox.nx + a.tx - 1) / a.tx;
-    if (mode == EDMD_MODE_GROW || c->force_generic) {
-        int blocks = (n + kThreads - 1) / kThreads;
-        if (mode == EDMD_MODE_GROW)
-            k_predict_generic<true><<<blocks, kThreads, 0, c->stream>>>(a);
-        else
-            k_predict_generic<false><<<blocks, kThreads, 0, c->stream>>>(a);
-        return 1;
-    }
-    int tiles_y = (c->dbox.ny + a.ty - 1) / a.ty;
-    k_predict_tile<<<a.tiles_x * tiles_y, kTileThreads, 0, c->stream>>>(a);
+    a.stats = reinterpret_cast<unsigned int *>(c->flags + kFlagRescans);
+    const int blocks = (a.max_chunks + kStageWarps - 1) / kStageWarps;
+    if (mode == EDMD_MODE_GROW)
+        k_predict_generic<true><<<blocks, kStageThreads, 0, c->stream>>>(a);
+    else if (c->force_generic)
+        k_predict_generic<false><<<blocks, kStageThreads, 0, c->stream>>>(a);
+    else
+        k_predict_rows<<<blocks, kStageThreads, 0, c->stream>>>(a);
     return 1;
 }
 
@@ -496,11 +439,12 @@ int edmd_launch_free_fly(edmd_ctx *c, int mode, double dt)
     int n = c->n;
     if (n == 0) return 0;
     int blocks = (n + 255) / 256;
+    cudaMemsetAsync(c->flags + kFlagInsane, 0, sizeof(int32_t), c->stream);
     if (mode == EDMD_MODE_GROW)
-        k_free_fly<true><<<blocks, 256, 0, c->stream>>>(n, c->dbox, dt, c->xv,
-                                                        c->rad, c->vr);
+        k_free_fly<true><<<blocks, 256, 0, c->stream>>>(n, c->dbox, c->ps, dt, c->xv, c->rad,
+                                                        c->vr, c->cid, c->flags);
     else
-        k_free_fly<false><<<blocks, 256, 0, c->stream>>>(n, c->dbox, dt, c->xv,
-                                                         c->rad, c->vr);
+        k_free_fly<false><<<blocks, 256, 0, c->stream>>>(n, c->dbox, c->ps, dt, c->xv, c->rad,
+                                                         c->vr, c->cid, c->flags);
     return 1;
 }

@@ -108,34 +108,28 @@ __device__ __forceinline__ void boop_range(const edmd_dev_box &b, double rc2, co
 __global__ void __launch_bounds__(kStageThreads)
 k_boop_rows(const __grid_constant__ BoopArgs a)
 {
-    __shared__ WarpStage stage[kStageWarps];
-    const int warp = threadIdx.x >> 5;
-    const int chunk = blockIdx.x * kStageWarps + warp;
-    if (chunk >= a.max_chunks) return;
-    RowLane rl;
-    const int st = row_stage(stage[warp], a.g, chunk, rl);
-    if (st == 0) return;
-    BoopAcc acc;
-    if (st == 2) {  // segments do not fit: straight from global memory
-        if (!rl.active) return;
-        const SRec p1 = a.g.srec[rl.s];
+    const bool sane = a.g.flags[kFlagInsane] == 0;
+    row_pipeline(a.g, a.g.meta, a.max_chunks,
+                 [&](const StageBuf &buf, const ChunkMeta &m, const RowLane &rl, int status) {
+                     if (!rl.active) return;
+                     BoopAcc acc;
+                     if (status == 2) {  // segments do not fit: straight from global memory
+                         const SRec p1 = a.g.srec[rl.s];
 #pragma unroll
-        for (int j = 0; j < 3; j++)
-            boop_range<true>(a.b, a.rc2, p1, a.g.srec, rl.lo[j], rl.hi[j], acc);
-        boop_emit(a, p1.id, acc);
-        return;
-    }
-    const bool interior = !rl.active || (rl.pcx >= 2 && rl.pcx <= a.g.nx - 1);
-    const bool fast = (a.g.nx >= 12) && (a.g.ny >= 12) && (rl.Y >= 1) && (rl.Y <= a.g.ny - 2) &&
-                      (a.g.flags[kFlagInsane] == 0) && __all_sync(0xffffffffu, interior);
-    if (!rl.active) return;
-    const SRec p1 = stage[warp].rec[1][rl.self];
+                         for (int j = 0; j < 3; j++)
+                             boop_range<true>(a.b, a.rc2, p1, a.g.srec, rl.lo[j], rl.hi[j], acc);
+                         boop_emit(a, p1.id, acc);
+                         return;
+                     }
+                     const bool fast = sane && (m.flags & kMetaInterior);
+                     const SRec p1 = buf.rec[1][rl.self];
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        if (fast) boop_range<false>(a.b, a.rc2, p1, stage[warp].rec[j], rl.lo[j], rl.hi[j], acc);
-        else boop_range<true>(a.b, a.rc2, p1, stage[warp].rec[j], rl.lo[j], rl.hi[j], acc);
-    }
-    boop_emit(a, p1.id, acc);
+                     for (int j = 0; j < 3; j++) {
+                         if (fast) boop_range<false>(a.b, a.rc2, p1, buf.rec[j], rl.lo[j], rl.hi[j], acc);
+                         else boop_range<true>(a.b, a.rc2, p1, buf.rec[j], rl.lo[j], rl.hi[j], acc);
+                     }
+                     boop_emit(a, p1.id, acc);
+                 });
 }
 
 // deterministic two-stage sum: fixed block partials, then one block in order
@@ -262,7 +256,12 @@ int edmd_launch_boop(edmd_ctx *c, double r_c)
     a.q6arg = c->boop + 3 * N;
     a.nbr = c->boop_nb;
     const int blocks = (a.max_chunks + kStageWarps - 1) / kStageWarps;
-    k_boop_rows<<<blocks, kStageThreads, 0, c->stream>>>(a);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_boop_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem);
+        attr = true;
+    }
+    k_boop_rows<<<min(blocks, edmd_persistent_blocks(c)), kStageThreads, kStageSmem, c->stream>>>(a);
     return 1;
 }
 

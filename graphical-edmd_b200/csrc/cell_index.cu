@@ -12,12 +12,14 @@
 //   rowscan  one CTA per cell row: exclusive scan of the padded row (ghost
 //            cells take the count of the cell they mirror), row total, and the
 //            histogram is zeroed again (no memset between sweeps)
-//   rowbase  one CTA: scan of the row totals rounded up to 32; chunk -> row map
+//   rowbase  one CTA: scan of the row totals rounded up to 32
+//   chunkmeta one CTA per row: the staging plan (ChunkMeta) of every 32-slot chunk
 //   scatter  every particle writes its 48-byte record (and its ghost copy when
 //            it sits in an edge cell) to row_base + off + rank
 //
 // Integer / data movement only: HBM- and L2-bound.
 #include "edmd_internal.cuh"
+#include "rowstage.cuh"
 
 namespace {
 
@@ -124,8 +126,7 @@ k_rowscan(int nx, int ps, int32_t *__restrict__ cnt, int32_t *__restrict__ off,
 constexpr int kBaseThreads = 1024;
 
 __global__ void __launch_bounds__(kBaseThreads)
-k_rowbase(int ny, const int32_t *__restrict__ row_total, int32_t *__restrict__ row_base,
-          int32_t *__restrict__ chunk_row, int max_chunks)
+k_rowbase(int ny, const int32_t *__restrict__ row_total, int32_t *__restrict__ row_base)
 {
     __shared__ int s_warp[kBaseThreads / 32];
     __shared__ int s_carry;
@@ -146,19 +147,83 @@ k_rowbase(int ny, const int32_t *__restrict__ row_total, int32_t *__restrict__ r
         int wbase = 0;
         for (int w = 0; w < (tid >> 5); w++) wbase += s_warp[w];
         const int carry = s_carry;
-        const int excl = carry + wbase + incl - v;
-        if (Y < ny) {
-            row_base[Y] = excl;
-            for (int ch = excl >> 5; ch < ((excl + v) >> 5); ch++)
-                if (ch < max_chunks) chunk_row[ch] = Y;
-        }
+        if (Y < ny) row_base[Y] = carry + wbase + incl - v;
         __syncthreads();
         if (tid == kBaseThreads - 1) s_carry = carry + wbase + incl;
         __syncthreads();
     }
-    const int total = s_carry;
-    if (tid == 0) row_base[ny] = total;
-    for (int ch = (total >> 5) + tid; ch < max_chunks; ch += kBaseThreads) chunk_row[ch] = -1;
+    if (tid == 0) row_base[ny] = s_carry;
+}
+
+// ------------------------------------------------------------- chunkmeta --
+// one CTA per cell row: the staging plan of each of the row's 32-slot chunks
+constexpr int kMetaThreads = 64;
+
+// smallest column pcx with off[pcx + 1] > slot  (the cell that holds `slot`)
+__device__ __forceinline__ int cell_of_slot(const int32_t *__restrict__ o, int ps, int slot)
+{
+    int lo = 0, hi = ps - 2;  // answer in [0, ps-2]; off[ps-1] = row total > slot
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (o[mid + 1] > slot) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kMetaThreads)
+k_chunkmeta(int nx, int ny, int ps, const int32_t *__restrict__ off,
+            const int32_t *__restrict__ row_total, const int32_t *__restrict__ row_base,
+            ChunkMeta *__restrict__ meta, int max_chunks, int cap_rec, int cap_off)
+{
+    const int Y = blockIdx.x;
+    const int rb = row_base[Y];
+    const int tot = row_total[Y];
+    const int nch = (tot + 31) >> 5;
+    const int32_t *o = off + (size_t)Y * ps;
+    for (int q = threadIdx.x; q < nch; q += kMetaThreads) {
+        ChunkMeta m;
+        const int first = 32 * q, last = min(first + 31, tot - 1);
+        const int ca = max(cell_of_slot(o, ps, first), 1);
+        const int cb = min(cell_of_slot(o, ps, last), nx);
+        m.Y = ca <= cb ? Y : -1;   // only ghost entries: nothing to do
+        m.cfirst = ca;
+        m.ncells = cb - ca + 1;
+        m.row_end = rb + tot;
+        m.flags = 0;
+        m.pad[0] = m.pad[1] = 0;
+        if (m.Y >= 0) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                int Yr = Y - 1 + j;
+                if (Yr < 0) Yr += ny;
+                else if (Yr >= ny) Yr -= ny;
+                const int rbr = row_base[Yr];
+                const int32_t *orow = off + (size_t)Yr * ps;
+                const int lo = rbr + orow[ca - 1];
+                const int hi = rbr + orow[cb + 2];
+                m.seg_lo[j] = lo;
+                m.seg_len[j] = hi - lo;
+                m.delta[j] = rbr - lo;
+                if (hi - lo > cap_rec) m.flags |= kMetaOverflow;
+            }
+            if (m.ncells + 3 > cap_off) m.flags |= kMetaOverflow;
+            if (nx >= 12 && ny >= 12 && Y >= 1 && Y <= ny - 2 && ca >= 2 && cb <= nx - 1)
+                m.flags |= kMetaInterior;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 3; j++) m.seg_lo[j] = m.seg_len[j] = m.delta[j] = 0;
+        }
+        const int ch = (rb >> 5) + q;
+        if (ch < max_chunks) meta[ch] = m;
+    }
+    if (Y == ny - 1) {  // chunks past the last row are empty
+        ChunkMeta e;
+        e.Y = -1; e.cfirst = 0; e.ncells = 0; e.row_end = 0; e.flags = 0; e.pad[0] = e.pad[1] = 0;
+        for (int j = 0; j < 3; j++) e.seg_lo[j] = e.seg_len[j] = e.delta[j] = 0;
+        for (int ch = ((rb + ((tot + 31) & ~31)) >> 5) + threadIdx.x; ch < max_chunks; ch += kMetaThreads)
+            meta[ch] = e;
+    }
 }
 
 // --------------------------------------------------------------- scatter --
@@ -230,9 +295,11 @@ int edmd_launch_cell_index(edmd_ctx *c, int mode)
     }
     k_rowscan<<<c->dbox.ny, kThreads, 0, c->stream>>>(c->dbox.nx, c->ps, c->cell_cnt, c->off,
                                                      c->row_total);
-    k_rowbase<<<1, kBaseThreads, 0, c->stream>>>(c->dbox.ny, c->row_total, c->row_base,
-                                                 c->chunk_row, c->max_chunks);
-    launched += 2;
+    k_rowbase<<<1, kBaseThreads, 0, c->stream>>>(c->dbox.ny, c->row_total, c->row_base);
+    k_chunkmeta<<<c->dbox.ny, kMetaThreads, 0, c->stream>>>(
+        c->dbox.nx, c->dbox.ny, c->ps, c->off, c->row_total, c->row_base, c->meta,
+        edmd_chunks_bound(c), kCapW, kOffW);
+    launched += 3;
     if (n > 0) {
         if (mode == EDMD_MODE_GROW)
             k_scatter<true><<<blocks, kThreads, 0, c->stream>>>(

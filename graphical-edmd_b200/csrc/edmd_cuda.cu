@@ -143,6 +143,12 @@ int check_flags(edmd_ctx *c)
 
 }  // namespace
 
+int edmd_persistent_blocks(const edmd_ctx *c)
+{
+    // 4 CTAs of 4 warps fit one SM (55 KB of staging buffers each)
+    return (c->sm_count > 0 ? c->sm_count : 148) * 4;
+}
+
 extern "C" {
 
 int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
@@ -178,6 +184,7 @@ int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
     c->dbox.fy = c->box.celly_fac;
 
     CU(cudaSetDevice(device));
+    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int k = 0; k < 4; k++) CU(cudaEventCreateWithFlags(&c->ev[k], cudaEventDisableTiming));
     size_t N = (size_t)n;
@@ -202,7 +209,7 @@ int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
     if ((r = dev_alloc(c, &c->rank, N))) return r;
     if ((r = dev_alloc(c, &c->row_total, (size_t)c->dbox.ny + 8))) return r;
     if ((r = dev_alloc(c, &c->row_base, (size_t)c->dbox.ny + 8))) return r;
-    if ((r = dev_alloc(c, &c->chunk_row, (size_t)c->max_chunks + 8))) return r;
+    if ((r = dev_alloc(c, &c->meta, (size_t)c->max_chunks + 8))) return r;
     CU(cudaMemsetAsync(c->cell_cnt, 0, ((size_t)ncp + 8) * sizeof(int32_t), c->stream));
     if ((r = dev_alloc(c, &c->srec, c->cap + 32))) return r;
     CU(cudaMemsetAsync(c->srec, 0, (c->cap + 32) * sizeof(SRec), c->stream));
@@ -228,7 +235,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->cell_cnt,
-                   c->off, c->rank, c->row_total, c->row_base, c->chunk_row, c->srec, c->svr,
+                   c->off, c->rank, c->row_total, c->row_base, c->meta, c->srec, c->svr,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
                    c->overlap_key, c->flags, c->pcf_counts, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};

@@ -23,7 +23,8 @@
 //     off       int32[ny*PS]    exclusive scan of the padded row (row-local)
 //     row_total int32[ny]       entries in the row (ghosts included)
 //     row_base  int32[ny+1]     first slot of each row (multiple of 32)
-//     chunk_row int32[cap/32]   row of every 32-slot chunk, -1 past the end
+//     meta      ChunkMeta[cap/32]  per 32-slot chunk: its row, the three staged
+//                               row segments and the cell-offset window (Y = -1: empty)
 //     srec      SRec [cap]      48-byte records in cell order (arbitrary order
 //                               inside a cell; consumers are order-independent
 //                               and break exact ties by the reference's rule:
@@ -53,13 +54,29 @@ struct __align__(16) SRec {
 };
 static_assert(sizeof(SRec) == 48, "SRec must be 48 bytes");
 
+// Per 32-slot chunk of the record array (all slots in one cell row Y): what a
+// warp of K1 / K4 stages.  Active (non-ghost) entries of the chunk lie in cell
+// columns cfirst .. cfirst+ncells-1; row j = -1,0,1 contributes the records
+// [seg_lo[j], seg_lo[j]+seg_len[j]) = columns cfirst-1 .. cfirst+ncells; a
+// row-local cell offset o maps to staged index o + delta[j].
+enum { kMetaOverflow = 1, kMetaInterior = 2 };
+struct __align__(16) ChunkMeta {
+    int Y, cfirst, ncells, row_end;
+    int seg_lo[3];
+    int seg_len[3];
+    int delta[3];
+    int flags;
+    int pad[2];
+};
+static_assert(sizeof(ChunkMeta) == 64, "ChunkMeta must be 64 bytes");
+
 // everything a consumer of the cell index needs (kernel argument block)
 struct CellIndex {
     int nx, ny, ps;           // ps = nx + 3
     const int32_t *off;
     const int32_t *row_total;
     const int32_t *row_base;
-    const int32_t *chunk_row;
+    const ChunkMeta *meta;
     const SRec *srec;
     const double *svr;
     const int32_t *flags;     // [3] != 0: some particle is far from its filed cell
@@ -86,6 +103,7 @@ struct edmd_ctx {
     bool have_vr;
     double t;            // time of the resident snapshot
     int nghost;          // ghost entries of the current upload
+    int sm_count;
 
     // upload staging (device SoA mirror of the host arrays)
     double *in_soa;      // 5*N doubles: x | y | vx | vy | rad
@@ -104,7 +122,8 @@ struct edmd_ctx {
     int ncp;             // ny * ps
     size_t cap;          // slots in srec
     int max_chunks;
-    int32_t *cell_cnt, *rank, *off, *row_total, *row_base, *chunk_row;
+    int32_t *cell_cnt, *rank, *off, *row_total, *row_base;
+    ChunkMeta *meta;
     SRec *srec;
     double *svr;
 
@@ -135,7 +154,7 @@ inline CellIndex edmd_cell_index(const edmd_ctx *c)
     g.off = c->off;
     g.row_total = c->row_total;
     g.row_base = c->row_base;
-    g.chunk_row = c->chunk_row;
+    g.meta = c->meta;
     g.srec = c->srec;
     g.svr = c->svr;
     g.flags = c->flags;
@@ -149,6 +168,9 @@ inline int edmd_chunks_bound(const edmd_ctx *c)
     long long ch = (slots + 31) / 32;
     return (int)(ch < c->max_chunks ? ch : c->max_chunks);
 }
+
+// grid of the persistent row-pipeline kernels: every SM full, warps loop over chunks
+int edmd_persistent_blocks(const edmd_ctx *c);
 
 // ---- launchers (each returns the number of kernels it launched) ----------
 int edmd_launch_pack(edmd_ctx *c, bool have_cells);

@@ -229,9 +229,9 @@ k_predict_generic(const __grid_constant__ SweepArgs a)
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = s >> 5;
     if (chunk >= a.max_chunks) return;
-    const int Y = a.g.chunk_row[chunk];
+    const int Y = a.g.meta[chunk].Y;
     if (Y < 0) return;
-    if (s >= a.g.row_base[Y] + a.g.row_total[Y]) return;
+    if (s >= a.g.meta[chunk].row_end) return;
     const int pcx = a.g.srec[s].pc - Y * a.g.ps;
     if (pcx < 1 || pcx > a.g.nx) return;  // ghost entry
     predict_one_global<GROW>(a, s, Y, pcx);
@@ -261,11 +261,12 @@ __device__ __forceinline__ bool hi_suspicious(int h)
 constexpr int kBandHi = 128;  // 128 * 2^-20 = 2^-13 relative
 
 template <bool WRAP>
-__device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const WarpStage &w,
+__device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const StageBuf &w,
                                                    const RowLane &rl)
 {
     const edmd_dev_box &b = a.b;
-    const SRec p1 = w.rec[1][rl.self];
+    const SRec *self = &w.rec[1][rl.self];
+    const SRec p1 = *self;
     const double four_r1 = __dmul_rn(4.0, p1.rad);
     const int X = rl.pcx - 1, Y = rl.Y;
 
@@ -296,31 +297,33 @@ __device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const War
     }
 
     // ---- collision, phase 1: exact filter + seed ranking ---------------------
+    // An overlapping approaching pair (c < -0.01, b <= 0) always has det >= 0 and
+    // a negative estimate, so it lands in the re-scan, which reports it.
     double m1 = EDMD_NEVER;   // smallest estimate so far; its hi word is the band centre
-    int jbest = 0, ibest = -1;
-    bool amb = false, ovany = false;
+    const SRec *pbest = nullptr;
+    bool amb = false;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        const SRec *row = w.rec[j];
+        const SRec *pe = &w.rec[j][rl.hi[j]];
 #pragma unroll 1
-        for (int p = rl.lo[j]; p < rl.hi[j]; p++) {
-            const SRec p2 = row[p];
+        for (const SRec *pp = &w.rec[j][rl.lo[j]]; pp < pe; pp++) {
+            const SRec p2 = *pp;
             double bb, v2, c, b2, vc;
             pair_terms<WRAP>(b, p1, four_r1, p2, bb, v2, c, b2, vc);
             const double det = __dsub_rn(b2, vc);
-            // reference: `if (b > 0) never` ... overlap check ... `if (det < 0) never`
-            const bool approaching = !(bb > 0) && (WRAP ? (p2.id != p1.id) : (j != 1 || p != rl.self));
-            ovany |= approaching && (c < -0.01);
-            if (approaching && (det >= 0)) {
+            // reference: `if (b > 0) never` ... `if (det < 0) never`; `p1 != p2` is identity
+            const bool cand = !(bb > 0) && (det >= 0) && (WRAP ? (p2.id != p1.id) : (pp != self));
+            if (cand) {
                 const double sq = det * rsqrt_seed(det);   // ~sqrt(det); NaN when det == 0
                 const double qd = c * rcp_seed(sq - bb);   // ~ c / (sqrt(det) - b)
                 const int hq = __double2hiint(qd);
+                // near-tie with the best so far, odd estimate, or cancellation in
+                // -b - sqrt(det)  (v2*c < 2^-33 b^2, compared on the exponents)
                 amb |= hi_suspicious(hq) || (abs(hq - __double2hiint(m1)) <= kBandHi) ||
-                       (vc < 1e-10 * b2);                  // cancellation in -b - sqrt(det)
+                       (__double2hiint(b2) - __double2hiint(vc) > (33 << 20));
                 if (qd < m1) {
                     m1 = qd;
-                    jbest = j;
-                    ibest = p;
+                    pbest = pp;
                 }
             }
         }
@@ -328,10 +331,10 @@ __device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const War
 
     double best = EDMD_NEVER;
     int best_id = -1, best_pc = -1, ov_id = -1, ov_pc = -1;
-    if (!amb && !ovany) {
+    if (!amb) {
         // ---- phase 2: the reference's formula for the winner -------------------
-        if (ibest >= 0) {
-            const SRec p2 = w.rec[jbest][ibest];
+        if (pbest) {
+            const SRec p2 = *pbest;
             double bb, v2, c, b2, vc;
             pair_terms<WRAP>(b, p1, four_r1, p2, bb, v2, c, b2, vc);
             const double dt = __ddiv_rn(__dsub_rn(-bb, __dsqrt_rn(__dsub_rn(b2, vc))), v2);
@@ -342,8 +345,8 @@ __device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const War
         }
     } else {
         // ---- exact re-scan in reference order ---------------------------------
-        if (amb) atomicAdd(a.stats, 1u);
-#pragma unroll 1
+        atomicAdd(a.stats, 1u);
+#pragma unroll
         for (int j = 0; j < 3; j++)
             exact_scan_range<false, WRAP>(b, p1, four_r1, 0.0, w.rec[j], nullptr, rl.lo[j], rl.hi[j],
                                           best, best_id, best_pc, ov_id, ov_pc);
@@ -354,25 +357,19 @@ __device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const War
 __global__ void __launch_bounds__(kStageThreads)
 k_predict_rows(const __grid_constant__ SweepArgs a)
 {
-    __shared__ WarpStage stage[kStageWarps];
-    const int warp = threadIdx.x >> 5;
-    const int chunk = blockIdx.x * kStageWarps + warp;
-    if (chunk >= a.max_chunks) return;
-    RowLane rl;
-    const int st = row_stage(stage[warp], a.g, chunk, rl);
-    if (st == 0) return;
-    if (st == 2) {  // a segment does not fit the staging window
-        if (rl.active) predict_one_global<false>(a, rl.s, rl.Y, rl.pcx);
-        return;
-    }
-    // no periodic image can be involved: interior rows and columns, a grid at
-    // least 12 cells wide, and every particle within a cell width of its cell
-    const bool interior = !rl.active || (rl.pcx >= 2 && rl.pcx <= a.g.nx - 1);
-    const bool fast = (a.g.nx >= 12) && (a.g.ny >= 12) && (rl.Y >= 1) && (rl.Y <= a.g.ny - 2) &&
-                      (a.g.flags[kFlagInsane] == 0) && __all_sync(0xffffffffu, interior);
-    if (!rl.active) return;
-    if (fast) predict_one_staged<false>(a, stage[warp], rl);
-    else predict_one_staged<true>(a, stage[warp], rl);
+    const bool sane = a.g.flags[kFlagInsane] == 0;
+    row_pipeline(a.g, a.g.meta, a.max_chunks,
+                 [&](const StageBuf &buf, const ChunkMeta &m, const RowLane &rl, int status) {
+                     if (!rl.active) return;
+                     if (status == 2) {  // segments do not fit the staging window
+                         predict_one_global<false>(a, rl.s, rl.Y, rl.pcx);
+                         return;
+                     }
+                     // interior chunk of a wide grid with every particle near its cell:
+                     // no periodic image can be involved
+                     if (sane && (m.flags & kMetaInterior)) predict_one_staged<false>(a, buf, rl);
+                     else predict_one_staged<true>(a, buf, rl);
+                 });
 }
 
 // ---- K2: batched free flight (freeFlyNormal / freeFlyGrow) -----------------
@@ -429,8 +426,14 @@ int edmd_launch_predict(edmd_ctx *c, int mode)
         k_predict_generic<true><<<blocks, kStageThreads, 0, c->stream>>>(a);
     else if (c->force_generic)
         k_predict_generic<false><<<blocks, kStageThreads, 0, c->stream>>>(a);
-    else
-        k_predict_rows<<<blocks, kStageThreads, 0, c->stream>>>(a);
+    else {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(k_predict_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem);
+            attr = true;
+        }
+        k_predict_rows<<<min(blocks, edmd_persistent_blocks(c)), kStageThreads, kStageSmem, c->stream>>>(a);
+    }
     return 1;
 }
 

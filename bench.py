@@ -169,10 +169,11 @@ def run_reference(args, cfg):
 
 def workload_config(cfg):
     return {"workload": f"N={cfg['n']} phi={PHI} monodisperse liquid-density jittered-lattice "
-                        "snapshot, shuffled ids, full re-predict sweep (BASELINE configs[2])",
+                        f"snapshot, {cfg.get('order', 'shuffled')} ids, full re-predict sweep (BASELINE configs[2])",
             "n_particles": cfg["n"], "phi": PHI, "seed": SEED,
             "box": [cfg["lx"], cfg["ly"]],
-            "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset outside the timed events)"}
+            "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB written then {L2_FLUSH_BYTES >> 20} MiB "
+                  "read, outside the timed events: cold and clean)"}
 
 
 def profile_traffic():
@@ -328,11 +329,15 @@ def main():
     ap.add_argument("--analysis", choices=["none", "psi6", "full"], default="full")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--n", type=int, default=N_PART)
+    ap.add_argument("--order", choices=["shuffled", "lattice"], default="shuffled",
+                    help="particle id order: uncorrelated with position (default, like a "
+                         "reference-made configuration) or lattice order")
     args = ap.parse_args()
 
     import __graft_entry__ as entry
     pkg = entry.load_package()
-    cfg = pkg.synth.lattice_config(args.n, PHI, SEED, shuffle=True)
+    cfg = pkg.synth.lattice_config(args.n, PHI, SEED, shuffle=(args.order == "shuffled"))
+    cfg["order"] = args.order
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

@@ -95,17 +95,19 @@ __device__ __forceinline__ void boop_emit(const BoopArgs &a, int id, const BoopA
 
 template <bool WRAP>
 __device__ __forceinline__ void boop_range(const edmd_dev_box &b, double rc2, const SRec &p1,
-                                           const SRec *recs, int lo, int hi, BoopAcc &acc)
+                                           const SPos *pos, const SAux *aux, int lo, int hi, BoopAcc &acc)
 {
 #pragma unroll 1
     for (int p = lo; p < hi; p++) {
-        const SRec p2 = recs[p];
-        if (p2.id == p1.id) continue;  // `p2->num != p1->num`
+        if (aux[p].id == p1.id) continue;  // `p2->num != p1->num`
+        const SPos q = pos[p];
+        SRec p2;
+        p2.x = q.x; p2.y = q.y;
         boop_pair<WRAP>(b, rc2, p1, p2, acc);
     }
 }
 
-__global__ void __launch_bounds__(kStageThreads)
+__global__ void __launch_bounds__(kStageThreads, kStageCtasPerSm)
 k_boop_rows(const __grid_constant__ BoopArgs a)
 {
     const bool sane = a.g.flags[kFlagInsane] == 0;
@@ -114,19 +116,19 @@ k_boop_rows(const __grid_constant__ BoopArgs a)
                      if (!rl.active) return;
                      BoopAcc acc;
                      if (status == 2) {  // segments do not fit: straight from global memory
-                         const SRec p1 = a.g.srec[rl.s];
+                         const SRec p1 = make_rec(a.g.spos[rl.s], a.g.saux[rl.s]);
 #pragma unroll
                          for (int j = 0; j < 3; j++)
-                             boop_range<true>(a.b, a.rc2, p1, a.g.srec, rl.lo[j], rl.hi[j], acc);
+                             boop_range<true>(a.b, a.rc2, p1, a.g.spos, a.g.saux, rl.lo[j], rl.hi[j], acc);
                          boop_emit(a, p1.id, acc);
                          return;
                      }
                      const bool fast = sane && (m.flags & kMetaInterior);
-                     const SRec p1 = buf.rec[1][rl.self];
+                     const SRec p1 = make_rec(buf.pos[1][rl.self], buf.aux[1][rl.self]);
 #pragma unroll
                      for (int j = 0; j < 3; j++) {
-                         if (fast) boop_range<false>(a.b, a.rc2, p1, buf.rec[j], rl.lo[j], rl.hi[j], acc);
-                         else boop_range<true>(a.b, a.rc2, p1, buf.rec[j], rl.lo[j], rl.hi[j], acc);
+                         if (fast) boop_range<false>(a.b, a.rc2, p1, buf.pos[j], buf.aux[j], rl.lo[j], rl.hi[j], acc);
+                         else boop_range<true>(a.b, a.rc2, p1, buf.pos[j], buf.aux[j], rl.lo[j], rl.hi[j], acc);
                      }
                      boop_emit(a, p1.id, acc);
                  });
@@ -259,6 +261,7 @@ int edmd_launch_boop(edmd_ctx *c, double r_c)
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_boop_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem);
+        cudaFuncSetAttribute(k_boop_rows, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr = true;
     }
     k_boop_rows<<<min(blocks, edmd_persistent_blocks(c)), kStageThreads, kStageSmem, c->stream>>>(a);

@@ -14,7 +14,7 @@
 //            histogram is zeroed again (no memset between sweeps)
 //   rowbase  one CTA: scan of the row totals rounded up to 32
 //   chunkmeta one CTA per row: the staging plan (ChunkMeta) of every 32-slot chunk
-//   scatter  every particle writes its 48-byte record (and its ghost copy when
+//   scatter  every particle writes its 32+16-byte record (and its ghost copy when
 //            it sits in an edge cell) to row_base + off + rank
 //
 // Integer / data movement only: HBM- and L2-bound.
@@ -70,12 +70,23 @@ k_pack(int n, edmd_dev_box b, int ps, const double *__restrict__ soa,
 }
 
 // ----------------------------------------------------------------- count --
+// four particles per thread: four independent L2 atomics in flight
 __global__ void __launch_bounds__(kThreads)
 k_count(int n, const int32_t *__restrict__ cid, int32_t *__restrict__ cnt,
         int32_t *__restrict__ rank)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) rank[i] = atomicAdd(&cnt[cid[i]], 1);
+    const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (i + 3 < n) {
+        const int4 c = *reinterpret_cast<const int4 *>(cid + i);
+        int4 r;
+        r.x = atomicAdd(&cnt[c.x], 1);
+        r.y = atomicAdd(&cnt[c.y], 1);
+        r.z = atomicAdd(&cnt[c.z], 1);
+        r.w = atomicAdd(&cnt[c.w], 1);
+        *reinterpret_cast<int4 *>(rank + i) = r;
+    } else {
+        for (int k = i; k < n; k++) rank[k] = atomicAdd(&cnt[cid[k]], 1);
+    }
 }
 
 // --------------------------------------------------------------- rowscan --
@@ -157,12 +168,12 @@ k_rowbase(int ny, const int32_t *__restrict__ row_total, int32_t *__restrict__ r
 
 // ------------------------------------------------------------- chunkmeta --
 // one CTA per cell row: the staging plan of each of the row's 32-slot chunks
-constexpr int kMetaThreads = 64;
+constexpr int kMetaThreads = 128;
 
 // smallest column pcx with off[pcx + 1] > slot  (the cell that holds `slot`)
 __device__ __forceinline__ int cell_of_slot(const int32_t *__restrict__ o, int ps, int slot)
 {
-    int lo = 0, hi = ps - 2;  // answer in [0, ps-2]; off[ps-1] = row total > slot
+    int lo = 0, hi = ps - 2;  // off[ps-1] = row total > slot (columns past nx+1 are empty)
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (o[mid + 1] > slot) hi = mid;
@@ -174,13 +185,16 @@ __device__ __forceinline__ int cell_of_slot(const int32_t *__restrict__ o, int p
 __global__ void __launch_bounds__(kMetaThreads)
 k_chunkmeta(int nx, int ny, int ps, const int32_t *__restrict__ off,
             const int32_t *__restrict__ row_total, const int32_t *__restrict__ row_base,
-            ChunkMeta *__restrict__ meta, int max_chunks, int cap_rec, int cap_off)
+            ChunkMeta *__restrict__ meta, int32_t *__restrict__ cstart, int max_chunks, int cap_rec,
+            int cap_off)
 {
     const int Y = blockIdx.x;
     const int rb = row_base[Y];
     const int tot = row_total[Y];
     const int nch = (tot + 31) >> 5;
     const int32_t *o = off + (size_t)Y * ps;
+    // absolute first slot of every padded cell of this row (one gather for the scatter)
+    for (int k = threadIdx.x; k < ps; k += kMetaThreads) cstart[(size_t)Y * ps + k] = rb + o[k];
     for (int q = threadIdx.x; q < nch; q += kMetaThreads) {
         ChunkMeta m;
         const int first = 32 * q, last = min(first + 31, tot - 1);
@@ -191,7 +205,9 @@ k_chunkmeta(int nx, int ny, int ps, const int32_t *__restrict__ off,
         m.ncells = cb - ca + 1;
         m.row_end = rb + tot;
         m.flags = 0;
-        m.pad[0] = m.pad[1] = 0;
+        m.wstart = (ca - 1) & ~3;
+        m.wlen = ((cb + 2 - m.wstart + 1) + 3) & ~3;   // columns wstart .. cb+2, rounded up to 4
+        if (m.wstart + m.wlen > ps) m.wlen = ps - m.wstart;
         if (m.Y >= 0) {
 #pragma unroll
             for (int j = 0; j < 3; j++) {
@@ -207,7 +223,7 @@ k_chunkmeta(int nx, int ny, int ps, const int32_t *__restrict__ off,
                 m.delta[j] = rbr - lo;
                 if (hi - lo > cap_rec) m.flags |= kMetaOverflow;
             }
-            if (m.ncells + 3 > cap_off) m.flags |= kMetaOverflow;
+            if (m.wlen > cap_off) m.flags |= kMetaOverflow;
             if (nx >= 12 && ny >= 12 && Y >= 1 && Y <= ny - 2 && ca >= 2 && cb <= nx - 1)
                 m.flags |= kMetaInterior;
         } else {
@@ -219,7 +235,7 @@ k_chunkmeta(int nx, int ny, int ps, const int32_t *__restrict__ off,
     }
     if (Y == ny - 1) {  // chunks past the last row are empty
         ChunkMeta e;
-        e.Y = -1; e.cfirst = 0; e.ncells = 0; e.row_end = 0; e.flags = 0; e.pad[0] = e.pad[1] = 0;
+        e.Y = -1; e.cfirst = 0; e.ncells = 0; e.row_end = 0; e.flags = 0; e.wstart = e.wlen = 0;
         for (int j = 0; j < 3; j++) e.seg_lo[j] = e.seg_len[j] = e.delta[j] = 0;
         for (int ch = ((rb + ((tot + 31) & ~31)) >> 5) + threadIdx.x; ch < max_chunks; ch += kMetaThreads)
             meta[ch] = e;
@@ -227,48 +243,73 @@ k_chunkmeta(int nx, int ny, int ps, const int32_t *__restrict__ off,
 }
 
 // --------------------------------------------------------------- scatter --
+__device__ __forceinline__ void put_rec(SPos *__restrict__ spos, SAux *__restrict__ saux,
+                                        double *__restrict__ svr, int d, const SPos &p, const SAux &a,
+                                        double g, bool grow)
+{
+    // one full 32-byte sector with a single 256-bit store + one 16-byte tag
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(&p);
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(spos + d), "r"(w[0]), "r"(w[1]),
+                 "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+    *reinterpret_cast<uint4 *>(saux + d) = *reinterpret_cast<const uint4 *>(&a);
+    if (grow) svr[d] = g;
+}
+
+// two particles per thread (more loads in flight); destination = one gather
+// of the cell's absolute start + the particle's arrival rank
 template <bool GROW>
 __global__ void __launch_bounds__(kThreads)
 k_scatter(int n, int nx, int ps, const int32_t *__restrict__ cid,
-          const int32_t *__restrict__ rank, const int32_t *__restrict__ off,
-          const int32_t *__restrict__ row_base, const double4 *__restrict__ xv,
-          const double *__restrict__ rad, const double *__restrict__ vr,
-          SRec *__restrict__ srec, double *__restrict__ svr)
+          const int32_t *__restrict__ rank, const int32_t *__restrict__ cstart,
+          const double4 *__restrict__ xv, const double *__restrict__ rad,
+          const double *__restrict__ vr, SPos *__restrict__ spos, SAux *__restrict__ saux,
+          double *__restrict__ svr)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int pc = cid[i];
-    const int Y = pc / ps;
-    const int pcx = pc - Y * ps;
-    const int rk = rank[i];
-    const int rb = row_base[Y];
-    const double4 p = xv[i];
-    SRec r;
-    r.x = p.x; r.y = p.y; r.vx = p.z; r.vy = p.w;
-    r.rad = rad[i];
-    r.id = i;
-    r.pc = pc;
-    const double g = GROW ? vr[i] : 0.0;
-    const uint4 *src = reinterpret_cast<const uint4 *>(&r);
-    {
-        const int d = rb + off[pc] + rk;
-        uint4 *dst = reinterpret_cast<uint4 *>(srec + d);
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
-        if (GROW) svr[d] = g;
+    const int i0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (i0 >= n) return;
+    const bool two = i0 + 1 < n;
+    int pc[2], rk[2];
+    if (two) {
+        const int2 c2 = *reinterpret_cast<const int2 *>(cid + i0);
+        const int2 r2 = *reinterpret_cast<const int2 *>(rank + i0);
+        pc[0] = c2.x; pc[1] = c2.y; rk[0] = r2.x; rk[1] = r2.y;
+    } else {
+        pc[0] = pc[1] = cid[i0];
+        rk[0] = rk[1] = rank[i0];
     }
-    if (pcx == 1) {  // cell 0 is mirrored by the right ghost
-        r.pc = Y * ps + nx + 1;
-        const int d = rb + off[r.pc] + rk;
-        uint4 *dst = reinterpret_cast<uint4 *>(srec + d);
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
-        if (GROW) svr[d] = g;
+    int base[2];
+    base[0] = cstart[pc[0]];
+    base[1] = cstart[pc[1]];
+    SPos r[2];
+    SAux t[2];
+    double g[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int i = i0 + (two ? k : 0);
+        const double4 p = xv[i];
+        r[k].x = p.x; r[k].y = p.y; r[k].vx = p.z; r[k].vy = p.w;
+        t[k].rad = rad[i];
+        t[k].id = i;
+        t[k].pc = pc[k];
+        if (GROW) g[k] = vr[i];
     }
-    if (pcx == nx) {  // cell nx-1 is mirrored by the left ghost
-        r.pc = Y * ps;
-        const int d = rb + off[r.pc] + rk;
-        uint4 *dst = reinterpret_cast<uint4 *>(srec + d);
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
-        if (GROW) svr[d] = g;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (k == 1 && !two) break;
+        put_rec(spos, saux, svr, base[k] + rk[k], r[k], t[k], g[k], GROW);
+        const int Y = pc[k] / ps;
+        const int pcx = pc[k] - Y * ps;
+        if (pcx == 1) {  // cell 0 is mirrored by the right ghost
+            SAux q = t[k];
+            q.pc = Y * ps + nx + 1;
+            put_rec(spos, saux, svr, cstart[q.pc] + rk[k], r[k], q, g[k], GROW);
+        }
+        if (pcx == nx) {  // cell nx-1 is mirrored by the left ghost
+            SAux q = t[k];
+            q.pc = Y * ps;
+            put_rec(spos, saux, svr, cstart[q.pc] + rk[k], r[k], q, g[k], GROW);
+        }
     }
 }
 
@@ -287,28 +328,29 @@ int edmd_launch_pack(edmd_ctx *c, bool have_cells)
 int edmd_launch_cell_index(edmd_ctx *c, int mode)
 {
     const int n = c->n;
-    const int blocks = (n + kThreads - 1) / kThreads;
+    const int blocks4 = ((n + 3) / 4 + kThreads - 1) / kThreads;
+    const int blocks = ((n + 1) / 2 + kThreads - 1) / kThreads;
     int launched = 0;
     if (n > 0) {
-        k_count<<<blocks, kThreads, 0, c->stream>>>(n, c->cid, c->cell_cnt, c->rank);
+        k_count<<<blocks4, kThreads, 0, c->stream>>>(n, c->cid, c->cell_cnt, c->rank);
         launched++;
     }
     k_rowscan<<<c->dbox.ny, kThreads, 0, c->stream>>>(c->dbox.nx, c->ps, c->cell_cnt, c->off,
                                                      c->row_total);
     k_rowbase<<<1, kBaseThreads, 0, c->stream>>>(c->dbox.ny, c->row_total, c->row_base);
     k_chunkmeta<<<c->dbox.ny, kMetaThreads, 0, c->stream>>>(
-        c->dbox.nx, c->dbox.ny, c->ps, c->off, c->row_total, c->row_base, c->meta,
+        c->dbox.nx, c->dbox.ny, c->ps, c->off, c->row_total, c->row_base, c->meta, c->cstart,
         edmd_chunks_bound(c), kCapW, kOffW);
     launched += 3;
     if (n > 0) {
         if (mode == EDMD_MODE_GROW)
             k_scatter<true><<<blocks, kThreads, 0, c->stream>>>(
-                n, c->dbox.nx, c->ps, c->cid, c->rank, c->off, c->row_base, c->xv, c->rad,
-                c->vr, c->srec, c->svr);
+                n, c->dbox.nx, c->ps, c->cid, c->rank, c->cstart, c->xv, c->rad,
+                c->vr, c->spos, c->saux, c->svr);
         else
             k_scatter<false><<<blocks, kThreads, 0, c->stream>>>(
-                n, c->dbox.nx, c->ps, c->cid, c->rank, c->off, c->row_base, c->xv, c->rad,
-                c->vr, c->srec, c->svr);
+                n, c->dbox.nx, c->ps, c->cid, c->rank, c->cstart, c->xv, c->rad,
+                c->vr, c->spos, c->saux, c->svr);
         launched++;
     }
     c->index_has_vr = (mode == EDMD_MODE_GROW);

@@ -7,13 +7,14 @@
 //     xv    double4[N]   (x, y, vx, vy)   one 32-byte sector per particle
 //     rad   double [N]
 //     vr    double [N]   growth rates (GROW mode only)
-//     cid   int32  [N]   PADDED cell id  Y*PS + X + 1,  PS = nx + 3
+//     cid   int32  [N]   PADDED cell id  Y*PS + X + 1,  PS = nx + 3 rounded up to 4
 //
 //   cell index, rebuilt by every sweep (K0).  The reference's intrusive linked
 //   cell list (src/EDMD.c:1906-1920, 2053-2078) becomes a counting sort over a
 //   PADDED grid: every row of cells carries a left ghost cell (copy of cell
-//   nx-1), the nx real cells, a right ghost cell (copy of cell 0) and an empty
-//   sentinel.  With the ghosts the three cells X-1, X, X+1 the reference scans
+//   nx-1), the nx real cells, a right ghost cell (copy of cell 0) and 1..4 empty
+//   sentinels (PS is a multiple of 4 so every row of off[] is 16-byte aligned
+//   and windows of it can be fetched with TMA bulk copies).  With the ghosts the three cells X-1, X, X+1 the reference scans
 //   (PBCcellX, src/EDMD.c:2110-2116) are ALWAYS one contiguous run of the
 //   cell-ordered array, periodic edge included; with the sentinel, off[] of a
 //   row ends in the row total.  Rows start on 32-slot boundaries so a warp of
@@ -21,11 +22,12 @@
 //     cell_cnt  int32[ny*PS]    histogram (self-cleaning: zeroed by the row scan)
 //     rank      int32[N]        arrival rank of particle i inside its cell
 //     off       int32[ny*PS]    exclusive scan of the padded row (row-local)
+//     cstart    int32[ny*PS]    row_base + off: absolute first slot of every cell
 //     row_total int32[ny]       entries in the row (ghosts included)
 //     row_base  int32[ny+1]     first slot of each row (multiple of 32)
 //     meta      ChunkMeta[cap/32]  per 32-slot chunk: its row, the three staged
 //                               row segments and the cell-offset window (Y = -1: empty)
-//     srec      SRec [cap]      48-byte records in cell order (arbitrary order
+//     spos/saux SPos/SAux[cap]  32 + 16-byte records in cell order (arbitrary order
 //                               inside a cell; consumers are order-independent
 //                               and break exact ties by the reference's rule:
 //                               descending particle id = its linked-list order)
@@ -46,13 +48,31 @@ struct edmd_dev_box {
     double csx, csy, fx, fy;
 };
 
-// one particle in cell order: exactly three 16-byte words
-struct __align__(16) SRec {
-    double x, y, vx, vy, rad;
+// One particle in cell order = a 32-byte kinematic record + a 16-byte tag, in
+// two parallel arrays.  Measured on B200 (profiles/microbench/scatter_stores.cu,
+// 1M records to random slots, cold L2): one 256-bit + one 128-bit store per
+// particle 30.7 us, three 128-bit stores into 48-byte records 54.1 us -- the
+// 32-byte record is exactly one L2 sector and is written with a single
+// STG.256, so no partial-sector writes.
+struct __align__(32) SPos { double x, y, vx, vy; };
+struct __align__(16) SAux {
+    double rad;
     int id;   // original particle id
     int pc;   // padded cell id
 };
-static_assert(sizeof(SRec) == 48, "SRec must be 48 bytes");
+static_assert(sizeof(SPos) == 32 && sizeof(SAux) == 16, "record layout");
+// register view of one particle
+struct SRec {
+    double x, y, vx, vy, rad;
+    int id, pc;
+};
+__host__ __device__ inline SRec make_rec(const SPos &p, const SAux &a)
+{
+    SRec r;
+    r.x = p.x; r.y = p.y; r.vx = p.vx; r.vy = p.vy;
+    r.rad = a.rad; r.id = a.id; r.pc = a.pc;
+    return r;
+}
 
 // Per 32-slot chunk of the record array (all slots in one cell row Y): what a
 // warp of K1 / K4 stages.  Active (non-ghost) entries of the chunk lie in cell
@@ -66,18 +86,20 @@ struct __align__(16) ChunkMeta {
     int seg_len[3];
     int delta[3];
     int flags;
-    int pad[2];
+    int wstart;   // first column of the staged off[] window (multiple of 4, <= cfirst-1)
+    int wlen;     // its length in ints (multiple of 4)
 };
 static_assert(sizeof(ChunkMeta) == 64, "ChunkMeta must be 64 bytes");
 
 // everything a consumer of the cell index needs (kernel argument block)
 struct CellIndex {
-    int nx, ny, ps;           // ps = nx + 3
+    int nx, ny, ps;           // ps = nx + 3 rounded up to a multiple of 4
     const int32_t *off;
     const int32_t *row_total;
     const int32_t *row_base;
     const ChunkMeta *meta;
-    const SRec *srec;
+    const SPos *spos;
+    const SAux *saux;
     const double *svr;
     const int32_t *flags;     // [3] != 0: some particle is far from its filed cell
 };
@@ -118,13 +140,14 @@ struct edmd_ctx {
     int32_t *cid;
 
     // cell index
-    int ps;              // padded row stride nx + 3
+    int ps;              // padded row stride: nx + 3 rounded up to a multiple of 4
     int ncp;             // ny * ps
     size_t cap;          // slots in srec
     int max_chunks;
-    int32_t *cell_cnt, *rank, *off, *row_total, *row_base;
+    int32_t *cell_cnt, *rank, *off, *cstart, *row_total, *row_base;
     ChunkMeta *meta;
-    SRec *srec;
+    SPos *spos;
+    SAux *saux;
     double *svr;
 
     // outputs
@@ -155,7 +178,8 @@ inline CellIndex edmd_cell_index(const edmd_ctx *c)
     g.row_total = c->row_total;
     g.row_base = c->row_base;
     g.meta = c->meta;
-    g.srec = c->srec;
+    g.spos = c->spos;
+    g.saux = c->saux;
     g.svr = c->svr;
     g.flags = c->flags;
     return g;

@@ -168,13 +168,13 @@ __device__ __forceinline__ void emit_collision(const SweepArgs &a, int id, doubl
 // Exact loop over candidate records [lo, hi) of one row (shared or global).
 template <bool GROW, bool WRAP>
 __device__ __forceinline__ void exact_scan_range(const edmd_dev_box &b, const SRec &p1, double four_r1,
-                                                 double vr1, const SRec *recs, const double *vrs,
-                                                 int lo, int hi, double &best, int &best_id,
-                                                 int &best_pc, int &ov_id, int &ov_pc)
+                                                 double vr1, const SPos *pos, const SAux *aux,
+                                                 const double *vrs, int lo, int hi, double &best,
+                                                 int &best_id, int &best_pc, int &ov_id, int &ov_pc)
 {
 #pragma unroll 1
     for (int p = lo; p < hi; p++) {
-        const SRec p2 = recs[p];
+        const SRec p2 = make_rec(pos[p], aux[p]);
         if (p2.id == p1.id) continue;  // `p1 != p2` is identity (ghost copies included)
         bool ov = false;
         double dt;
@@ -200,7 +200,7 @@ __device__ void predict_one_global(const SweepArgs &a, int s, int Y, int pcx)
 {
     const edmd_dev_box &b = a.b;
     const CellIndex &g = a.g;
-    const SRec p1 = g.srec[s];
+    const SRec p1 = make_rec(g.spos[s], g.saux[s]);
     const double vr1 = GROW ? g.svr[s] : 0.0;
     const double four_r1 = __dmul_rn(4.0, p1.rad);
     double dtc;
@@ -216,7 +216,7 @@ __device__ void predict_one_global(const SweepArgs &a, int s, int Y, int pcx)
         const int Yr = row_wrap(Y - 1 + j, g.ny);
         const int rb = g.row_base[Yr];
         const int32_t *o = g.off + (size_t)Yr * g.ps;
-        exact_scan_range<GROW, true>(b, p1, four_r1, vr1, g.srec, g.svr, rb + o[pcx - 1],
+        exact_scan_range<GROW, true>(b, p1, four_r1, vr1, g.spos, g.saux, g.svr, rb + o[pcx - 1],
                                      rb + o[pcx + 2], best, best_id, best_pc, ov_id, ov_pc);
     }
     emit_collision(a, p1.id, best, best_id, ov_id);
@@ -232,7 +232,7 @@ k_predict_generic(const __grid_constant__ SweepArgs a)
     const int Y = a.g.meta[chunk].Y;
     if (Y < 0) return;
     if (s >= a.g.meta[chunk].row_end) return;
-    const int pcx = a.g.srec[s].pc - Y * a.g.ps;
+    const int pcx = a.g.saux[s].pc - Y * a.g.ps;
     if (pcx < 1 || pcx > a.g.nx) return;  // ghost entry
     predict_one_global<GROW>(a, s, Y, pcx);
 }
@@ -265,8 +265,10 @@ __device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const Sta
                                                    const RowLane &rl)
 {
     const edmd_dev_box &b = a.b;
-    const SRec *self = &w.rec[1][rl.self];
-    const SRec p1 = *self;
+    const int self = kCapW + rl.self;   // flat index into pos[] / aux[]
+    const SPos *pos = &w.pos[0][0];
+    const SAux *aux = &w.aux[0][0];
+    const SRec p1 = make_rec(pos[self], aux[self]);
     const double four_r1 = __dmul_rn(4.0, p1.rad);
     const int X = rl.pcx - 1, Y = rl.Y;
 
@@ -297,44 +299,63 @@ __device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const Sta
     }
 
     // ---- collision, phase 1: exact filter + seed ranking ---------------------
-    // An overlapping approaching pair (c < -0.01, b <= 0) always has det >= 0 and
-    // a negative estimate, so it lands in the re-scan, which reports it.
-    double m1 = EDMD_NEVER;   // smallest estimate so far; its hi word is the band centre
-    const SRec *pbest = nullptr;
+    // Branch-free and two candidates per trip, so that two independent FP64
+    // dependency chains are in flight per warp.  Estimates are NaN-free for
+    // finite inputs (the 1e-300 guards), so anything odd -- an overlapping or
+    // touching approaching pair (c <= 0), total cancellation in -b - sqrt(det)
+    // (estimate forced to 0) -- surfaces as a non-positive winning estimate and
+    // sends the particle to the exact re-scan, which also reports overlaps.
+    double m1 = EDMD_NEVER;   // smallest estimate so far
+    int hband = __double2hiint(EDMD_NEVER) - kBandHi;   // hi word of m1, minus the band
+    int pbest = -1;
     bool amb = false;
+    auto rank_one = [&](int pp, const SRec &p2, double bb, double c, double b2, double vc) {
+        const double det = __dsub_rn(b2, vc);
+        // reference: `if (b > 0) never` ... `if (det < 0) never`; `p1 != p2` is identity
+        const bool cand = !(bb > 0) && (det >= 0) && (WRAP ? (p2.id != p1.id) : (pp != self));
+        const double sq = det * rsqrt_seed(det + 1e-300);    // ~sqrt(det), 0 when det == 0
+        double qd = c * rcp_seed((sq - bb) + 1e-300);        // ~ c / (sqrt(det) - b)
+        // v2*c < 2^-33 b^2 (exponent compare): -b - sqrt(det) cancels, distrust the estimate
+        if (__double2hiint(b2) - __double2hiint(vc) > (33 << 20)) qd = 0.0;
+        // within 2^-13 of the best so far (either side)?
+        amb |= cand && ((unsigned)(__double2hiint(qd) - hband) <= 2u * kBandHi);
+        if (cand && qd < m1) {
+            m1 = qd;
+            hband = __double2hiint(qd) - kBandHi;
+            pbest = pp;
+        }
+    };
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        const SRec *pe = &w.rec[j][rl.hi[j]];
+        int pp = j * kCapW + rl.lo[j];
+        const int pe = j * kCapW + rl.hi[j];
 #pragma unroll 1
-        for (const SRec *pp = &w.rec[j][rl.lo[j]]; pp < pe; pp++) {
-            const SRec p2 = *pp;
-            double bb, v2, c, b2, vc;
-            pair_terms<WRAP>(b, p1, four_r1, p2, bb, v2, c, b2, vc);
-            const double det = __dsub_rn(b2, vc);
-            // reference: `if (b > 0) never` ... `if (det < 0) never`; `p1 != p2` is identity
-            const bool cand = !(bb > 0) && (det >= 0) && (WRAP ? (p2.id != p1.id) : (pp != self));
-            if (cand) {
-                const double sq = det * rsqrt_seed(det);   // ~sqrt(det); NaN when det == 0
-                const double qd = c * rcp_seed(sq - bb);   // ~ c / (sqrt(det) - b)
-                const int hq = __double2hiint(qd);
-                // near-tie with the best so far, odd estimate, or cancellation in
-                // -b - sqrt(det)  (v2*c < 2^-33 b^2, compared on the exponents)
-                amb |= hi_suspicious(hq) || (abs(hq - __double2hiint(m1)) <= kBandHi) ||
-                       (__double2hiint(b2) - __double2hiint(vc) > (33 << 20));
-                if (qd < m1) {
-                    m1 = qd;
-                    pbest = pp;
-                }
-            }
+        for (; pp + 1 < pe; pp += 2) {
+            SRec pa, pb;   // the id is only needed where cells can repeat (WRAP)
+            pa = make_rec(pos[pp], aux[pp]);
+            pb = make_rec(pos[pp + 1], aux[pp + 1]);
+            double bba, v2a, ca, b2a, vca, bbb, v2b, cb, b2b, vcb;
+            pair_terms<WRAP>(b, p1, four_r1, pa, bba, v2a, ca, b2a, vca);
+            pair_terms<WRAP>(b, p1, four_r1, pb, bbb, v2b, cb, b2b, vcb);
+            rank_one(pp, pa, bba, ca, b2a, vca);
+            rank_one(pp + 1, pb, bbb, cb, b2b, vcb);
+        }
+        if (pp < pe) {
+            const SRec pa = make_rec(pos[pp], aux[pp]);
+            double bba, v2a, ca, b2a, vca;
+            pair_terms<WRAP>(b, p1, four_r1, pa, bba, v2a, ca, b2a, vca);
+            rank_one(pp, pa, bba, ca, b2a, vca);
         }
     }
+    // the winning estimate must be a positive, normal, finite number
+    amb |= (pbest >= 0) && hi_suspicious(__double2hiint(m1));
 
     double best = EDMD_NEVER;
     int best_id = -1, best_pc = -1, ov_id = -1, ov_pc = -1;
     if (!amb) {
         // ---- phase 2: the reference's formula for the winner -------------------
-        if (pbest) {
-            const SRec p2 = *pbest;
+        if (pbest >= 0) {
+            const SRec p2 = make_rec(pos[pbest], aux[pbest]);
             double bb, v2, c, b2, vc;
             pair_terms<WRAP>(b, p1, four_r1, p2, bb, v2, c, b2, vc);
             const double dt = __ddiv_rn(__dsub_rn(-bb, __dsqrt_rn(__dsub_rn(b2, vc))), v2);
@@ -348,13 +369,13 @@ __device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const Sta
         atomicAdd(a.stats, 1u);
 #pragma unroll
         for (int j = 0; j < 3; j++)
-            exact_scan_range<false, WRAP>(b, p1, four_r1, 0.0, w.rec[j], nullptr, rl.lo[j], rl.hi[j],
-                                          best, best_id, best_pc, ov_id, ov_pc);
+            exact_scan_range<false, WRAP>(b, p1, four_r1, 0.0, w.pos[j], w.aux[j], nullptr, rl.lo[j],
+                                          rl.hi[j], best, best_id, best_pc, ov_id, ov_pc);
     }
     emit_collision(a, p1.id, best, best_id, ov_id);
 }
 
-__global__ void __launch_bounds__(kStageThreads)
+__global__ void __launch_bounds__(kStageThreads, kStageCtasPerSm)
 k_predict_rows(const __grid_constant__ SweepArgs a)
 {
     const bool sane = a.g.flags[kFlagInsane] == 0;
@@ -430,6 +451,7 @@ int edmd_launch_predict(edmd_ctx *c, int mode)
         static bool attr = false;
         if (!attr) {
             cudaFuncSetAttribute(k_predict_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem);
+            cudaFuncSetAttribute(k_predict_rows, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
             attr = true;
         }
         k_predict_rows<<<min(blocks, edmd_persistent_blocks(c)), kStageThreads, kStageSmem, c->stream>>>(a);

@@ -9,18 +9,21 @@
 // periodic x edge too), and the union over the 32 lanes is one contiguous
 // segment per row.  K0 precomputes those three segments per chunk (ChunkMeta).
 //
-// Each warp is persistent and runs its own two-stage pipeline, no block
-// barriers anywhere:
-//     issue(next chunk):  one lane arms an mbarrier with the byte count and
-//                         fires three cp.async.bulk (TMA 1-D bulk copies,
-//                         48-byte records -> 16-byte aligned, any length) from
-//                         the record array into the stage's shared buffer;
-//                         all lanes cp.async the window of per-cell offsets
-//     wait(current chunk): mbarrier try_wait + cp.async.wait_group
-//     compute(current chunk) out of shared memory
-// so the HBM/L2 latency of chunk k+1 hides behind the FP64 work of chunk k.
-// The 48-byte record stride is bank-conflict-free for 128-bit shared loads of
-// consecutive records.  Row order j = -1, 0, 1 and ascending cell order inside
+// Each warp is persistent and independent (no block barriers anywhere):
+//     issue:   one lane arms an mbarrier with the byte count and fires three
+//              cp.async.bulk (TMA 1-D bulk copies) per record array (32-byte
+//              kinematics, 16-byte tags) into the warp's shared buffer and
+//              three more for the windows of per-cell offsets
+//              (rows of off[] are 16-byte aligned); the next chunk's plan is
+//              prefetched into L1
+//     wait:    mbarrier try_wait
+//     compute: out of shared memory
+// A warp's instruction stream is a chain of dependent FP64 operations (one
+// issue every ~7 cycles), so the SM is filled with 32 such warps (8 CTAs x 4):
+// the copy latency of one warp hides behind the arithmetic of the other seven
+// on its scheduler, which is worth more here than a second buffer per warp
+// (measured: double buffering at 16 warps/SM was no faster).
+// Row order j = -1, 0, 1 and ascending cell order inside
 // a segment are the reference's scan order (src/EDMD.c:2959-2965).
 #pragma once
 
@@ -28,11 +31,12 @@
 
 constexpr int kStageThreads = 128;               // 4 independent warps per CTA
 constexpr int kStageWarps = kStageThreads / 32;
-constexpr int kCapW = 40;                         // records per staged row segment
-constexpr int kOffW = 96;                         // cell-offset window per row
+constexpr int kCapW = 40;                         // records per staged row segment (48 B each)
+constexpr int kOffW = 64;                         // cell-offset window per row
 
-struct __align__(16) StageBuf {
-    SRec rec[3][kCapW];
+struct __align__(32) StageBuf {
+    SPos pos[3][kCapW];
+    SAux aux[3][kCapW];
     int offw[3][kOffW];
 };
 
@@ -112,30 +116,46 @@ __device__ __forceinline__ ChunkMeta load_meta(const ChunkMeta *m, int chunk)
     return r;
 }
 
-// Fire the asynchronous copies of a chunk into `buf`.  Warp-uniform.
-__device__ __forceinline__ void stage_issue(StageBuf &buf, uint64_t *bar, const CellIndex &g,
-                                            const ChunkMeta &m, int lane)
+// shared-window addresses of one warp's buffer, computed once
+struct StageAddr {
+    uint32_t pos[3], aux[3], offw[3], bar;
+};
+
+// Fire the asynchronous copies of a chunk.  Warp-uniform; one lane issues nine
+// TMA bulk copies (three segments of each record array, three off[] windows).
+__device__ __forceinline__ void stage_issue(const StageAddr &sa, const CellIndex &g, const ChunkMeta &m,
+                                            int lane)
 {
-    if (m.Y < 0 || (m.flags & kMetaOverflow)) {
-        cp_async_commit();  // keep the per-thread group count in step
-        return;
-    }
+    if (m.Y < 0 || (m.flags & kMetaOverflow)) return;
     if (lane == 0) {
-        const uint32_t bytes = (uint32_t)sizeof(SRec) * (uint32_t)(m.seg_len[0] + m.seg_len[1] + m.seg_len[2]);
-        mbar_expect_tx(bar, bytes);
+        const uint32_t rbytes = (uint32_t)(sizeof(SPos) + sizeof(SAux)) *
+                                (uint32_t)(m.seg_len[0] + m.seg_len[1] + m.seg_len[2]);
+        const uint32_t wbytes = 4u * (uint32_t)m.wlen;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sa.bar),
+                     "r"(rbytes + 3u * wbytes)
+                     : "memory");
 #pragma unroll
-        for (int j = 0; j < 3; j++)
-            if (m.seg_len[j] > 0)
-                bulk_g2s(&buf.rec[j][0], g.srec + m.seg_lo[j], (uint32_t)sizeof(SRec) * m.seg_len[j], bar);
+        for (int j = 0; j < 3; j++) {
+            if (m.seg_len[j] > 0) {
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        sa.pos[j]),
+                    "l"(g.spos + m.seg_lo[j]), "r"((uint32_t)sizeof(SPos) * (uint32_t)m.seg_len[j]), "r"(sa.bar)
+                    : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        sa.aux[j]),
+                    "l"(g.saux + m.seg_lo[j]), "r"((uint32_t)sizeof(SAux) * (uint32_t)m.seg_len[j]), "r"(sa.bar)
+                    : "memory");
+            }
+            const int32_t *o = g.off + (size_t)row_wrap(m.Y - 1 + j, g.ny) * g.ps + m.wstart;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    sa.offw[j]),
+                "l"(o), "r"(wbytes), "r"(sa.bar)
+                : "memory");
+        }
     }
-    // per-cell offsets of columns cfirst-1 .. cfirst+ncells+1 (ncells + 3 values) of the three rows
-    const int nwin = m.ncells + 3;
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const int32_t *o = g.off + (size_t)row_wrap(m.Y - 1 + j, g.ny) * g.ps + (m.cfirst - 1);
-        for (int k = lane; k < nwin; k += 32) cp_async4(&buf.offw[j][k], o + k);
-    }
-    cp_async_commit();
 }
 
 // Wait for a chunk's copies and derive this lane's view of it.  Returns 0 when
@@ -143,16 +163,14 @@ __device__ __forceinline__ void stage_issue(StageBuf &buf, uint64_t *bar, const 
 // slots read from global memory).  Warp-uniform result.
 __device__ __forceinline__ int stage_wait(const StageBuf &buf, uint64_t *bar, uint32_t parity,
                                           const CellIndex &g, const ChunkMeta &m, int chunk, int lane,
-                                          bool more_in_flight, RowLane &rl)
+                                          RowLane &rl)
 {
-    if (more_in_flight) cp_async_wait<1>();
-    else cp_async_wait<0>();
     if (m.Y < 0) return 0;
     rl.Y = m.Y;
     rl.s = chunk * 32 + lane;
     const bool valid = rl.s < m.row_end;
     if (m.flags & kMetaOverflow) {
-        const int pc = valid ? g.srec[rl.s].pc : 0;
+        const int pc = valid ? g.saux[rl.s].pc : 0;
         rl.pcx = pc - m.Y * g.ps;
         rl.active = valid && rl.pcx >= 1 && rl.pcx <= g.nx;
 #pragma unroll
@@ -166,12 +184,11 @@ __device__ __forceinline__ int stage_wait(const StageBuf &buf, uint64_t *bar, ui
         return 2;
     }
     mbar_wait(bar, parity);
-    __syncwarp();
     rl.self = rl.s - m.seg_lo[1];
-    const int pc = valid ? buf.rec[1][rl.self].pc : 0;
+    const int pc = valid ? buf.aux[1][rl.self].pc : 0;
     rl.pcx = pc - m.Y * g.ps;
     rl.active = valid && rl.pcx >= 1 && rl.pcx <= g.nx;
-    const int w = rl.active ? rl.pcx - m.cfirst : 0;   // window index of column pcx-1
+    const int w = rl.active ? rl.pcx - 1 - m.wstart : 0;   // window index of column pcx-1
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         rl.lo[j] = buf.offw[j][w] + m.delta[j];
@@ -181,7 +198,8 @@ __device__ __forceinline__ int stage_wait(const StageBuf &buf, uint64_t *bar, ui
 }
 
 // dynamic shared memory a row_pipeline kernel must be launched with
-constexpr size_t kStageSmem = sizeof(StageBuf) * kStageWarps * 2 + sizeof(uint64_t) * kStageWarps * 2;
+constexpr size_t kStageSmem = sizeof(StageBuf) * kStageWarps + sizeof(uint64_t) * kStageWarps;
+constexpr int kStageCtasPerSm = 8;
 
 // Persistent per-warp pipeline.  `body(buf, meta, rl, status)` is called with
 // all 32 lanes converged for every non-empty chunk.
@@ -190,39 +208,42 @@ __device__ __forceinline__ void row_pipeline(const CellIndex &g, const ChunkMeta
                                              Body body)
 {
     extern __shared__ __align__(128) unsigned char stage_smem[];
-    StageBuf(*bufs)[2] = reinterpret_cast<StageBuf(*)[2]>(stage_smem);
-    uint64_t(*bars)[2] = reinterpret_cast<uint64_t(*)[2]>(stage_smem + sizeof(StageBuf) * kStageWarps * 2);
+    StageBuf *bufs = reinterpret_cast<StageBuf *>(stage_smem);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_smem + sizeof(StageBuf) * kStageWarps);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = gridDim.x * kStageWarps;
     int c = blockIdx.x * kStageWarps + warp;
     if (c >= nchunks) return;
+    StageBuf &buf = bufs[warp];
+    uint64_t *bar = &bars[warp];
+    StageAddr sa;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        sa.pos[j] = smem_u32(&buf.pos[j][0]);
+        sa.aux[j] = smem_u32(&buf.aux[j][0]);
+        sa.offw[j] = smem_u32(&buf.offw[j][0]);
+    }
+    sa.bar = smem_u32(bar);
     if (lane == 0) {
-        mbar_init(&bars[warp][0], 1);
-        mbar_init(&bars[warp][1], 1);
+        mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    uint32_t parity = 0;  // bit st = phase parity of stage st
-    int st = 0;
+    uint32_t parity = 0;
     ChunkMeta m = load_meta(meta, c);
-    stage_issue(bufs[warp][0], &bars[warp][0], g, m, lane);
+    stage_issue(sa, g, m, lane);
     while (true) {
         const int cn = c + stride;
         const bool more = cn < nchunks;
-        ChunkMeta mn;
-        if (more) {
-            mn = load_meta(meta, cn);
-            stage_issue(bufs[warp][st ^ 1], &bars[warp][st ^ 1], g, mn, lane);
-        }
+        if (more && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(meta + cn));
         RowLane rl;
-        const int status = stage_wait(bufs[warp][st], &bars[warp][st], (parity >> st) & 1u, g, m, c, lane,
-                                      more, rl);
-        if (status == 1) parity ^= 1u << st;
-        if (status != 0) body(bufs[warp][st], m, rl, status);
-        __syncwarp();  // every lane is done with this stage before it is refilled
+        const int status = stage_wait(buf, bar, parity, g, m, c, lane, rl);
+        if (status == 1) parity ^= 1u;
+        if (status != 0) body(buf, m, rl, status);
+        __syncwarp();  // every lane is done with the buffer before it is refilled
         if (!more) break;
-        m = mn;
         c = cn;
-        st ^= 1;
+        m = load_meta(meta, c);
+        stage_issue(sa, g, m, lane);
     }
 }

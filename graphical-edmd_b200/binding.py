@@ -31,6 +31,7 @@ SYMBOLS = [
     "edmd_cuda_fetch_predictions", "edmd_cuda_set_growth", "edmd_cuda_free_fly",
     "edmd_cuda_download_state", "edmd_cuda_pcf", "edmd_cuda_boop_cutoff",
     "edmd_cuda_bench", "edmd_cuda_set_option", "edmd_cuda_get_stat",
+    "edmd_cuda_host_alloc", "edmd_cuda_host_free",
 ]
 
 
@@ -83,6 +84,9 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_boop_cutoff.argtypes = [vp, C.c_double, vp, vp, vp, vp, vp, vp]
     lib.edmd_cuda_bench.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double,
                                     C.c_int, C.c_int, C.c_size_t, vp, vp]
+    lib.edmd_cuda_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.edmd_cuda_host_free.argtypes = [vp]
+    lib.edmd_cuda_host_free.restype = None
     lib.edmd_cuda_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.edmd_cuda_get_stat.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
     for name in SYMBOLS:

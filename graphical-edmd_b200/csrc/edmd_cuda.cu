@@ -298,6 +298,18 @@ int edmd_cuda_get_stat(edmd_ctx *c, int stat, uint64_t *value)
     return 0;
 }
 
+int edmd_cuda_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return EDMD_EINVAL;
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+
+void edmd_cuda_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+}
+
 int edmd_cuda_upload(edmd_ctx *c, const double *x, const double *y, const double *vx,
                      const double *vy, const double *rad, const int32_t *cell_xy,
                      double t)

@@ -1,0 +1,735 @@
+/*
+ * edmd_host.c -- sequential C host of the B200 hot path.
+ *
+ * A from-scratch hard-disk event-driven MD driver that keeps what a user of
+ * the reference touches -- its command line (-N/--number, -p/--phi, -x/--xs,
+ * -q/--sizeratio, -a/--aspect, -t/--time, -D/--dt, -o/--dtimeThermo,
+ * -T/--temperature, -v/--version = seed; src/EDMD.c:750-792), its event API (a
+ * calendar of bucketed lists feeding a binary search tree with a cached
+ * minimum, two event slots per particle; src/EDMD.c:2144-2327, 1923-1934) and
+ * its ovito-readable LAMMPS text dump (src/EDMD.c:5052-5134) -- and calls CUDA
+ * through the C ABI of include/edmd_cuda.h wherever the reference loops over
+ * ALL particles:
+ *     setup sweep          (eventListInit,  src/EDMD.c:2007-2012)
+ *     thermostat tick      (addNoise,       src/EDMD.c:4828-4923)
+ *     psi6 columns of a frame (saveTXT,     src/EDMD.c:5057-5060)
+ *     g(r) at thermo time  (save_pcf,       src/EDMD.c:5636-5637)
+ * The per-event predictions (1-2 particles, asynchronous positions, lat2 != 0)
+ * stay here on the host next to the calendar, as in the reference
+ * (doTheCollisionNormal src/EDMD.c:3542, doTheCrossing :2501).
+ *
+ * Unlike the reference's CLI build (where `noise` is a compile-time 0,
+ * src/EDMD.c:289) the thermostat is a run-time switch: --noise 2 --dtnoise dt.
+ * Start configuration: --init grow (default, the reference's default start,
+ * src/EDMD.c:1690-1829: random points of radius 0 grown Lubachevsky-Stillinger
+ * style at rate vr until t = 1/vr, then stopGrow :4740-4779; the setup sweep is
+ * then a GROW-mode GPU sweep and stopGrow a NORMAL-mode one) or --init lattice
+ * (jittered triangular lattice, no growth phase; needs phi below close packing
+ * of the large disks).
+ * --verify checks the first GPU sweep against this file's own per-particle
+ * predictors (bit-exact) -- a check, not a fallback: without the CUDA library
+ * nothing runs.
+ */
+#define _GNU_SOURCE
+#include <getopt.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+
+#include "edmd_cuda.h"
+
+#define NEVER EDMD_NEVER
+enum { EV_CELLCROSS = 0, EV_COLLISION = 1, EV_SCREENSHOT = 2, EV_THERMO = 3, EV_NOISE = 4, EV_GROWSTOP = 9 };
+
+/* ---- options (names and defaults of src/EDMD.c:80-260 where they exist) --- */
+static int N = 500;
+static double phi = 0.38, sizeratio = 0.4, fractionSmallN = 0.3, aspectRatio = 1.0;
+static double tmax = 4000, dtime = 100, dtimeThermo = 100, firstScreen = 1, firstThermo = 1;
+static double T = 1.0, dtnoise = 0.5;
+static int noise = 0, seed = 1, boopThermo = 0, pcfThermo = 0, verify = 0, quiet = 0;
+static int init_grow = 1, growing = 0;
+static double vr = 0.1;
+static const char *outdir = "dump";
+
+/* ---- state ------------------------------------------------------------------ */
+static double Lx, Ly, halfLx, halfLy, csx, csy;
+static int Nx, Ny;
+static double t = 0;
+static double *px, *py, *pvx, *pvy, *prad, *pt;   /* pinned SoA (pt = local time) */
+static double *pvr;                               /* growth rates (growth phase) */
+static int32_t *pcell;                            /* interleaved X,Y */
+static unsigned long *pcoll;
+static int *ptype, *cnext, *cprev, *chead;
+static unsigned long ncol = 0, ncross = 0;
+static double collTermX = 0, collTermY = 0, lastThermoT = 0;
+
+typedef struct node {
+	struct node *lft, *rgt, *top;
+	int i, j, q, type;
+	double t;
+	unsigned long collActual;
+} node;
+static node *events, *root, *treeMin, **paul;
+static int paulN, actualPaul = 0;
+static double paulTime = 0, dtPaul;
+
+static edmd_ctx *gpu;
+static double *g_tcross, *g_tcoll;
+static uint8_t *g_dir, *g_type;
+static int32_t *g_partner;
+static double gpu_sweep_seconds = 0;
+static int gpu_sweeps = 0;
+
+static double now(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void die_gpu(int rc, const char *what)
+{
+	fprintf(stderr, "edmd_host: %s failed (%d): %s\n", what, rc, gpu ? edmd_cuda_last_error(gpu) : "no context");
+	exit(2);
+}
+
+/* ---- calendar: bucketed lists + BST (same contract as src/EDMD.c:2144-2327) -- */
+static void tree_add(node *e)
+{
+	node *w = root;
+	for (;;) {
+		if (e->t < w->t) {
+			if (!w->lft) { w->lft = e; break; }
+			w = w->lft;
+		} else {
+			if (!w->rgt) { w->rgt = e; break; }
+			w = w->rgt;
+		}
+	}
+	e->lft = e->rgt = NULL;
+	e->top = w;
+	if (!treeMin || e->t < treeMin->t) treeMin = e;
+}
+
+static void tree_remove(node *e)
+{
+	node *top = e->top, *n;
+	if (e == treeMin) {
+		if (e->rgt) {
+			treeMin = e->rgt;
+			while (treeMin->lft) treeMin = treeMin->lft;
+		} else
+			treeMin = (top == root) ? NULL : top;
+	}
+	if (!e->lft && !e->rgt)
+		n = NULL;
+	else if (!e->lft) { n = e->rgt; n->top = top; }
+	else if (!e->rgt) { n = e->lft; n->top = top; }
+	else {
+		n = e->rgt;
+		while (n->lft) n = n->lft;
+		if (n->top != e) {
+			n->top->lft = n->rgt;
+			if (n->rgt) n->rgt->top = n->top;
+			e->rgt->top = n;
+			n->rgt = e->rgt;
+		}
+		e->lft->top = n;
+		n->lft = e->lft;
+		n->top = top;
+	}
+	if (top->lft == e) top->lft = n;
+	else top->rgt = n;
+}
+
+static void queue_add(node *e)
+{
+	double dt = e->t - paulTime;
+	if (dt < dtPaul) {
+		e->q = actualPaul;
+		tree_add(e);
+		return;
+	}
+	int k;
+	if (dt >= dtPaul * paulN)
+		k = paulN; /* overflow bucket: "never" events live here */
+	else {
+		k = actualPaul + (int)(dt / dtPaul);
+		if (k >= paulN) k -= paulN;
+	}
+	e->q = k;
+	e->lft = NULL;
+	e->rgt = paul[k];
+	if (e->rgt) e->rgt->lft = e;
+	paul[k] = e;
+}
+
+static void queue_remove(node *e)
+{
+	if (e->q != actualPaul) {
+		if (e->rgt) e->rgt->lft = e->lft;
+		if (e->lft) e->lft->rgt = e->rgt;
+		else paul[e->q] = e->rgt;
+	} else
+		tree_remove(e);
+}
+
+static node *queue_next(void)
+{
+	while (!treeMin) {
+		actualPaul++;
+		paulTime += dtPaul;
+		if (actualPaul == paulN) {
+			actualPaul = 0;
+			node *p = paul[paulN];
+			paul[paulN] = NULL;
+			while (p) { node *nx = p->rgt; queue_add(p); p = nx; }
+		}
+		node *p = paul[actualPaul];
+		while (p) { node *nx = p->rgt; tree_add(p); p = nx; }
+		paul[actualPaul] = NULL;
+	}
+	return treeMin;
+}
+
+/* ---- geometry helpers (PBC :5896, PBCpost :5948, free flight :4954) ---------- */
+static inline double min_image(double d, double half, double len)
+{
+	if (d >= half) return d - len;
+	else if (d < -half) return d + len;
+	return d;
+}
+
+static inline void free_fly(int i)
+{
+	double dt = t - pt[i];
+	pt[i] = t;
+	px[i] += dt * pvx[i];
+	py[i] += dt * pvy[i];
+	if (growing) prad[i] += dt * pvr[i]; /* freeFlyGrow :4992-5007 */
+	if (px[i] < 0) px[i] += Lx; else if (px[i] >= Lx) px[i] -= Lx;
+	if (py[i] < 0) py[i] += Ly; else if (py[i] >= Ly) py[i] -= Ly;
+}
+
+static inline int wrapc(int a, int n) { return a < 0 ? a + n : (a >= n ? a - n : a); }
+
+static void cell_insert(int i)
+{
+	int c = pcell[2 * i + 1] * Nx + pcell[2 * i];
+	cprev[i] = -1;
+	cnext[i] = chead[c];
+	if (chead[c] >= 0) cprev[chead[c]] = i;
+	chead[c] = i;
+}
+
+static void cell_remove(int i)
+{
+	int c = pcell[2 * i + 1] * Nx + pcell[2 * i];
+	if (cprev[i] < 0) chead[c] = cnext[i];
+	else cnext[cprev[i]] = cnext[i];
+	if (cnext[i] >= 0) cprev[cnext[i]] = cprev[i];
+}
+
+/* ---- per-event predictors (asynchronous form, lat2 = t - t_j) ---------------- */
+static void predict_crossing(int i, double *tc, int *dir)
+{
+	double tx, ty;
+	int xx, yy;
+	int X = pcell[2 * i], Y = pcell[2 * i + 1];
+	if (pvx[i] < 0) { tx = min_image(X * csx - px[i], halfLx, Lx) / pvx[i]; xx = 1; }
+	else { tx = min_image((1 + X) * csx - px[i], halfLx, Lx) / pvx[i]; xx = 2; }
+	if (pvy[i] < 0) { ty = min_image(Y * csy - py[i], halfLy, Ly) / pvy[i]; yy = 3; }
+	else { ty = min_image((1 + Y) * csy - py[i], halfLy, Ly) / pvy[i]; yy = 4; }
+	if (tx < ty) { *tc = t + tx; *dir = xx; }
+	else { *tc = t + ty; *dir = yy; }
+}
+
+static void overlap_abort(int i, int j)
+{
+	fprintf(stderr, "\nERROR: Overlaps detected during SIMULATION between particle %d and particle %d !\n", i, j);
+	exit(3);
+}
+
+/* collisionTimeGrow, src/EDMD.c:2598-2659 */
+static double pair_time_grow(int i, int p2)
+{
+	double lat2 = t - pt[p2];
+	double dvx = pvx[p2] - pvx[i], dvy = pvy[p2] - pvy[i], dvr = pvr[i] + pvr[p2];
+	double dx = (px[p2] + lat2 * pvx[p2]) - px[i], dy = (py[p2] + lat2 * pvy[p2]) - py[i];
+	double dr = sqrt(4 * prad[i] * (prad[p2] + lat2 * pvr[p2]));
+	dx = min_image(dx, halfLx, Lx);
+	dy = min_image(dy, halfLy, Ly);
+	double b = dx * dvx + dy * dvy - dvr * dr;
+	double v2 = dvx * dvx + dvy * dvy, d2 = dx * dx + dy * dy;
+	double a = v2 - dvr * dvr;
+	double det = b * b - a * (d2 - dr * dr);
+	if (det < 0) return NEVER;
+	double plus = (-b + sqrt(det)) / a, minus = (-b - sqrt(det)) / a;
+	if (((minus > 0) && (plus > 0) && (minus < plus)) || ((minus > 0) && (plus < 0))) return minus;
+	else if (((minus > 0) && (plus > 0.000000001) && (plus < minus)) || ((minus < 0) && (plus > 0.000000001))) return plus;
+	if (d2 - dr * dr < -0.01) {
+		fprintf(stderr, "\nERROR: Overlaps detected during GROWTH between particle %d and particle %d !\n", i, p2);
+		exit(3);
+	}
+	return NEVER;
+}
+
+static void predict_collision(int i, double *tcoll, int *partner)
+{
+	double best = growing ? 10000000 : NEVER;
+	int bj = 0;
+	int X = pcell[2 * i], Y = pcell[2 * i + 1];
+	for (int j = -1; j <= 1; j++)
+		for (int k = -1; k <= 1; k++) {
+			int c = wrapc(Y + j, Ny) * Nx + wrapc(X + k, Nx);
+			for (int p2 = chead[c]; p2 >= 0; p2 = cnext[p2]) {
+				if (p2 == i) continue;
+				if (growing) {
+					double dtg = pair_time_grow(i, p2);
+					if (best > dtg) { best = dtg; bj = p2; }
+					continue;
+				}
+				double lat2 = t - pt[p2];
+				double dvx = pvx[p2] - pvx[i], dvy = pvy[p2] - pvy[i];
+				double dx = min_image((px[p2] + lat2 * pvx[p2]) - px[i], halfLx, Lx);
+				double dy = min_image((py[p2] + lat2 * pvy[p2]) - py[i], halfLy, Ly);
+				double b = dx * dvx + dy * dvy;
+				if (b > 0) continue;
+				double v2 = dvx * dvx + dvy * dvy;
+				double cc = dx * dx + dy * dy - (4 * prad[i] * prad[p2]);
+				double det = b * b - v2 * cc;
+				if (cc < -0.01) overlap_abort(i, p2);
+				if (det < 0) continue;
+				double dt = (-b - sqrt(det)) / v2;
+				if (best > dt) { best = dt; bj = p2; }
+			}
+		}
+	*tcoll = t + best;
+	*partner = bj;
+}
+
+static void schedule_crossing(int i)
+{
+	double tc; int d;
+	predict_crossing(i, &tc, &d);
+	node *e = &events[i];
+	e->j = d; e->type = EV_CELLCROSS; e->t = tc;
+	queue_add(e);
+}
+
+static void schedule_collision(int i)
+{
+	double tc; int j;
+	predict_collision(i, &tc, &j);
+	node *e = &events[N + i];
+	e->j = j; e->type = EV_COLLISION; e->t = tc; e->collActual = pcoll[j];
+	queue_add(e);
+}
+
+static void schedule_special(int slot, int type, double when)
+{
+	node *e = &events[2 * N + slot];
+	e->type = type; e->t = when; e->j = 0; e->i = -1;
+	queue_add(e);
+}
+
+/* ---- the whole-system sweep on the GPU -------------------------------------- */
+static void gpu_upload(void)
+{
+	int rc = edmd_cuda_upload(gpu, px, py, pvx, pvy, prad, pcell, t);
+	if (rc) die_gpu(rc, "edmd_cuda_upload");
+}
+
+/* every particle must already be at time t.  remove_first: events are in the
+ * calendar (thermostat tick, stopGrow) or not (setup). */
+static void gpu_predict_all(int remove_first)
+{
+	double t0 = now();
+	int32_t ov[2];
+	gpu_upload();
+	int rc = edmd_cuda_predict_all(gpu, growing ? EDMD_MODE_GROW : EDMD_MODE_NORMAL, growing ? pvr : NULL,
+	                               g_tcross, g_dir, g_tcoll, g_partner, g_type, ov);
+	if (rc == EDMD_EOVERLAP) overlap_abort(ov[0], ov[1]);
+	if (rc) die_gpu(rc, "edmd_cuda_predict_all");
+	gpu_sweep_seconds += now() - t0;
+	gpu_sweeps++;
+	/* sequential calendar ingest in the reference's order: crossing, then collision */
+	for (int i = 0; i < N; i++) {
+		node *e = &events[i];
+		if (remove_first) queue_remove(e);
+		e->j = g_dir[i]; e->type = EV_CELLCROSS; e->t = g_tcross[i];
+		queue_add(e);
+		e = &events[N + i];
+		if (remove_first) queue_remove(e);
+		e->j = g_partner[i]; e->type = EV_COLLISION; e->t = g_tcoll[i];
+		e->collActual = pcoll[g_partner[i]];
+		queue_add(e);
+	}
+}
+
+static void verify_first_sweep(void)
+{
+	long bad = 0;
+	for (int i = 0; i < N; i++) {
+		double tc, tl; int d, j;
+		predict_crossing(i, &tc, &d);
+		predict_collision(i, &tl, &j);
+		if (tc != g_tcross[i] || d != g_dir[i] || tl != g_tcoll[i] || j != g_partner[i]) {
+			if (bad < 5)
+				fprintf(stderr, "verify: particle %d host (%.17g,%d,%.17g,%d) gpu (%.17g,%d,%.17g,%d)\n", i, tc, d,
+				        tl, j, g_tcross[i], g_dir[i], g_tcoll[i], g_partner[i]);
+			bad++;
+		}
+	}
+	printf("verify: first GPU sweep vs host per-particle predictors: %ld mismatches of %d (bit-exact compare)\n", bad, N);
+	if (bad) exit(5);
+}
+
+/* ---- event handlers ---------------------------------------------------------- */
+static void do_collision(node *ev)
+{
+	int i = ev->i, j = ev->j;
+	free_fly(i);
+	if (ev->collActual != pcoll[j]) { /* stale partner: re-predict i only (:3553-3556) */
+		schedule_collision(i);
+		return;
+	}
+	ncol++;
+	free_fly(j);
+	pcoll[i]++;
+	pcoll[j]++;
+	double dx = min_image(px[j] - px[i], halfLx, Lx), dy = min_image(py[j] - py[i], halfLy, Ly);
+	double dvx = pvx[j] - pvx[i], dvy = pvy[j] - pvy[i];
+	if (growing) {
+		/* doTheCollisionGrow, src/EDMD.c:3465-3540 (unit masses, res = 1) */
+		double dist = sqrt(dx * dx + dy * dy), dxr = dx / dist, dyr = dy / dist;
+		double k = dxr * dvx + dyr * dvy - (pvr[i] + pvr[j]);
+		pvx[i] += k * dxr; pvy[i] += k * dyr;
+		pvx[j] -= k * dxr; pvy[j] -= k * dyr;
+	} else {
+		/* elastic, unit masses: invMass*(1+res) = 1 (:3583-3605, 3802-3827) */
+		double f = (dx * dvx + dy * dvy) / (4 * prad[i] * prad[j]);
+		collTermX += f * dx * dx;
+		collTermY += f * dy * dy;
+		pvx[i] += f * dx; pvy[i] += f * dy;
+		pvx[j] -= f * dx; pvy[j] -= f * dy;
+	}
+	queue_remove(&events[i]);
+	queue_remove(&events[j]);
+	schedule_crossing(i);
+	schedule_crossing(j);
+	queue_remove(&events[N + j]);
+	schedule_collision(i);
+	schedule_collision(j);
+}
+
+static void do_crossing(node *ev)
+{
+	int i = ev->i;
+	ncross++;
+	free_fly(i);
+	cell_remove(i);
+	switch (ev->j) {
+	case 1: pcell[2 * i] = pcell[2 * i] == 0 ? Nx - 1 : pcell[2 * i] - 1; break;
+	case 2: pcell[2 * i] = pcell[2 * i] == Nx - 1 ? 0 : pcell[2 * i] + 1; break;
+	case 3: pcell[2 * i + 1] = pcell[2 * i + 1] == 0 ? Ny - 1 : pcell[2 * i + 1] - 1; break;
+	default: pcell[2 * i + 1] = pcell[2 * i + 1] == Ny - 1 ? 0 : pcell[2 * i + 1] + 1; break;
+	}
+	cell_insert(i);
+	schedule_crossing(i);
+	queue_remove(&events[N + i]);
+	schedule_collision(i);
+}
+
+static double kinetic_energy(void)
+{
+	double E = 0;
+	for (int i = 0; i < N; i++) E += 0.5 * (pvx[i] * pvx[i] + pvy[i] * pvy[i]);
+	return E;
+}
+
+static double kinetic_energy(void);
+
+/* stopGrow, src/EDMD.c:4740-4779 */
+static void do_growstop(void)
+{
+	for (int i = 0; i < N; i++) { free_fly(i); pcoll[i] = 0; }
+	ncol = ncross = 0;
+	growing = 0;
+	/* normalizePhysicalQ :5723-5764: remove the COM momentum, rescale to E/N = T */
+	double sx = 0, sy = 0;
+	for (int i = 0; i < N; i++) { sx += pvx[i]; sy += pvy[i]; }
+	for (int i = 0; i < N; i++) { pvx[i] -= sx / N; pvy[i] -= sy / N; }
+	double s = sqrt(kinetic_energy() / N / T);
+	for (int i = 0; i < N; i++) { pvx[i] /= s; pvy[i] /= s; pcoll[i]++; }
+	collTermX = collTermY = 0;
+	lastThermoT = t;
+	gpu_predict_all(1);
+}
+
+/* thermostat tick = addNoise with noise == 2 (velocity rescale, :4899-4902) */
+static void do_noise(void)
+{
+	double E = kinetic_energy();
+	double s = sqrt(E / N / T);
+	for (int i = 0; i < N; i++) {
+		free_fly(i);
+		pcoll[i]++;
+		pvx[i] /= s;
+		pvy[i] /= s;
+	}
+	gpu_predict_all(1);
+	schedule_special(2, EV_NOISE, t + dtnoise);
+}
+
+static FILE *fdump, *fthermo, *fpcf;
+
+static void do_screenshot(void)
+{
+	for (int i = 0; i < N; i++) free_fly(i);
+	schedule_special(1, EV_SCREENSHOT, t + dtime);
+	double *q5 = NULL, *q6 = NULL, *q7 = NULL, *qa = NULL;
+	int32_t *nb = NULL;
+	if (boopThermo) {
+		q5 = malloc(sizeof(double) * N); q6 = malloc(sizeof(double) * N); q7 = malloc(sizeof(double) * N);
+		qa = malloc(sizeof(double) * N); nb = malloc(sizeof(int32_t) * N);
+		gpu_upload();
+		int rc = edmd_cuda_boop_cutoff(gpu, 2.5, q5, q6, q7, qa, nb, NULL);
+		if (rc) die_gpu(rc, "edmd_cuda_boop_cutoff");
+	}
+	/* byte format of saveTXT, src/EDMD.c:5052-5069, row :5124-5134 */
+	fprintf(fdump, "ITEM: TIMESTEP\n%lf\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n0 %lf\n0 %lf\n0 0\nITEM: ATOMS id type x y vx vy radius m coll",
+	        t, N, Lx, Ly);
+	if (boopThermo) fprintf(fdump, " q5 q6 q7 argq6 neighbors");
+	fprintf(fdump, "\n");
+	for (int i = 0; i < N; i++) {
+		fprintf(fdump, "%d %d %.3lf %lf %lf %lf %lf %lf %d", i, ptype[i], px[i], py[i], pvx[i], pvy[i], prad[i], 1.0, ptype[i]);
+		if (boopThermo) fprintf(fdump, " %.2lf %.2lf %.2lf %.2lf %d", q5[i], q6[i], q7[i], qa[i], nb[i]);
+		fprintf(fdump, "\n");
+	}
+	fflush(fdump);
+	free(q5); free(q6); free(q7); free(qa); free(nb);
+	if (!quiet) printf("t = %-10.3lf collisions = %-12lu E/N = %.6lf\n", t, ncol, kinetic_energy() / N);
+}
+
+static double last_pressure = 0;
+
+static void do_thermo(void)
+{
+	schedule_special(3, EV_THERMO, t + dtimeThermo);
+	double E = kinetic_energy();
+	double area = Lx * Ly, dtm = t - lastThermoT;
+	/* virial pressure, src/EDMD.c:5324-5328 */
+	double p = dtm > 0 ? (-1 / dtm) * (collTermX + collTermY) / (2 * area) + E / area : E / area;
+	last_pressure = p;
+	collTermX = collTermY = 0;
+	lastThermoT = t;
+	fprintf(fthermo, "%lf %lu %.10lf %.10lf\n", t, ncol, E / N, p);
+	fflush(fthermo);
+	if (pcfThermo) {
+		for (int i = 0; i < N; i++) free_fly(i);
+		gpu_upload();
+		double dr = 0.1, max_r = (Lx < Ly ? Lx : Ly) / 2;
+		int nbins = 0;
+		edmd_cuda_pcf(gpu, dr, max_r, NULL, NULL, &nbins);
+		uint64_t *cnt = malloc(sizeof(uint64_t) * (nbins > 0 ? nbins : 1));
+		double *g = malloc(sizeof(double) * (nbins > 0 ? nbins : 1));
+		int rc = edmd_cuda_pcf(gpu, dr, max_r, cnt, g, &nbins);
+		if (rc) die_gpu(rc, "edmd_cuda_pcf");
+		for (int b = 0; b < nbins; b++) fprintf(fpcf, "%lf %lf %lf\n", t, (b + 0.5) * dr, g[b]);
+		fflush(fpcf);
+		free(cnt); free(g);
+	}
+}
+
+/* ---- set-up ------------------------------------------------------------------ */
+static uint64_t rng_state;
+static double urand(void)
+{
+	uint64_t z = (rng_state += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	z ^= z >> 31;
+	return (z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+static void *pinned(size_t bytes)
+{
+	void *p = NULL;
+	int rc = edmd_cuda_host_alloc(&p, bytes);
+	if (rc) { fprintf(stderr, "edmd_host: pinned allocation failed (%d)\n", rc); exit(2); }
+	return p;
+}
+
+static void particles_init(void)
+{
+	/* box from N, phi as constantInit does (src/EDMD.c:1121-1152) */
+	double r2 = 1 + fractionSmallN * (sizeratio * sizeratio - 1);
+	/* jittered triangular lattice in a near-square box (Hex formulas :1026-1033) */
+	int ny = (int)floor(sqrt((double)N));
+	ny -= ny % 2;
+	if (ny < 2) ny = 2;
+	int nx = N / ny;
+	N = nx * ny;
+	Ly = sqrt(sqrt(3.0) / 2.0 * ny / nx * M_PI * N / phi * r2) * sqrt(aspectRatio);
+	Lx = 2.0 / sqrt(3.0) * nx / ny * Ly / aspectRatio;
+	double dx = Lx / nx, dy = Ly / ny;
+	if (!init_grow && dx <= 2.0) { fprintf(stderr, "edmd_host: phi too large for --init lattice\n"); exit(1); }
+	/* optimizeGrowConstant, src/EDMD.c:5766-5799 */
+	vr = phi < 0.8 ? 0.1 : 0.1 * pow(0.8 / phi, 30);
+	if (phi > 0.7) vr /= 8;
+	px = pinned(sizeof(double) * N); py = pinned(sizeof(double) * N);
+	pvx = pinned(sizeof(double) * N); pvy = pinned(sizeof(double) * N);
+	prad = pinned(sizeof(double) * N); pcell = pinned(sizeof(int32_t) * 2 * N);
+	pt = malloc(sizeof(double) * N);
+	pvr = pinned(sizeof(double) * N);
+	pcoll = calloc(N, sizeof(unsigned long));
+	ptype = malloc(sizeof(int) * N);
+	double amp = 0.3 * (dx - 2.0), sx = 0, sy = 0;
+	for (int i = 0; i < N; i++) {
+		int a = i % nx, b = i / nx;
+		px[i] = a * dx + (b % 2) * dx / 2 + amp * (2 * urand() - 1);
+		py[i] = b * dy + amp * (2 * urand() - 1);
+		if (px[i] < 0) px[i] += Lx; else if (px[i] >= Lx) px[i] -= Lx;
+		if (py[i] < 0) py[i] += Ly; else if (py[i] >= Ly) py[i] -= Ly;
+		double u1 = 1 - urand(), u2 = urand(), rr = sqrt(-2 * log(u1));
+		pvx[i] = rr * cos(2 * M_PI * u2);
+		pvy[i] = rr * sin(2 * M_PI * u2);
+		sx += pvx[i]; sy += pvy[i];
+		ptype[i] = urand() < fractionSmallN ? 0 : 1;
+		prad[i] = ptype[i] ? 1.0 : sizeratio;
+		pvr[i] = 0;
+		pt[i] = 0;
+		if (init_grow) { /* random points, radius 0, growing to the target radius at t = 1/vr */
+			px[i] = urand() * Lx;
+			py[i] = urand() * Ly;
+			pvr[i] = vr * prad[i];
+			prad[i] = 0;
+		}
+	}
+	for (int i = 0; i < N; i++) { pvx[i] -= sx / N; pvy[i] -= sy / N; }
+	/* growth runs at E/N = 0.05 (EinitGrow :1692); stopGrow rescales to T */
+	double s = sqrt(kinetic_energy() / N / (init_grow ? 0.05 : T));
+	for (int i = 0; i < N; i++) { pvx[i] /= s; pvy[i] /= s; }
+	growing = init_grow;
+}
+
+int main(int argc, char **argv)
+{
+	static struct option longopt[] = {
+		{"number", required_argument, NULL, 'N'}, {"phi", required_argument, NULL, 'p'},
+		{"xs", required_argument, NULL, 'x'}, {"sizeratio", required_argument, NULL, 'q'},
+		{"aspect", required_argument, NULL, 'a'}, {"time", required_argument, NULL, 't'},
+		{"dt", required_argument, NULL, 'D'}, {"dtimeThermo", required_argument, NULL, 'o'},
+		{"temperature", required_argument, NULL, 'T'}, {"version", required_argument, NULL, 'v'},
+		{"noise", required_argument, NULL, 1001}, {"dtnoise", required_argument, NULL, 1002},
+		{"boop", no_argument, NULL, 1003}, {"pcf", no_argument, NULL, 1004},
+		{"verify", no_argument, NULL, 1005}, {"outdir", required_argument, NULL, 1006},
+		{"quiet", no_argument, NULL, 1007}, {"device", required_argument, NULL, 1008},
+		{"init", required_argument, NULL, 1009},
+		{NULL, 0, NULL, 0}};
+	int c, device = 0;
+	while ((c = getopt_long(argc, argv, "N:p:x:q:a:t:D:o:T:v:", longopt, NULL)) != -1) {
+		switch (c) {
+		case 'N': N = atoi(optarg); break;
+		case 'p': phi = atof(optarg); break;
+		case 'x': fractionSmallN = atof(optarg); break;
+		case 'q': sizeratio = atof(optarg); break;
+		case 'a': aspectRatio = atof(optarg); break;
+		case 't': tmax = atof(optarg); break;
+		case 'D': dtime = atof(optarg); break;
+		case 'o': dtimeThermo = atof(optarg); break;
+		case 'T': T = atof(optarg); break;
+		case 'v': seed = atoi(optarg); break;
+		case 1001: noise = atoi(optarg); break;
+		case 1002: dtnoise = atof(optarg); break;
+		case 1003: boopThermo = 2; break;
+		case 1004: pcfThermo = 1; break;
+		case 1005: verify = 1; break;
+		case 1006: outdir = optarg; break;
+		case 1007: quiet = 1; break;
+		case 1008: device = atoi(optarg); break;
+		case 1009: init_grow = strcmp(optarg, "lattice") != 0; break;
+		default: fprintf(stderr, "usage: edmd_host -N n --phi f [-x xs -q ratio -a aspect -t tmax -D dt -o dtThermo -T temp -v seed]\n"
+		                         "       [--init grow|lattice] [--noise 2 --dtnoise dt] [--boop] [--pcf] [--verify] [--outdir dir] [--quiet]\n");
+			return 2;
+		}
+	}
+	if (noise != 0 && noise != 2) { fprintf(stderr, "edmd_host: only --noise 0 (none) and 2 (velocity rescale) are implemented\n"); return 2; }
+	rng_state = 0x1234567ull * (uint64_t)(seed + 1);
+
+	/* the pinned allocator needs the CUDA runtime: touch the library first */
+	particles_init();
+	int rc = edmd_cuda_create(device, N, Lx, Ly, &gpu);
+	if (rc) die_gpu(rc, "edmd_cuda_create");
+	edmd_box box;
+	edmd_cuda_get_box(gpu, &box);
+	Nx = box.nxcells; Ny = box.nycells; csx = box.cellx_size; csy = box.celly_size;
+	halfLx = box.half_lx; halfLy = box.half_ly;
+	dtPaul = box.dt_paul;
+	paulN = N;
+
+	chead = malloc(sizeof(int) * Nx * Ny); cnext = malloc(sizeof(int) * N); cprev = malloc(sizeof(int) * N);
+	for (int k = 0; k < Nx * Ny; k++) chead[k] = -1;
+	for (int i = 0; i < N; i++) {
+		pcell[2 * i] = (int)(px[i] * box.cellx_fac);     /* coordToCell :2098-2107 */
+		pcell[2 * i + 1] = (int)(py[i] * box.celly_fac);
+		cell_insert(i);
+	}
+	events = calloc(2 * N + 10, sizeof(node));
+	paul = calloc(paulN + 1, sizeof(node *));
+	root = &events[2 * N];
+	root->t = NEVER + 1;
+	for (int i = 0; i < N; i++) events[i].i = events[N + i].i = i;
+	g_tcross = pinned(sizeof(double) * N); g_tcoll = pinned(sizeof(double) * N);
+	g_dir = pinned(N); g_type = pinned(N); g_partner = pinned(sizeof(int32_t) * N);
+
+	mkdir(outdir, 0777);
+	char name[512];
+	snprintf(name, sizeof name, "%s/N_%dphi_%.4f.dump", outdir, N, phi); fdump = fopen(name, "w");
+	snprintf(name, sizeof name, "%s/N_%dphi_%.4f.thermo", outdir, N, phi); fthermo = fopen(name, "w");
+	if (pcfThermo) { snprintf(name, sizeof name, "%s/N_%dphi_%.4f.pcf", outdir, N, phi); fpcf = fopen(name, "w"); }
+	if (!fdump || !fthermo || (pcfThermo && !fpcf)) { perror("edmd_host: output files"); return 1; }
+	fprintf(fthermo, "t Ncol E p\n");
+
+	if (!quiet)
+		printf("edmd_host: N = %d  phi = %g  Lx = %.3f  Ly = %.3f  cells = %d x %d  noise = %d\n", N, phi, Lx, Ly, Nx, Ny, noise);
+	double wall0 = now();
+	double t_grow = init_grow ? 1 / vr : 0;   /* eventListInit shifts everything by 1/vr :1958-1976 */
+	tmax += t_grow;
+	schedule_special(3, EV_THERMO, t_grow + firstThermo);
+	schedule_special(1, EV_SCREENSHOT, t_grow + firstScreen);
+	if (noise) schedule_special(2, EV_NOISE, t_grow + dtnoise);
+	if (init_grow) schedule_special(5, EV_GROWSTOP, t_grow);
+	gpu_predict_all(0); /* setup sweep */
+	if (verify) verify_first_sweep();
+	double wall_setup = now() - wall0;
+
+	double wall1 = now();
+	while (t <= tmax) {
+		node *ev = queue_next();
+		t = ev->t;
+		queue_remove(ev);
+		switch (ev->type) {
+		case EV_COLLISION: do_collision(ev); break;
+		case EV_CELLCROSS: do_crossing(ev); break;
+		case EV_NOISE: do_noise(); break;
+		case EV_GROWSTOP: do_growstop(); wall1 = now(); break;
+		case EV_SCREENSHOT: do_screenshot(); break;
+		case EV_THERMO: do_thermo(); break;
+		}
+	}
+	double wall = now() - wall1;
+	printf("edmd_host: %lu collisions, %lu crossings in %.3f s => %.4g coll/s ; setup %.3f s ; "
+	       "%d GPU sweeps, %.3f ms each (upload + K0 + K1 + download) ; E/N = %.6f ; p = %.6f\n",
+	       ncol, ncross, wall, ncol / wall, wall_setup, gpu_sweeps,
+	       gpu_sweeps ? 1e3 * gpu_sweep_seconds / gpu_sweeps : 0.0, kinetic_energy() / N, last_pressure);
+	fclose(fdump); fclose(fthermo);
+	if (fpcf) fclose(fpcf);
+	edmd_cuda_destroy(gpu);
+	return 0;
+}

@@ -86,6 +86,12 @@ int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 #define EDMD_STAT_EXACT_RESCANS 1
 int edmd_cuda_get_stat(edmd_ctx *ctx, int stat, uint64_t *value);
 
+/* Page-locked host memory for the caller's particle arrays: uploads and
+ * downloads from/to such memory go straight to the copy engines (pageable
+ * memory is bounced through an internal pinned buffer instead). */
+int edmd_cuda_host_alloc(void **ptr, size_t bytes);
+void edmd_cuda_host_free(void *ptr);
+
 /* ---- state upload ---------------------------------------------------- */
 
 /* Synchronous snapshot: every particle already advanced to time t (the state

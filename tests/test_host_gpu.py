@@ -1,0 +1,63 @@
+"""End-to-end test of the C host (graphical-edmd_b200/host/edmd_host.c) driving
+the CUDA library: the first GPU sweep must equal the host's own per-particle
+predictors bit for bit (--verify), the thermostat must hold the temperature,
+the ovito dump must keep the reference's byte format, and -- chaotic dynamics
+can only be compared statistically -- the virial pressure must sit on the
+hard-disk equation of state."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+HOST = ROOT / "graphical-edmd_b200" / "host" / "edmd_host"
+
+
+def run_host(tmp_path, *args):
+    if not HOST.exists():
+        subprocess.run(["make", "-C", str(ROOT), "host"], check=True, capture_output=True)
+    r = subprocess.run([str(HOST), *map(str, args), "--outdir", str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def test_host_reference_cli_defaults_verify_and_dump(tmp_path):
+    # BASELINE configs[0] flavour: -N 2000 --phi 0.7, 30 % small disks, growth start
+    # (reference defaults); --verify then checks a GROW-mode sweep
+    out = run_host(tmp_path, "-N", 2000, "--phi", 0.7, "-t", 30, "-D", 10, "-o", 10, "--verify",
+                   "--noise", 2, "--dtnoise", 0.5, "--boop", "--pcf", "--quiet")
+    assert "0 mismatches" in out
+    m = re.search(r"(\d+) collisions.*?([\d.e+]+) coll/s.*?(\d+) GPU sweeps.*?E/N = ([\d.]+)", out)
+    assert m, out
+    ncol, rate, sweeps, e_n = int(m.group(1)), float(m.group(2)), int(m.group(3)), float(m.group(4))
+    assert ncol > 100000 and sweeps >= 60
+    assert abs(e_n - 1.0) < 1e-9          # velocity-rescale thermostat holds E/N = T
+    dump = next(tmp_path.glob("*.dump")).read_text().splitlines()
+    assert dump[0] == "ITEM: TIMESTEP"
+    assert dump[2] == "ITEM: NUMBER OF ATOMS" and dump[3] == "1980"
+    assert dump[8] == "ITEM: ATOMS id type x y vx vy radius m coll q5 q6 q7 argq6 neighbors"
+    assert len(dump[9].split()) == 14
+    pcf = np.loadtxt(next(tmp_path.glob("*.pcf")))
+    last = pcf[pcf[:, 0] == pcf[-1, 0]]
+    g_far = last[last[:, 1] > 15][:, 2]
+    assert abs(g_far.mean() - 1.0) < 0.05   # g(r) -> 1 at large r
+    assert last[last[:, 1] < 0.75][:, 2].max() == 0.0   # nothing inside the smallest contact (2*0.4)
+
+
+def test_host_pressure_on_hard_disk_equation_of_state(tmp_path):
+    """Monodisperse fluid at phi = 0.5: Z = p / (rho T) = 4.17 +- 3 % (Kolafa-Rottner /
+    Henderson 4.13); energy is conserved without thermostat."""
+    out = run_host(tmp_path, "-N", 4000, "--phi", 0.5, "-x", 0, "-t", 80, "-D", 1000, "-o", 10, "--quiet",
+                   "--init", "lattice")
+    th = np.loadtxt(next(tmp_path.glob("*.thermo")), skiprows=1)
+    th = th[th[:, 0] > 15]                  # drop the lattice melt
+    n = 3968                                # lattice rounding of 4000
+    lx_ly = np.pi * n / 0.5
+    z = th[:, 3].mean() / (n / lx_ly * 1.0)
+    assert abs(z - 4.17) / 4.17 < 0.03, z
+    assert np.abs(th[:, 2] - 1.0).max() < 1e-9

@@ -9,5 +9,5 @@ synthetic-input generator (``synth``) used by tests and ``bench.py``.
 The directory name contains a hyphen, so it is loaded by path -- see
 ``__graft_entry__.load_package()``.
 """
-from . import binding, synth  # noqa: F401
+from . import binding, slab, synth  # noqa: F401
 from .binding import EdmdCuda, EdmdError, load_library  # noqa: F401

@@ -32,7 +32,10 @@ SYMBOLS = [
     "edmd_cuda_download_state", "edmd_cuda_pcf", "edmd_cuda_boop_cutoff",
     "edmd_cuda_bench", "edmd_cuda_set_option", "edmd_cuda_get_stat",
     "edmd_cuda_host_alloc", "edmd_cuda_host_free",
+    "edmd_cuda_create_slab", "edmd_cuda_upload_owned", "edmd_cuda_halo_pack",
+    "edmd_cuda_halo_append", "edmd_cuda_get_counts", "edmd_cuda_pcf_device",
 ]
+HALO_RECORD_BYTES = 48
 
 
 class Box(C.Structure):
@@ -84,6 +87,14 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_boop_cutoff.argtypes = [vp, C.c_double, vp, vp, vp, vp, vp, vp]
     lib.edmd_cuda_bench.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double,
                                     C.c_int, C.c_int, C.c_size_t, vp, vp]
+    lib.edmd_cuda_create_slab.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                          C.POINTER(vp)]
+    lib.edmd_cuda_upload_owned.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_double]
+    lib.edmd_cuda_halo_pack.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
+    lib.edmd_cuda_halo_append.argtypes = [vp, C.c_int, vp, C.c_int]
+    lib.edmd_cuda_get_counts.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.edmd_cuda_pcf_device.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, vp,
+                                         C.POINTER(C.c_int)]
     lib.edmd_cuda_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.edmd_cuda_host_free.argtypes = [vp]
     lib.edmd_cuda_host_free.restype = None
@@ -111,11 +122,17 @@ def _f64(a, n):
 class EdmdCuda:
     """One context = one GPU + one particle system (edmd_cuda_create)."""
 
-    def __init__(self, n: int, lx: float, ly: float, device: int = 0):
+    def __init__(self, n: int, lx: float, ly: float, device: int = 0, slab_rows=None):
+        """slab_rows=(row_lo, row_hi): a slab context of capacity n (edmd_cuda_create_slab)."""
         self.lib = load_library()
         self.n = int(n)
+        self.slab_rows = slab_rows
         h = C.c_void_p()
-        rc = self.lib.edmd_cuda_create(device, self.n, lx, ly, C.byref(h))
+        if slab_rows is None:
+            rc = self.lib.edmd_cuda_create(device, self.n, lx, ly, C.byref(h))
+        else:
+            rc = self.lib.edmd_cuda_create_slab(device, self.n, lx, ly, int(slab_rows[0]),
+                                                int(slab_rows[1]), C.byref(h))
         self._h = h
         if rc != 0:
             msg = self.lib.edmd_cuda_last_error(h).decode() if h else "create failed"
@@ -172,6 +189,36 @@ class EdmdCuda:
             cells = np.ascontiguousarray(cell_xy, dtype=np.int32).reshape(-1)
             assert cells.size == 2 * n
         self._check(self.lib.edmd_cuda_upload(self._h, *[_ptr(a) for a in arrs], _ptr(cells), float(t)))
+
+    # ---- slab (multi-GPU) ----------------------------------------------------
+    def upload_owned(self, x, y, vx, vy, rad, cell_xy, global_id, t=0.0):
+        n = len(x)
+        arrs = [_f64(a, n) for a in (x, y, vx, vy, rad)]
+        cells = np.ascontiguousarray(cell_xy, dtype=np.int32).reshape(-1)
+        gid = np.ascontiguousarray(global_id, dtype=np.int32)
+        assert cells.size == 2 * n and gid.size == n
+        self._check(self.lib.edmd_cuda_upload_owned(self._h, n, *[_ptr(a) for a in arrs], _ptr(cells),
+                                                    _ptr(gid), float(t)))
+        self.n = n   # outputs cover the owned particles
+
+    def halo_pack(self, side: int, dev_ptr: int, capacity: int) -> int:
+        cnt = C.c_int(0)
+        self._check(self.lib.edmd_cuda_halo_pack(self._h, side, C.c_void_p(dev_ptr), capacity, C.byref(cnt)))
+        return cnt.value
+
+    def halo_append(self, side: int, dev_ptr: int, count: int):
+        self._check(self.lib.edmd_cuda_halo_append(self._h, side, C.c_void_p(dev_ptr), count))
+
+    def counts(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self._check(self.lib.edmd_cuda_get_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def pcf_device(self, xy_dev_ptr: int, n_total: int, dr, max_r, part, nparts, counts_dev_ptr: int) -> int:
+        nb = C.c_int(0)
+        self._check(self.lib.edmd_cuda_pcf_device(self._h, C.c_void_p(xy_dev_ptr), n_total, dr, max_r,
+                                                  part, nparts, C.c_void_p(counts_dev_ptr), C.byref(nb)))
+        return nb.value
 
     def upload_aos(self, records: np.ndarray, t=0.0, with_cells=True):
         """records: structured array with fields x,y,vx,vy,rad[,cell (2 x i4)]."""

@@ -117,6 +117,7 @@ k_boop_rows(const __grid_constant__ BoopArgs a)
                      BoopAcc acc;
                      if (status == 2) {  // segments do not fit: straight from global memory
                          const SRec p1 = make_rec(a.g.spos[rl.s], a.g.saux[rl.s]);
+                         if (p1.id >= a.g.n_owned) return;
 #pragma unroll
                          for (int j = 0; j < 3; j++)
                              boop_range<true>(a.b, a.rc2, p1, a.g.spos, a.g.saux, rl.lo[j], rl.hi[j], acc);
@@ -125,6 +126,7 @@ k_boop_rows(const __grid_constant__ BoopArgs a)
                      }
                      const bool fast = sane && (m.flags & kMetaInterior);
                      const SRec p1 = make_rec(buf.pos[1][rl.self], buf.aux[1][rl.self]);
+                     if (p1.id >= a.g.n_owned) return;
 #pragma unroll
                      for (int j = 0; j < 3; j++) {
                          if (fast) boop_range<false>(a.b, a.rc2, p1, buf.pos[j], buf.aux[j], rl.lo[j], rl.hi[j], acc);
@@ -182,8 +184,8 @@ constexpr int kTile = 256;
 
 __global__ void __launch_bounds__(kPcfThreads)
 k_pcf(int n, edmd_dev_box b, double bin_width, double max_r, int num_bins,
-      const double4 *__restrict__ xv, unsigned long long *__restrict__ counts,
-      int use_smem_hist)
+      const double *__restrict__ xy, int stride, int part, int nparts,
+      unsigned long long *__restrict__ counts, int use_smem_hist)
 {
     extern __shared__ unsigned char smem_raw[];
     double2 *tile = reinterpret_cast<double2 *>(smem_raw);
@@ -193,7 +195,7 @@ k_pcf(int n, edmd_dev_box b, double bin_width, double max_r, int num_bins,
     }
     const int nt = (n + kTile - 1) / kTile;
     const long long npairs = (long long)nt * (nt + 1) / 2;
-    for (long long w = blockIdx.x; w < npairs; w += gridDim.x) {
+    for (long long w = (long long)blockIdx.x * nparts + part; w < npairs; w += (long long)gridDim.x * nparts) {
         // unrank w -> (ta, tb) with ta <= tb, row-major over the upper triangle
         // row ta starts at ta*nt - ta*(ta-1)/2
         double fn = (double)nt + 0.5;
@@ -204,15 +206,12 @@ k_pcf(int n, edmd_dev_box b, double bin_width, double max_r, int num_bins,
         __syncthreads();
         {
             int jj = (int)tb * kTile + threadIdx.x;
-            if (jj < n) {
-                double4 q = xv[jj];
-                tile[threadIdx.x] = make_double2(q.x, q.y);
-            }
+            if (jj < n) tile[threadIdx.x] = *reinterpret_cast<const double2 *>(xy + (size_t)jj * stride);
         }
         __syncthreads();
         const int i = (int)ta * kTile + threadIdx.x;
         if (i < n) {
-            const double4 pi = xv[i];
+            const double2 pi = *reinterpret_cast<const double2 *>(xy + (size_t)i * stride);
             const int jbase = (int)tb * kTile;
             const int jcount = min(kTile, n - jbase);
             const int jstart = (ta == tb) ? threadIdx.x + 1 : 0;
@@ -278,9 +277,11 @@ int edmd_launch_mean(edmd_ctx *c, const double *v, int n, double *out_dev)
     return 2;
 }
 
-int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins)
+// xy: positions as (x, y) pairs every `stride` doubles (the resident xv array: stride 4);
+// this launch handles tile pairs w = part (mod nparts) and ADDS into counts.
+int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
+                    int n, int part, int nparts, unsigned long long *counts)
 {
-    int n = c->n;
     if (n < 2 || num_bins <= 0) return 0;
     size_t tile_bytes = kTile * sizeof(double2);
     size_t hist_bytes = (size_t)num_bins * sizeof(unsigned int);
@@ -292,16 +293,15 @@ int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins)
                              227 * 1024);
         attr_set = true;
     }
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf, kPcfThreads, smem);
     if (per_sm < 1) per_sm = 1;
     long long nt = (n + kTile - 1) / kTile;
-    long long npairs = nt * (nt + 1) / 2;
-    long long grid = (long long)sms * per_sm;
+    long long npairs = (nt * (nt + 1) / 2 + nparts - 1) / nparts;
+    long long grid = (long long)(c->sm_count > 0 ? c->sm_count : 148) * per_sm;
     if (grid > npairs) grid = npairs;
-    k_pcf<<<(int)grid, kPcfThreads, smem, c->stream>>>(
-        n, c->dbox, dr, max_r, num_bins, c->xv, c->pcf_counts, use_smem);
+    if (grid < 1) grid = 1;
+    k_pcf<<<(int)grid, kPcfThreads, smem, c->stream>>>(n, c->dbox, dr, max_r, num_bins, xy, stride, part,
+                                                       nparts, counts, use_smem);
     return 1;
 }

@@ -27,7 +27,7 @@ constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------ pack --
 __global__ void __launch_bounds__(kThreads)
-k_pack(int n, edmd_dev_box b, int ps, const double *__restrict__ soa,
+k_pack(int n, size_t N, edmd_dev_box b, int ps, const double *__restrict__ soa,
        const int32_t *__restrict__ cell_xy, double4 *__restrict__ xv,
        double *__restrict__ rad, int32_t *__restrict__ cid,
        int32_t *__restrict__ flags)
@@ -35,7 +35,6 @@ k_pack(int n, edmd_dev_box b, int ps, const double *__restrict__ soa,
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int ghosts = 0, insane = 0;
     if (i < n) {
-        size_t N = (size_t)n;
         double x = soa[i], y = soa[N + i];
         xv[i] = make_double4(x, y, soa[2 * N + i], soa[3 * N + i]);
         rad[i] = soa[4 * N + i];
@@ -54,12 +53,18 @@ k_pack(int n, edmd_dev_box b, int ps, const double *__restrict__ soa,
             X = min(max(X, 0), b.nx - 1);
             Y = min(max(Y, 0), b.ny - 1);
         }
-        cid[i] = Y * ps + X + 1;
-        ghosts = (X == 0) + (X == b.nx - 1);
         // within one cell width of the filed cell?  (lets the sweep skip the
         // minimum-image test away from the periodic edges)
         insane = !(fabs(x - ((double)X + 0.5) * b.csx) <= 1.5 * b.csx) ||
                  !(fabs(y - ((double)Y + 0.5) * b.csy) <= 1.5 * b.csy);
+        int l = Y - b.yoff;   // row inside this context (slab: owned rows + halo)
+        if (l < 0) l += b.ny;
+        if (l >= b.nl) {
+            atomicOr(&flags[kFlagBadCell], 1);
+            l = b.nl - 1;
+        }
+        cid[i] = l * ps + X + 1;
+        ghosts = (X == 0) + (X == b.nx - 1);
     }
     ghosts = __reduce_add_sync(0xffffffffu, ghosts);
     insane = __reduce_add_sync(0xffffffffu, insane);
@@ -183,7 +188,7 @@ __device__ __forceinline__ int cell_of_slot(const int32_t *__restrict__ o, int p
 }
 
 __global__ void __launch_bounds__(kMetaThreads)
-k_chunkmeta(int nx, int ny, int ps, const int32_t *__restrict__ off,
+k_chunkmeta(int nx, int ny, int ps, int gny, int yoff, int slab, const int32_t *__restrict__ off,
             const int32_t *__restrict__ row_total, const int32_t *__restrict__ row_base,
             ChunkMeta *__restrict__ meta, int32_t *__restrict__ cstart, int max_chunks, int cap_rec,
             int cap_off)
@@ -201,6 +206,7 @@ k_chunkmeta(int nx, int ny, int ps, const int32_t *__restrict__ off,
         const int ca = max(cell_of_slot(o, ps, first), 1);
         const int cb = min(cell_of_slot(o, ps, last), nx);
         m.Y = ca <= cb ? Y : -1;   // only ghost entries: nothing to do
+        if (slab && (Y == 0 || Y == ny - 1)) m.Y = -1;   // halo rows are never predicted
         m.cfirst = ca;
         m.ncells = cb - ca + 1;
         m.row_end = rb + tot;
@@ -224,7 +230,9 @@ k_chunkmeta(int nx, int ny, int ps, const int32_t *__restrict__ off,
                 if (hi - lo > cap_rec) m.flags |= kMetaOverflow;
             }
             if (m.wlen > cap_off) m.flags |= kMetaOverflow;
-            if (nx >= 12 && ny >= 12 && Y >= 1 && Y <= ny - 2 && ca >= 2 && cb <= nx - 1)
+            int Yg = Y + yoff;   // global row: no periodic image in y away from rows 0 and gny-1
+            if (Yg >= gny) Yg -= gny;
+            if (nx >= 12 && gny >= 12 && Yg >= 1 && Yg <= gny - 2 && ca >= 2 && cb <= nx - 1)
                 m.flags |= kMetaInterior;
         } else {
 #pragma unroll
@@ -315,13 +323,79 @@ k_scatter(int n, int nx, int ps, const int32_t *__restrict__ cid,
 
 }  // namespace
 
-int edmd_launch_pack(edmd_ctx *c, bool have_cells)
+// pack `count` staged particles into the resident arrays starting at `first`
+int edmd_launch_pack(edmd_ctx *c, bool have_cells, int first, int count)
 {
-    int n = c->n;
+    if (count == 0) return 0;
+    k_pack<<<(count + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(
+        count, (size_t)c->n_cap, c->dbox, c->ps, c->in_soa, have_cells ? c->in_cell : nullptr,
+        c->xv + first, c->rad + first, c->cid + first, c->flags);
+    return 1;
+}
+
+// ---- slab halo: one 48-byte record per particle of a boundary row -------------
+struct __align__(16) HaloRec {
+    double x, y, vx, vy, rad;
+    int gid;
+    int cell;   // padded column 1..nx (the row is implied by which neighbour sent it)
+};
+
+namespace {
+__global__ void __launch_bounds__(kThreads)
+k_halo_pack(int n_owned, int ps, int row, const int32_t *__restrict__ cid,
+            const double4 *__restrict__ xv, const double *__restrict__ rad,
+            const int32_t *__restrict__ gid, HaloRec *__restrict__ out, int cap,
+            int32_t *__restrict__ count)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_owned) return;
+    const int pc = cid[i];
+    if (pc / ps != row) return;
+    const int k = atomicAdd(count, 1);
+    if (k >= cap) return;
+    const double4 p = xv[i];
+    HaloRec r;
+    r.x = p.x; r.y = p.y; r.vx = p.z; r.vy = p.w;
+    r.rad = rad[i];
+    r.gid = gid[i];
+    r.cell = pc - row * ps;   // padded column 1..nx
+    out[k] = r;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_halo_append(int count, int first, int ps, int row, const HaloRec *__restrict__ in,
+              double4 *__restrict__ xv, double *__restrict__ rad, int32_t *__restrict__ cid,
+              int32_t *__restrict__ gid, int nx, int32_t *__restrict__ flags)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const HaloRec r = in[k];
+    const int i = first + k;
+    xv[i] = make_double4(r.x, r.y, r.vx, r.vy);
+    rad[i] = r.rad;
+    gid[i] = r.gid;
+    cid[i] = row * ps + r.cell;
+    const int g = (r.cell == 1) + (r.cell == nx);
+    if (g) atomicAdd(&flags[kFlagGhosts], g);
+}
+}  // namespace
+
+// side 0: first owned row (local row 1) -> lower neighbour; side 1: last owned row -> upper neighbour
+int edmd_launch_halo_pack(edmd_ctx *c, int side, void *out, int cap, int32_t *count_dev)
+{
+    const int n = c->n_owned;
     if (n == 0) return 0;
-    k_pack<<<(n + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(
-        n, c->dbox, c->ps, c->in_soa, have_cells ? c->in_cell : nullptr, c->xv, c->rad,
-        c->cid, c->flags);
+    const int row = side == 0 ? 1 : c->dbox.nl - 2;
+    k_halo_pack<<<(n + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(
+        n, c->ps, row, c->cid, c->xv, c->rad, c->gid, (HaloRec *)out, cap, count_dev);
+    return 1;
+}
+
+int edmd_launch_halo_append_row(edmd_ctx *c, const void *in, int count, int row)
+{
+    if (count == 0) return 0;
+    k_halo_append<<<(count + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(
+        count, c->n, c->ps, row, (const HaloRec *)in, c->xv, c->rad, c->cid, c->gid, c->dbox.nx, c->flags);
     return 1;
 }
 
@@ -335,12 +409,12 @@ int edmd_launch_cell_index(edmd_ctx *c, int mode)
         k_count<<<blocks4, kThreads, 0, c->stream>>>(n, c->cid, c->cell_cnt, c->rank);
         launched++;
     }
-    k_rowscan<<<c->dbox.ny, kThreads, 0, c->stream>>>(c->dbox.nx, c->ps, c->cell_cnt, c->off,
+    k_rowscan<<<c->dbox.nl, kThreads, 0, c->stream>>>(c->dbox.nx, c->ps, c->cell_cnt, c->off,
                                                      c->row_total);
-    k_rowbase<<<1, kBaseThreads, 0, c->stream>>>(c->dbox.ny, c->row_total, c->row_base);
-    k_chunkmeta<<<c->dbox.ny, kMetaThreads, 0, c->stream>>>(
-        c->dbox.nx, c->dbox.ny, c->ps, c->off, c->row_total, c->row_base, c->meta, c->cstart,
-        edmd_chunks_bound(c), kCapW, kOffW);
+    k_rowbase<<<1, kBaseThreads, 0, c->stream>>>(c->dbox.nl, c->row_total, c->row_base);
+    k_chunkmeta<<<c->dbox.nl, kMetaThreads, 0, c->stream>>>(
+        c->dbox.nx, c->dbox.nl, c->ps, c->dbox.ny, c->dbox.yoff, c->slab ? 1 : 0, c->off, c->row_total,
+        c->row_base, c->meta, c->cstart, edmd_chunks_bound(c), kCapW, kOffW);
     launched += 3;
     if (n > 0) {
         if (mode == EDMD_MODE_GROW)

@@ -165,7 +165,8 @@ int edmd_persistent_blocks(const edmd_ctx *c)
 
 extern "C" {
 
-int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
+static int create_impl(int device, int n, double lx, double ly, int slab, int row_lo, int row_hi,
+                       edmd_ctx **out)
 {
     if (!out) return EDMD_EINVAL;
     *out = nullptr;
@@ -179,7 +180,10 @@ int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
     memset(c, 0, sizeof(*c));
     *out = c;  // returned even on failure so last_error() is readable
     c->device = device;
-    c->n = n;
+    c->n = slab ? 0 : n;
+    c->n_cap = n;
+    c->n_owned = c->n;
+    c->slab = slab != 0;
     box_init(&c->box, n > 0 ? n : 1, lx, ly);
     c->box.n = n;
     long long nc = (long long)c->box.nxcells * c->box.nycells;
@@ -196,6 +200,15 @@ int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
     c->dbox.csy = c->box.celly_size;
     c->dbox.fx = c->box.cellx_fac;
     c->dbox.fy = c->box.celly_fac;
+    c->dbox.nl = c->dbox.ny;
+    c->dbox.yoff = 0;
+    if (slab) {
+        // owned rows [row_lo, row_hi) of the global grid plus one halo row on each side
+        if (row_lo < 0 || row_hi > c->dbox.ny || row_hi - row_lo < 1 || row_hi - row_lo + 2 > c->dbox.ny)
+            return fail(c, EDMD_EINVAL, "bad slab row range (needs 1 <= rows <= ny - 2)");
+        c->dbox.nl = row_hi - row_lo + 2;
+        c->dbox.yoff = row_lo == 0 ? c->dbox.ny - 1 : row_lo - 1;
+    }
 
     CU(cudaSetDevice(device));
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -211,19 +224,20 @@ int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
     if ((r = dev_alloc(c, &c->rad, N))) return r;
     if ((r = dev_alloc(c, &c->vr, N))) return r;
     if ((r = dev_alloc(c, &c->cid, N))) return r;
+    if ((r = dev_alloc(c, &c->gid, N))) return r;
     c->ps = (c->dbox.nx + 3 + 3) & ~3;
-    long long ncp = (long long)c->dbox.ny * c->ps;
+    long long ncp = (long long)c->dbox.nl * c->ps;
     if (ncp >= (1ll << 31) - 8) return fail(c, EDMD_EINVAL, "cell grid too large");
     c->ncp = (int)ncp;
     // every particle has at most one ghost copy (two when nx < 3); rows are padded to 32
-    c->cap = (size_t)(c->dbox.nx < 3 ? 3 : 2) * N + 32 * (size_t)c->dbox.ny + 64;
+    c->cap = (size_t)(c->dbox.nx < 3 ? 3 : 2) * N + 32 * (size_t)c->dbox.nl + 64;
     c->max_chunks = (int)((c->cap + 31) / 32);
     if ((r = dev_alloc(c, &c->cell_cnt, (size_t)ncp + 8))) return r;
     if ((r = dev_alloc(c, &c->off, (size_t)ncp + 8))) return r;
     if ((r = dev_alloc(c, &c->cstart, (size_t)ncp + 8))) return r;
     if ((r = dev_alloc(c, &c->rank, N))) return r;
-    if ((r = dev_alloc(c, &c->row_total, (size_t)c->dbox.ny + 8))) return r;
-    if ((r = dev_alloc(c, &c->row_base, (size_t)c->dbox.ny + 8))) return r;
+    if ((r = dev_alloc(c, &c->row_total, (size_t)c->dbox.nl + 8))) return r;
+    if ((r = dev_alloc(c, &c->row_base, (size_t)c->dbox.nl + 8))) return r;
     if ((r = dev_alloc(c, &c->meta, (size_t)c->max_chunks + 8))) return r;
     CU(cudaMemsetAsync(c->cell_cnt, 0, ((size_t)ncp + 8) * sizeof(int32_t), c->stream));
     if ((r = dev_alloc(c, &c->spos, c->cap + 32))) return r;
@@ -247,11 +261,22 @@ int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
     return 0;
 }
 
+int edmd_cuda_create(int device, int n, double lx, double ly, edmd_ctx **out)
+{
+    return create_impl(device, n, lx, ly, 0, 0, 0, out);
+}
+
+int edmd_cuda_create_slab(int device, int n_capacity, double lx, double ly, int row_lo, int row_hi,
+                          edmd_ctx **out)
+{
+    return create_impl(device, n_capacity, lx, ly, 1, row_lo, row_hi, out);
+}
+
 void edmd_cuda_destroy(edmd_ctx *c)
 {
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
-    void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->cell_cnt,
+    void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->gid, c->cell_cnt,
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
                    c->overlap_key, c->flags, c->pcf_counts, c->boop, c->boop_nb,
@@ -310,30 +335,96 @@ void edmd_cuda_host_free(void *ptr)
     if (ptr) cudaFreeHost(ptr);
 }
 
-int edmd_cuda_upload(edmd_ctx *c, const double *x, const double *y, const double *vx,
-                     const double *vy, const double *rad, const int32_t *cell_xy,
-                     double t)
+static int upload_impl(edmd_ctx *c, int n, const double *x, const double *y, const double *vx,
+                       const double *vy, const double *rad, const int32_t *cell_xy,
+                       const int32_t *gid, double t)
 {
-    if (!c) return EDMD_EINVAL;
-    if (c->n > 0 && (!x || !y || !vx || !vy || !rad)) return fail(c, EDMD_EINVAL, "null state array");
+    if (n > 0 && (!x || !y || !vx || !vy || !rad)) return fail(c, EDMD_EINVAL, "null state array");
     CU(cudaSetDevice(c->device));
-    size_t N = (size_t)c->n, B = N * sizeof(double);
+    size_t N = (size_t)c->n_cap, B = (size_t)n * sizeof(double);
     int r;
     if ((r = h2d(c, c->in_soa, x, B))) return r;
     if ((r = h2d(c, c->in_soa + N, y, B))) return r;
     if ((r = h2d(c, c->in_soa + 2 * N, vx, B))) return r;
     if ((r = h2d(c, c->in_soa + 3 * N, vy, B))) return r;
     if ((r = h2d(c, c->in_soa + 4 * N, rad, B))) return r;
-    if (cell_xy && (r = h2d(c, c->in_cell, cell_xy, 2 * N * sizeof(int32_t)))) return r;
+    if (cell_xy && (r = h2d(c, c->in_cell, cell_xy, 2 * (size_t)n * sizeof(int32_t)))) return r;
+    if (gid && (r = h2d(c, c->gid, gid, (size_t)n * sizeof(int32_t)))) return r;
     CU(cudaMemsetAsync(c->flags + kFlagGhosts, 0, 2 * sizeof(int32_t), c->stream));
     c->nghost = 0;
-    c->launches += edmd_launch_pack(c, cell_xy != nullptr);
+    c->n = n;
+    c->n_owned = n;
+    c->launches += edmd_launch_pack(c, cell_xy != nullptr, 0, n);
     CU(cudaGetLastError());
     c->t = t;
     c->have_pred = false;
     c->have_index = false;
     if ((r = check_flags(c))) return r;
     c->have_state = true;
+    return 0;
+}
+
+int edmd_cuda_upload(edmd_ctx *c, const double *x, const double *y, const double *vx,
+                     const double *vy, const double *rad, const int32_t *cell_xy,
+                     double t)
+{
+    if (!c) return EDMD_EINVAL;
+    if (c->slab) return fail(c, EDMD_ESTATE, "slab contexts take edmd_cuda_upload_owned");
+    return upload_impl(c, c->n_cap, x, y, vx, vy, rad, cell_xy, nullptr, t);
+}
+
+int edmd_cuda_upload_owned(edmd_ctx *c, int n_owned, const double *x, const double *y,
+                           const double *vx, const double *vy, const double *rad,
+                           const int32_t *cell_xy, const int32_t *global_id, double t)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->slab) return fail(c, EDMD_ESTATE, "not a slab context");
+    if (n_owned < 0 || n_owned > c->n_cap) return fail(c, EDMD_EINVAL, "n_owned exceeds the slab capacity");
+    if (n_owned > 0 && !global_id) return fail(c, EDMD_EINVAL, "slab upload needs global ids");
+    return upload_impl(c, n_owned, x, y, vx, vy, rad, cell_xy, global_id, t);
+}
+
+int edmd_cuda_halo_pack(edmd_ctx *c, int side, void *dev_records, int capacity, int *count)
+{
+    if (!c || !count || (side != 0 && side != 1)) return EDMD_EINVAL;
+    if (!c->slab || !c->have_state) return fail(c, EDMD_ESTATE, "halo_pack needs an uploaded slab");
+    CU(cudaSetDevice(c->device));
+    int32_t *cnt = c->flags + kFlagCount - 2;
+    CU(cudaMemsetAsync(cnt, 0, sizeof(int32_t), c->stream));
+    c->launches += edmd_launch_halo_pack(c, side, dev_records, capacity, cnt);
+    CU(cudaGetLastError());
+    int32_t k = 0;
+    CU(cudaMemcpyAsync(&k, cnt, sizeof(k), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *count = k;
+    if (k > capacity) return fail(c, EDMD_EINVAL, "halo buffer too small");
+    return 0;
+}
+
+int edmd_cuda_halo_append(edmd_ctx *c, int side, const void *dev_records, int count)
+{
+    if (!c || count < 0 || (side != 0 && side != 1)) return EDMD_EINVAL;
+    if (!c->slab || !c->have_state) return fail(c, EDMD_ESTATE, "halo_append needs an uploaded slab");
+    if (c->n + count > c->n_cap) return fail(c, EDMD_EINVAL, "halo does not fit the slab capacity");
+    CU(cudaSetDevice(c->device));
+    // records from the lower neighbour are its LAST row = our local row 0; from the upper, row nl-1
+    const int row = side == 0 ? 0 : c->dbox.nl - 1;
+    c->launches += edmd_launch_halo_append_row(c, dev_records, count, row);
+    CU(cudaGetLastError());
+    c->n += count;
+    int r = check_flags(c);   // picks up the ghost count of the appended particles
+    if (r) return r;
+    c->have_state = true;
+    c->have_index = false;
+    c->have_pred = false;
+    return 0;
+}
+
+int edmd_cuda_get_counts(const edmd_ctx *c, int *n_owned, int *n_total)
+{
+    if (!c) return EDMD_EINVAL;
+    if (n_owned) *n_owned = c->n_owned;
+    if (n_total) *n_total = c->n;
     return 0;
 }
 
@@ -407,7 +498,7 @@ int edmd_cuda_fetch_predictions(edmd_ctx *c, double *t_cross, uint8_t *dir, doub
     if (!c) return EDMD_EINVAL;
     if (!c->have_pred) return fail(c, EDMD_ESTATE, "no device predictions to fetch");
     CU(cudaSetDevice(c->device));
-    size_t N = (size_t)c->n;
+    size_t N = (size_t)c->n_owned;
     int r;
     if (t_cross && (r = d2h(c, t_cross, c->t_cross, N * sizeof(double)))) return r;
     if (t_coll && (r = d2h(c, t_coll, c->t_coll, N * sizeof(double)))) return r;
@@ -540,7 +631,8 @@ int edmd_cuda_pcf(edmd_ctx *c, double dr, double max_r, uint64_t *counts, double
     }
     if (nb > 0) {
         CU(cudaMemsetAsync(c->pcf_counts, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
-        c->launches += edmd_launch_pcf(c, dr, max_r, nb);
+        c->launches += edmd_launch_pcf(c, dr, max_r, nb, reinterpret_cast<const double *>(c->xv), 4, c->n, 0, 1,
+                                       c->pcf_counts);
         CU(cudaGetLastError());
         int r = d2h(c, counts, c->pcf_counts, (size_t)nb * sizeof(uint64_t));
         if (r) return r;
@@ -558,6 +650,23 @@ int edmd_cuda_pcf(edmd_ctx *c, double dr, double max_r, uint64_t *counts, double
             g_r[i] = norm > 0 ? g / norm : 0.0;
         }
     }
+    return 0;
+}
+
+int edmd_cuda_pcf_device(edmd_ctx *c, const double *xy_dev, int n_total, double dr, double max_r,
+                         int part, int nparts, uint64_t *counts_dev, int *num_bins)
+{
+    if (!c || !num_bins || nparts < 1 || part < 0 || part >= nparts) return EDMD_EINVAL;
+    if (!(dr > 0) || !(max_r >= 0) || !(max_r / dr < 1e8)) return fail(c, EDMD_EINVAL, "bad dr / max_r");
+    const int nb = (int)(max_r / dr);
+    *num_bins = nb;
+    if (!counts_dev) return 0;
+    if (!xy_dev || n_total < 0) return fail(c, EDMD_EINVAL, "null positions");
+    CU(cudaSetDevice(c->device));
+    c->launches += edmd_launch_pcf(c, dr, max_r, nb, xy_dev, 2, n_total, part, nparts,
+                                   reinterpret_cast<unsigned long long *>(counts_dev));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -625,7 +734,8 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
         case EDMD_BENCH_PCF:
             CU(cudaMemsetAsync(c->pcf_counts, 0, (size_t)(nb > 0 ? nb : 1) * sizeof(unsigned long long), c->stream));
             if (e) CU(cudaEventRecord(e[1], c->stream));
-            c->launches += edmd_launch_pcf(c, dr, max_r, nb);
+            c->launches += edmd_launch_pcf(c, dr, max_r, nb, reinterpret_cast<const double *>(c->xv), 4, c->n, 0, 1,
+                                           c->pcf_counts);
             break;
         default:
             return fail(c, EDMD_EINVAL, "bad bench id");

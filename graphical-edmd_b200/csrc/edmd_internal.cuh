@@ -43,10 +43,19 @@
 #include "edmd_cuda.h"
 
 struct edmd_dev_box {
-    int n, nx, ny, nc;
+    int n, nx, ny, nc;     // ny = rows of the GLOBAL cell grid
+    int nl, yoff;          // rows held by this context and the global row of local row 0
+                           // (whole system: nl = ny, yoff = 0; slab: owned rows + one halo row each side)
     double lx, ly, half_lx, half_ly;
     double csx, csy, fx, fy;
 };
+
+// global cell row of a local row
+__host__ __device__ inline int edmd_global_row(const edmd_dev_box &b, int l)
+{
+    int y = l + b.yoff;
+    return y >= b.ny ? y - b.ny : y;
+}
 
 // One particle in cell order = a 32-byte kinematic record + a 16-byte tag, in
 // two parallel arrays.  Measured on B200 (profiles/microbench/scatter_stores.cu,
@@ -93,7 +102,7 @@ static_assert(sizeof(ChunkMeta) == 64, "ChunkMeta must be 64 bytes");
 
 // everything a consumer of the cell index needs (kernel argument block)
 struct CellIndex {
-    int nx, ny, ps;           // ps = nx + 3 rounded up to a multiple of 4
+    int nx, ny, ps;           // ny = LOCAL rows; ps = nx + 3 rounded up to a multiple of 4
     const int32_t *off;
     const int32_t *row_total;
     const int32_t *row_base;
@@ -102,6 +111,8 @@ struct CellIndex {
     const SAux *saux;
     const double *svr;
     const int32_t *flags;     // [3] != 0: some particle is far from its filed cell
+    const int32_t *gid;       // global particle ids (slab mode), nullptr = identity
+    int n_owned;              // local ids >= n_owned are halo copies: never predicted
 };
 
 // device flag words
@@ -109,7 +120,10 @@ enum { kFlagBadCell = 0, kFlagRescans = 1, kFlagGhosts = 2, kFlagInsane = 3, kFl
 
 struct edmd_ctx {
     int device;
-    int n;
+    int n;               // particles currently held (slab: owned + halo)
+    int n_cap;           // capacity
+    int n_owned;         // particles this context predicts (== n unless slab)
+    bool slab;
     edmd_box box;
     edmd_dev_box dbox;
     cudaStream_t stream;
@@ -138,6 +152,7 @@ struct edmd_ctx {
     double4 *xv;
     double *rad, *vr;
     int32_t *cid;
+    int32_t *gid;        // slab mode: global particle id of every local particle
 
     // cell index
     int ps;              // padded row stride: nx + 3 rounded up to a multiple of 4
@@ -172,7 +187,7 @@ inline CellIndex edmd_cell_index(const edmd_ctx *c)
 {
     CellIndex g;
     g.nx = c->dbox.nx;
-    g.ny = c->dbox.ny;
+    g.ny = c->dbox.nl;
     g.ps = c->ps;
     g.off = c->off;
     g.row_total = c->row_total;
@@ -182,13 +197,15 @@ inline CellIndex edmd_cell_index(const edmd_ctx *c)
     g.saux = c->saux;
     g.svr = c->svr;
     g.flags = c->flags;
+    g.gid = c->slab ? c->gid : nullptr;
+    g.n_owned = c->n_owned;
     return g;
 }
 
 // number of 32-slot chunks the current index can occupy (host-side bound)
 inline int edmd_chunks_bound(const edmd_ctx *c)
 {
-    long long slots = (long long)c->n + c->nghost + 32ll * c->dbox.ny;
+    long long slots = (long long)c->n + c->nghost + 32ll * c->dbox.nl;
     long long ch = (slots + 31) / 32;
     return (int)(ch < c->max_chunks ? ch : c->max_chunks);
 }
@@ -197,10 +214,13 @@ inline int edmd_chunks_bound(const edmd_ctx *c)
 int edmd_persistent_blocks(const edmd_ctx *c);
 
 // ---- launchers (each returns the number of kernels it launched) ----------
-int edmd_launch_pack(edmd_ctx *c, bool have_cells);
+int edmd_launch_pack(edmd_ctx *c, bool have_cells, int first, int count);
+int edmd_launch_halo_pack(edmd_ctx *c, int side, void *out, int cap, int32_t *count_dev);
+int edmd_launch_halo_append_row(edmd_ctx *c, const void *in, int count, int row);
 int edmd_launch_cell_index(edmd_ctx *c, int mode);
 int edmd_launch_predict(edmd_ctx *c, int mode);
 int edmd_launch_free_fly(edmd_ctx *c, int mode, double dt);
 int edmd_launch_boop(edmd_ctx *c, double r_c);
 int edmd_launch_mean(edmd_ctx *c, const double *v, int n, double *out_dev);
-int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins);
+int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
+                    int n, int part, int nparts, unsigned long long *counts);

@@ -146,28 +146,32 @@ __device__ __forceinline__ void crossing_exact(const edmd_dev_box &b, const SRec
     d = takex ? (p1.vx < 0 ? 1 : 2) : (p1.vy < 0 ? 3 : 4);
 }
 
+// local particle id -> the id the caller knows (slab contexts hold a subset)
+__device__ __forceinline__ int global_id(const CellIndex &g, int id) { return g.gid ? g.gid[id] : id; }
+
 // The reference's first-minimum-in-scan-order rule for a candidate that ties
 // the current best exactly: only a larger id in the SAME cell comes earlier.
-__device__ __forceinline__ bool tie_wins(const SRec &cand, int best_pc, int best_id)
+__device__ __forceinline__ bool tie_wins(const CellIndex &g, const SRec &cand, int best_pc, int best_id)
 {
-    return cand.pc == best_pc && cand.id > best_id;
+    return cand.pc == best_pc && global_id(g, cand.id) > global_id(g, best_id);
 }
 
 __device__ __forceinline__ void emit_collision(const SweepArgs &a, int id, double best, int best_id,
                                                int ov_id)
 {
     a.t_coll[id] = __dadd_rn(a.t, best);
-    a.partner[id] = best_id >= 0 ? best_id : 0;
+    a.partner[id] = best_id >= 0 ? global_id(a.g, best_id) : 0;
     a.ctype[id] = EDMD_EV_COLLISION;
     if (ov_id >= 0) {
-        unsigned long long key = ((unsigned long long)(uint32_t)id << 32) | (uint32_t)ov_id;
+        unsigned long long key = ((unsigned long long)(uint32_t)global_id(a.g, id) << 32) |
+                                 (uint32_t)global_id(a.g, ov_id);
         atomicMin(a.overlap_key, key);
     }
 }
 
 // Exact loop over candidate records [lo, hi) of one row (shared or global).
 template <bool GROW, bool WRAP>
-__device__ __forceinline__ void exact_scan_range(const edmd_dev_box &b, const SRec &p1, double four_r1,
+__device__ __forceinline__ void exact_scan_range(const CellIndex &g, const edmd_dev_box &b, const SRec &p1, double four_r1,
                                                  double vr1, const SPos *pos, const SAux *aux,
                                                  const double *vrs, int lo, int hi, double &best,
                                                  int &best_id, int &best_pc, int &ov_id, int &ov_pc)
@@ -182,11 +186,11 @@ __device__ __forceinline__ void exact_scan_range(const edmd_dev_box &b, const SR
             dt = pair_time_grow(b, p1, vr1, p2, vrs[p], ov);
         else
             dt = pair_time_normal<WRAP>(b, p1, four_r1, p2, ov);
-        if (ov && (ov_id < 0 || (p2.pc == ov_pc && p2.id > ov_id))) {
+        if (ov && (ov_id < 0 || (p2.pc == ov_pc && global_id(g, p2.id) > global_id(g, ov_id)))) {
             ov_id = p2.id;
             ov_pc = p2.pc;
         }
-        if (best > dt || (best == dt && best_id >= 0 && tie_wins(p2, best_pc, best_id))) {
+        if (best > dt || (best == dt && best_id >= 0 && tie_wins(g, p2, best_pc, best_id))) {
             best = dt;
             best_id = p2.id;
             best_pc = p2.pc;
@@ -201,11 +205,12 @@ __device__ void predict_one_global(const SweepArgs &a, int s, int Y, int pcx)
     const edmd_dev_box &b = a.b;
     const CellIndex &g = a.g;
     const SRec p1 = make_rec(g.spos[s], g.saux[s]);
+    if (p1.id >= g.n_owned) return;   // halo copy of a neighbour slab's particle
     const double vr1 = GROW ? g.svr[s] : 0.0;
     const double four_r1 = __dmul_rn(4.0, p1.rad);
     double dtc;
     int d;
-    crossing_exact<true>(b, p1, pcx - 1, Y, dtc, d);
+    crossing_exact<true>(b, p1, pcx - 1, edmd_global_row(b, Y), dtc, d);
     a.t_cross[p1.id] = __dadd_rn(a.t, dtc);
     a.dir[p1.id] = (uint8_t)d;
 
@@ -216,7 +221,7 @@ __device__ void predict_one_global(const SweepArgs &a, int s, int Y, int pcx)
         const int Yr = row_wrap(Y - 1 + j, g.ny);
         const int rb = g.row_base[Yr];
         const int32_t *o = g.off + (size_t)Yr * g.ps;
-        exact_scan_range<GROW, true>(b, p1, four_r1, vr1, g.spos, g.saux, g.svr, rb + o[pcx - 1],
+        exact_scan_range<GROW, true>(g, b, p1, four_r1, vr1, g.spos, g.saux, g.svr, rb + o[pcx - 1],
                                      rb + o[pcx + 2], best, best_id, best_pc, ov_id, ov_pc);
     }
     emit_collision(a, p1.id, best, best_id, ov_id);
@@ -269,8 +274,9 @@ __device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const Sta
     const SPos *pos = &w.pos[0][0];
     const SAux *aux = &w.aux[0][0];
     const SRec p1 = make_rec(pos[self], aux[self]);
+    if (p1.id >= a.g.n_owned) return;   // halo copy of a neighbour slab's particle
     const double four_r1 = __dmul_rn(4.0, p1.rad);
-    const int X = rl.pcx - 1, Y = rl.Y;
+    const int X = rl.pcx - 1, Y = edmd_global_row(b, rl.Y);
 
     // ---- crossing: rank the two axes by reciprocal seeds, divide once --------
     {
@@ -369,7 +375,7 @@ __device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const Sta
         atomicAdd(a.stats, 1u);
 #pragma unroll
         for (int j = 0; j < 3; j++)
-            exact_scan_range<false, WRAP>(b, p1, four_r1, 0.0, w.pos[j], w.aux[j], nullptr, rl.lo[j],
+            exact_scan_range<false, WRAP>(a.g, b, p1, four_r1, 0.0, w.pos[j], w.aux[j], nullptr, rl.lo[j],
                                           rl.hi[j], best, best_id, best_pc, ov_id, ov_pc);
     }
     emit_collision(a, p1.id, best, best_id, ov_id);
@@ -416,8 +422,9 @@ k_free_fly(int n, edmd_dev_box b, int ps, double dt, double4 *__restrict__ xv,
         // cells are host state and do not move with the particle: re-check that
         // it is still near the cell it is filed under
         const int pc = cid[i];
-        const int Y = pc / ps;
-        const int X = pc - Y * ps - 1;
+        const int l = pc / ps;
+        const int X = pc - l * ps - 1;
+        const int Y = edmd_global_row(b, l);
         insane = !(fabs(x - ((double)X + 0.5) * b.csx) <= 1.5 * b.csx) ||
                  !(fabs(y - ((double)Y + 0.5) * b.csy) <= 1.5 * b.csy);
     }

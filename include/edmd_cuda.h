@@ -142,6 +142,37 @@ int edmd_cuda_fetch_predictions(edmd_ctx *ctx, double *t_cross, uint8_t *dir,
                                 uint8_t *ctype, int32_t *overlap_pair);
 int edmd_cuda_set_growth(edmd_ctx *ctx, const double *vr);
 
+/* ---- multi-GPU: row slabs of the cell grid ---------------------------- */
+
+/* One context per GPU/rank owning the cell rows [row_lo, row_hi) of the GLOBAL
+ * grid (row-major cell index Y*Nxcells + X, src/EDMD.c:2071, makes a slab one
+ * contiguous cell range; periodic in y like PBCcellY :2118-2124).  It holds its
+ * owned particles plus copies of the neighbouring slabs' boundary rows (a
+ * one-cell-row halo) and predicts only the owned ones.  n_capacity bounds
+ * owned + halo particles.  The box is the global one. */
+int edmd_cuda_create_slab(int device, int n_capacity, double lx, double ly, int row_lo, int row_hi,
+                          edmd_ctx **out);
+/* Owned particles of this slab (all in rows [row_lo,row_hi)); global_id[i] is
+ * the id the caller knows the particle by: partner[] outputs carry global ids,
+ * outputs are indexed by the LOCAL index 0..n_owned-1. */
+int edmd_cuda_upload_owned(edmd_ctx *ctx, int n_owned, const double *x, const double *y,
+                           const double *vx, const double *vy, const double *rad,
+                           const int32_t *cell_xy, const int32_t *global_id, double t);
+/* Halo exchange, device buffers of 48-byte records owned by the caller (e.g.
+ * NCCL send/recv buffers): pack the first (side 0, for the lower neighbour) or
+ * last (side 1, for the upper neighbour) owned row; append what the lower
+ * (side 0) / upper (side 1) neighbour sent.  The transport between ranks is
+ * the caller's (ncclSend/ncclRecv, or P2P copies). */
+#define EDMD_HALO_RECORD_BYTES 48
+int edmd_cuda_halo_pack(edmd_ctx *ctx, int side, void *dev_records, int capacity, int *count);
+int edmd_cuda_halo_append(edmd_ctx *ctx, int side, const void *dev_records, int count);
+int edmd_cuda_get_counts(const edmd_ctx *ctx, int *n_owned, int *n_total);
+/* g(r) share of one rank: positions of ALL particles as (x,y) pairs in device
+ * memory (e.g. after an all-gather), tile pairs part (mod nparts); ADDS into
+ * counts_dev[num_bins] (device, caller zeroes it and all-reduces it). */
+int edmd_cuda_pcf_device(edmd_ctx *ctx, const double *xy_dev, int n_total, double dr, double max_r,
+                         int part, int nparts, uint64_t *counts_dev, int *num_bins);
+
 /* ---- free flight ------------------------------------------------------ */
 
 /* Replaces `for i<N freeFly(particles+i)` (takeAScreenshot, src/EDMD.c:

@@ -12,7 +12,7 @@ ARCH       = -gencode arch=compute_100a,code=sm_100a
 # parity-critical arithmetic additionally uses explicit __d*_rn intrinsics.
 NVCCFLAGS  = $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Iinclude -I$(CSRC) \
              -Xcompiler -fPIC,-Wall,-Wno-unused-function
-CU_SRCS    = $(CSRC)/edmd_cuda.cu $(CSRC)/cell_index.cu $(CSRC)/predict.cu $(CSRC)/analysis.cu
+CU_SRCS    = $(CSRC)/edmd_cuda.cu $(CSRC)/cell_index.cu $(CSRC)/predict.cu $(CSRC)/analysis.cu $(CSRC)/halo.cu
 CU_OBJS    = $(CU_SRCS:.cu=.o)
 LIB        = $(PKG)/libedmd_cuda.so
 

@@ -187,6 +187,95 @@ def profile_traffic():
     return None
 
 
+def run_slabs(args, pkg, rank, world, local):
+    """N > 1: weak scaling -- the system is N x 1M disks in one periodic box, cut
+    into N row slabs of the cell grid (one per GPU).  A step = halo exchange
+    (pack boundary rows, NCCL send/recv with both neighbours, append) + K0 + K1
+    on every rank; outputs are disjoint, no collective on the data path."""
+    import torch
+    import torch.distributed as dist
+
+    slab = pkg.slab
+    B = pkg.binding
+    n_total = args.n * world
+    cfg = pkg.synth.lattice_config(n_total, PHI, SEED, shuffle=(args.order == "shuffled"))
+    N, lx, ly = cfg["n"], cfg["lx"], cfg["ly"]
+    fx, fy = 1.0 / (lx / int(lx / 2)), 1.0 / (ly / int(ly / 2))     # cellxFac, cellyFac (src/EDMD.c:694-706)
+    cells = np.stack([(cfg["x"] * fx).astype(np.int32), (cfg["y"] * fy).astype(np.int32)], 1)
+    steps, warm = args.steps, max(args.warmup, 3)
+    sr = slab.SlabRank(pkg, N, lx, ly, rank, world, local)
+    sr.connect_p2p(dist)   # halo = peer stores over NVLink from the pack kernel (csrc/halo.cu)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    gid = sr.load_owned(cfg, cells, 0.0)
+    n_owned = len(gid)
+    halo_bytes = sr.exchange(dist)
+    _, n_local = sr.ctx.counts()
+    barrier()
+    l0 = sr.ctx.launches
+    with ClockSampler(local) as clk:
+        tot, main = sr.ctx.bench(B.BENCH_SWEEP, warmup=warm, iters=steps, flush_bytes=L2_FLUSH_BYTES)
+        launches_timed = (sr.ctx.launches - l0) * steps // (steps + warm)
+        # the exchange step (device buffers over NVLink), timed between synchronisations
+        own = {k: np.ascontiguousarray(cfg[k][gid]) for k in ("x", "y", "vx", "vy", "rad")}
+        own_cells = np.ascontiguousarray(cells[gid])
+        ex = []
+        for it in range(warm + steps):
+            sr.ctx.upload_owned(own["x"], own["y"], own["vx"], own["vy"], own["rad"], own_cells, gid, t=0.0)
+            barrier()
+            t0 = time.perf_counter()
+            sr.exchange(dist)
+            torch.cuda.synchronize()
+            if it >= warm:
+                ex.append(time.perf_counter() - t0)
+        barrier()
+        # end to end: host buffers -> upload owned, exchange, sweep, results back on the host
+        e2e = []
+        for it in range(3 + steps):
+            barrier()
+            t0 = time.perf_counter()
+            sr.ctx.upload_owned(own["x"], own["y"], own["vx"], own["vy"], own["rad"], own_cells, gid, t=0.0)
+            sr.exchange(dist)
+            sr.predict()
+            if it >= 3:
+                e2e.append(time.perf_counter() - t0)
+        barrier()
+    clocks = clk.summary()
+    ms_sweep, ms_k1, ms_ex, ms_e2e = (float(np.mean(tot)), float(np.mean(main)), 1e3 * float(np.mean(ex)),
+                                      1e3 * float(np.mean(e2e)))
+    tt = torch.tensor([ms_sweep, ms_k1, ms_ex, ms_e2e, float(n_local)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_sweep, ms_k1, ms_ex, ms_e2e, n_local_max = tt.tolist()
+    ms_step = ms_sweep + ms_ex
+    if rank == 0:
+        peak, how = peaks()
+        achieved = BYTES_PER_PARTICLE * n_owned / (ms_k1 * 1e-3) / 1e9
+        wc = workload_config({**cfg, "order": args.order})
+        wc["workload"] = (f"N={N} phi={PHI} ({world} x {args.n} disks, one periodic box), row slabs of the cell grid, "
+                          f"one-cell-row halo by peer stores over NVLink, full re-predict sweep (BASELINE configs[3] at 4 GPUs)")
+        wc["parallelism"] = f"{world} row slabs, halo {halo_bytes} B/rank/step, no data-path collective"
+        wc["step_breakdown_ms"] = {"halo_exchange": ms_ex, "sweep_K0_K1": ms_sweep, "K1": ms_k1}
+        line = {
+            "metric": METRIC, "value": N / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wc,
+            "clocks": clocks,
+            "e2e": {"value": N / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 52 * n_owned, "d2h_bytes_per_step": 22 * n_owned,
+                    "api": "edmd_cuda_upload_owned + halo exchange + edmd_cuda_predict_all per rank"},
+            "gpu_launches": int(launches_timed) * world,
+            "roofline": {"bound": "hbm", "kernel": "k_predict_rows (K1), rank 0", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": how + " (burst copy)", "traffic": profile_traffic(),
+                         "ms_kernel": ms_k1, "bytes_per_particle": BYTES_PER_PARTICLE},
+        }
+        print(json.dumps(line, default=float))
+    sr.close()
+
+
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
@@ -201,6 +290,10 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        run_slabs(args, pkg, rank, world, local)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
     def barrier():
         if world > 1:
@@ -336,6 +429,10 @@ def main():
 
     import __graft_entry__ as entry
     pkg = entry.load_package()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl != "reference" and world > 1:
+        run_ours(args, None)
+        return
     cfg = pkg.synth.lattice_config(args.n, PHI, SEED, shuffle=(args.order == "shuffled"))
     cfg["order"] = args.order
     if args.impl == "reference":

@@ -34,6 +34,7 @@ SYMBOLS = [
     "edmd_cuda_host_alloc", "edmd_cuda_host_free",
     "edmd_cuda_create_slab", "edmd_cuda_upload_owned", "edmd_cuda_halo_pack",
     "edmd_cuda_halo_append", "edmd_cuda_get_counts", "edmd_cuda_pcf_device",
+    "edmd_cuda_halo_export", "edmd_cuda_halo_connect", "edmd_cuda_halo_exchange",
 ]
 HALO_RECORD_BYTES = 48
 
@@ -93,6 +94,9 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_halo_pack.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
     lib.edmd_cuda_halo_append.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.edmd_cuda_get_counts.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.edmd_cuda_halo_export.argtypes = [vp, C.c_int, C.c_char_p]
+    lib.edmd_cuda_halo_connect.argtypes = [vp, C.c_char_p, C.c_char_p]
+    lib.edmd_cuda_halo_exchange.argtypes = [vp]
     lib.edmd_cuda_pcf_device.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, vp,
                                          C.POINTER(C.c_int)]
     lib.edmd_cuda_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -208,6 +212,17 @@ class EdmdCuda:
 
     def halo_append(self, side: int, dev_ptr: int, count: int):
         self._check(self.lib.edmd_cuda_halo_append(self._h, side, C.c_void_p(dev_ptr), count))
+
+    def halo_export(self, halo_capacity: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.edmd_cuda_halo_export(self._h, halo_capacity, buf))
+        return buf.raw
+
+    def halo_connect(self, lower: bytes | None, upper: bytes | None):
+        self._check(self.lib.edmd_cuda_halo_connect(self._h, lower, upper))
+
+    def halo_exchange(self):
+        self._check(self.lib.edmd_cuda_halo_exchange(self._h))
 
     def counts(self):
         a, b = C.c_int(0), C.c_int(0)

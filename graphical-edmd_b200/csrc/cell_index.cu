@@ -84,13 +84,15 @@ k_count(int n, const int32_t *__restrict__ cid, int32_t *__restrict__ cnt,
     if (i + 3 < n) {
         const int4 c = *reinterpret_cast<const int4 *>(cid + i);
         int4 r;
-        r.x = atomicAdd(&cnt[c.x], 1);
-        r.y = atomicAdd(&cnt[c.y], 1);
-        r.z = atomicAdd(&cnt[c.z], 1);
-        r.w = atomicAdd(&cnt[c.w], 1);
+        // cid < 0: unused halo slot of a slab context
+        r.x = c.x >= 0 ? atomicAdd(&cnt[c.x], 1) : 0;
+        r.y = c.y >= 0 ? atomicAdd(&cnt[c.y], 1) : 0;
+        r.z = c.z >= 0 ? atomicAdd(&cnt[c.z], 1) : 0;
+        r.w = c.w >= 0 ? atomicAdd(&cnt[c.w], 1) : 0;
         *reinterpret_cast<int4 *>(rank + i) = r;
     } else {
-        for (int k = i; k < n; k++) rank[k] = atomicAdd(&cnt[cid[k]], 1);
+        for (int k = i; k < n; k++)
+            if (cid[k] >= 0) rank[k] = atomicAdd(&cnt[cid[k]], 1);
     }
 }
 
@@ -287,8 +289,8 @@ k_scatter(int n, int nx, int ps, const int32_t *__restrict__ cid,
         rk[0] = rk[1] = rank[i0];
     }
     int base[2];
-    base[0] = cstart[pc[0]];
-    base[1] = cstart[pc[1]];
+    base[0] = pc[0] >= 0 ? cstart[pc[0]] : 0;
+    base[1] = pc[1] >= 0 ? cstart[pc[1]] : 0;
     SPos r[2];
     SAux t[2];
     double g[2] = {0.0, 0.0};
@@ -305,6 +307,7 @@ k_scatter(int n, int nx, int ps, const int32_t *__restrict__ cid,
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         if (k == 1 && !two) break;
+        if (pc[k] < 0) continue;   // unused halo slot
         put_rec(spos, saux, svr, base[k] + rk[k], r[k], t[k], g[k], GROW);
         const int Y = pc[k] / ps;
         const int pcx = pc[k] - Y * ps;

@@ -133,6 +133,10 @@ int check_flags(edmd_ctx *c)
     CU(cudaMemcpyAsync(f, c->flags, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->nghost = f[kFlagGhosts];
+    if (f[kFlagBadCell] & 2) {
+        CU(cudaMemsetAsync(c->flags + kFlagBadCell, 0, sizeof(int32_t), c->stream));
+        return fail(c, EDMD_EINVAL, "halo buffer too small for a boundary row");
+    }
     if (f[kFlagBadCell] & 1) {
         CU(cudaMemsetAsync(c->flags + kFlagBadCell, 0, sizeof(int32_t), c->stream));
         c->have_state = false;
@@ -283,6 +287,10 @@ void edmd_cuda_destroy(edmd_ctx *c)
                    c->red_partial, c->flush_buf};
     for (void *p : dev)
         if (p) cudaFree(p);
+    for (int k = 0; k < 2; k++)
+        if (c->peer_opened[k] && c->peer_mem[k]) cudaIpcCloseMemHandle(c->peer_mem[k]);
+    if (c->halo_mem) cudaFree(c->halo_mem);
+    if (c->halo_cnt) cudaFree(c->halo_cnt);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (int k = 0; k < 4; k++)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
@@ -354,6 +362,7 @@ static int upload_impl(edmd_ctx *c, int n, const double *x, const double *y, con
     c->nghost = 0;
     c->n = n;
     c->n_owned = n;
+    c->nghost_extra = 0;
     c->launches += edmd_launch_pack(c, cell_xy != nullptr, 0, n);
     CU(cudaGetLastError());
     c->t = t;
@@ -415,6 +424,69 @@ int edmd_cuda_halo_append(edmd_ctx *c, int side, const void *dev_records, int co
     int r = check_flags(c);   // picks up the ghost count of the appended particles
     if (r) return r;
     c->have_state = true;
+    c->have_index = false;
+    c->have_pred = false;
+    return 0;
+}
+
+// ---- peer-to-peer halo (NVLink, CUDA IPC) -------------------------------------
+int edmd_cuda_halo_export(edmd_ctx *c, int halo_capacity, void *handle64)
+{
+    if (!c || !handle64 || halo_capacity < 1) return EDMD_EINVAL;
+    if (!c->slab) return fail(c, EDMD_ESTATE, "not a slab context");
+    CU(cudaSetDevice(c->device));
+    if (!c->halo_mem) {
+        c->halo_cap = halo_capacity;
+        size_t bytes = edmd_halo_mem_bytes(halo_capacity);
+        CU(cudaMalloc((void **)&c->halo_mem, bytes));
+        CU(cudaMemset(c->halo_mem, 0, bytes));
+        CU(cudaMalloc((void **)&c->halo_cnt, 8 * sizeof(int32_t)));
+        CU(cudaMemset(c->halo_cnt, 0, 8 * sizeof(int32_t)));
+        c->halo_epoch = 0;
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->halo_mem));
+    static_assert(sizeof(h) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int edmd_cuda_halo_connect(edmd_ctx *c, const void *lower64, const void *upper64)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->slab || !c->halo_mem) return fail(c, EDMD_ESTATE, "halo_export first");
+    CU(cudaSetDevice(c->device));
+    const void *hs[2] = {lower64, upper64};
+    for (int k = 0; k < 2; k++) {
+        if (!hs[k]) {               // the neighbour is this very context (single slab)
+            c->peer_mem[k] = c->halo_mem;
+            continue;
+        }
+        if (k == 1 && lower64 && memcmp(lower64, upper64, 64) == 0) {   // two slabs: same peer
+            c->peer_mem[1] = c->peer_mem[0];
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs[k], 64);
+        void *p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_mem[k] = (char *)p;
+        c->peer_opened[k] = true;
+    }
+    return 0;
+}
+
+int edmd_cuda_halo_exchange(edmd_ctx *c)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->slab || !c->have_state) return fail(c, EDMD_ESTATE, "halo_exchange needs an uploaded slab");
+    if (!c->peer_mem[0] || !c->peer_mem[1]) return fail(c, EDMD_ESTATE, "halo_connect first");
+    if (c->n_owned + 2 * c->halo_cap > c->n_cap) return fail(c, EDMD_EINVAL, "halo does not fit the slab capacity");
+    CU(cudaSetDevice(c->device));
+    c->launches += edmd_launch_halo_p2p(c);
+    CU(cudaGetLastError());
+    c->n = c->n_owned + 2 * c->halo_cap;      // fixed halo region; unused slots carry cell id -1
+    c->nghost_extra = 2 * c->halo_cap;        // bound: every halo particle could sit in an edge cell
     c->have_index = false;
     c->have_pred = false;
     return 0;

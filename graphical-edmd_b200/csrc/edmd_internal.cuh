@@ -154,6 +154,15 @@ struct edmd_ctx {
     int32_t *cid;
     int32_t *gid;        // slab mode: global particle id of every local particle
 
+    // slab mode: peer-to-peer halo over NVLink (see halo.cu)
+    int halo_cap;        // records per inbox
+    int halo_epoch;
+    char *halo_mem;      // my inboxes + acks (exported through CUDA IPC)
+    char *peer_mem[2];   // lower / upper neighbour's halo_mem (IPC mapped, or my own)
+    bool peer_opened[2];
+    int32_t *halo_cnt;   // [4] device counters: records packed per side, finished blocks per side
+    int nghost_extra;    // upper bound of ghost entries contributed by halo particles
+
     // cell index
     int ps;              // padded row stride: nx + 3 rounded up to a multiple of 4
     int ncp;             // ny * ps
@@ -205,7 +214,7 @@ inline CellIndex edmd_cell_index(const edmd_ctx *c)
 // number of 32-slot chunks the current index can occupy (host-side bound)
 inline int edmd_chunks_bound(const edmd_ctx *c)
 {
-    long long slots = (long long)c->n + c->nghost + 32ll * c->dbox.nl;
+    long long slots = (long long)c->n + c->nghost + c->nghost_extra + 32ll * c->dbox.nl;
     long long ch = (slots + 31) / 32;
     return (int)(ch < c->max_chunks ? ch : c->max_chunks);
 }
@@ -217,6 +226,8 @@ int edmd_persistent_blocks(const edmd_ctx *c);
 int edmd_launch_pack(edmd_ctx *c, bool have_cells, int first, int count);
 int edmd_launch_halo_pack(edmd_ctx *c, int side, void *out, int cap, int32_t *count_dev);
 int edmd_launch_halo_append_row(edmd_ctx *c, const void *in, int count, int row);
+size_t edmd_halo_mem_bytes(int halo_cap);
+int edmd_launch_halo_p2p(edmd_ctx *c);
 int edmd_launch_cell_index(edmd_ctx *c, int mode);
 int edmd_launch_predict(edmd_ctx *c, int mode);
 int edmd_launch_free_fly(edmd_ctx *c, int mode, double dt);

@@ -108,16 +108,31 @@ class SlabRank:
         self.rows = slab_rows(ny, world)[rank]
         nrows = self.rows[1] - self.rows[0]
         per_row = n_total / ny
-        if capacity is None:
-            capacity = int(per_row * (nrows + 2) * 1.25) + 4096
         if halo_capacity is None:
-            halo_capacity = int(per_row * 2) + 4096
+            halo_capacity = int(per_row * 1.5) + 1024
+        if capacity is None:
+            capacity = int(per_row * nrows * 1.1) + 2 * halo_capacity + 4096
         self.halo_capacity = halo_capacity
         self.ctx = pkg.binding.EdmdCuda(capacity, lx, ly, device=device, slab_rows=self.rows)
         dev = torch.device("cuda", device)
         self.send = [torch.empty(halo_capacity * HALO_REC.itemsize, dtype=torch.uint8, device=dev)
                      for _ in range(2)]
+        self.p2p = False
         del probe
+
+    def connect_p2p(self, dist):
+        """Map the neighbours' halo inboxes through CUDA IPC so that the exchange
+        becomes peer stores over NVLink issued by the pack kernel itself."""
+        mine = self.ctx.halo_export(self.halo_capacity)
+        if self.world == 1:
+            self.ctx.halo_connect(None, None)
+        else:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine)
+            lower, upper = neighbours(self.rank, self.world)
+            self.ctx.halo_connect(handles[lower], handles[upper])
+            dist.barrier()
+        self.p2p = True
 
     def close(self):
         self.ctx.close()
@@ -133,6 +148,9 @@ class SlabRank:
     def exchange(self, dist):
         """One-cell-row halo exchange with the two neighbouring slabs over NCCL."""
         torch = self.torch
+        if self.p2p:
+            self.ctx.halo_exchange()        # asynchronous, on the context's stream
+            return 2 * self.halo_capacity * HALO_REC.itemsize
         n_lo = self.ctx.halo_pack(0, self.send[0].data_ptr(), self.halo_capacity)
         n_hi = self.ctx.halo_pack(1, self.send[1].data_ptr(), self.halo_capacity)
         s_lo = self.send[0][: n_lo * HALO_REC.itemsize]

@@ -166,6 +166,16 @@ int edmd_cuda_upload_owned(edmd_ctx *ctx, int n_owned, const double *x, const do
 #define EDMD_HALO_RECORD_BYTES 48
 int edmd_cuda_halo_pack(edmd_ctx *ctx, int side, void *dev_records, int capacity, int *count);
 int edmd_cuda_halo_append(edmd_ctx *ctx, int side, const void *dev_records, int count);
+/* The same exchange done by the GPUs themselves over NVLink peer memory (no
+ * NCCL call, no host synchronisation; see csrc/halo.cu): every rank exports
+ * its inbox (a 64-byte CUDA IPC handle), the caller ships the handles to the
+ * neighbours by any means, connect() maps them (NULL = the neighbour is this
+ * context itself), and halo_exchange() enqueues pack-and-peer-store + unpack
+ * kernels on the context's stream.  halo_capacity = records per boundary row
+ * buffer; n_capacity must hold n_owned + 2 * halo_capacity. */
+int edmd_cuda_halo_export(edmd_ctx *ctx, int halo_capacity, void *handle64);
+int edmd_cuda_halo_connect(edmd_ctx *ctx, const void *lower_handle64, const void *upper_handle64);
+int edmd_cuda_halo_exchange(edmd_ctx *ctx);
 int edmd_cuda_get_counts(const edmd_ctx *ctx, int *n_owned, int *n_total);
 /* g(r) share of one rank: positions of ALL particles as (x,y) pairs in device
  * memory (e.g. after an all-gather), tile pairs part (mod nparts); ADDS into

@@ -31,14 +31,22 @@ def main():
     slab = pkg.slab
     orc = Oracle()
     ok = True
-    for (n, phi, seed, sf) in [(200000, 0.70, 5, 0.3), (60000, 0.85, 6, 0.0)]:
+    for (n, phi, seed, sf, p2p) in [(200000, 0.70, 5, 0.3, False), (200000, 0.70, 5, 0.3, True),
+                                    (60000, 0.85, 6, 0.0, True)]:
         cfg = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf)
         N, lx, ly, t = cfg["n"], cfg["lx"], cfg["ly"], 1.25
         cells = orc.cells(N, lx, ly, cfg["x"], cfg["y"]).reshape(N, 2)
         sr = slab.SlabRank(pkg, N, lx, ly, rank, world, local)
+        if p2p:
+            sr.connect_p2p(dist)
         gid = sr.load_owned(cfg, cells, t)
         sr.exchange(dist)
         out = sr.predict()
+        if p2p:   # a second and third exchange on fresh uploads: epochs / parities / acks
+            for _ in range(2):
+                sr.load_owned(cfg, cells, t)
+                sr.exchange(dist)
+                out = sr.predict()
         gathered = [None] * world
         dist.all_gather_object(gathered, {"gid": gid, **{k: out[k] for k in ("t_cross", "dir", "t_coll", "partner", "ctype")}})
         # g(r): all-gather owned positions, bin my share of the pairs, all-reduce the counts
@@ -70,7 +78,8 @@ def main():
             if not np.array_equal(counts.cpu().numpy().astype(np.uint64), wp["counts"]):
                 ok = False
                 print("MISMATCH g(r) counts")
-            print(f"slab check N={N} phi={phi} world={world}: sweep + g(r) {'bit-exact' if ok else 'FAILED'}")
+            print(f"slab check N={N} phi={phi} world={world} halo={'NVLink peer stores' if p2p else 'NCCL send/recv'}: "
+                  f"sweep + g(r) {'bit-exact' if ok else 'FAILED'}")
         sr.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -190,8 +190,9 @@ def profile_traffic():
 def run_slabs(args, pkg, rank, world, local):
     """N > 1: weak scaling -- the system is N x 1M disks in one periodic box, cut
     into N row slabs of the cell grid (one per GPU).  A step = halo exchange
-    (pack boundary rows, NCCL send/recv with both neighbours, append) + K0 + K1
-    on every rank; outputs are disjoint, no collective on the data path."""
+    (boundary rows packed and stored straight into the neighbours' memory over
+    NVLink) + K0 + K1 on every rank, all inside the CUDA-event bracket; outputs
+    are disjoint, no collective on the data path."""
     import torch
     import torch.distributed as dist
 
@@ -219,18 +220,15 @@ def run_slabs(args, pkg, rank, world, local):
     with ClockSampler(local) as clk:
         tot, main = sr.ctx.bench(B.BENCH_SWEEP, warmup=warm, iters=steps, flush_bytes=L2_FLUSH_BYTES)
         launches_timed = (sr.ctx.launches - l0) * steps // (steps + warm)
-        # the exchange step (device buffers over NVLink), timed between synchronisations
-        own = {k: np.ascontiguousarray(cfg[k][gid]) for k in ("x", "y", "vx", "vy", "rad")}
-        own_cells = np.ascontiguousarray(cells[gid])
-        ex = []
-        for it in range(warm + steps):
-            sr.ctx.upload_owned(own["x"], own["y"], own["vx"], own["vy"], own["rad"], own_cells, gid, t=0.0)
-            barrier()
-            t0 = time.perf_counter()
-            sr.exchange(dist)
-            torch.cuda.synchronize()
-            if it >= warm:
-                ex.append(time.perf_counter() - t0)
+        own = {}
+        keep = []
+        for k in ("x", "y", "vx", "vy", "rad"):
+            tpin = torch.from_numpy(np.ascontiguousarray(cfg[k][gid])).pin_memory()
+            keep.append(tpin)
+            own[k] = tpin.numpy()
+        tpin = torch.from_numpy(np.ascontiguousarray(cells[gid])).pin_memory()
+        keep.append(tpin)
+        own_cells = tpin.numpy()
         barrier()
         # end to end: host buffers -> upload owned, exchange, sweep, results back on the host
         e2e = []
@@ -244,12 +242,10 @@ def run_slabs(args, pkg, rank, world, local):
                 e2e.append(time.perf_counter() - t0)
         barrier()
     clocks = clk.summary()
-    ms_sweep, ms_k1, ms_ex, ms_e2e = (float(np.mean(tot)), float(np.mean(main)), 1e3 * float(np.mean(ex)),
-                                      1e3 * float(np.mean(e2e)))
-    tt = torch.tensor([ms_sweep, ms_k1, ms_ex, ms_e2e, float(n_local)], device="cuda", dtype=torch.float64)
+    ms_step, ms_k1, ms_e2e = float(np.mean(tot)), float(np.mean(main)), 1e3 * float(np.mean(e2e))
+    tt = torch.tensor([ms_step, ms_k1, ms_e2e, float(n_local)], device="cuda", dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_sweep, ms_k1, ms_ex, ms_e2e, n_local_max = tt.tolist()
-    ms_step = ms_sweep + ms_ex
+    ms_step, ms_k1, ms_e2e, n_local_max = tt.tolist()
     if rank == 0:
         peak, how = peaks()
         achieved = BYTES_PER_PARTICLE * n_owned / (ms_k1 * 1e-3) / 1e9
@@ -257,7 +253,7 @@ def run_slabs(args, pkg, rank, world, local):
         wc["workload"] = (f"N={N} phi={PHI} ({world} x {args.n} disks, one periodic box), row slabs of the cell grid, "
                           f"one-cell-row halo by peer stores over NVLink, full re-predict sweep (BASELINE configs[3] at 4 GPUs)")
         wc["parallelism"] = f"{world} row slabs, halo {halo_bytes} B/rank/step, no data-path collective"
-        wc["step_breakdown_ms"] = {"halo_exchange": ms_ex, "sweep_K0_K1": ms_sweep, "K1": ms_k1}
+        wc["step_breakdown_ms"] = {"halo_exchange_plus_K0": ms_step - ms_k1, "K1": ms_k1}
         line = {
             "metric": METRIC, "value": N / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,

@@ -789,6 +789,13 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
         switch (what) {
         case EDMD_BENCH_SWEEP:
             CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));
+            if (c->slab && c->peer_mem[0] && c->peer_mem[1]) {
+                // multi-GPU step: the halo exchange (peer stores over NVLink) is part of it;
+                // every rank runs the same number of iterations, epochs advance in lockstep
+                c->launches += edmd_launch_halo_p2p(c);
+                c->n = c->n_owned + 2 * c->halo_cap;
+                c->nghost_extra = 2 * c->halo_cap;
+            }
             c->launches += edmd_launch_cell_index(c, mode);
             if (e) CU(cudaEventRecord(e[1], c->stream));
             c->launches += edmd_launch_predict(c, mode);

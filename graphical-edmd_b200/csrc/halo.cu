@@ -49,100 +49,125 @@ __device__ __forceinline__ int ld_volatile(const int *p)
     return *reinterpret_cast<const volatile int *>(p);
 }
 
-// side 0: first owned row -> lower neighbour's inbox[from=1]; side 1: last owned row -> upper's inbox[from=0]
+// One pass over the owned particles serves both boundary rows:
+// side 0: first owned row -> lower neighbour's inbox[from=1];
+// side 1: last owned row  -> upper neighbour's inbox[from=0].
+struct SendArgs {
+    int n_owned, ps, row[2], H, epoch;
+    const int32_t *cid;
+    const double4 *xv;
+    const double *rad;
+    const int32_t *gid;
+    char *peer_inbox[2];
+    const int *ack;     // [2]
+    int32_t *cnt;       // [2] records packed per side
+    int32_t *done;      // finished blocks
+    int32_t *flags;
+};
+
 __global__ void __launch_bounds__(kThreads)
-k_halo_send(int n_owned, int ps, int row, int H, int epoch, const int32_t *__restrict__ cid,
-            const double4 *__restrict__ xv, const double *__restrict__ rad,
-            const int32_t *__restrict__ gid, char *peer_inbox, const int *ack, int32_t *cnt,
-            int32_t *done, int32_t *flags)
+k_halo_send(const __grid_constant__ SendArgs a)
 {
     __shared__ bool last;
-    // do not overwrite a buffer the neighbour may still be reading
-    if (threadIdx.x == 0)
-        while (ld_volatile(ack) < epoch - 2) __nanosleep(50);
+    // do not overwrite a buffer a neighbour may still be reading
+    if (threadIdx.x < 2)
+        while (ld_volatile(a.ack + threadIdx.x) < a.epoch - 2) __nanosleep(50);
     __syncthreads();
-    InboxHeader *hdr = reinterpret_cast<InboxHeader *>(peer_inbox);
-    HaloRec *rec = reinterpret_cast<HaloRec *>(peer_inbox + sizeof(InboxHeader));
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_owned) {
-        const int pc = cid[i];
-        if (pc / ps == row) {
-            const int k = atomicAdd(cnt, 1);
-            if (k < H) {
-                const double4 p = xv[i];
+    if (i < a.n_owned) {
+        const int pc = a.cid[i];
+        const int l = pc / a.ps;
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            if (l != a.row[side]) continue;
+            HaloRec *rec = reinterpret_cast<HaloRec *>(a.peer_inbox[side] + sizeof(InboxHeader));
+            const int k = atomicAdd(a.cnt + side, 1);
+            if (k < a.H) {
+                const double4 p = a.xv[i];
                 HaloRec r;
                 r.x = p.x; r.y = p.y; r.vx = p.z; r.vy = p.w;
-                r.rad = rad[i];
-                r.gid = gid[i];
-                r.cell = pc - row * ps;
+                r.rad = a.rad[i];
+                r.gid = a.gid[i];
+                r.cell = pc - l * a.ps;
                 const uint4 *src = reinterpret_cast<const uint4 *>(&r);
-                uint4 *dst = reinterpret_cast<uint4 *>(rec + k);
+                uint4 *dst = reinterpret_cast<uint4 *>(rec + k);   // peer store over NVLink
                 dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
             } else
-                atomicOr(&flags[kFlagBadCell], 2);   // halo buffer too small
+                atomicOr(&a.flags[kFlagBadCell], 2);   // halo buffer too small
         }
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    if (threadIdx.x == 0) last = atomicAdd(a.done, 1) == (int)gridDim.x - 1;
     __syncthreads();
-    if (last && threadIdx.x == 0) {
-        const int total = min(ld_volatile(cnt), H);
+    if (last && threadIdx.x < 2) {
+        const int side = threadIdx.x;
+        InboxHeader *hdr = reinterpret_cast<InboxHeader *>(a.peer_inbox[side]);
+        const int total = min(ld_volatile(a.cnt + side), a.H);
         *reinterpret_cast<volatile int *>(&hdr->count) = total;
         __threadfence_system();
-        *reinterpret_cast<volatile int *>(&hdr->epoch) = epoch;
+        *reinterpret_cast<volatile int *>(&hdr->epoch) = a.epoch;
         __threadfence_system();
-        *cnt = 0;
-        *done = 0;
+        a.cnt[side] = 0;
+        if (side == 0) *a.done = 0;
     }
 }
 
+struct RecvArgs {
+    int H, first, ps, row[2], epoch;
+    const char *inbox[2];
+    double4 *xv;
+    double *rad;
+    int32_t *cid, *gid;
+    int *peer_ack[2];
+    int32_t *done;
+};
+
+// blockIdx.y = from (0: lower neighbour's records -> local row 0, 1: upper -> row nl-1)
 __global__ void __launch_bounds__(kThreads)
-k_halo_recv(int H, int first, int ps, int row, int nx, int epoch, const char *inbox,
-            double4 *__restrict__ xv, double *__restrict__ rad, int32_t *__restrict__ cid,
-            int32_t *__restrict__ gid, int *peer_ack, int32_t *done)
+k_halo_recv(const __grid_constant__ RecvArgs a)
 {
     __shared__ bool last;
-    const InboxHeader *hdr = reinterpret_cast<const InboxHeader *>(inbox);
-    const HaloRec *rec = reinterpret_cast<const HaloRec *>(inbox + sizeof(InboxHeader));
+    const int from = blockIdx.y;
+    const InboxHeader *hdr = reinterpret_cast<const InboxHeader *>(a.inbox[from]);
+    const HaloRec *rec = reinterpret_cast<const HaloRec *>(a.inbox[from] + sizeof(InboxHeader));
     if (threadIdx.x == 0)
-        while (ld_volatile(&hdr->epoch) != epoch) __nanosleep(50);
+        while (ld_volatile(&hdr->epoch) != a.epoch) __nanosleep(50);
     __syncthreads();
     const int count = ld_volatile(&hdr->count);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < H) {
-        const int i = first + k;
+    if (k < a.H) {
+        const int i = a.first + from * a.H + k;
         if (k < count) {
             const uint4 *src = reinterpret_cast<const uint4 *>(rec + k);
             HaloRec r;
             uint4 *dst = reinterpret_cast<uint4 *>(&r);
             dst[0] = __ldcv(src); dst[1] = __ldcv(src + 1); dst[2] = __ldcv(src + 2);
-            xv[i] = make_double4(r.x, r.y, r.vx, r.vy);
-            rad[i] = r.rad;
-            gid[i] = r.gid;
-            cid[i] = row * ps + r.cell;
+            a.xv[i] = make_double4(r.x, r.y, r.vx, r.vy);
+            a.rad[i] = r.rad;
+            a.gid[i] = r.gid;
+            a.cid[i] = a.row[from] * a.ps + r.cell;
         } else {
-            cid[i] = -1;
-            gid[i] = -1;
+            a.cid[i] = -1;   // unused slot: skipped by the cell index
+            a.gid[i] = -1;
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    if (threadIdx.x == 0) last = atomicAdd(a.done + from, 1) == (int)gridDim.x - 1;
     __syncthreads();
     if (last && threadIdx.x == 0) {
         __threadfence_system();
-        *reinterpret_cast<volatile int *>(peer_ack) = epoch;
+        *reinterpret_cast<volatile int *>(a.peer_ack[from]) = a.epoch;   // "consumed", peer store
         __threadfence_system();
-        *done = 0;
+        a.done[from] = 0;
     }
-    (void)nx;
 }
 
 }  // namespace
 
 size_t edmd_halo_mem_bytes(int halo_cap) { return ack_offset(halo_cap) + 256; }
 
-// Launches send(both sides) then recv(both sides) on the context's stream.
+// Launches one send and one recv kernel on the context's stream.
 int edmd_launch_halo_p2p(edmd_ctx *c)
 {
     const int H = c->halo_cap;
@@ -151,25 +176,28 @@ int edmd_launch_halo_p2p(edmd_ctx *c)
     const int n = c->n_owned;
     const int nl = c->dbox.nl;
     int32_t *cnt = c->halo_cnt;
-    int *my_ack = reinterpret_cast<int *>(c->halo_mem + ack_offset(H));
+    SendArgs sa;
+    sa.n_owned = n; sa.ps = c->ps; sa.H = H; sa.epoch = e;
+    sa.row[0] = 1;          // my first owned row -> LOWER neighbour, where I am its upper one (from = 1)
+    sa.row[1] = nl - 2;     // my last owned row  -> UPPER neighbour, where I am its lower one (from = 0)
+    sa.cid = c->cid; sa.xv = c->xv; sa.rad = c->rad; sa.gid = c->gid;
+    sa.peer_inbox[0] = c->peer_mem[0] + inbox_offset(H, 1, par);
+    sa.peer_inbox[1] = c->peer_mem[1] + inbox_offset(H, 0, par);
+    sa.ack = reinterpret_cast<const int *>(c->halo_mem + ack_offset(H));
+    sa.cnt = cnt; sa.done = cnt + 2; sa.flags = c->flags;
     const int sblocks = n > 0 ? (n + kThreads - 1) / kThreads : 1;
-    // my first owned row goes to the LOWER neighbour, where I am its upper one (from = 1)
-    k_halo_send<<<sblocks, kThreads, 0, c->stream>>>(n, c->ps, 1, H, e, c->cid, c->xv, c->rad, c->gid,
-                                                     c->peer_mem[0] + inbox_offset(H, 1, par), my_ack + 0,
-                                                     cnt + 0, cnt + 2, c->flags);
-    // my last owned row goes to the UPPER neighbour, where I am its lower one (from = 0)
-    k_halo_send<<<sblocks, kThreads, 0, c->stream>>>(n, c->ps, nl - 2, H, e, c->cid, c->xv, c->rad, c->gid,
-                                                     c->peer_mem[1] + inbox_offset(H, 0, par), my_ack + 1,
-                                                     cnt + 1, cnt + 3, c->flags);
-    const int rblocks = (H + kThreads - 1) / kThreads;
-    // from the lower neighbour: its last row = my local row 0; I am its UPPER neighbour -> its ack[1]
-    int *ack_lower = reinterpret_cast<int *>(c->peer_mem[0] + ack_offset(H)) + 1;
-    int *ack_upper = reinterpret_cast<int *>(c->peer_mem[1] + ack_offset(H)) + 0;
-    k_halo_recv<<<rblocks, kThreads, 0, c->stream>>>(H, n, c->ps, 0, c->dbox.nx, e,
-                                                     c->halo_mem + inbox_offset(H, 0, par), c->xv, c->rad,
-                                                     c->cid, c->gid, ack_lower, cnt + 4);
-    k_halo_recv<<<rblocks, kThreads, 0, c->stream>>>(H, n + H, c->ps, nl - 1, c->dbox.nx, e,
-                                                     c->halo_mem + inbox_offset(H, 1, par), c->xv, c->rad,
-                                                     c->cid, c->gid, ack_upper, cnt + 5);
-    return 4;
+    k_halo_send<<<sblocks, kThreads, 0, c->stream>>>(sa);
+    RecvArgs ra;
+    ra.H = H; ra.first = n; ra.ps = c->ps; ra.epoch = e;
+    ra.row[0] = 0; ra.row[1] = nl - 1;
+    ra.inbox[0] = c->halo_mem + inbox_offset(H, 0, par);
+    ra.inbox[1] = c->halo_mem + inbox_offset(H, 1, par);
+    ra.xv = c->xv; ra.rad = c->rad; ra.cid = c->cid; ra.gid = c->gid;
+    // consuming the lower neighbour's records: I am its UPPER neighbour -> its ack[1]; and vice versa
+    ra.peer_ack[0] = reinterpret_cast<int *>(c->peer_mem[0] + ack_offset(H)) + 1;
+    ra.peer_ack[1] = reinterpret_cast<int *>(c->peer_mem[1] + ack_offset(H)) + 0;
+    ra.done = cnt + 4;
+    dim3 rgrid((H + kThreads - 1) / kThreads, 2);
+    k_halo_recv<<<rgrid, kThreads, 0, c->stream>>>(ra);
+    return 2;
 }

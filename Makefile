@@ -12,7 +12,8 @@ ARCH       = -gencode arch=compute_100a,code=sm_100a
 # parity-critical arithmetic additionally uses explicit __d*_rn intrinsics.
 NVCCFLAGS  = $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Iinclude -I$(CSRC) \
              -Xcompiler -fPIC,-Wall,-Wno-unused-function
-CU_SRCS    = $(CSRC)/edmd_cuda.cu $(CSRC)/cell_index.cu $(CSRC)/predict.cu $(CSRC)/analysis.cu $(CSRC)/halo.cu
+CU_SRCS    = $(CSRC)/edmd_cuda.cu $(CSRC)/cell_index.cu $(CSRC)/predict.cu $(CSRC)/analysis.cu $(CSRC)/halo.cu \
+             $(CSRC)/lean_index.cu $(CSRC)/predict_lean.cu
 CU_OBJS    = $(CU_SRCS:.cu=.o)
 LIB        = $(PKG)/libedmd_cuda.so
 
@@ -20,7 +21,7 @@ all: cuda host oracle
 
 cuda: $(LIB)
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/edmd_internal.cuh $(CSRC)/rowstage.cuh include/edmd_cuda.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/edmd_internal.cuh $(CSRC)/rowstage.cuh $(CSRC)/pairmath.cuh $(CSRC)/lean.cuh include/edmd_cuda.h
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 $(LIB): $(CU_OBJS)

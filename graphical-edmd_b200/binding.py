@@ -21,6 +21,7 @@ EV_CELLCROSS, EV_COLLISION = 0, 1
 EINVAL, ESTATE, EOVERLAP, ECELL, ENOMEM = 1, 2, 3, 4, 5
 BENCH_SWEEP, BENCH_FREEFLY, BENCH_BOOP, BENCH_PCF = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 1
+OPT_NO_LEAN = 2
 STAT_EXACT_RESCANS = 1
 
 # every symbol include/edmd_cuda.h declares

@@ -30,14 +30,20 @@ __global__ void __launch_bounds__(kThreads)
 k_pack(int n, size_t N, edmd_dev_box b, int ps, const double *__restrict__ soa,
        const int32_t *__restrict__ cell_xy, double4 *__restrict__ xv,
        double *__restrict__ rad, int32_t *__restrict__ cid,
-       int32_t *__restrict__ flags)
+       int32_t *__restrict__ flags, double rad0)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int ghosts = 0, insane = 0;
+    int ghosts = 0, insane = 0, notmono = 0;
+    float vm = 0.0f;
     if (i < n) {
         double x = soa[i], y = soa[N + i];
-        xv[i] = make_double4(x, y, soa[2 * N + i], soa[3 * N + i]);
-        rad[i] = soa[4 * N + i];
+        const double vx = soa[2 * N + i], vy = soa[3 * N + i], r = soa[4 * N + i];
+        xv[i] = make_double4(x, y, vx, vy);
+        rad[i] = r;
+        // what the lean sweep needs to know (lean.cuh): one common radius, the speed scale
+        notmono = !(r == rad0);
+        vm = __double2float_ru(fmax(fabs(vx), fabs(vy)));
+        if (!(vm == vm)) vm = __int_as_float(0x7f800000);
         int X, Y;
         if (cell_xy) {
             int2 c = reinterpret_cast<const int2 *>(cell_xy)[i];
@@ -68,9 +74,13 @@ k_pack(int n, size_t N, edmd_dev_box b, int ps, const double *__restrict__ soa,
     }
     ghosts = __reduce_add_sync(0xffffffffu, ghosts);
     insane = __reduce_add_sync(0xffffffffu, insane);
+    notmono = __reduce_or_sync(0xffffffffu, notmono);
+    const unsigned vmb = __reduce_max_sync(0xffffffffu, (unsigned)__float_as_int(vm));   // vm >= 0: bits order like values
     if ((threadIdx.x & 31) == 0) {
         if (ghosts) atomicAdd(&flags[kFlagGhosts], ghosts);
         if (insane) atomicAdd(&flags[kFlagInsane], insane);
+        if (notmono) atomicOr(&flags[kFlagNotMono], 1);
+        atomicMax(reinterpret_cast<unsigned int *>(&flags[kFlagVmax]), vmb);
     }
 }
 
@@ -332,7 +342,7 @@ int edmd_launch_pack(edmd_ctx *c, bool have_cells, int first, int count)
     if (count == 0) return 0;
     k_pack<<<(count + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(
         count, (size_t)c->n_cap, c->dbox, c->ps, c->in_soa, have_cells ? c->in_cell : nullptr,
-        c->xv + first, c->rad + first, c->cid + first, c->flags);
+        c->xv + first, c->rad + first, c->cid + first, c->flags, c->rad0);
     return 1;
 }
 
@@ -368,11 +378,17 @@ k_halo_pack(int n_owned, int ps, int row, const int32_t *__restrict__ cid,
 __global__ void __launch_bounds__(kThreads)
 k_halo_append(int count, int first, int ps, int row, const HaloRec *__restrict__ in,
               double4 *__restrict__ xv, double *__restrict__ rad, int32_t *__restrict__ cid,
-              int32_t *__restrict__ gid, int nx, int32_t *__restrict__ flags)
+              int32_t *__restrict__ gid, int nx, int32_t *__restrict__ flags, double rad0)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const HaloRec r = in[k];
+    if (!(r.rad == rad0)) atomicOr(&flags[kFlagNotMono], 1);
+    {
+        float vm = __double2float_ru(fmax(fabs(r.vx), fabs(r.vy)));
+        if (!(vm == vm)) vm = __int_as_float(0x7f800000);
+        atomicMax(reinterpret_cast<unsigned int *>(&flags[kFlagVmax]), (unsigned)__float_as_int(vm));
+    }
     const int i = first + k;
     xv[i] = make_double4(r.x, r.y, r.vx, r.vy);
     rad[i] = r.rad;
@@ -398,7 +414,8 @@ int edmd_launch_halo_append_row(edmd_ctx *c, const void *in, int count, int row)
 {
     if (count == 0) return 0;
     k_halo_append<<<(count + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(
-        count, c->n, c->ps, row, (const HaloRec *)in, c->xv, c->rad, c->cid, c->gid, c->dbox.nx, c->flags);
+        count, c->n, c->ps, row, (const HaloRec *)in, c->xv, c->rad, c->cid, c->gid, c->dbox.nx, c->flags,
+        c->rad0);
     return 1;
 }
 

@@ -133,6 +133,8 @@ int check_flags(edmd_ctx *c)
     CU(cudaMemcpyAsync(f, c->flags, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->nghost = f[kFlagGhosts];
+    memcpy(&c->vmax, &f[kFlagVmax], sizeof(float));
+    c->lean_ok = f[kFlagNotMono] == 0 && f[kFlagInsane] == 0 && c->vmax >= 1e-12f && c->vmax <= 1e12f;
     if (f[kFlagBadCell] & 2) {
         CU(cudaMemsetAsync(c->flags + kFlagBadCell, 0, sizeof(int32_t), c->stream));
         return fail(c, EDMD_EINVAL, "halo buffer too small for a boundary row");
@@ -249,6 +251,12 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
     CU(cudaMemsetAsync(c->spos, 0, (c->cap + 32) * sizeof(SPos), c->stream));
     CU(cudaMemsetAsync(c->saux, 0, (c->cap + 32) * sizeof(SAux), c->stream));
     if ((r = dev_alloc(c, &c->svr, c->cap + 32))) return r;
+    CU(cudaMalloc((void **)&c->lrec, (c->cap + 32) * 32));
+    CU(cudaMemsetAsync(c->lrec, 0, (c->cap + 32) * 32, c->stream));   // stale tags must be valid ids
+    if ((r = dev_alloc(c, &c->lchunks, (size_t)c->max_chunks + 8))) return r;
+    if ((r = dev_alloc(c, &c->lres, c->cap + 32))) return r;
+    if ((r = dev_alloc(c, &c->row_state, (size_t)c->dbox.nl + 8))) return r;
+    CU(cudaMemsetAsync(c->row_state, 0, ((size_t)c->dbox.nl + 8) * sizeof(unsigned long long), c->stream));
     if ((r = dev_alloc(c, &c->t_cross, N))) return r;
     if ((r = dev_alloc(c, &c->t_coll, N))) return r;
     if ((r = dev_alloc(c, &c->partner, N))) return r;
@@ -282,6 +290,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->gid, c->cell_cnt,
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
+                   c->lrec, c->lchunks, c->lres, c->row_state,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
                    c->overlap_key, c->flags, c->pcf_counts, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
@@ -314,6 +323,10 @@ int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
     if (!c) return EDMD_EINVAL;
     if (option == EDMD_OPT_FORCE_GENERIC) {
         c->force_generic = value != 0;
+        return 0;
+    }
+    if (option == EDMD_OPT_NO_LEAN) {
+        c->lean_off = value != 0;
         return 0;
     }
     return fail(c, EDMD_EINVAL, "unknown option");
@@ -358,7 +371,9 @@ static int upload_impl(edmd_ctx *c, int n, const double *x, const double *y, con
     if ((r = h2d(c, c->in_soa + 4 * N, rad, B))) return r;
     if (cell_xy && (r = h2d(c, c->in_cell, cell_xy, 2 * (size_t)n * sizeof(int32_t)))) return r;
     if (gid && (r = h2d(c, c->gid, gid, (size_t)n * sizeof(int32_t)))) return r;
-    CU(cudaMemsetAsync(c->flags + kFlagGhosts, 0, 2 * sizeof(int32_t), c->stream));
+    // ghosts, insane, vmax, notmono, leanfail
+    CU(cudaMemsetAsync(c->flags + kFlagGhosts, 0, 5 * sizeof(int32_t), c->stream));
+    c->rad0 = n > 0 ? rad[0] : 1.0;
     c->nghost = 0;
     c->n = n;
     c->n_owned = n;
@@ -548,6 +563,23 @@ int edmd_cuda_set_growth(edmd_ctx *c, const double *vr)
     return 0;
 }
 
+// K0 + K1 on the resident state: the lean path (lean.cuh) when the state is
+// eligible, else the full FP64 path
+static int sweep_launch(edmd_ctx *c, int mode)
+{
+    int launched = 0;
+    if (edmd_lean_eligible(c, mode)) {
+        launched += edmd_launch_lean_index(c);
+        launched += edmd_launch_predict_lean(c);
+        c->index_lean = true;
+    } else {
+        launched += edmd_launch_cell_index(c, mode);
+        launched += edmd_launch_predict(c, mode);
+        c->index_lean = false;
+    }
+    return launched;
+}
+
 int edmd_cuda_predict_device(edmd_ctx *c, int mode)
 {
     if (!c) return EDMD_EINVAL;
@@ -556,11 +588,29 @@ int edmd_cuda_predict_device(edmd_ctx *c, int mode)
     if (mode == EDMD_MODE_GROW && !c->have_vr) return fail(c, EDMD_ESTATE, "GROW mode needs growth rates");
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));
-    c->launches += edmd_launch_cell_index(c, mode);
-    c->launches += edmd_launch_predict(c, mode);
+    c->launches += sweep_launch(c, mode);
     CU(cudaGetLastError());
     c->have_index = true;
     c->have_pred = true;
+    c->pred_mode = mode;
+    return 0;
+}
+
+// The lean sweep declines on the device when the resident state turns out not
+// to be eligible (facts only the device knows: halo particles, free flight).
+// Redo the sweep with the full path then, and stay on it until the next upload.
+static int lean_fallback(edmd_ctx *c)
+{
+    if (!c->index_lean) return 0;
+    int32_t f = 0;
+    CU(cudaMemcpyAsync(&f, c->flags + kFlagLeanFail, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (!f) return 0;
+    c->lean_ok = false;
+    CU(cudaMemsetAsync(c->flags + kFlagLeanFail, 0, sizeof(int32_t), c->stream));
+    CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));
+    c->launches += sweep_launch(c, c->pred_mode);
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -572,6 +622,7 @@ int edmd_cuda_fetch_predictions(edmd_ctx *c, double *t_cross, uint8_t *dir, doub
     CU(cudaSetDevice(c->device));
     size_t N = (size_t)c->n_owned;
     int r;
+    if ((r = lean_fallback(c))) return r;
     if (t_cross && (r = d2h(c, t_cross, c->t_cross, N * sizeof(double)))) return r;
     if (t_coll && (r = d2h(c, t_coll, c->t_coll, N * sizeof(double)))) return r;
     if (partner && (r = d2h(c, partner, c->partner, N * sizeof(int32_t)))) return r;
@@ -649,11 +700,12 @@ int edmd_cuda_download_state(edmd_ctx *c, double *x, double *y, double *vx, doub
 
 static int ensure_index(edmd_ctx *c)
 {
-    if (c->have_index) return 0;
-    if (c->n == 0) { c->have_index = true; return 0; }
+    if (c->have_index && !c->index_lean) return 0;   // analysis kernels read the full records
+    if (c->n == 0) { c->have_index = true; c->index_lean = false; return 0; }
     c->launches += edmd_launch_cell_index(c, EDMD_MODE_NORMAL);
     CU(cudaGetLastError());
     c->have_index = true;
+    c->index_lean = false;
     return 0;
 }
 
@@ -796,11 +848,20 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
                 c->n = c->n_owned + 2 * c->halo_cap;
                 c->nghost_extra = 2 * c->halo_cap;
             }
-            c->launches += edmd_launch_cell_index(c, mode);
-            if (e) CU(cudaEventRecord(e[1], c->stream));
-            c->launches += edmd_launch_predict(c, mode);
+            if (edmd_lean_eligible(c, mode)) {
+                c->launches += edmd_launch_lean_index(c);
+                if (e) CU(cudaEventRecord(e[1], c->stream));
+                c->launches += edmd_launch_predict_lean(c);
+                c->index_lean = true;
+            } else {
+                c->launches += edmd_launch_cell_index(c, mode);
+                if (e) CU(cudaEventRecord(e[1], c->stream));
+                c->launches += edmd_launch_predict(c, mode);
+                c->index_lean = false;
+            }
             c->have_index = true;
             c->have_pred = true;
+            c->pred_mode = mode;
             break;
         case EDMD_BENCH_FREEFLY:
             if (e) CU(cudaEventRecord(e[1], c->stream));
@@ -824,6 +885,11 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
     }
     CU(cudaStreamSynchronize(c->stream));
     c->t = t_keep;
+    if (what == EDMD_BENCH_SWEEP && c->index_lean) {
+        int32_t f = 0;
+        CU(cudaMemcpy(&f, c->flags + kFlagLeanFail, sizeof(f), cudaMemcpyDeviceToHost));
+        if (f) return fail(c, EDMD_ESTATE, "bench: the lean sweep declined (state not eligible); fetch once, then bench");
+    }
     for (int it = 0; it < iters; it++) {
         float a = 0, b = 0;
         CU(cudaEventElapsedTime(&a, evs[3 * (size_t)it], evs[3 * (size_t)it + 2]));

@@ -116,7 +116,14 @@ struct CellIndex {
 };
 
 // device flag words
-enum { kFlagBadCell = 0, kFlagRescans = 1, kFlagGhosts = 2, kFlagInsane = 3, kFlagCount = 8 };
+enum {
+    kFlagBadCell = 0, kFlagRescans = 1, kFlagGhosts = 2, kFlagInsane = 3,
+    kFlagVmax = 4,       // bits of the largest |velocity component| (float, rounded up)
+    kFlagNotMono = 5,    // some radius differs from the first particle's
+    kFlagLeanFail = 6,   // the lean sweep declined (state not eligible): redo with the full path
+    kFlagTicket = 7,     // row ticket of the lean index kernel
+    kFlagCount = 16
+};
 
 struct edmd_ctx {
     int device;
@@ -136,6 +143,13 @@ struct edmd_ctx {
     bool have_pred;      // device predictions valid
     bool have_index;     // cell index matches resident state
     bool index_has_vr;   // ... and carries growth rates
+    bool index_lean;     // ... but is the LEAN index (lean.cuh): no spos / saux records
+    bool lean_ok;        // resident state is eligible for the lean sweep (monodisperse, sane speeds)
+    bool lean_off;       // EDMD_OPT_NO_LEAN
+    double rad0;         // radius of the first particle (the common radius when lean_ok)
+    float vmax;          // largest |velocity component| of the upload
+    uint32_t index_epoch;
+    int pred_mode;       // mode of the last sweep
     bool have_vr;
     double t;            // time of the resident snapshot
     int nghost;          // ghost entries of the current upload
@@ -173,6 +187,11 @@ struct edmd_ctx {
     SPos *spos;
     SAux *saux;
     double *svr;
+    // lean index (lean.cuh)
+    struct LeanRec *lrec;            // 32-byte records in cell order
+    int4 *lchunks;
+    int2 *lres;                      // k_screen -> k_resolve: (winner slot, second bound) per slot
+    unsigned long long *row_state;   // [nl] (epoch << 32 | row total rounded up to 32)
 
     // outputs
     double *t_cross, *t_coll;
@@ -231,6 +250,9 @@ int edmd_launch_halo_p2p(edmd_ctx *c);
 int edmd_launch_cell_index(edmd_ctx *c, int mode);
 int edmd_launch_predict(edmd_ctx *c, int mode);
 int edmd_launch_free_fly(edmd_ctx *c, int mode, double dt);
+int edmd_launch_lean_index(edmd_ctx *c);
+int edmd_launch_predict_lean(edmd_ctx *c);
+bool edmd_lean_eligible(const edmd_ctx *c, int mode);
 int edmd_launch_boop(edmd_ctx *c, double r_c);
 int edmd_launch_mean(edmd_ctx *c, const double *v, int n, double *out_dev);
 int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,

@@ -121,6 +121,8 @@ struct RecvArgs {
     int32_t *cid, *gid;
     int *peer_ack[2];
     int32_t *done;
+    int32_t *flags;
+    double rad0;
 };
 
 // blockIdx.y = from (0: lower neighbour's records -> local row 0, 1: upper -> row nl-1)
@@ -147,6 +149,12 @@ k_halo_recv(const __grid_constant__ RecvArgs a)
             a.rad[i] = r.rad;
             a.gid[i] = r.gid;
             a.cid[i] = a.row[from] * a.ps + r.cell;
+            // keep the lean sweep's eligibility facts current (lean.cuh)
+            if (!(r.rad == a.rad0)) atomicOr(&a.flags[kFlagNotMono], 1);
+            float vm = __double2float_ru(fmax(fabs(r.vx), fabs(r.vy)));
+            if (!(vm == vm)) vm = __int_as_float(0x7f800000);
+            if (__float_as_int(vm) > a.flags[kFlagVmax])
+                atomicMax(reinterpret_cast<unsigned int *>(&a.flags[kFlagVmax]), (unsigned)__float_as_int(vm));
         } else {
             a.cid[i] = -1;   // unused slot: skipped by the cell index
             a.gid[i] = -1;
@@ -197,6 +205,8 @@ int edmd_launch_halo_p2p(edmd_ctx *c)
     ra.peer_ack[0] = reinterpret_cast<int *>(c->peer_mem[0] + ack_offset(H)) + 1;
     ra.peer_ack[1] = reinterpret_cast<int *>(c->peer_mem[1] + ack_offset(H)) + 0;
     ra.done = cnt + 4;
+    ra.flags = c->flags;
+    ra.rad0 = c->rad0;
     dim3 rgrid((H + kThreads - 1) / kThreads, 2);
     k_halo_recv<<<rgrid, kThreads, 0, c->stream>>>(ra);
     return 2;

@@ -1,0 +1,68 @@
+// lean.cuh -- data layout of the LEAN cell index and of the certified-FP32
+// prediction sweep built on it (lean_index.cu, predict_lean.cu).
+//
+// The lean path is taken for the re-predict sweep of a MONODISPERSE system in
+// NORMAL mode (every BASELINE.json configuration but the reference's default
+// bidisperse run, which keeps the FP64 row kernel of predict.cu).  It moves
+// fewer bytes and issues fewer instructions than the full path:
+//
+//   K0-lean  count (RED atomics, no ranks) -> ONE index kernel (row scan, row
+//            bases by a flag-synchronised prefix over the row totals, chunk plan)
+//            -> scatter of ONE 32-byte record per particle (= one L2 sector, one
+//            256-bit store): a 16-byte FP32 "screening record" + (id, cell) tag;
+//            the FP64 state is NOT copied, it is read by particle id where
+//            needed (own particle: coalesced; the winner: one gather).
+//   K1-lean  per candidate, FP32 arithmetic produces a RIGOROUS LOWER BOUND of
+//            the reference's collision time (collisionTimeNormal,
+//            src/EDMD.c:2661-2723); the candidate with the smallest bound is
+//            evaluated in FP64 exactly as the reference does, and accepted only
+//            if its exact time lies below every other candidate's bound.  If
+//            not (near ties, near-contact pairs, overlaps) the particle is
+//            redone by the exact FP64 loop in the reference's order.  Results
+//            are therefore the reference's, bit for bit; FP32 only decides
+//            which ONE pair gets the exact evaluation.
+//
+// Screening record of a particle filed under padded cell column pcx of row Y:
+//     rx = (float)(x - (pcx - 1 + 0.5) * csx)     cell-centre relative
+//     ry = (float)(y - (Yglobal + 0.5) * csy)
+//     vx, vy = (float) velocities
+// Ghost copies (padded columns 0 and nx+1) carry the SAME rx, so the
+// displacement between a particle in column a and a candidate in column b is
+// (rx_b - rx_a) + (b - a) * csx with no periodic image logic at all; rows
+// likewise.  (Needs nx, ny >= 12 and every particle within 1.5 cells of the
+// centre of the cell it is filed under, which upload / free flight check.)
+#pragma once
+
+#include "edmd_internal.cuh"
+
+constexpr int kLeanCap = 144;   // screening records staged per chunk (three row segments, packed)
+constexpr int kLeanOffW = 64;   // cell-offset window per row
+
+// one particle in cell order: exactly one 32-byte sector
+struct __align__(32) LeanRec {
+    float rx, ry, vx, vy;   // screening record (the half that is staged in shared memory)
+    int id, pc;             // particle id, padded cell id
+    int pad0, pad1;
+};
+static_assert(sizeof(LeanRec) == 32, "LeanRec must be one sector");
+
+// per 32-slot chunk: x = cell row (-1: nothing to predict), y = first / z = last
+// padded column holding active entries of the chunk, w = end slot of the row
+typedef int4 LeanChunk;
+
+struct LeanIndex {
+    int nx, nl, ps;
+    const int32_t *off;        // row-local exclusive scan, [nl * ps]
+    const int32_t *row_base;   // [nl + 1]
+    const LeanChunk *chunks;
+    const LeanRec *rec;        // cell order
+};
+
+// constants of the FP32 error analysis (see predict_lean.cu)
+struct LeanConsts {
+    float csx, csy;
+    float inv_rho2, inv_om2;   // Psi = d2 * inv_rho2 + v2 * inv_om2 + 1
+    float A, Cc;               // c_lo = d2 * A - Cc
+    float Kb, Kdet;            // B_up = Kb * Psi - b ; det_up = det + Kdet * Psi^2
+    int ok;                    // 0: velocity scale outside the FP32-safe range
+};

@@ -80,6 +80,11 @@ uint64_t edmd_cuda_launch_count(const edmd_ctx *ctx);
  * global-memory kernel (the reference's loops as written) instead of the tiled
  * two-phase kernel; results are identical, it exists for cross-checking. */
 #define EDMD_OPT_FORCE_GENERIC 1
+/* EDMD_OPT_NO_LEAN = 1 keeps monodisperse NORMAL-mode sweeps on the full FP64
+ * row kernel instead of the lean path (FP32 screening certified against the
+ * exact FP64 evaluation, graphical-edmd_b200/csrc/lean.cuh); results are
+ * identical, it exists for cross-checking and timing. */
+#define EDMD_OPT_NO_LEAN 2
 int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 /* Counters: EDMD_STAT_EXACT_RESCANS = particles the tiled sweep had to resolve
  * with the exact re-scan (near-ties, ill-conditioned pairs) since create. */

@@ -321,6 +321,58 @@ def test_tiled_and_generic_kernels_agree(pkg, n, phi, seed, sf):
     assert rescans < 0.02 * c["n"], rescans
 
 
+# ------------------------------- lean (certified FP32 screening) vs full FP64 ----
+@pytest.mark.parametrize("n,phi,seed,vscale", [(300000, 0.70, 41, 1.0), (300000, 0.85, 42, 1.0),
+                                               (200000, 0.72, 43, 1e-6), (200000, 0.55, 44, 3e4),
+                                               (50000, 0.30, 45, 1.0)])
+def test_lean_and_full_sweeps_agree(pkg, n, phi, seed, vscale):
+    """Monodisperse NORMAL-mode sweeps take the lean path: FP32 lower bounds pick
+    the one pair that gets the exact FP64 evaluation.  Same bits as the full FP64
+    kernel at any velocity scale; the exact re-scan must stay rare."""
+    c = pkg.synth.lattice_config(n, phi, seed)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"] * vscale, c["vy"] * vscale, c["rad"], t=4.0)
+        r0 = ctx.stat(pkg.binding.STAT_EXACT_RESCANS)
+        a = ctx.predict_all()
+        rescans = ctx.stat(pkg.binding.STAT_EXACT_RESCANS) - r0
+        ctx.set_option(pkg.binding.OPT_NO_LEAN, 1)
+        b = ctx.predict_all()
+    for k in ("t_cross", "dir", "t_coll", "partner", "ctype"):
+        assert np.array_equal(a[k], b[k]), k
+    assert rescans < 0.02 * c["n"], rescans
+
+
+def test_lean_handles_heavy_velocity_tails_and_rest(pkg, oracle):
+    """A few very fast particles set the FP32 velocity scale (loose bounds => more
+    re-scans, same answers); particles at rest never collide by themselves."""
+    c = pkg.synth.lattice_config(60000, 0.70, seed=46)
+    vx, vy = c["vx"].copy(), c["vy"].copy()
+    vx[::1000] *= 500.0
+    vy[::1000] *= -300.0
+    vx[1::7] = 0.0
+    vy[1::7] = 0.0
+    c["vx"], c["vy"] = vx, vy
+    got = gpu_sweep(pkg, c, t=3.0)
+    want = oracle_sweep(oracle, c, t=3.0)
+    assert_events_equal(got, want)
+
+
+def test_lean_declines_after_free_flight_out_of_the_cells(pkg, oracle):
+    """Free flight moves particles but not their (host-owned) cells; once some
+    particle is more than a cell away from where it is filed the lean sweep
+    declines on the device and the call falls back to the full path."""
+    c = pkg.synth.lattice_config(20000, 0.30, seed=47)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        ctx.free_fly(1.5)
+        s = ctx.download_state()
+        cells = oracle.cells(c["n"], c["lx"], c["ly"], c["x"], c["y"]).reshape(c["n"], 2)
+        got = ctx.predict_all(allow_overlap=True)
+    c2 = dict(c, x=s["x"], y=s["y"])
+    want = oracle_sweep(oracle, c2, t=1.5, cells=cells)
+    assert_events_equal(got, want)
+
+
 def test_dense_small_disks_overflow_the_tile_buffer(pkg, oracle):
     """Many tiny disks per cell: more particles than a tile's staging buffer
     holds, so CTAs take the global-memory path; results unchanged."""

@@ -251,12 +251,22 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
     CU(cudaMemsetAsync(c->spos, 0, (c->cap + 32) * sizeof(SPos), c->stream));
     CU(cudaMemsetAsync(c->saux, 0, (c->cap + 32) * sizeof(SAux), c->stream));
     if ((r = dev_alloc(c, &c->svr, c->cap + 32))) return r;
-    CU(cudaMalloc((void **)&c->lrec, (c->cap + 32) * 32));
-    CU(cudaMemsetAsync(c->lrec, 0, (c->cap + 32) * 32, c->stream));   // stale tags must be valid ids
-    if ((r = dev_alloc(c, &c->lchunks, (size_t)c->max_chunks + 8))) return r;
-    if ((r = dev_alloc(c, &c->lres, c->cap + 32))) return r;
-    if ((r = dev_alloc(c, &c->row_state, (size_t)c->dbox.nl + 8))) return r;
-    CU(cudaMemsetAsync(c->row_state, 0, ((size_t)c->dbox.nl + 8) * sizeof(unsigned long long), c->stream));
+    // lean index: every cell row owns rowcap slots (3x the mean row population + slack;
+    // a denser row makes the lean sweep decline and the full path take over)
+    {
+        const long long mean = (long long)((N + (size_t)c->dbox.nl - 1) / (size_t)c->dbox.nl) + 8;
+        const long long rc = (3 * mean + 64 + 31) & ~31ll;
+        const long long slots = rc * c->dbox.nl;
+        if (slots < (1ll << 30)) {
+            c->rowcap = (int)rc;
+            c->lean_chunks = (int)(slots / 32);
+            CU(cudaMalloc((void **)&c->lrec, ((size_t)slots + 32) * 32));
+            CU(cudaMemsetAsync(c->lrec, 0, ((size_t)slots + 32) * 32, c->stream));   // stale tags must be valid ids
+            if ((r = dev_alloc(c, &c->lchunks, (size_t)c->lean_chunks + 8))) return r;
+            if ((r = dev_alloc(c, &c->lres, N + 32))) return r;
+            if ((r = dev_alloc(c, &c->lwork, (size_t)c->lean_chunks + 8))) return r;
+        }
+    }
     if ((r = dev_alloc(c, &c->t_cross, N))) return r;
     if ((r = dev_alloc(c, &c->t_coll, N))) return r;
     if ((r = dev_alloc(c, &c->partner, N))) return r;
@@ -290,7 +300,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->gid, c->cell_cnt,
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
-                   c->lrec, c->lchunks, c->lres, c->row_state,
+                   c->lrec, c->lchunks, c->lres, c->lwork,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
                    c->overlap_key, c->flags, c->pcf_counts, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};

@@ -121,7 +121,7 @@ enum {
     kFlagVmax = 4,       // bits of the largest |velocity component| (float, rounded up)
     kFlagNotMono = 5,    // some radius differs from the first particle's
     kFlagLeanFail = 6,   // the lean sweep declined (state not eligible): redo with the full path
-    kFlagTicket = 7,     // row ticket of the lean index kernel
+    kFlagWork = 7,       // number of entries in the lean work list (chunks that hold particles)
     kFlagCount = 16
 };
 
@@ -188,10 +188,12 @@ struct edmd_ctx {
     SAux *saux;
     double *svr;
     // lean index (lean.cuh)
-    struct LeanRec *lrec;            // 32-byte records in cell order
+    struct LeanRec *lrec;            // 32-byte records in cell order, rowcap slots per cell row
+    int rowcap;                      // multiple of 32
+    int lean_chunks;                 // nl * rowcap / 32
+    int32_t *lwork;                  // chunk ids that hold particles, any order (kFlagWork entries)
     int4 *lchunks;
     int2 *lres;                      // k_screen -> k_resolve: (winner slot, second bound) per slot
-    unsigned long long *row_state;   // [nl] (epoch << 32 | row total rounded up to 32)
 
     // outputs
     double *t_cross, *t_coll;

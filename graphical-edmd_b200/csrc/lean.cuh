@@ -6,8 +6,9 @@
 // bidisperse run, which keeps the FP64 row kernel of predict.cu).  It moves
 // fewer bytes and issues fewer instructions than the full path:
 //
-//   K0-lean  count (RED atomics, no ranks) -> ONE index kernel (row scan, row
-//            bases by a flag-synchronised prefix over the row totals, chunk plan)
+//   K0-lean  count (RED atomics, no ranks) -> ONE index kernel (row scan + chunk
+//            plan; every cell row owns a FIXED range of `rowcap` slots, so rows
+//            are independent: no scan across rows, no second pass)
 //            -> scatter of ONE 32-byte record per particle (= one L2 sector, one
 //            256-bit store): a 16-byte FP32 "screening record" + (id, cell) tag;
 //            the FP64 state is NOT copied, it is read by particle id where
@@ -52,9 +53,10 @@ typedef int4 LeanChunk;
 
 struct LeanIndex {
     int nx, nl, ps;
+    int rowcap;                // slots per cell row (multiple of 32): row Y starts at slot Y * rowcap
     const int32_t *off;        // row-local exclusive scan, [nl * ps]
-    const int32_t *row_base;   // [nl + 1]
     const LeanChunk *chunks;
+    const int32_t *work;       // ids of the chunks that hold particles, any order
     const LeanRec *rec;        // cell order
 };
 
@@ -66,3 +68,11 @@ struct LeanConsts {
     float Kb, Kdet;            // B_up = Kb * Psi - b ; det_up = det + Kdet * Psi^2
     int ok;                    // 0: velocity scale outside the FP32-safe range
 };
+
+// one 32-byte sector with a single 256-bit load (LDG.E.ENL2.256 on sm_100a)
+__device__ __forceinline__ double4 ld_sector(const double4 *p)
+{
+    double4 v;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}

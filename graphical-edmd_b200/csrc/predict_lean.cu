@@ -29,9 +29,9 @@
 //              trip; the candidates' 16-byte screening halves are staged in shared
 //              memory by cp.async (double-buffered, planned three chunks ahead);
 //              per slot it leaves (winner slot, second-smallest bound) -- FP32 only
-//   k_resolve  one thread per PARTICLE ID: coalesced own state and outputs; gathers
-//              the winner, evaluates crossing + the exact pair time, certifies or
-//              re-scans
+//   k_resolve  one thread per PARTICLE ID: coalesced own state, screening result and
+//              outputs; ONE gather (the winner's state), crossing + the exact pair
+//              time, certifies or re-scans
 //
 // Error model (u = 2^-24, all FP32 operations are explicit round-to-nearest
 // mul / add / fma, MUFU rsqrt / rcp with relative error < 2^-21):
@@ -68,16 +68,17 @@ struct __align__(16) LeanBuf {
     int plan[16];
 };
 // plan words
-enum { kPlStatus = 0, kPlY = 1, kPlRowEnd = 2, kPlWstart = 3, kPlSegLo = 4, kPlBase = 7, kPlCum = 10 };
+enum { kPlStatus = 0, kPlY = 1, kPlRowEnd = 2, kPlWstart = 3, kPlSegLo = 4, kPlCum1 = 7, kPlBase = 8,
+       kPlCum2 = 11 };
 //   status  0 empty, 1 staged, 2 not staged (segments exceed the buffer)
-//   SegLo[j] absolute slot of row j's segment;  Cum[j] its first index in scr[];
+//   SegLo[j] absolute slot of row j's segment;  Cum1 / Cum2 first scr[] index of rows 1 / 2;
 //   Base[j]  row-local cell offset o  ->  scr index o + Base[j]
 
 constexpr size_t kLeanSmem = sizeof(LeanBuf) * 2 * kLeanWarps;
 
-// what k_screen leaves per slot: x = winner's slot (kResNone: no candidate can
-// collide), y = bits of the second-smallest lower bound (NaN when the smallest
-// bound is not positive: never certifiable)
+// what k_screen leaves per PARTICLE ID: x = winner's particle id (kResNone: no
+// candidate can collide), y = bits of the second-smallest lower bound (NaN when
+// the smallest bound is not positive: never certifiable)
 enum { kResNone = -1 };
 
 struct ScreenArgs {
@@ -135,89 +136,60 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 }
 
 // ---- chunk planning and staging ------------------------------------------------
-// A chunk's plan is made in steps so that no load is waited for: its LeanChunk
-// word is fetched three trips ahead (lane k < 4 keeps component k), the row
-// bases / segment bounds two trips ahead (lane j < 3 keeps row Y-1+j), and the
-// copies (cp.async, 16 bytes each: the screening half of the 32-byte records,
-// and the windows of cell offsets) are issued one trip ahead by all lanes.
-struct RowPlan {
-    int rb, sa, sb;   // lane j < 3: row base, first and end offset of the row's segment
-};
-
-__device__ __forceinline__ int plan_word(const LeanIndex &g, int c, int nchunks, int lane)
+// All lanes read the six segment bounds of the chunk (uniform addresses: one
+// transaction each), then issue the copies one trip ahead:
+// cp.async, 16 bytes each -- the screening half of the 32-byte records of the
+// three row segments, packed back to back, and the windows of cell offsets.
+// Lane 0 leaves the plan in shared memory for the trip that consumes the buffer.
+__device__ __forceinline__ void plan_stage(const LeanIndex &g, LeanBuf *buf, const LeanChunk &m, int lane)
 {
-    return (c < nchunks && lane < 4) ? reinterpret_cast<const int *>(g.chunks + c)[lane] : -1;
-}
-
-__device__ __forceinline__ RowPlan plan_rows(const LeanIndex &g, int mw, int lane)
-{
-    const int Y = __shfl_sync(0xffffffffu, mw, 0);
-    const int ca = __shfl_sync(0xffffffffu, mw, 1);
-    const int cb = __shfl_sync(0xffffffffu, mw, 2);
-    RowPlan r;
-    r.rb = r.sa = r.sb = 0;
-    if (Y >= 0 && lane < 3) {
-        const int Yr = row_wrap(Y - 1 + lane, g.nl);
-        r.rb = g.row_base[Yr];
-        const int32_t *o = g.off + (size_t)Yr * g.ps;
-        r.sa = o[ca - 1];
-        r.sb = o[cb + 2];
-    }
-    return r;
-}
-
-__device__ __forceinline__ void plan_stage(const LeanIndex &g, LeanBuf *buf, int mw, const RowPlan &r,
-                                           int lane)
-{
-    const int Y = __shfl_sync(0xffffffffu, mw, 0);
-    const int ca = __shfl_sync(0xffffffffu, mw, 1);
-    const int cb = __shfl_sync(0xffffffffu, mw, 2);
-    const int row_end = __shfl_sync(0xffffffffu, mw, 3);
-    int seg_lo[3], cum[4];
-    cum[0] = 0;
+    const int Y = m.x, ca = m.y, cb = m.z;
+    int status = 0;
+    if (Y >= 0) {
+        int Yr[3], sa[3], sb[3];
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const int rb = __shfl_sync(0xffffffffu, r.rb, j);
-        const int sa = __shfl_sync(0xffffffffu, r.sa, j);
-        const int sb = __shfl_sync(0xffffffffu, r.sb, j);
-        seg_lo[j] = rb + sa;
-        cum[j + 1] = cum[j] + (sb - sa);
+        for (int j = 0; j < 3; j++) {
+            Yr[j] = row_wrap(Y - 1 + j, g.nl);
+            const int32_t *o = g.off + (size_t)Yr[j] * g.ps;
+            sa[j] = o[ca - 1];
+            sb[j] = o[cb + 2];
+        }
+        const int wstart = (ca - 1) & ~3;
+        int wlen = ((cb + 2 - wstart + 1) + 3) & ~3;   // columns wstart .. cb+2, rounded up to 4
+        if (wstart + wlen > g.ps) wlen = g.ps - wstart;
+        const int cum1 = sb[0] - sa[0], cum2 = cum1 + (sb[1] - sa[1]), cum3 = cum2 + (sb[2] - sa[2]);
+        status = (cum3 > kLeanCap || wlen > kLeanOffW) ? 2 : 1;
+        const int lo0 = Yr[0] * g.rowcap + sa[0], lo1 = Yr[1] * g.rowcap + sa[1],
+                  lo2 = Yr[2] * g.rowcap + sa[2];
         if (lane == 0) {
-            buf->plan[kPlSegLo + j] = seg_lo[j];
-            buf->plan[kPlBase + j] = cum[j] - sa;
-            buf->plan[kPlCum + j] = cum[j];
+            int4 *pl = reinterpret_cast<int4 *>(buf->plan);
+            pl[0] = make_int4(status, Y, m.w, wstart);
+            pl[1] = make_int4(lo0, lo1, lo2, cum1);
+            pl[2] = make_int4(-sa[0], cum1 - sa[1], cum2 - sa[2], cum2);
         }
-    }
-    const int wstart = (ca - 1) & ~3;
-    int wlen = ((cb + 2 - wstart + 1) + 3) & ~3;   // columns wstart .. cb+2, rounded up to 4
-    if (wstart + wlen > g.ps) wlen = g.ps - wstart;
-    const int status = Y < 0 ? 0 : ((cum[3] > kLeanCap || wlen > kLeanOffW) ? 2 : 1);
-    if (lane == 0) {
-        buf->plan[kPlStatus] = status;
-        buf->plan[kPlY] = Y;
-        buf->plan[kPlRowEnd] = row_end;
-        buf->plan[kPlWstart] = wstart;
-    }
-    if (status == 1) {
+        if (status == 1) {
+            // packed index q of scr[] -> record  q + (q < cum1 ? lo0 : q < cum2 ? lo1 - cum1 : lo2 - cum2)
+            const int d1 = lo1 - cum1, d2 = lo2 - cum2;
+            const uint32_t dst = smem_u32(&buf->scr[lane]);
 #pragma unroll
-        for (int t = 0; t < (kLeanCap + 31) / 32; t++) {
-            const int q = lane + 32 * t;
-            if (q < cum[3]) {
-                const int j = (q >= cum[1]) + (q >= cum[2]);
-                const int src = (j == 0 ? seg_lo[0] : (j == 1 ? seg_lo[1] : seg_lo[2])) -
-                                (j == 0 ? 0 : (j == 1 ? cum[1] : cum[2])) + q;
-                cp_async16(&buf->scr[q], g.rec + src);
+            for (int t = 0; t < (kLeanCap + 31) / 32; t++) {
+                const int q = lane + 32 * t;
+                const int src = q + (q < cum1 ? lo0 : (q < cum2 ? d1 : d2));
+                if (q < cum3)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u * t),
+                                 "l"(g.rec + src)
+                                 : "memory");
+            }
+            // windows: 16-byte granules, rows 0 and 1 by the two half-warps, then row 2
+            const int h = lane >> 4, k4 = 4 * (lane & 15);
+            if (k4 < wlen) {
+                const int32_t *wsrc = g.off + wstart + k4;
+                cp_async16(&buf->offw[h][k4], wsrc + (size_t)(h ? Yr[1] : Yr[0]) * g.ps);
+                if (h == 0) cp_async16(&buf->offw[2][k4], wsrc + (size_t)Yr[2] * g.ps);
             }
         }
-#pragma unroll
-        for (int t = 0; t < (3 * kLeanOffW / 4 + 31) / 32; t++) {
-            const int q = lane + 32 * t;   // 16-byte granule
-            const int j = q / (kLeanOffW / 4), k4 = 4 * (q % (kLeanOffW / 4));
-            if (j < 3 && k4 < wlen) {
-                const int Yr = row_wrap(Y - 1 + j, g.nl);
-                cp_async16(&buf->offw[j][k4], g.off + (size_t)Yr * g.ps + wstart + k4);
-            }
-        }
+    } else if (lane == 0) {
+        buf->plan[kPlStatus] = 0;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -226,11 +198,28 @@ __device__ __forceinline__ void plan_stage(const LeanIndex &g, LeanBuf *buf, int
 // STAGED: candidates and cell offsets come from the warp's shared buffer; else
 // (segments exceed the buffer: very dense rows, clustered tiny disks) from
 // global memory, same arithmetic.
+// The result (winner's particle id, second bound) is handed back in `out`
+// (out.id < 0: nothing to store) with the id gather still in flight: the caller
+// stores it one trip later, so nobody waits for that load.
+struct Pending {
+    int id, wid, y;
+};
+
+// Store a particle's screening result (the winner-id gather issued one trip ago
+// has landed by now).  Measured: prefetching the FP64 states k_resolve will read
+// into L2 from here does not make k_resolve faster.
+__device__ __forceinline__ void flush_pending(const ScreenArgs &a, Pending &pend)
+{
+    if (pend.id >= 0) a.res[pend.id] = make_int2(pend.wid, pend.y);
+    pend.id = -1;
+}
+
 template <bool STAGED>
 __device__ __forceinline__ void screen_chunk(const ScreenArgs &a, const LeanConsts &K, const LeanBuf &w,
-                                             int c, int lane, int pc)
+                                             int c, int lane, int2 tag, Pending &out)
 {
     const LeanIndex &g = a.g;
+    const int pc = tag.y;
     const int Y = w.plan[kPlY];
     const int s = c * 32 + lane;
     const bool valid = s < w.plan[kPlRowEnd];
@@ -250,7 +239,7 @@ __device__ __forceinline__ void screen_chunk(const ScreenArgs &a, const LeanCons
             hi[j] = active ? w.offw[j][wi + 3] + base : 0;
         } else {
             const int Yr = row_wrap(Y - 1 + j, g.nl);
-            const int rb = g.row_base[Yr];
+            const int rb = Yr * g.rowcap;
             const int32_t *o = g.off + (size_t)Yr * g.ps + (active ? pcx - 1 : 0);
             lo[j] = active ? rb + o[0] : 0;
             t1[j] = rb + o[1];
@@ -259,7 +248,7 @@ __device__ __forceinline__ void screen_chunk(const ScreenArgs &a, const LeanCons
         }
     }
     const float4 *scr = STAGED ? w.scr : nullptr;
-    const int self = STAGED ? s - w.plan[kPlSegLo + 1] + w.plan[kPlCum + 1] : s;
+    const int self = STAGED ? s - w.plan[kPlSegLo + 1] + w.plan[kPlCum1] : s;
     const int selfc = active ? self : (STAGED ? 0 : c * 32);
     const float4 own = STAGED ? scr[selfc] : *reinterpret_cast<const float4 *>(g.rec + selfc);
     // dx = rx_j - (rx_i - k csx), k = column(j) - column(i) in {-1, 0, 1}
@@ -304,15 +293,17 @@ __device__ __forceinline__ void screen_chunk(const ScreenArgs &a, const LeanCons
         }
         if (p < pe) screen(j, p, py);
     }
-    if (active) {
-        int2 r;
-        r.x = idx;
-        if (STAGED && idx >= 0) {
-            const int wj = (idx >= w.plan[kPlCum + 1]) + (idx >= w.plan[kPlCum + 2]);
-            r.x = w.plan[kPlSegLo + wj] + (idx - w.plan[kPlCum + wj]);
+    out.id = active ? tag.x : -1;
+    out.wid = kResNone;
+    out.y = __float_as_int(lo1 > 0.0f ? lo2 : fnan);
+    if (active && idx >= 0) {
+        int wslot = idx;
+        if (STAGED) {
+            const int cum1 = w.plan[kPlCum1], cum2 = w.plan[kPlCum2];
+            wslot = idx >= cum2 ? w.plan[kPlSegLo + 2] + (idx - cum2)
+                                : (idx >= cum1 ? w.plan[kPlSegLo + 1] + (idx - cum1) : w.plan[kPlSegLo] + idx);
         }
-        r.y = __float_as_int(lo1 > 0.0f ? lo2 : fnan);
-        a.res[s] = r;
+        out.wid = g.rec[wslot].id;
     }
 }
 
@@ -323,46 +314,62 @@ k_screen(const __grid_constant__ ScreenArgs a)
     // the state must be eligible (the host checked what it knows; halo particles
     // arrive on the device): otherwise decline and let the host take the full path
     const LeanConsts K = make_consts(a.b, a.rad0, __int_as_float(a.flags[kFlagVmax]));
+    if (a.flags[kFlagLeanFail] != 0) return;   // the index declined (a row denser than its slot range)
     if (a.flags[kFlagInsane] != 0 || a.flags[kFlagNotMono] != 0 || !K.ok) {
         if (blockIdx.x == 0 && threadIdx.x == 0) a.flags[kFlagLeanFail] = 1;
         return;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     LeanBuf *bufs = reinterpret_cast<LeanBuf *>(lean_smem) + 2 * warp;
-    const int nchunks = a.max_chunks;
     const int stride = gridDim.x * kLeanWarps;
-    int c = blockIdx.x * kLeanWarps + warp;
-    if (c >= nchunks) return;
-    // prologue: chunk c is staged, c + stride has its rows planned, c + 2 stride its word fetched
-    int mw1 = plan_word(a.g, c + stride, nchunks, lane);
-    int mw2 = plan_word(a.g, c + 2 * stride, nchunks, lane);
-    {
-        const int mw0 = plan_word(a.g, c, nchunks, lane);
-        const RowPlan r0 = plan_rows(a.g, mw0, lane);
-        plan_stage(a.g, &bufs[0], mw0, r0, lane);
-    }
-    RowPlan r1 = plan_rows(a.g, mw1, lane);
-    int pc = a.g.rec[c * 32 + lane].pc;
-    for (int k = 0; c < nchunks; c += stride, k ^= 1) {
-        // in flight during this trip: copies of chunk c + stride, rows of c + 2 stride,
-        // word of c + 3 stride, own cell ids of c + stride
-        plan_stage(a.g, &bufs[k ^ 1], mw1, r1, lane);
-        const RowPlan r2 = plan_rows(a.g, mw2, lane);
-        const int mw3 = plan_word(a.g, c + 3 * stride, nchunks, lane);
-        const int cn = c + stride;
-        const int pcn = cn < nchunks ? a.g.rec[cn * 32 + lane].pc : 0;
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this chunk's copies have landed
+    Pending pend;
+    pend.id = -1; pend.wid = 0; pend.y = 0;
+    const LeanChunk none = make_int4(-1, 0, 0, 0);
+    // Work list: the chunks that hold particles, in any order (rows own fixed slot
+    // ranges, most chunk slots are empty).  Lane l fetches entry w + (32 t + l) stride
+    // of the warp and its plan word; a ballot tells which lanes hold real work.
+    const int nwork = a.flags[kFlagWork];
+    for (int k0 = blockIdx.x * kLeanWarps + warp; k0 < nwork; k0 += 32 * stride) {
+        const int kl = k0 + lane * stride;
+        const int cl = kl < nwork ? a.g.work[kl] : 0;
+        const LeanChunk ml = kl < nwork ? a.g.chunks[cl] : none;
+        unsigned todo = __ballot_sync(0xffffffffu, ml.x >= 0);
+        if (todo == 0) continue;
+        auto word = [&](int b) {
+            return make_int4(__shfl_sync(0xffffffffu, ml.x, b), __shfl_sync(0xffffffffu, ml.y, b),
+                             __shfl_sync(0xffffffffu, ml.z, b), __shfl_sync(0xffffffffu, ml.w, b));
+        };
+        int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        int k = 0;
+        int c = __shfl_sync(0xffffffffu, cl, b);
+        plan_stage(a.g, &bufs[0], word(b), lane);
+        int2 tag = *reinterpret_cast<const int2 *>(&a.g.rec[c * 32 + lane].id);
+        while (b >= 0) {
+            // in flight during this trip: the copies and the own tags of the next chunk
+            const int bn = todo ? __ffs(todo) - 1 : -1;
+            todo &= todo - 1;
+            const int cn = __shfl_sync(0xffffffffu, cl, bn >= 0 ? bn : 0);
+            plan_stage(a.g, &bufs[k ^ 1], bn >= 0 ? word(bn) : none, lane);
+            const int2 tagn = bn >= 0 ? *reinterpret_cast<const int2 *>(&a.g.rec[cn * 32 + lane].id)
+                                      : make_int2(0, 0);
+            flush_pending(a, pend);   // last trip's result
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // this chunk's copies have landed
+            __syncwarp();
+            const LeanBuf &buf = bufs[k];
+            const int status = buf.plan[kPlStatus];
+            if (status == 1) screen_chunk<true>(a, K, buf, c, lane, tag, pend);
+            else if (status == 2) screen_chunk<false>(a, K, buf, c, lane, tag, pend);
+            __syncwarp();   // every lane is done with the buffer before it is refilled
+            tag = tagn;
+            b = bn;
+            c = cn;
+            k ^= 1;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        const LeanBuf &buf = bufs[k];
-        const int status = buf.plan[kPlStatus];
-        if (status == 1) screen_chunk<true>(a, K, buf, c, lane, pc);
-        else if (status == 2) screen_chunk<false>(a, K, buf, c, lane, pc);
-        __syncwarp();   // every lane is done with the buffer before it is refilled
-        mw1 = mw2;
-        mw2 = mw3;
-        r1 = r2;
-        pc = pcn;
     }
+    flush_pending(a, pend);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
@@ -374,7 +381,6 @@ struct ResolveArgs {
     int n_owned;
     const double4 *xv;
     const int32_t *cid;
-    const int32_t *slot_of;
     const int2 *res;
     const int32_t *gid;
     int32_t *flags;
@@ -398,7 +404,7 @@ __device__ __forceinline__ void exact_scan_lean(const ResolveArgs &a, const SRec
     for (int p = lo; p < hi; p++) {
         const int2 tag = *reinterpret_cast<const int2 *>(&a.g.rec[p].id);
         if (tag.x == p1.id) continue;  // `p1 != p2` is identity (ghost copies included)
-        const double4 q = a.xv[tag.x];
+        const double4 q = ld_sector(a.xv + tag.x);
         SRec p2;
         p2.x = q.x; p2.y = q.y; p2.vx = q.z; p2.vy = q.w;
         p2.rad = a.rad0; p2.id = tag.x; p2.pc = tag.y;
@@ -424,14 +430,10 @@ k_resolve(const __grid_constant__ ResolveArgs a)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_owned) return;
     const int pc = a.cid[i];
-    const double4 me = a.xv[i];
-    const int2 r = a.res[a.slot_of[i]];
-    int2 wtag = make_int2(0, 0);
+    const double4 me = ld_sector(a.xv + i);
+    const int2 r = a.res[i];
     double4 wq = make_double4(0, 0, 0, 0);
-    if (r.x >= 0) {
-        wtag = *reinterpret_cast<const int2 *>(&a.g.rec[r.x].id);
-        wq = a.xv[wtag.x];
-    }
+    if (r.x >= 0) wq = ld_sector(a.xv + r.x);
     const int Y = pc / a.g.ps;
     const int pcx = pc - Y * a.g.ps;
     SRec p1;
@@ -451,7 +453,7 @@ k_resolve(const __grid_constant__ ResolveArgs a)
     if (r.x >= 0) {
         SRec p2;
         p2.x = wq.x; p2.y = wq.y; p2.vx = wq.z; p2.vy = wq.w;
-        p2.rad = a.rad0; p2.id = wtag.x; p2.pc = wtag.y;
+        p2.rad = a.rad0; p2.id = r.x; p2.pc = 0;
         double bb, v2, cc, b2, vc;
         pair_terms<true>(a.b, p1, four_r1, p2, bb, v2, cc, b2, vc);
         const double det = __dsub_rn(b2, vc);
@@ -469,7 +471,7 @@ k_resolve(const __grid_constant__ ResolveArgs a)
 #pragma unroll 1
         for (int j = 0; j < 3; j++) {
             const int Yr = row_wrap(Y - 1 + j, a.g.nl);
-            const int rb = a.g.row_base[Yr];
+            const int rb = Yr * a.g.rowcap;
             const int32_t *o = a.g.off + (size_t)Yr * a.g.ps;
             exact_scan_lean(a, p1, four_r1, rb + o[pcx - 1], rb + o[pcx + 2], best, best_id, best_pc,
                             ov_id, ov_pc);
@@ -490,14 +492,15 @@ k_resolve(const __grid_constant__ ResolveArgs a)
 bool edmd_lean_eligible(const edmd_ctx *c, int mode)
 {
     return mode == EDMD_MODE_NORMAL && !c->force_generic && !c->lean_off && c->lean_ok && c->n > 0 &&
-           c->dbox.nx >= 12 && c->dbox.ny >= 12 && c->dbox.nl >= 3;
+           c->dbox.nx >= 12 && c->dbox.ny >= 12 && c->dbox.nl >= 3 && c->rowcap > 0;
 }
 
 static LeanIndex lean_index_of(const edmd_ctx *c)
 {
     LeanIndex g;
     g.nx = c->dbox.nx; g.nl = c->dbox.nl; g.ps = c->ps;
-    g.off = c->off; g.row_base = c->row_base; g.chunks = c->lchunks;
+    g.rowcap = c->rowcap;
+    g.off = c->off; g.chunks = c->lchunks; g.work = c->lwork;
     g.rec = c->lrec;
     return g;
 }
@@ -509,7 +512,7 @@ int edmd_launch_predict_lean(edmd_ctx *c)
     sa.g = lean_index_of(c);
     sa.b = c->dbox;
     sa.rad0 = c->rad0;
-    sa.max_chunks = edmd_chunks_bound(c);
+    sa.max_chunks = c->lean_chunks;
     sa.flags = c->flags;
     sa.res = c->lres;
     static bool attr = false;
@@ -529,7 +532,7 @@ int edmd_launch_predict_lean(edmd_ctx *c)
         ra.t = c->t;
         ra.rad0 = c->rad0;
         ra.n_owned = c->n_owned;
-        ra.xv = c->xv; ra.cid = c->cid; ra.slot_of = c->rank; ra.res = c->lres;
+        ra.xv = c->xv; ra.cid = c->cid; ra.res = c->lres;
         ra.gid = c->slab ? c->gid : nullptr;
         ra.flags = c->flags;
         ra.t_cross = c->t_cross; ra.dir = c->dir; ra.t_coll = c->t_coll; ra.partner = c->partner;

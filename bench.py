@@ -320,11 +320,13 @@ def run_ours(args, cfg):
     P = B._ptr
 
     def e2e_step():
+        # a thermostat tick: positions and velocities up (radii are unchanged: rad = NULL),
+        # crossing + collision events down (ctype is the constant COLLISION: not fetched)
         rc = lib.edmd_cuda_upload(h, P(host["x"]), P(host["y"]), P(host["vx"]), P(host["vy"]),
-                                  P(host["rad"]), None, 0.0)
+                                  None, None, 0.0)
         assert rc == 0, lib.edmd_cuda_last_error(h)
         rc = lib.edmd_cuda_predict_all(h, B.MODE_NORMAL, None, P(outs["t_cross"]), P(outs["dir"]),
-                                       P(outs["t_coll"]), P(outs["partner"]), P(outs["ctype"]), P(ov))
+                                       P(outs["t_coll"]), P(outs["partner"]), None, P(ov))
         assert rc == 0, lib.edmd_cuda_last_error(h)
 
     ctx.upload(host["x"], host["y"], host["vx"], host["vy"], host["rad"], t=0.0)
@@ -389,10 +391,11 @@ def run_ours(args, cfg):
             "dtype": "f64", "data": "synthetic", "config": workload_config(cfg),
             "clocks": clocks,
             "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": 40 * n, "d2h_bytes_per_step": 22 * n,
-                    "api": "edmd_cuda_upload + edmd_cuda_predict_all, pinned host buffers"},
+                    "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 21 * n,
+                    "api": "edmd_cuda_upload(x,y,vx,vy; radii resident) + edmd_cuda_predict_all"
+                           "(t_cross,dir,t_coll,partner), pinned host buffers"},
             "gpu_launches": int(launches_timed),
-            "roofline": {"bound": "hbm", "kernel": "k_predict (K1)",
+            "roofline": {"bound": "hbm", "kernel": "K1 = k_screen + k_resolve (lean sweep)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": how + " (burst copy)",
                          "traffic": profile_traffic(),

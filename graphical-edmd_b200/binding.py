@@ -22,6 +22,7 @@ EINVAL, ESTATE, EOVERLAP, ECELL, ENOMEM = 1, 2, 3, 4, 5
 BENCH_SWEEP, BENCH_FREEFLY, BENCH_BOOP, BENCH_PCF = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 1
 OPT_NO_LEAN = 2
+EPLAN = 6
 STAT_EXACT_RESCANS = 1
 
 # every symbol include/edmd_cuda.h declares
@@ -36,6 +37,7 @@ SYMBOLS = [
     "edmd_cuda_create_slab", "edmd_cuda_upload_owned", "edmd_cuda_halo_pack",
     "edmd_cuda_halo_append", "edmd_cuda_get_counts", "edmd_cuda_pcf_device",
     "edmd_cuda_halo_export", "edmd_cuda_halo_connect", "edmd_cuda_halo_exchange",
+    "edmd_cuda_calendar_plan",
 ]
 HALO_RECORD_BYTES = 48
 
@@ -104,6 +106,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_host_free.argtypes = [vp]
     lib.edmd_cuda_host_free.restype = None
     lib.edmd_cuda_set_option.argtypes = [vp, C.c_int, C.c_int]
+    lib.edmd_cuda_calendar_plan.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, vp,
+                                            C.POINTER(C.c_int32)]
     lib.edmd_cuda_get_stat.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
     for name in SYMBOLS:
         fn = getattr(lib, name)
@@ -188,7 +192,8 @@ class EdmdCuda:
 
     def upload(self, x, y, vx, vy, rad, cell_xy=None, t=0.0):
         n = self.n
-        arrs = [_f64(a, n) for a in (x, y, vx, vy, rad)]
+        # rad=None: radii unchanged since the last upload (kept resident)
+        arrs = [None if a is None else _f64(a, n) for a in (x, y, vx, vy, rad)]
         cells = None
         if cell_xy is not None:
             cells = np.ascontiguousarray(cell_xy, dtype=np.int32).reshape(-1)
@@ -303,6 +308,21 @@ class EdmdCuda:
         self._check(self.lib.edmd_cuda_boop_cutoff(
             self._h, r_c, _ptr(q5), _ptr(q6), _ptr(q7), _ptr(arg), _ptr(nb), C.addressof(mean)))
         return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, mean_q6=mean.value)
+
+    def calendar_plan(self, paul_time, dt_paul, paul_n, actual_paul, allow_declined=False):
+        """Ingest plan of the last sweep's 2N events for an empty calendar
+        (addEventToQueue, src/EDMD.c:2144-2170, applied in the batch loops' order)."""
+        e2 = 2 * self.n
+        bucket = np.empty(e2, np.int32)
+        nxt = np.empty(e2, np.int32)
+        prv = np.empty(e2, np.int32)
+        head = np.empty(paul_n + 1, np.int32)
+        n_tree = C.c_int32(0)
+        rc = self.lib.edmd_cuda_calendar_plan(self._h, float(paul_time), float(dt_paul), int(paul_n),
+                                              int(actual_paul), _ptr(bucket), _ptr(nxt), _ptr(prv),
+                                              _ptr(head), C.byref(n_tree))
+        self._check(rc, allow=(EPLAN,) if allow_declined else ())
+        return dict(rc=rc, bucket=bucket, next=nxt, prev=prv, head=head, n_tree=n_tree.value)
 
     def bench(self, what, mode=MODE_NORMAL, dr=0.0, max_r=0.0, warmup=3, iters=10,
               flush_bytes=0):

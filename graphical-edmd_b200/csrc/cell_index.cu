@@ -30,16 +30,17 @@ __global__ void __launch_bounds__(kThreads)
 k_pack(int n, size_t N, edmd_dev_box b, int ps, const double *__restrict__ soa,
        const int32_t *__restrict__ cell_xy, double4 *__restrict__ xv,
        double *__restrict__ rad, int32_t *__restrict__ cid,
-       int32_t *__restrict__ flags, double rad0)
+       int32_t *__restrict__ flags, double rad0, int keep_rad)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int ghosts = 0, insane = 0, notmono = 0;
     float vm = 0.0f;
     if (i < n) {
         double x = soa[i], y = soa[N + i];
-        const double vx = soa[2 * N + i], vy = soa[3 * N + i], r = soa[4 * N + i];
+        const double vx = soa[2 * N + i], vy = soa[3 * N + i];
+        const double r = keep_rad ? rad[i] : soa[4 * N + i];   // keep_rad: radii unchanged since the last upload
         xv[i] = make_double4(x, y, vx, vy);
-        rad[i] = r;
+        if (!keep_rad) rad[i] = r;
         // what the lean sweep needs to know (lean.cuh): one common radius, the speed scale
         notmono = !(r == rad0);
         vm = __double2float_ru(fmax(fabs(vx), fabs(vy)));
@@ -337,12 +338,12 @@ k_scatter(int n, int nx, int ps, const int32_t *__restrict__ cid,
 }  // namespace
 
 // pack `count` staged particles into the resident arrays starting at `first`
-int edmd_launch_pack(edmd_ctx *c, bool have_cells, int first, int count)
+int edmd_launch_pack(edmd_ctx *c, bool have_cells, int first, int count, bool keep_rad)
 {
     if (count == 0) return 0;
     k_pack<<<(count + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(
         count, (size_t)c->n_cap, c->dbox, c->ps, c->in_soa, have_cells ? c->in_cell : nullptr,
-        c->xv + first, c->rad + first, c->cid + first, c->flags, c->rad0);
+        c->xv + first, c->rad + first, c->cid + first, c->flags, c->rad0, keep_rad ? 1 : 0);
     return 1;
 }
 

@@ -300,7 +300,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->gid, c->cell_cnt,
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
-                   c->lrec, c->lchunks, c->lres, c->lwork,
+                   c->lrec, c->lchunks, c->lres, c->lwork, c->cal_mem,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
                    c->overlap_key, c->flags, c->pcf_counts, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
@@ -370,7 +370,10 @@ static int upload_impl(edmd_ctx *c, int n, const double *x, const double *y, con
                        const double *vy, const double *rad, const int32_t *cell_xy,
                        const int32_t *gid, double t)
 {
-    if (n > 0 && (!x || !y || !vx || !vy || !rad)) return fail(c, EDMD_EINVAL, "null state array");
+    if (n > 0 && (!x || !y || !vx || !vy)) return fail(c, EDMD_EINVAL, "null state array");
+    const bool keep_rad = rad == nullptr;   // radii unchanged since the last upload of this many particles
+    if (keep_rad && n > 0 && (!c->have_rad || n != c->n_owned))
+        return fail(c, EDMD_ESTATE, "rad == NULL needs an earlier upload of the same particles with radii");
     CU(cudaSetDevice(c->device));
     size_t N = (size_t)c->n_cap, B = (size_t)n * sizeof(double);
     int r;
@@ -378,23 +381,24 @@ static int upload_impl(edmd_ctx *c, int n, const double *x, const double *y, con
     if ((r = h2d(c, c->in_soa + N, y, B))) return r;
     if ((r = h2d(c, c->in_soa + 2 * N, vx, B))) return r;
     if ((r = h2d(c, c->in_soa + 3 * N, vy, B))) return r;
-    if ((r = h2d(c, c->in_soa + 4 * N, rad, B))) return r;
+    if (!keep_rad && (r = h2d(c, c->in_soa + 4 * N, rad, B))) return r;
     if (cell_xy && (r = h2d(c, c->in_cell, cell_xy, 2 * (size_t)n * sizeof(int32_t)))) return r;
     if (gid && (r = h2d(c, c->gid, gid, (size_t)n * sizeof(int32_t)))) return r;
     // ghosts, insane, vmax, notmono, leanfail
     CU(cudaMemsetAsync(c->flags + kFlagGhosts, 0, 5 * sizeof(int32_t), c->stream));
-    c->rad0 = n > 0 ? rad[0] : 1.0;
+    if (!keep_rad) c->rad0 = n > 0 ? rad[0] : 1.0;
     c->nghost = 0;
     c->n = n;
     c->n_owned = n;
     c->nghost_extra = 0;
-    c->launches += edmd_launch_pack(c, cell_xy != nullptr, 0, n);
+    c->launches += edmd_launch_pack(c, cell_xy != nullptr, 0, n, keep_rad);
     CU(cudaGetLastError());
     c->t = t;
     c->have_pred = false;
     c->have_index = false;
     if ((r = check_flags(c))) return r;
     c->have_state = true;
+    c->have_rad = true;
     return 0;
 }
 
@@ -575,6 +579,8 @@ int edmd_cuda_set_growth(edmd_ctx *c, const double *vr)
 
 // K0 + K1 on the resident state: the lean path (lean.cuh) when the state is
 // eligible, else the full FP64 path
+static int lean_fallback(edmd_ctx *c);
+
 static int sweep_launch(edmd_ctx *c, int mode)
 {
     int launched = 0;
@@ -665,6 +671,51 @@ int edmd_cuda_predict_all(edmd_ctx *c, int mode, const double *vr, double *t_cro
     }
     if ((r = edmd_cuda_predict_device(c, mode))) return r;
     return edmd_cuda_fetch_predictions(c, t_cross, dir, t_coll, partner, ctype, overlap_pair);
+}
+
+int edmd_cuda_calendar_plan(edmd_ctx *c, double paul_time, double dt_paul, int paul_n, int actual_paul,
+                            int32_t *bucket, int32_t *next, int32_t *prev, int32_t *head, int32_t *n_tree)
+{
+    if (!c || !bucket || !next || !prev || !head) return EDMD_EINVAL;
+    if (!c->have_pred) return fail(c, EDMD_ESTATE, "calendar_plan needs the predictions of a sweep");
+    if (paul_n < 1 || actual_paul < 0 || actual_paul >= paul_n || !(dt_paul > 0))
+        return fail(c, EDMD_EINVAL, "bad calendar geometry");
+    CU(cudaSetDevice(c->device));
+    int r;
+    if ((r = lean_fallback(c))) return r;   // the predictions must be final
+    const size_t e2 = 2 * (size_t)c->n_owned, pn1 = (size_t)paul_n + 1;
+    const size_t nsum = (e2 > pn1 ? e2 : pn1) / 1024 + 2;
+    const size_t scratch = 4 * e2 + 3 * pn1 + nsum + 8;
+    const size_t need = scratch + 3 * e2 + pn1;
+    if (need > c->cal_ints) {
+        if (c->cal_mem) CU(cudaFree(c->cal_mem));
+        c->cal_mem = nullptr;
+        c->cal_ints = 0;
+        if ((r = dev_alloc(c, &c->cal_mem, need))) return r;
+        c->cal_ints = need;
+    }
+    // counts / fill cursors start from zero (the link kernel leaves them so, but the geometry may change)
+    CU(cudaMemsetAsync(c->cal_mem + 4 * e2, 0, 3 * pn1 * sizeof(int32_t), c->stream));
+    int32_t *d_bucket = c->cal_mem + scratch, *d_next = d_bucket + e2, *d_prev = d_next + e2,
+            *d_head = d_prev + e2;
+    if (e2 > 0) {
+        c->launches += edmd_launch_calendar_plan(c, paul_time, dt_paul, paul_n, actual_paul, c->cal_mem,
+                                                 d_bucket, d_next, d_prev, d_head, nullptr);
+        CU(cudaGetLastError());
+    } else {
+        CU(cudaMemsetAsync(d_head, 0xff, pn1 * sizeof(int32_t), c->stream));
+        c->cal_tree = 0;
+        c->cal_declined = false;
+    }
+    if ((r = d2h(c, bucket, d_bucket, e2 * sizeof(int32_t)))) return r;
+    if ((r = d2h(c, next, d_next, e2 * sizeof(int32_t)))) return r;
+    if ((r = d2h(c, prev, d_prev, e2 * sizeof(int32_t)))) return r;
+    if ((r = d2h(c, head, d_head, pn1 * sizeof(int32_t)))) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_tree) *n_tree = c->cal_tree;
+    if (c->cal_declined)
+        return fail(c, EDMD_EPLAN, "a calendar bucket holds more than 128 events: ingest this sweep event by event");
+    return 0;
 }
 
 int edmd_cuda_free_fly(edmd_ctx *c, int mode, double t_new)

@@ -140,6 +140,7 @@ struct edmd_ctx {
     bool force_generic;  // EDMD_OPT_FORCE_GENERIC: global-memory exact kernel only
 
     bool have_state;     // upload done
+    bool have_rad;       // resident radii are valid (an upload carried them)
     bool have_pred;      // device predictions valid
     bool have_index;     // cell index matches resident state
     bool index_has_vr;   // ... and carries growth rates
@@ -202,6 +203,12 @@ struct edmd_ctx {
     unsigned long long *overlap_key;  // min over (i<<32 | j), ~0ull = none
     int32_t *flags;                   // kFlagCount words
 
+    // calendar ingest plan (calendar.cu)
+    int32_t *cal_mem;                 // scratch + outputs
+    size_t cal_ints;                  // its size
+    int cal_tree;                     // events of the last plan that go to the BST
+    bool cal_declined;                // a bucket held too many events
+
     // analysis scratch
     unsigned long long *pcf_counts;   // capacity pcf_cap bins
     int pcf_cap;
@@ -244,7 +251,7 @@ inline int edmd_chunks_bound(const edmd_ctx *c)
 int edmd_persistent_blocks(const edmd_ctx *c);
 
 // ---- launchers (each returns the number of kernels it launched) ----------
-int edmd_launch_pack(edmd_ctx *c, bool have_cells, int first, int count);
+int edmd_launch_pack(edmd_ctx *c, bool have_cells, int first, int count, bool keep_rad);
 int edmd_launch_halo_pack(edmd_ctx *c, int side, void *out, int cap, int32_t *count_dev);
 int edmd_launch_halo_append_row(edmd_ctx *c, const void *in, int count, int row);
 size_t edmd_halo_mem_bytes(int halo_cap);
@@ -252,6 +259,9 @@ int edmd_launch_halo_p2p(edmd_ctx *c);
 int edmd_launch_cell_index(edmd_ctx *c, int mode);
 int edmd_launch_predict(edmd_ctx *c, int mode);
 int edmd_launch_free_fly(edmd_ctx *c, int mode, double dt);
+int edmd_launch_calendar_plan(edmd_ctx *c, double paul_time, double dt_paul, int paul_n, int actual,
+                              int32_t *scratch, int32_t *bucket, int32_t *next, int32_t *prev,
+                              int32_t *head, int *n_overflow_host_sync);
 int edmd_launch_lean_index(edmd_ctx *c);
 int edmd_launch_predict_lean(edmd_ctx *c);
 bool edmd_lean_eligible(const edmd_ctx *c, int mode);

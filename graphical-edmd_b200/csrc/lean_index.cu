@@ -173,7 +173,7 @@ __device__ __forceinline__ void put_lean(const ScatterArgs &a, int slot, int pc,
 }
 
 // four particles per thread; all loads, then all cursor atomics, then the stores
-constexpr int kPer = 4;
+constexpr int kPer = 1;
 
 __global__ void __launch_bounds__(kThreads)
 k_lean_scatter(const __grid_constant__ ScatterArgs a)
@@ -182,9 +182,12 @@ k_lean_scatter(const __grid_constant__ ScatterArgs a)
     if (i0 >= a.n || a.flags[kFlagLeanFail] != 0) return;   // a row overflowed its slot range: declined
     int pc[kPer], slot[kPer];
     double4 p[kPer];
-    if (i0 + kPer <= a.n) {
+    if (kPer == 4 && i0 + kPer <= a.n) {
         const int4 c4 = *reinterpret_cast<const int4 *>(a.cid + i0);
-        pc[0] = c4.x; pc[1] = c4.y; pc[2] = c4.z; pc[3] = c4.w;
+        pc[0] = c4.x; pc[1] = c4.y; pc[kPer - 2] = c4.z; pc[kPer - 1] = c4.w;
+    } else if (kPer == 2 && i0 + kPer <= a.n) {
+        const int2 c2 = *reinterpret_cast<const int2 *>(a.cid + i0);
+        pc[0] = c2.x; pc[1] = c2.y;
     } else {
 #pragma unroll
         for (int k = 0; k < kPer; k++) pc[k] = i0 + k < a.n ? a.cid[i0 + k] : -1;

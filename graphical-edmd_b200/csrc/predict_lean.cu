@@ -426,12 +426,14 @@ __device__ __forceinline__ void exact_scan_lean(const ResolveArgs &a, const SRec
 __global__ void __launch_bounds__(256)
 k_resolve(const __grid_constant__ ResolveArgs a)
 {
-    if (a.flags[kFlagLeanFail] != 0) return;   // k_screen declined
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_owned) return;
+    // all first-level loads go out together (the decline flag is one of them)
+    const int declined = a.flags[kFlagLeanFail];
+    const int2 r = a.res[i];
     const int pc = a.cid[i];
     const double4 me = ld_sector(a.xv + i);
-    const int2 r = a.res[i];
+    if (declined != 0) return;   // k_screen (or the index) declined: res[] is stale
     double4 wq = make_double4(0, 0, 0, 0);
     if (r.x >= 0) wq = ld_sector(a.xv + r.x);
     const int Y = pc / a.g.ps;

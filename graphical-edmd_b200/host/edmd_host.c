@@ -52,6 +52,7 @@ static double tmax = 4000, dtime = 100, dtimeThermo = 100, firstScreen = 1, firs
 static double T = 1.0, dtnoise = 0.5;
 static int noise = 0, seed = 1, boopThermo = 0, pcfThermo = 0, verify = 0, quiet = 0;
 static int init_grow = 1, growing = 0;
+static int bulk_ingest = 1;   /* --ingest bulk|seq: calendar rebuilt from the GPU's ingest plan / event by event */
 static double vr = 0.1;
 static const char *outdir = "dump";
 
@@ -81,8 +82,11 @@ static edmd_ctx *gpu;
 static double *g_tcross, *g_tcoll;
 static uint8_t *g_dir, *g_type;
 static int32_t *g_partner;
-static double gpu_sweep_seconds = 0;
-static int gpu_sweeps = 0;
+static int32_t *g_bucket, *g_next, *g_prev, *g_head;   /* edmd_cuda_calendar_plan outputs (pinned) */
+static double gpu_sweep_seconds = 0, ingest_seconds = 0;
+static int gpu_sweeps = 0, bulk_sweeps = 0;
+#define NSPECIAL 10
+static int special_queued[NSPECIAL];
 
 static double now(void)
 {
@@ -335,6 +339,7 @@ static void schedule_special(int slot, int type, double when)
 	node *e = &events[2 * N + slot];
 	e->type = type; e->t = when; e->j = 0; e->i = -1;
 	queue_add(e);
+	special_queued[slot] = 1;
 }
 
 /* ---- the whole-system sweep on the GPU -------------------------------------- */
@@ -342,6 +347,54 @@ static void gpu_upload(void)
 {
 	int rc = edmd_cuda_upload(gpu, px, py, pvx, pvy, prad, pcell, t);
 	if (rc) die_gpu(rc, "edmd_cuda_upload");
+}
+
+/* Whole-calendar rebuild from the device's ingest plan (edmd_cuda_calendar_plan):
+ * every particle event is being replaced, so instead of 2N removals and 2N
+ * insertions (one division and two cache misses each) the calendar is emptied,
+ * the nodes are filled in one streaming pass from the plan -- bucket, list
+ * neighbours, list heads, exactly what the sequential head insertions would
+ * have produced -- and only the handful of special events and BST events go
+ * through queue_add / tree_add.  Returns 0 (calendar emptied, only the special
+ * events re-inserted) when the device declines the plan; the caller then
+ * inserts the particle events one by one. */
+static int ingest_from_plan(void)
+{
+	/* empty the calendar */
+	memset(paul, 0, sizeof(node *) * (size_t)(paulN + 1));
+	root->lft = root->rgt = NULL;
+	treeMin = NULL;
+	int rc = edmd_cuda_calendar_plan(gpu, paulTime, dtPaul, paulN, actualPaul, g_bucket, g_next, g_prev,
+	                                 g_head, NULL);
+	if (rc && rc != EDMD_EPLAN) die_gpu(rc, "edmd_cuda_calendar_plan");
+	if (rc == 0) {
+		for (int k = 0; k <= paulN; k++) paul[k] = g_head[k] >= 0 ? &events[g_head[k]] : NULL;
+		for (int i = 0; i < N; i++) {
+			node *ev = &events[i];
+			ev->j = g_dir[i]; ev->type = EV_CELLCROSS; ev->t = g_tcross[i];
+			int b = g_bucket[i];
+			if (b < 0) { ev->q = actualPaul; tree_add(ev); }
+			else {
+				ev->q = b;
+				ev->lft = g_prev[i] >= 0 ? &events[g_prev[i]] : NULL;
+				ev->rgt = g_next[i] >= 0 ? &events[g_next[i]] : NULL;
+			}
+			ev = &events[N + i];
+			ev->j = g_partner[i]; ev->type = EV_COLLISION; ev->t = g_tcoll[i];
+			ev->collActual = pcoll[g_partner[i]];
+			b = g_bucket[N + i];
+			if (b < 0) { ev->q = actualPaul; tree_add(ev); }
+			else {
+				ev->q = b;
+				ev->lft = g_prev[N + i] >= 0 ? &events[g_prev[N + i]] : NULL;
+				ev->rgt = g_next[N + i] >= 0 ? &events[g_next[N + i]] : NULL;
+			}
+		}
+	}
+	/* the special events (a handful) go back in the ordinary way */
+	for (int s = 0; s < NSPECIAL; s++)
+		if (special_queued[s]) queue_add(&events[2 * N + s]);
+	return rc == 0;
 }
 
 /* every particle must already be at time t.  remove_first: events are in the
@@ -357,6 +410,15 @@ static void gpu_predict_all(int remove_first)
 	if (rc) die_gpu(rc, "edmd_cuda_predict_all");
 	gpu_sweep_seconds += now() - t0;
 	gpu_sweeps++;
+	double t1 = now();
+	if (bulk_ingest) {
+		if (ingest_from_plan()) {
+			ingest_seconds += now() - t1;
+			bulk_sweeps++;
+			return;
+		}
+		remove_first = 0;   /* declined: the calendar is empty, insert one by one */
+	}
 	/* sequential calendar ingest in the reference's order: crossing, then collision */
 	for (int i = 0; i < N; i++) {
 		node *e = &events[i];
@@ -369,6 +431,7 @@ static void gpu_predict_all(int remove_first)
 		e->collActual = pcoll[g_partner[i]];
 		queue_add(e);
 	}
+	ingest_seconds += now() - t1;
 }
 
 static void verify_first_sweep(void)
@@ -630,7 +693,7 @@ int main(int argc, char **argv)
 		{"boop", no_argument, NULL, 1003}, {"pcf", no_argument, NULL, 1004},
 		{"verify", no_argument, NULL, 1005}, {"outdir", required_argument, NULL, 1006},
 		{"quiet", no_argument, NULL, 1007}, {"device", required_argument, NULL, 1008},
-		{"init", required_argument, NULL, 1009},
+		{"init", required_argument, NULL, 1009}, {"ingest", required_argument, NULL, 1010},
 		{NULL, 0, NULL, 0}};
 	int c, device = 0;
 	while ((c = getopt_long(argc, argv, "N:p:x:q:a:t:D:o:T:v:", longopt, NULL)) != -1) {
@@ -654,8 +717,9 @@ int main(int argc, char **argv)
 		case 1007: quiet = 1; break;
 		case 1008: device = atoi(optarg); break;
 		case 1009: init_grow = strcmp(optarg, "lattice") != 0; break;
+		case 1010: bulk_ingest = strcmp(optarg, "seq") != 0; break;
 		default: fprintf(stderr, "usage: edmd_host -N n --phi f [-x xs -q ratio -a aspect -t tmax -D dt -o dtThermo -T temp -v seed]\n"
-		                         "       [--init grow|lattice] [--noise 2 --dtnoise dt] [--boop] [--pcf] [--verify] [--outdir dir] [--quiet]\n");
+		                         "       [--init grow|lattice] [--ingest bulk|seq] [--noise 2 --dtnoise dt] [--boop] [--pcf] [--verify] [--outdir dir] [--quiet]\n");
 			return 2;
 		}
 	}
@@ -687,6 +751,8 @@ int main(int argc, char **argv)
 	for (int i = 0; i < N; i++) events[i].i = events[N + i].i = i;
 	g_tcross = pinned(sizeof(double) * N); g_tcoll = pinned(sizeof(double) * N);
 	g_dir = pinned(N); g_type = pinned(N); g_partner = pinned(sizeof(int32_t) * N);
+	g_bucket = pinned(sizeof(int32_t) * 2 * N); g_next = pinned(sizeof(int32_t) * 2 * N);
+	g_prev = pinned(sizeof(int32_t) * 2 * N); g_head = pinned(sizeof(int32_t) * ((size_t)paulN + 1));
 
 	mkdir(outdir, 0777);
 	char name[512];
@@ -714,6 +780,7 @@ int main(int argc, char **argv)
 		node *ev = queue_next();
 		t = ev->t;
 		queue_remove(ev);
+		if (ev - events >= 2 * N) special_queued[ev - events - 2 * N] = 0;
 		switch (ev->type) {
 		case EV_COLLISION: do_collision(ev); break;
 		case EV_CELLCROSS: do_crossing(ev); break;
@@ -725,9 +792,11 @@ int main(int argc, char **argv)
 	}
 	double wall = now() - wall1;
 	printf("edmd_host: %lu collisions, %lu crossings in %.3f s => %.4g coll/s ; setup %.3f s ; "
-	       "%d GPU sweeps, %.3f ms each (upload + K0 + K1 + download) ; E/N = %.6f ; p = %.6f\n",
+	       "%d GPU sweeps, %.3f ms each (upload + K0 + K1 + download) ; calendar ingest %.3f ms each "
+	       "(%d from the device plan) ; E/N = %.6f ; p = %.6f\n",
 	       ncol, ncross, wall, ncol / wall, wall_setup, gpu_sweeps,
-	       gpu_sweeps ? 1e3 * gpu_sweep_seconds / gpu_sweeps : 0.0, kinetic_energy() / N, last_pressure);
+	       gpu_sweeps ? 1e3 * gpu_sweep_seconds / gpu_sweeps : 0.0,
+	       gpu_sweeps ? 1e3 * ingest_seconds / gpu_sweeps : 0.0, bulk_sweeps, kinetic_energy() / N, last_pressure);
 	fclose(fdump); fclose(fthermo);
 	if (fpcf) fclose(fpcf);
 	edmd_cuda_destroy(gpu);

@@ -42,6 +42,7 @@ typedef struct edmd_ctx edmd_ctx;
 #define EDMD_EOVERLAP 3  /* predict found c < -0.01: reference would exit(3) */
 #define EDMD_ECELL 4     /* a cell id outside the grid */
 #define EDMD_ENOMEM 5
+#define EDMD_EPLAN 6     /* calendar_plan declined (a bucket too full): ingest event by event */
 
 /* prediction mode: which set of reference function pointers is emulated
  * (src/EDMD.c:1977-1989) */
@@ -103,7 +104,10 @@ void edmd_cuda_host_free(void *ptr);
  * the reference has after its freeFly loop, src/EDMD.c:4838-4886, :4744).
  * cell_xy (interleaved X,Y = particle.cell[0..1], src/EDMD.h:57) may be NULL:
  * the device then computes (int)(x*cellxFac) like coordToCell (:2098-2107).
- * Mid-run callers MUST pass the host's cell ids. */
+ * Mid-run callers MUST pass the host's cell ids.
+ * rad may be NULL on any upload after the first one of the same particles:
+ * the resident radii are kept (NORMAL mode never changes them), which saves 8
+ * of the 40 bytes per particle that cross PCIe at a thermostat tick. */
 int edmd_cuda_upload(edmd_ctx *ctx, const double *x, const double *y,
                      const double *vx, const double *vy, const double *rad,
                      const int32_t *cell_xy, double t);
@@ -187,6 +191,29 @@ int edmd_cuda_get_counts(const edmd_ctx *ctx, int *n_owned, int *n_total);
  * counts_dev[num_bins] (device, caller zeroes it and all-reduces it). */
 int edmd_cuda_pcf_device(edmd_ctx *ctx, const double *xy_dev, int n_total, double dr, double max_r,
                          int part, int nparts, uint64_t *counts_dev, int *num_bins);
+
+/* ---- calendar ingest plan ----------------------------------------------- */
+
+/* For the 2N events of the last sweep (event e = i: crossing of particle i at
+ * t_cross[i]; e = N + i: its collision at t_coll[i] -- the indices of the
+ * reference's eventList[], src/EDMD.c:1923-1934) compute what 2N calls of
+ * addEventToQueue (src/EDMD.c:2144-2170) in the batch loops' order (crossing
+ * 0, collision 0, crossing 1, ...; :2007-2012, :4909-4915) would do to an EMPTY
+ * calendar with the given geometry (paulTime, dtPaul, paulListN,
+ * actualPaulList):
+ *   bucket[e]  -1: the event belongs in the BST (dt < dtPaul), the host adds it
+ *              itself; else the Paul list it lands in (paul_n = overflow list)
+ *   next[e] / prev[e]   its ->rgt / ->lft neighbour in that list (-1 = NULL)
+ *   head[k]    eventPaul[k] for k = 0 .. paul_n  (-1 = NULL)
+ *   n_tree     number of BST events
+ * so the host can fill its nodes in one streaming pass instead of 2N divisions
+ * and pointer-chasing insertions.  Same FP64 operations as the reference, hence
+ * the same buckets bit for bit.  Arrays are caller-owned: bucket/next/prev
+ * [2N], head [paul_n + 1].  Returns EDMD_EPLAN (outputs unusable) if some list
+ * would hold more than 128 of the events; the caller then inserts one by one. */
+int edmd_cuda_calendar_plan(edmd_ctx *ctx, double paul_time, double dt_paul, int paul_n,
+                            int actual_paul, int32_t *bucket, int32_t *next, int32_t *prev,
+                            int32_t *head, int32_t *n_tree);
 
 /* ---- free flight ------------------------------------------------------ */
 

@@ -214,3 +214,35 @@ class Reference:
         nb = np.empty(n, np.int32)
         sec = self.lib.ref_boop_cutoff(r_c, _p(q5), _p(q6), _p(q7), _p(arg), _p(nb))
         return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, seconds=sec)
+
+
+def calendar_plan_oracle(t_cross, t_coll, paul_time, dt_paul, paul_n, actual_paul):
+    """What 2N calls of the reference's addEventToQueue (src/EDMD.c:2144-2170), in the
+    order of its batch loops (crossing 0, collision 0, crossing 1, ...;
+    :2007-2012, :4909-4915), do to an empty calendar.  Test infrastructure: a plain
+    Python/numpy restatement, event e = i (crossing) / N + i (collision)."""
+    n = len(t_cross)
+    bucket = np.empty(2 * n, np.int32)
+    nxt = np.full(2 * n, -1, np.int32)
+    prv = np.full(2 * n, -1, np.int32)
+    head = np.full(paul_n + 1, -1, np.int32)
+    n_tree = 0
+    for i in range(n):
+        for e, te in ((i, t_cross[i]), (n + i, t_coll[i])):
+            dt = np.float64(te) - np.float64(paul_time)
+            if dt < dt_paul:
+                bucket[e] = -1
+                n_tree += 1
+                continue
+            if dt >= np.float64(dt_paul) * paul_n:
+                k = paul_n
+            else:
+                k = actual_paul + int(dt / np.float64(dt_paul))
+                if k >= paul_n:
+                    k -= paul_n
+            bucket[e] = k
+            nxt[e] = head[k]          # toAdd->rgt = eventPaul[k]
+            if head[k] >= 0:
+                prv[head[k]] = e      # toAdd->rgt->lft = toAdd
+            head[k] = e               # eventPaul[k] = toAdd   (toAdd->lft = NULL)
+    return dict(bucket=bucket, next=nxt, prev=prv, head=head, n_tree=n_tree)

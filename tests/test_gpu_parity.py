@@ -117,6 +117,23 @@ def test_sweep_is_deterministic_and_reentrant(pkg):
         assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], d[k])
 
 
+def test_upload_without_radii_keeps_them(pkg, oracle):
+    """A thermostat tick re-uploads positions and velocities only (rad = NULL)."""
+    c = pkg.synth.lattice_config(30000, 0.70, seed=6, small_fraction=0.3)
+    rng = np.random.default_rng(6)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        with pytest.raises(pkg.EdmdError):
+            ctx.upload(c["x"], c["y"], c["vx"], c["vy"], None, t=0.0)   # nothing resident yet
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        ctx.predict_all()
+        c2 = dict(c, vx=c["vx"] * 0.5 + 0.1 * rng.standard_normal(c["n"]), vy=c["vy"] * 0.9)
+        ctx.upload(c2["x"], c2["y"], c2["vx"], c2["vy"], None, t=1.0)
+        got = ctx.predict_all()
+        s = ctx.download_state()
+    assert np.array_equal(s["rad"], c["rad"])
+    assert_events_equal(got, oracle_sweep(oracle, c2, t=1.0))
+
+
 def test_growth_sweep_matches_oracle(pkg, oracle):
     c = pkg.synth.growth_config(100000, 0.70, seed=7)
     rng = np.random.default_rng(7)
@@ -157,6 +174,43 @@ def test_host_cells_and_aos_upload(pkg, oracle):
         ctx.upload_aos(rec, t=2.0, with_cells=True)
         got2 = ctx.predict_all()
     assert_events_equal(got2, want)
+
+
+# ------------------------------------------------- calendar ingest plan ----
+@pytest.mark.parametrize("n,phi,seed,sf,t", [(20000, 0.70, 51, 0.0, 0.0), (20000, 0.72, 52, 0.3, 37.25),
+                                             (3000, 0.30, 53, 0.0, 2.0)])
+def test_calendar_plan_matches_sequential_inserts(pkg, n, phi, seed, sf, t):
+    """The device's bucket / next / prev / head equal what 2N sequential
+    addEventToQueue calls leave in an empty calendar (the oracle walks them)."""
+    from oracle.oracle_py import calendar_plan_oracle
+    c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf)
+    n = c["n"]
+    dt_paul, paul_n = 5.0 / n, n                       # boxConstantHelper, src/EDMD.c:707-708
+    actual = (7 * n) // 11
+    paul_time = t - 0.4 * dt_paul                      # mid-bucket, like a running calendar
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=t)
+        ev = ctx.predict_all()
+        got = ctx.calendar_plan(paul_time, dt_paul, paul_n, actual)
+    want = calendar_plan_oracle(ev["t_cross"], ev["t_coll"], paul_time, dt_paul, paul_n, actual)
+    assert got["n_tree"] == want["n_tree"]
+    for k in ("bucket", "head"):
+        assert np.array_equal(got[k], want[k]), k
+    listed = want["bucket"] >= 0                        # next / prev are undefined for BST events
+    assert np.array_equal(got["next"][listed], want["next"][listed])
+    assert np.array_equal(got["prev"][listed], want["prev"][listed])
+    assert (want["bucket"] == paul_n).sum() > 0 or phi > 0.5   # dilute: "never" events fill the overflow list
+
+
+def test_calendar_plan_declines_crowded_buckets(pkg):
+    """Few, wide buckets: more than 128 events per list => EDMD_EPLAN, the host
+    then inserts one by one."""
+    c = pkg.synth.lattice_config(5000, 0.70, seed=54)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        ctx.predict_all()
+        got = ctx.calendar_plan(0.0, 0.25, 4, 1, allow_declined=True)
+    assert got["rc"] == pkg.binding.EPLAN
 
 
 # ------------------------------------------------------------ edge cases ----

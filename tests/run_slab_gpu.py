@@ -32,7 +32,8 @@ def main():
     orc = Oracle()
     ok = True
     for (n, phi, seed, sf, p2p) in [(200000, 0.70, 5, 0.3, False), (200000, 0.70, 5, 0.3, True),
-                                    (60000, 0.85, 6, 0.0, True)]:
+                                    (60000, 0.85, 6, 0.0, True), (150000, 0.70, 7, 0.0, False),
+                                    (150000, 0.72, 8, 0.0, True)]:   # monodisperse: the lean sweep
         cfg = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf)
         N, lx, ly, t = cfg["n"], cfg["lx"], cfg["ly"], 1.25
         cells = orc.cells(N, lx, ly, cfg["x"], cfg["y"]).reshape(N, 2)

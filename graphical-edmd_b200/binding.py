@@ -24,6 +24,7 @@ OPT_FORCE_GENERIC = 1
 OPT_NO_LEAN = 2
 EPLAN = 6
 STAT_EXACT_RESCANS = 1
+STAT_LEAN_SWEEPS = 2
 
 # every symbol include/edmd_cuda.h declares
 SYMBOLS = [

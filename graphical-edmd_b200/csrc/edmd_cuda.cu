@@ -345,6 +345,10 @@ int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
 int edmd_cuda_get_stat(edmd_ctx *c, int stat, uint64_t *value)
 {
     if (!c || !value) return EDMD_EINVAL;
+    if (stat == EDMD_STAT_LEAN_SWEEPS) {
+        *value = c->lean_sweeps;
+        return 0;
+    }
     if (stat != EDMD_STAT_EXACT_RESCANS) return fail(c, EDMD_EINVAL, "unknown stat");
     CU(cudaSetDevice(c->device));
     uint32_t v = 0;
@@ -588,6 +592,7 @@ static int sweep_launch(edmd_ctx *c, int mode)
         launched += edmd_launch_lean_index(c);
         launched += edmd_launch_predict_lean(c);
         c->index_lean = true;
+        c->lean_pending = true;
     } else {
         launched += edmd_launch_cell_index(c, mode);
         launched += edmd_launch_predict(c, mode);
@@ -621,7 +626,12 @@ static int lean_fallback(edmd_ctx *c)
     int32_t f = 0;
     CU(cudaMemcpyAsync(&f, c->flags + kFlagLeanFail, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (!f) return 0;
+    if (!f) {
+        if (c->lean_pending) c->lean_sweeps++;
+        c->lean_pending = false;
+        return 0;
+    }
+    c->lean_pending = false;
     c->lean_ok = false;
     CU(cudaMemsetAsync(c->flags + kFlagLeanFail, 0, sizeof(int32_t), c->stream));
     CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));

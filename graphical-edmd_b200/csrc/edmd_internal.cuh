@@ -151,6 +151,8 @@ struct edmd_ctx {
     float vmax;          // largest |velocity component| of the upload
     uint32_t index_epoch;
     int pred_mode;       // mode of the last sweep
+    bool lean_pending;   // the last sweep was launched on the lean path and not yet confirmed
+    uint64_t lean_sweeps; // sweeps confirmed on the lean path
     bool have_vr;
     double t;            // time of the resident snapshot
     int nghost;          // ghost entries of the current upload

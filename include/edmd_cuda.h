@@ -90,6 +90,9 @@ int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 /* Counters: EDMD_STAT_EXACT_RESCANS = particles the tiled sweep had to resolve
  * with the exact re-scan (near-ties, ill-conditioned pairs) since create. */
 #define EDMD_STAT_EXACT_RESCANS 1
+/* EDMD_STAT_LEAN_SWEEPS = sweeps that completed on the lean path (counted when
+ * their results are fetched or planned from; declined ones are not). */
+#define EDMD_STAT_LEAN_SWEEPS 2
 int edmd_cuda_get_stat(edmd_ctx *ctx, int stat, uint64_t *value);
 
 /* Page-locked host memory for the caller's particle arrays: uploads and

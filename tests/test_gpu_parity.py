@@ -389,11 +389,75 @@ def test_lean_and_full_sweeps_agree(pkg, n, phi, seed, vscale):
         r0 = ctx.stat(pkg.binding.STAT_EXACT_RESCANS)
         a = ctx.predict_all()
         rescans = ctx.stat(pkg.binding.STAT_EXACT_RESCANS) - r0
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 1
         ctx.set_option(pkg.binding.OPT_NO_LEAN, 1)
         b = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 1
     for k in ("t_cross", "dir", "t_coll", "partner", "ctype"):
         assert np.array_equal(a[k], b[k]), k
     assert rescans < 0.02 * c["n"], rescans
+
+
+def _adversarial_clusters(seed, n_clusters, vscale):
+    """Isolated 3-particle clusters on a coarse grid, built so that the FP32 screening
+    of the lean sweep is at its limits: two partners whose collision times with the
+    centre particle differ by a relative 10^-k (k = 1 .. 12, incl. exact ties), partners
+    almost in contact (gap 10^-k), grazing trajectories (det ~ 0 within 10^-k), and
+    nearly parallel motion (b ~ 0)."""
+    rng = np.random.default_rng(seed)
+    pitch = 16.0     # centres >= 10 apart, clusters <= 3.3 in radius: no overlaps between clusters
+    m = int(np.ceil(np.sqrt(n_clusters)))
+    lx = ly = m * pitch
+    x, y, vx, vy = [], [], [], []
+    for q in range(n_clusters):
+        cx, cy = (q % m + 0.5) * pitch + rng.uniform(-3, 3), (q // m + 0.5) * pitch + rng.uniform(-3, 3)
+        kind = q % 4
+        eps = 10.0 ** -rng.integers(1, 13)
+        v0 = rng.uniform(0.2, 3.0) * vscale
+        ang = rng.uniform(0, 2 * np.pi)
+        ca, sa = np.cos(ang), np.sin(ang)
+        pts = [(0.0, 0.0, 0.0, 0.0)]
+        if kind == 0:      # two head-on partners, times t and t (1 + eps) (eps = 1e-12 ~ a tie)
+            d1 = rng.uniform(2.05, 3.2)
+            t1 = (d1 - 2.0) / v0
+            d2 = 2.0 + v0 * t1 * (1.0 + (eps if rng.random() < 0.8 else 0.0))
+            pts += [(d1, 0.0, -v0, 0.0), (-d2, 0.0, v0, 0.0)]
+        elif kind == 1:    # a partner almost in contact, approaching slowly or fast
+            pts += [(2.0 + eps, 0.0, -v0 * rng.choice([1e-3, 1.0]), 0.0),
+                    (0.0, rng.uniform(2.3, 3.0), 0.0, -v0)]
+        elif kind == 2:    # grazing: impact parameter 2 (1 -+ eps)
+            b_imp = 2.0 * (1.0 + eps * rng.choice([-1.0, 1.0]))
+            pts += [(rng.uniform(2.5, 3.3), b_imp if b_imp < 3.2 else 2.0, -v0, 0.0),
+                    (-rng.uniform(2.2, 3.0), 0.0, 0.3 * v0, 0.0)]
+        else:              # nearly parallel motion (b ~ 0) next to a real partner
+            pts += [(0.0, 2.0 + rng.uniform(0.01, 0.8), v0 * eps, v0 * eps * rng.choice([-1.0, 1.0])),
+                    (rng.uniform(2.2, 3.2), 0.0, -v0, 0.0)]
+        for (dx, dy, ux, uy) in pts:
+            x.append(cx + ca * dx - sa * dy)
+            y.append(cy + sa * dx + ca * dy)
+            vx.append(ca * ux - sa * uy)
+            vy.append(sa * ux + ca * uy)
+    n = len(x)
+    return dict(n=n, lx=lx, ly=ly, x=np.array(x), y=np.array(y), vx=np.array(vx), vy=np.array(vy),
+                rad=np.ones(n))
+
+
+@pytest.mark.parametrize("seed,vscale", [(61, 1.0), (62, 1.0), (63, 1e-5), (64, 2e3)])
+def test_lean_certificate_on_adversarial_pairs(pkg, oracle, seed, vscale):
+    """Near-ties, near-contacts, grazing and nearly parallel pairs at relative
+    margins from 10^-1 down to 10^-12: whatever the FP32 bounds cannot decide must
+    reach the exact re-scan, so the lean sweep still equals the oracle bit for bit."""
+    c = _adversarial_clusters(seed, 20000, vscale)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.5)
+        r0 = ctx.stat(pkg.binding.STAT_EXACT_RESCANS)
+        got = ctx.predict_all(allow_overlap=True)
+        rescans = ctx.stat(pkg.binding.STAT_EXACT_RESCANS) - r0
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 1       # it did run on the lean path
+    want = oracle_sweep(oracle, c, t=0.5)
+    assert tuple(got["overlap"]) == tuple(want["overlap"])
+    assert_events_equal(got, want)
+    assert 0 < rescans < 0.6 * c["n"], rescans     # the hard cases do take the exact path, the rest do not
 
 
 def test_lean_handles_heavy_velocity_tails_and_rest(pkg, oracle):
@@ -422,6 +486,7 @@ def test_lean_declines_after_free_flight_out_of_the_cells(pkg, oracle):
         s = ctx.download_state()
         cells = oracle.cells(c["n"], c["lx"], c["ly"], c["x"], c["y"]).reshape(c["n"], 2)
         got = ctx.predict_all(allow_overlap=True)
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 0       # declined on the device
     c2 = dict(c, x=s["x"], y=s["y"])
     want = oracle_sweep(oracle, c2, t=1.5, cells=cells)
     assert_events_equal(got, want)

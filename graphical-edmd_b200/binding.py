@@ -22,6 +22,7 @@ EINVAL, ESTATE, EOVERLAP, ECELL, ENOMEM = 1, 2, 3, 4, 5
 BENCH_SWEEP, BENCH_FREEFLY, BENCH_BOOP, BENCH_PCF = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 1
 OPT_NO_LEAN = 2
+OPT_NO_PDL = 3
 EPLAN = 6
 STAT_EXACT_RESCANS = 1
 STAT_LEAN_SWEEPS = 2

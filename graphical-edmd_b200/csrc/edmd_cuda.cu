@@ -190,6 +190,7 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
     c->n_cap = n;
     c->n_owned = c->n;
     c->slab = slab != 0;
+    c->lean_pdl = true;
     box_init(&c->box, n > 0 ? n : 1, lx, ly);
     c->box.n = n;
     long long nc = (long long)c->box.nxcells * c->box.nycells;
@@ -337,6 +338,10 @@ int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
     }
     if (option == EDMD_OPT_NO_LEAN) {
         c->lean_off = value != 0;
+        return 0;
+    }
+    if (option == EDMD_OPT_NO_PDL) {
+        c->lean_pdl = value == 0;
         return 0;
     }
     return fail(c, EDMD_EINVAL, "unknown option");

@@ -147,6 +147,7 @@ struct edmd_ctx {
     bool index_lean;     // ... but is the LEAN index (lean.cuh): no spos / saux records
     bool lean_ok;        // resident state is eligible for the lean sweep (monodisperse, sane speeds)
     bool lean_off;       // EDMD_OPT_NO_LEAN
+    bool lean_pdl;       // launch the lean chain with programmatic dependent launch (default on)
     double rad0;         // radius of the first particle (the common radius when lean_ok)
     float vmax;          // largest |velocity component| of the upload
     uint32_t index_epoch;

@@ -86,6 +86,9 @@ uint64_t edmd_cuda_launch_count(const edmd_ctx *ctx);
  * exact FP64 evaluation, graphical-edmd_b200/csrc/lean.cuh); results are
  * identical, it exists for cross-checking and timing. */
 #define EDMD_OPT_NO_LEAN 2
+/* EDMD_OPT_NO_PDL = 1 launches the lean sweep's kernel chain without programmatic
+ * dependent launch (plain stream order); for timing comparisons. */
+#define EDMD_OPT_NO_PDL 3
 int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 /* Counters: EDMD_STAT_EXACT_RESCANS = particles the tiled sweep had to resolve
  * with the exact re-scan (near-ties, ill-conditioned pairs) since create. */

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kThreads)
 k_count(int n, const int32_t *__restrict__ cid, int32_t *__restrict__ cnt,
         int32_t *__restrict__ rank)
 {
+    edmd_pdl_wait();
     const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (i + 3 < n) {
         const int4 c = *reinterpret_cast<const int4 *>(cid + i);
@@ -116,6 +117,7 @@ k_rowscan(int nx, int ps, int32_t *__restrict__ cnt, int32_t *__restrict__ off,
     __shared__ int s_carry;
     const int Y = blockIdx.x;
     const int tid = threadIdx.x;
+    edmd_pdl_wait();
     int32_t *row = cnt + (size_t)Y * ps;
     int32_t *orow = off + (size_t)Y * ps;
     if (tid == 0) s_carry = 0;
@@ -160,6 +162,7 @@ k_rowbase(int ny, const int32_t *__restrict__ row_total, int32_t *__restrict__ r
     __shared__ int s_warp[kBaseThreads / 32];
     __shared__ int s_carry;
     const int tid = threadIdx.x;
+    edmd_pdl_wait();
     if (tid == 0) s_carry = 0;
     __syncthreads();
     for (int base = 0; base < ny; base += kBaseThreads) {
@@ -207,6 +210,7 @@ k_chunkmeta(int nx, int ny, int ps, int gny, int yoff, int slab, const int32_t *
             int cap_off)
 {
     const int Y = blockIdx.x;
+    edmd_pdl_wait();
     const int rb = row_base[Y];
     const int tot = row_total[Y];
     const int nch = (tot + 31) >> 5;
@@ -288,6 +292,7 @@ k_scatter(int n, int nx, int ps, const int32_t *__restrict__ cid,
           double *__restrict__ svr)
 {
     const int i0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    edmd_pdl_wait();
     if (i0 >= n) return;
     const bool two = i0 + 1 < n;
     int pc[2], rk[2];
@@ -427,25 +432,25 @@ int edmd_launch_cell_index(edmd_ctx *c, int mode)
     const int blocks = ((n + 1) / 2 + kThreads - 1) / kThreads;
     int launched = 0;
     if (n > 0) {
-        k_count<<<blocks4, kThreads, 0, c->stream>>>(n, c->cid, c->cell_cnt, c->rank);
+        // first kernel of the chain: plain launch (everything before it on the stream completes first)
+        edmd_launch(k_count, dim3(blocks4), dim3(kThreads), 0, c->stream, false, n, c->cid, c->cell_cnt, c->rank);
         launched++;
     }
-    k_rowscan<<<c->dbox.nl, kThreads, 0, c->stream>>>(c->dbox.nx, c->ps, c->cell_cnt, c->off,
-                                                     c->row_total);
-    k_rowbase<<<1, kBaseThreads, 0, c->stream>>>(c->dbox.nl, c->row_total, c->row_base);
-    k_chunkmeta<<<c->dbox.nl, kMetaThreads, 0, c->stream>>>(
-        c->dbox.nx, c->dbox.nl, c->ps, c->dbox.ny, c->dbox.yoff, c->slab ? 1 : 0, c->off, c->row_total,
-        c->row_base, c->meta, c->cstart, edmd_chunks_bound(c), kCapW, kOffW);
+    const bool pdl = c->lean_pdl;
+    edmd_launch(k_rowscan, dim3(c->dbox.nl), dim3(kThreads), 0, c->stream, pdl && n > 0, c->dbox.nx, c->ps,
+                c->cell_cnt, c->off, c->row_total);
+    edmd_launch(k_rowbase, dim3(1), dim3(kBaseThreads), 0, c->stream, pdl, c->dbox.nl, c->row_total, c->row_base);
+    edmd_launch(k_chunkmeta, dim3(c->dbox.nl), dim3(kMetaThreads), 0, c->stream, pdl, c->dbox.nx, c->dbox.nl,
+                c->ps, c->dbox.ny, c->dbox.yoff, c->slab ? 1 : 0, c->off, c->row_total, c->row_base, c->meta,
+                c->cstart, edmd_chunks_bound(c), kCapW, kOffW);
     launched += 3;
     if (n > 0) {
         if (mode == EDMD_MODE_GROW)
-            k_scatter<true><<<blocks, kThreads, 0, c->stream>>>(
-                n, c->dbox.nx, c->ps, c->cid, c->rank, c->cstart, c->xv, c->rad,
-                c->vr, c->spos, c->saux, c->svr);
+            edmd_launch(k_scatter<true>, dim3(blocks), dim3(kThreads), 0, c->stream, pdl, n, c->dbox.nx, c->ps,
+                        c->cid, c->rank, c->cstart, c->xv, c->rad, c->vr, c->spos, c->saux, c->svr);
         else
-            k_scatter<false><<<blocks, kThreads, 0, c->stream>>>(
-                n, c->dbox.nx, c->ps, c->cid, c->rank, c->cstart, c->xv, c->rad,
-                c->vr, c->spos, c->saux, c->svr);
+            edmd_launch(k_scatter<false>, dim3(blocks), dim3(kThreads), 0, c->stream, pdl, n, c->dbox.nx, c->ps,
+                        c->cid, c->rank, c->cstart, c->xv, c->rad, c->vr, c->spos, c->saux, c->svr);
         launched++;
     }
     c->index_has_vr = (mode == EDMD_MODE_GROW);

@@ -76,35 +76,3 @@ __device__ __forceinline__ double4 ld_sector(const double4 *p)
     asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
     return v;
 }
-
-// ---- programmatic dependent launch -----------------------------------------------
-// The five kernels of a lean sweep form a dependent chain on one stream.  Each is
-// launched with the programmatic-stream-serialization attribute and begins with
-// griddepcontrol.wait (nothing reads predecessor data before it): the launch and
-// scheduling latency of kernel k+1 then overlaps the tail of kernel k.  Measured at
-// N = 10^6: 110 -> 103 us per step.  Triggering the dependents EARLY
-// (griddepcontrol.launch_dependents at kernel start) was slower, 117 us: the waiting
-// CTAs of the next kernel take SM resources from the running one.
-__device__ __forceinline__ void lean_pdl_begin()
-{
-#if __CUDA_ARCH__ >= 900
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-}
-
-template <typename Kernel, typename Args>
-inline cudaError_t lean_launch(Kernel k, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
-                               const Args &args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k, args);
-}

@@ -31,7 +31,7 @@ k_lean_count(const __grid_constant__ CountArgs a)
     const int32_t *__restrict__ cid = a.cid;
     int32_t *__restrict__ cnt = a.cnt;
     int32_t *__restrict__ flags = a.flags;
-    lean_pdl_begin();   // the previous kernel on the stream may still be reading the histogram's inputs
+    edmd_pdl_wait();   // the previous kernel on the stream may still be reading the histogram's inputs
     const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (i == 0) flags[kFlagWork] = 0;   // the index kernel (next launch) appends to the work list
     if (i + 3 < n) {
@@ -79,7 +79,7 @@ k_lean_index(const __grid_constant__ IndexArgs a)
     const int tid = threadIdx.x;
     const int Y = blockIdx.x;
     const int nx = a.nx, ps = a.ps;
-    lean_pdl_begin();
+    edmd_pdl_wait();
     int32_t *row = a.cnt + (size_t)Y * ps;
     int32_t *orow = a.off + (size_t)Y * ps;
     const int rb = Y * a.rowcap;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kThreads)
 k_lean_scatter(const __grid_constant__ ScatterArgs a)
 {
     const int i0 = kPer * (blockIdx.x * blockDim.x + threadIdx.x);
-    lean_pdl_begin();
+    edmd_pdl_wait();
     if (i0 >= a.n || a.flags[kFlagLeanFail] != 0) return;   // a row overflowed its slot range: declined
     int pc[kPer], slot[kPer];
     double4 p[kPer];
@@ -241,7 +241,7 @@ int edmd_launch_lean_index(edmd_ctx *c)
     CountArgs ca;
     ca.n = n; ca.cid = c->cid; ca.cnt = c->cell_cnt; ca.flags = c->flags;
     // the first kernel of the chain is launched plainly: whatever precedes it on the stream completes first
-    lean_launch(k_lean_count, dim3(((n + 3) / 4 + kThreads - 1) / kThreads), dim3(kThreads), 0, c->stream, false, ca);
+    edmd_launch(k_lean_count, dim3(((n + 3) / 4 + kThreads - 1) / kThreads), dim3(kThreads), 0, c->stream, false, ca);
     IndexArgs ia;
     ia.nx = c->dbox.nx; ia.nl = c->dbox.nl; ia.ps = c->ps; ia.slab = c->slab ? 1 : 0;
     ia.rowcap = c->rowcap;
@@ -249,12 +249,12 @@ int edmd_launch_lean_index(edmd_ctx *c)
     ia.chunks = c->lchunks;
     ia.work = c->lwork;
     ia.row_in_smem = (size_t)c->ps * sizeof(int) <= 40960 ? 1 : 0;
-    lean_launch(k_lean_index, dim3(c->dbox.nl), dim3(kThreads), ia.row_in_smem ? (size_t)c->ps * sizeof(int) : 0,
+    edmd_launch(k_lean_index, dim3(c->dbox.nl), dim3(kThreads), ia.row_in_smem ? (size_t)c->ps * sizeof(int) : 0,
                 c->stream, c->lean_pdl, ia);
     ScatterArgs sa;
     sa.n = n; sa.nx = c->dbox.nx; sa.ps = c->ps; sa.b = c->dbox;
     sa.cid = c->cid; sa.xv = c->xv; sa.cursor = c->cstart; sa.flags = c->flags; sa.rec = c->lrec;
-    lean_launch(k_lean_scatter, dim3(((n + kPer - 1) / kPer + kThreads - 1) / kThreads), dim3(kThreads), 0, c->stream,
+    edmd_launch(k_lean_scatter, dim3(((n + kPer - 1) / kPer + kThreads - 1) / kThreads), dim3(kThreads), 0, c->stream,
                 c->lean_pdl, sa);
     c->index_has_vr = false;
     return 3;

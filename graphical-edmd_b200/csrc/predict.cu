@@ -170,6 +170,7 @@ template <bool GROW>
 __global__ void __launch_bounds__(kStageThreads)
 k_predict_generic(const __grid_constant__ SweepArgs a)
 {
+    edmd_pdl_wait();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = s >> 5;
     if (chunk >= a.max_chunks) return;
@@ -283,6 +284,7 @@ __device__ __forceinline__ void predict_one_staged(const SweepArgs &a, const Sta
 __global__ void __launch_bounds__(kStageThreads, kStageCtasPerSm)
 k_predict_rows(const __grid_constant__ SweepArgs a)
 {
+    edmd_pdl_wait();
     const bool sane = a.g.flags[kFlagInsane] == 0;
     row_pipeline(a.g, a.g.meta, a.max_chunks,
                  [&](const StageBuf &buf, const ChunkMeta &m, const RowLane &rl, int status) {
@@ -350,9 +352,9 @@ int edmd_launch_predict(edmd_ctx *c, int mode)
     a.stats = reinterpret_cast<unsigned int *>(c->flags + kFlagRescans);
     const int blocks = (a.max_chunks + kStageWarps - 1) / kStageWarps;
     if (mode == EDMD_MODE_GROW)
-        k_predict_generic<true><<<blocks, kStageThreads, 0, c->stream>>>(a);
+        edmd_launch(k_predict_generic<true>, dim3(blocks), dim3(kStageThreads), 0, c->stream, c->lean_pdl, a);
     else if (c->force_generic)
-        k_predict_generic<false><<<blocks, kStageThreads, 0, c->stream>>>(a);
+        edmd_launch(k_predict_generic<false>, dim3(blocks), dim3(kStageThreads), 0, c->stream, c->lean_pdl, a);
     else {
         static bool attr = false;
         if (!attr) {
@@ -360,7 +362,8 @@ int edmd_launch_predict(edmd_ctx *c, int mode)
             cudaFuncSetAttribute(k_predict_rows, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
             attr = true;
         }
-        k_predict_rows<<<min(blocks, edmd_persistent_blocks(c)), kStageThreads, kStageSmem, c->stream>>>(a);
+        edmd_launch(k_predict_rows, dim3(min(blocks, edmd_persistent_blocks(c))), dim3(kStageThreads), kStageSmem,
+                    c->stream, c->lean_pdl, a);
     }
     return 1;
 }

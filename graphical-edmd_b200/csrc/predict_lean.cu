@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kLeanThreads, kLeanCtas)
 k_screen(const __grid_constant__ ScreenArgs a)
 {
     extern __shared__ __align__(128) unsigned char lean_smem[];
-    lean_pdl_begin();
+    edmd_pdl_wait();
     // the state must be eligible (the host checked what it knows; halo particles
     // arrive on the device): otherwise decline and let the host take the full path
     const LeanConsts K = make_consts(a.b, a.rad0, __int_as_float(a.flags[kFlagVmax]));
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(256)
 k_resolve(const __grid_constant__ ResolveArgs a)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    lean_pdl_begin();
+    edmd_pdl_wait();
     if (i >= a.n_owned) return;
     // all first-level loads go out together (the decline flag is one of them)
     const int declined = a.flags[kFlagLeanFail];
@@ -527,7 +527,7 @@ int edmd_launch_predict_lean(edmd_ctx *c)
     }
     const int blocks = (sa.max_chunks + kLeanWarps - 1) / kLeanWarps;
     const int grid = (c->sm_count > 0 ? c->sm_count : 148) * kLeanCtas;
-    lean_launch(k_screen, dim3(blocks < grid ? blocks : grid), dim3(kLeanThreads), kLeanSmem, c->stream, c->lean_pdl, sa);
+    edmd_launch(k_screen, dim3(blocks < grid ? blocks : grid), dim3(kLeanThreads), kLeanSmem, c->stream, c->lean_pdl, sa);
     int launched = 1;
     if (c->n_owned > 0) {
         ResolveArgs ra;
@@ -542,7 +542,7 @@ int edmd_launch_predict_lean(edmd_ctx *c)
         ra.t_cross = c->t_cross; ra.dir = c->dir; ra.t_coll = c->t_coll; ra.partner = c->partner;
         ra.ctype = c->ctype;
         ra.overlap_key = c->overlap_key;
-        lean_launch(k_resolve, dim3((c->n_owned + 255) / 256), dim3(256), 0, c->stream, c->lean_pdl, ra);
+        edmd_launch(k_resolve, dim3((c->n_owned + 255) / 256), dim3(256), 0, c->stream, c->lean_pdl, ra);
         launched++;
     }
     return launched;

@@ -39,7 +39,7 @@ SYMBOLS = [
     "edmd_cuda_create_slab", "edmd_cuda_upload_owned", "edmd_cuda_halo_pack",
     "edmd_cuda_halo_append", "edmd_cuda_get_counts", "edmd_cuda_pcf_device",
     "edmd_cuda_halo_export", "edmd_cuda_halo_connect", "edmd_cuda_halo_exchange",
-    "edmd_cuda_calendar_plan",
+    "edmd_cuda_calendar_plan", "edmd_cuda_pcf_bond_order", "edmd_cuda_bragg_peak",
 ]
 HALO_RECORD_BYTES = 48
 
@@ -108,6 +108,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_host_free.argtypes = [vp]
     lib.edmd_cuda_host_free.restype = None
     lib.edmd_cuda_set_option.argtypes = [vp, C.c_int, C.c_int]
+    lib.edmd_cuda_pcf_bond_order.argtypes = [vp, C.c_double, C.c_double, vp, vp, vp, vp, C.POINTER(C.c_int)]
+    lib.edmd_cuda_bragg_peak.argtypes = [vp, C.c_double, vp, C.POINTER(C.c_double)]
     lib.edmd_cuda_calendar_plan.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, vp,
                                             C.POINTER(C.c_int32)]
     lib.edmd_cuda_get_stat.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
@@ -310,6 +312,26 @@ class EdmdCuda:
         self._check(self.lib.edmd_cuda_boop_cutoff(
             self._h, r_c, _ptr(q5), _ptr(q6), _ptr(q7), _ptr(arg), _ptr(nb), C.addressof(mean)))
         return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, mean_q6=mean.value)
+
+    def pcf_bond_order(self, dr, max_r, k_vector):
+        """calculate_bond_order_pcf (src/pcf.c:77-167) on the resident positions."""
+        k = np.ascontiguousarray(k_vector, dtype=np.float64)
+        nb = C.c_int(0)
+        self._check(self.lib.edmd_cuda_pcf_bond_order(self._h, dr, max_r, _ptr(k), None, None, None,
+                                                      C.byref(nb)))
+        counts = np.zeros(nb.value, np.uint64)
+        g = np.zeros(nb.value, np.float64)
+        g6 = np.zeros(nb.value, np.float64)
+        self._check(self.lib.edmd_cuda_pcf_bond_order(self._h, dr, max_r, _ptr(k), _ptr(counts), _ptr(g),
+                                                      _ptr(g6), C.byref(nb)))
+        return dict(num_bins=nb.value, counts=counts, g_r=g, g6_r=g6)
+
+    def bragg_peak(self, expected_bragg):
+        """find_max_structure_factor_bragg (src/pcf.c:405-467) on the resident positions."""
+        k = np.zeros(2, np.float64)
+        s = C.c_double(0.0)
+        self._check(self.lib.edmd_cuda_bragg_peak(self._h, float(expected_bragg), _ptr(k), C.byref(s)))
+        return dict(k=k, s_max=s.value)
 
     def calendar_plan(self, paul_time, dt_paul, paul_n, actual_paul, allow_declined=False):
         """Ingest plan of the last sweep's 2N events for an empty calendar

@@ -303,7 +303,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
                    c->lrec, c->lchunks, c->lres, c->lwork, c->cal_mem,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
-                   c->overlap_key, c->flags, c->pcf_counts, c->boop, c->boop_nb,
+                   c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
     for (void *p : dev)
         if (p) cudaFree(p);
@@ -850,6 +850,121 @@ int edmd_cuda_pcf(edmd_ctx *c, double dr, double max_r, uint64_t *counts, double
             g_r[i] = norm > 0 ? g / norm : 0.0;
         }
     }
+    return 0;
+}
+
+// calculate_bond_order_pcf, src/pcf.c:77-167
+int edmd_cuda_pcf_bond_order(edmd_ctx *c, double dr, double max_r, const double *k_vector,
+                             uint64_t *counts, double *g_r, double *g6_r, int *num_bins)
+{
+    if (!c || !num_bins || !k_vector) return EDMD_EINVAL;
+    if (!(dr > 0) || !(max_r >= 0)) return fail(c, EDMD_EINVAL, "bad dr / max_r");
+    double q = max_r / dr;
+    if (!(q < 1e8)) return fail(c, EDMD_EINVAL, "too many bins");
+    const int nb = (int)q;  // `(int)(max_r / dr)` src/pcf.c:82
+    *num_bins = nb;
+    if (!counts && !g_r && !g6_r) return 0;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "pcf before upload");
+    CU(cudaSetDevice(c->device));
+    int r;
+    if (nb > c->pcf_cap) {
+        if (c->pcf_counts) CU(cudaFree(c->pcf_counts));
+        c->pcf_counts = nullptr;
+        c->pcf_cap = 0;
+        if ((r = dev_alloc(c, &c->pcf_counts, (size_t)nb))) return r;
+        c->pcf_cap = nb;
+    }
+    if (nb > c->pcf_wcap) {
+        if (c->pcf_wsum) CU(cudaFree(c->pcf_wsum));
+        c->pcf_wsum = nullptr;
+        c->pcf_wcap = 0;
+        if ((r = dev_alloc(c, &c->pcf_wsum, (size_t)nb))) return r;
+        c->pcf_wcap = nb;
+    }
+    std::vector<unsigned long long> hc((size_t)(nb > 0 ? nb : 1)), hw((size_t)(nb > 0 ? nb : 1));
+    if (nb > 0) {
+        CU(cudaMemsetAsync(c->pcf_counts, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(c->pcf_wsum, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
+        c->launches += edmd_launch_pcf_bond_order(c, dr, max_r, nb, k_vector[0], k_vector[1], c->pcf_counts,
+                                                  c->pcf_wsum);
+        CU(cudaGetLastError());
+        if ((r = d2h(c, hc.data(), c->pcf_counts, (size_t)nb * sizeof(unsigned long long)))) return r;
+        if ((r = d2h(c, hw.data(), c->pcf_wsum, (size_t)nb * sizeof(unsigned long long)))) return r;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    // per-bin average and normalisation, src/pcf.c:146-166 (ordered pairs = 2 x unordered)
+    const double volume = c->box.lx * c->box.ly;
+    const double density = c->n / volume;
+    for (int i = 0; i < nb; i++) {
+        if (counts) counts[i] = hc[i];
+        const double sum = (double)(long long)hw[i] / 4294967296.0;
+        if (g6_r) g6_r[i] = hc[i] ? sum / (double)hc[i] : 0.0;
+        if (g_r) {
+            const double rr = (i + 0.5) * dr;
+            const double expected = 2 * M_PI * rr * dr * density * c->n;
+            g_r[i] = expected > 0 ? 2.0 * (double)hc[i] / expected : 0.0;
+        }
+    }
+    return 0;
+}
+
+// find_max_structure_factor_bragg, src/pcf.c:405-467
+int edmd_cuda_bragg_peak(edmd_ctx *c, double expected_bragg, double *k_out, double *s_max)
+{
+    if (!c || !k_out) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "bragg_peak before upload");
+    if (!(expected_bragg > 0) || !(expected_bragg < 1e3)) return fail(c, EDMD_EINVAL, "bad expected_bragg");
+    CU(cudaSetDevice(c->device));
+    // the reference's grid and wedge (:407-437), same expressions, same loop order
+    const double Lx = c->box.lx, Ly = c->box.ly;
+    const double dkx = 2 * M_PI / Lx, dky = 2 * M_PI / Ly;
+    const double kx_min = floor((-expected_bragg - 0.8) / dkx) * dkx;
+    const double kx_max = ceil((expected_bragg + 0.8) / dkx) * dkx;
+    const double ky_min = floor((-expected_bragg - 0.8) / dky) * dky;
+    const double ky_max = ceil((expected_bragg + 0.8) / dky) * dky;
+    std::vector<double2> ks;
+    try {
+        for (int iky = 0; iky <= (int)((ky_max - ky_min) / dky); iky++) {
+            for (int ikx = 0; ikx <= (int)((kx_max - kx_min) / dkx); ikx++) {
+                const double kx = kx_min + ikx * dkx;
+                const double ky = ky_max - iky * dky;
+                const double k_abs = sqrt(kx * kx + ky * ky);
+                const double theta = atan2(ky, kx);
+                if (k_abs < 1.5 || theta < M_PI / 2 - M_PI / 5 || theta > M_PI / 2 + M_PI / 5) continue;
+                ks.push_back(make_double2(kx, ky));
+            }
+        }
+    } catch (...) {
+        return fail(c, EDMD_ENOMEM, "host staging allocation failed");
+    }
+    k_out[0] = k_out[1] = 0.0;   // `best_k = {0, 0}` when nothing qualifies
+    if (s_max) *s_max = -1.0;
+    const int nk = (int)ks.size();
+    if (nk == 0 || c->n == 0) return 0;
+    double *scratch = nullptr;
+    const size_t doubles = 4 * (size_t)nk + 4;
+    CU(cudaMalloc((void **)&scratch, doubles * sizeof(double)));
+    double2 *d_k = reinterpret_cast<double2 *>(scratch);
+    double *d_re = scratch + 2 * (size_t)nk, *d_im = d_re + nk, *d_s = d_im + nk;
+    int *d_i = reinterpret_cast<int *>(d_s + 1);
+    cudaError_t e = cudaMemcpyAsync(d_k, ks.data(), (size_t)nk * sizeof(double2), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_re, 0, 2 * (size_t)nk * sizeof(double), c->stream);
+    if (e == cudaSuccess) {
+        c->launches += edmd_launch_bragg(c, nk, d_k, d_re, d_im, d_s, d_i);
+        e = cudaGetLastError();
+    }
+    double best = -1.0;
+    int bi = -1;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&best, d_s, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bi, d_i, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return fail_cuda(c, e, "bragg_peak");
+    if (bi >= 0) {
+        k_out[0] = ks[(size_t)bi].x;
+        k_out[1] = ks[(size_t)bi].y;
+    }
+    if (s_max) *s_max = best;
     return 0;
 }
 

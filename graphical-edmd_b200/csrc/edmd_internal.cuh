@@ -214,6 +214,8 @@ struct edmd_ctx {
 
     // analysis scratch
     unsigned long long *pcf_counts;   // capacity pcf_cap bins
+    unsigned long long *pcf_wsum;     // weighted sums (2^-32 fixed point), capacity pcf_wcap bins
+    int pcf_wcap;
     int pcf_cap;
     double *boop;                     // 4*N doubles q5|q6|q7|arg
     int32_t *boop_nb;                 // N
@@ -270,6 +272,10 @@ int edmd_launch_predict_lean(edmd_ctx *c);
 bool edmd_lean_eligible(const edmd_ctx *c, int mode);
 int edmd_launch_boop(edmd_ctx *c, double r_c);
 int edmd_launch_mean(edmd_ctx *c, const double *v, int n, double *out_dev);
+int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bins, double kx, double ky,
+                               unsigned long long *counts, unsigned long long *wsum);
+int edmd_launch_bragg(edmd_ctx *c, int nk, const double2 *kvec, double *re, double *im, double *best_s,
+                      int *best_i);
 int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
                     int n, int part, int nparts, unsigned long long *counts);
 

@@ -198,6 +198,23 @@ int edmd_cuda_get_counts(const edmd_ctx *ctx, int *n_owned, int *n_total);
 int edmd_cuda_pcf_device(edmd_ctx *ctx, const double *xy_dev, int n_total, double dr, double max_r,
                          int part, int nparts, uint64_t *counts_dev, int *num_bins);
 
+/* ---- weighted g(r) family -------------------------------------------------- */
+
+/* Replaces calculate_bond_order_pcf (src/pcf.c:77-167; caller save_pcf_boop
+ * :338-403 with dr = 2, max_r = min(Lx,Ly)/2): g(r) and the average of
+ * cos(k_vector . d) over the pairs of each bin, on the resident positions.
+ * counts[b] = unordered pairs in bin b (the reference's g_r[b] before
+ * normalisation is 2 counts[b]); g_r is normalised as the reference does; g6_r
+ * = per-bin average (0 for empty bins).  Any output may be NULL. */
+int edmd_cuda_pcf_bond_order(edmd_ctx *ctx, double dr, double max_r, const double *k_vector,
+                             uint64_t *counts, double *g_r, double *g6_r, int *num_bins);
+/* Replaces find_max_structure_factor_bragg (src/pcf.c:405-467): the wave vector
+ * k = (2 pi i / Lx, 2 pi j / Ly) with the largest S(k) = |sum_j e^{i k.r_j}|^2 / N
+ * among those with |k| >= 1.5 inside the wedge |arg k - pi/2| <= pi/5 and the
+ * square |k_x|, |k_y| <= expected_bragg + 0.8; the first maximum in the
+ * reference's loop order wins.  s_max (optional) = that S(k). */
+int edmd_cuda_bragg_peak(edmd_ctx *ctx, double expected_bragg, double *k_out, double *s_max);
+
 /* ---- calendar ingest plan ----------------------------------------------- */
 
 /* For the 2N events of the last sweep (event e = i: crossing of particle i at

@@ -399,3 +399,86 @@ void oracle_boop_cutoff(const oracle_box *b, int n, const double *x,
 	cell_list_free(&cl);
 	free(cell_xy);
 }
+
+/* calculate_bond_order_pcf, src/pcf.c:77-167.  The reference walks ORDERED pairs
+ * (i != j) and adds 1 and cos(k.d) per pair; cos is even and d_ji = -d_ij, so
+ * both sums are twice the sums over unordered pairs, which is what is walked
+ * here (counts as integers).  g6_r = sum / count per bin (0 where empty), g_r
+ * normalised like calculate_pcf with the ordered count. */
+int oracle_bond_order_pcf(const oracle_box *b, int n, const double *x, const double *y,
+                          double dr, double max_r, double kx, double ky, uint64_t *counts,
+                          double *g_r, double *g6_r)
+{
+	int num_bins = oracle_pcf_num_bins(dr, max_r);
+	double bin_width = dr;
+	if (num_bins <= 0)
+		return num_bins;
+	memset(counts, 0, (size_t)num_bins * sizeof(uint64_t));
+	double *sum = (double *)calloc((size_t)num_bins, sizeof(double));
+	for (int i = 0; i < n; i++) {
+		for (int j = i + 1; j < n; j++) {
+			double dx = x[j] - x[i];
+			double dy = y[j] - y[i];
+			dx = min_image(dx, b->half_lx, b->lx);
+			dy = min_image(dy, b->half_ly, b->ly);
+			double r = sqrt(dx * dx + dy * dy);
+			if (r < max_r) {
+				int bin = (int)(r / bin_width);
+				if (bin < num_bins) {
+					counts[bin] += 1;
+					sum[bin] += cos(kx * dx + ky * dy); /* src/pcf.c:123 */
+				}
+			}
+		}
+	}
+	double volume = b->lx * b->ly;
+	double density = n / volume;
+	for (int i = 0; i < num_bins; i++) {
+		double r = (i + 0.5) * bin_width;
+		g6_r[i] = counts[i] ? sum[i] / (double)counts[i] : 0.0; /* :147-153 */
+		double expected = 2 * M_PI * r * bin_width * density * n;   /* :158-166 */
+		g_r[i] = expected > 0 ? 2.0 * (double)counts[i] / expected : 0.0;
+	}
+	free(sum);
+	return num_bins;
+}
+
+/* find_max_structure_factor_bragg, src/pcf.c:405-467: S(k) = |sum_j exp(i k.r_j)|^2 / N
+ * on the reciprocal grid inside the wedge the reference searches; the first
+ * maximum in its (iky, ikx) loop order wins.  s_out (optional) = that maximum. */
+void oracle_bragg_peak(int n, const double *x, const double *y, double lx, double ly,
+                       double expected_bragg, double *k_out, double *s_out)
+{
+	double max_S = -1, best[2] = {0.0, 0.0};
+	double dkx = 2 * M_PI / lx, dky = 2 * M_PI / ly;
+	double kx_min = floor((-expected_bragg - 0.8) / dkx) * dkx;
+	double kx_max = ceil((expected_bragg + 0.8) / dkx) * dkx;
+	double ky_min = floor((-expected_bragg - 0.8) / dky) * dky;
+	double ky_max = ceil((expected_bragg + 0.8) / dky) * dky;
+	for (int iky = 0; iky <= (int)((ky_max - ky_min) / dky); iky++) {
+		for (int ikx = 0; ikx <= (int)((kx_max - kx_min) / dkx); ikx++) {
+			double kx = kx_min + ikx * dkx;
+			double ky = ky_max - iky * dky;
+			double k_abs = sqrt(kx * kx + ky * ky);
+			double theta = atan2(ky, kx);
+			if (k_abs < 1.5 || theta < M_PI / 2 - M_PI / 5 || theta > M_PI / 2 + M_PI / 5)
+				continue;
+			double re = 0.0, im = 0.0;
+			for (int j = 0; j < n; j++) {
+				double phase = kx * x[j] + ky * y[j];
+				re += cos(phase);
+				im += sin(phase);
+			}
+			double S = (re * re + im * im) / n;
+			if (S > max_S) {
+				max_S = S;
+				best[0] = kx;
+				best[1] = ky;
+			}
+		}
+	}
+	k_out[0] = best[0];
+	k_out[1] = best[1];
+	if (s_out)
+		*s_out = max_S;
+}

@@ -80,4 +80,11 @@ void oracle_boop_cutoff(const oracle_box *b, int n, const double *x,
 #ifdef __cplusplus
 }
 #endif
+/* weighted g(r) family (src/pcf.c:77-167, 405-467) */
+int oracle_bond_order_pcf(const oracle_box *b, int n, const double *x, const double *y,
+                          double dr, double max_r, double kx, double ky, uint64_t *counts,
+                          double *g_r, double *g6_r);
+void oracle_bragg_peak(int n, const double *x, const double *y, double lx, double ly,
+                       double expected_bragg, double *k_out, double *s_out);
+
 #endif

@@ -122,6 +122,26 @@ class Oracle:
         return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb)
 
 
+    def bond_order_pcf(self, n, lx, ly, x, y, dr, max_r, k):
+        b = self.box(n, lx, ly)
+        x, y = _f64(x), _f64(y)
+        nb = self.lib.oracle_pcf_num_bins(C.c_double(dr), C.c_double(max_r))
+        counts = np.zeros(max(nb, 1), np.uint64)
+        g = np.zeros(max(nb, 1), np.float64)
+        g6 = np.zeros(max(nb, 1), np.float64)
+        self.lib.oracle_bond_order_pcf(C.byref(b), n, _p(x), _p(y), C.c_double(dr), C.c_double(max_r),
+                                       C.c_double(k[0]), C.c_double(k[1]), _p(counts), _p(g), _p(g6))
+        return dict(num_bins=nb, counts=counts[:nb], g_r=g[:nb], g6_r=g6[:nb])
+
+    def bragg_peak(self, n, lx, ly, x, y, expected_bragg):
+        x, y = _f64(x), _f64(y)
+        k = np.zeros(2, np.float64)
+        s = C.c_double(0.0)
+        self.lib.oracle_bragg_peak(n, _p(x), _p(y), C.c_double(lx), C.c_double(ly),
+                                   C.c_double(expected_bragg), _p(k), C.byref(s))
+        return dict(k=k, s_max=s.value)
+
+
 class Reference:
     """The unmodified reference behind ref_shim.c.  Holds global state: one
     system at a time per process."""
@@ -214,6 +234,22 @@ class Reference:
         nb = np.empty(n, np.int32)
         sec = self.lib.ref_boop_cutoff(r_c, _p(q5), _p(q6), _p(q7), _p(arg), _p(nb))
         return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, seconds=sec)
+
+    def bond_order_pcf(self, dr, max_r, k):
+        nb_guess = int(max_r / dr) + 2
+        g = np.zeros(nb_guess, np.float64)
+        g6 = np.zeros(nb_guess, np.float64)
+        nb = C.c_int(0)
+        self.lib.ref_bond_order_pcf.restype = C.c_double
+        sec = self.lib.ref_bond_order_pcf(C.c_double(dr), C.c_double(max_r), C.c_double(k[0]),
+                                          C.c_double(k[1]), _p(g), _p(g6), C.byref(nb))
+        return dict(num_bins=nb.value, g_r=g[:nb.value], g6_r=g6[:nb.value], seconds=sec)
+
+    def bragg_peak(self, expected_bragg):
+        k = np.zeros(2, np.float64)
+        self.lib.ref_bragg_peak.restype = C.c_double
+        sec = self.lib.ref_bragg_peak(C.c_double(expected_bragg), _p(k))
+        return dict(k=k, seconds=sec)
 
 
 def calendar_plan_oracle(t_cross, t_coll, paul_time, dt_paul, paul_n, actual_paul):

@@ -300,4 +300,32 @@ double ref_boop_cutoff(double r_c, double *q5, double *q6, double *q7,
 	return t1 - t0;
 }
 
+/* calculate_bond_order_pcf (src/pcf.c:77-167): g(r) and the cos(k.r)-weighted
+ * average per bin, for a given wave vector.  Returns seconds. */
+double ref_bond_order_pcf(double dr, double max_r, double kx, double ky, double *g_r,
+                          double *g6_r, int *num_bins)
+{
+	double k[2] = {kx, ky};
+	double t0 = shim_now();
+	bond_order_pcf_data *d = calculate_bond_order_pcf(particles, N, dr, max_r, k, Lx, Ly);
+	double t1 = shim_now();
+	*num_bins = d->num_bins;
+	for (int i = 0; i < d->num_bins; i++) {
+		if (g_r)
+			g_r[i] = d->g_r[i];
+		if (g6_r)
+			g6_r[i] = d->g6_r[i];
+	}
+	free_bond_order_pcf_data(d);
+	return t1 - t0;
+}
+
+/* find_max_structure_factor_bragg (src/pcf.c:405-467).  Returns seconds. */
+double ref_bragg_peak(double expected_bragg, double *k_out)
+{
+	double t0 = shim_now();
+	find_max_structure_factor_bragg(particles, N, Lx, Ly, expected_bragg, k_out);
+	return shim_now() - t0;
+}
+
 int ref_num_particles(void) { return N; }

@@ -72,4 +72,25 @@ rng = np.random.default_rng(4)
 g["vr"] = g["vr"] * (0.5 + rng.random(g["n"]))
 g["rad"] = g["rad"] * (0.7 + 0.3 * rng.random(g["n"]))
 sweep_case("sweep_n2000_grow", g, t=g["t"], grow=True)
+
+
+def weighted_case(name, cfg, dr, max_r):
+    """The weighted g(r) family: the Bragg-peak search and the
+    cos(k.r)-weighted pair correlation at that wave vector, from the reference."""
+    n = cfg["n"]
+    ref2 = ref
+    ref2.setup(n, cfg["lx"], cfg["ly"], 0.0, cfg["x"], cfg["y"], cfg["vx"], cfg["vy"], cfg["rad"])
+    phi = float(np.pi * (cfg["rad"] ** 2).sum() / (cfg["lx"] * cfg["ly"]))
+    expected = float(np.sqrt(8 * np.pi * phi / np.sqrt(3)))   # save_pcf_boop, src/pcf.c:341
+    k = ref2.bragg_peak(expected)["k"]
+    bo = ref2.bond_order_pcf(dr, max_r, k)
+    np.savez_compressed(HERE / f"{name}.npz", n=n, lx=cfg["lx"], ly=cfg["ly"], x=cfg["x"], y=cfg["y"],
+                        rad=cfg["rad"], expected_bragg=expected, k=k, dr=dr, max_r=max_r,
+                        g_r=bo["g_r"], g6_r=bo["g6_r"])
+    print("wrote", name, "n =", n, "k =", k)
+
+
+weighted_case("weighted_n1500_phi072", pkg.synth.lattice_config(1500, 0.72, seed=5), 2.0, 30.0)
+weighted_case("weighted_n1200_phi060_bidisperse",
+              pkg.synth.lattice_config(1200, 0.60, seed=6, small_fraction=0.3), 0.5, 20.0)
 ref.teardown()

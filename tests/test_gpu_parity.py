@@ -357,6 +357,52 @@ def test_pcf_counts_every_pair_once(pkg):
     assert p["counts"][: int(1.99 / 0.1)].sum() == 0
 
 
+# -------------------------------------------------- weighted g(r) family ----
+@pytest.mark.parametrize("name", ["weighted_n1500_phi072", "weighted_n1200_phi060_bidisperse"])
+def test_weighted_pcf_family_matches_reference_golden(pkg, name):
+    """Bragg-peak search + cos(k.r)-weighted g(r) against the reference's own
+    outputs (find_max_structure_factor_bragg, calculate_bond_order_pcf)."""
+    g = load_golden(name)
+    n = int(g["n"])
+    z = np.zeros(n)
+    with pkg.EdmdCuda(n, float(g["lx"]), float(g["ly"])) as ctx:
+        ctx.upload(g["x"], g["y"], z, z, g["rad"], t=0.0)
+        peak = ctx.bragg_peak(float(g["expected_bragg"]))
+        bo = ctx.pcf_bond_order(float(g["dr"]), float(g["max_r"]), g["k"])
+        plain = ctx.pcf(float(g["dr"]), float(g["max_r"]))
+    assert np.allclose(peak["k"], g["k"], rtol=0, atol=1e-12)
+    assert bo["num_bins"] == len(g["g_r"])
+    assert np.abs(bo["g_r"] - g["g_r"]).max() <= ANALYSIS_ATOL
+    assert np.abs(bo["g6_r"] - g["g6_r"]).max() <= ANALYSIS_ATOL
+    assert np.array_equal(bo["counts"], plain["counts"])
+
+
+@pytest.mark.parametrize("n,phi,seed,dr", [(20000, 0.72, 71, 2.0), (12000, 0.85, 72, 0.25)])
+def test_weighted_pcf_family_matches_oracle(pkg, oracle, n, phi, seed, dr):
+    c = pkg.synth.lattice_config(n, phi, seed)
+    n = c["n"]
+    max_r = min(c["lx"], c["ly"]) / 2
+    expected = float(np.sqrt(8 * np.pi * phi / np.sqrt(3)))
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        peak = ctx.bragg_peak(expected)
+        bo = ctx.pcf_bond_order(dr, max_r, peak["k"])
+    want_peak = oracle.bragg_peak(n, c["lx"], c["ly"], c["x"], c["y"], expected)
+    assert np.allclose(peak["k"], want_peak["k"], rtol=0, atol=1e-12)
+    assert abs(peak["s_max"] - want_peak["s_max"]) <= 1e-10 * want_peak["s_max"]
+    assert peak["s_max"] > 0.1 * n          # a (jittered) crystal: S at the Bragg peak is O(N)
+    want = oracle.bond_order_pcf(n, c["lx"], c["ly"], c["x"], c["y"], dr, max_r, peak["k"])
+    assert np.array_equal(bo["counts"], want["counts"])
+    assert np.abs(bo["g_r"] - want["g_r"]).max() <= ANALYSIS_ATOL
+    assert np.abs(bo["g6_r"] - want["g6_r"]).max() <= ANALYSIS_ATOL
+    # size-independent properties: k = 0 weights every pair by 1; the average is bounded
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        one = ctx.pcf_bond_order(dr, max_r, np.zeros(2))
+    assert np.array_equal(one["g6_r"][one["counts"] > 0], np.ones((one["counts"] > 0).sum()))
+    assert np.abs(bo["g6_r"]).max() <= 1.0
+
+
 # ------------------------------------------- tiled kernel vs generic kernel ----
 @pytest.mark.parametrize("n,phi,seed,sf", [(300000, 0.70, 21, 0.3), (300000, 0.85, 22, 0.0),
                                            (50000, 0.30, 23, 0.0)])

@@ -110,3 +110,24 @@ def test_oracle_empty_and_single(oracle):
                              np.array([0.5]), np.array([-0.25]), np.array([1.0]))
     assert one["partner"][0] == 0 and one["t_coll"][0] == 2.0 + 1e26
     assert one["dir"][0] == 2 and one["t_cross"][0] == 2.0 + (2.0 - 1.0) / 0.5
+
+
+WEIGHTED_CASES = ["weighted_n1500_phi072", "weighted_n1200_phi060_bidisperse"]
+
+
+@pytest.mark.parametrize("name", WEIGHTED_CASES)
+def test_oracle_weighted_pcf_family_matches_golden(oracle, name):
+    """Bragg-peak search and cos(k.r)-weighted g(r) (src/pcf.c:77-167, 405-467):
+    the restatement against the reference's own outputs."""
+    g = load_golden(name)
+    n, lx, ly = int(g["n"]), float(g["lx"]), float(g["ly"])
+    peak = oracle.bragg_peak(n, lx, ly, g["x"], g["y"], float(g["expected_bragg"]))
+    assert np.allclose(peak["k"], g["k"], rtol=0, atol=1e-12)
+    assert peak["s_max"] > 1.0
+    bo = oracle.bond_order_pcf(n, lx, ly, g["x"], g["y"], float(g["dr"]), float(g["max_r"]), g["k"])
+    assert bo["num_bins"] == len(g["g_r"])
+    assert np.abs(bo["g_r"] - g["g_r"]).max() <= ANALYSIS_ATOL
+    assert np.abs(bo["g6_r"] - g["g6_r"]).max() <= ANALYSIS_ATOL
+    # plain g(r) of the same snapshot: same counts
+    p = oracle.pcf(n, lx, ly, g["x"], g["y"], float(g["dr"]), float(g["max_r"]))
+    assert np.array_equal(p["counts"], bo["counts"])

@@ -23,9 +23,12 @@ BENCH_SWEEP, BENCH_FREEFLY, BENCH_BOOP, BENCH_PCF = 0, 1, 2, 3
 OPT_FORCE_GENERIC = 1
 OPT_NO_LEAN = 2
 OPT_NO_PDL = 3
+OPT_PCF_LEGACY = 4
 EPLAN = 6
 STAT_EXACT_RESCANS = 1
 STAT_LEAN_SWEEPS = 2
+STAT_PCF_EXACT_PAIRS = 3
+STAT_PCF_SKIPPED_TILE_PAIRS = 4
 
 # every symbol include/edmd_cuda.h declares
 SYMBOLS = [

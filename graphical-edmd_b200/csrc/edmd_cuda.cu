@@ -303,7 +303,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
                    c->lrec, c->lchunks, c->lres, c->lwork, c->cal_mem,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
-                   c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->boop, c->boop_nb,
+                   c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
     for (void *p : dev)
         if (p) cudaFree(p);
@@ -340,6 +340,10 @@ int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
         c->lean_off = value != 0;
         return 0;
     }
+    if (option == EDMD_OPT_PCF_LEGACY) {
+        c->pcf_legacy = value != 0;
+        return 0;
+    }
     if (option == EDMD_OPT_NO_PDL) {
         c->lean_pdl = value == 0;
         return 0;
@@ -350,6 +354,16 @@ int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
 int edmd_cuda_get_stat(edmd_ctx *c, int stat, uint64_t *value)
 {
     if (!c || !value) return EDMD_EINVAL;
+    if (stat == EDMD_STAT_PCF_EXACT_PAIRS || stat == EDMD_STAT_PCF_SKIPPED_TILE_PAIRS) {
+        unsigned long long v[2] = {0, 0};
+        if (c->pcfs_stats) {
+            CU(cudaSetDevice(c->device));
+            CU(cudaMemcpyAsync(v, c->pcfs_stats, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        *value = v[stat == EDMD_STAT_PCF_EXACT_PAIRS ? 0 : 1];
+        return 0;
+    }
     if (stat == EDMD_STAT_LEAN_SWEEPS) {
         *value = c->lean_sweeps;
         return 0;

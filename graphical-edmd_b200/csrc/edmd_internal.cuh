@@ -214,6 +214,10 @@ struct edmd_ctx {
 
     // analysis scratch
     unsigned long long *pcf_counts;   // capacity pcf_cap bins
+    char *pcfs_mem;                   // sorted-tile g(r) scratch (analysis_pcf_sorted.cu)
+    size_t pcfs_bytes;
+    unsigned long long *pcfs_stats;   // [0] pairs binned by the exact path, [1] tile pairs skipped
+    bool pcf_legacy;                  // EDMD_OPT_PCF_LEGACY
     unsigned long long *pcf_wsum;     // weighted sums (2^-32 fixed point), capacity pcf_wcap bins
     int pcf_wcap;
     int pcf_cap;
@@ -276,6 +280,8 @@ int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bin
                                unsigned long long *counts, unsigned long long *wsum);
 int edmd_launch_bragg(edmd_ctx *c, int nk, const double2 *kvec, double *re, double *im, double *best_s,
                       int *best_i);
+int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
+                           int n, unsigned long long *counts);
 int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
                     int n, int part, int nparts, unsigned long long *counts);
 

@@ -89,6 +89,10 @@ uint64_t edmd_cuda_launch_count(const edmd_ctx *ctx);
 /* EDMD_OPT_NO_PDL = 1 launches the lean sweep's kernel chain without programmatic
  * dependent launch (plain stream order); for timing comparisons. */
 #define EDMD_OPT_NO_PDL 3
+/* EDMD_OPT_PCF_LEGACY = 1 makes edmd_cuda_pcf use the plain tile kernel (IEEE sqrt and
+ * division per pair, id-ordered tiles) instead of the sorted-tile kernel with certified
+ * bins; same counts, for cross-checking and timing. */
+#define EDMD_OPT_PCF_LEGACY 4
 int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 /* Counters: EDMD_STAT_EXACT_RESCANS = particles the tiled sweep had to resolve
  * with the exact re-scan (near-ties, ill-conditioned pairs) since create. */
@@ -96,6 +100,10 @@ int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 /* EDMD_STAT_LEAN_SWEEPS = sweeps that completed on the lean path (counted when
  * their results are fetched or planned from; declined ones are not). */
 #define EDMD_STAT_LEAN_SWEEPS 2
+/* g(r), sorted-tile kernel, since create: pairs whose bin needed the exact sqrt + division;
+ * tile pairs skipped because every pair in them is beyond max_r. */
+#define EDMD_STAT_PCF_EXACT_PAIRS 3
+#define EDMD_STAT_PCF_SKIPPED_TILE_PAIRS 4
 int edmd_cuda_get_stat(edmd_ctx *ctx, int stat, uint64_t *value);
 
 /* Page-locked host memory for the caller's particle arrays: uploads and

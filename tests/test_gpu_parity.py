@@ -344,6 +344,25 @@ def test_pcf_counts_match_oracle(pkg, oracle, n, phi, seed, dr, frac):
     assert np.abs(p["g_r"] - want["g_r"]).max() <= ANALYSIS_ATOL
 
 
+@pytest.mark.parametrize("n,phi,seed,dr,frac", [(120000, 0.70, 81, 0.1, 0.5), (60000, 0.85, 82, 0.013, 0.3),
+                                                (100000, 0.30, 83, 2.0, 0.75)])
+def test_pcf_sorted_tiles_equal_plain_kernel(pkg, n, phi, seed, dr, frac):
+    """Large systems take the sorted-tile kernel (bins certified in FP64 from an
+    FP32 estimate, periodic image and far tile pairs decided per tile pair); the
+    plain kernel (IEEE sqrt + division per pair) must count the same integers."""
+    c = pkg.synth.lattice_config(n, phi, seed)
+    max_r = min(c["lx"], c["ly"]) * frac
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        a = ctx.pcf(dr, max_r)
+        exact = ctx.stat(pkg.binding.STAT_PCF_EXACT_PAIRS)
+        ctx.set_option(pkg.binding.OPT_PCF_LEGACY, 1)
+        b = ctx.pcf(dr, max_r)
+    assert np.array_equal(a["counts"], b["counts"])
+    npairs = c["n"] * (c["n"] - 1) // 2
+    assert exact < 0.02 * npairs, (exact, npairs)      # the certificate settles almost every pair
+
+
 def test_pcf_counts_every_pair_once(pkg):
     """Checksum at full size: with max_r beyond the half-diagonal every one of
     the N(N-1)/2 pairs lands in exactly one bin."""

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(kThreads)
 k_pack(int n, size_t N, edmd_dev_box b, int ps, const double *__restrict__ soa,
        const int32_t *__restrict__ cell_xy, double4 *__restrict__ xv,
        double *__restrict__ rad, int32_t *__restrict__ cid,
-       int32_t *__restrict__ flags, double rad0, int keep_rad)
+       int32_t *__restrict__ flags, double rad0, int keep_rad,
+       int32_t *__restrict__ halo_list, int32_t *__restrict__ halo_cnt, int halo_cap, int first)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int ghosts = 0, insane = 0, notmono = 0;
@@ -72,6 +73,17 @@ k_pack(int n, size_t N, edmd_dev_box b, int ps, const double *__restrict__ soa,
         }
         cid[i] = l * ps + X + 1;
         ghosts = (X == 0) + (X == b.nx - 1);
+        // slab contexts with peer-to-peer halo: list the particles of the two boundary
+        // rows now, so that every exchange until the next upload can skip that pass
+        if (halo_list && (l == 1 || l == b.nl - 2)) {
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                if (l != (side == 0 ? 1 : b.nl - 2)) continue;
+                const int k = atomicAdd(halo_cnt + side, 1);
+                if (k < halo_cap) halo_list[side * halo_cap + k] = first + i;
+                else atomicOr(&flags[kFlagBadCell], 2);
+            }
+        }
     }
     ghosts = __reduce_add_sync(0xffffffffu, ghosts);
     insane = __reduce_add_sync(0xffffffffu, insane);
@@ -348,7 +360,8 @@ int edmd_launch_pack(edmd_ctx *c, bool have_cells, int first, int count, bool ke
     if (count == 0) return 0;
     k_pack<<<(count + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(
         count, (size_t)c->n_cap, c->dbox, c->ps, c->in_soa, have_cells ? c->in_cell : nullptr,
-        c->xv + first, c->rad + first, c->cid + first, c->flags, c->rad0, keep_rad ? 1 : 0);
+        c->xv + first, c->rad + first, c->cid + first, c->flags, c->rad0, keep_rad ? 1 : 0,
+        c->halo_list_at_pack ? c->halo_list : nullptr, c->halo_cnt, c->halo_cap, first);
     return 1;
 }
 

@@ -311,6 +311,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
         if (c->peer_opened[k] && c->peer_mem[k]) cudaIpcCloseMemHandle(c->peer_mem[k]);
     if (c->halo_mem) cudaFree(c->halo_mem);
     if (c->halo_cnt) cudaFree(c->halo_cnt);
+    if (c->halo_list) cudaFree(c->halo_list);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (int k = 0; k < 4; k++)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
@@ -414,7 +415,10 @@ static int upload_impl(edmd_ctx *c, int n, const double *x, const double *y, con
     c->n = n;
     c->n_owned = n;
     c->nghost_extra = 0;
+    c->halo_list_at_pack = c->slab && c->halo_list != nullptr;
+    if (c->halo_list_at_pack) CU(cudaMemsetAsync(c->halo_cnt, 0, 2 * sizeof(int32_t), c->stream));
     c->launches += edmd_launch_pack(c, cell_xy != nullptr, 0, n, keep_rad);
+    c->halo_list_valid = c->halo_list_at_pack;
     CU(cudaGetLastError());
     c->t = t;
     c->have_pred = false;
@@ -494,6 +498,7 @@ int edmd_cuda_halo_export(edmd_ctx *c, int halo_capacity, void *handle64)
         CU(cudaMemset(c->halo_mem, 0, bytes));
         CU(cudaMalloc((void **)&c->halo_cnt, 8 * sizeof(int32_t)));
         CU(cudaMemset(c->halo_cnt, 0, 8 * sizeof(int32_t)));
+        CU(cudaMalloc((void **)&c->halo_list, 2 * (size_t)halo_capacity * sizeof(int32_t)));
         c->halo_epoch = 0;
     }
     cudaIpcMemHandle_t h;

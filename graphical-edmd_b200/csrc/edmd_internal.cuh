@@ -178,7 +178,10 @@ struct edmd_ctx {
     char *halo_mem;      // my inboxes + acks (exported through CUDA IPC)
     char *peer_mem[2];   // lower / upper neighbour's halo_mem (IPC mapped, or my own)
     bool peer_opened[2];
-    int32_t *halo_cnt;   // [4] device counters: records packed per side, finished blocks per side
+    int32_t *halo_cnt;   // [8] device counters: records listed per side, finished blocks
+    bool halo_list_at_pack;   // the next pack kernel fills halo_list (peer-to-peer halo configured)
+    bool halo_list_valid;     // halo_list matches the resident cell ids (filled by the last upload)
+    int32_t *halo_list;  // [2][halo_cap] indices of the owned particles in the two boundary rows
     int nghost_extra;    // upper bound of ghost entries contributed by halo particles
 
     // cell index

@@ -10,9 +10,10 @@
 //         { int count; int epoch; int pad[2]; HaloRec rec[H]; }
 //     ack[2]                ack[0] written by my lower neighbour, ack[1] by my upper
 //                           one: "I have consumed your exchange number e"
-// k_halo_send packs a boundary row of the owned particles and writes the
-// 48-byte records STRAIGHT INTO THE NEIGHBOUR'S inbox (peer stores over
-// NVLink); the last block publishes count, then epoch, behind system fences.
+// k_halo_collect lists the owned particles of the two boundary rows; k_halo_send
+// writes their 48-byte records STRAIGHT INTO THE NEIGHBOURS' inboxes (peer
+// stores over NVLink); its last block publishes count, then epoch, behind
+// system fences.
 // k_halo_recv waits for the epoch, unpacks the records into the fixed halo
 // region [n_owned + from*H, n_owned + (from+1)*H) of the resident arrays (unused
 // slots get cell id -1 and are skipped by the cell index), and acks.  A sender
@@ -49,68 +50,96 @@ __device__ __forceinline__ int ld_volatile(const int *p)
     return *reinterpret_cast<const volatile int *>(p);
 }
 
-// One pass over the owned particles serves both boundary rows:
-// side 0: first owned row -> lower neighbour's inbox[from=1];
-// side 1: last owned row  -> upper neighbour's inbox[from=0].
-struct SendArgs {
-    int n_owned, ps, row[2], H, epoch;
+// Sending is two steps.  The indices of the owned particles in the two boundary
+// rows are listed once per upload (by the pack kernel, or by k_halo_collect if the
+// inboxes were exported after the upload; device-scope atomics only).  k_halo_send, a few blocks, builds their records and writes them
+// straight into the neighbours' inboxes; only these few threads pay for
+// system-scope fences.  (One kernel doing both cost 55 us at 10^6 owned
+// particles -- a system fence in each of its 3900 blocks -- against 9 us.)
+//   side 0: first owned row -> lower neighbour's inbox[from=1];
+//   side 1: last owned row  -> upper neighbour's inbox[from=0].
+struct CollectArgs {
+    int n_owned, ps, row[2], H;
     const int32_t *cid;
-    const double4 *xv;
-    const double *rad;
-    const int32_t *gid;
-    char *peer_inbox[2];
-    const int *ack;     // [2]
-    int32_t *cnt;       // [2] records packed per side
-    int32_t *done;      // finished blocks
+    int32_t *list;      // [2][H] particle indices per side
+    int32_t *cnt;       // [2]
     int32_t *flags;
 };
 
 __global__ void __launch_bounds__(kThreads)
+k_halo_collect(const __grid_constant__ CollectArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_owned) return;
+    const int l = a.cid[i] / a.ps;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        if (l != a.row[side]) continue;
+        const int k = atomicAdd(a.cnt + side, 1);
+        if (k < a.H) a.list[side * a.H + k] = i;
+        else atomicOr(&a.flags[kFlagBadCell], 2);   // halo buffer too small
+    }
+}
+
+struct SendArgs {
+    int ps, H, epoch;
+    const int32_t *cid;
+    const double4 *xv;
+    const double *rad;
+    const int32_t *gid;
+    const int32_t *list;
+    char *peer_inbox[2];
+    const int *ack;     // [2]
+    int32_t *cnt;       // [2] records listed per side
+    int32_t *done;      // finished blocks
+};
+
+// blockIdx.y = side
+__global__ void __launch_bounds__(kThreads)
 k_halo_send(const __grid_constant__ SendArgs a)
 {
     __shared__ bool last;
-    // do not overwrite a buffer a neighbour may still be reading
-    if (threadIdx.x < 2)
-        while (ld_volatile(a.ack + threadIdx.x) < a.epoch - 2) __nanosleep(50);
+    const int side = blockIdx.y;
+    // do not overwrite a buffer the neighbour may still be reading
+    if (threadIdx.x == 0)
+        while (ld_volatile(a.ack + side) < a.epoch - 2) __nanosleep(50);
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n_owned) {
+    const int total = min(a.cnt[side], a.H);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < total) {
+        const int i = a.list[side * a.H + k];
         const int pc = a.cid[i];
-        const int l = pc / a.ps;
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            if (l != a.row[side]) continue;
-            HaloRec *rec = reinterpret_cast<HaloRec *>(a.peer_inbox[side] + sizeof(InboxHeader));
-            const int k = atomicAdd(a.cnt + side, 1);
-            if (k < a.H) {
-                const double4 p = a.xv[i];
-                HaloRec r;
-                r.x = p.x; r.y = p.y; r.vx = p.z; r.vy = p.w;
-                r.rad = a.rad[i];
-                r.gid = a.gid[i];
-                r.cell = pc - l * a.ps;
-                const uint4 *src = reinterpret_cast<const uint4 *>(&r);
-                uint4 *dst = reinterpret_cast<uint4 *>(rec + k);   // peer store over NVLink
-                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
-            } else
-                atomicOr(&a.flags[kFlagBadCell], 2);   // halo buffer too small
-        }
+        const double4 p = a.xv[i];
+        HaloRec r;
+        r.x = p.x; r.y = p.y; r.vx = p.z; r.vy = p.w;
+        r.rad = a.rad[i];
+        r.gid = a.gid[i];
+        r.cell = pc - (pc / a.ps) * a.ps;
+        HaloRec *rec = reinterpret_cast<HaloRec *>(a.peer_inbox[side] + sizeof(InboxHeader));
+        const uint4 *src = reinterpret_cast<const uint4 *>(&r);
+        uint4 *dst = reinterpret_cast<uint4 *>(rec + k);   // peer store over NVLink
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
     }
-    __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(a.done, 1) == (int)gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        // one system-scope fence per block: it is cumulative over the stores the barrier
+        // ordered before it, so they are visible to the neighbour before `done` counts
+        // this block (and hence before count / epoch are published)
+        __threadfence_system();
+        last = atomicAdd(a.done, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    }
     __syncthreads();
     if (last && threadIdx.x < 2) {
-        const int side = threadIdx.x;
-        InboxHeader *hdr = reinterpret_cast<InboxHeader *>(a.peer_inbox[side]);
-        const int total = min(ld_volatile(a.cnt + side), a.H);
-        *reinterpret_cast<volatile int *>(&hdr->count) = total;
+        const int sd = threadIdx.x;
+        InboxHeader *hdr = reinterpret_cast<InboxHeader *>(a.peer_inbox[sd]);
+        const int tot = min(ld_volatile(a.cnt + sd), a.H);
+        *reinterpret_cast<volatile int *>(&hdr->count) = tot;
         __threadfence_system();
         *reinterpret_cast<volatile int *>(&hdr->epoch) = a.epoch;
         __threadfence_system();
-        a.cnt[side] = 0;
-        if (side == 0) *a.done = 0;
     }
+    __syncthreads();
+    if (last && threadIdx.x == 0) *a.done = 0;   // cnt / list stay valid until the next upload
 }
 
 struct RecvArgs {
@@ -184,17 +213,25 @@ int edmd_launch_halo_p2p(edmd_ctx *c)
     const int n = c->n_owned;
     const int nl = c->dbox.nl;
     int32_t *cnt = c->halo_cnt;
+    CollectArgs ca;
+    ca.n_owned = n; ca.ps = c->ps; ca.H = H;
+    ca.row[0] = 1;          // my first owned row -> LOWER neighbour, where I am its upper one (from = 1)
+    ca.row[1] = nl - 2;     // my last owned row  -> UPPER neighbour, where I am its lower one (from = 0)
+    ca.cid = c->cid; ca.list = c->halo_list; ca.cnt = cnt; ca.flags = c->flags;
+    const bool collect = n > 0 && !c->halo_list_valid;   // else the upload's pack kernel listed them
+    if (collect) {
+        cudaMemsetAsync(cnt, 0, 2 * sizeof(int32_t), c->stream);
+        k_halo_collect<<<(n + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(ca);
+        c->halo_list_valid = true;
+    }
     SendArgs sa;
-    sa.n_owned = n; sa.ps = c->ps; sa.H = H; sa.epoch = e;
-    sa.row[0] = 1;          // my first owned row -> LOWER neighbour, where I am its upper one (from = 1)
-    sa.row[1] = nl - 2;     // my last owned row  -> UPPER neighbour, where I am its lower one (from = 0)
-    sa.cid = c->cid; sa.xv = c->xv; sa.rad = c->rad; sa.gid = c->gid;
+    sa.ps = c->ps; sa.H = H; sa.epoch = e;
+    sa.cid = c->cid; sa.xv = c->xv; sa.rad = c->rad; sa.gid = c->gid; sa.list = c->halo_list;
     sa.peer_inbox[0] = c->peer_mem[0] + inbox_offset(H, 1, par);
     sa.peer_inbox[1] = c->peer_mem[1] + inbox_offset(H, 0, par);
     sa.ack = reinterpret_cast<const int *>(c->halo_mem + ack_offset(H));
-    sa.cnt = cnt; sa.done = cnt + 2; sa.flags = c->flags;
-    const int sblocks = n > 0 ? (n + kThreads - 1) / kThreads : 1;
-    k_halo_send<<<sblocks, kThreads, 0, c->stream>>>(sa);
+    sa.cnt = cnt; sa.done = cnt + 2;
+    k_halo_send<<<dim3((H + kThreads - 1) / kThreads, 2), kThreads, 0, c->stream>>>(sa);
     RecvArgs ra;
     ra.H = H; ra.first = n; ra.ps = c->ps; ra.epoch = e;
     ra.row[0] = 0; ra.row[1] = nl - 1;
@@ -209,5 +246,5 @@ int edmd_launch_halo_p2p(edmd_ctx *c)
     ra.rad0 = c->rad0;
     dim3 rgrid((H + kThreads - 1) / kThreads, 2);
     k_halo_recv<<<rgrid, kThreads, 0, c->stream>>>(ra);
-    return 2;
+    return collect ? 3 : 2;
 }

@@ -170,6 +170,49 @@ __device__ __forceinline__ void bin_add(const PcfArgs &a, uint32_t hist_addr, in
     else atomicAdd(&a.counts[bin], 1ull);
 }
 
+// predicated shared-memory increment: no branch in the instruction stream
+__device__ __forceinline__ void bin_add_if(uint32_t hist_addr, int bin, bool p)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.s32 q, %2, 0;\n@q red.shared.add.u32 [%0], %1;\n}" ::"r"(
+                     hist_addr + 4u * (uint32_t)bin),
+                 "r"(1u), "r"((int)p)
+                 : "memory");
+}
+
+// One pair: s exactly as the reference, the range test, the FP32 bin estimate and its
+// FP64 certificate.  Returns the estimate k; `take` = in range, certified and a real
+// bin; `redo` = in range but not certified.
+template <bool WX, bool WY>
+__device__ __forceinline__ int pair_bin(const PcfArgs &a, const double2 pi, const double2 pj, double s_max,
+                                        double dr_lo, double dr_hi, float inv_dr, int num_bins, double &s,
+                                        bool &take, bool &redo)
+{
+    double dx = __dsub_rn(pj.x, pi.x);
+    double dy = __dsub_rn(pj.y, pi.y);
+    if (WX) dx = min_image(dx, a.b.half_lx, a.b.lx);
+    if (WY) dy = min_image(dy, a.b.half_ly, a.b.ly);
+    s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    // FP32 estimate of r / dr from the bits of s (truncated to float).  For s outside
+    // the float range the estimate is garbage and the certificate rejects it (or k = 0
+    // is right anyway).
+    const float sf = __int_as_float(((__double2hiint(s) - 0x38000000) << 3) |
+                                    (int)((unsigned)__double2loint(s) >> 29));
+    float rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(sf));
+    const int k = __float2int_rz(sf * rs * inv_dr);
+    // certificate in FP64: (k dr)^2 (1 + 2^-48) <= s < ((k+1) dr)^2 (1 - 2^-48)
+    const double kd = __dsub_rn(__hiloint2double(0x43300000, k), 4503599627370496.0);
+    const double e0 = __dmul_rn(kd, dr_lo);
+    const double e1 = __dmul_rn(__dadd_rn(kd, 1.0), dr_hi);
+    const bool in_range = s < s_max;   // r < max_r
+    const bool ok = (s >= __dmul_rn(e0, e0)) && (s < __dmul_rn(e1, e1));
+    take = in_range && ok && k < num_bins;
+    redo = in_range && !ok;
+    return k;
+}
+
+// Four pairs per trip, branch-free (their dependency chains interleave); the rare
+// uncertified pair is redone with the reference's sqrt and division after the batch.
 template <bool WX, bool WY>
 __device__ __forceinline__ void pair_loop(const PcfArgs &a, const double2 pi, uint32_t tile_addr, int jstart,
                                           int jcount, uint32_t hist_addr, unsigned int &slow)
@@ -178,35 +221,36 @@ __device__ __forceinline__ void pair_loop(const PcfArgs &a, const double2 pi, ui
     const float inv_dr = a.inv_dr;
     const int num_bins = a.num_bins;
     uint32_t addr = tile_addr + 16u * (uint32_t)jstart;
-#pragma unroll 4
-    for (int jj = jstart; jj < jcount; jj++, addr += 16u) {
-        const double2 pj = lds_double2(addr);
-        double dx = __dsub_rn(pj.x, pi.x);
-        double dy = __dsub_rn(pj.y, pi.y);
-        if (WX) dx = min_image(dx, a.b.half_lx, a.b.lx);
-        if (WY) dy = min_image(dy, a.b.half_ly, a.b.ly);
-        const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        // FP32 estimate of r / dr from the bits of s (truncated to float).  For s outside
-        // the float range the estimate is garbage and the certificate below rejects it
-        // (or k = 0 is right anyway).
-        const float sf = __int_as_float(((__double2hiint(s) - 0x38000000) << 3) |
-                                        (int)((unsigned)__double2loint(s) >> 29));
-        float rs;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(sf));
-        const int k = __float2int_rz(sf * rs * inv_dr);
-        // certificate in FP64: (k dr)^2 (1 + 2^-48) <= s < ((k+1) dr)^2 (1 - 2^-48)
-        const double kd = __dsub_rn(__hiloint2double(0x43300000, k), 4503599627370496.0);
-        const double e0 = __dmul_rn(kd, dr_lo);
-        const double e1 = __dmul_rn(__dadd_rn(kd, 1.0), dr_hi);
-        const bool in_range = s < s_max;   // r < max_r
-        const bool ok = (s >= __dmul_rn(e0, e0)) && (s < __dmul_rn(e1, e1));
-        if (in_range && ok) {
-            if (k < num_bins) bin_add(a, hist_addr, k);
-        } else if (in_range) {   // the reference's own arithmetic
-            const int bin = (int)__ddiv_rn(__dsqrt_rn(s), a.dr);
-            slow++;
-            if (bin < num_bins) bin_add(a, hist_addr, bin);
+    auto exact = [&](double s) {   // the reference's own arithmetic
+        const int bin = (int)__ddiv_rn(__dsqrt_rn(s), a.dr);
+        slow++;
+        if (bin < num_bins) bin_add(a, hist_addr, bin);
+    };
+    int jj = jstart;
+    if (hist_addr) {
+        for (; jj + 4 <= jcount; jj += 4, addr += 64u) {
+            double s[4];
+            int k[4];
+            bool take[4], redo[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                k[u] = pair_bin<WX, WY>(a, pi, lds_double2(addr + 16u * u), s_max, dr_lo, dr_hi, inv_dr, num_bins,
+                                        s[u], take[u], redo[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) bin_add_if(hist_addr, take[u] ? k[u] : 0, take[u]);
+            if (redo[0] | redo[1] | redo[2] | redo[3]) {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (redo[u]) exact(s[u]);
+            }
         }
+    }
+    for (; jj < jcount; jj++, addr += 16u) {
+        double s;
+        bool take, redo;
+        const int k = pair_bin<WX, WY>(a, pi, lds_double2(addr), s_max, dr_lo, dr_hi, inv_dr, num_bins, s, take, redo);
+        if (take) bin_add(a, hist_addr, k);
+        else if (redo) exact(s);
     }
 }
 

@@ -657,6 +657,9 @@ static int lean_fallback(edmd_ctx *c)
     }
     c->lean_pending = false;
     c->lean_ok = false;
+    // a system that keeps declining (e.g. rows denser than the lean layout provides for)
+    // stops trying: the attempt costs two kernel launches every sweep
+    if (++c->lean_declines >= 2) c->lean_off = true;
     CU(cudaMemsetAsync(c->flags + kFlagLeanFail, 0, sizeof(int32_t), c->stream));
     CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));
     c->launches += sweep_launch(c, c->pred_mode);
@@ -761,6 +764,7 @@ int edmd_cuda_free_fly(edmd_ctx *c, int mode, double t_new)
     double dt = t_new - c->t;  // `double dt = t - p->t;` src/EDMD.c:4955
     c->launches += edmd_launch_free_fly(c, mode, dt);
     CU(cudaGetLastError());
+    if (mode == EDMD_MODE_GROW) c->lean_ok = false;   // radii changed on the device: no longer known to be equal
     c->t = t_new;
     c->have_pred = false;
     c->have_index = false;

@@ -154,6 +154,7 @@ struct edmd_ctx {
     int pred_mode;       // mode of the last sweep
     bool lean_pending;   // the last sweep was launched on the lean path and not yet confirmed
     uint64_t lean_sweeps; // sweeps confirmed on the lean path
+    int lean_declines;   // sweeps the device declined
     bool have_vr;
     double t;            // time of the resident snapshot
     int nghost;          // ghost entries of the current upload

@@ -540,6 +540,26 @@ def test_lean_handles_heavy_velocity_tails_and_rest(pkg, oracle):
     assert_events_equal(got, want)
 
 
+def test_normal_sweep_after_growth_free_flight(pkg, oracle):
+    """Growth free flight changes the radii on the device (rad += dt vr); a NORMAL
+    sweep afterwards must use them (and must not assume they are still equal)."""
+    c = pkg.synth.lattice_config(30000, 0.55, seed=48)
+    rng = np.random.default_rng(48)
+    vr = 0.02 * rng.random(c["n"])
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        ctx.set_growth(vr)
+        ctx.free_fly(0.125, mode=1)
+        s = ctx.download_state()
+        cells = oracle.cells(c["n"], c["lx"], c["ly"], c["x"], c["y"]).reshape(c["n"], 2)
+        got = ctx.predict_all(allow_overlap=True)
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 0
+    assert not np.array_equal(s["rad"], c["rad"])
+    c2 = dict(c, x=s["x"], y=s["y"], rad=s["rad"])
+    want = oracle_sweep(oracle, c2, t=0.125, cells=cells)
+    assert_events_equal(got, want)
+
+
 def test_lean_declines_after_free_flight_out_of_the_cells(pkg, oracle):
     """Free flight moves particles but not their (host-owned) cells; once some
     particle is more than a cell away from where it is filed the lean sweep

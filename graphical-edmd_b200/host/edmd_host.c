@@ -364,17 +364,20 @@ static int ingest_from_plan(void)
 	memset(paul, 0, sizeof(node *) * (size_t)(paulN + 1));
 	root->lft = root->rgt = NULL;
 	treeMin = NULL;
+	int32_t n_tree = 0;
 	int rc = edmd_cuda_calendar_plan(gpu, paulTime, dtPaul, paulN, actualPaul, g_bucket, g_next, g_prev,
-	                                 g_head, NULL);
+	                                 g_head, &n_tree);
 	if (rc && rc != EDMD_EPLAN) die_gpu(rc, "edmd_cuda_calendar_plan");
 	if (rc == 0) {
+		/* streaming passes over independent nodes: split over the host cores */
+#pragma omp parallel for schedule(static)
 		for (int k = 0; k <= paulN; k++) paul[k] = g_head[k] >= 0 ? &events[g_head[k]] : NULL;
+#pragma omp parallel for schedule(static)
 		for (int i = 0; i < N; i++) {
 			node *ev = &events[i];
 			ev->j = g_dir[i]; ev->type = EV_CELLCROSS; ev->t = g_tcross[i];
 			int b = g_bucket[i];
-			if (b < 0) { ev->q = actualPaul; tree_add(ev); }
-			else {
+			if (b >= 0) {
 				ev->q = b;
 				ev->lft = g_prev[i] >= 0 ? &events[g_prev[i]] : NULL;
 				ev->rgt = g_next[i] >= 0 ? &events[g_next[i]] : NULL;
@@ -383,13 +386,18 @@ static int ingest_from_plan(void)
 			ev->j = g_partner[i]; ev->type = EV_COLLISION; ev->t = g_tcoll[i];
 			ev->collActual = pcoll[g_partner[i]];
 			b = g_bucket[N + i];
-			if (b < 0) { ev->q = actualPaul; tree_add(ev); }
-			else {
+			if (b >= 0) {
 				ev->q = b;
 				ev->lft = g_prev[N + i] >= 0 ? &events[g_prev[N + i]] : NULL;
 				ev->rgt = g_next[N + i] >= 0 ? &events[g_next[N + i]] : NULL;
 			}
 		}
+		/* the few events of the current bucket go into the BST, in the reference's order */
+		if (n_tree > 0)
+			for (int i = 0; i < N; i++) {
+				if (g_bucket[i] < 0) { events[i].q = actualPaul; tree_add(&events[i]); }
+				if (g_bucket[N + i] < 0) { events[N + i].q = actualPaul; tree_add(&events[N + i]); }
+			}
 	}
 	/* the special events (a handful) go back in the ordinary way */
 	for (int s = 0; s < NSPECIAL; s++)

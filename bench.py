@@ -126,6 +126,52 @@ def cpu_baseline(cfg, repeats=3):
             "seconds_per_sweep": min(secs)}
 
 
+def end_to_end_coll_rate(t_end=150.0):
+    """Third part of BASELINE.json's metric: end-to-end collisions per second of the
+    whole program on configs[0] (`-N 2000 --phi 0.7`, the reference CLI defaults:
+    30 % small disks, growth start).  Ours = graphical-edmd_b200/host/edmd_host
+    (sequential C host + the CUDA library for the whole-system sweeps); reference =
+    the unmodified reference's own main(), called through oracle/_ref.  Both are
+    sequential event loops on one host core; a bounded run of `t_end` time units."""
+    import re
+    import tempfile
+    out = {"config": f"-N 2000 --phi 0.7 -t {t_end:g} (reference CLI defaults, BASELINE configs[0])"}
+    host = ROOT / "graphical-edmd_b200" / "host" / "edmd_host"
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            r = subprocess.run([str(host), "-N", "2000", "--phi", "0.7", "-t", str(t_end), "-D", "1000",
+                                "-o", "1000", "--quiet", "--outdir", d], capture_output=True, text=True,
+                               timeout=300)
+            m = re.search(r"(\d+) collisions, \d+ crossings in ([\d.]+) s => ([\d.e+]+) coll/s", r.stdout)
+            if m:
+                out["ours"] = {"collisions": int(m.group(1)), "seconds": float(m.group(2)),
+                               "coll_per_s": float(m.group(3)), "cores": 1}
+    except Exception as e:   # the host program is optional for the headline number
+        out["ours_error"] = str(e)[:200]
+    ref_so = ROOT / "oracle" / "_ref" / "libedmd_ref.so"
+    if ref_so.exists():
+        code = ("import ctypes as C, sys, time\n"
+                f"lib = C.CDLL({str(ref_so)!r})\n"
+                "a = [b'a.out', b'-N', b'2000', b'--phi', b'0.7', b'-t', sys.argv[1].encode()]\n"
+                "argv = (C.c_char_p * (len(a) + 1))(*a, None)\n"
+                "t0 = time.time(); lib.edmd_reference_main(len(a), argv)\n"
+                "sys.stdout.flush(); print('\\nWALL', time.time() - t0)\n")
+        try:
+            with tempfile.TemporaryDirectory() as d:
+                os.makedirs(os.path.join(d, "dump"), exist_ok=True)
+                r = subprocess.run([sys.executable, "-c", code, str(t_end)], cwd=d, capture_output=True,
+                                   text=True, timeout=300)
+                ncoll = re.findall(r"coll = (?:\x1b\[[\d;]*m)?([\d.e+]+)", r.stdout)
+                wall = re.search(r"WALL ([\d.]+)", r.stdout)
+                if ncoll and wall:
+                    out["reference"] = {"collisions": float(ncoll[-1]), "seconds": float(wall.group(1)),
+                                        "coll_per_s": float(ncoll[-1]) / float(wall.group(1)), "cores": 1,
+                                        "note": "whole run incl. its growth phase and console output"}
+        except Exception as e:
+            out["reference_error"] = str(e)[:200]
+    return out
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -406,6 +452,8 @@ def run_ours(args, cfg):
             line["config"]["parallelism"] = f"{world} independent replicas (slab path: see DESIGN.md)"
         if cpu:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_cpu:
+            line["end_to_end"] = end_to_end_coll_rate()
         print(json.dumps(line, default=float))
     ctx.close()
     if world > 1:

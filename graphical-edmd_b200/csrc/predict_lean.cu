@@ -424,7 +424,9 @@ __device__ __forceinline__ void exact_scan_lean(const ResolveArgs &a, const SRec
     }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kResolveThreads = 128;
+
+__global__ void __launch_bounds__(kResolveThreads)
 k_resolve(const __grid_constant__ ResolveArgs a)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -542,7 +544,8 @@ int edmd_launch_predict_lean(edmd_ctx *c)
         ra.t_cross = c->t_cross; ra.dir = c->dir; ra.t_coll = c->t_coll; ra.partner = c->partner;
         ra.ctype = c->ctype;
         ra.overlap_key = c->overlap_key;
-        edmd_launch(k_resolve, dim3((c->n_owned + 255) / 256), dim3(256), 0, c->stream, c->lean_pdl, ra);
+        edmd_launch(k_resolve, dim3((c->n_owned + kResolveThreads - 1) / kResolveThreads), dim3(kResolveThreads), 0,
+                    c->stream, c->lean_pdl, ra);
         launched++;
     }
     return launched;

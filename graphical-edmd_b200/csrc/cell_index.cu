@@ -34,7 +34,7 @@ k_pack(int n, size_t N, edmd_dev_box b, int ps, const double *__restrict__ soa,
        int32_t *__restrict__ halo_list, int32_t *__restrict__ halo_cnt, int halo_cap, int first)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int ghosts = 0, insane = 0, notmono = 0;
+    int ghosts = 0, insane = 0;
     float vm = 0.0f;
     if (i < n) {
         double x = soa[i], y = soa[N + i];
@@ -43,7 +43,7 @@ k_pack(int n, size_t N, edmd_dev_box b, int ps, const double *__restrict__ soa,
         xv[i] = make_double4(x, y, vx, vy);
         if (!keep_rad) rad[i] = r;
         // what the lean sweep needs to know (lean.cuh): one common radius, the speed scale
-        notmono = !(r == rad0);
+        edmd_note_radius(flags, r, rad0);
         vm = __double2float_ru(fmax(fabs(vx), fabs(vy)));
         if (!(vm == vm)) vm = __int_as_float(0x7f800000);
         int X, Y;
@@ -87,12 +87,10 @@ k_pack(int n, size_t N, edmd_dev_box b, int ps, const double *__restrict__ soa,
     }
     ghosts = __reduce_add_sync(0xffffffffu, ghosts);
     insane = __reduce_add_sync(0xffffffffu, insane);
-    notmono = __reduce_or_sync(0xffffffffu, notmono);
     const unsigned vmb = __reduce_max_sync(0xffffffffu, (unsigned)__float_as_int(vm));   // vm >= 0: bits order like values
     if ((threadIdx.x & 31) == 0) {
         if (ghosts) atomicAdd(&flags[kFlagGhosts], ghosts);
         if (insane) atomicAdd(&flags[kFlagInsane], insane);
-        if (notmono) atomicOr(&flags[kFlagNotMono], 1);
         atomicMax(reinterpret_cast<unsigned int *>(&flags[kFlagVmax]), vmb);
     }
 }
@@ -402,7 +400,7 @@ k_halo_append(int count, int first, int ps, int row, const HaloRec *__restrict__
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const HaloRec r = in[k];
-    if (!(r.rad == rad0)) atomicOr(&flags[kFlagNotMono], 1);
+    edmd_note_radius(flags, r.rad, rad0);
     {
         float vm = __double2float_ru(fmax(fabs(r.vx), fabs(r.vy)));
         if (!(vm == vm)) vm = __int_as_float(0x7f800000);

@@ -134,7 +134,9 @@ int check_flags(edmd_ctx *c)
     CU(cudaStreamSynchronize(c->stream));
     c->nghost = f[kFlagGhosts];
     memcpy(&c->vmax, &f[kFlagVmax], sizeof(float));
-    c->lean_ok = f[kFlagNotMono] == 0 && f[kFlagInsane] == 0 && c->vmax >= 1e-12f && c->vmax <= 1e12f;
+    c->lean_ok = f[kFlagNotMono] <= 1 && f[kFlagInsane] == 0 && c->vmax >= 1e-12f && c->vmax <= 1e12f;
+    c->lean_two = f[kFlagNotMono] == 1;
+    memcpy(&c->rad1, &f[kFlagRad1], sizeof(double));
     if (f[kFlagBadCell] & 2) {
         CU(cudaMemsetAsync(c->flags + kFlagBadCell, 0, sizeof(int32_t), c->stream));
         return fail(c, EDMD_EINVAL, "halo buffer too small for a boundary row");
@@ -408,8 +410,9 @@ static int upload_impl(edmd_ctx *c, int n, const double *x, const double *y, con
     if (!keep_rad && (r = h2d(c, c->in_soa + 4 * N, rad, B))) return r;
     if (cell_xy && (r = h2d(c, c->in_cell, cell_xy, 2 * (size_t)n * sizeof(int32_t)))) return r;
     if (gid && (r = h2d(c, c->gid, gid, (size_t)n * sizeof(int32_t)))) return r;
-    // ghosts, insane, vmax, notmono, leanfail
+    // ghosts, insane, vmax, notmono, leanfail; the second radius class
     CU(cudaMemsetAsync(c->flags + kFlagGhosts, 0, 5 * sizeof(int32_t), c->stream));
+    CU(cudaMemsetAsync(c->flags + kFlagRad1, 0, 2 * sizeof(int32_t), c->stream));
     if (!keep_rad) c->rad0 = n > 0 ? rad[0] : 1.0;
     c->nghost = 0;
     c->n = n;

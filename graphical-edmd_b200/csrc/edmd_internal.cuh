@@ -119,9 +119,10 @@ struct CellIndex {
 enum {
     kFlagBadCell = 0, kFlagRescans = 1, kFlagGhosts = 2, kFlagInsane = 3,
     kFlagVmax = 4,       // bits of the largest |velocity component| (float, rounded up)
-    kFlagNotMono = 5,    // some radius differs from the first particle's
+    kFlagNotMono = 5,    // radii: 0 all equal rad0, 1 exactly one other value (kFlagRad1), >= 2 more
     kFlagLeanFail = 6,   // the lean sweep declined (state not eligible): redo with the full path
     kFlagWork = 7,       // number of entries in the lean work list (chunks that hold particles)
+    kFlagRad1 = 8,       // (two words, 8-byte aligned) bits of the second radius, 0 = none seen
     kFlagCount = 16
 };
 
@@ -148,7 +149,9 @@ struct edmd_ctx {
     bool lean_ok;        // resident state is eligible for the lean sweep (monodisperse, sane speeds)
     bool lean_off;       // EDMD_OPT_NO_LEAN
     bool lean_pdl;       // launch the lean chain with programmatic dependent launch (default on)
-    double rad0;         // radius of the first particle (the common radius when lean_ok)
+    double rad0;         // radius of the first particle = radius class 0 of the lean sweep
+    double rad1;         // radius class 1 (valid when lean_two: exactly two radii in the system)
+    bool lean_two;
     float vmax;          // largest |velocity component| of the upload
     uint32_t index_epoch;
     int pred_mode;       // mode of the last sweep
@@ -288,6 +291,27 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
                            int n, unsigned long long *counts);
 int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
                     int n, int part, int nparts, unsigned long long *counts);
+
+// Radius classes of the lean sweep: class 0 = rad0 (the first particle's radius),
+// class 1 = one other value.  Called for every particle whose radius enters the
+// resident state (upload, halo).  Plain reads first: after the first claim lands
+// nobody issues atomics any more.
+#ifdef __CUDACC__
+__device__ __forceinline__ void edmd_note_radius(int32_t *flags, double r, double rad0)
+{
+    if (r == rad0) return;
+    unsigned long long *slot = reinterpret_cast<unsigned long long *>(flags + kFlagRad1);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(r);
+    int level = 2;
+    if (r > 0) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(slot);
+        if (cur == 0ull) cur = atomicCAS(slot, 0ull, bits);
+        if (cur == 0ull || cur == bits) level = 1;
+    }
+    if ((*reinterpret_cast<volatile int32_t *>(flags + kFlagNotMono) & level) != level)
+        atomicOr(&flags[kFlagNotMono], level);
+}
+#endif
 
 // ---- programmatic dependent launch -----------------------------------------------
 // The kernels of a sweep form a dependent chain on one stream.  Each is launched

@@ -179,7 +179,7 @@ k_halo_recv(const __grid_constant__ RecvArgs a)
             a.gid[i] = r.gid;
             a.cid[i] = a.row[from] * a.ps + r.cell;
             // keep the lean sweep's eligibility facts current (lean.cuh)
-            if (!(r.rad == a.rad0)) atomicOr(&a.flags[kFlagNotMono], 1);
+            edmd_note_radius(a.flags, r.rad, a.rad0);
             float vm = __double2float_ru(fmax(fabs(r.vx), fabs(r.vy)));
             if (!(vm == vm)) vm = __int_as_float(0x7f800000);
             if (__float_as_int(vm) > a.flags[kFlagVmax])

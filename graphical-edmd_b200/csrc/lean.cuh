@@ -1,10 +1,12 @@
 // lean.cuh -- data layout of the LEAN cell index and of the certified-FP32
 // prediction sweep built on it (lean_index.cu, predict_lean.cu).
 //
-// The lean path is taken for the re-predict sweep of a MONODISPERSE system in
-// NORMAL mode (every BASELINE.json configuration but the reference's default
-// bidisperse run, which keeps the FP64 row kernel of predict.cu).  It moves
-// fewer bytes and issues fewer instructions than the full path:
+// The lean path is taken for the re-predict sweep in NORMAL mode of a system with
+// ONE or TWO distinct radii (every BASELINE.json configuration, including the
+// reference's default bidisperse run; general polydisperse systems keep the FP64
+// row kernel of predict.cu).  With two radii the class of a particle rides in the
+// least significant mantissa bit of its FP32 vy (one more ulp in the error model).
+// It moves fewer bytes and issues fewer instructions than the full path:
 //
 //   K0-lean  count (RED atomics, no ranks) -> ONE index kernel (row scan + chunk
 //            plan; every cell row owns a FIXED range of `rowcap` slots, so rows
@@ -64,7 +66,8 @@ struct LeanIndex {
 struct LeanConsts {
     float csx, csy;
     float inv_rho2, inv_om2;   // Psi = d2 * inv_rho2 + v2 * inv_om2 + 1
-    float A, Cc;               // c_lo = d2 * A - Cc
+    float A;                   // c_lo = d2 * A - Cc
+    float Cc00, Cc01, Cc11;    // Cc per pair of radius classes (all equal when there is one radius)
     float Kb, Kdet;            // B_up = Kb * Psi - b ; det_up = det + Kdet * Psi^2
     int ok;                    // 0: velocity scale outside the FP32-safe range
 };

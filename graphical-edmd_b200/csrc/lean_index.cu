@@ -173,6 +173,8 @@ struct ScatterArgs {
     int32_t *cursor;
     const int32_t *flags;
     LeanRec *rec;
+    const double *rad;   // two radius classes: class bit = (rad[i] != rad0), carried in vy's last mantissa bit
+    double rad0;
 };
 
 // one full 32-byte sector with a single 256-bit store
@@ -193,6 +195,7 @@ k_lean_scatter(const __grid_constant__ ScatterArgs a)
     const int i0 = kPer * (blockIdx.x * blockDim.x + threadIdx.x);
     edmd_pdl_wait();
     if (i0 >= a.n || a.flags[kFlagLeanFail] != 0) return;   // a row overflowed its slot range: declined
+    const bool two = a.flags[kFlagNotMono] == 1;
     int pc[kPer], slot[kPer];
     double4 p[kPer];
     if (kPer == 4 && i0 + kPer <= a.n) {
@@ -220,6 +223,7 @@ k_lean_scatter(const __grid_constant__ ScatterArgs a)
         r.y = __double2float_rn(__dsub_rn(p[k].y, __dmul_rn((double)Yg + 0.5, a.b.csy)));
         r.z = __double2float_rn(p[k].z);
         r.w = __double2float_rn(p[k].w);
+        if (two) r.w = __int_as_float((__float_as_int(r.w) & ~1) | (a.rad[i0 + k] != a.rad0 ? 1 : 0));
         put_lean(a, slot[k], pc[k], i0 + k, r);
         if (pcx == 1) {   // cell 0 -> right ghost
             const int g = Yl * a.ps + a.nx + 1;
@@ -254,6 +258,7 @@ int edmd_launch_lean_index(edmd_ctx *c)
     ScatterArgs sa;
     sa.n = n; sa.nx = c->dbox.nx; sa.ps = c->ps; sa.b = c->dbox;
     sa.cid = c->cid; sa.xv = c->xv; sa.cursor = c->cstart; sa.flags = c->flags; sa.rec = c->lrec;
+    sa.rad = c->rad; sa.rad0 = c->rad0;
     edmd_launch(k_lean_scatter, dim3(((n + kPer - 1) / kPer + kThreads - 1) / kThreads), dim3(kThreads), 0, c->stream,
                 c->lean_pdl, sa);
     c->index_has_vr = false;

@@ -90,7 +90,8 @@ struct ScreenArgs {
     int2 *res;
 };
 
-__device__ __forceinline__ LeanConsts make_consts(const edmd_dev_box &b, double rad0, float vmaxf)
+__device__ __forceinline__ LeanConsts make_consts(const edmd_dev_box &b, double rad0, double rad1, bool two,
+                                                   float vmaxf)
 {
     LeanConsts K;
     const double V = (double)vmaxf;
@@ -98,8 +99,10 @@ __device__ __forceinline__ LeanConsts make_consts(const edmd_dev_box &b, double 
     const double u = 5.9604644775390625e-08;    // 2^-24
     const double cs = fmax(b.csx, b.csy);
     const double Rm = 1.5 * cs, rho = cs, om = 0.5 * V;
-    const double s2 = 4.0 * rad0 * rad0;
-    const double ed = 8.0 * Rm, ew = 4.0 * V;   // e_d / u, e_w / u
+    const double rmax = two ? fmax(rad0, rad1) : rad0;
+    const double s2 = 4.0 * rmax * rmax;        // the error terms take the largest contact distance
+    // two radii: the class bit in the last mantissa bit of vy costs one more ulp per particle
+    const double ed = 8.0 * Rm, ew = (two ? 8.0 : 4.0) * V;   // e_d / u, e_w / u
     const double kb = 0.7072 * (rho * ew + om * ed) + rho * om;
     const double kv = 1.4143 * om * ew + 2.0 * om * om;
     const double kdet = rho * om * kb + (rho * rho + s2) * kv + om * om * (4.0 * rho * rho + s2);
@@ -110,7 +113,11 @@ __device__ __forceinline__ LeanConsts make_consts(const edmd_dev_box &b, double 
     K.inv_rho2 = __double2float_rn(1.0 / (rho * rho));
     K.inv_om2 = __double2float_rn(1.0 / (om * om));
     K.A = __double2float_rd(1.0 - k4);
-    K.Cc = __double2float_ru(s2 + k5);
+    // 4 r1 r2 of the reference (src/EDMD.c:2700) per pair of classes
+    const double r1 = two ? rad1 : rad0;
+    K.Cc00 = __double2float_ru(4.0 * rad0 * rad0 + k5);
+    K.Cc01 = __double2float_ru(4.0 * rad0 * r1 + k5);
+    K.Cc11 = __double2float_ru(4.0 * r1 * r1 + k5);
     K.Kb = __double2float_ru(1.5 * u * kb + 1.9073486328125e-06 * rho * om);   // + 2^-19 rho om
     K.Kdet = __double2float_ru(1.5 * u * kdet);
     return K;
@@ -214,7 +221,7 @@ __device__ __forceinline__ void flush_pending(const ScreenArgs &a, Pending &pend
     pend.id = -1;
 }
 
-template <bool STAGED>
+template <bool STAGED, bool TWO>
 __device__ __forceinline__ void screen_chunk(const ScreenArgs &a, const LeanConsts &K, const LeanBuf &w,
                                              int c, int lane, int2 tag, Pending &out)
 {
@@ -253,6 +260,9 @@ __device__ __forceinline__ void screen_chunk(const ScreenArgs &a, const LeanCons
     const float4 own = STAGED ? scr[selfc] : *reinterpret_cast<const float4 *>(g.rec + selfc);
     // dx = rx_j - (rx_i - k csx), k = column(j) - column(i) in {-1, 0, 1}
     const float pxm = __fadd_rn(own.x, K.csx), px0 = own.x, pxp = __fsub_rn(own.x, K.csx);
+    // contact distance squared (+ slack) against a candidate of class 0 / class 1
+    const bool own1 = TWO && (__float_as_int(own.w) & 1);
+    const float cc_a = own1 ? K.Cc01 : K.Cc00, cc_b = own1 ? K.Cc11 : K.Cc01;
 
     float lo1 = __int_as_float(0x7f800000), lo2 = __int_as_float(0x7f800000);   // two smallest bounds
     int idx = -1;
@@ -267,7 +277,7 @@ __device__ __forceinline__ void screen_chunk(const ScreenArgs &a, const LeanCons
         const float v2 = __fmaf_rn(dvy, dvy, __fmul_rn(dvx, dvx));
         const float bb = __fmaf_rn(dy, dvy, __fmul_rn(dx, dvx));
         const float psi = __fmaf_rn(d2, K.inv_rho2, __fmaf_rn(v2, K.inv_om2, 1.0f));
-        const float clo = __fmaf_rn(d2, K.A, -K.Cc);
+        const float clo = __fmaf_rn(d2, K.A, TWO ? ((__float_as_int(q.w) & 1) ? -cc_b : -cc_a) : -cc_a);
         const float det = __fmaf_rn(-v2, clo, __fmul_rn(bb, bb));
         const float detu = __fmaf_rn(__fmul_rn(K.Kdet, psi), psi, det);
         const float bup = __fmaf_rn(K.Kb, psi, -bb);
@@ -307,19 +317,9 @@ __device__ __forceinline__ void screen_chunk(const ScreenArgs &a, const LeanCons
     }
 }
 
-__global__ void __launch_bounds__(kLeanThreads, kLeanCtas)
-k_screen(const __grid_constant__ ScreenArgs a)
+template <bool TWO>
+__device__ __forceinline__ void screen_main(const ScreenArgs &a, const LeanConsts &K, unsigned char *lean_smem)
 {
-    extern __shared__ __align__(128) unsigned char lean_smem[];
-    edmd_pdl_wait();
-    // the state must be eligible (the host checked what it knows; halo particles
-    // arrive on the device): otherwise decline and let the host take the full path
-    const LeanConsts K = make_consts(a.b, a.rad0, __int_as_float(a.flags[kFlagVmax]));
-    if (a.flags[kFlagLeanFail] != 0) return;   // the index declined (a row denser than its slot range)
-    if (a.flags[kFlagInsane] != 0 || a.flags[kFlagNotMono] != 0 || !K.ok) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) a.flags[kFlagLeanFail] = 1;
-        return;
-    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     LeanBuf *bufs = reinterpret_cast<LeanBuf *>(lean_smem) + 2 * warp;
     const int stride = gridDim.x * kLeanWarps;
@@ -359,8 +359,8 @@ k_screen(const __grid_constant__ ScreenArgs a)
             __syncwarp();
             const LeanBuf &buf = bufs[k];
             const int status = buf.plan[kPlStatus];
-            if (status == 1) screen_chunk<true>(a, K, buf, c, lane, tag, pend);
-            else if (status == 2) screen_chunk<false>(a, K, buf, c, lane, tag, pend);
+            if (status == 1) screen_chunk<true, TWO>(a, K, buf, c, lane, tag, pend);
+            else if (status == 2) screen_chunk<false, TWO>(a, K, buf, c, lane, tag, pend);
             __syncwarp();   // every lane is done with the buffer before it is refilled
             tag = tagn;
             b = bn;
@@ -374,6 +374,25 @@ k_screen(const __grid_constant__ ScreenArgs a)
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+__global__ void __launch_bounds__(kLeanThreads, kLeanCtas)
+k_screen(const __grid_constant__ ScreenArgs a)
+{
+    extern __shared__ __align__(128) unsigned char lean_smem[];
+    edmd_pdl_wait();
+    // the state must be eligible (the host checked what it knows; halo particles
+    // arrive on the device): otherwise decline and let the host take the full path
+    const int classes = a.flags[kFlagNotMono];   // 0: one radius, 1: two, more: not eligible
+    const double rad1 = __longlong_as_double(*reinterpret_cast<const long long *>(a.flags + kFlagRad1));
+    const LeanConsts K = make_consts(a.b, a.rad0, rad1, classes == 1, __int_as_float(a.flags[kFlagVmax]));
+    if (a.flags[kFlagLeanFail] != 0) return;   // the index declined (a row denser than its slot range)
+    if (a.flags[kFlagInsane] != 0 || classes > 1 || !K.ok) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.flags[kFlagLeanFail] = 1;
+        return;
+    }
+    if (classes == 1) screen_main<true>(a, K, lean_smem);
+    else screen_main<false>(a, K, lean_smem);
+}
+
 // ---- k_resolve: exact evaluation of the winner, one thread per particle -------------
 struct ResolveArgs {
     edmd_dev_box b;
@@ -381,6 +400,7 @@ struct ResolveArgs {
     double t, rad0;
     int n_owned;
     const double4 *xv;
+    const double *rad;
     const int32_t *cid;
     const int2 *res;
     const int32_t *gid;
@@ -397,7 +417,7 @@ __device__ __forceinline__ int gid_of(const ResolveArgs &a, int id) { return a.g
 
 // The plain FP64 loop over the candidate slots [lo, hi) of one row, straight
 // from global memory: the reference's scan with its tie rule (see predict.cu).
-__device__ __forceinline__ void exact_scan_lean(const ResolveArgs &a, const SRec &p1, double four_r1,
+__device__ __forceinline__ void exact_scan_lean(const ResolveArgs &a, bool two, const SRec &p1, double four_r1,
                                                 int lo, int hi, double &best, int &best_id,
                                                 int &best_pc, int &ov_id, int &ov_pc)
 {
@@ -408,7 +428,7 @@ __device__ __forceinline__ void exact_scan_lean(const ResolveArgs &a, const SRec
         const double4 q = ld_sector(a.xv + tag.x);
         SRec p2;
         p2.x = q.x; p2.y = q.y; p2.vx = q.z; p2.vy = q.w;
-        p2.rad = a.rad0; p2.id = tag.x; p2.pc = tag.y;
+        p2.rad = two ? a.rad[tag.x] : a.rad0; p2.id = tag.x; p2.pc = tag.y;
         bool ov = false;
         const double dt = pair_time_normal<true>(a.b, p1, four_r1, p2, ov);
         if (ov && (ov_id < 0 || (p2.pc == ov_pc && gid_of(a, p2.id) > gid_of(a, ov_id)))) {
@@ -437,14 +457,20 @@ k_resolve(const __grid_constant__ ResolveArgs a)
     const int2 r = a.res[i];
     const int pc = a.cid[i];
     const double4 me = ld_sector(a.xv + i);
+    const bool two = a.flags[kFlagNotMono] == 1;   // two radius classes: radii come from the resident array
+    const double rad_i = two ? a.rad[i] : a.rad0;
     if (declined != 0) return;   // k_screen (or the index) declined: res[] is stale
     double4 wq = make_double4(0, 0, 0, 0);
-    if (r.x >= 0) wq = ld_sector(a.xv + r.x);
+    double rad_w = a.rad0;
+    if (r.x >= 0) {
+        wq = ld_sector(a.xv + r.x);
+        if (two) rad_w = a.rad[r.x];
+    }
     const int Y = pc / a.g.ps;
     const int pcx = pc - Y * a.g.ps;
     SRec p1;
     p1.x = me.x; p1.y = me.y; p1.vx = me.z; p1.vy = me.w;
-    p1.rad = a.rad0; p1.id = i; p1.pc = pc;
+    p1.rad = rad_i; p1.id = i; p1.pc = pc;
     const double four_r1 = __dmul_rn(4.0, p1.rad);
     {
         double dtc;
@@ -459,7 +485,7 @@ k_resolve(const __grid_constant__ ResolveArgs a)
     if (r.x >= 0) {
         SRec p2;
         p2.x = wq.x; p2.y = wq.y; p2.vx = wq.z; p2.vy = wq.w;
-        p2.rad = a.rad0; p2.id = r.x; p2.pc = 0;
+        p2.rad = rad_w; p2.id = r.x; p2.pc = 0;
         double bb, v2, cc, b2, vc;
         pair_terms<true>(a.b, p1, four_r1, p2, bb, v2, cc, b2, vc);
         const double det = __dsub_rn(b2, vc);
@@ -479,7 +505,7 @@ k_resolve(const __grid_constant__ ResolveArgs a)
             const int Yr = row_wrap(Y - 1 + j, a.g.nl);
             const int rb = Yr * a.g.rowcap;
             const int32_t *o = a.g.off + (size_t)Yr * a.g.ps;
-            exact_scan_lean(a, p1, four_r1, rb + o[pcx - 1], rb + o[pcx + 2], best, best_id, best_pc,
+            exact_scan_lean(a, two, p1, four_r1, rb + o[pcx - 1], rb + o[pcx + 2], best, best_id, best_pc,
                             ov_id, ov_pc);
         }
     }
@@ -538,7 +564,7 @@ int edmd_launch_predict_lean(edmd_ctx *c)
         ra.t = c->t;
         ra.rad0 = c->rad0;
         ra.n_owned = c->n_owned;
-        ra.xv = c->xv; ra.cid = c->cid; ra.res = c->lres;
+        ra.xv = c->xv; ra.rad = c->rad; ra.cid = c->cid; ra.res = c->lres;
         ra.gid = c->slab ? c->gid : nullptr;
         ra.flags = c->flags;
         ra.t_cross = c->t_cross; ra.dir = c->dir; ra.t_coll = c->t_coll; ra.partner = c->partner;

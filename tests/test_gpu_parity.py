@@ -463,6 +463,34 @@ def test_lean_and_full_sweeps_agree(pkg, n, phi, seed, vscale):
     assert rescans < 0.02 * c["n"], rescans
 
 
+@pytest.mark.parametrize("n,phi,seed,ratio", [(200000, 0.70, 49, 0.4), (120000, 0.80, 50, 0.85)])
+def test_lean_sweep_with_two_radius_classes(pkg, oracle, n, phi, seed, ratio):
+    """Bidisperse systems (the reference's default) stay on the lean path: the radius
+    class rides in the last mantissa bit of the FP32 vy; three radii do not."""
+    c = pkg.synth.lattice_config(n, phi, seed, small_fraction=0.3)
+    rad = np.where(c["rad"] < 1.0, ratio, 1.0)
+    c = dict(c, rad=rad)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=2.0)
+        a = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 1
+        rescans = ctx.stat(pkg.binding.STAT_EXACT_RESCANS)
+        ctx.set_option(pkg.binding.OPT_NO_LEAN, 1)
+        b = ctx.predict_all()
+        # a third radius: not eligible any more
+        rad3 = rad.copy()
+        rad3[5::11] = 0.5 * ratio
+        ctx.set_option(pkg.binding.OPT_NO_LEAN, 0)
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], rad3, t=2.0)
+        d = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 1
+    for k in ("t_cross", "dir", "t_coll", "partner", "ctype"):
+        assert np.array_equal(a[k], b[k]), k
+    assert rescans < 0.02 * c["n"], rescans
+    assert_events_equal(a, oracle_sweep(oracle, c, t=2.0))
+    assert_events_equal(d, oracle_sweep(oracle, dict(c, rad=rad3), t=2.0))
+
+
 def _adversarial_clusters(seed, n_clusters, vscale):
     """Isolated 3-particle clusters on a coarse grid, built so that the FP32 screening
     of the lean sweep is at its limits: two partners whose collision times with the
@@ -507,12 +535,21 @@ def _adversarial_clusters(seed, n_clusters, vscale):
                 rad=np.ones(n))
 
 
-@pytest.mark.parametrize("seed,vscale", [(61, 1.0), (62, 1.0), (63, 1e-5), (64, 2e3)])
+@pytest.mark.parametrize("seed,vscale", [(61, 1.0), (62, 1.0), (63, 1e-5), (64, 2e3), (65, 1.0)])
 def test_lean_certificate_on_adversarial_pairs(pkg, oracle, seed, vscale):
     """Near-ties, near-contacts, grazing and nearly parallel pairs at relative
     margins from 10^-1 down to 10^-12: whatever the FP32 bounds cannot decide must
     reach the exact re-scan, so the lean sweep still equals the oracle bit for bit."""
     c = _adversarial_clusters(seed, 20000, vscale)
+    if seed == 65:   # two radius classes: isolated small disks between the clusters
+        rng = np.random.default_rng(seed)
+        m = int(np.ceil(np.sqrt(20000)))
+        gx, gy = np.meshgrid(np.arange(m), np.arange(m))
+        ex, ey = (gx.ravel() * 16.0 + 0.3)[:8000], (gy.ravel() * 16.0 + 0.3)[:8000]   # cluster-free corners
+        c = dict(n=c["n"] + 8000, lx=c["lx"], ly=c["ly"], x=np.concatenate([c["x"], ex]),
+                 y=np.concatenate([c["y"], ey]), vx=np.concatenate([c["vx"], rng.standard_normal(8000)]),
+                 vy=np.concatenate([c["vy"], rng.standard_normal(8000)]),
+                 rad=np.concatenate([c["rad"], np.full(8000, 0.25)]))
     with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
         ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.5)
         r0 = ctx.stat(pkg.binding.STAT_EXACT_RESCANS)

@@ -153,7 +153,6 @@ struct edmd_ctx {
     double rad1;         // radius class 1 (valid when lean_two: exactly two radii in the system)
     bool lean_two;
     float vmax;          // largest |velocity component| of the upload
-    uint32_t index_epoch;
     int pred_mode;       // mode of the last sweep
     bool lean_pending;   // the last sweep was launched on the lean path and not yet confirmed
     uint64_t lean_sweeps; // sweeps confirmed on the lean path

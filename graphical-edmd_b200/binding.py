@@ -19,7 +19,7 @@ LIB_PATH = _HERE / "libedmd_cuda.so"
 MODE_NORMAL, MODE_GROW = 0, 1
 EV_CELLCROSS, EV_COLLISION = 0, 1
 EINVAL, ESTATE, EOVERLAP, ECELL, ENOMEM = 1, 2, 3, 4, 5
-BENCH_SWEEP, BENCH_FREEFLY, BENCH_BOOP, BENCH_PCF = 0, 1, 2, 3
+BENCH_SWEEP, BENCH_FREEFLY, BENCH_BOOP, BENCH_PCF, BENCH_VORONOI = 0, 1, 2, 3, 4
 OPT_FORCE_GENERIC = 1
 OPT_NO_LEAN = 2
 OPT_NO_PDL = 3
@@ -43,7 +43,10 @@ SYMBOLS = [
     "edmd_cuda_halo_append", "edmd_cuda_get_counts", "edmd_cuda_pcf_device",
     "edmd_cuda_halo_export", "edmd_cuda_halo_connect", "edmd_cuda_halo_exchange",
     "edmd_cuda_calendar_plan", "edmd_cuda_pcf_bond_order", "edmd_cuda_bragg_peak",
+    "edmd_cuda_boop_voronoi", "edmd_cuda_voronoi_cells", "edmd_cuda_g6_correlation",
+    "edmd_cuda_structure_factor",
 ]
+EVORONOI = 7
 HALO_RECORD_BYTES = 48
 
 
@@ -116,6 +119,11 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_calendar_plan.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, vp,
                                             C.POINTER(C.c_int32)]
     lib.edmd_cuda_get_stat.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
+    lib.edmd_cuda_boop_voronoi.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.edmd_cuda_voronoi_cells.argtypes = [vp, vp, vp, vp]
+    lib.edmd_cuda_g6_correlation.argtypes = [vp, C.c_double, C.c_double, vp, vp, vp, vp, C.POINTER(C.c_int)]
+    lib.edmd_cuda_structure_factor.argtypes = [vp, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                               vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:
@@ -315,6 +323,50 @@ class EdmdCuda:
         self._check(self.lib.edmd_cuda_boop_cutoff(
             self._h, r_c, _ptr(q5), _ptr(q6), _ptr(q7), _ptr(arg), _ptr(nb), C.addressof(mean)))
         return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, mean_q6=mean.value)
+
+    def boop_voronoi(self):
+        """computeBOOPVoronoi (src/boop.c:15-59) on the resident positions."""
+        n = self.n
+        q5, q6, q7, arg = (np.empty(n, np.float64) for _ in range(4))
+        nb = np.empty(n, np.int32)
+        mean = C.c_double(0.0)
+        self._check(self.lib.edmd_cuda_boop_voronoi(
+            self._h, _ptr(q5), _ptr(q6), _ptr(q7), _ptr(arg), _ptr(nb), C.addressof(mean)))
+        return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, mean_q6=mean.value)
+
+    def voronoi_cells(self):
+        """get_particle_voronoi_area / _perimeter (src/voronoi_edmd.c:123-149)."""
+        n = self.n
+        area, per = np.empty(n, np.float64), np.empty(n, np.float64)
+        nb = np.empty(n, np.int32)
+        self._check(self.lib.edmd_cuda_voronoi_cells(self._h, _ptr(area), _ptr(per), _ptr(nb)))
+        return dict(area=area, perimeter=per, neighbors=nb)
+
+    def g6_correlation(self, dr, max_r, psi_re=None, psi_im=None):
+        """compute_g6_correlation (src/pcf.c:169-230); psi None = Voronoi psi6 from the device."""
+        nb = C.c_int(0)
+        self._check(self.lib.edmd_cuda_g6_correlation(self._h, dr, max_r, None, None, None, None, C.byref(nb)))
+        counts = np.zeros(nb.value, np.uint64)
+        g6 = np.zeros(nb.value, np.float64)
+        pr = None if psi_re is None else _f64(psi_re, self.n)
+        pi = None if psi_im is None else _f64(psi_im, self.n)
+        self._check(self.lib.edmd_cuda_g6_correlation(self._h, dr, max_r, _ptr(pr), _ptr(pi), _ptr(counts),
+                                                      _ptr(g6), C.byref(nb)))
+        return dict(num_bins=nb.value, counts=counts, g6_corr=g6)
+
+    def structure_factor(self, q_max, velocity=False):
+        """initStructureFactor's grid + computeStructureFactor / computeVelocityStructureFactor
+        (src/struc.c:328-345, 364-408); s[i, j] for (qx[i], qy[j])."""
+        nqx, nqy = C.c_int(0), C.c_int(0)
+        self._check(self.lib.edmd_cuda_structure_factor(self._h, q_max, int(velocity), C.byref(nqx), C.byref(nqy),
+                                                        None, None, None, None, None))
+        qx, qy = np.zeros(nqx.value), np.zeros(nqy.value)
+        nk = nqx.value * nqy.value
+        s, re, im = np.zeros(nk), np.zeros(nk), np.zeros(nk)
+        self._check(self.lib.edmd_cuda_structure_factor(self._h, q_max, int(velocity), C.byref(nqx), C.byref(nqy),
+                                                        _ptr(qx), _ptr(qy), _ptr(s), _ptr(re), _ptr(im)))
+        shape = (nqx.value, nqy.value)
+        return dict(qx=qx, qy=qy, s=s.reshape(shape), re=re.reshape(shape), im=im.reshape(shape))
 
     def pcf_bond_order(self, dr, max_r, k_vector):
         """calculate_bond_order_pcf (src/pcf.c:77-167) on the resident positions."""

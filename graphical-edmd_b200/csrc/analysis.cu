@@ -283,11 +283,10 @@ int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const do
                     int n, int part, int nparts, unsigned long long *counts)
 {
     if (n < 2 || num_bins <= 0) return 0;
-    // whole-system call on a large system: spatially sorted tiles + certified bins
-    // (analysis_pcf_sorted.cu).  The multi-GPU split (part / nparts) keeps this kernel:
-    // its tile pairs are the same on every rank.
-    if (part == 0 && nparts == 1 && n >= 8192 && !c->pcf_legacy) {
-        const int r = edmd_launch_pcf_sorted(c, dr, max_r, num_bins, xy, stride, n, counts);
+    // large systems: spatially sorted tiles + certified bins (analysis_pcf_sorted.cu); for
+    // the multi-GPU split the sort is made deterministic so that every rank cuts the same tiles
+    if (n >= 8192 && !c->pcf_legacy) {
+        const int r = edmd_launch_pcf_sorted(c, dr, max_r, num_bins, xy, stride, n, part, nparts, counts);
         if (r >= 0) return r;
     }
     size_t tile_bytes = kTile * sizeof(double2);

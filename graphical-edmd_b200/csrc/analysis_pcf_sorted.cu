@@ -44,6 +44,7 @@ struct SortArgs {
     int32_t *cnt;        // [gx * gy + 1]
     int32_t *cell;       // [n]
     double2 *sorted;
+    int32_t *sidx;       // [n] original index of sorted[k] (nullptr: not needed)
 };
 
 __device__ __forceinline__ int coarse_cell(const SortArgs &a, double x, double y)
@@ -100,7 +101,32 @@ k_coarse_scatter(const __grid_constant__ SortArgs a)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const double2 p = *reinterpret_cast<const double2 *>(a.xy + (size_t)i * a.stride);
-    a.sorted[atomicAdd(&a.cnt[a.cell[i]], 1)] = p;   // cnt holds the running cursors now
+    const int k = atomicAdd(&a.cnt[a.cell[i]], 1);   // cnt holds the running cursors now
+    a.sorted[k] = p;
+    if (a.sidx) a.sidx[k] = i;
+}
+
+// Multi-GPU split: every rank must cut the SAME tiles, so the arrival order inside a
+// coarse cell (atomics) is replaced by the order of the original indices.  One CTA
+// per coarse cell; rank of an entry = number of entries of the cell with a smaller index.
+__global__ void __launch_bounds__(kThreads)
+k_coarse_order(int ncoarse, const int32_t *__restrict__ cend, const double2 *__restrict__ in,
+               const int32_t *__restrict__ idx, double2 *__restrict__ out)
+{
+    __shared__ int s_idx[1024];
+    const int c = blockIdx.x;
+    const int lo = c == 0 ? 0 : cend[c - 1], hi = cend[c];   // cursors ended at the cell ends
+    const int m = hi - lo;
+    const bool cached = m <= 1024;
+    if (cached)
+        for (int k = threadIdx.x; k < m; k += kThreads) s_idx[k] = idx[lo + k];
+    __syncthreads();
+    for (int k = threadIdx.x; k < m; k += kThreads) {
+        const int mine = idx[lo + k];
+        int rank = 0;
+        for (int q = 0; q < m; q++) rank += (cached ? s_idx[q] : idx[lo + q]) < mine;
+        out[lo + rank] = in[lo + k];
+    }
 }
 
 // exact bounding box of each tile
@@ -148,6 +174,7 @@ struct PcfArgs {
     const double4 *bbox;
     unsigned long long *counts;
     unsigned long long *stats;   // [0] pairs that took the exact path, [1] tile pairs skipped
+    int part, nparts;            // this launch takes the tile pairs w = part (mod nparts)
 };
 
 // distance of the interval [lo, hi] from 0
@@ -267,7 +294,7 @@ k_pcf_sorted(const __grid_constant__ PcfArgs a)
     const long long npairs = (long long)nt * (nt + 1) / 2;
     unsigned int slow = 0, skipped = 0;
     const double rcut = a.max_r * (1.0 + 1e-12);
-    for (long long w = blockIdx.x; w < npairs; w += gridDim.x) {
+    for (long long w = (long long)blockIdx.x * a.nparts + a.part; w < npairs; w += (long long)gridDim.x * a.nparts) {
         // unrank w -> (ta, tb), ta <= tb, row-major over the upper triangle
         const double fn = (double)nt + 0.5;
         long long ta = (long long)(fn - sqrt(fn * fn - 2.0 * (double)w));
@@ -337,9 +364,9 @@ static double s_threshold(double max_r)
     return s;
 }
 
-// Sorted-tile g(r) of the resident positions; ADDS into counts.  Returns launches.
+// Sorted-tile g(r); ADDS into counts the tile pairs w = part (mod nparts).  Returns launches.
 int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
-                           int n, unsigned long long *counts)
+                           int n, int part, int nparts, unsigned long long *counts)
 {
     if (n < 2 || num_bins <= 0) return 0;
     // coarse cells of ~192 particles, row-major
@@ -350,8 +377,9 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     if (gy < 1) gy = 1;
     const int ncoarse = gx * gy;
     const int nt = (n + kTile - 1) / kTile;
-    const size_t need = (size_t)n * sizeof(double2) + (size_t)nt * sizeof(double4) +
-                        ((size_t)n + ncoarse + 8) * sizeof(int32_t) + 64;
+    const bool ordered = nparts > 1;   // every rank must cut identical tiles
+    const size_t need = (size_t)n * sizeof(double2) * (ordered ? 2 : 1) + (size_t)nt * sizeof(double4) +
+                        ((size_t)n * (ordered ? 2 : 1) + ncoarse + 8) * sizeof(int32_t) + 64;
     if (need > c->pcfs_bytes) {
         if (c->pcfs_mem) cudaFree(c->pcfs_mem);
         c->pcfs_mem = nullptr;
@@ -365,19 +393,30 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     }
     char *m = c->pcfs_mem;
     double2 *sorted = reinterpret_cast<double2 *>(m);
-    double4 *bbox = reinterpret_cast<double4 *>(m + (size_t)n * sizeof(double2));
-    int32_t *cnt = reinterpret_cast<int32_t *>(m + (size_t)n * sizeof(double2) + (size_t)nt * sizeof(double4));
+    m += (size_t)n * sizeof(double2);
+    double2 *sorted2 = reinterpret_cast<double2 *>(m);
+    if (ordered) m += (size_t)n * sizeof(double2);
+    double4 *bbox = reinterpret_cast<double4 *>(m);
+    m += (size_t)nt * sizeof(double4);
+    int32_t *cnt = reinterpret_cast<int32_t *>(m);
     int32_t *cell = cnt + ncoarse + 8;
+    int32_t *sidx = ordered ? cell + n : nullptr;
     unsigned long long *stats = reinterpret_cast<unsigned long long *>(c->pcfs_stats);
     SortArgs sa;
     sa.n = n; sa.stride = stride; sa.gx = gx; sa.gy = gy;
     sa.fx = gx / c->box.lx; sa.fy = gy / c->box.ly;
-    sa.xy = xy; sa.cnt = cnt; sa.cell = cell; sa.sorted = sorted;
+    sa.xy = xy; sa.cnt = cnt; sa.cell = cell; sa.sorted = sorted; sa.sidx = sidx;
     cudaMemsetAsync(cnt, 0, ((size_t)ncoarse + 8) * sizeof(int32_t), c->stream);
     const int pb = (n + kThreads - 1) / kThreads;
     k_coarse_count<<<pb, kThreads, 0, c->stream>>>(sa);
     k_small_scan<<<1, 1024, 0, c->stream>>>(ncoarse + 1, cnt);
     k_coarse_scatter<<<pb, kThreads, 0, c->stream>>>(sa);
+    int launched = 5;
+    if (ordered) {
+        k_coarse_order<<<ncoarse, kThreads, 0, c->stream>>>(ncoarse, cnt, sorted, sidx, sorted2);
+        sorted = sorted2;
+        launched++;
+    }
     k_tile_bbox<<<nt, kTile, 0, c->stream>>>(n, sorted, bbox);
     PcfArgs a;
     a.n = n; a.num_bins = num_bins;
@@ -388,6 +427,7 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     a.dr_hi = dr * (1.0 - 1.7763568394002505e-15);
     a.inv_dr = (float)(1.0 / dr);
     a.sorted = sorted; a.bbox = bbox; a.counts = counts; a.stats = stats;
+    a.part = part; a.nparts = nparts;
     const size_t tile_bytes = kTile * sizeof(double2);
     const size_t hist_bytes = (size_t)num_bins * sizeof(unsigned int);
     a.use_smem = (tile_bytes + hist_bytes) <= 200 * 1024;
@@ -401,8 +441,9 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_sorted, kThreads, smem);
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)(c->sm_count > 0 ? c->sm_count : 148) * per_sm;
-    const long long npairs = (long long)nt * (nt + 1) / 2;
+    const long long npairs = ((long long)nt * (nt + 1) / 2 + nparts - 1) / nparts;
     if (grid > npairs) grid = npairs;
+    if (grid < 1) grid = 1;
     k_pcf_sorted<<<(int)grid, kThreads, smem, c->stream>>>(a);
-    return 5;
+    return launched;
 }

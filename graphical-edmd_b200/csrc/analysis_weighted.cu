@@ -2,6 +2,8 @@
 // analysis:
 //   calculate_bond_order_pcf          src/pcf.c:77-167    g(r) and <cos(k.r)>(r)
 //   find_max_structure_factor_bragg   src/pcf.c:405-467   argmax_k S(k) in a wedge
+//   compute_g6_correlation (pair loop) src/pcf.c:189-228   <Re psi6_i^* psi6_j>(r)
+//   computeStructureFactor / computeVelocityStructureFactor  src/struc.c:364-408
 // Same pair tiling as K3 (analysis.cu).  The pair distance and its bin use the
 // reference's unfused FP64 operations (integer counts identical to
 // calculate_pcf's); the weights are accumulated in 2^-32 fixed point (exact
@@ -28,18 +30,25 @@ struct WPcfArgs {
     edmd_dev_box b;
     double bin_width, max_r, kx, ky;
     const double *xy;
+    const double2 *psi;           // PSI weights: psi6 of every particle (re, im)
     unsigned long long *counts;   // [num_bins] unordered pairs
-    unsigned long long *wsum;     // [num_bins] sum of cos(k.d) * 2^32 (two's complement)
+    unsigned long long *wsum;     // [num_bins] sum of the weights * 2^32 (two's complement)
 };
+
+// weight of a pair: cos(k_vector . d) (calculate_bond_order_pcf) or Re(conj(psi_i) psi_j)
+// (compute_g6_correlation)
+enum { kWeightCos = 0, kWeightPsi = 1 };
 
 // All unordered pairs i < j; the reference walks ordered pairs, which doubles
 // both sums (cos is even, d_ji = -d_ij) and leaves their ratio unchanged.
+template <int WEIGHT>
 __global__ void __launch_bounds__(kThreads)
 k_pcf_bond_order(const __grid_constant__ WPcfArgs a)
 {
     extern __shared__ unsigned char smem_raw[];
     double2 *tile = reinterpret_cast<double2 *>(smem_raw);
-    unsigned long long *hw = reinterpret_cast<unsigned long long *>(smem_raw + kTile * sizeof(double2));
+    double2 *ptile = tile + kTile;
+    unsigned long long *hw = reinterpret_cast<unsigned long long *>(smem_raw + 2 * kTile * sizeof(double2));
     unsigned int *hc = reinterpret_cast<unsigned int *>(hw + a.num_bins);
     if (a.use_smem)
         for (int k = threadIdx.x; k < a.num_bins; k += kThreads) {
@@ -58,12 +67,16 @@ k_pcf_bond_order(const __grid_constant__ WPcfArgs a)
         __syncthreads();
         {
             const int jj = (int)tb * kTile + threadIdx.x;
-            if (jj < a.n) tile[threadIdx.x] = *reinterpret_cast<const double2 *>(a.xy + (size_t)jj * a.stride);
+            if (jj < a.n) {
+                tile[threadIdx.x] = *reinterpret_cast<const double2 *>(a.xy + (size_t)jj * a.stride);
+                if (WEIGHT == kWeightPsi) ptile[threadIdx.x] = a.psi[jj];
+            }
         }
         __syncthreads();
         const int i = (int)ta * kTile + threadIdx.x;
         if (i < a.n) {
             const double2 pi = *reinterpret_cast<const double2 *>(a.xy + (size_t)i * a.stride);
+            const double2 si = WEIGHT == kWeightPsi ? a.psi[i] : make_double2(0.0, 0.0);
             const int jbase = (int)tb * kTile;
             const int jcount = min(kTile, a.n - jbase);
             const int jstart = (ta == tb) ? threadIdx.x + 1 : 0;
@@ -76,7 +89,10 @@ k_pcf_bond_order(const __grid_constant__ WPcfArgs a)
                     const int bin = (int)__ddiv_rn(r, a.bin_width);
                     if (bin < a.num_bins) {
                         // `cos(k_vector[0]*dx + k_vector[1]*dy)` src/pcf.c:123
-                        const double cw = cos(__dadd_rn(__dmul_rn(a.kx, dx), __dmul_rn(a.ky, dy)));
+                        // `creal(conj(psi6[i]) * psi6[j])` src/pcf.c:204
+                        const double cw = WEIGHT == kWeightPsi
+                                              ? __dadd_rn(__dmul_rn(si.x, ptile[jj].x), __dmul_rn(si.y, ptile[jj].y))
+                                              : cos(__dadd_rn(__dmul_rn(a.kx, dx), __dmul_rn(a.ky, dy)));
                         const unsigned long long q = (unsigned long long)__double2ll_rn(cw * kWFix);
                         if (a.use_smem) {
                             atomicAdd(&hc[bin], 1u);
@@ -140,6 +156,54 @@ k_bragg_sums(const __grid_constant__ BraggArgs a)
     }
 }
 
+// Structure factor on the reference's wave-vector grid: the same sums with the
+// weights of computeStructureFactor (1) or computeVelocityStructureFactor
+// (`re += vx cos + vy sin; im += vx sin - vy cos`, src/struc.c:395-396).  Wave
+// vector ik = i * nqy + j  ->  (qx[i], qy[j]).
+struct SqArgs {
+    int n, nqx, nqy, chunk;
+    const double4 *xv;
+    const double *qx, *qy;
+    double *re, *im;   // [nqx * nqy]
+};
+
+template <bool VEL>
+__global__ void __launch_bounds__(kThreads)
+k_sq_sums(const __grid_constant__ SqArgs a)
+{
+    __shared__ double4 tile[kTile];
+    const int nk = a.nqx * a.nqy;
+    const int ik = blockIdx.x * kThreads + threadIdx.x;
+    const double kx = ik < nk ? a.qx[ik / a.nqy] : 0.0, ky = ik < nk ? a.qy[ik % a.nqy] : 0.0;
+    double re = 0.0, im = 0.0;
+    const int j0 = blockIdx.y * a.chunk, j1 = min(a.n, j0 + a.chunk);
+    for (int base = j0; base < j1; base += kTile) {
+        __syncthreads();
+        const int jj = base + threadIdx.x;
+        if (jj < j1) tile[threadIdx.x] = a.xv[jj];
+        __syncthreads();
+        const int cnt = min(kTile, j1 - base);
+        for (int q = 0; q < cnt; q++) {
+            const double4 p = tile[q];
+            // `qr = qx[i]*p->x + qy[j]*p->y` src/struc.c:373
+            const double qr = __dadd_rn(__dmul_rn(kx, p.x), __dmul_rn(ky, p.y));
+            double s, c;
+            sincos(qr, &s, &c);
+            if (VEL) {
+                re += p.z * c + p.w * s;
+                im += p.z * s - p.w * c;
+            } else {
+                re += c;
+                im += s;
+            }
+        }
+    }
+    if (ik < nk) {
+        atomicAdd(&a.re[ik], re);
+        atomicAdd(&a.im[ik], im);
+    }
+}
+
 // one block: S per wave vector, the first maximum in list order wins
 __global__ void __launch_bounds__(1024)
 k_bragg_argmax(int n, int nk, const double *__restrict__ re, const double *__restrict__ im,
@@ -178,8 +242,10 @@ k_bragg_argmax(int n, int nk, const double *__restrict__ re, const double *__res
 
 }  // namespace
 
+// psi == nullptr: weights cos(k.d) (calculate_bond_order_pcf); else Re(conj(psi_i) psi_j)
+// (compute_g6_correlation)
 int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bins, double kx, double ky,
-                               unsigned long long *counts, unsigned long long *wsum)
+                               const double2 *psi, unsigned long long *counts, unsigned long long *wsum)
 {
     const int n = c->n;
     if (n < 2 || num_bins <= 0) return 0;
@@ -188,23 +254,25 @@ int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bin
     a.b = c->dbox;
     a.bin_width = dr; a.max_r = max_r; a.kx = kx; a.ky = ky;
     a.xy = reinterpret_cast<const double *>(c->xv);
-    a.counts = counts; a.wsum = wsum;
-    const size_t tile_bytes = kTile * sizeof(double2);
+    a.counts = counts; a.wsum = wsum; a.psi = psi;
+    auto kern = psi ? k_pcf_bond_order<kWeightPsi> : k_pcf_bond_order<kWeightCos>;
+    const size_t tile_bytes = 2 * kTile * sizeof(double2);
     const size_t hist_bytes = (size_t)num_bins * (sizeof(unsigned long long) + sizeof(unsigned int));
     a.use_smem = (tile_bytes + hist_bytes) <= 200 * 1024;
     const size_t smem = tile_bytes + (a.use_smem ? hist_bytes : 0);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_pcf_bond_order, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_pcf_bond_order<kWeightCos>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_pcf_bond_order<kWeightPsi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr = true;
     }
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_bond_order, kThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
     if (per_sm < 1) per_sm = 1;
     const long long nt = (n + kTile - 1) / kTile;
     long long grid = (long long)(c->sm_count > 0 ? c->sm_count : 148) * per_sm;
     if (grid > nt * (nt + 1) / 2) grid = nt * (nt + 1) / 2;
-    k_pcf_bond_order<<<(int)grid, kThreads, smem, c->stream>>>(a);
+    kern<<<(int)grid, kThreads, smem, c->stream>>>(a);
     return 1;
 }
 
@@ -229,4 +297,25 @@ int edmd_launch_bragg(edmd_ctx *c, int nk, const double2 *kvec, double *re, doub
     k_bragg_sums<<<dim3(kb, parts), kThreads, 0, c->stream>>>(a);
     k_bragg_argmax<<<1, 1024, 0, c->stream>>>(n, nk, re, im, best_s, best_i);
     return 2;
+}
+
+// S(q) sums on the grid qx[nqx] x qy[nqy] (device arrays); re / im [nqx*nqy] zeroed by the caller
+int edmd_launch_structure_factor(edmd_ctx *c, int velocity, int nqx, int nqy, const double *qx, const double *qy,
+                                 double *re, double *im)
+{
+    const int n = c->n, nk = nqx * nqy;
+    if (n < 1 || nk < 1) return 0;
+    SqArgs a;
+    a.n = n; a.nqx = nqx; a.nqy = nqy;
+    a.xv = c->xv; a.qx = qx; a.qy = qy; a.re = re; a.im = im;
+    const int kb = (nk + kThreads - 1) / kThreads;
+    int parts = (2 * (c->sm_count > 0 ? c->sm_count : 148) + kb - 1) / kb;
+    const int max_parts = (n + kTile - 1) / kTile;
+    if (parts > max_parts) parts = max_parts;
+    if (parts < 1) parts = 1;
+    a.chunk = (((n + parts - 1) / parts) + kTile - 1) / kTile * kTile;
+    parts = (n + a.chunk - 1) / a.chunk;
+    if (velocity) k_sq_sums<true><<<dim3(kb, parts), kThreads, 0, c->stream>>>(a);
+    else k_sq_sums<false><<<dim3(kb, parts), kThreads, 0, c->stream>>>(a);
+    return 1;
 }

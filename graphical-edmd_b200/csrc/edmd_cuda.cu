@@ -305,7 +305,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
                    c->lrec, c->lchunks, c->lres, c->lwork, c->cal_mem,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
-                   c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->boop, c->boop_nb,
+                   c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->vor_mem, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
     for (void *p : dev)
         if (p) cudaFree(p);
@@ -911,8 +911,8 @@ int edmd_cuda_pcf_bond_order(edmd_ctx *c, double dr, double max_r, const double 
     if (nb > 0) {
         CU(cudaMemsetAsync(c->pcf_counts, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
         CU(cudaMemsetAsync(c->pcf_wsum, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
-        c->launches += edmd_launch_pcf_bond_order(c, dr, max_r, nb, k_vector[0], k_vector[1], c->pcf_counts,
-                                                  c->pcf_wsum);
+        c->launches += edmd_launch_pcf_bond_order(c, dr, max_r, nb, k_vector[0], k_vector[1], nullptr,
+                                                  c->pcf_counts, c->pcf_wsum);
         CU(cudaGetLastError());
         if ((r = d2h(c, hc.data(), c->pcf_counts, (size_t)nb * sizeof(unsigned long long)))) return r;
         if ((r = d2h(c, hw.data(), c->pcf_wsum, (size_t)nb * sizeof(unsigned long long)))) return r;
@@ -994,6 +994,229 @@ int edmd_cuda_bragg_peak(edmd_ctx *c, double expected_bragg, double *k_out, doub
     return 0;
 }
 
+// ---- Voronoi family (analysis_voronoi.cu) -----------------------------------
+namespace {
+
+// scratch layout: [grid scratch | psi6 double2[N] | area f64[N] | perimeter f64[N] | fail i32[2]]
+int voronoi_scratch(edmd_ctx *c, char **grid, double2 **psi, double **area, double **perim, int32_t **failp)
+{
+    int gx, gy;
+    const size_t gbytes = (edmd_voronoi_scratch_bytes(c, &gx, &gy) + 255) / 256 * 256;
+    const size_t N = (size_t)(c->n > 0 ? c->n : 1);
+    const size_t need = gbytes + N * (sizeof(double2) + 2 * sizeof(double)) + 64;
+    if (need > c->vor_bytes) {
+        if (c->vor_mem) CU(cudaFree(c->vor_mem));
+        c->vor_mem = nullptr;
+        c->vor_bytes = 0;
+        CU(cudaMalloc((void **)&c->vor_mem, need));
+        c->vor_bytes = need;
+    }
+    *grid = c->vor_mem;
+    *psi = reinterpret_cast<double2 *>(c->vor_mem + gbytes);
+    *area = reinterpret_cast<double *>(*psi + N);
+    *perim = *area + N;
+    *failp = reinterpret_cast<int32_t *>(*perim + N);
+    return 0;
+}
+
+// runs K5 on the resident positions; results in c->boop / c->boop_nb and the scratch arrays
+int voronoi_run(edmd_ctx *c, bool boop, bool geom, double2 **psi_out, double **area_out, double **perim_out)
+{
+    if (c->slab) return fail(c, EDMD_ESTATE, "the Voronoi analysis needs a whole-system context");
+    char *grid = nullptr;
+    double2 *psi = nullptr;
+    double *area = nullptr, *perim = nullptr;
+    int32_t *failp = nullptr;
+    int r;
+    if ((r = voronoi_scratch(c, &grid, &psi, &area, &perim, &failp))) return r;
+    const size_t N = (size_t)c->n;
+    c->launches += edmd_launch_voronoi(c, grid, boop ? 1 : 0, c->boop, c->boop + N, c->boop + 2 * N, c->boop + 3 * N,
+                                       c->boop_nb, geom ? area : nullptr, geom ? perim : nullptr, failp);
+    CU(cudaGetLastError());
+    int32_t f[2] = {0, 0};
+    CU(cudaMemcpyAsync(f, failp, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (f[0] || f[1]) {
+        snprintf(c->err, sizeof(c->err),
+                 "Voronoi: %d cells not closed within the periodic box, %d cells with too many edges "
+                 "(system too small or too inhomogeneous for the local construction)", f[0], f[1]);
+        return EDMD_EVORONOI;
+    }
+    if (psi_out) *psi_out = psi;
+    if (area_out) *area_out = area;
+    if (perim_out) *perim_out = perim;
+    return 0;
+}
+
+}  // namespace
+
+int edmd_cuda_boop_voronoi(edmd_ctx *c, double *q5, double *q6, double *q7, double *q6_arg,
+                           int32_t *neighbors, double *mean_q6)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "boop before upload");
+    CU(cudaSetDevice(c->device));
+    int r;
+    if ((r = voronoi_run(c, true, false, nullptr, nullptr, nullptr))) return r;
+    size_t N = (size_t)c->n, B = N * sizeof(double);
+    if (mean_q6) c->launches += edmd_launch_mean(c, c->boop + N, c->n, c->red_partial + c->red_cap);
+    CU(cudaGetLastError());
+    if (q5 && (r = d2h(c, q5, c->boop, B))) return r;
+    if (q6 && (r = d2h(c, q6, c->boop + N, B))) return r;
+    if (q7 && (r = d2h(c, q7, c->boop + 2 * N, B))) return r;
+    if (q6_arg && (r = d2h(c, q6_arg, c->boop + 3 * N, B))) return r;
+    if (neighbors && (r = d2h(c, neighbors, c->boop_nb, N * sizeof(int32_t)))) return r;
+    if (mean_q6)
+        CU(cudaMemcpyAsync(mean_q6, c->red_partial + c->red_cap, sizeof(double),
+                           cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int edmd_cuda_voronoi_cells(edmd_ctx *c, double *area, double *perimeter, int32_t *neighbors)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "voronoi_cells before upload");
+    CU(cudaSetDevice(c->device));
+    int r;
+    double *d_area, *d_per;
+    if ((r = voronoi_run(c, false, true, nullptr, &d_area, &d_per))) return r;
+    const size_t N = (size_t)c->n;
+    if (area && (r = d2h(c, area, d_area, N * sizeof(double)))) return r;
+    if (perimeter && (r = d2h(c, perimeter, d_per, N * sizeof(double)))) return r;
+    if (neighbors && (r = d2h(c, neighbors, c->boop_nb, N * sizeof(int32_t)))) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// compute_g6_correlation, src/pcf.c:169-230
+int edmd_cuda_g6_correlation(edmd_ctx *c, double dr, double max_r, const double *psi_re, const double *psi_im,
+                             uint64_t *counts, double *g6_corr, int *num_bins)
+{
+    if (!c || !num_bins) return EDMD_EINVAL;
+    if (!(dr > 0) || !(max_r >= 0)) return fail(c, EDMD_EINVAL, "bad dr / max_r");
+    if ((psi_re == nullptr) != (psi_im == nullptr)) return fail(c, EDMD_EINVAL, "psi_re and psi_im go together");
+    double q = max_r / dr;
+    if (!(q < 1e8)) return fail(c, EDMD_EINVAL, "too many bins");
+    const int nb = (int)q;  // `(int)(max_r / dr)` src/pcf.c:170
+    *num_bins = nb;
+    if (!counts && !g6_corr) return 0;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "g6_correlation before upload");
+    if (c->slab) return fail(c, EDMD_ESTATE, "g6_correlation needs a whole-system context");
+    CU(cudaSetDevice(c->device));
+    int r;
+    const size_t N = (size_t)c->n;
+    double2 *psi = nullptr;
+    if (!psi_re) {
+        // `boop = computeBOOPVoronoi(...); psi6[i] = boop[i].q6 * cexp(I * boop[i].q6_arg)` :182-186
+        if ((r = voronoi_run(c, true, false, &psi, nullptr, nullptr))) return r;
+        c->launches += edmd_launch_psi6(c, c->boop + N, c->boop + 3 * N, psi);
+    } else {
+        char *grid = nullptr;
+        double *area = nullptr, *perim = nullptr;
+        int32_t *failp = nullptr;
+        if ((r = voronoi_scratch(c, &grid, &psi, &area, &perim, &failp))) return r;
+        std::vector<double2> h;
+        try {
+            h.resize(N);
+        } catch (...) {
+            return fail(c, EDMD_ENOMEM, "host staging allocation failed");
+        }
+        for (size_t i = 0; i < N; i++) h[i] = make_double2(psi_re[i], psi_im[i]);
+        if ((r = h2d(c, psi, h.data(), N * sizeof(double2)))) return r;
+        CU(cudaStreamSynchronize(c->stream));   // h goes out of scope below
+    }
+    if (nb > c->pcf_cap) {
+        if (c->pcf_counts) CU(cudaFree(c->pcf_counts));
+        c->pcf_counts = nullptr;
+        c->pcf_cap = 0;
+        if ((r = dev_alloc(c, &c->pcf_counts, (size_t)nb))) return r;
+        c->pcf_cap = nb;
+    }
+    if (nb > c->pcf_wcap) {
+        if (c->pcf_wsum) CU(cudaFree(c->pcf_wsum));
+        c->pcf_wsum = nullptr;
+        c->pcf_wcap = 0;
+        if ((r = dev_alloc(c, &c->pcf_wsum, (size_t)nb))) return r;
+        c->pcf_wcap = nb;
+    }
+    std::vector<unsigned long long> hc((size_t)(nb > 0 ? nb : 1)), hw((size_t)(nb > 0 ? nb : 1));
+    if (nb > 0) {
+        CU(cudaMemsetAsync(c->pcf_counts, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(c->pcf_wsum, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
+        c->launches += edmd_launch_pcf_bond_order(c, dr, max_r, nb, 0.0, 0.0, psi, c->pcf_counts, c->pcf_wsum);
+        CU(cudaGetLastError());
+        if ((r = d2h(c, hc.data(), c->pcf_counts, (size_t)nb * sizeof(unsigned long long)))) return r;
+        if ((r = d2h(c, hw.data(), c->pcf_wsum, (size_t)nb * sizeof(unsigned long long)))) return r;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < nb; i++) {   // :219-225
+        if (counts) counts[i] = hc[i];
+        if (g6_corr) g6_corr[i] = hc[i] ? ((double)(long long)hw[i] / 4294967296.0) / (double)hc[i] : 0.0;
+    }
+    return 0;
+}
+
+// initStructureFactor's grid (src/struc.c:328-345) + computeStructureFactor /
+// computeVelocityStructureFactor (:364-408)
+int edmd_cuda_structure_factor(edmd_ctx *c, double q_max, int velocity, int *nqx_out, int *nqy_out, double *qx,
+                               double *qy, double *s, double *re, double *im)
+{
+    if (!c || !nqx_out || !nqy_out) return EDMD_EINVAL;
+    if (!(q_max >= 0) || !(q_max < 1e3)) return fail(c, EDMD_EINVAL, "bad q_max");
+    const double xx = 2 * M_PI / c->box.lx, yy = 2 * M_PI / c->box.ly;
+    const double fx = 2 * q_max / xx + 1, fy = 2 * q_max / yy + 1;
+    if (!(fx * fy < 5e7)) return fail(c, EDMD_EINVAL, "too many wave vectors");
+    const int nqx = (int)fx, nqy = (int)fy;   // `nqx = 2*qmax/xx + 1` :331
+    *nqx_out = nqx;
+    *nqy_out = nqy;
+    std::vector<double> hq;
+    try {
+        hq.resize((size_t)nqx + nqy);
+    } catch (...) {
+        return fail(c, EDMD_ENOMEM, "host staging allocation failed");
+    }
+    for (int i = 0; i < nqx; i++) hq[i] = xx * (i - (nqx - 1) / 2);          // :338-340
+    for (int i = 0; i < nqy; i++) hq[(size_t)nqx + i] = yy * (i - (nqy - 1) / 2);
+    if (qx) memcpy(qx, hq.data(), (size_t)nqx * sizeof(double));
+    if (qy) memcpy(qy, hq.data() + nqx, (size_t)nqy * sizeof(double));
+    if (!s && !re && !im) return 0;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "structure_factor before upload");
+    if (c->slab) return fail(c, EDMD_ESTATE, "structure_factor needs a whole-system context");
+    CU(cudaSetDevice(c->device));
+    const size_t nk = (size_t)nqx * nqy;
+    double *scratch = nullptr;
+    CU(cudaMalloc((void **)&scratch, (2 * nk + nqx + nqy) * sizeof(double)));
+    double *d_re = scratch, *d_im = scratch + nk, *d_q = scratch + 2 * nk;
+    std::vector<double> hre, him;
+    cudaError_t e = cudaSuccess;
+    try {
+        hre.resize(nk);
+        him.resize(nk);
+    } catch (...) {
+        cudaFree(scratch);
+        return fail(c, EDMD_ENOMEM, "host staging allocation failed");
+    }
+    e = cudaMemcpyAsync(d_q, hq.data(), ((size_t)nqx + nqy) * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_re, 0, 2 * nk * sizeof(double), c->stream);
+    if (e == cudaSuccess) {
+        c->launches += edmd_launch_structure_factor(c, velocity, nqx, nqy, d_q, d_q + nqx, d_re, d_im);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hre.data(), d_re, nk * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(him.data(), d_im, nk * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return fail_cuda(c, e, "structure_factor");
+    for (size_t k = 0; k < nk; k++) {
+        if (re) re[k] = hre[k];
+        if (im) im[k] = him[k];
+        if (s) s[k] = (hre[k] * hre[k] + him[k] * him[k]) / c->n;   // :381
+    }
+    return 0;
+}
+
+
 int edmd_cuda_pcf_device(edmd_ctx *c, const double *xy_dev, int n_total, double dr, double max_r,
                          int part, int nparts, uint64_t *counts_dev, int *num_bins)
 {
@@ -1041,6 +1264,15 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
     }
     if (what == EDMD_BENCH_BOOP) {
         int r = ensure_index(c);
+        if (r) return r;
+    }
+    char *vgrid = nullptr;
+    double2 *vpsi = nullptr;
+    double *varea = nullptr, *vperim = nullptr;
+    int32_t *vfail = nullptr;
+    if (what == EDMD_BENCH_VORONOI) {
+        if (c->slab) return fail(c, EDMD_ESTATE, "the Voronoi analysis needs a whole-system context");
+        int r = voronoi_scratch(c, &vgrid, &vpsi, &varea, &vperim, &vfail);
         if (r) return r;
     }
     std::vector<cudaEvent_t> evs(3 * (size_t)iters);
@@ -1094,6 +1326,12 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
             c->launches += edmd_launch_pcf(c, dr, max_r, nb, reinterpret_cast<const double *>(c->xv), 4, c->n, 0, 1,
                                            c->pcf_counts);
             break;
+        case EDMD_BENCH_VORONOI: {
+            const size_t N = (size_t)c->n;
+            c->launches += edmd_launch_voronoi(c, vgrid, 1, c->boop, c->boop + N, c->boop + 2 * N, c->boop + 3 * N,
+                                               c->boop_nb, varea, vperim, vfail, e ? e[1] : nullptr);
+            break;
+        }
         default:
             return fail(c, EDMD_EINVAL, "bad bench id");
         }

@@ -227,6 +227,8 @@ struct edmd_ctx {
     unsigned long long *pcf_wsum;     // weighted sums (2^-32 fixed point), capacity pcf_wcap bins
     int pcf_wcap;
     int pcf_cap;
+    char *vor_mem;                    // Voronoi grid scratch (analysis_voronoi.cu) + psi6 + area/perimeter
+    size_t vor_bytes;
     double *boop;                     // 4*N doubles q5|q6|q7|arg
     int32_t *boop_nb;                 // N
     double *red_partial;              // block partials for deterministic sums
@@ -283,11 +285,17 @@ bool edmd_lean_eligible(const edmd_ctx *c, int mode);
 int edmd_launch_boop(edmd_ctx *c, double r_c);
 int edmd_launch_mean(edmd_ctx *c, const double *v, int n, double *out_dev);
 int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bins, double kx, double ky,
-                               unsigned long long *counts, unsigned long long *wsum);
+                               const double2 *psi, unsigned long long *counts, unsigned long long *wsum);
+int edmd_launch_structure_factor(edmd_ctx *c, int velocity, int nqx, int nqy, const double *qx, const double *qy,
+                                 double *re, double *im);
+size_t edmd_voronoi_scratch_bytes(const edmd_ctx *c, int *gx_out, int *gy_out);
+int edmd_launch_voronoi(edmd_ctx *c, char *scratch, int boop, double *q5, double *q6, double *q7, double *q6arg,
+                        int32_t *nbr, double *area, double *perim, int32_t *fail_dev, cudaEvent_t before_cells = nullptr);
+int edmd_launch_psi6(edmd_ctx *c, const double *q6, const double *arg, double2 *psi);
 int edmd_launch_bragg(edmd_ctx *c, int nk, const double2 *kvec, double *re, double *im, double *best_s,
                       int *best_i);
 int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
-                           int n, unsigned long long *counts);
+                           int n, int part, int nparts, unsigned long long *counts);
 int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
                     int n, int part, int nparts, unsigned long long *counts);
 

@@ -43,6 +43,7 @@ typedef struct edmd_ctx edmd_ctx;
 #define EDMD_ECELL 4     /* a cell id outside the grid */
 #define EDMD_ENOMEM 5
 #define EDMD_EPLAN 6     /* calendar_plan declined (a bucket too full): ingest event by event */
+#define EDMD_EVORONOI 7  /* a Voronoi cell could not be built locally (tiny or very inhomogeneous system) */
 
 /* prediction mode: which set of reference function pointers is emulated
  * (src/EDMD.c:1977-1989) */
@@ -223,6 +224,24 @@ int edmd_cuda_pcf_bond_order(edmd_ctx *ctx, double dr, double max_r, const doubl
  * reference's loop order wins.  s_max (optional) = that S(k). */
 int edmd_cuda_bragg_peak(edmd_ctx *ctx, double expected_bragg, double *k_out, double *s_max);
 
+/* Replaces compute_g6_correlation (src/pcf.c:169-230; caller save_g6_correlation
+ * :297-336): per-bin average of Re(conj(psi6_i) psi6_j) over the unordered pairs
+ * with r < max_r (g6_corr, 0 for empty bins) and the pair counts.  psi_re / psi_im
+ * [N] = the bond-orientational field to correlate; both NULL = the reference's
+ * choice, psi6_i = q6_i e^{i q6_arg_i} of the VORONOI neighbours (:182-186),
+ * computed on the device by the kernels behind edmd_cuda_boop_voronoi. */
+int edmd_cuda_g6_correlation(edmd_ctx *ctx, double dr, double max_r, const double *psi_re,
+                             const double *psi_im, uint64_t *counts, double *g6_corr, int *num_bins);
+/* Replaces initStructureFactor's wave-vector grid (src/struc.c:328-345; qx[i] =
+ * (2 pi/Lx)(i - (nqx-1)/2), nqx = (int)(2 q_max/(2 pi/Lx) + 1), same in y) and
+ * computeStructureFactor (velocity = 0) / computeVelocityStructureFactor
+ * (velocity = 1) (src/struc.c:364-408; caller saveStructureFactor :409-425) on the
+ * resident state: s[i*nqy + j] = |sum_n w_n e^{i q.r_n}|^2 / N; re / im = the sums
+ * themselves (the reference's structFactorComplex, doFQT).  With s, re and im all
+ * NULL only the grid is returned (qx / qy may be NULL too: sizes only). */
+int edmd_cuda_structure_factor(edmd_ctx *ctx, double q_max, int velocity, int *nqx, int *nqy,
+                               double *qx, double *qy, double *s, double *re, double *im);
+
 /* ---- calendar ingest plan ----------------------------------------------- */
 
 /* For the 2N events of the last sweep (event e = i: crossing of particle i at
@@ -275,6 +294,22 @@ int edmd_cuda_boop_cutoff(edmd_ctx *ctx, double r_c, double *q5, double *q6,
                           double *q7, double *q6_arg, int32_t *neighbors,
                           double *mean_q6);
 
+/* Replaces computeBOOPVoronoi (src/boop.c:15-59; callers saveTXT src/EDMD.c:5053-5056
+ * and saveThermo :5523-5525 with boopThermo == 1): psi_5,6,7 over the VORONOI
+ * neighbours of every particle in the periodic box.  The reference runs Fortune's
+ * sweep (jc_voronoi.h) over the particles plus the periodic images within 6.0 of
+ * the edges (get_particle_voronoi, src/voronoi_edmd.c:33-121); here every particle
+ * builds its own cell by clipping against the bisectors of its surroundings --
+ * the same diagram wherever it is unique.  Returns EDMD_EVORONOI when some cell
+ * cannot be closed locally (fewer than ~3 x 3 grid cells of particles, huge voids). */
+int edmd_cuda_boop_voronoi(edmd_ctx *ctx, double *q5, double *q6, double *q7, double *q6_arg,
+                           int32_t *neighbors, double *mean_q6);
+/* Replaces get_particle_voronoi_area / get_particle_voronoi_perimeter
+ * (src/voronoi_edmd.c:123-149; caller saveTXT src/EDMD.c:5061-5064 for the local
+ * packing fraction): area and perimeter of every particle's Voronoi cell, and
+ * its number of edges.  Any output may be NULL. */
+int edmd_cuda_voronoi_cells(edmd_ctx *ctx, double *area, double *perimeter, int32_t *neighbors);
+
 /* ---- measurement helpers (used by bench.py; timed with CUDA events on the
  * context's own stream, inputs resident in HBM) ------------------------ */
 
@@ -283,6 +318,7 @@ int edmd_cuda_boop_cutoff(edmd_ctx *ctx, double r_c, double *q5, double *q6,
 #define EDMD_BENCH_FREEFLY 1
 #define EDMD_BENCH_BOOP 2
 #define EDMD_BENCH_PCF 3    /* uses dr / max_r arguments */
+#define EDMD_BENCH_VORONOI 4 /* K5: grid sort + one Voronoi cell per particle (psi, area, perimeter) */
 
 /* Runs `warmup` untimed and `iters` timed passes of the chosen device path,
  * writing `flush_bytes` of scratch between passes (L2 flush, outside the timed

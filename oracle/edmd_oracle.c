@@ -482,3 +482,74 @@ void oracle_bragg_peak(int n, const double *x, const double *y, double lx, doubl
 	if (s_out)
 		*s_out = max_S;
 }
+
+/* pair loop of compute_g6_correlation, src/pcf.c:189-228 (same pair walk, min
+ * image and bin as calculate_pcf; `creal(conj(psi6[i]) * psi6[j])` :204). */
+int oracle_g6_correlation(const oracle_box *b, int n, const double *x, const double *y,
+                          const double *psi_re, const double *psi_im, double dr, double max_r,
+                          uint64_t *counts, double *g6_corr)
+{
+	int num_bins = oracle_pcf_num_bins(dr, max_r);
+	if (num_bins <= 0)
+		return num_bins;
+	memset(counts, 0, (size_t)num_bins * sizeof(uint64_t));
+	memset(g6_corr, 0, (size_t)num_bins * sizeof(double));
+	for (int i = 0; i < n; i++) {
+		for (int j = i + 1; j < n; j++) {
+			double dx = x[j] - x[i];
+			double dy = y[j] - y[i];
+			dx = min_image(dx, b->half_lx, b->lx);
+			dy = min_image(dy, b->half_ly, b->ly);
+			double r = sqrt(dx * dx + dy * dy);
+			if (r < max_r) {
+				int bin = (int)(r / dr);
+				if (bin >= 0 && bin < num_bins) {
+					g6_corr[bin] += psi_re[i] * psi_re[j] + psi_im[i] * psi_im[j];
+					counts[bin] += 1;
+				}
+			}
+		}
+	}
+	for (int i = 0; i < num_bins; i++) /* :219-225 */
+		g6_corr[i] = counts[i] ? g6_corr[i] / (double)counts[i] : 0.0;
+	return num_bins;
+}
+
+/* initStructureFactor, src/struc.c:328-345 (`nqx = 2*qmax/xx + 1` truncates) */
+void oracle_sq_grid(double q_max, double lx, double ly, int *nqx, int *nqy, double *qx, double *qy)
+{
+	double xx = 2 * M_PI / lx;
+	double yy = 2 * M_PI / ly;
+	*nqx = (int)(2 * q_max / xx + 1);
+	*nqy = (int)(2 * q_max / yy + 1);
+	if (qx)
+		for (int i = 0; i < *nqx; i++)
+			qx[i] = xx * (i - (*nqx - 1) / 2);
+	if (qy)
+		for (int i = 0; i < *nqy; i++)
+			qy[i] = yy * (i - (*nqy - 1) / 2);
+}
+
+/* computeStructureFactor :364-384 / computeVelocityStructureFactor :386-408 */
+void oracle_structure_factor(int n, const double *x, const double *y, const double *vx,
+                             const double *vy, int nqx, const double *qx, int nqy,
+                             const double *qy, int velocity, double *s)
+{
+#pragma omp parallel for collapse(2)
+	for (int i = 0; i < nqx; i++) {
+		for (int j = 0; j < nqy; j++) {
+			double im = 0, re = 0;
+			for (int k = 0; k < n; k++) {
+				double qr = qx[i] * x[k] + qy[j] * y[k];
+				if (velocity) {
+					re += vx[k] * cos(qr) + vy[k] * sin(qr);
+					im += vx[k] * sin(qr) - vy[k] * cos(qr);
+				} else {
+					re += cos(qr);
+					im += sin(qr);
+				}
+			}
+			s[i * nqy + j] = (re * re + im * im) / n;
+		}
+	}
+}

@@ -87,4 +87,20 @@ int oracle_bond_order_pcf(const oracle_box *b, int n, const double *x, const dou
 void oracle_bragg_peak(int n, const double *x, const double *y, double lx, double ly,
                        double expected_bragg, double *k_out, double *s_out);
 
+/* pair loop of compute_g6_correlation (src/pcf.c:189-228): per-bin average of
+ * Re(conj(psi6_i) psi6_j) over the unordered pairs with r < max_r; psi6 given
+ * (the reference takes it from computeBOOPVoronoi, :182-186).  counts as integers.
+ * Returns num_bins. */
+int oracle_g6_correlation(const oracle_box *b, int n, const double *x, const double *y,
+                          const double *psi_re, const double *psi_im, double dr, double max_r,
+                          uint64_t *counts, double *g6_corr);
+/* initStructureFactor's wave-vector grid (src/struc.c:328-345); qx / qy may be
+ * NULL to query the sizes. */
+void oracle_sq_grid(double q_max, double lx, double ly, int *nqx, int *nqy, double *qx, double *qy);
+/* computeStructureFactor / computeVelocityStructureFactor (src/struc.c:364-408):
+ * s[i*nqy + j] = |sum_n w_n e^{i q.r_n}|^2 / N. */
+void oracle_structure_factor(int n, const double *x, const double *y, const double *vx,
+                             const double *vy, int nqx, const double *qx, int nqy,
+                             const double *qy, int velocity, double *s);
+
 #endif

@@ -141,6 +141,94 @@ class Oracle:
                                    C.c_double(expected_bragg), _p(k), C.byref(s))
         return dict(k=k, s_max=s.value)
 
+    def g6_correlation(self, n, lx, ly, x, y, psi_re, psi_im, dr, max_r):
+        """Pair loop of compute_g6_correlation (src/pcf.c:189-228) for a given psi6."""
+        b = self.box(n, lx, ly)
+        x, y, pr, pi = map(_f64, (x, y, psi_re, psi_im))
+        nb = self.lib.oracle_pcf_num_bins(C.c_double(dr), C.c_double(max_r))
+        counts = np.zeros(max(nb, 1), np.uint64)
+        g6 = np.zeros(max(nb, 1), np.float64)
+        self.lib.oracle_g6_correlation(C.byref(b), n, _p(x), _p(y), _p(pr), _p(pi), C.c_double(dr),
+                                       C.c_double(max_r), _p(counts), _p(g6))
+        return dict(num_bins=nb, counts=counts[:nb], g6_corr=g6[:nb])
+
+    def sq_grid(self, q_max, lx, ly):
+        nqx, nqy = C.c_int(0), C.c_int(0)
+        f = self.lib.oracle_sq_grid
+        f(C.c_double(q_max), C.c_double(lx), C.c_double(ly), C.byref(nqx), C.byref(nqy), None, None)
+        qx, qy = np.zeros(max(nqx.value, 1)), np.zeros(max(nqy.value, 1))
+        f(C.c_double(q_max), C.c_double(lx), C.c_double(ly), C.byref(nqx), C.byref(nqy), _p(qx), _p(qy))
+        return qx[:nqx.value], qy[:nqy.value]
+
+    def structure_factor(self, n, lx, ly, x, y, q_max, vx=None, vy=None):
+        """computeStructureFactor (vx None) / computeVelocityStructureFactor, src/struc.c:364-408."""
+        qx, qy = self.sq_grid(q_max, lx, ly)
+        x, y, vx, vy = map(_f64, (x, y, vx, vy))
+        s = np.zeros(max(len(qx) * len(qy), 1), np.float64)
+        self.lib.oracle_structure_factor(n, _p(x), _p(y), _p(vx), _p(vy), len(qx), _p(qx), len(qy),
+                                         _p(qy), int(vx is not None), _p(s))
+        return dict(qx=qx, qy=qy, s=s[:len(qx) * len(qy)].reshape(len(qx), len(qy)))
+
+    # ---- Voronoi family.  The reference's algorithm is Fortune's sweep in the vendored
+    # jc_voronoi.h (src/jc_voronoi.h, patched to double :19-22); what it outputs is the
+    # Voronoi diagram of the point set built by get_particle_voronoi
+    # (src/voronoi_edmd.c:33-121).  The restatement builds THAT point set as written and
+    # takes the diagram from Qhull (scipy.spatial): Voronoi neighbours = Delaunay edges.
+    @staticmethod
+    def voronoi_points(n, lx, ly, x, y):
+        """Particles + periodic images within 6.0 of the box edges, in the
+        reference's order (src/voronoi_edmd.c:36-52, 63-111)."""
+        bd = 6.0
+        x, y = _f64(x)[:n], _f64(y)[:n]
+        px, py, src = [x], [y], [np.arange(n)]
+        # the reference appends, per particle, up to 8 images; the order of the
+        # appended points does not matter for the diagram
+        for cond, sx, sy in ((x < bd, lx, 0.0), (x > lx - bd, -lx, 0.0),
+                             (y < bd, 0.0, ly), (y > ly - bd, 0.0, -ly),
+                             ((x < bd) & (y < bd), lx, ly), ((x > lx - bd) & (y < bd), -lx, ly),
+                             ((x < bd) & (y > ly - bd), lx, -ly),
+                             ((x > lx - bd) & (y > ly - bd), -lx, -ly)):
+            idx = np.nonzero(cond)[0]
+            px.append(x[idx] + sx)
+            py.append(y[idx] + sy)
+            src.append(idx)
+        return np.concatenate(px), np.concatenate(py), np.concatenate(src)
+
+    def boop_voronoi(self, n, lx, ly, x, y):
+        """computeBOOPVoronoi, src/boop.c:15-59."""
+        from scipy.spatial import Delaunay
+        px, py, _ = self.voronoi_points(n, lx, ly, x, y)
+        tri = Delaunay(np.stack([px, py], axis=1))
+        indptr, indices = tri.vertex_neighbor_vertices
+        q5, q6, q7, arg = (np.zeros(n) for _ in range(4))
+        nbr = np.zeros(n, np.int32)
+        for i in range(n):
+            nb = indices[indptr[i]:indptr[i + 1]]
+            # `dx = e->neighbor->p.x - particles[index].x` :29-32 (image positions as built)
+            th = np.arctan2(py[nb] - py[i], px[nb] - px[i])
+            nbr[i] = len(nb)
+            if len(nb):
+                s5, s6, s7 = (np.exp(1j * k * th).sum() for k in (5, 6, 7))
+                q5[i], q6[i], q7[i] = abs(s5) / len(nb), abs(s6) / len(nb), abs(s7) / len(nb)
+                arg[i] = np.angle(s6)
+        return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nbr)
+
+    def voronoi_area(self, n, lx, ly, x, y):
+        """get_particle_voronoi_area / _perimeter, src/voronoi_edmd.c:123-149."""
+        from scipy.spatial import Voronoi
+        px, py, _ = self.voronoi_points(n, lx, ly, x, y)
+        vor = Voronoi(np.stack([px, py], axis=1))
+        area, per = np.zeros(n), np.zeros(n)
+        for i in range(n):
+            reg = vor.regions[vor.point_region[i]]
+            assert -1 not in reg and len(reg) >= 3
+            v = vor.vertices[reg] - np.array([px[i], py[i]])
+            v = v[np.argsort(np.arctan2(v[:, 1], v[:, 0]))]
+            w = np.roll(v, -1, axis=0)
+            area[i] = 0.5 * abs(np.sum(v[:, 0] * w[:, 1] - v[:, 1] * w[:, 0]))
+            per[i] = np.sum(np.hypot(w[:, 0] - v[:, 0], w[:, 1] - v[:, 1]))
+        return dict(area=area, perimeter=per)
+
 
 class Reference:
     """The unmodified reference behind ref_shim.c.  Holds global state: one
@@ -250,6 +338,42 @@ class Reference:
         self.lib.ref_bragg_peak.restype = C.c_double
         sec = self.lib.ref_bragg_peak(C.c_double(expected_bragg), _p(k))
         return dict(k=k, seconds=sec)
+
+    def boop_voronoi(self):
+        n = self.n
+        q5, q6, q7, arg = (np.empty(n, np.float64) for _ in range(4))
+        nb = np.empty(n, np.int32)
+        self.lib.ref_boop_voronoi.restype = C.c_double
+        sec = self.lib.ref_boop_voronoi(_p(q5), _p(q6), _p(q7), _p(arg), _p(nb))
+        return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, seconds=sec)
+
+    def voronoi_area(self):
+        area, per = np.empty(self.n), np.empty(self.n)
+        self.lib.ref_voronoi_area.restype = C.c_double
+        sec = self.lib.ref_voronoi_area(_p(area), _p(per))
+        return dict(area=area, perimeter=per, seconds=sec)
+
+    def g6_correlation(self, dr, max_r):
+        nb_guess = int(max_r / dr) + 2
+        g6 = np.zeros(nb_guess, np.float64)
+        cnt = np.zeros(nb_guess, np.int32)
+        nb = C.c_int(0)
+        self.lib.ref_g6_correlation.restype = C.c_double
+        sec = self.lib.ref_g6_correlation(C.c_double(dr), C.c_double(max_r), _p(g6), _p(cnt), C.byref(nb))
+        return dict(num_bins=nb.value, g6_corr=g6[:nb.value], counts=cnt[:nb.value].astype(np.uint64),
+                    seconds=sec)
+
+    def structure_factor(self, q_max, velocity=False, lx=None, ly=None):
+        cap = 4096
+        qx, qy = np.zeros(cap), np.zeros(cap)
+        nqx, nqy = C.c_int(0), C.c_int(0)
+        f = self.lib.ref_structure_factor
+        f.restype = C.c_double
+        f(C.c_double(q_max), int(velocity), C.byref(nqx), C.byref(nqy), _p(qx), _p(qy), None)
+        s = np.zeros(max(nqx.value * nqy.value, 1))
+        sec = f(C.c_double(q_max), int(velocity), C.byref(nqx), C.byref(nqy), _p(qx), _p(qy), _p(s))
+        return dict(qx=qx[:nqx.value].copy(), qy=qy[:nqy.value].copy(),
+                    s=s[:nqx.value * nqy.value].reshape(nqx.value, nqy.value), seconds=sec)
 
 
 def calendar_plan_oracle(t_cross, t_coll, paul_time, dt_paul, paul_n, actual_paul):

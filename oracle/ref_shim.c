@@ -329,3 +329,101 @@ double ref_bragg_peak(double expected_bragg, double *k_out)
 }
 
 int ref_num_particles(void) { return N; }
+
+/* computeBOOPVoronoi (src/boop.c:15-59): psi_k over the Voronoi neighbours
+ * (jc_voronoi on the particles plus the periodic images within 6.0 of the box
+ * edges, src/voronoi_edmd.c:33-121).  Returns seconds. */
+double ref_boop_voronoi(double *q5, double *q6, double *q7, double *q6_arg,
+                        int32_t *neighbors)
+{
+	double t0 = shim_now();
+	boop_data *b = computeBOOPVoronoi(particles, N, Lx, Ly);
+	double t1 = shim_now();
+	for (int i = 0; i < N; i++) {
+		if (q5)
+			q5[i] = b[i].q5;
+		if (q6)
+			q6[i] = b[i].q6;
+		if (q7)
+			q7[i] = b[i].q7;
+		if (q6_arg)
+			q6_arg[i] = b[i].q6_arg;
+		if (neighbors)
+			neighbors[i] = b[i].neighbors;
+	}
+	free(b);
+	return t1 - t0;
+}
+
+/* get_particle_voronoi_area / _perimeter (src/voronoi_edmd.c:123-149). */
+double ref_voronoi_area(double *area, double *perimeter)
+{
+	double t0 = shim_now();
+	if (area) {
+		double *a = get_particle_voronoi_area(particles, N, Lx, Ly);
+		memcpy(area, a, (size_t)N * sizeof(double));
+		free(a);
+	}
+	if (perimeter) {
+		double *p = get_particle_voronoi_perimeter(particles, N, Lx, Ly);
+		memcpy(perimeter, p, (size_t)N * sizeof(double));
+		free(p);
+	}
+	return shim_now() - t0;
+}
+
+/* compute_g6_correlation (src/pcf.c:169-230): <Re psi6_i^* psi6_j>(r) with the
+ * Voronoi psi6.  Returns seconds. */
+double ref_g6_correlation(double dr, double max_r, double *g6_corr, int32_t *counts,
+                          int *num_bins)
+{
+	double t0 = shim_now();
+	g6corr_data *d = compute_g6_correlation(particles, N, dr, max_r, Lx, Ly);
+	double t1 = shim_now();
+	*num_bins = d->num_bins;
+	for (int i = 0; i < d->num_bins; i++) {
+		if (g6_corr)
+			g6_corr[i] = d->g6_corr[i];
+		if (counts)
+			counts[i] = d->counts[i];
+	}
+	free(d->r);
+	free(d->g6_corr);
+	free(d->counts);
+	free(d);
+	return t1 - t0;
+}
+
+/* initStructureFactor's wave-vector grid (src/struc.c:328-345) +
+ * computeStructureFactor / computeVelocityStructureFactor (:364-408).
+ * s[i*nqy + j]; qx_out / qy_out hold at least 2*qmax/(2 pi/L) + 2 entries.
+ * Returns seconds of the compute call. */
+double ref_structure_factor(double q_max, int velocity, int *nqx_out, int *nqy_out,
+                            double *qx_out, double *qy_out, double *s)
+{
+	FILE *sink = fopen("/dev/null", "w");
+	structFactorComplex = NULL;
+	initStructureFactor(q_max, Lx, Ly, N, sink, 0);
+	*nqx_out = nqx;
+	*nqy_out = nqy;
+	for (int i = 0; i < nqx; i++)
+		qx_out[i] = qx[i];
+	for (int j = 0; j < nqy; j++)
+		qy_out[j] = qy[j];
+	double t0 = shim_now();
+	if (s) {
+		if (velocity)
+			computeVelocityStructureFactor(particles);
+		else
+			computeStructureFactor(particles);
+	}
+	double t1 = shim_now();
+	if (s)
+		memcpy(s, structFactor, (size_t)nqx * nqy * sizeof(double));
+	free(qx);
+	free(qy);
+	free(structFactor);
+	qx = qy = structFactor = NULL;
+	fclose(sink);
+	return t1 - t0;
+}

@@ -20,6 +20,12 @@ from oracle.oracle_py import Reference  # noqa: E402
 
 pkg = entry.load_package()
 ref = Reference()
+ONLY = set(sys.argv[1:])   # e.g. `make_golden.py voronoi` regenerates only that family
+
+
+def want(family):
+    return not ONLY or family in ONLY
+
 
 
 def sweep_case(name, cfg, t, grow=False, with_analysis=True, pcf_max_r=None):
@@ -57,21 +63,26 @@ def sweep_case(name, cfg, t, grow=False, with_analysis=True, pcf_max_r=None):
     print("wrote", name, "n =", n)
 
 
-# BASELINE config 1 flavour: N=2000, phi=0.7, 30 % small disks (reference CLI defaults)
-sweep_case("sweep_n2000_phi070_bidisperse",
-           pkg.synth.lattice_config(2000, 0.70, seed=1, small_fraction=0.3), t=0.0)
-# dense monodisperse, non-zero sweep time
-sweep_case("sweep_n3000_phi085_mono",
-           pkg.synth.lattice_config(3000, 0.85, seed=2), t=17.25)
-# lattice order (ids correlated with position), near liquid-hexatic density
-sweep_case("sweep_n2500_phi072_ordered",
-           pkg.synth.lattice_config(2500, 0.72, seed=3, shuffle=False), t=3.0)
-# growth mode (setup sweep)
-g = pkg.synth.growth_config(2000, 0.70, seed=4)
-rng = np.random.default_rng(4)
-g["vr"] = g["vr"] * (0.5 + rng.random(g["n"]))
-g["rad"] = g["rad"] * (0.7 + 0.3 * rng.random(g["n"]))
-sweep_case("sweep_n2000_grow", g, t=g["t"], grow=True)
+def sweep_cases():
+    # BASELINE config 1 flavour: N=2000, phi=0.7, 30 % small disks (reference CLI defaults)
+    sweep_case("sweep_n2000_phi070_bidisperse",
+               pkg.synth.lattice_config(2000, 0.70, seed=1, small_fraction=0.3), t=0.0)
+    # dense monodisperse, non-zero sweep time
+    sweep_case("sweep_n3000_phi085_mono",
+               pkg.synth.lattice_config(3000, 0.85, seed=2), t=17.25)
+    # lattice order (ids correlated with position), near liquid-hexatic density
+    sweep_case("sweep_n2500_phi072_ordered",
+               pkg.synth.lattice_config(2500, 0.72, seed=3, shuffle=False), t=3.0)
+    # growth mode (setup sweep)
+    g = pkg.synth.growth_config(2000, 0.70, seed=4)
+    rng = np.random.default_rng(4)
+    g["vr"] = g["vr"] * (0.5 + rng.random(g["n"]))
+    g["rad"] = g["rad"] * (0.7 + 0.3 * rng.random(g["n"]))
+    sweep_case("sweep_n2000_grow", g, t=g["t"], grow=True)
+
+
+if want("sweep"):
+    sweep_cases()
 
 
 def weighted_case(name, cfg, dr, max_r):
@@ -90,7 +101,56 @@ def weighted_case(name, cfg, dr, max_r):
     print("wrote", name, "n =", n, "k =", k)
 
 
-weighted_case("weighted_n1500_phi072", pkg.synth.lattice_config(1500, 0.72, seed=5), 2.0, 30.0)
-weighted_case("weighted_n1200_phi060_bidisperse",
-              pkg.synth.lattice_config(1200, 0.60, seed=6, small_fraction=0.3), 0.5, 20.0)
+if want("weighted"):
+    weighted_case("weighted_n1500_phi072", pkg.synth.lattice_config(1500, 0.72, seed=5), 2.0, 30.0)
+    weighted_case("weighted_n1200_phi060_bidisperse",
+                  pkg.synth.lattice_config(1200, 0.60, seed=6, small_fraction=0.3), 0.5, 20.0)
+
+
+def voronoi_case(name, cfg, dr, q_max):
+    """The Voronoi family and the structure factor:
+    computeBOOPVoronoi, get_particle_voronoi_area/_perimeter, compute_g6_correlation,
+    computeStructureFactor / computeVelocityStructureFactor, from the reference."""
+    n, lx, ly = cfg["n"], cfg["lx"], cfg["ly"]
+    ref.setup(n, lx, ly, 0.0, cfg["x"], cfg["y"], cfg["vx"], cfg["vy"], cfg["rad"])
+    b = ref.boop_voronoi()
+    a = ref.voronoi_area()
+    max_r = min(lx, ly) / 2
+    g6 = ref.g6_correlation(dr, max_r)
+    sp = ref.structure_factor(q_max, velocity=False)
+    sv = ref.structure_factor(q_max, velocity=True)
+    np.savez_compressed(HERE / f"{name}.npz", n=n, lx=lx, ly=ly, x=cfg["x"], y=cfg["y"], vx=cfg["vx"],
+                        vy=cfg["vy"], rad=cfg["rad"],
+                        vor_q5=b["q5"], vor_q6=b["q6"], vor_q7=b["q7"], vor_q6_arg=b["q6_arg"],
+                        vor_neighbors=b["neighbors"], vor_area=a["area"], vor_perimeter=a["perimeter"],
+                        g6_dr=dr, g6_max_r=max_r, g6_corr=g6["g6_corr"], g6_counts=g6["counts"],
+                        sq_qmax=q_max, sq_qx=sp["qx"], sq_qy=sp["qy"], sq_s=sp["s"], sq_s_velocity=sv["s"])
+    print("wrote", name, "n =", n, "neighbours", np.bincount(b["neighbors"]))
+
+
+def point_config(n, lx, ly, seed, jitter=None):
+    """Positions only matter for this family (no overlap checks in the analysis
+    functions): Poisson points (jitter None) or a square lattice with a large
+    uniform jitter in units of the spacing -- many 5/7-fold and rarer 4/8-fold cells."""
+    rng = np.random.default_rng(seed)
+    if jitter is None:
+        x, y = rng.random(n) * lx, rng.random(n) * ly
+    else:
+        m = int(round(np.sqrt(n)))
+        n = m * m
+        gx, gy = np.meshgrid(np.arange(m), np.arange(m))
+        x = ((gx.ravel() + 0.5 + jitter * (rng.random(n) - 0.5)) * lx / m) % lx
+        y = ((gy.ravel() + 0.5 + jitter * (rng.random(n) - 0.5)) * ly / m) % ly
+        p = rng.permutation(n)
+        x, y = x[p], y[p]
+    return dict(n=n, lx=lx, ly=ly, x=x, y=y, vx=rng.standard_normal(n), vy=rng.standard_normal(n),
+                rad=np.full(n, 0.05))
+
+
+if want("voronoi"):
+    # dense nearly ordered monodisperse disks (every cell six-sided), a strongly
+    # disordered lattice, and Poisson points (cells with 3 to 12 sides, big voids)
+    voronoi_case("voronoi_n1500_phi085", pkg.synth.lattice_config(1500, 0.85, seed=8), 1.0, 0.8)
+    voronoi_case("voronoi_n2025_jittered", point_config(2025, 97.0, 88.0, seed=7, jitter=0.9), 0.5, 1.0)
+    voronoi_case("voronoi_n1500_poisson", point_config(1500, 80.0, 70.0, seed=9), 1.0, 0.5)
 ref.teardown()

@@ -64,3 +64,25 @@ def pcf_counts_from_g(g_r, n, lx, ly, dr):
     ci = np.rint(c)
     assert np.abs(c - ci).max() < 1e-6
     return ci.astype(np.uint64)
+
+
+VORONOI_CASES = ["voronoi_n1500_phi085", "voronoi_n2025_jittered", "voronoi_n1500_poisson"]
+VORONOI_GEOM_ATOL = 1e-9   # area / perimeter: the reference sums cross products of absolute coordinates
+
+
+def random_points(n, lx, ly, seed, jitter=None):
+    """Point configurations for the Voronoi / S(q) family (radii are irrelevant to
+    it): Poisson points, or a square lattice with a large jitter (units of the spacing)."""
+    rng = np.random.default_rng(seed)
+    if jitter is None:
+        x, y = rng.random(n) * lx, rng.random(n) * ly
+    else:
+        m = int(round(np.sqrt(n)))
+        n = m * m
+        gx, gy = np.meshgrid(np.arange(m), np.arange(m))
+        x = ((gx.ravel() + 0.5 + jitter * (rng.random(n) - 0.5)) * lx / m) % lx
+        y = ((gy.ravel() + 0.5 + jitter * (rng.random(n) - 0.5)) * ly / m) % ly
+        p = rng.permutation(n)
+        x, y = x[p], y[p]
+    return dict(n=n, lx=lx, ly=ly, x=x, y=y, vx=rng.standard_normal(n), vy=rng.standard_normal(n),
+                rad=np.full(n, 0.05))

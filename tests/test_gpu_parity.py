@@ -376,6 +376,31 @@ def test_pcf_counts_every_pair_once(pkg):
     assert p["counts"][: int(1.99 / 0.1)].sum() == 0
 
 
+@pytest.mark.parametrize("n,phi,seed,dr,frac,nparts", [(60000, 0.70, 91, 0.1, 0.5, 3), (40000, 0.85, 92, 0.05, 0.25, 2),
+                                                       (5000, 0.70, 93, 0.1, 0.5, 2)])
+def test_pcf_rank_shares_sum_to_the_whole(pkg, oracle, n, phi, seed, dr, frac, nparts):
+    """Multi-GPU split of g(r) (edmd_cuda_pcf_device): every rank sorts the
+    all-gathered positions itself and takes the tile pairs w = rank (mod nparts), so
+    the sort must cut the same tiles on every rank.  Each share here comes from its
+    own context (its own atomic arrival order); the shares must add up to the
+    oracle's counts."""
+    import torch
+    c = pkg.synth.lattice_config(n, phi, seed)
+    max_r = min(c["lx"], c["ly"]) * frac
+    xy = torch.from_numpy(np.stack([c["x"], c["y"]], axis=1).copy()).cuda()
+    nb = int(max_r / dr)
+    total = torch.zeros(nb, dtype=torch.int64, device="cuda")
+    for part in range(nparts):
+        share = torch.zeros(nb, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+            assert ctx.pcf_device(xy.data_ptr(), c["n"], dr, max_r, part, nparts, share.data_ptr()) == nb
+        assert int(share.sum()) > 0
+        total += share
+    want = oracle.pcf(c["n"], c["lx"], c["ly"], c["x"], c["y"], dr, max_r)
+    assert np.array_equal(total.cpu().numpy().astype(np.uint64), want["counts"])
+
+
 # -------------------------------------------------- weighted g(r) family ----
 @pytest.mark.parametrize("name", ["weighted_n1500_phi072", "weighted_n1200_phi060_bidisperse"])
 def test_weighted_pcf_family_matches_reference_golden(pkg, name):
@@ -633,3 +658,122 @@ def test_dense_small_disks_overflow_the_tile_buffer(pkg, oracle):
         ctx.upload(x, y, vx, vy, rad, t=0.25)
         b = ctx.boop_cutoff(0.5)
     assert_boop_close(b, oracle.boop_cutoff(n, lx, ly, x, y, 0.5))
+
+
+# ------------------------------------ Voronoi family, g6 correlation, S(q) ----
+from helpers import VORONOI_CASES, VORONOI_GEOM_ATOL, random_points  # noqa: E402
+
+
+def _upload_points(pkg, c):
+    ctx = pkg.EdmdCuda(c["n"], c["lx"], c["ly"])
+    ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+    return ctx
+
+
+@pytest.mark.parametrize("name", VORONOI_CASES)
+def test_voronoi_family_matches_reference_golden(pkg, name):
+    """K5 (one locally clipped Voronoi cell per particle) against the reference's
+    global jc_voronoi diagram: neighbour counts exact, psi within 1e-10; cell area
+    and perimeter; g6 correlation with the device's own Voronoi psi6 and with the
+    reference's psi6 handed in."""
+    g = load_golden(name)
+    c = dict(n=int(g["n"]), lx=float(g["lx"]), ly=float(g["ly"]), x=g["x"], y=g["y"], vx=g["vx"], vy=g["vy"],
+             rad=g["rad"])
+    with _upload_points(pkg, c) as ctx:
+        b = ctx.boop_voronoi()
+        cells = ctx.voronoi_cells()
+        g6 = ctx.g6_correlation(float(g["g6_dr"]), float(g["g6_max_r"]))
+        g6b = ctx.g6_correlation(float(g["g6_dr"]), float(g["g6_max_r"]),
+                                 g["vor_q6"] * np.cos(g["vor_q6_arg"]), g["vor_q6"] * np.sin(g["vor_q6_arg"]))
+    assert_boop_close(b, g, prefix="vor_")
+    assert abs(b["mean_q6"] - g["vor_q6"].mean()) <= ANALYSIS_ATOL
+    assert np.array_equal(cells["neighbors"], g["vor_neighbors"])
+    assert np.abs(cells["area"] - g["vor_area"]).max() <= VORONOI_GEOM_ATOL
+    assert np.abs(cells["perimeter"] - g["vor_perimeter"]).max() <= VORONOI_GEOM_ATOL
+    for r in (g6, g6b):
+        assert np.array_equal(r["counts"], g["g6_counts"])
+        assert np.abs(r["g6_corr"] - g["g6_corr"]).max() <= ANALYSIS_ATOL
+
+
+@pytest.mark.parametrize("name", VORONOI_CASES)
+def test_structure_factor_matches_reference_golden(pkg, name):
+    g = load_golden(name)
+    c = dict(n=int(g["n"]), lx=float(g["lx"]), ly=float(g["ly"]), x=g["x"], y=g["y"], vx=g["vx"], vy=g["vy"],
+             rad=g["rad"])
+    with _upload_points(pkg, c) as ctx:
+        s = ctx.structure_factor(float(g["sq_qmax"]))
+        v = ctx.structure_factor(float(g["sq_qmax"]), velocity=True)
+    assert np.array_equal(s["qx"], g["sq_qx"]) and np.array_equal(s["qy"], g["sq_qy"])
+    assert (np.abs(s["s"] - g["sq_s"]) / np.maximum(1.0, g["sq_s"])).max() <= ANALYSIS_ATOL
+    assert (np.abs(v["s"] - g["sq_s_velocity"]) / np.maximum(1.0, g["sq_s_velocity"])).max() <= ANALYSIS_ATOL
+    assert np.abs(s["s"] - (s["re"] ** 2 + s["im"] ** 2) / c["n"]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("kind,n,seed", [("liquid", 40000, 21), ("poisson", 30000, 22), ("jitter", 40000, 23),
+                                         ("dense", 30000, 24)])
+def test_voronoi_family_matches_oracle(pkg, oracle, kind, n, seed):
+    if kind == "liquid":
+        c = pkg.synth.lattice_config(n, 0.70, seed=seed, small_fraction=0.3)
+    elif kind == "dense":
+        c = pkg.synth.lattice_config(n, 0.88, seed=seed)
+    elif kind == "poisson":
+        c = random_points(n, 310.0, 290.0, seed)
+    else:
+        c = random_points(n, 400.0, 380.0, seed, jitter=0.95)
+    n, lx, ly = c["n"], c["lx"], c["ly"]
+    with _upload_points(pkg, c) as ctx:
+        b = ctx.boop_voronoi()
+        b2 = ctx.boop_voronoi()
+        cells = ctx.voronoi_cells()
+    want = oracle.boop_voronoi(n, lx, ly, c["x"], c["y"])
+    assert_boop_close(b, want)
+    assert b["neighbors"].sum() == 6 * n
+    for k in ("q5", "q6", "q7", "q6_arg", "neighbors"):      # reproducible bit for bit
+        assert np.array_equal(b[k], b2[k]), k
+    wa = oracle.voronoi_area(n, lx, ly, c["x"], c["y"])
+    assert np.abs(cells["area"] - wa["area"]).max() <= VORONOI_GEOM_ATOL
+    assert np.abs(cells["perimeter"] - wa["perimeter"]).max() <= VORONOI_GEOM_ATOL
+    assert abs(cells["area"].sum() - lx * ly) <= 1e-10 * lx * ly   # the cells tile the periodic box
+
+
+def test_voronoi_cells_tile_the_box_at_full_size(pkg):
+    """Size-independent checks at N = 10^6: the cells tile the box, and a periodic
+    triangulation has exactly 3N edges (mean coordination 6)."""
+    c = pkg.synth.lattice_config(1000000, 0.70, seed=31)
+    with _upload_points(pkg, c) as ctx:
+        cells = ctx.voronoi_cells()
+        b = ctx.boop_voronoi()
+    assert int(cells["neighbors"].sum()) == 6 * c["n"]
+    assert abs(cells["area"].sum() - c["lx"] * c["ly"]) <= 1e-10 * c["lx"] * c["ly"]
+    assert np.array_equal(b["neighbors"], cells["neighbors"])
+    assert 0.0 < b["mean_q6"] <= 1.0
+
+
+def test_voronoi_declines_systems_too_small_to_close_locally(pkg):
+    x = np.array([1.0, 4.0, 2.5, 7.0])
+    y = np.array([1.0, 2.0, 6.0, 7.5])
+    with pkg.EdmdCuda(4, 9.0, 9.0) as ctx:
+        ctx.upload(x, y, np.zeros(4), np.zeros(4), np.full(4, 0.1), t=0.0)
+        with pytest.raises(pkg.EdmdError) as e:
+            ctx.boop_voronoi()
+    assert e.value.code == pkg.binding.EVORONOI
+
+
+@pytest.mark.parametrize("n,seed,qmax", [(20000, 41, 0.6), (3000, 42, 2.0)])
+def test_structure_factor_and_g6_match_oracle(pkg, oracle, n, seed, qmax):
+    c = pkg.synth.lattice_config(n, 0.72, seed=seed)
+    n, lx, ly = c["n"], c["lx"], c["ly"]
+    rng = np.random.default_rng(seed)
+    psi = rng.standard_normal((2, n)) * 0.5
+    with _upload_points(pkg, c) as ctx:
+        s = ctx.structure_factor(qmax)
+        v = ctx.structure_factor(qmax, velocity=True)
+        g6 = ctx.g6_correlation(0.25, min(lx, ly) / 2, psi[0], psi[1])
+    ws = oracle.structure_factor(n, lx, ly, c["x"], c["y"], qmax)
+    wv = oracle.structure_factor(n, lx, ly, c["x"], c["y"], qmax, c["vx"], c["vy"])
+    assert np.array_equal(s["qx"], ws["qx"]) and np.array_equal(s["qy"], ws["qy"])
+    assert (np.abs(s["s"] - ws["s"]) / np.maximum(1.0, ws["s"])).max() <= ANALYSIS_ATOL
+    assert (np.abs(v["s"] - wv["s"]) / np.maximum(1.0, wv["s"])).max() <= ANALYSIS_ATOL
+    wg = oracle.g6_correlation(n, lx, ly, c["x"], c["y"], psi[0], psi[1], 0.25, min(lx, ly) / 2)
+    assert np.array_equal(g6["counts"], wg["counts"])
+    assert np.abs(g6["g6_corr"] - wg["g6_corr"]).max() <= ANALYSIS_ATOL

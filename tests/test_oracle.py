@@ -131,3 +131,43 @@ def test_oracle_weighted_pcf_family_matches_golden(oracle, name):
     # plain g(r) of the same snapshot: same counts
     p = oracle.pcf(n, lx, ly, g["x"], g["y"], float(g["dr"]), float(g["max_r"]))
     assert np.array_equal(p["counts"], bo["counts"])
+
+
+from helpers import VORONOI_CASES, VORONOI_GEOM_ATOL  # noqa: E402
+
+
+@pytest.mark.parametrize("name", VORONOI_CASES)
+def test_oracle_voronoi_family_matches_golden(oracle, name):
+    """computeBOOPVoronoi, Voronoi cell area / perimeter, compute_g6_correlation
+    (src/boop.c:15-59, src/voronoi_edmd.c:33-149, src/pcf.c:169-230): the restatement
+    (the reference's image-augmented point set, diagram from Qhull) against the
+    reference's own outputs (jc_voronoi)."""
+    g = load_golden(name)
+    n, lx, ly = int(g["n"]), float(g["lx"]), float(g["ly"])
+    b = oracle.boop_voronoi(n, lx, ly, g["x"], g["y"])
+    assert_boop_close(b, g, prefix="vor_")
+    assert b["neighbors"].sum() == 6 * n          # Euler: a periodic triangulation has 3N edges
+    a = oracle.voronoi_area(n, lx, ly, g["x"], g["y"])
+    assert np.abs(a["area"] - g["vor_area"]).max() <= VORONOI_GEOM_ATOL
+    assert np.abs(a["perimeter"] - g["vor_perimeter"]).max() <= VORONOI_GEOM_ATOL
+    assert abs(a["area"].sum() - lx * ly) <= 1e-9 * lx * ly
+    psi_re, psi_im = b["q6"] * np.cos(b["q6_arg"]), b["q6"] * np.sin(b["q6_arg"])
+    c = oracle.g6_correlation(n, lx, ly, g["x"], g["y"], psi_re, psi_im, float(g["g6_dr"]), float(g["g6_max_r"]))
+    assert np.array_equal(c["counts"], g["g6_counts"])
+    assert np.abs(c["g6_corr"] - g["g6_corr"]).max() <= ANALYSIS_ATOL
+
+
+@pytest.mark.parametrize("name", VORONOI_CASES)
+def test_oracle_structure_factor_matches_golden(oracle, name):
+    """initStructureFactor's grid + computeStructureFactor / computeVelocityStructureFactor
+    (src/struc.c:328-345, 364-408)."""
+    g = load_golden(name)
+    n, lx, ly = int(g["n"]), float(g["lx"]), float(g["ly"])
+    s = oracle.structure_factor(n, lx, ly, g["x"], g["y"], float(g["sq_qmax"]))
+    assert np.array_equal(s["qx"], g["sq_qx"]) and np.array_equal(s["qy"], g["sq_qy"])
+    assert s["s"].shape == g["sq_s"].shape
+    assert (np.abs(s["s"] - g["sq_s"]) / np.maximum(1.0, g["sq_s"])).max() <= ANALYSIS_ATOL
+    i0, j0 = (len(s["qx"]) - 1) // 2, (len(s["qy"]) - 1) // 2
+    assert s["s"][i0, j0] == n                       # q = 0: S = N
+    v = oracle.structure_factor(n, lx, ly, g["x"], g["y"], float(g["sq_qmax"]), g["vx"], g["vy"])
+    assert (np.abs(v["s"] - g["sq_s_velocity"]) / np.maximum(1.0, g["sq_s_velocity"])).max() <= ANALYSIS_ATOL

@@ -51,6 +51,10 @@ static double phi = 0.38, sizeratio = 0.4, fractionSmallN = 0.3, aspectRatio = 1
 static double tmax = 4000, dtime = 100, dtimeThermo = 100, firstScreen = 1, firstThermo = 1;
 static double T = 1.0, dtnoise = 0.5;
 static int noise = 0, seed = 1, boopThermo = 0, pcfThermo = 0, verify = 0, quiet = 0;
+/* more of the reference's analysis switches (src/EDMD.c:223-231): areaThermo = Voronoi packing-fraction
+ * column, strucThermo = S(q) mode (1 positions, 2.. = 0 velocity as saveStructureFactor's `mode`), pcfg6Thermo */
+static int areaThermo = 0, strucThermo = 0, pcfg6Thermo = 0;
+static double qmax = 0.3; /* src/EDMD.c:225 */
 static int init_grow = 1, growing = 0;
 static int bulk_ingest = 1;   /* --ingest bulk|seq: calendar rebuilt from the GPU's ingest plan / event by event */
 static double vr = 0.1;
@@ -557,7 +561,8 @@ static void do_noise(void)
 	schedule_special(2, EV_NOISE, t + dtnoise);
 }
 
-static FILE *fdump, *fthermo, *fpcf;
+static FILE *fdump, *fthermo, *fpcf, *fstruc;
+static char pcfg6Name[600];
 
 static void do_screenshot(void)
 {
@@ -565,25 +570,35 @@ static void do_screenshot(void)
 	schedule_special(1, EV_SCREENSHOT, t + dtime);
 	double *q5 = NULL, *q6 = NULL, *q7 = NULL, *qa = NULL;
 	int32_t *nb = NULL;
+	double *area = NULL;
+	if (boopThermo || areaThermo) gpu_upload();
 	if (boopThermo) {
 		q5 = malloc(sizeof(double) * N); q6 = malloc(sizeof(double) * N); q7 = malloc(sizeof(double) * N);
 		qa = malloc(sizeof(double) * N); nb = malloc(sizeof(int32_t) * N);
-		gpu_upload();
-		int rc = edmd_cuda_boop_cutoff(gpu, 2.5, q5, q6, q7, qa, nb, NULL);
-		if (rc) die_gpu(rc, "edmd_cuda_boop_cutoff");
+		/* `boopThermo == 1` Voronoi neighbours, `== 2` cutoff 2.5, src/EDMD.c:5053-5060 */
+		int rc = boopThermo == 1 ? edmd_cuda_boop_voronoi(gpu, q5, q6, q7, qa, nb, NULL)
+		                         : edmd_cuda_boop_cutoff(gpu, 2.5, q5, q6, q7, qa, nb, NULL);
+		if (rc) die_gpu(rc, boopThermo == 1 ? "edmd_cuda_boop_voronoi" : "edmd_cuda_boop_cutoff");
+	}
+	if (areaThermo) { /* get_particle_voronoi_area, src/EDMD.c:5061-5064 */
+		area = malloc(sizeof(double) * N);
+		int rc = edmd_cuda_voronoi_cells(gpu, area, NULL, NULL);
+		if (rc) die_gpu(rc, "edmd_cuda_voronoi_cells");
 	}
 	/* byte format of saveTXT, src/EDMD.c:5052-5069, row :5124-5134 */
 	fprintf(fdump, "ITEM: TIMESTEP\n%lf\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n0 %lf\n0 %lf\n0 0\nITEM: ATOMS id type x y vx vy radius m coll",
 	        t, N, Lx, Ly);
 	if (boopThermo) fprintf(fdump, " q5 q6 q7 argq6 neighbors");
+	if (areaThermo) fprintf(fdump, " packingFraction");
 	fprintf(fdump, "\n");
 	for (int i = 0; i < N; i++) {
 		fprintf(fdump, "%d %d %.3lf %lf %lf %lf %lf %lf %d", i, ptype[i], px[i], py[i], pvx[i], pvy[i], prad[i], 1.0, ptype[i]);
 		if (boopThermo) fprintf(fdump, " %.2lf %.2lf %.2lf %.2lf %d", q5[i], q6[i], q7[i], qa[i], nb[i]);
+		if (areaThermo) fprintf(fdump, " %lf", M_PI * prad[i] * prad[i] / area[i]); /* :5131-5133 */
 		fprintf(fdump, "\n");
 	}
 	fflush(fdump);
-	free(q5); free(q6); free(q7); free(qa); free(nb);
+	free(q5); free(q6); free(q7); free(qa); free(nb); free(area);
 	if (!quiet) printf("t = %-10.3lf collisions = %-12lu E/N = %.6lf\n", t, ncol, kinetic_energy() / N);
 }
 
@@ -614,6 +629,41 @@ static void do_thermo(void)
 		for (int b = 0; b < nbins; b++) fprintf(fpcf, "%lf %lf %lf\n", t, (b + 0.5) * dr, g[b]);
 		fflush(fpcf);
 		free(cnt); free(g);
+	}
+	if (strucThermo || pcfg6Thermo) {
+		for (int i = 0; i < N; i++) free_fly(i);
+		gpu_upload();
+	}
+	if (strucThermo) { /* saveStructureFactor(particles, strucThermo), src/struc.c:409-425: mode 0 = velocity */
+		int nqx = 0, nqy = 0;
+		edmd_cuda_structure_factor(gpu, qmax, 0, &nqx, &nqy, NULL, NULL, NULL, NULL, NULL);
+		double *sq = malloc(sizeof(double) * (size_t)(nqx * nqy > 0 ? nqx * nqy : 1));
+		int rc = edmd_cuda_structure_factor(gpu, qmax, strucThermo == 2, &nqx, &nqy, NULL, NULL, sq, NULL, NULL);
+		if (rc) die_gpu(rc, "edmd_cuda_structure_factor");
+		for (int i = 0; i < nqx; i++) {
+			for (int j = 0; j < nqy; j++) fprintf(fstruc, "%g ", sq[i * nqy + j]);
+			fprintf(fstruc, "\n");
+		}
+		fflush(fstruc);
+		free(sq);
+	}
+	if (pcfg6Thermo) { /* save_pcf_g6(name, particles, N, 2, fmin(Lx, Ly)/2, ...), src/EDMD.c:5639-5641, src/pcf.c:297-336 */
+		double dr = 2, max_r = (Lx < Ly ? Lx : Ly) / 2;
+		int nbins = 0;
+		edmd_cuda_g6_correlation(gpu, dr, max_r, NULL, NULL, NULL, NULL, &nbins);
+		double *g6 = malloc(sizeof(double) * (nbins > 0 ? nbins : 1));
+		int rc = edmd_cuda_g6_correlation(gpu, dr, max_r, NULL, NULL, NULL, g6, &nbins);
+		if (rc) die_gpu(rc, "edmd_cuda_g6_correlation");
+		FILE *chk = fopen(pcfg6Name, "r");
+		FILE *f = fopen(pcfg6Name, chk ? "a" : "w");
+		if (!chk) {
+			for (int b = 0; b < nbins; b++) fprintf(f, "%lf ", (b + 0.5) * dr);
+			fprintf(f, "\n");
+		} else fclose(chk);
+		for (int b = 0; b < nbins; b++) fprintf(f, "%lf ", g6[b]);
+		fprintf(f, "\n");
+		fclose(f);
+		free(g6);
 	}
 }
 
@@ -702,6 +752,9 @@ int main(int argc, char **argv)
 		{"verify", no_argument, NULL, 1005}, {"outdir", required_argument, NULL, 1006},
 		{"quiet", no_argument, NULL, 1007}, {"device", required_argument, NULL, 1008},
 		{"init", required_argument, NULL, 1009}, {"ingest", required_argument, NULL, 1010},
+		{"boop-voronoi", no_argument, NULL, 1011}, {"area", no_argument, NULL, 1012},
+		{"struc", required_argument, NULL, 1013}, {"qmax", required_argument, NULL, 1014},
+		{"pcfg6", no_argument, NULL, 1015},
 		{NULL, 0, NULL, 0}};
 	int c, device = 0;
 	while ((c = getopt_long(argc, argv, "N:p:x:q:a:t:D:o:T:v:", longopt, NULL)) != -1) {
@@ -726,8 +779,13 @@ int main(int argc, char **argv)
 		case 1008: device = atoi(optarg); break;
 		case 1009: init_grow = strcmp(optarg, "lattice") != 0; break;
 		case 1010: bulk_ingest = strcmp(optarg, "seq") != 0; break;
+		case 1011: boopThermo = 1; break;
+		case 1012: areaThermo = 1; break;
+		case 1013: strucThermo = atoi(optarg) == 0 ? 2 : 1; break; /* reference: mode 0 = velocity S(q), else positions */
+		case 1014: qmax = atof(optarg); break;
+		case 1015: pcfg6Thermo = 1; break;
 		default: fprintf(stderr, "usage: edmd_host -N n --phi f [-x xs -q ratio -a aspect -t tmax -D dt -o dtThermo -T temp -v seed]\n"
-		                         "       [--init grow|lattice] [--ingest bulk|seq] [--noise 2 --dtnoise dt] [--boop] [--pcf] [--verify] [--outdir dir] [--quiet]\n");
+		                         "       [--init grow|lattice] [--ingest bulk|seq] [--noise 2 --dtnoise dt] [--boop | --boop-voronoi] [--area] [--pcf] [--pcfg6] [--struc mode --qmax q] [--verify] [--outdir dir] [--quiet]\n");
 			return 2;
 		}
 	}
@@ -767,7 +825,23 @@ int main(int argc, char **argv)
 	snprintf(name, sizeof name, "%s/N_%dphi_%.4f.dump", outdir, N, phi); fdump = fopen(name, "w");
 	snprintf(name, sizeof name, "%s/N_%dphi_%.4f.thermo", outdir, N, phi); fthermo = fopen(name, "w");
 	if (pcfThermo) { snprintf(name, sizeof name, "%s/N_%dphi_%.4f.pcf", outdir, N, phi); fpcf = fopen(name, "w"); }
-	if (!fdump || !fthermo || (pcfThermo && !fpcf)) { perror("edmd_host: output files"); return 1; }
+	if (strucThermo) {
+		snprintf(name, sizeof name, "%s/N_%dphi_%.4f.struc", outdir, N, phi); fstruc = fopen(name, "w");
+		if (fstruc) { /* header of initStructureFactor, src/struc.c:347-355 */
+			int nqx = 0, nqy = 0;
+			edmd_cuda_structure_factor(gpu, qmax, 0, &nqx, &nqy, NULL, NULL, NULL, NULL, NULL);
+			double *qx = malloc(sizeof(double) * (nqx + 1)), *qy = malloc(sizeof(double) * (nqy + 1));
+			edmd_cuda_structure_factor(gpu, qmax, 0, &nqx, &nqy, qx, qy, NULL, NULL, NULL);
+			fprintf(fstruc, "-%lf \n", 0.0);
+			for (int i = 0; i < nqx; i++) fprintf(fstruc, "%g ", qx[i]);
+			fprintf(fstruc, "\n");
+			for (int j = 0; j < nqy; j++) fprintf(fstruc, "%g ", qy[j]);
+			fprintf(fstruc, "\n");
+			free(qx); free(qy);
+		}
+	}
+	if (pcfg6Thermo) { snprintf(pcfg6Name, sizeof pcfg6Name, "%s/N_%dphi_%.4f.pcfg6", outdir, N, phi); remove(pcfg6Name); }
+	if (!fdump || !fthermo || (pcfThermo && !fpcf) || (strucThermo && !fstruc)) { perror("edmd_host: output files"); return 1; }
 	fprintf(fthermo, "t Ncol E p\n");
 
 	if (!quiet)
@@ -807,6 +881,7 @@ int main(int argc, char **argv)
 	       gpu_sweeps ? 1e3 * ingest_seconds / gpu_sweeps : 0.0, bulk_sweeps, kinetic_energy() / N, last_pressure);
 	fclose(fdump); fclose(fthermo);
 	if (fpcf) fclose(fpcf);
+	if (fstruc) fclose(fstruc);
 	edmd_cuda_destroy(gpu);
 	return 0;
 }

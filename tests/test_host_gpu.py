@@ -81,3 +81,35 @@ def test_host_bulk_calendar_ingest_equals_sequential(tmp_path):
     assert outs["seq"][:3] == outs["bulk"][:3]
     assert outs["seq"][4] == outs["bulk"][4]      # identical dumps
     assert outs["seq"][5] == outs["bulk"][5]      # identical thermo records
+
+
+def test_host_voronoi_area_struc_and_g6_outputs(tmp_path):
+    """The reference's other frame-analysis switches (boopThermo == 1, areaThermo,
+    strucThermo, pcfg6Thermo; src/EDMD.c:5053-5064, 5620-5641) through the host:
+    dump columns in the reference's format, S(q) file with initStructureFactor's
+    header, g6 correlation file in save_pcf_g6's layout."""
+    run_host(tmp_path, "-N", 2500, "--phi", 0.72, "-x", 0, "-t", 6, "-D", 3, "-o", 3, "--quiet", "--init", "lattice",
+             "--boop-voronoi", "--area", "--struc", 1, "--qmax", 0.5, "--pcfg6")
+    dump = next(tmp_path.glob("*.dump")).read_text().splitlines()
+    assert dump[8] == "ITEM: ATOMS id type x y vx vy radius m coll q5 q6 q7 argq6 neighbors packingFraction"
+    n = int(dump[3])
+    rows = np.array([[float(v) for v in line.split()] for line in dump[9:9 + n]])
+    assert rows.shape == (n, 15)
+    assert rows[:, 13].sum() == 6 * n                 # Voronoi neighbours: mean coordination exactly 6
+    lx, ly = float(dump[5].split()[1]), float(dump[6].split()[1])
+    # sum_i pi r_i^2 / (local packing fraction) = the box area (columns are %lf: 1e-6 each)
+    assert abs((np.pi * rows[:, 7] ** 2 / rows[:, 14]).sum() - lx * ly) < 1e-3 * lx * ly
+    struc = next(tmp_path.glob("*.struc")).read_text().splitlines()
+    qx = np.array(struc[1].split(), float)
+    qy = np.array(struc[2].split(), float)
+    assert abs(qx[1] - qx[0] - 2 * np.pi / lx) < 1e-5 and abs(qy[1] - qy[0] - 2 * np.pi / ly) < 1e-5
+    frames = (len(struc) - 3) // len(qx)
+    assert frames >= 2 and (len(struc) - 3) % len(qx) == 0
+    s0 = np.array([line.split() for line in struc[3:3 + len(qx)]], float)
+    assert s0.shape == (len(qx), len(qy))
+    assert s0[(len(qx) - 1) // 2, (len(qy) - 1) // 2] == n      # S(q = 0) = N
+    g6 = next(tmp_path.glob("*.pcfg6")).read_text().splitlines()
+    r = np.array(g6[0].split(), float)
+    assert r[0] == 1.0 and len(g6) == 1 + frames
+    c = np.array(g6[1].split(), float)
+    assert len(c) == len(r) and np.abs(c).max() <= 1.0

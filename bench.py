@@ -412,6 +412,25 @@ def run_ours(args, cfg):
         analysis["psi6_particles_per_s"] = float(n / (np.mean(bt) * 1e-3))
         analysis["psi6_hbm_frac"] = 56.0 * n / (np.mean(bt) * 1e-3) / 1e9 / peaks()[0]
         max_r_cut = 12.0
+        if world == 1:
+            # K5: Voronoi psi6 + cell area / perimeter (computeBOOPVoronoi, get_particle_voronoi_area)
+            vt, vm = ctx.bench(B.BENCH_VORONOI, warmup=2, iters=5, flush_bytes=L2_FLUSH_BYTES)
+            analysis["voronoi_ms"] = float(np.mean(vt))
+            analysis["voronoi_cells_kernel_ms"] = float(np.mean(vm))
+            analysis["voronoi_particles_per_s"] = float(n / (np.mean(vt) * 1e-3))
+            # a whole thermostat tick on the resident state: free flight (dt = 0), kinetic energy,
+            # velocity rescale, K0 + K1 -- wall clock around the C-ABI calls, nothing crosses PCIe
+            # but the two scalars of the rescale
+            torch.cuda.synchronize()
+            ticks = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                ctx.free_fly(0.0)              # the snapshot was uploaded at t = 0: dt = 0
+                ctx.rescale_velocities(1.0)
+                ctx.predict_device()
+                ctx.stat(B.STAT_EXACT_RESCANS)   # synchronises the context's stream
+                ticks.append(time.perf_counter() - t0)
+            analysis["device_tick_ms"] = float(np.median(ticks) * 1e3)
         if args.analysis == "full":
             max_r = min(cfg["lx"], cfg["ly"]) / 2
             pt, _ = ctx.bench(B.BENCH_PCF, dr=0.1, max_r=max_r, warmup=0, iters=1)

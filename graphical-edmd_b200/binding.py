@@ -44,7 +44,7 @@ SYMBOLS = [
     "edmd_cuda_halo_export", "edmd_cuda_halo_connect", "edmd_cuda_halo_exchange",
     "edmd_cuda_calendar_plan", "edmd_cuda_pcf_bond_order", "edmd_cuda_bragg_peak",
     "edmd_cuda_boop_voronoi", "edmd_cuda_voronoi_cells", "edmd_cuda_g6_correlation",
-    "edmd_cuda_structure_factor",
+    "edmd_cuda_structure_factor", "edmd_cuda_kinetic", "edmd_cuda_rescale_velocities",
 ]
 EVORONOI = 7
 HALO_RECORD_BYTES = 48
@@ -119,6 +119,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_calendar_plan.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, vp,
                                             C.POINTER(C.c_int32)]
     lib.edmd_cuda_get_stat.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
+    lib.edmd_cuda_kinetic.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.edmd_cuda_rescale_velocities.argtypes = [vp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.edmd_cuda_boop_voronoi.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.edmd_cuda_voronoi_cells.argtypes = [vp, vp, vp, vp]
     lib.edmd_cuda_g6_correlation.argtypes = [vp, C.c_double, C.c_double, vp, vp, vp, vp, C.POINTER(C.c_int)]
@@ -323,6 +325,18 @@ class EdmdCuda:
         self._check(self.lib.edmd_cuda_boop_cutoff(
             self._h, r_c, _ptr(q5), _ptr(q6), _ptr(q7), _ptr(arg), _ptr(nb), C.addressof(mean)))
         return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, mean_q6=mean.value)
+
+    def kinetic(self):
+        """physicalQ's sums (src/EDMD.c:5968-5997) over the resident velocities."""
+        e, px, py = C.c_double(0), C.c_double(0), C.c_double(0)
+        self._check(self.lib.edmd_cuda_kinetic(self._h, C.byref(e), C.byref(px), C.byref(py)))
+        return dict(E=e.value, px=px.value, py=py.value)
+
+    def rescale_velocities(self, T):
+        """addNoise's velocity rescale (src/EDMD.c:4899-4902) on the resident velocities."""
+        e, s = C.c_double(0), C.c_double(0)
+        self._check(self.lib.edmd_cuda_rescale_velocities(self._h, float(T), C.byref(e), C.byref(s)))
+        return dict(E_before=e.value, divisor=s.value)
 
     def boop_voronoi(self):
         """computeBOOPVoronoi (src/boop.c:15-59) on the resident positions."""

@@ -305,7 +305,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
                    c->lrec, c->lchunks, c->lres, c->lwork, c->cal_mem,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
-                   c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->vor_mem, c->boop, c->boop_nb,
+                   c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->vor_mem, c->thermo_mem, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
     for (void *p : dev)
         if (p) cudaFree(p);
@@ -991,6 +991,56 @@ int edmd_cuda_bragg_peak(edmd_ctx *c, double expected_bragg, double *k_out, doub
         k_out[1] = ks[(size_t)bi].y;
     }
     if (s_max) *s_max = best;
+    return 0;
+}
+
+// ---- thermostat on the resident state (thermostat.cu) -------------------------
+namespace {
+int kinetic_run(edmd_ctx *c, double T, double **red)
+{
+    if (!c->thermo_mem) CU(cudaMalloc((void **)&c->thermo_mem, edmd_thermostat_scratch_doubles() * sizeof(double)));
+    int launched = 0;
+    *red = edmd_launch_kinetic(c, T, c->thermo_mem, &launched);
+    c->launches += launched;
+    CU(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+int edmd_cuda_kinetic(edmd_ctx *c, double *E, double *px, double *py)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "kinetic before upload");
+    CU(cudaSetDevice(c->device));
+    double *red = nullptr, h[4] = {0, 0, 0, 0};
+    int r;
+    if ((r = kinetic_run(c, 0.0, &red))) return r;
+    CU(cudaMemcpyAsync(h, red, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (E) *E = h[0];
+    if (px) *px = h[1];
+    if (py) *py = h[2];
+    return 0;
+}
+
+int edmd_cuda_rescale_velocities(edmd_ctx *c, double T, double *E_before, double *divisor)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "rescale before upload");
+    if (!(T > 0)) return fail(c, EDMD_EINVAL, "temperature must be positive");
+    CU(cudaSetDevice(c->device));
+    double *red = nullptr, h[4] = {0, 0, 0, 0};
+    int r;
+    if ((r = kinetic_run(c, T, &red))) return r;
+    c->launches += edmd_launch_rescale(c, red);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h, red, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    c->have_pred = false;
+    c->have_index = false;   // the cell-ordered records carry velocities
+    if ((r = check_flags(c))) return r;   // synchronises; refreshes vmax / lean eligibility
+    if (E_before) *E_before = h[0];
+    if (divisor) *divisor = h[3];
+    if (!(h[3] > 0)) return fail(c, EDMD_EINVAL, "rescale: the system has no kinetic energy");
     return 0;
 }
 

@@ -227,6 +227,7 @@ struct edmd_ctx {
     unsigned long long *pcf_wsum;     // weighted sums (2^-32 fixed point), capacity pcf_wcap bins
     int pcf_wcap;
     int pcf_cap;
+    double *thermo_mem;               // kinetic sums: block partials + results (thermostat.cu)
     char *vor_mem;                    // Voronoi grid scratch (analysis_voronoi.cu) + psi6 + area/perimeter
     size_t vor_bytes;
     double *boop;                     // 4*N doubles q5|q6|q7|arg
@@ -292,6 +293,9 @@ size_t edmd_voronoi_scratch_bytes(const edmd_ctx *c, int *gx_out, int *gy_out);
 int edmd_launch_voronoi(edmd_ctx *c, char *scratch, int boop, double *q5, double *q6, double *q7, double *q6arg,
                         int32_t *nbr, double *area, double *perim, int32_t *fail_dev, cudaEvent_t before_cells = nullptr);
 int edmd_launch_psi6(edmd_ctx *c, const double *q6, const double *arg, double2 *psi);
+size_t edmd_thermostat_scratch_doubles();
+double *edmd_launch_kinetic(edmd_ctx *c, double T, double *scratch, int *launched);
+int edmd_launch_rescale(edmd_ctx *c, const double *red);
 int edmd_launch_bragg(edmd_ctx *c, int nk, const double2 *kvec, double *re, double *im, double *best_s,
                       int *best_i);
 int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,

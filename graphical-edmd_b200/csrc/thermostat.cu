@@ -1,0 +1,114 @@
+// thermostat.cu -- the velocity part of a thermostat tick on the RESIDENT state
+// (SURVEY.md 8f rank 2):
+//   physicalQ        src/EDMD.c:5968-5997   E = sum 1/2 m v^2, px, py   (m = 1: the
+//                                           reference's default initial conditions, :1467-1548)
+//   addNoise, velocity-rescale branch  :4830-4832, :4899-4902   v /= sqrt(E/N/T)
+// With edmd_cuda_free_fly (the `freeFly(p)` of the same loop, :4893) and
+// edmd_cuda_predict_device (the re-predict loop :4909-4915) the whole tick runs on
+// the device without the state crossing PCIe in between.
+//
+// The reference adds the N terms in particle order; a parallel sum cannot reproduce
+// that rounding, so E (and with it every rescaled velocity) agrees to ~1e-15
+// relative, not bit for bit -- inside the 1e-12 bar of the event times.  The sum IS
+// reproducible run to run: fixed partition (kBlocks x kThreads strided), fixed tree.
+#include "edmd_internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBlocks = 592;   // 4 per SM
+
+__device__ __forceinline__ void block_sum3(double &a, double &b, double &c)
+{
+    __shared__ double sh[3][kThreads];
+    sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b; sh[2][threadIdx.x] = c;
+    __syncthreads();
+    for (int d = kThreads / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + d];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + d];
+            sh[2][threadIdx.x] += sh[2][threadIdx.x + d];
+        }
+        __syncthreads();
+    }
+    a = sh[0][0]; b = sh[1][0]; c = sh[2][0];
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_kinetic_partial(int n, const double4 *__restrict__ xv, double *__restrict__ partial)
+{
+    double e = 0, px = 0, py = 0;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const double4 p = xv[i];
+        // `E += 0.5 * particles[i].m * (vx * vx + particles[i].vy * particles[i].vy)` :5988
+        e += 0.5 * (p.z * p.z + p.w * p.w);
+        px += p.z;
+        py += p.w;
+    }
+    block_sum3(e, px, py);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = e;
+        partial[kBlocks + blockIdx.x] = px;
+        partial[2 * kBlocks + blockIdx.x] = py;
+    }
+}
+
+// out[0..2] = E, px, py;  out[3] = sqrt(E/N/T) (the divisor of the rescale), 0 when T <= 0
+__global__ void __launch_bounds__(kThreads)
+k_kinetic_final(int n, double T, const double *__restrict__ partial, double *__restrict__ out)
+{
+    double e = 0, px = 0, py = 0;
+    for (int i = threadIdx.x; i < kBlocks; i += kThreads) {
+        e += partial[i];
+        px += partial[kBlocks + i];
+        py += partial[2 * kBlocks + i];
+    }
+    block_sum3(e, px, py);
+    if (threadIdx.x == 0) {
+        out[0] = e; out[1] = px; out[2] = py;
+        out[3] = T > 0 ? sqrt(e / n / T) : 0.0;   // `sqrt(E/N/T)` :4899
+    }
+}
+
+// `p->vx /= sqrt(E/N/T); p->vy /= sqrt(E/N/T);` :4899-4900, and the new largest |component|
+// for the lean sweep's error model
+__global__ void __launch_bounds__(kThreads)
+k_rescale(int n, const double *__restrict__ red, double4 *__restrict__ xv, int32_t *__restrict__ flags)
+{
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    const double s = red[3];
+    float vm = 0.0f;
+    if (i < n && s > 0) {
+        double4 p = xv[i];
+        p.z = __ddiv_rn(p.z, s);
+        p.w = __ddiv_rn(p.w, s);
+        xv[i] = p;
+        vm = __double2float_ru(fmax(fabs(p.z), fabs(p.w)));
+        if (!(vm == vm)) vm = __int_as_float(0x7f800000);
+    }
+    const unsigned vmb = __reduce_max_sync(0xffffffffu, (unsigned)__float_as_int(vm));
+    if ((threadIdx.x & 31) == 0 && vmb) atomicMax(reinterpret_cast<unsigned int *>(&flags[kFlagVmax]), vmb);
+}
+
+}  // namespace
+
+size_t edmd_thermostat_scratch_doubles() { return 3 * (size_t)kBlocks + 8; }
+
+// scratch: edmd_thermostat_scratch_doubles(); results in scratch[3*kBlocks .. +3]
+double *edmd_launch_kinetic(edmd_ctx *c, double T, double *scratch, int *launched)
+{
+    double *out = scratch + 3 * kBlocks;
+    k_kinetic_partial<<<kBlocks, kThreads, 0, c->stream>>>(c->n_owned, c->xv, scratch);
+    k_kinetic_final<<<1, kThreads, 0, c->stream>>>(c->n_owned, T, scratch, out);
+    *launched += 2;
+    return out;
+}
+
+int edmd_launch_rescale(edmd_ctx *c, const double *red)
+{
+    const int n = c->n_owned;
+    if (n == 0) return 0;
+    cudaMemsetAsync(c->flags + kFlagVmax, 0, sizeof(int32_t), c->stream);
+    k_rescale<<<(n + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(n, red, c->xv, c->flags);
+    return 1;
+}

@@ -276,6 +276,22 @@ int edmd_cuda_free_fly(edmd_ctx *ctx, int mode, double t_new);
 int edmd_cuda_download_state(edmd_ctx *ctx, double *x, double *y, double *vx,
                              double *vy, double *rad);
 
+/* ---- thermostat tick on the resident state -------------------------------- */
+
+/* Replaces physicalQ's sums (src/EDMD.c:5968-5997) over the resident velocities,
+ * unit masses (the reference's default initial conditions, :1467-1548):
+ * E = sum 1/2 (vx^2 + vy^2), px = sum vx, py = sum vy.  Parallel, reproducible
+ * (fixed summation tree); agrees with the reference's sequential sum to ~1e-15
+ * relative, not bit for bit. */
+int edmd_cuda_kinetic(edmd_ctx *ctx, double *E, double *px, double *py);
+/* Replaces the velocity-rescale branch of addNoise (src/EDMD.c:4830-4832 +
+ * :4899-4902): `physicalQ(); ... p->vx /= sqrt(E/N/T); p->vy /= sqrt(E/N/T);` on
+ * the resident velocities.  E_before / divisor (nullable) = E and sqrt(E/N/T).
+ * A whole tick without the state crossing PCIe: edmd_cuda_free_fly(t) (the
+ * freeFly(p) of the same loop, :4893), this call, edmd_cuda_predict_device()
+ * (the re-predict loop :4909-4915). */
+int edmd_cuda_rescale_velocities(edmd_ctx *ctx, double T, double *E_before, double *divisor);
+
 /* ---- per-frame structure analysis ----------------------------------- */
 
 /* Replaces calculate_pcf (src/pcf.c:16-75; caller save_pcf, src/EDMD.c:

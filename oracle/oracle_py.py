@@ -141,6 +141,24 @@ class Oracle:
                                    C.c_double(expected_bragg), _p(k), C.byref(s))
         return dict(k=k, s_max=s.value)
 
+    def tick_rescale(self, n, lx, ly, t_old, t_new, T, x, y, vx, vy, rad, cell_xy=None):
+        """Thermostat tick, velocity-rescale branch: physicalQ's E (src/EDMD.c:5968-5997,
+        sequential sum, unit masses), then addNoise :4889-4915 -- freeFly to t_new,
+        `v /= sqrt(E/N/T)`, re-predict everything.  Free flight does not re-file
+        particles: the sweep runs with the cell ids the particles had BEFORE the flight
+        (cell_xy None = coordToCell of the old positions)."""
+        if cell_xy is None:
+            cell_xy = self.cells(n, lx, ly, x, y)
+        vx, vy = _f64(vx), _f64(vy)
+        terms = 0.5 * 1.0 * (vx * vx + vy * vy)
+        E = float(np.cumsum(terms)[-1]) if n else 0.0      # left-to-right, like the loop
+        s = np.sqrt(E / n / T)
+        ff = self.free_fly(n, lx, ly, t_old, t_new, x, y, vx, vy, rad=rad)
+        vx2, vy2 = vx / s, vy / s
+        out = self.predict_all(n, lx, ly, t_new, ff["x"], ff["y"], vx2, vy2, rad, cell_xy=cell_xy)
+        out.update(x=ff["x"], y=ff["y"], vx=vx2, vy=vy2, E_before=E, divisor=float(s))
+        return out
+
     def g6_correlation(self, n, lx, ly, x, y, psi_re, psi_im, dr, max_r):
         """Pair loop of compute_g6_correlation (src/pcf.c:189-228) for a given psi6."""
         b = self.box(n, lx, ly)
@@ -338,6 +356,19 @@ class Reference:
         self.lib.ref_bragg_peak.restype = C.c_double
         sec = self.lib.ref_bragg_peak(C.c_double(expected_bragg), _p(k))
         return dict(k=k, seconds=sec)
+
+    def tick_rescale(self, t_new, T):
+        """physicalQ + addNoise (velocity-rescale branch) at time t_new."""
+        n = self.n
+        x, y, vx, vy = (np.empty(n, np.float64) for _ in range(4))
+        tc, d, tl, p, ct = self._outs()
+        e = C.c_double(0.0)
+        f = self.lib.ref_tick_rescale
+        f.restype = C.c_double
+        sec = f(C.c_double(t_new), C.c_double(T), C.byref(e), _p(x), _p(y), _p(vx), _p(vy),
+                _p(tc), _p(d), _p(tl), _p(p), _p(ct))
+        return dict(t_cross=tc, dir=d, t_coll=tl, partner=p, ctype=ct, x=x, y=y, vx=vx, vy=vy,
+                    E_before=e.value, seconds=sec)
 
     def boop_voronoi(self):
         n = self.n

@@ -427,3 +427,34 @@ double ref_structure_factor(double q_max, int velocity, int *nqx_out, int *nqy_o
 	fclose(sink);
 	return t1 - t0;
 }
+
+/* A real thermostat tick with the velocity-rescale branch at time t_new:
+ * physicalQ() (src/EDMD.c:5968-5997) for E, then addNoise() (:4828-4923): every
+ * particle is free-flown to t_new, its velocity divided by sqrt(E/N/T), and the
+ * whole system re-predicted.  (In the CLI build `noise` is const 0, which skips
+ * the physicalQ() call inside addNoise; it is made here, as the noise == 2 build
+ * does at :4830-4832.)  Outputs: E before the tick, the new state, the new events.
+ * Requires a previous ref_predict_first.  Returns seconds. */
+double ref_tick_rescale(double t_new, double T_target, double *E_out, double *x, double *y,
+                        double *vx, double *vy, double *t_cross, uint8_t *dir, double *t_coll,
+                        int32_t *partner, uint8_t *ctype)
+{
+	shim_set_mode(0);
+	T = T_target;
+	t = t_new;
+	double t0 = shim_now();
+	physicalQ();
+	if (E_out)
+		*E_out = E;
+	addNoise();
+	double t1 = shim_now();
+	removeEventFromQueue(eventList[2 * N + 2]); /* the re-armed NOISE event */
+	for (int i = 0; i < N; i++) {
+		x[i] = particles[i].x;
+		y[i] = particles[i].y;
+		vx[i] = particles[i].vx;
+		vy[i] = particles[i].vy;
+	}
+	shim_copy_out(t_cross, dir, t_coll, partner, ctype);
+	return t1 - t0;
+}

@@ -153,4 +153,24 @@ if want("voronoi"):
     voronoi_case("voronoi_n1500_phi085", pkg.synth.lattice_config(1500, 0.85, seed=8), 1.0, 0.8)
     voronoi_case("voronoi_n2025_jittered", point_config(2025, 97.0, 88.0, seed=7, jitter=0.9), 0.5, 1.0)
     voronoi_case("voronoi_n1500_poisson", point_config(1500, 80.0, 70.0, seed=9), 1.0, 0.5)
+
+def tick_case(name, cfg, t0, t_new, T):
+    """A whole thermostat tick: physicalQ + addNoise with the
+    velocity-rescale branch, from the reference."""
+    n = cfg["n"]
+    ref.setup(n, cfg["lx"], cfg["ly"], t0, cfg["x"], cfg["y"], cfg["vx"], cfg["vy"], cfg["rad"])
+    ref.predict_first()
+    k = ref.tick_rescale(t_new, T)
+    np.savez_compressed(HERE / f"{name}.npz", n=n, lx=cfg["lx"], ly=cfg["ly"], t=t0, t_new=t_new, T=T,
+                        x=cfg["x"], y=cfg["y"], vx=cfg["vx"], vy=cfg["vy"], rad=cfg["rad"],
+                        E_before=k["E_before"], tick_x=k["x"], tick_y=k["y"], tick_vx=k["vx"], tick_vy=k["vy"],
+                        **{"tick_" + q: k[q] for q in ("t_cross", "dir", "t_coll", "partner", "ctype")})
+    print("wrote", name, "n =", n, "E/N before", k["E_before"] / n)
+
+
+if want("tick"):
+    # the free flight must not create overlaps: short flights of a dilute-ish liquid
+    tick_case("tick_n2000_phi060", pkg.synth.lattice_config(2000, 0.60, seed=10), 1.25, 1.2625, 0.7)
+    tick_case("tick_n1500_phi045_bidisperse",
+              pkg.synth.lattice_config(1500, 0.45, seed=11, small_fraction=0.3), 0.0, 0.03125, 1.6)
 ref.teardown()

@@ -86,3 +86,21 @@ def random_points(n, lx, ly, seed, jitter=None):
         x, y = x[p], y[p]
     return dict(n=n, lx=lx, ly=ly, x=x, y=y, vx=rng.standard_normal(n), vy=rng.standard_normal(n),
                 rad=np.full(n, 0.05))
+
+
+TICK_CASES = ["tick_n2000_phi060", "tick_n1500_phi045_bidisperse"]
+TICK_RTOL = 1e-12   # the kinetic-energy sum is order dependent: rescaled velocities and event times to 1e-12
+
+
+def assert_tick_close(got, want, prefix="tick_"):
+    """State and events after a thermostat tick: positions bit-exact (free flight),
+    velocities and times within 1e-12 relative, partners / directions exact."""
+    assert np.array_equal(got["x"], want[prefix + "x"]) and np.array_equal(got["y"], want[prefix + "y"])
+    for k in ("vx", "vy"):
+        w = want[prefix + k]
+        assert (np.abs(got[k] - w) <= TICK_RTOL * np.abs(w).max()).all(), k
+    for k in ("partner", "dir", "ctype"):
+        assert np.array_equal(got[k], want[prefix + k]), k
+    for k in ("t_cross", "t_coll"):
+        w = want[prefix + k]
+        assert (np.abs(got[k] - w) <= TICK_RTOL * np.abs(w)).all(), k

@@ -777,3 +777,62 @@ def test_structure_factor_and_g6_match_oracle(pkg, oracle, n, seed, qmax):
     wg = oracle.g6_correlation(n, lx, ly, c["x"], c["y"], psi[0], psi[1], 0.25, min(lx, ly) / 2)
     assert np.array_equal(g6["counts"], wg["counts"])
     assert np.abs(g6["g6_corr"] - wg["g6_corr"]).max() <= ANALYSIS_ATOL
+
+
+# ------------------------------------------ thermostat tick on resident state ----
+from helpers import TICK_CASES, TICK_RTOL, assert_tick_close  # noqa: E402
+
+
+def _device_tick(ctx, t_new, T):
+    ctx.free_fly(t_new)
+    r = ctx.rescale_velocities(T)
+    out = ctx.predict_all()
+    out.update(ctx.download_state())
+    out.update(r)
+    return out
+
+
+@pytest.mark.parametrize("name", TICK_CASES)
+def test_device_thermostat_tick_matches_reference_golden(pkg, name):
+    """A whole tick without the state leaving the device -- free flight, kinetic
+    energy, velocity rescale, re-predict -- against the reference's physicalQ +
+    addNoise on the same snapshot."""
+    g = load_golden(name)
+    c = cfg_of(g)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=c["t"])
+        k = ctx.kinetic()
+        got = _device_tick(ctx, float(g["t_new"]), float(g["T"]))
+        after = ctx.kinetic()
+    assert abs(k["E"] - float(g["E_before"])) <= TICK_RTOL * float(g["E_before"])
+    assert abs(k["px"] - c["vx"].sum()) < 1e-9 and abs(k["py"] - c["vy"].sum()) < 1e-9
+    assert abs(got["E_before"] - k["E"]) == 0.0          # reproducible sum
+    assert_tick_close(got, g)
+    assert abs(after["E"] / c["n"] - float(g["T"])) < 1e-12
+
+
+@pytest.mark.parametrize("n,phi,seed,sf", [(200000, 0.60, 51, 0.0), (1000000, 0.70, 52, 0.0), (100000, 0.55, 53, 0.3)])
+def test_device_thermostat_tick_matches_oracle(pkg, oracle, n, phi, seed, sf):
+    c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf)
+    n = c["n"]
+    t0, t1, T = 2.0, 2.0 + 1.0 / 64, 1.3
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=t0)
+        ctx.predict_all()
+        lean_before = ctx.stat(pkg.binding.STAT_LEAN_SWEEPS)
+        got = _device_tick(ctx, t1, T)
+        lean_after = ctx.stat(pkg.binding.STAT_LEAN_SWEEPS)
+    want = oracle.tick_rescale(n, c["lx"], c["ly"], t0, t1, T, c["x"], c["y"], c["vx"], c["vy"], c["rad"])
+    assert want["rc"] == 0
+    assert abs(got["E_before"] - want["E_before"]) <= TICK_RTOL * want["E_before"]
+    assert np.array_equal(got["x"], want["x"]) and np.array_equal(got["y"], want["y"])
+    for k in ("vx", "vy"):
+        assert (np.abs(got[k] - want[k]) <= TICK_RTOL * np.abs(want[k]).max()).all()
+    # a velocity that differs in the last bits can flip an exact near-tie: allow a handful
+    same = got["partner"] == want["partner"]
+    assert (~same).sum() <= max(2, n // 200000)
+    assert np.array_equal(got["dir"], want["dir"])
+    for k in ("t_cross", "t_coll"):
+        ok = np.abs(got[k] - want[k]) <= TICK_RTOL * np.abs(want[k])
+        assert (ok | ~same).all(), k
+    assert lean_after == lean_before + 1     # the rescaled state stays on the lean path

@@ -98,7 +98,7 @@ def test_host_voronoi_area_struc_and_g6_outputs(tmp_path):
     assert rows[:, 13].sum() == 6 * n                 # Voronoi neighbours: mean coordination exactly 6
     lx, ly = float(dump[5].split()[1]), float(dump[6].split()[1])
     # sum_i pi r_i^2 / (local packing fraction) = the box area (columns are %lf: 1e-6 each)
-    assert abs((np.pi * rows[:, 7] ** 2 / rows[:, 14]).sum() - lx * ly) < 1e-3 * lx * ly
+    assert abs((np.pi * rows[:, 6] ** 2 / rows[:, 14]).sum() - lx * ly) < 1e-3 * lx * ly
     struc = next(tmp_path.glob("*.struc")).read_text().splitlines()
     qx = np.array(struc[1].split(), float)
     qy = np.array(struc[2].split(), float)

@@ -171,3 +171,19 @@ def test_oracle_structure_factor_matches_golden(oracle, name):
     assert s["s"][i0, j0] == n                       # q = 0: S = N
     v = oracle.structure_factor(n, lx, ly, g["x"], g["y"], float(g["sq_qmax"]), g["vx"], g["vy"])
     assert (np.abs(v["s"] - g["sq_s_velocity"]) / np.maximum(1.0, g["sq_s_velocity"])).max() <= ANALYSIS_ATOL
+
+
+from helpers import TICK_CASES, TICK_RTOL, assert_tick_close  # noqa: E402
+
+
+@pytest.mark.parametrize("name", TICK_CASES)
+def test_oracle_thermostat_tick_matches_golden(oracle, name):
+    """physicalQ + addNoise's velocity-rescale branch (src/EDMD.c:5968-5997, 4828-4923)."""
+    g = load_golden(name)
+    c = cfg_of(g)
+    got = oracle.tick_rescale(c["n"], c["lx"], c["ly"], c["t"], float(g["t_new"]), float(g["T"]),
+                              c["x"], c["y"], c["vx"], c["vy"], c["rad"])
+    assert abs(got["E_before"] - float(g["E_before"])) <= TICK_RTOL * float(g["E_before"])
+    assert_tick_close(got, g)
+    e_after = 0.5 * (got["vx"] ** 2 + got["vy"] ** 2).sum()
+    assert abs(e_after / c["n"] - float(g["T"])) < 1e-12          # the tick sets E/N = T

@@ -29,6 +29,8 @@ STAT_EXACT_RESCANS = 1
 STAT_LEAN_SWEEPS = 2
 STAT_PCF_EXACT_PAIRS = 3
 STAT_PCF_SKIPPED_TILE_PAIRS = 4
+STAT_LEAN_DECLINES = 5
+STAT_LEAN_ELIGIBLE = 6
 
 # every symbol include/edmd_cuda.h declares
 SYMBOLS = [

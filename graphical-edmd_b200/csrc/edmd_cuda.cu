@@ -371,6 +371,14 @@ int edmd_cuda_get_stat(edmd_ctx *c, int stat, uint64_t *value)
         *value = c->lean_sweeps;
         return 0;
     }
+    if (stat == EDMD_STAT_LEAN_DECLINES) {
+        *value = (uint64_t)c->lean_declines;
+        return 0;
+    }
+    if (stat == EDMD_STAT_LEAN_ELIGIBLE) {
+        *value = edmd_lean_eligible(c, EDMD_MODE_NORMAL) ? 1 : 0;
+        return 0;
+    }
     if (stat != EDMD_STAT_EXACT_RESCANS) return fail(c, EDMD_EINVAL, "unknown stat");
     CU(cudaSetDevice(c->device));
     uint32_t v = 0;

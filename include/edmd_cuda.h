@@ -103,6 +103,10 @@ int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 #define EDMD_STAT_LEAN_SWEEPS 2
 /* g(r), sorted-tile kernel, since create: pairs whose bin needed the exact sqrt + division;
  * tile pairs skipped because every pair in them is beyond max_r. */
+/* EDMD_STAT_LEAN_DECLINES = lean sweeps the device declined (re-run on the full path);
+ * EDMD_STAT_LEAN_ELIGIBLE = 1 when the next NORMAL-mode sweep would try the lean path. */
+#define EDMD_STAT_LEAN_DECLINES 5
+#define EDMD_STAT_LEAN_ELIGIBLE 6
 #define EDMD_STAT_PCF_EXACT_PAIRS 3
 #define EDMD_STAT_PCF_SKIPPED_TILE_PAIRS 4
 int edmd_cuda_get_stat(edmd_ctx *ctx, int stat, uint64_t *value);

@@ -819,9 +819,7 @@ def test_device_thermostat_tick_matches_oracle(pkg, oracle, n, phi, seed, sf):
     with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
         ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=t0)
         ctx.predict_all()
-        lean_before = ctx.stat(pkg.binding.STAT_LEAN_SWEEPS)
         got = _device_tick(ctx, t1, T)
-        lean_after = ctx.stat(pkg.binding.STAT_LEAN_SWEEPS)
     want = oracle.tick_rescale(n, c["lx"], c["ly"], t0, t1, T, c["x"], c["y"], c["vx"], c["vy"], c["rad"])
     assert want["rc"] == 0
     assert abs(got["E_before"] - want["E_before"]) <= TICK_RTOL * want["E_before"]
@@ -835,4 +833,26 @@ def test_device_thermostat_tick_matches_oracle(pkg, oracle, n, phi, seed, sf):
     for k in ("t_cross", "t_coll"):
         ok = np.abs(got[k] - want[k]) <= TICK_RTOL * np.abs(want[k])
         assert (ok | ~same).all(), k
-    assert lean_after == lean_before + 1     # the rescaled state stays on the lean path
+
+
+def test_rescale_keeps_the_lean_path_and_the_sweep_exact(pkg, oracle):
+    """The rescale refreshes the velocity bound of the lean sweep's error model on the
+    device: the next sweep still runs (and certifies) on the lean path, bit-exact
+    for the rescaled velocities.  (A batched free flight that carries particles
+    across the periodic edge without their crossing events -- as the synthetic ticks
+    above do -- makes the device decline the lean path: positions then sit a box
+    length from their filed cells.)"""
+    c = pkg.synth.lattice_config(300000, 0.70, seed=54)
+    B = pkg.binding
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"] * 7.0, c["vy"] * 7.0, c["rad"], t=1.0)
+        ctx.predict_all()
+        r = ctx.rescale_velocities(0.01)          # a 70-fold change of the velocity scale
+        assert ctx.stat(B.STAT_LEAN_ELIGIBLE) == 1
+        got = ctx.predict_all()
+        s = ctx.download_state()
+        assert ctx.stat(B.STAT_LEAN_SWEEPS) == 2 and ctx.stat(B.STAT_LEAN_DECLINES) == 0
+    assert abs(r["divisor"] - np.sqrt(r["E_before"] / c["n"] / 0.01)) <= 1e-15 * r["divisor"]
+    assert np.array_equal(s["vx"], c["vx"] * 7.0 / r["divisor"])
+    want = oracle.predict_all(c["n"], c["lx"], c["ly"], 1.0, c["x"], c["y"], s["vx"], s["vy"], c["rad"])
+    assert_events_equal(got, want)

@@ -289,9 +289,15 @@ def run_slabs(args, pkg, rank, world, local):
         barrier()
     clocks = clk.summary()
     ms_step, ms_k1, ms_e2e = float(np.mean(tot)), float(np.mean(main)), 1e3 * float(np.mean(e2e))
-    tt = torch.tensor([ms_step, ms_k1, ms_e2e, float(n_local)], device="cuda", dtype=torch.float64)
+    # BASELINE configs[3] second half: g(r) of the whole N-GPU system, pairs split over the ranks
+    ms_gr, gr_pairs = 0.0, 0
+    if args.analysis == "full":
+        max_r = min(lx, ly) / 2
+        counts, ms_gr = sr.pcf(dist, cfg["x"][gid], cfg["y"][gid], N, 0.1, max_r)
+        gr_pairs = int(counts.sum())
+    tt = torch.tensor([ms_step, ms_k1, ms_e2e, float(n_local), ms_gr], device="cuda", dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_step, ms_k1, ms_e2e, n_local_max = tt.tolist()
+    ms_step, ms_k1, ms_e2e, n_local_max, ms_gr = tt.tolist()
     if rank == 0:
         peak, how = peaks()
         achieved = BYTES_PER_PARTICLE * n_owned / (ms_k1 * 1e-3) / 1e9
@@ -314,6 +320,13 @@ def run_slabs(args, pkg, rank, world, local):
                          "peak_source": how + " (burst copy)", "traffic": profile_traffic(),
                          "ms_kernel": ms_k1, "bytes_per_particle": BYTES_PER_PARTICLE},
         }
+        if args.analysis == "full":
+            line["analysis"] = {
+                "gr_full_ms": ms_gr, "gr_full_bins": int(min(lx, ly) / 2 / 0.1),
+                "gr_full_pairs_per_s": N * (N - 1) / 2 / (ms_gr * 1e-3), "gr_pairs_binned": gr_pairs,
+                "note": "calculate_pcf dr=0.1 max_r=min(L)/2 of the whole system: all-gather of the positions "
+                        "(NCCL) + sorted-tile kernel on the tile pairs w = rank (mod N) + all-reduce of the "
+                        "counts, CUDA events, max over ranks"}
         print(json.dumps(line, default=float))
     sr.close()
 

@@ -166,3 +166,42 @@ class SlabRank:
 
     def predict(self):
         return self.ctx.predict_all()
+
+    def pcf(self, dist, x_owned, y_owned, n_total: int, dr: float, max_r: float):
+        """g(r) of the whole system across the ranks (calculate_pcf, src/pcf.c:16-75):
+        the owned positions are all-gathered (NCCL), every rank sorts them into the
+        same tiles and bins the tile pairs w = rank (mod world)
+        (edmd_cuda_pcf_device), the integer counts are all-reduced.  Returns the
+        counts (uint64, every rank) and the device time of the three stages in ms."""
+        torch = self.torch
+        dev = torch.device("cuda", self.device)
+        own_xy = torch.from_numpy(np.stack([x_owned, y_owned], 1)).to(dev)
+        sizes = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(sizes, int(own_xy.shape[0]))
+        else:
+            sizes = [int(own_xy.shape[0])]
+        assert sum(sizes) == n_total
+        cap = max(sizes)
+        pad = torch.zeros(cap, 2, dtype=torch.float64, device=dev)
+        pad[: own_xy.shape[0]] = own_xy
+        nb = int(max_r / dr)
+        counts = torch.zeros(max(nb, 1), dtype=torch.int64, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        ev[0].record()
+        if self.world > 1:
+            allpad = torch.empty(self.world * cap, 2, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allpad, pad)
+            xy = torch.cat([allpad[r * cap: r * cap + sizes[r]] for r in range(self.world)]).contiguous()
+        else:
+            xy = own_xy.contiguous()
+        torch.cuda.synchronize()      # the library bins on its own stream
+        self.ctx.pcf_device(xy.data_ptr(), n_total, dr, max_r, self.rank, self.world, counts.data_ptr())
+        if self.world > 1:
+            dist.all_reduce(counts)
+        ev[1].record()
+        torch.cuda.synchronize()
+        return counts[:nb].cpu().numpy().astype(np.uint64), ev[0].elapsed_time(ev[1])

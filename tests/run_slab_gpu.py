@@ -50,21 +50,13 @@ def main():
                 out = sr.predict()
         gathered = [None] * world
         dist.all_gather_object(gathered, {"gid": gid, **{k: out[k] for k in ("t_cross", "dir", "t_coll", "partner", "ctype")}})
-        # g(r): all-gather owned positions, bin my share of the pairs, all-reduce the counts
-        own_xy = torch.from_numpy(np.stack([cfg["x"][gid], cfg["y"][gid]], 1)).cuda()
-        sizes = [None] * world
-        dist.all_gather_object(sizes, own_xy.shape[0])
-        pad = torch.zeros(max(sizes), 2, dtype=torch.float64, device="cuda")
-        pad[: own_xy.shape[0]] = own_xy
-        allpad = torch.empty(world * max(sizes), 2, dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(allpad, pad)
-        xy = torch.cat([allpad[r * max(sizes): r * max(sizes) + sizes[r]] for r in range(world)]).contiguous()
+        # g(r): all-gather owned positions, bin my share of the tile pairs, all-reduce the counts
         dr, max_r = 0.1, 15.0
-        nb = int(max_r / dr)
-        counts = torch.zeros(nb, dtype=torch.int64, device="cuda")
-        torch.cuda.synchronize()
-        sr.ctx.pcf_device(xy.data_ptr(), N, dr, max_r, rank, world, counts.data_ptr())
-        dist.all_reduce(counts)
+        counts, _ = sr.pcf(dist, cfg["x"][gid], cfg["y"][gid], N, dr, max_r)
+        # full range on the larger system: the sorted-tile kernel, tiles cut identically on every rank
+        counts_full = None
+        if N >= 8192:
+            counts_full, _ = sr.pcf(dist, cfg["x"][gid], cfg["y"][gid], N, 0.25, min(lx, ly) / 2)
         if rank == 0:
             want = orc.predict_all(N, lx, ly, t, cfg["x"], cfg["y"], cfg["vx"], cfg["vy"], cfg["rad"])
             seen = np.zeros(N, bool)
@@ -77,9 +69,14 @@ def main():
             ok = ok and bool(seen.all())
             if N < 100000:   # the oracle's g(r) is O(N^2)
                 wp = orc.pcf(N, lx, ly, cfg["x"], cfg["y"], dr, max_r)
-                if not np.array_equal(counts.cpu().numpy().astype(np.uint64), wp["counts"]):
+                if not np.array_equal(counts, wp["counts"]):
                     ok = False
                     print("MISMATCH g(r) counts")
+                if counts_full is not None:
+                    wf = orc.pcf(N, lx, ly, cfg["x"], cfg["y"], 0.25, min(lx, ly) / 2)
+                    if not np.array_equal(counts_full, wf["counts"]):
+                        ok = False
+                        print("MISMATCH full-range g(r) counts (sorted tiles)")
             print(f"slab check N={N} phi={phi} world={world} halo={'NVLink peer stores' if p2p else 'NCCL send/recv'}: "
                   f"sweep + g(r) {'bit-exact' if ok else 'FAILED'}")
         sr.close()

@@ -453,8 +453,21 @@ def run_ours(args, cfg):
             analysis["gr_full_pairs_per_s"] = pairs / (pt[0] * 1e-3)
             analysis["gr_full_fp64_tflops_9op"] = 9 * pairs / (pt[0] * 1e-3) / 1e12
             analysis["frames_per_s_gr_full_plus_psi6"] = 1e3 / (pt[0] + np.mean(bt))
+            # the same frame with every bin certified in FP64 (the previous default kernel):
+            # its time, and the two histograms compared bin by bin at full size
+            e0 = ctx.stat(B.STAT_PCF_EXACT_PAIRS)
+            fast = ctx.pcf(0.1, max_r)["counts"]
+            analysis["gr_full_exact_path_share"] = (ctx.stat(B.STAT_PCF_EXACT_PAIRS) - e0) / pairs
+            ctx.set_option(B.OPT_PCF_LEGACY, 2)
+            p64, _ = ctx.bench(B.BENCH_PCF, dr=0.1, max_r=max_r, warmup=0, iters=1)
+            slow = ctx.pcf(0.1, max_r)["counts"]
+            ctx.set_option(B.OPT_PCF_LEGACY, 0)
+            analysis["gr_full_ms_fp64_certified_kernel"] = float(p64[0])
+            analysis["gr_full_counts_equal_fp64_certified"] = bool(np.array_equal(fast, slow))
+            analysis["gr_full_pairs_in_range"] = int(fast.sum())
         analysis["note"] = ("psi6 = computeBOOPCutoff r_c=2.5 (56 B/particle, HBM); g(r) full range = "
-                            "calculate_pcf dr=0.1 max_r=min(L)/2, all N(N-1)/2 pairs (FP64 pipe)")
+                            "calculate_pcf dr=0.1 max_r=min(L)/2, all N(N-1)/2 pairs; bins decided in FP32 under "
+                            "a rigorous error bound, undecided pairs (exact_path_share) redone in FP64")
         del max_r_cut
 
     cpu = cpu_baseline(cfg) if (rank == 0 and world == 1 and not args.no_cpu) else None

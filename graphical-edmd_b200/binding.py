@@ -47,6 +47,7 @@ SYMBOLS = [
     "edmd_cuda_calendar_plan", "edmd_cuda_pcf_bond_order", "edmd_cuda_bragg_peak",
     "edmd_cuda_boop_voronoi", "edmd_cuda_voronoi_cells", "edmd_cuda_g6_correlation",
     "edmd_cuda_structure_factor", "edmd_cuda_kinetic", "edmd_cuda_rescale_velocities",
+    "edmd_cuda_selftest_rsqrt",
 ]
 EVORONOI = 7
 HALO_RECORD_BYTES = 48
@@ -121,6 +122,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_calendar_plan.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, vp,
                                             C.POINTER(C.c_int32)]
     lib.edmd_cuda_get_stat.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
+    lib.edmd_cuda_selftest_rsqrt.argtypes = [vp, C.POINTER(C.c_double)]
     lib.edmd_cuda_kinetic.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.edmd_cuda_rescale_velocities.argtypes = [vp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.edmd_cuda_boop_voronoi.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -304,6 +306,12 @@ class EdmdCuda:
         out = [np.empty(n, np.float64) for _ in range(5)]
         self._check(self.lib.edmd_cuda_download_state(self._h, *[_ptr(a) for a in out]))
         return dict(zip(("x", "y", "vx", "vy", "rad"), out))
+
+    def selftest_rsqrt(self) -> float:
+        """Largest relative error of the hardware rsqrt over [2^-100, 2^64) (edmd_cuda_selftest_rsqrt)."""
+        v = C.c_double(0.0)
+        self._check(self.lib.edmd_cuda_selftest_rsqrt(self._h, C.byref(v)))
+        return float(v.value)
 
     def pcf_num_bins(self, dr, max_r) -> int:
         nb = C.c_int(0)

@@ -285,7 +285,7 @@ int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const do
     if (n < 2 || num_bins <= 0) return 0;
     // large systems: spatially sorted tiles + certified bins (analysis_pcf_sorted.cu); for
     // the multi-GPU split the sort is made deterministic so that every rank cuts the same tiles
-    if (n >= 8192 && !c->pcf_legacy) {
+    if (n >= 8192 && c->pcf_mode != 1) {
         const int r = edmd_launch_pcf_sorted(c, dr, max_r, num_bins, xy, stride, n, part, nparts, counts);
         if (r >= 0) return r;
     }

@@ -52,6 +52,7 @@ __device__ __forceinline__ int coarse_cell(const SortArgs &a, double x, double y
     int cx = (int)(x * a.fx), cy = (int)(y * a.fy);
     cx = min(max(cx, 0), a.gx - 1);
     cy = min(max(cy, 0), a.gy - 1);
+    if (cy & 1) cx = a.gx - 1 - cx;   // boustrophedon: consecutive tiles stay compact at row ends
     return cy * a.gx + cx;
 }
 
@@ -129,16 +130,20 @@ k_coarse_order(int ncoarse, const int32_t *__restrict__ cend, const double2 *__r
     }
 }
 
-// exact bounding box of each tile
+// exact bounding box of each tile; optionally also the tile centre and the FP32
+// coordinates of its particles relative to that centre in units of dr (k_pcf_f32)
 __global__ void __launch_bounds__(kTile)
-k_tile_bbox(int n, const double2 *__restrict__ sorted, double4 *__restrict__ bbox)
+k_tile_bbox(int n, const double2 *__restrict__ sorted, double4 *__restrict__ bbox, double inv_dr,
+            double2 *__restrict__ ctr, float2 *__restrict__ rel)
 {
     __shared__ double s[4][kTile / 32];
+    __shared__ double2 s_ctr;
     const int i = blockIdx.x * kTile + threadIdx.x;
     const double big = 1e300;
     double x0 = big, x1 = -big, y0 = big, y1 = -big;
+    double2 p = make_double2(0.0, 0.0);
     if (i < n) {
-        const double2 p = sorted[i];
+        p = sorted[i];
         x0 = x1 = p.x;
         y0 = y1 = p.y;
     }
@@ -160,6 +165,17 @@ k_tile_bbox(int n, const double2 *__restrict__ sorted, double4 *__restrict__ bbo
             y0 = fmin(y0, s[2][w]); y1 = fmax(y1, s[3][w]);
         }
         bbox[blockIdx.x] = make_double4(x0, x1, y0, y1);
+        if (rel) {
+            s_ctr = make_double2(0.5 * (x0 + x1), 0.5 * (y0 + y1));
+            ctr[blockIdx.x] = s_ctr;
+        }
+    }
+    if (rel) {
+        __syncthreads();
+        if (i < n) {
+            const double2 c = s_ctr;
+            rel[i] = make_float2(__double2float_rn((p.x - c.x) * inv_dr), __double2float_rn((p.y - c.y) * inv_dr));
+        }
     }
 }
 
@@ -353,7 +369,334 @@ k_pcf_sorted(const __grid_constant__ PcfArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------
+// k_pcf_f32 -- the bin of a pair decided in FP32 with a RIGOROUS error bound,
+// the FP64 arithmetic of the reference only for the pairs FP32 cannot settle.
+//
+// Per tile the particles are stored as FP32 offsets from the tile centre in units
+// of dr (b_j, by k_tile_bbox).  Per tile pair (a, b) one thread derives from the two
+// exact bounding boxes
+//   * the periodic image every pair of the tile pair takes (S = 0, -L or +L per
+//     axis), or that the pairs are mixed (then |d| >= L/2 -> |d| - L per pair, in
+//     FP32: the magnitude after the reference's single wrap is a 1-Lipschitz
+//     function of d, so a different decision next to the threshold costs no more
+//     than the rounding error that caused it);
+//   * a bound eps on |q32 - q*|, q* = the reference's FP64 sqrt(dx^2+dy^2)/dr and
+//     q32 its FP32 estimate (derivation below);
+//   * whether every pair is in range (then the range test is dropped).
+// Thread i holds p_i = fl32(((x_i - S) - C_b) / dr); per pair
+//     d = b_j - p_i,  s = fma(dy, dy, fma(dx, dx, 1e-30)),  q32 = s * rsqrt(s),
+//     t = RD(q32 + 1.5 * 2^23)          (bits of t = 0x4B400000 + floor(q32), exact)
+//     frac = q32 - (t - 1.5 * 2^23)     (exact)
+// and the pair is CERTAIN when eps <= frac <= 1 - eps (floor(q*) = floor(q32)) and
+// q32 < lim (in range, bin < num_bins); it is certainly out of range when
+// q32 > hi; everything else goes to a shared-memory queue that the CTA drains with
+// the reference's own FP64 operations (~1 % of the pairs at N = 10^6, dr = 0.1).
+//
+// Error bound (u = 2^-24, lengths in units of dr):
+//   b_j, p_i are roundings of FP64 values: |err| <= u |b_j| <= u h_b and
+//   u |p_i| <= u (h_b + M) with h_b the half extent of tile b and M the largest
+//   |d| of the tile pair; the subtraction adds u |d| <= u M:
+//       E_axis = u (2 h_b + 2 M) (+ u L when the FP32 wrap subtracts fl32(L)),
+//   E = |(E_x, E_y)|; by the triangle inequality the exact norm of the FP32 vector is
+//   within E of the true distance.  s carries two roundings (<= 2u), the MUFU
+//   rsqrt <= 3.0e-7 relative (PTX: 2^-22.9; edmd_cuda_selftest_rsqrt measures it
+//   exhaustively, the test asserts <= 2^-22), the product one more:
+//       |q32 - q_true| <= (R + E) (3.0e-7 + 4u) + E + 1e-15 (the 1e-30 floor)
+//   with R the largest distance of the tile pair.  FP64 roundings on either side
+//   (ours and the reference's) stay below 2^-48 L/dr; 2^-44 (L/dr + 1) is budgeted.
+// ---------------------------------------------------------------------------
+constexpr int kQueue = 2048;                 // undecided pairs parked per tile pair (u32 each: counted bin | i | j)
+constexpr float kMagic = 12582912.0f;        // 1.5 * 2^23
+constexpr uint32_t kMagicBits = 0x4B400000u;
+
+struct TilePairPlan {
+    double2 cbs;         // C_b + S: p_i = ((x_i - cbs.x) / dr, ...)
+    float c;             // certain  <=>  |frac - 0.5| <= c   (c = 0.5 - eps, rounded down)
+    float lim, hi;       // take needs q32 < lim; q32 > hi is certainly out of range
+    int flags;           // 1 wrap x per pair, 2 wrap y per pair, 4 every pair in range, 8 skip
+};
+
+struct F32Args {
+    PcfArgs p;
+    const float2 *rel;
+    const double2 *ctr;
+    double inv_dr, q_maxr, slack;
+    float lx32, ly32, hx32, hy32;   // fl32(L / dr) and exactly half of it
+};
+
+__device__ __forceinline__ float2 lds_float2(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ float4 lds_float4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// the reference's own arithmetic for one pair (pcf.c:34-47 + PBC), into the shared histogram;
+// `counted` = the FP32 bin this pair was already counted in (kNotCounted: none)
+constexpr unsigned int kNotCounted = 0xFFFFu;
+
+__device__ __forceinline__ void exact_pair(const PcfArgs &a, int gi, int gj, uint32_t hist_addr, unsigned int counted)
+{
+    const double2 pi = a.sorted[gi], pj = a.sorted[gj];
+    const double dx = min_image(__dsub_rn(pj.x, pi.x), a.b.half_lx, a.b.lx);
+    const double dy = min_image(__dsub_rn(pj.y, pi.y), a.b.half_ly, a.b.ly);
+    const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    unsigned int bin = kNotCounted;
+    if (s < a.s_max) {
+        const int k = (int)__ddiv_rn(__dsqrt_rn(s), a.dr);
+        if (k < a.num_bins) bin = (unsigned int)k;
+    }
+    if (bin == counted) return;
+    if (counted != kNotCounted) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * counted), "r"(0xFFFFFFFFu) : "memory");
+    if (bin != kNotCounted) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * bin), "r"(1u) : "memory");
+}
+
+// One pair in FP32.  INR (every pair of the tile pair certainly in range): the pair is
+// counted in its FP32 bin unconditionally -- no predicate, no branch -- and an undecided
+// pair is corrected by the exact path afterwards (minus one here, plus one there).
+// Otherwise a pair that is not taken increments a per-lane dummy slot behind the histogram.
+// Returns whether the pair must go to the exact path; tbits = bits of t (bin = tbits - kMagicBits).
+template <bool WX, bool WY, bool INR>
+__device__ __forceinline__ bool pair32(float bx, float by, float px, float py, float c, float lim, float hi,
+                                       float lx32, float ly32, float hx32, float hy32, uint32_t hbase,
+                                       uint32_t trash, uint32_t &tbits)
+{
+    float dx = __fsub_rn(bx, px), dy = __fsub_rn(by, py);
+    if (WX) {
+        const float m = fabsf(dx);
+        dx = m >= hx32 ? __fsub_rn(m, lx32) : m;
+    }
+    if (WY) {
+        const float m = fabsf(dy);
+        dy = m >= hy32 ? __fsub_rn(m, ly32) : m;
+    }
+    const float s = __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, 1e-30f));
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+    const float q = __fmul_rn(s, y);
+    const float t = __fadd_rd(q, kMagic);
+    const float frac = __fsub_rn(q, __fsub_rn(t, kMagic));
+    const bool cert = fabsf(__fsub_rn(frac, 0.5f)) <= c;
+    tbits = __float_as_uint(t);
+    const uint32_t addr = hbase + (tbits << 2);
+    if (INR) {
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
+        return !cert;
+    }
+    const bool take = cert && q < lim;
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(take ? addr : trash), "r"(1u) : "memory");
+    return !take && q <= hi;
+}
+
+template <bool WX, bool WY, bool INR>
+__device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan &tp, float px, float py, int gi0,
+                                            int gj0, uint32_t tile_addr, int jstart, int jcount, uint32_t hist_addr,
+                                            uint32_t queue_addr, int *qn, unsigned int &slow)
+{
+    const float c = tp.c, lim = tp.lim, hi = tp.hi;
+    const float lx32 = a.lx32, ly32 = a.ly32, hx32 = a.hx32, hy32 = a.hy32;
+    uint32_t hbase, trash;
+    // opaque moves: keep the two addresses in registers instead of re-deriving them per trip
+    asm volatile("mov.u32 %0, %1;" : "=r"(hbase) : "r"(hist_addr - (kMagicBits << 2)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(trash) : "r"(hist_addr + 4u * (uint32_t)(a.p.num_bins + (threadIdx.x & 31))));
+    auto park = [&](int j, uint32_t tbits) {
+        const unsigned int counted = INR ? (tbits - kMagicBits) & 0xFFFFu : kNotCounted;
+        const int slot = atomicAdd(qn, 1);
+        if (slot < kQueue) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(queue_addr + 4u * (uint32_t)slot),
+                         "r"((counted << 16) | (threadIdx.x << 8) | (unsigned int)j)
+                         : "memory");
+        } else {
+            exact_pair(a.p, gi0 + (int)threadIdx.x, gj0 + j, hist_addr, counted);
+            slow++;
+        }
+    };
+    int jj = jstart;
+    uint32_t tb;
+    for (; jj < jcount && (jj & 3); jj++) {
+        const float2 b = lds_float2(tile_addr + 8u * (uint32_t)jj);
+        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, tb)) park(jj, tb);
+    }
+    uint32_t addr = tile_addr + 8u * (uint32_t)jj;
+    for (; jj + 4 <= jcount; jj += 4, addr += 32u) {
+        const float4 b01 = lds_float4(addr), b23 = lds_float4(addr + 16u);
+        uint32_t t0, t1, t2, t3;
+        const bool u0 = pair32<WX, WY, INR>(b01.x, b01.y, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t0);
+        const bool u1 = pair32<WX, WY, INR>(b01.z, b01.w, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t1);
+        const bool u2 = pair32<WX, WY, INR>(b23.x, b23.y, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t2);
+        const bool u3 = pair32<WX, WY, INR>(b23.z, b23.w, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t3);
+        if (u0 | u1 | u2 | u3) {
+            if (u0) park(jj, t0);
+            if (u1) park(jj + 1, t1);
+            if (u2) park(jj + 2, t2);
+            if (u3) park(jj + 3, t3);
+        }
+    }
+    for (; jj < jcount; jj++) {
+        const float2 b = lds_float2(tile_addr + 8u * (uint32_t)jj);
+        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, tb)) park(jj, tb);
+    }
+}
+
+// One axis of the tile-pair plan: the image shift S every pair takes (or per-pair
+// wrapping), the largest |d| before (m_un) and after (m_w) the wrap, the gap for
+// the skip test.  d0, d1 = range of fl(x_b - x_a) over the tile pair.
+__device__ __forceinline__ void plan_axis(double d0, double d1, double half, double len, double &shift, bool &wrap,
+                                          double &m_un, double &m_w, double &g)
+{
+    shift = 0.0;
+    wrap = false;
+    if (d1 < half && d0 >= -half) {
+        g = gap(d0, d1);
+    } else if (d0 >= half) {
+        shift = -len;
+        g = gap(d0 - len, d1 - len);
+    } else if (d1 < -half) {
+        shift = len;
+        g = gap(d0 + len, d1 + len);
+    } else {
+        wrap = true;
+        g = fmin(gap(d0, d1), fmin(gap(d0 - len, d1 - len), gap(d0 + len, d1 + len)));
+    }
+    m_un = fmax(fabs(d0 + shift), fabs(d1 + shift)) * (1.0 + 1e-12);
+    m_w = wrap ? fmax(half, m_un - len) : m_un;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_pcf_f32(const __grid_constant__ F32Args a)
+{
+    extern __shared__ unsigned char smem_raw[];
+    float2 *tile = reinterpret_cast<float2 *>(smem_raw);
+    unsigned int *queue = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2));
+    unsigned int *hist = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2) + kQueue * sizeof(unsigned int));
+    __shared__ TilePairPlan s_tp;
+    __shared__ int s_qn;
+    const PcfArgs &p = a.p;
+    for (int k = threadIdx.x; k < p.num_bins; k += kThreads) hist[k] = 0;
+    const int nt = (p.n + kTile - 1) / kTile;
+    const long long npairs = (long long)nt * (nt + 1) / 2;
+    unsigned int slow = 0, skipped = 0;
+    const double rcut = p.max_r * (1.0 + 1e-12);
+    const uint32_t tile_addr = smem_addr(tile), hist_addr = smem_addr(hist), queue_addr = smem_addr(queue);
+    for (long long w = (long long)blockIdx.x * p.nparts + p.part; w < npairs; w += (long long)gridDim.x * p.nparts) {
+        const double fn = (double)nt + 0.5;
+        long long ta = (long long)(fn - sqrt(fn * fn - 2.0 * (double)w));
+        while (ta * nt - ta * (ta - 1) / 2 > w) ta--;
+        while ((ta + 1) * nt - (ta + 1) * ta / 2 <= w) ta++;
+        const long long tb = ta + (w - (ta * nt - ta * (ta - 1) / 2));
+        __syncthreads();   // previous tile pair drained, plan and tile consumed
+        if (threadIdx.x == 0) {
+            const double4 A = p.bbox[ta], B = p.bbox[tb];
+            double sx, sy, mxu, mxw, myu, myw, gx, gy;
+            bool wx, wy;
+            plan_axis(B.x - A.y, B.y - A.x, p.b.half_lx, p.b.lx, sx, wx, mxu, mxw, gx);
+            plan_axis(B.z - A.w, B.w - A.z, p.b.half_ly, p.b.ly, sy, wy, myu, myw, gy);
+            TilePairPlan tp;
+            if (gx * gx + gy * gy >= rcut * rcut) {
+                tp.flags = 8;
+            } else {
+                const double u = 5.9604644775390625e-08 * 1.001;   // 2^-24, padded
+                const double id = a.inv_dr;
+                const double hbx = 0.5 * (B.y - B.x) * id, hby = 0.5 * (B.w - B.z) * id;
+                const double ex = u * (2.0 * hbx + 2.0 * mxu * id) + (wx ? u * p.b.lx * id : 0.0) + a.slack;
+                const double ey = u * (2.0 * hby + 2.0 * myu * id) + (wy ? u * p.b.ly * id : 0.0) + a.slack;
+                const double e = sqrt(ex * ex + ey * ey) * 1.001;
+                const double rmax = sqrt(mxw * mxw + myw * myw) * id * (1.0 + 1e-9);
+                const double rho = 3.0e-7 + 4.0 * u;
+                const double eps = ((rmax + e) * rho + e + 1e-14 + a.slack) * 1.001 + 2.384185791015625e-07;   // + 2^-22
+                const float eps32 = __double2float_ru(eps);
+                tp.c = __double2float_rd(0.5 - (double)eps32);
+                const double lim = fmin(a.q_maxr - (double)eps32 - a.slack, (double)p.num_bins);
+                tp.lim = __double2float_rd(lim);
+                tp.hi = __double2float_ru(a.q_maxr + (double)eps32 + a.slack);
+                const bool inr = (rmax + e) * (1.0 + 1e-6) < (double)tp.lim;
+                tp.flags = (wx ? 1 : 0) | (wy ? 2 : 0) | ((inr && !wx && !wy) ? 4 : 0);
+                const double2 cb = a.ctr[tb];
+                tp.cbs = make_double2(cb.x + sx, cb.y + sy);
+            }
+            s_tp = tp;
+            s_qn = 0;
+        }
+        __syncthreads();
+        const int flags = s_tp.flags;
+        if (flags == 8) {
+            skipped++;
+            continue;
+        }
+        const int gi0 = (int)ta * kTile, gj0 = (int)tb * kTile;
+        if (gj0 + (int)threadIdx.x < p.n) tile[threadIdx.x] = a.rel[gj0 + threadIdx.x];
+        __syncthreads();
+        const int i = gi0 + threadIdx.x;
+        if (i < p.n) {
+            const double2 pi = p.sorted[i];
+            const double2 cbs = s_tp.cbs;
+            const float px = __double2float_rn((pi.x - cbs.x) * a.inv_dr);
+            const float py = __double2float_rn((pi.y - cbs.y) * a.inv_dr);
+            const int jcount = min(kTile, p.n - gj0);
+            const int jstart = (ta == tb) ? threadIdx.x + 1 : 0;
+            switch (flags) {
+            case 4: pair_loop32<false, false, true>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, &s_qn, slow); break;
+            case 0: pair_loop32<false, false, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, &s_qn, slow); break;
+            case 1: pair_loop32<true, false, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, &s_qn, slow); break;
+            case 2: pair_loop32<false, true, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, &s_qn, slow); break;
+            default: pair_loop32<true, true, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, &s_qn, slow); break;
+            }
+        }
+        __syncthreads();
+        // drain: the parked pairs with the reference's FP64 operations
+        const int qn = min(s_qn, kQueue);
+        for (int k = threadIdx.x; k < qn; k += kThreads) {
+            const unsigned int e = queue[k];
+            exact_pair(p, gi0 + (int)((e >> 8) & 255u), gj0 + (int)(e & 255u), hist_addr, e >> 16);
+            slow++;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < p.num_bins; k += kThreads) {
+        const unsigned int v = hist[k];
+        if (v) atomicAdd(&p.counts[k], (unsigned long long)v);
+    }
+    if (p.stats) {
+        if (slow) atomicAdd(&p.stats[0], (unsigned long long)slow);
+        if (threadIdx.x == 0 && skipped) atomicAdd(&p.stats[1], (unsigned long long)skipped);
+    }
+}
+
+// largest relative error of the MUFU reciprocal square root over every float in
+// [2^-100, 2^64) (the kernel's s lies in [1e-30, 2^46)): the measured side of the
+// 3.0e-7 budgeted in k_pcf_f32
+__global__ void __launch_bounds__(256)
+k_rsqrt_selftest(unsigned long long *worst_bits)
+{
+    double worst = 0.0;
+    const uint32_t lo = (127u - 100u) << 23, hi = (127u + 64u) << 23;
+    for (uint64_t b = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < hi; b += (uint64_t)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((uint32_t)b);
+        float y;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        const double rel = fabs((double)y * sqrt((double)x) - 1.0);
+        worst = fmax(worst, rel);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(worst_bits, (unsigned long long)__double_as_longlong(worst));
+}
+
 }  // namespace
+
+int edmd_launch_rsqrt_selftest(edmd_ctx *c, unsigned long long *worst_bits_dev)
+{
+    k_rsqrt_selftest<<<(c->sm_count > 0 ? c->sm_count : 148) * 8, 256, 0, c->stream>>>(worst_bits_dev);
+    return 1;
+}
 
 // smallest double s with correctly rounded sqrt(s) >= max_r
 static double s_threshold(double max_r)
@@ -369,7 +712,7 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
                            int n, int part, int nparts, unsigned long long *counts)
 {
     if (n < 2 || num_bins <= 0) return 0;
-    // coarse cells of ~192 particles, row-major
+    // coarse cells of ~192 particles, row-major (alternate rows reversed)
     const double area = c->box.lx * c->box.ly;
     const double side = sqrt(192.0 * area / (double)n);
     int gx = (int)(c->box.lx / side), gy = (int)(c->box.ly / side);
@@ -378,8 +721,15 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     const int ncoarse = gx * gy;
     const int nt = (n + kTile - 1) / kTile;
     const bool ordered = nparts > 1;   // every rank must cut identical tiles
-    const size_t need = (size_t)n * sizeof(double2) * (ordered ? 2 : 1) + (size_t)nt * sizeof(double4) +
-                        ((size_t)n * (ordered ? 2 : 1) + ncoarse + 8) * sizeof(int32_t) + 64;
+    // FP32-decided bins (k_pcf_f32) when the histogram fits in shared memory next to the
+    // queue, q = r/dr stays far below 2^22 and the expected share of undecided pairs
+    // (~2 q_max * 5.4e-7) is small; else bins certified in FP64 (k_pcf_sorted)
+    const double lmax = c->box.lx > c->box.ly ? c->box.lx : c->box.ly;
+    const size_t f32_smem = kTile * sizeof(float2) + kQueue * sizeof(unsigned int) + ((size_t)num_bins + 32) * sizeof(unsigned int);
+    const bool f32 = c->pcf_mode == 0 && f32_smem <= 200 * 1024 && num_bins < 65535 && dr > 0.0 && max_r > 0.0 &&
+                     1.5 * lmax / dr < 2097152.0 && max_r / dr <= 60000.0 && lmax / dr <= 120000.0;
+    const size_t need = (size_t)n * sizeof(double2) * (ordered ? 2 : 1) + (size_t)nt * (sizeof(double4) + sizeof(double2)) +
+                        (size_t)n * sizeof(float2) + ((size_t)n * (ordered ? 2 : 1) + ncoarse + 8) * sizeof(int32_t) + 64;
     if (need > c->pcfs_bytes) {
         if (c->pcfs_mem) cudaFree(c->pcfs_mem);
         c->pcfs_mem = nullptr;
@@ -398,6 +748,10 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     if (ordered) m += (size_t)n * sizeof(double2);
     double4 *bbox = reinterpret_cast<double4 *>(m);
     m += (size_t)nt * sizeof(double4);
+    double2 *ctr = reinterpret_cast<double2 *>(m);
+    m += (size_t)nt * sizeof(double2);
+    float2 *rel = reinterpret_cast<float2 *>(m);
+    m += (size_t)n * sizeof(float2);
     int32_t *cnt = reinterpret_cast<int32_t *>(m);
     int32_t *cell = cnt + ncoarse + 8;
     int32_t *sidx = ordered ? cell + n : nullptr;
@@ -417,7 +771,8 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
         sorted = sorted2;
         launched++;
     }
-    k_tile_bbox<<<nt, kTile, 0, c->stream>>>(n, sorted, bbox);
+    const double inv_dr = 1.0 / dr;
+    k_tile_bbox<<<nt, kTile, 0, c->stream>>>(n, sorted, bbox, inv_dr, f32 ? ctr : nullptr, f32 ? rel : nullptr);
     PcfArgs a;
     a.n = n; a.num_bins = num_bins;
     a.b = c->dbox;
@@ -428,6 +783,34 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     a.inv_dr = (float)(1.0 / dr);
     a.sorted = sorted; a.bbox = bbox; a.counts = counts; a.stats = stats;
     a.part = part; a.nparts = nparts;
+    const long long npairs = ((long long)nt * (nt + 1) / 2 + nparts - 1) / nparts;
+    const long long sms = c->sm_count > 0 ? c->sm_count : 148;
+    if (f32) {
+        F32Args fa;
+        a.use_smem = 1;
+        fa.p = a;
+        fa.rel = rel; fa.ctr = ctr;
+        fa.inv_dr = inv_dr;
+        fa.q_maxr = max_r * inv_dr;
+        fa.slack = 5.684341886080802e-14 * (lmax * inv_dr + 1.0);   // 2^-44 (L/dr + 1)
+        fa.lx32 = (float)(c->box.lx * inv_dr);
+        fa.ly32 = (float)(c->box.ly * inv_dr);
+        fa.hx32 = 0.5f * fa.lx32;
+        fa.hy32 = 0.5f * fa.ly32;
+        static bool attr32 = false;
+        if (!attr32) {
+            cudaFuncSetAttribute(k_pcf_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+            attr32 = true;
+        }
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_f32, kThreads, f32_smem);
+        if (per_sm < 1) per_sm = 1;
+        long long grid = sms * per_sm;
+        if (grid > npairs) grid = npairs;
+        if (grid < 1) grid = 1;
+        k_pcf_f32<<<(int)grid, kThreads, f32_smem, c->stream>>>(fa);
+        return launched;
+    }
     const size_t tile_bytes = kTile * sizeof(double2);
     const size_t hist_bytes = (size_t)num_bins * sizeof(unsigned int);
     a.use_smem = (tile_bytes + hist_bytes) <= 200 * 1024;
@@ -440,8 +823,7 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_sorted, kThreads, smem);
     if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)(c->sm_count > 0 ? c->sm_count : 148) * per_sm;
-    const long long npairs = ((long long)nt * (nt + 1) / 2 + nparts - 1) / nparts;
+    long long grid = sms * per_sm;
     if (grid > npairs) grid = npairs;
     if (grid < 1) grid = 1;
     k_pcf_sorted<<<(int)grid, kThreads, smem, c->stream>>>(a);

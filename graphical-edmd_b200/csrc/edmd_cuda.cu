@@ -344,7 +344,7 @@ int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
         return 0;
     }
     if (option == EDMD_OPT_PCF_LEGACY) {
-        c->pcf_legacy = value != 0;
+        c->pcf_mode = (value == 1 || value == 2) ? value : 0;
         return 0;
     }
     if (option == EDMD_OPT_NO_PDL) {
@@ -884,6 +884,26 @@ int edmd_cuda_pcf(edmd_ctx *c, double dr, double max_r, uint64_t *counts, double
             g_r[i] = norm > 0 ? g / norm : 0.0;
         }
     }
+    return 0;
+}
+
+int edmd_cuda_selftest_rsqrt(edmd_ctx *c, double *max_rel_err)
+{
+    if (!c || !max_rel_err) return EDMD_EINVAL;
+    CU(cudaSetDevice(c->device));
+    if (c->pcf_cap < 1) {
+        int r = dev_alloc(c, &c->pcf_counts, (size_t)64);
+        if (r) return r;
+        c->pcf_cap = 64;
+    }
+    CU(cudaMemsetAsync(c->pcf_counts, 0, sizeof(unsigned long long), c->stream));
+    c->launches += edmd_launch_rsqrt_selftest(c, c->pcf_counts);
+    CU(cudaGetLastError());
+    unsigned long long bits = 0;
+    int r = d2h(c, &bits, c->pcf_counts, sizeof(bits));
+    if (r) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(max_rel_err, &bits, sizeof(double));
     return 0;
 }
 

@@ -223,7 +223,7 @@ struct edmd_ctx {
     char *pcfs_mem;                   // sorted-tile g(r) scratch (analysis_pcf_sorted.cu)
     size_t pcfs_bytes;
     unsigned long long *pcfs_stats;   // [0] pairs binned by the exact path, [1] tile pairs skipped
-    bool pcf_legacy;                  // EDMD_OPT_PCF_LEGACY
+    int pcf_mode;                     // EDMD_OPT_PCF_LEGACY: 0 FP32-decided sorted tiles, 1 plain kernel, 2 FP64-certified sorted tiles
     unsigned long long *pcf_wsum;     // weighted sums (2^-32 fixed point), capacity pcf_wcap bins
     int pcf_wcap;
     int pcf_cap;
@@ -298,6 +298,7 @@ double *edmd_launch_kinetic(edmd_ctx *c, double T, double *scratch, int *launche
 int edmd_launch_rescale(edmd_ctx *c, const double *red);
 int edmd_launch_bragg(edmd_ctx *c, int nk, const double2 *kvec, double *re, double *im, double *best_s,
                       int *best_i);
+int edmd_launch_rsqrt_selftest(edmd_ctx *c, unsigned long long *worst_bits_dev);
 int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
                            int n, int part, int nparts, unsigned long long *counts);
 int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,

@@ -90,9 +90,11 @@ uint64_t edmd_cuda_launch_count(const edmd_ctx *ctx);
 /* EDMD_OPT_NO_PDL = 1 launches the lean sweep's kernel chain without programmatic
  * dependent launch (plain stream order); for timing comparisons. */
 #define EDMD_OPT_NO_PDL 3
-/* EDMD_OPT_PCF_LEGACY = 1 makes edmd_cuda_pcf use the plain tile kernel (IEEE sqrt and
- * division per pair, id-ordered tiles) instead of the sorted-tile kernel with certified
- * bins; same counts, for cross-checking and timing. */
+/* EDMD_OPT_PCF_LEGACY selects the g(r) kernel: 0 (default) = spatially sorted tiles, the
+ * bin of a pair decided in FP32 under a rigorous error bound and the pairs FP32 cannot
+ * settle redone with the reference's FP64 operations; 1 = the plain tile kernel (IEEE
+ * sqrt and division per pair, id-ordered tiles); 2 = sorted tiles with every bin
+ * certified in FP64.  Same integer counts; for cross-checking and timing. */
 #define EDMD_OPT_PCF_LEGACY 4
 int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 /* Counters: EDMD_STAT_EXACT_RESCANS = particles the tiled sweep had to resolve
@@ -110,6 +112,12 @@ int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 #define EDMD_STAT_PCF_EXACT_PAIRS 3
 #define EDMD_STAT_PCF_SKIPPED_TILE_PAIRS 4
 int edmd_cuda_get_stat(edmd_ctx *ctx, int stat, uint64_t *value);
+
+/* Self-test of an assumption the default g(r) kernel's error bound rests on: runs the
+ * hardware's approximate reciprocal square root over every float in [2^-100, 2^64) and
+ * returns the largest relative error found (the kernel budgets 3.0e-7; PTX documents
+ * 2^-22.9).  No reference counterpart. */
+int edmd_cuda_selftest_rsqrt(edmd_ctx *ctx, double *max_rel_err);
 
 /* Page-locked host memory for the caller's particle arrays: uploads and
  * downloads from/to such memory go straight to the copy engines (pageable

@@ -345,22 +345,78 @@ def test_pcf_counts_match_oracle(pkg, oracle, n, phi, seed, dr, frac):
 
 
 @pytest.mark.parametrize("n,phi,seed,dr,frac", [(120000, 0.70, 81, 0.1, 0.5), (60000, 0.85, 82, 0.013, 0.3),
-                                                (100000, 0.30, 83, 2.0, 0.75)])
+                                                (100000, 0.30, 83, 2.0, 0.75), (20000, 0.70, 84, 0.0011, 0.2)])
 def test_pcf_sorted_tiles_equal_plain_kernel(pkg, n, phi, seed, dr, frac):
-    """Large systems take the sorted-tile kernel (bins certified in FP64 from an
-    FP32 estimate, periodic image and far tile pairs decided per tile pair); the
-    plain kernel (IEEE sqrt + division per pair) must count the same integers."""
+    """Large systems take the sorted-tile kernels: by default the bin of a pair is
+    decided in FP32 under a rigorous error bound and undecided pairs are redone with
+    the reference's FP64 operations (k_pcf_f32); option 2 certifies every bin in FP64
+    (k_pcf_sorted; also what very fine bins fall back to, last case).  The plain
+    kernel (IEEE sqrt + division per pair) must count the same integers."""
     c = pkg.synth.lattice_config(n, phi, seed)
     max_r = min(c["lx"], c["ly"]) * frac
     with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
         ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
         a = ctx.pcf(dr, max_r)
         exact = ctx.stat(pkg.binding.STAT_PCF_EXACT_PAIRS)
+        ctx.set_option(pkg.binding.OPT_PCF_LEGACY, 2)
+        a64 = ctx.pcf(dr, max_r)
+        exact64 = ctx.stat(pkg.binding.STAT_PCF_EXACT_PAIRS) - exact
         ctx.set_option(pkg.binding.OPT_PCF_LEGACY, 1)
         b = ctx.pcf(dr, max_r)
     assert np.array_equal(a["counts"], b["counts"])
+    assert np.array_equal(a64["counts"], b["counts"])
     npairs = c["n"] * (c["n"] - 1) // 2
-    assert exact < 0.02 * npairs, (exact, npairs)      # the certificate settles almost every pair
+    assert exact < 0.02 * npairs, (exact, npairs)      # FP32 settles almost every pair
+    assert exact64 < 0.02 * npairs, (exact64, npairs)
+
+
+def test_hardware_rsqrt_stays_inside_the_budget_of_the_pcf_kernel(pkg):
+    """k_pcf_f32 budgets 3.0e-7 for the relative error of rsqrt.approx.ftz.f32; measured
+    here over every float in [2^-100, 2^64)."""
+    with pkg.EdmdCuda(16, 30.0, 30.0) as ctx:
+        worst = ctx.selftest_rsqrt()
+    assert 0.0 < worst <= 2.0 ** -22, worst
+
+
+@pytest.mark.parametrize("dr,spacing,frac", [(0.1, 0.5, 0.5), (0.25, 0.75, 0.75), (0.05, 1.0, 0.35)])
+def test_pcf_points_on_bin_edges(pkg, oracle, dr, spacing, frac):
+    """Adversarial for the FP32 decision: a square lattice whose spacing is a multiple
+    of dr puts a large share of all distances exactly on bin edges, where only the
+    reference's own FP64 rounding decides the bin (1.5/0.1 is not 15)."""
+    m = 128
+    n = m * m
+    ix, iy = np.meshgrid(np.arange(m), np.arange(m), indexing="ij")
+    x, y = (ix.ravel() * spacing).astype(np.float64), (iy.ravel() * spacing).astype(np.float64)
+    lx = ly = m * spacing
+    perm = np.random.default_rng(5).permutation(n)
+    x, y = x[perm], y[perm]
+    z = np.zeros(n)
+    max_r = frac * lx
+    with pkg.EdmdCuda(n, lx, ly) as ctx:
+        ctx.upload(x, y, z + 1.0, z, z + 0.1, t=0.0)
+        p = ctx.pcf(dr, max_r)
+        exact = ctx.stat(pkg.binding.STAT_PCF_EXACT_PAIRS)
+        ctx.set_option(pkg.binding.OPT_PCF_LEGACY, 2)
+        p64 = ctx.pcf(dr, max_r)
+    want = oracle.pcf(n, lx, ly, x, y, dr, max_r)
+    assert np.array_equal(p["counts"], want["counts"])
+    assert np.array_equal(p64["counts"], want["counts"])
+    assert exact > 0          # the edge pairs did go through the FP64 path
+
+
+def test_pcf_fp32_decision_at_full_size(pkg):
+    """N = 10^6 (BASELINE configs[2]) at a range the test can afford twice: the default
+    kernel against the FP64-certified one, and the pair checksum."""
+    c = pkg.synth.lattice_config(1000000, 0.70, seed=12345)
+    n = c["n"]
+    max_r = 0.12 * min(c["lx"], c["ly"])
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        a = ctx.pcf(0.1, max_r)
+        ctx.set_option(pkg.binding.OPT_PCF_LEGACY, 2)
+        b = ctx.pcf(0.1, max_r)
+    assert np.array_equal(a["counts"], b["counts"])
+    assert int(a["counts"].sum()) > 0
 
 
 def test_pcf_counts_every_pair_once(pkg):

@@ -134,7 +134,7 @@ k_coarse_order(int ncoarse, const int32_t *__restrict__ cend, const double2 *__r
 // coordinates of its particles relative to that centre in units of dr (k_pcf_f32)
 __global__ void __launch_bounds__(kTile)
 k_tile_bbox(int n, const double2 *__restrict__ sorted, double4 *__restrict__ bbox, double inv_dr,
-            double2 *__restrict__ ctr, float2 *__restrict__ rel)
+            double2 *__restrict__ ctr, float2 *__restrict__ rel, double coord_max)
 {
     __shared__ double s[4][kTile / 32];
     __shared__ double2 s_ctr;
@@ -142,11 +142,15 @@ k_tile_bbox(int n, const double2 *__restrict__ sorted, double4 *__restrict__ bbo
     const double big = 1e300;
     double x0 = big, x1 = -big, y0 = big, y1 = -big;
     double2 p = make_double2(0.0, 0.0);
+    int bad = 0;
     if (i < n) {
         p = sorted[i];
         x0 = x1 = p.x;
         y0 = y1 = p.y;
+        // non-finite or far outside the box: the FP32 offsets of this tile mean nothing
+        bad = !(fabs(p.x) <= coord_max && fabs(p.y) <= coord_max);
     }
+    bad = __syncthreads_or(bad);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, d));
@@ -164,7 +168,8 @@ k_tile_bbox(int n, const double2 *__restrict__ sorted, double4 *__restrict__ bbo
             x0 = fmin(x0, s[0][w]); x1 = fmax(x1, s[1][w]);
             y0 = fmin(y0, s[2][w]); y1 = fmax(y1, s[3][w]);
         }
-        bbox[blockIdx.x] = make_double4(x0, x1, y0, y1);
+        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+        bbox[blockIdx.x] = (bad && rel) ? make_double4(qnan, qnan, qnan, qnan) : make_double4(x0, x1, y0, y1);
         if (rel) {
             s_ctr = make_double2(0.5 * (x0 + x1), 0.5 * (y0 + y1));
             ctr[blockIdx.x] = s_ctr;
@@ -385,13 +390,15 @@ k_pcf_sorted(const __grid_constant__ PcfArgs a)
 //     q32 its FP32 estimate (derivation below);
 //   * whether every pair is in range (then the range test is dropped).
 // Thread i holds p_i = fl32(((x_i - S) - C_b) / dr); per pair
-//     d = b_j - p_i,  s = fma(dy, dy, fma(dx, dx, 1e-30)),  q32 = s * rsqrt(s),
-//     t = RD(q32 + 1.5 * 2^23)          (bits of t = 0x4B400000 + floor(q32), exact)
-//     frac = q32 - (t - 1.5 * 2^23)     (exact)
-// and the pair is CERTAIN when eps <= frac <= 1 - eps (floor(q*) = floor(q32)) and
-// q32 < lim (in range, bin < num_bins); it is certainly out of range when
-// q32 > hi; everything else goes to a shared-memory queue that the CTA drains with
-// the reference's own FP64 operations (~1 % of the pairs at N = 10^6, dr = 0.1).
+//     d = b_j - p_i,  s = fma(dy, dy, fma(dx, dx, 1e-30)),  y = rsqrt(s),
+//     q_lo = fma(s, y, -eps)                                  (q* lies in [q_lo, q_lo + 2 eps])
+//     t = RD(q_lo + 1.5 * 2^23)     (bits of t = 0x4B400000 + floor(q_lo), exact for |q| < 2^22)
+//     frac = q_lo - (t - 1.5 * 2^23)                          (exact)
+// and the pair is CERTAIN when frac < 1 - 2 eps -- no integer in (q_lo, q_lo + 2 eps], so
+// floor(q*) = floor(q_lo) -- and q_lo < lim (in range, bin < num_bins); it is certainly out
+// of range when q_lo > hi;
+// everything else goes to a shared-memory queue that the CTA drains with the
+// reference's own FP64 operations (~1 % of the pairs at N = 10^6, dr = 0.1).
 //
 // Error bound (u = 2^-24, lengths in units of dr):
 //   b_j, p_i are roundings of FP64 values: |err| <= u |b_j| <= u h_b and
@@ -400,10 +407,11 @@ k_pcf_sorted(const __grid_constant__ PcfArgs a)
 //       E_axis = u (2 h_b + 2 M) (+ u L when the FP32 wrap subtracts fl32(L)),
 //   E = |(E_x, E_y)|; by the triangle inequality the exact norm of the FP32 vector is
 //   within E of the true distance.  s carries two roundings (<= 2u), the MUFU
-//   rsqrt <= 3.0e-7 relative (PTX: 2^-22.9; edmd_cuda_selftest_rsqrt measures it
-//   exhaustively, the test asserts <= 2^-22), the product one more:
-//       |q32 - q_true| <= (R + E) (3.0e-7 + 4u) + E + 1e-15 (the 1e-30 floor)
-//   with R the largest distance of the tile pair.  FP64 roundings on either side
+//   rsqrt <= 2^-22 relative (PTX documents 2^-22.9; edmd_cuda_selftest_rsqrt measures it
+//   exhaustively and the GPU test asserts <= 2^-22), the product one more:
+//       |s y - q_true| <= (R + E) (2^-22 + 1.01u) + E + 1e-15 (the 1e-30 floor)
+//   with R the largest distance of the tile pair; the rounding of the fma adds
+//   u (R + E) more: eps = (R + E) (2^-22 + 2.5u) + E + slack.  FP64 roundings on either side
 //   (ours and the reference's) stay below 2^-48 L/dr; 2^-44 (L/dr + 1) is budgeted.
 // ---------------------------------------------------------------------------
 constexpr int kQueue = 2048;                 // undecided pairs parked per tile pair (u32 each: counted bin | i | j)
@@ -412,9 +420,11 @@ constexpr uint32_t kMagicBits = 0x4B400000u;
 
 struct TilePairPlan {
     double2 cbs;         // C_b + S: p_i = ((x_i - cbs.x) / dr, ...)
-    float c;             // certain  <=>  |frac - 0.5| <= c   (c = 0.5 - eps, rounded down)
-    float lim, hi;       // take needs q32 < lim; q32 > hi is certainly out of range
-    int flags;           // 1 wrap x per pair, 2 wrap y per pair, 4 every pair in range, 8 skip
+    float eps;           // q* in [q_lo, q_lo + 2 eps], q_lo = fma(s, y, -eps)
+    float cth;           // certain  <=>  frac(q_lo) < cth   (cth = 1 - 2 eps, rounded down)
+    float lim, hi;       // take needs q_lo < lim (= range limit - 2 eps); q_lo > hi is certainly out of range
+    int flags;           // 1 wrap x per pair, 2 wrap y per pair, 4 every pair in range, 8 skip,
+                         // 16 every pair by the exact path (bad coordinates, or eps too large to decide anything)
 };
 
 struct F32Args {
@@ -464,10 +474,12 @@ __device__ __forceinline__ void exact_pair(const PcfArgs &a, int gi, int gj, uin
 // pair is corrected by the exact path afterwards (minus one here, plus one there).
 // Otherwise a pair that is not taken increments a per-lane dummy slot behind the histogram.
 // Returns whether the pair must go to the exact path; tbits = bits of t (bin = tbits - kMagicBits).
+// Returns w: the pair must go to the exact path  <=>  w >= cth  (one comparison, so that four
+// pairs are checked with three max and one compare).
 template <bool WX, bool WY, bool INR>
-__device__ __forceinline__ bool pair32(float bx, float by, float px, float py, float c, float lim, float hi,
-                                       float lx32, float ly32, float hx32, float hy32, uint32_t hbase,
-                                       uint32_t trash, uint32_t &tbits)
+__device__ __forceinline__ float pair32(float bx, float by, float px, float py, float eps, float cth, float lim,
+                                        float hi, float lx32, float ly32, float hx32, float hy32, uint32_t hbase,
+                                        uint32_t trash, uint32_t &tbits)
 {
     float dx = __fsub_rn(bx, px), dy = __fsub_rn(by, py);
     if (WX) {
@@ -481,27 +493,27 @@ __device__ __forceinline__ bool pair32(float bx, float by, float px, float py, f
     const float s = __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, 1e-30f));
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
-    const float q = __fmul_rn(s, y);
-    const float t = __fadd_rd(q, kMagic);
-    const float frac = __fsub_rn(q, __fsub_rn(t, kMagic));
-    const bool cert = fabsf(__fsub_rn(frac, 0.5f)) <= c;
+    const float qlo = __fmaf_rn(s, y, -eps);                 // q_lo <= q* <= q_lo + 2 eps
+    const float t = __fadd_rd(qlo, kMagic);
+    const float frac = __fsub_rn(qlo, __fsub_rn(t, kMagic));   // exact, in [0, 1)
     tbits = __float_as_uint(t);
+    // q_lo < 0 (a pair closer than eps dr) gives bin -1: the word in front of the histogram is a pad
     const uint32_t addr = hbase + (tbits << 2);
     if (INR) {
         asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
-        return !cert;
+        return frac;
     }
-    const bool take = cert && q < lim;
+    const bool take = frac < cth && qlo < lim;
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(take ? addr : trash), "r"(1u) : "memory");
-    return !take && q <= hi;
+    return (!take && qlo <= hi) ? 2.0f : 0.0f;
 }
 
 template <bool WX, bool WY, bool INR>
 __device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan &tp, float px, float py, int gi0,
                                             int gj0, uint32_t tile_addr, int jstart, int jcount, uint32_t hist_addr,
-                                            uint32_t queue_addr, int *qn, unsigned int &slow)
+                                            uint32_t queue_addr, uint32_t qn, unsigned int &slow)
 {
-    const float c = tp.c, lim = tp.lim, hi = tp.hi;
+    const float c = tp.eps, cth = tp.cth, lim = tp.lim, hi = tp.hi;
     const float lx32 = a.lx32, ly32 = a.ly32, hx32 = a.hx32, hy32 = a.hy32;
     uint32_t hbase, trash;
     // opaque moves: keep the two addresses in registers instead of re-deriving them per trip
@@ -509,8 +521,11 @@ __device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan
     asm volatile("mov.u32 %0, %1;" : "=r"(trash) : "r"(hist_addr + 4u * (uint32_t)(a.p.num_bins + (threadIdx.x & 31))));
     auto park = [&](int j, uint32_t tbits) {
         const unsigned int counted = INR ? (tbits - kMagicBits) & 0xFFFFu : kNotCounted;
-        const int slot = atomicAdd(qn, 1);
-        if (slot < kQueue) {
+        uint32_t slot;
+        // (tbits >> 31) is always 0 (t lies in [2^23, 2^24)), but an address ptxas can prove uniform makes it
+        // emit the warp-aggregated form of the atomic: ~25 instructions for one or two lanes at a time
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(qn + ((tbits >> 31) << 2)) : "memory");
+        if (slot < (uint32_t)kQueue) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(queue_addr + 4u * (uint32_t)slot),
                          "r"((counted << 16) | (threadIdx.x << 8) | (unsigned int)j)
                          : "memory");
@@ -523,26 +538,26 @@ __device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan
     uint32_t tb;
     for (; jj < jcount && (jj & 3); jj++) {
         const float2 b = lds_float2(tile_addr + 8u * (uint32_t)jj);
-        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, tb)) park(jj, tb);
+        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, tb) >= cth) park(jj, tb);
     }
     uint32_t addr = tile_addr + 8u * (uint32_t)jj;
     for (; jj + 4 <= jcount; jj += 4, addr += 32u) {
         const float4 b01 = lds_float4(addr), b23 = lds_float4(addr + 16u);
         uint32_t t0, t1, t2, t3;
-        const bool u0 = pair32<WX, WY, INR>(b01.x, b01.y, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t0);
-        const bool u1 = pair32<WX, WY, INR>(b01.z, b01.w, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t1);
-        const bool u2 = pair32<WX, WY, INR>(b23.x, b23.y, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t2);
-        const bool u3 = pair32<WX, WY, INR>(b23.z, b23.w, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t3);
-        if (u0 | u1 | u2 | u3) {
-            if (u0) park(jj, t0);
-            if (u1) park(jj + 1, t1);
-            if (u2) park(jj + 2, t2);
-            if (u3) park(jj + 3, t3);
+        const float u0 = pair32<WX, WY, INR>(b01.x, b01.y, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t0);
+        const float u1 = pair32<WX, WY, INR>(b01.z, b01.w, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t1);
+        const float u2 = pair32<WX, WY, INR>(b23.x, b23.y, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t2);
+        const float u3 = pair32<WX, WY, INR>(b23.z, b23.w, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t3);
+        if (fmaxf(fmaxf(u0, u1), fmaxf(u2, u3)) >= cth) {
+            if (u0 >= cth) park(jj, t0);
+            if (u1 >= cth) park(jj + 1, t1);
+            if (u2 >= cth) park(jj + 2, t2);
+            if (u3 >= cth) park(jj + 3, t3);
         }
     }
     for (; jj < jcount; jj++) {
         const float2 b = lds_float2(tile_addr + 8u * (uint32_t)jj);
-        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, tb)) park(jj, tb);
+        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, tb) >= cth) park(jj, tb);
     }
 }
 
@@ -576,7 +591,8 @@ k_pcf_f32(const __grid_constant__ F32Args a)
     extern __shared__ unsigned char smem_raw[];
     float2 *tile = reinterpret_cast<float2 *>(smem_raw);
     unsigned int *queue = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2));
-    unsigned int *hist = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2) + kQueue * sizeof(unsigned int));
+    // [pad: 4 words][histogram][32 dummy words]: bin -1 (see pair32) lands in the pad
+    unsigned int *hist = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2) + kQueue * sizeof(unsigned int)) + 4;
     __shared__ TilePairPlan s_tp;
     __shared__ int s_qn;
     const PcfArgs &p = a.p;
@@ -600,7 +616,9 @@ k_pcf_f32(const __grid_constant__ F32Args a)
             plan_axis(B.x - A.y, B.y - A.x, p.b.half_lx, p.b.lx, sx, wx, mxu, mxw, gx);
             plan_axis(B.z - A.w, B.w - A.z, p.b.half_ly, p.b.ly, sy, wy, myu, myw, gy);
             TilePairPlan tp;
-            if (gx * gx + gy * gy >= rcut * rcut) {
+            if (A.x != A.x || B.x != B.x) {
+                tp.flags = 16;   // a tile with non-finite or far-out coordinates (k_tile_bbox): FP64 for every pair
+            } else if (gx * gx + gy * gy >= rcut * rcut) {
                 tp.flags = 8;
             } else {
                 const double u = 5.9604644775390625e-08 * 1.001;   // 2^-24, padded
@@ -610,15 +628,16 @@ k_pcf_f32(const __grid_constant__ F32Args a)
                 const double ey = u * (2.0 * hby + 2.0 * myu * id) + (wy ? u * p.b.ly * id : 0.0) + a.slack;
                 const double e = sqrt(ex * ex + ey * ey) * 1.001;
                 const double rmax = sqrt(mxw * mxw + myw * myw) * id * (1.0 + 1e-9);
-                const double rho = 3.0e-7 + 4.0 * u;
-                const double eps = ((rmax + e) * rho + e + 1e-14 + a.slack) * 1.001 + 2.384185791015625e-07;   // + 2^-22
+                const double rho = 2.384185791015625e-07 + 2.5 * u;   // rsqrt <= 2^-22 (asserted by the self-test)
+                const double eps = ((rmax + e) * rho + e + 1e-12 + a.slack) * 1.001;
                 const float eps32 = __double2float_ru(eps);
-                tp.c = __double2float_rd(0.5 - (double)eps32);
-                const double lim = fmin(a.q_maxr - (double)eps32 - a.slack, (double)p.num_bins);
-                tp.lim = __double2float_rd(lim);
-                tp.hi = __double2float_ru(a.q_maxr + (double)eps32 + a.slack);
+                tp.eps = eps32;
+                tp.cth = __double2float_rd(1.0 - 2.0 * (double)eps32 - 2.384185791015625e-07);
+                // q_lo < lim  =>  q* <= q_lo + 2 eps is in range and below num_bins;  q_lo > hi  =>  out of range
+                tp.lim = __double2float_rd(fmin(a.q_maxr - a.slack, (double)p.num_bins) - 2.0 * (double)eps32);
+                tp.hi = __double2float_ru(a.q_maxr + a.slack);
                 const bool inr = (rmax + e) * (1.0 + 1e-6) < (double)tp.lim;
-                tp.flags = (wx ? 1 : 0) | (wy ? 2 : 0) | ((inr && !wx && !wy) ? 4 : 0);
+                tp.flags = !(eps < 0.45) ? 16 : ((wx ? 1 : 0) | (wy ? 2 : 0) | ((inr && !wx && !wy) ? 4 : 0));
                 const double2 cb = a.ctr[tb];
                 tp.cbs = make_double2(cb.x + sx, cb.y + sy);
             }
@@ -642,12 +661,17 @@ k_pcf_f32(const __grid_constant__ F32Args a)
             const float py = __double2float_rn((pi.y - cbs.y) * a.inv_dr);
             const int jcount = min(kTile, p.n - gj0);
             const int jstart = (ta == tb) ? threadIdx.x + 1 : 0;
+            const uint32_t qn_addr = smem_addr(&s_qn);
             switch (flags) {
-            case 4: pair_loop32<false, false, true>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, &s_qn, slow); break;
-            case 0: pair_loop32<false, false, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, &s_qn, slow); break;
-            case 1: pair_loop32<true, false, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, &s_qn, slow); break;
-            case 2: pair_loop32<false, true, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, &s_qn, slow); break;
-            default: pair_loop32<true, true, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, &s_qn, slow); break;
+            case 16:
+                for (int jj = jstart; jj < jcount; jj++) exact_pair(p, i, gj0 + jj, hist_addr, kNotCounted);
+                slow += (unsigned int)max(jcount - jstart, 0);
+                break;
+            case 4: pair_loop32<false, false, true>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
+            case 0: pair_loop32<false, false, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
+            case 1: pair_loop32<true, false, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
+            case 2: pair_loop32<false, true, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
+            default: pair_loop32<true, true, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
             }
         }
         __syncthreads();
@@ -672,7 +696,7 @@ k_pcf_f32(const __grid_constant__ F32Args a)
 
 // largest relative error of the MUFU reciprocal square root over every float in
 // [2^-100, 2^64) (the kernel's s lies in [1e-30, 2^46)): the measured side of the
-// 3.0e-7 budgeted in k_pcf_f32
+// 2^-22 budgeted in k_pcf_f32
 __global__ void __launch_bounds__(256)
 k_rsqrt_selftest(unsigned long long *worst_bits)
 {
@@ -725,7 +749,7 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     // queue, q = r/dr stays far below 2^22 and the expected share of undecided pairs
     // (~2 q_max * 5.4e-7) is small; else bins certified in FP64 (k_pcf_sorted)
     const double lmax = c->box.lx > c->box.ly ? c->box.lx : c->box.ly;
-    const size_t f32_smem = kTile * sizeof(float2) + kQueue * sizeof(unsigned int) + ((size_t)num_bins + 32) * sizeof(unsigned int);
+    const size_t f32_smem = kTile * sizeof(float2) + kQueue * sizeof(unsigned int) + ((size_t)num_bins + 4 + 32) * sizeof(unsigned int);
     const bool f32 = c->pcf_mode == 0 && f32_smem <= 200 * 1024 && num_bins < 65535 && dr > 0.0 && max_r > 0.0 &&
                      1.5 * lmax / dr < 2097152.0 && max_r / dr <= 60000.0 && lmax / dr <= 120000.0;
     const size_t need = (size_t)n * sizeof(double2) * (ordered ? 2 : 1) + (size_t)nt * (sizeof(double4) + sizeof(double2)) +
@@ -772,7 +796,7 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
         launched++;
     }
     const double inv_dr = 1.0 / dr;
-    k_tile_bbox<<<nt, kTile, 0, c->stream>>>(n, sorted, bbox, inv_dr, f32 ? ctr : nullptr, f32 ? rel : nullptr);
+    k_tile_bbox<<<nt, kTile, 0, c->stream>>>(n, sorted, bbox, inv_dr, f32 ? ctr : nullptr, f32 ? rel : nullptr, 2.0 * lmax);
     PcfArgs a;
     a.n = n; a.num_bins = num_bins;
     a.b = c->dbox;

@@ -6,3 +6,4 @@ with pkg.EdmdCuda(c["n"],c["lx"],c["ly"]) as ctx:
     ctx.upload(c["x"],c["y"],c["vx"],c["vy"],c["rad"],t=0.0)
     tot,main=ctx.bench(B.BENCH_PCF, dr=0.1, max_r=min(c["lx"],c["ly"])/2, warmup=0, iters=1)
     print(tot)
+    print("rsqrt worst rel err", ctx.selftest_rsqrt(), "exact-path pairs", ctx.stat(B.STAT_PCF_EXACT_PAIRS))

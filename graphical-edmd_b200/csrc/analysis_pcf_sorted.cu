@@ -395,10 +395,11 @@ k_pcf_sorted(const __grid_constant__ PcfArgs a)
 //     t = RD(q_lo + 1.5 * 2^23)     (bits of t = 0x4B400000 + floor(q_lo), exact for |q| < 2^22)
 //     frac = q_lo - (t - 1.5 * 2^23)                          (exact)
 // and the pair is CERTAIN when frac < 1 - 2 eps -- no integer in (q_lo, q_lo + 2 eps], so
-// floor(q*) = floor(q_lo) -- and q_lo < lim (in range, bin < num_bins); it is certainly out
-// of range when q_lo > hi;
+// floor(q*) = floor(q_lo).  Every pair is counted in floor(q_lo) at once (clamped to one dummy
+// word at num_bins: `bin < num_bins` is the reference's whole range test, see pair32);
 // everything else goes to a shared-memory queue that the CTA drains with the
-// reference's own FP64 operations (~1 % of the pairs at N = 10^6, dr = 0.1).
+// reference's own FP64 operations (~0.6 % of the pairs at N = 10^6, dr = 0.1) and moves the
+// count to the exact bin when it differs.
 //
 // Error bound (u = 2^-24, lengths in units of dr):
 //   b_j, p_i are roundings of FP64 values: |err| <= u |b_j| <= u h_b and
@@ -407,11 +408,11 @@ k_pcf_sorted(const __grid_constant__ PcfArgs a)
 //       E_axis = u (2 h_b + 2 M) (+ u L when the FP32 wrap subtracts fl32(L)),
 //   E = |(E_x, E_y)|; by the triangle inequality the exact norm of the FP32 vector is
 //   within E of the true distance.  s carries two roundings (<= 2u), the MUFU
-//   rsqrt <= 2^-22 relative (PTX documents 2^-22.9; edmd_cuda_selftest_rsqrt measures it
-//   exhaustively and the GPU test asserts <= 2^-22), the product one more:
-//       |s y - q_true| <= (R + E) (2^-22 + 1.01u) + E + 1e-15 (the 1e-30 floor)
+//   rsqrt <= 1.28e-7 relative (PTX documents 2^-22.9 = 1.2775e-7; edmd_cuda_selftest_rsqrt measures it
+//   exhaustively -- 1.2467e-7 on B200 -- and the GPU test asserts <= 1.28e-7), the product one more:
+//       |s y - q_true| <= (R + E) (1.28e-7 + 1.01u) + E + 1e-15 (the 1e-30 floor)
 //   with R the largest distance of the tile pair; the rounding of the fma adds
-//   u (R + E) more: eps = (R + E) (2^-22 + 2.5u) + E + slack.  FP64 roundings on either side
+//   u (R + E) more: eps = (R + E) (1.28e-7 + 2.1u) + E + slack.  FP64 roundings on either side
 //   (ours and the reference's) stay below 2^-48 L/dr; 2^-44 (L/dr + 1) is budgeted.
 // ---------------------------------------------------------------------------
 constexpr int kQueue = 2048;                 // undecided pairs parked per tile pair (u32 each: counted bin | i | j)
@@ -422,8 +423,8 @@ struct TilePairPlan {
     double2 cbs;         // C_b + S: p_i = ((x_i - cbs.x) / dr, ...)
     float eps;           // q* in [q_lo, q_lo + 2 eps], q_lo = fma(s, y, -eps)
     float cth;           // certain  <=>  frac(q_lo) < cth   (cth = 1 - 2 eps, rounded down)
-    float lim, hi;       // take needs q_lo < lim (= range limit - 2 eps); q_lo > hi is certainly out of range
-    int flags;           // 1 wrap x per pair, 2 wrap y per pair, 4 every pair in range, 8 skip,
+    int ta, tb;          // the tile pair
+    int flags;           // 1 wrap x per pair, 2 wrap y per pair, 4 every pair certainly below num_bins, 8 skip,
                          // 16 every pair by the exact path (bad coordinates, or eps too large to decide anything)
 };
 
@@ -431,7 +432,8 @@ struct F32Args {
     PcfArgs p;
     const float2 *rel;
     const double2 *ctr;
-    double inv_dr, q_maxr, slack;
+    double inv_dr, slack;
+    float tmax;                     // 1.5 * 2^23 + num_bins: t of the dummy word behind the histogram
     float lx32, ly32, hx32, hy32;   // fl32(L / dr) and exactly half of it
 };
 
@@ -469,17 +471,16 @@ __device__ __forceinline__ void exact_pair(const PcfArgs &a, int gi, int gj, uin
     if (bin != kNotCounted) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_addr + 4u * bin), "r"(1u) : "memory");
 }
 
-// One pair in FP32.  INR (every pair of the tile pair certainly in range): the pair is
-// counted in its FP32 bin unconditionally -- no predicate, no branch -- and an undecided
-// pair is corrected by the exact path afterwards (minus one here, plus one there).
-// Otherwise a pair that is not taken increments a per-lane dummy slot behind the histogram.
-// Returns whether the pair must go to the exact path; tbits = bits of t (bin = tbits - kMagicBits).
-// Returns w: the pair must go to the exact path  <=>  w >= cth  (one comparison, so that four
-// pairs are checked with three max and one compare).
+// One pair in FP32.  The pair is counted in its FP32 bin unconditionally -- no predicate, no
+// branch -- and an undecided pair (frac >= cth) is corrected by the exact path afterwards
+// (minus one here, plus one there).  `bin < num_bins` is the whole range test: num_bins =
+// (int)(max_r / dr) and rounding is monotone, so fl(r / dr) < num_bins implies r < max_r
+// (src/pcf.c:44-47).  Unless every pair of the tile pair is certainly below num_bins (INR), t is
+// clamped to num_bins: one dummy word behind the histogram takes every pair beyond the range.
+// Returns frac(q_lo); tbits = bits of the (clamped) t, bin = tbits - kMagicBits.
 template <bool WX, bool WY, bool INR>
-__device__ __forceinline__ float pair32(float bx, float by, float px, float py, float eps, float cth, float lim,
-                                        float hi, float lx32, float ly32, float hx32, float hy32, uint32_t hbase,
-                                        uint32_t trash, uint32_t &tbits)
+__device__ __forceinline__ float pair32(float bx, float by, float px, float py, float eps, float tmax, float lx32,
+                                        float ly32, float hx32, float hy32, uint32_t hbase, uint32_t &tbits)
 {
     float dx = __fsub_rn(bx, px), dy = __fsub_rn(by, py);
     if (WX) {
@@ -496,16 +497,10 @@ __device__ __forceinline__ float pair32(float bx, float by, float px, float py, 
     const float qlo = __fmaf_rn(s, y, -eps);                 // q_lo <= q* <= q_lo + 2 eps
     const float t = __fadd_rd(qlo, kMagic);
     const float frac = __fsub_rn(qlo, __fsub_rn(t, kMagic));   // exact, in [0, 1)
-    tbits = __float_as_uint(t);
+    tbits = __float_as_uint(INR ? t : fminf(t, tmax));
     // q_lo < 0 (a pair closer than eps dr) gives bin -1: the word in front of the histogram is a pad
-    const uint32_t addr = hbase + (tbits << 2);
-    if (INR) {
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u) : "memory");
-        return frac;
-    }
-    const bool take = frac < cth && qlo < lim;
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(take ? addr : trash), "r"(1u) : "memory");
-    return (!take && qlo <= hi) ? 2.0f : 0.0f;
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hbase + (tbits << 2)), "r"(1u) : "memory");
+    return frac;
 }
 
 template <bool WX, bool WY, bool INR>
@@ -513,14 +508,12 @@ __device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan
                                             int gj0, uint32_t tile_addr, int jstart, int jcount, uint32_t hist_addr,
                                             uint32_t queue_addr, uint32_t qn, unsigned int &slow)
 {
-    const float c = tp.eps, cth = tp.cth, lim = tp.lim, hi = tp.hi;
+    const float c = tp.eps, cth = tp.cth, tmax = a.tmax;
     const float lx32 = a.lx32, ly32 = a.ly32, hx32 = a.hx32, hy32 = a.hy32;
-    uint32_t hbase, trash;
-    // opaque moves: keep the two addresses in registers instead of re-deriving them per trip
-    asm volatile("mov.u32 %0, %1;" : "=r"(hbase) : "r"(hist_addr - (kMagicBits << 2)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(trash) : "r"(hist_addr + 4u * (uint32_t)(a.p.num_bins + (threadIdx.x & 31))));
+    const uint32_t hbase = hist_addr - (kMagicBits << 2);
+    const uint32_t tmaxbits = __float_as_uint(tmax);
     auto park = [&](int j, uint32_t tbits) {
-        const unsigned int counted = INR ? (tbits - kMagicBits) & 0xFFFFu : kNotCounted;
+        const unsigned int counted = (tbits - kMagicBits) & 0xFFFFu;   // -1 (the pad) reads as kNotCounted
         uint32_t slot;
         // (tbits >> 31) is always 0 (t lies in [2^23, 2^24)), but an address ptxas can prove uniform makes it
         // emit the warp-aggregated form of the atomic: ~25 instructions for one or two lanes at a time
@@ -538,26 +531,27 @@ __device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan
     uint32_t tb;
     for (; jj < jcount && (jj & 3); jj++) {
         const float2 b = lds_float2(tile_addr + 8u * (uint32_t)jj);
-        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, tb) >= cth) park(jj, tb);
+        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, tb) >= cth && (INR || tb != tmaxbits)) park(jj, tb);
     }
     uint32_t addr = tile_addr + 8u * (uint32_t)jj;
     for (; jj + 4 <= jcount; jj += 4, addr += 32u) {
         const float4 b01 = lds_float4(addr), b23 = lds_float4(addr + 16u);
         uint32_t t0, t1, t2, t3;
-        const float u0 = pair32<WX, WY, INR>(b01.x, b01.y, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t0);
-        const float u1 = pair32<WX, WY, INR>(b01.z, b01.w, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t1);
-        const float u2 = pair32<WX, WY, INR>(b23.x, b23.y, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t2);
-        const float u3 = pair32<WX, WY, INR>(b23.z, b23.w, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, t3);
+        const float u0 = pair32<WX, WY, INR>(b01.x, b01.y, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t0);
+        const float u1 = pair32<WX, WY, INR>(b01.z, b01.w, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t1);
+        const float u2 = pair32<WX, WY, INR>(b23.x, b23.y, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t2);
+        const float u3 = pair32<WX, WY, INR>(b23.z, b23.w, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t3);
         if (fmaxf(fmaxf(u0, u1), fmaxf(u2, u3)) >= cth) {
-            if (u0 >= cth) park(jj, t0);
-            if (u1 >= cth) park(jj + 1, t1);
-            if (u2 >= cth) park(jj + 2, t2);
-            if (u3 >= cth) park(jj + 3, t3);
+            // (a pair clamped to the dummy word is certainly beyond the range: q* >= q_lo >= num_bins)
+            if (u0 >= cth && (INR || t0 != tmaxbits)) park(jj, t0);
+            if (u1 >= cth && (INR || t1 != tmaxbits)) park(jj + 1, t1);
+            if (u2 >= cth && (INR || t2 != tmaxbits)) park(jj + 2, t2);
+            if (u3 >= cth && (INR || t3 != tmaxbits)) park(jj + 3, t3);
         }
     }
     for (; jj < jcount; jj++) {
         const float2 b = lds_float2(tile_addr + 8u * (uint32_t)jj);
-        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, cth, lim, hi, lx32, ly32, hx32, hy32, hbase, trash, tb) >= cth) park(jj, tb);
+        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, tb) >= cth && (INR || tb != tmaxbits)) park(jj, tb);
     }
 }
 
@@ -591,7 +585,7 @@ k_pcf_f32(const __grid_constant__ F32Args a)
     extern __shared__ unsigned char smem_raw[];
     float2 *tile = reinterpret_cast<float2 *>(smem_raw);
     unsigned int *queue = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2));
-    // [pad: 4 words][histogram][32 dummy words]: bin -1 (see pair32) lands in the pad
+    // [pad: 4 words][histogram][dummy words]: bin -1 (see pair32) lands in the pad, bins >= num_bins in hist[num_bins]
     unsigned int *hist = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2) + kQueue * sizeof(unsigned int)) + 4;
     __shared__ TilePairPlan s_tp;
     __shared__ int s_qn;
@@ -599,28 +593,41 @@ k_pcf_f32(const __grid_constant__ F32Args a)
     for (int k = threadIdx.x; k < p.num_bins; k += kThreads) hist[k] = 0;
     const int nt = (p.n + kTile - 1) / kTile;
     const long long npairs = (long long)nt * (nt + 1) / 2;
-    unsigned int slow = 0, skipped = 0;
+    unsigned int slow = 0;
+    unsigned long long skipped = 0;
     const double rcut = p.max_r * (1.0 + 1e-12);
     const uint32_t tile_addr = smem_addr(tile), hist_addr = smem_addr(hist), queue_addr = smem_addr(queue);
-    for (long long w = (long long)blockIdx.x * p.nparts + p.part; w < npairs; w += (long long)gridDim.x * p.nparts) {
-        const double fn = (double)nt + 0.5;
-        long long ta = (long long)(fn - sqrt(fn * fn - 2.0 * (double)w));
-        while (ta * nt - ta * (ta - 1) / 2 > w) ta--;
-        while ((ta + 1) * nt - (ta + 1) * ta / 2 <= w) ta++;
-        const long long tb = ta + (w - (ta * nt - ta * (ta - 1) / 2));
+    // thread 0 walks this CTA's tile pairs w = first, first + stride, ... to the next one that is not
+    // skipped and leaves its plan in shared memory (flags 32: no tile pair left)
+    long long w = (long long)blockIdx.x * p.nparts + p.part;
+    const long long wstride = (long long)gridDim.x * p.nparts;
+    for (;;) {
         __syncthreads();   // previous tile pair drained, plan and tile consumed
         if (threadIdx.x == 0) {
-            const double4 A = p.bbox[ta], B = p.bbox[tb];
-            double sx, sy, mxu, mxw, myu, myw, gx, gy;
-            bool wx, wy;
-            plan_axis(B.x - A.y, B.y - A.x, p.b.half_lx, p.b.lx, sx, wx, mxu, mxw, gx);
-            plan_axis(B.z - A.w, B.w - A.z, p.b.half_ly, p.b.ly, sy, wy, myu, myw, gy);
             TilePairPlan tp;
-            if (A.x != A.x || B.x != B.x) {
-                tp.flags = 16;   // a tile with non-finite or far-out coordinates (k_tile_bbox): FP64 for every pair
-            } else if (gx * gx + gy * gy >= rcut * rcut) {
-                tp.flags = 8;
-            } else {
+            tp.flags = 32;
+            for (; w < npairs; w += wstride) {
+                // unrank w -> (ta, tb), ta <= tb, row-major over the upper triangle
+                const double fn = (double)nt + 0.5;
+                long long ta = (long long)(fn - sqrt(fn * fn - 2.0 * (double)w));
+                while (ta * nt - ta * (ta - 1) / 2 > w) ta--;
+                while ((ta + 1) * nt - (ta + 1) * ta / 2 <= w) ta++;
+                const long long tb = ta + (w - (ta * nt - ta * (ta - 1) / 2));
+                const double4 A = p.bbox[ta], B = p.bbox[tb];
+                double sx, sy, mxu, mxw, myu, myw, gx, gy;
+                bool wx, wy;
+                plan_axis(B.x - A.y, B.y - A.x, p.b.half_lx, p.b.lx, sx, wx, mxu, mxw, gx);
+                plan_axis(B.z - A.w, B.w - A.z, p.b.half_ly, p.b.ly, sy, wy, myu, myw, gy);
+                tp.ta = (int)ta;
+                tp.tb = (int)tb;
+                if (A.x != A.x || B.x != B.x) {
+                    tp.flags = 16;   // a tile with non-finite or far-out coordinates (k_tile_bbox): FP64 for every pair
+                    break;
+                }
+                if (gx * gx + gy * gy >= rcut * rcut) {
+                    skipped++;
+                    continue;
+                }
                 const double u = 5.9604644775390625e-08 * 1.001;   // 2^-24, padded
                 const double id = a.inv_dr;
                 const double hbx = 0.5 * (B.y - B.x) * id, hby = 0.5 * (B.w - B.z) * id;
@@ -628,28 +635,27 @@ k_pcf_f32(const __grid_constant__ F32Args a)
                 const double ey = u * (2.0 * hby + 2.0 * myu * id) + (wy ? u * p.b.ly * id : 0.0) + a.slack;
                 const double e = sqrt(ex * ex + ey * ey) * 1.001;
                 const double rmax = sqrt(mxw * mxw + myw * myw) * id * (1.0 + 1e-9);
-                const double rho = 2.384185791015625e-07 + 2.5 * u;   // rsqrt <= 2^-22 (asserted by the self-test)
+                // rsqrt.approx <= 2^-22.9 relative (PTX; measured 1.2467e-7 on B200, asserted by the GPU test);
+                // 1.01u from the two roundings of s under the square root, u from the fma of q_lo
+                const double rho = 1.28e-07 + 2.1 * u;
                 const double eps = ((rmax + e) * rho + e + 1e-12 + a.slack) * 1.001;
                 const float eps32 = __double2float_ru(eps);
                 tp.eps = eps32;
                 tp.cth = __double2float_rd(1.0 - 2.0 * (double)eps32 - 2.384185791015625e-07);
-                // q_lo < lim  =>  q* <= q_lo + 2 eps is in range and below num_bins;  q_lo > hi  =>  out of range
-                tp.lim = __double2float_rd(fmin(a.q_maxr - a.slack, (double)p.num_bins) - 2.0 * (double)eps32);
-                tp.hi = __double2float_ru(a.q_maxr + a.slack);
-                const bool inr = (rmax + e) * (1.0 + 1e-6) < (double)tp.lim;
+                const bool inr = (rmax + e) * (1.0 + 1e-6) < (double)p.num_bins;   // every q_lo below num_bins
                 tp.flags = !(eps < 0.45) ? 16 : ((wx ? 1 : 0) | (wy ? 2 : 0) | ((inr && !wx && !wy) ? 4 : 0));
                 const double2 cb = a.ctr[tb];
                 tp.cbs = make_double2(cb.x + sx, cb.y + sy);
+                break;
             }
+            w += wstride;
             s_tp = tp;
             s_qn = 0;
         }
         __syncthreads();
         const int flags = s_tp.flags;
-        if (flags == 8) {
-            skipped++;
-            continue;
-        }
+        if (flags == 32) break;
+        const int ta = s_tp.ta, tb = s_tp.tb;
         const int gi0 = (int)ta * kTile, gj0 = (int)tb * kTile;
         if (gj0 + (int)threadIdx.x < p.n) tile[threadIdx.x] = a.rel[gj0 + threadIdx.x];
         __syncthreads();
@@ -690,13 +696,13 @@ k_pcf_f32(const __grid_constant__ F32Args a)
     }
     if (p.stats) {
         if (slow) atomicAdd(&p.stats[0], (unsigned long long)slow);
-        if (threadIdx.x == 0 && skipped) atomicAdd(&p.stats[1], (unsigned long long)skipped);
+        if (threadIdx.x == 0 && skipped) atomicAdd(&p.stats[1], skipped);
     }
 }
 
 // largest relative error of the MUFU reciprocal square root over every float in
 // [2^-100, 2^64) (the kernel's s lies in [1e-30, 2^46)): the measured side of the
-// 2^-22 budgeted in k_pcf_f32
+// 1.28e-7 budgeted in k_pcf_f32
 __global__ void __launch_bounds__(256)
 k_rsqrt_selftest(unsigned long long *worst_bits)
 {
@@ -751,6 +757,7 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     const double lmax = c->box.lx > c->box.ly ? c->box.lx : c->box.ly;
     const size_t f32_smem = kTile * sizeof(float2) + kQueue * sizeof(unsigned int) + ((size_t)num_bins + 4 + 32) * sizeof(unsigned int);
     const bool f32 = c->pcf_mode == 0 && f32_smem <= 200 * 1024 && num_bins < 65535 && dr > 0.0 && max_r > 0.0 &&
+                     num_bins <= (int)(max_r / dr) &&   // then `bin < num_bins` implies r < max_r (see pair32)
                      1.5 * lmax / dr < 2097152.0 && max_r / dr <= 60000.0 && lmax / dr <= 120000.0;
     const size_t need = (size_t)n * sizeof(double2) * (ordered ? 2 : 1) + (size_t)nt * (sizeof(double4) + sizeof(double2)) +
                         (size_t)n * sizeof(float2) + ((size_t)n * (ordered ? 2 : 1) + ncoarse + 8) * sizeof(int32_t) + 64;
@@ -815,7 +822,7 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
         fa.p = a;
         fa.rel = rel; fa.ctr = ctr;
         fa.inv_dr = inv_dr;
-        fa.q_maxr = max_r * inv_dr;
+        fa.tmax = kMagic + (float)num_bins;
         fa.slack = 5.684341886080802e-14 * (lmax * inv_dr + 1.0);   // 2^-44 (L/dr + 1)
         fa.lx32 = (float)(c->box.lx * inv_dr);
         fa.ly32 = (float)(c->box.ly * inv_dr);

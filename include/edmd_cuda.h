@@ -115,7 +115,7 @@ int edmd_cuda_get_stat(edmd_ctx *ctx, int stat, uint64_t *value);
 
 /* Self-test of an assumption the default g(r) kernel's error bound rests on: runs the
  * hardware's approximate reciprocal square root over every float in [2^-100, 2^64) and
- * returns the largest relative error found (the kernel budgets 2^-22; PTX documents
+ * returns the largest relative error found (the kernel budgets 1.28e-7; PTX documents
  * 2^-22.9).  No reference counterpart. */
 int edmd_cuda_selftest_rsqrt(edmd_ctx *ctx, double *max_rel_err);
 

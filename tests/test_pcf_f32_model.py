@@ -4,7 +4,7 @@ tile pair (image shift or per-pair wrap, error bound eps, range limits) and the
 same FP32 operations per pair in numpy float32 (q_lo = fma(s, rsqrt(s), -eps), certain
 when frac(q_lo) < 1 - 2 eps), with the hardware's approximate
 rsqrt replaced by an ADVERSARIAL one (correct value pushed to either end of the
-2^-22 relative budget).  Every pair the model calls certain must land in the
+1.28e-7 relative budget).  Every pair the model calls certain must land in the
 bin / range decision of the reference's FP64 arithmetic (src/pcf.c:34-47 with
 PBC, src/EDMD.c:5896-5913); the share of undecided pairs must stay small.
 
@@ -69,15 +69,12 @@ def model_tile_pair(xa, ya, xb, yb, lx, ly, dr, max_r, num_bins, rsqrt_bias):
     ey = U * (2 * hby + 2 * myu * inv_dr) + (U * ly * inv_dr if wy else 0.0) + slack
     e = np.hypot(ex, ey) * 1.001
     rmax = np.hypot(mxw, myw) * inv_dr * (1 + 1e-9)
-    rho = 2.0 ** -22 + 2.5 * U
+    rho = 1.28e-7 + 2.1 * U
     eps = ((rmax + e) * rho + e + 1e-12 + slack) * 1.001
     eps32 = up32(eps)
     assert float(eps32) < 0.45           # else the kernel sends the whole tile pair to FP64
     cth = down32(1.0 - 2.0 * float(eps32) - 2.0 ** -22)
-    q_maxr = max_r * inv_dr
-    lim = down32(min(q_maxr - slack, float(num_bins)) - 2.0 * float(eps32))
-    hi = up32(q_maxr + slack)
-    inr = (rmax + e) * (1 + 1e-6) < float(lim) and not wx and not wy
+    inr = (rmax + e) * (1 + 1e-6) < float(num_bins) and not wx and not wy
     cb = (0.5 * (B[0] + B[1]), 0.5 * (B[2] + B[3]))
     bx = ((xb - cb[0]) * inv_dr).astype(f32)
     by = ((yb - cb[1]) * inv_dr).astype(f32)
@@ -103,11 +100,12 @@ def model_tile_pair(xa, ya, xb, yb, lx, ly, dr, max_r, num_bins, rsqrt_bias):
     nf = np.floor(qlo).astype(f32)       # t = RD(q_lo + 1.5 * 2^23) holds floor(q_lo) exactly
     frac = qlo - nf
     cert = frac < cth
+    # every pair is counted in floor(q_lo) clamped to num_bins (the dummy word); `bin < num_bins`
+    # is the whole range test
     if inr:
-        take, drop = cert, np.zeros_like(cert)
-    else:
-        take = cert & (qlo < lim)
-        drop = ~take & ~(qlo <= hi)
+        assert float(nf.max()) < num_bins
+    take = cert & (nf < num_bins)
+    drop = cert & (nf >= num_bins)
     return take, drop, nf.astype(np.int64), float(eps32)
 
 
@@ -144,7 +142,7 @@ def test_certain_pairs_match_the_reference_bins(lx, ly, dr, frac, tile):
             xb, yb = xa[0] + dr * rng.integers(-200, 200, 48), ya[0] + dr * rng.integers(-200, 200, 48)
             xb, yb = np.mod(xb, lx), np.mod(yb, ly)
         want = reference_bins(xa, ya, xb, yb, lx, ly, dr, max_r, num_bins)
-        for bias in (-2.0 ** -22, 0.0, 2.0 ** -22):
+        for bias in (-1.28e-7, 0.0, 1.28e-7):
             got = model_tile_pair(xa, ya, xb, yb, lx, ly, dr, max_r, num_bins, bias)
             if got is None:
                 assert (want < 0).all()      # a skipped tile pair holds no pair in range

@@ -470,6 +470,28 @@ def run_ours(args, cfg):
                             "a rigorous error bound, undecided pairs (exact_path_share) redone in FP64")
         del max_r_cut
 
+    # ---- second input family: the reference-grown liquid, tiled ------------
+    liquid = None
+    fixture = ROOT / "tests" / "golden" / "liquid_n10000_phi070.npz"
+    if rank == 0 and world == 1 and args.analysis != "none" and fixture.exists() and n >= 40000:
+        k = max(2, int(round((n / 10000) ** 0.5)))
+        lc = pkg.synth.tiled_config(np.load(fixture), k, SEED)
+        with pkg.EdmdCuda(lc["n"], lc["lx"], lc["ly"], device=local) as lctx:
+            lctx.upload(lc["x"], lc["y"], lc["vx"], lc["vy"], lc["rad"], t=0.0)
+            eligible = lctx.stat(B.STAT_LEAN_ELIGIBLE)
+            ltot, lmain = lctx.bench(B.BENCH_SWEEP, warmup=warm, iters=steps, flush_bytes=L2_FLUSH_BYTES)
+            declines = lctx.stat(B.STAT_LEAN_DECLINES)
+            liquid = {
+                "workload": f"liquid grown and equilibrated by the reference itself (N0=10000, phi=0.70, "
+                            f"tests/golden/make_liquid.py) tiled {k}x{k}, fresh Maxwell velocities, shuffled ids",
+                "n_particles": lc["n"], "distinct_radii": int(len(np.unique(lc["rad"]))),
+                "ms_per_step": float(np.mean(ltot)), "particles_per_s": lc["n"] / (float(np.mean(ltot)) * 1e-3),
+                "k1_ms": float(np.mean(lmain)), "lean_path": bool(eligible and not declines),
+            }
+            if args.analysis == "full":
+                lp, _ = lctx.bench(B.BENCH_PCF, dr=0.1, max_r=min(lc["lx"], lc["ly"]) / 2, warmup=0, iters=1)
+                liquid["gr_full_ms"] = float(lp[0])
+
     cpu = cpu_baseline(cfg) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
     if rank == 0:
@@ -495,6 +517,8 @@ def run_ours(args, cfg):
         }
         if world > 1:
             line["config"]["parallelism"] = f"{world} independent replicas (slab path: see DESIGN.md)"
+        if liquid:
+            line["liquid_input"] = liquid
         if cpu:
             line["cpu_baseline"] = cpu
         if world == 1 and not args.no_cpu:

@@ -119,10 +119,10 @@ struct CellIndex {
 enum {
     kFlagBadCell = 0, kFlagRescans = 1, kFlagGhosts = 2, kFlagInsane = 3,
     kFlagVmax = 4,       // bits of the largest |velocity component| (float, rounded up)
-    kFlagNotMono = 5,    // radii: 0 all equal rad0, 1 exactly one other value (kFlagRad1), >= 2 more
+    kFlagNotMono = 5,    // radii: 0 all EXACTLY rad0, 1 at most two classes (rad0's and kFlagRad1's, see edmd_note_radius), >= 2 more
     kFlagLeanFail = 6,   // the lean sweep declined (state not eligible): redo with the full path
     kFlagWork = 7,       // number of entries in the lean work list (chunks that hold particles)
-    kFlagRad1 = 8,       // (two words, 8-byte aligned) bits of the second radius, 0 = none seen
+    kFlagRad1 = 8,       // (two words, 8-byte aligned) bits of the first radius seen outside rad0's class, 0 = none
     kFlagCount = 16
 };
 
@@ -309,6 +309,15 @@ int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const do
 // resident state (upload, halo).  Plain reads first: after the first claim lands
 // nobody issues atomics any more.
 #ifdef __CUDACC__
+// A radius CLASS is a value and everything within kRadClassTol of it (relative): the reference's
+// growth phase leaves every disk at vr * t with its own rounding (src/EDMD.c:4992-5007, stopGrow
+// :4740 does not reset it), so its "monodisperse" and "bidisperse" runs hold ~10 distinct radii per
+// species within 1e-15 of each other.  Level 0 = every radius EXACTLY rad0 (the exact stage may use
+// the constant); level 1 = at most two classes (rad0's, and kFlagRad1's if one was seen): the
+// screening takes the class radius inflated by the tolerance, the exact stage reads each disk's own
+// FP64 radius.
+constexpr double kRadClassTol = 1e-9;
+__device__ __forceinline__ bool edmd_same_class(double r, double rc) { return fabs(r - rc) <= kRadClassTol * rc; }
 __device__ __forceinline__ void edmd_note_radius(int32_t *flags, double r, double rad0)
 {
     if (r == rad0) return;
@@ -316,9 +325,13 @@ __device__ __forceinline__ void edmd_note_radius(int32_t *flags, double r, doubl
     const unsigned long long bits = (unsigned long long)__double_as_longlong(r);
     int level = 2;
     if (r > 0) {
-        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(slot);
-        if (cur == 0ull) cur = atomicCAS(slot, 0ull, bits);
-        if (cur == 0ull || cur == bits) level = 1;
+        if (edmd_same_class(r, rad0)) {
+            level = 1;
+        } else {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(slot);
+            if (cur == 0ull) cur = atomicCAS(slot, 0ull, bits);
+            if (cur == 0ull || cur == bits || edmd_same_class(r, __longlong_as_double((long long)cur))) level = 1;
+        }
     }
     if ((*reinterpret_cast<volatile int32_t *>(flags + kFlagNotMono) & level) != level)
         atomicOr(&flags[kFlagNotMono], level);

@@ -2,9 +2,13 @@
 // prediction sweep built on it (lean_index.cu, predict_lean.cu).
 //
 // The lean path is taken for the re-predict sweep in NORMAL mode of a system with
-// ONE or TWO distinct radii (every BASELINE.json configuration, including the
+// ONE or TWO radius classes (every BASELINE.json configuration, including the
 // reference's default bidisperse run; general polydisperse systems keep the FP64
-// row kernel of predict.cu).  With two radii the class of a particle rides in the
+// row kernel of predict.cu).  A class is a value and everything within 1e-9 of it
+// (edmd_note_radius, edmd_internal.cuh): the reference's growth phase leaves ~10
+// distinct radii per species within 1e-15 of each other.  The screening uses the
+// class radius inflated by that tolerance; the exact stage reads each disk's own
+// FP64 radius unless all radii are exactly equal.  With two classes the class of a particle rides in the
 // least significant mantissa bit of its FP32 vy (one more ulp in the error model).
 // It moves fewer bytes and issues fewer instructions than the full path:
 //

@@ -223,7 +223,7 @@ k_lean_scatter(const __grid_constant__ ScatterArgs a)
         r.y = __double2float_rn(__dsub_rn(p[k].y, __dmul_rn((double)Yg + 0.5, a.b.csy)));
         r.z = __double2float_rn(p[k].z);
         r.w = __double2float_rn(p[k].w);
-        if (two) r.w = __int_as_float((__float_as_int(r.w) & ~1) | (a.rad[i0 + k] != a.rad0 ? 1 : 0));
+        if (two) r.w = __int_as_float((__float_as_int(r.w) & ~1) | (edmd_same_class(a.rad[i0 + k], a.rad0) ? 0 : 1));
         put_lean(a, slot[k], pc[k], i0 + k, r);
         if (pcx == 1) {   // cell 0 -> right ghost
             const int g = Yl * a.ps + a.nx + 1;

@@ -99,6 +99,12 @@ __device__ __forceinline__ LeanConsts make_consts(const edmd_dev_box &b, double 
     const double u = 5.9604644775390625e-08;    // 2^-24
     const double cs = fmax(b.csx, b.csy);
     const double Rm = 1.5 * cs, rho = cs, om = 0.5 * V;
+    // two classes: the class radii, inflated by the class tolerance (every disk of a class is at most
+    // that large: Cc stays an upper bound of 4 r_i r_j); no second class seen: class 1 is empty
+    if (two) {
+        rad1 = (rad1 > 0.0 ? rad1 : rad0) * (1.0 + kRadClassTol);
+        rad0 = rad0 * (1.0 + kRadClassTol);
+    }
     const double rmax = two ? fmax(rad0, rad1) : rad0;
     const double s2 = 4.0 * rmax * rmax;        // the error terms take the largest contact distance
     // two radii: the class bit in the last mantissa bit of vy costs one more ulp per particle

@@ -99,3 +99,42 @@ def growth_config(n: int, phi: float, seed: int) -> dict:
     cfg["vr"] = np.full(cfg["n"], vr)
     cfg["t"] = 0.6 / vr
     return cfg
+
+
+def tiled_config(base: dict, k: int, seed: int, *, shuffle: bool = True) -> dict:
+    """k x k periodic tiling of a periodic hard-disk configuration `base` (keys x, y,
+    rad, lx, ly: e.g. the reference-grown liquid of tests/golden/liquid_*.npz, SURVEY.md
+    8d second input family).  Copies are shifted by whole box lengths, so every
+    distance of the tiling is a distance (or a periodic image distance) of the base:
+    no overlaps are created.  Fresh Maxwell velocities (unit temperature, zero total
+    momentum) from the counter-based generator; shuffle=True permutes the particle ids.
+    The radii are taken as they are -- a reference-grown system holds ~10 distinct radii
+    within 1e-15 of each other (its growth phase rounds every disk on its own)."""
+    bx, by, brad = (np.asarray(base[key], dtype=np.float64) for key in ("x", "y", "rad"))
+    l0x, l0y = float(base["lx"]), float(base["ly"])
+    n0 = len(bx)
+    n = n0 * k * k
+    ids = np.arange(n, dtype=np.int64)
+    src = ids
+    if shuffle:
+        src = np.argsort(uniform01(seed, ids, 7), kind="stable")
+    p, tile = src % n0, src // n0
+    x = bx[p] + (tile % k).astype(np.float64) * l0x
+    y = by[p] + (tile // k).astype(np.float64) * l0y
+    lx, ly = k * l0x, k * l0y
+    # a sum like 3 * l0x + x can round up to the box length itself
+    x = np.where(x >= lx, np.nextafter(lx, 0.0), x)
+    y = np.where(y >= ly, np.nextafter(ly, 0.0), y)
+    u1 = 1.0 - uniform01(seed, ids, 2)
+    u2 = uniform01(seed, ids, 3)
+    rr = np.sqrt(-2.0 * np.log(u1))
+    vx = rr * np.cos(2.0 * math.pi * u2)
+    vy = rr * np.sin(2.0 * math.pi * u2)
+    vx -= vx.mean()
+    vy -= vy.mean()
+    rad = brad[p]
+    phi = float(math.pi * np.sum(rad * rad) / (lx * ly))
+    return dict(n=n, lx=lx, ly=ly, phi=phi, seed=seed,
+                x=np.ascontiguousarray(x), y=np.ascontiguousarray(y),
+                vx=np.ascontiguousarray(vx), vy=np.ascontiguousarray(vy),
+                rad=np.ascontiguousarray(rad))

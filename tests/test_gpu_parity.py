@@ -616,6 +616,67 @@ def _adversarial_clusters(seed, n_clusters, vscale):
                 rad=np.ones(n))
 
 
+@pytest.mark.parametrize("n,phi,seed,sf", [(120000, 0.70, 141, 0.0), (120000, 0.72, 142, 0.3)])
+def test_lean_sweep_with_radii_spread_inside_their_classes(pkg, oracle, n, phi, seed, sf):
+    """The reference's growth phase leaves every disk at vr * t with its own rounding
+    (src/EDMD.c:4992-5007; stopGrow :4740 does not reset it): its "monodisperse" and
+    "bidisperse" runs hold many distinct radii within ~1e-15 of one or two values.  The
+    lean path groups radii into classes (relative tolerance 1e-9), screens with the
+    inflated class radius and reads every disk's own FP64 radius in the exact stage:
+    same bits as the oracle, and the lean path is the one that ran."""
+    c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf)
+    ulps = np.random.default_rng(seed).integers(-4, 5, c["n"])
+    rad = c["rad"] * (1.0 + ulps * 2.0 ** -52)
+    assert len(np.unique(rad)) > 5
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], rad, t=1.5)
+        got = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 1
+        assert ctx.stat(pkg.binding.STAT_LEAN_DECLINES) == 0
+        rescans = ctx.stat(pkg.binding.STAT_EXACT_RESCANS)
+    want = oracle.predict_all(c["n"], c["lx"], c["ly"], 1.5, c["x"], c["y"], c["vx"], c["vy"], rad)
+    assert_events_equal(got, want)
+    assert rescans < 0.02 * c["n"], rescans
+
+
+def test_three_radius_classes_take_the_full_path(pkg, oracle):
+    c = pkg.synth.lattice_config(30000, 0.65, 143, small_fraction=0.3)
+    rad = c["rad"].copy()
+    rad[::7] *= 0.9          # a third species
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], rad, t=0.0)
+        got = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 0
+    want = oracle.predict_all(c["n"], c["lx"], c["ly"], 0.0, c["x"], c["y"], c["vx"], c["vy"], rad)
+    assert_events_equal(got, want)
+
+
+@pytest.mark.parametrize("k,seed", [(3, 151), (2, 152)])
+def test_reference_grown_liquid_tiled(pkg, oracle, k, seed):
+    """SURVEY.md 8d, second input family: a liquid grown and equilibrated by the reference
+    itself (tests/golden/liquid_n10000_phi070.npz, made by make_liquid.py from the
+    reference's own main()), tiled k x k with fresh velocities.  Sweep bit-exact on the
+    lean path (its radii are spread inside one class), psi6 and g(r) against the oracle."""
+    base = load_golden("liquid_n10000_phi070")
+    c = pkg.synth.tiled_config(base, k, seed)
+    n = c["n"]
+    assert len(np.unique(c["rad"])) > 1
+    max_r = min(c["lx"], c["ly"]) / 2
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        got = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 1
+        b = ctx.boop_cutoff(2.5)
+        p = ctx.pcf(0.1, max_r)
+    want = oracle.predict_all(n, c["lx"], c["ly"], 0.0, c["x"], c["y"], c["vx"], c["vy"], c["rad"])
+    assert_events_equal(got, want)
+    assert_boop_close(b, oracle.boop_cutoff(n, c["lx"], c["ly"], c["x"], c["y"], 2.5))
+    wp = oracle.pcf(n, c["lx"], c["ly"], c["x"], c["y"], 0.1, max_r)
+    assert np.array_equal(p["counts"], wp["counts"])
+    # a liquid: the first peak of g(r) sits at contact and g -> 1 at long range
+    assert p["g_r"][20:23].max() > 3.0 and abs(p["g_r"][-200:].mean() - 1.0) < 0.02
+
+
 @pytest.mark.parametrize("seed,vscale", [(61, 1.0), (62, 1.0), (63, 1e-5), (64, 2e3), (65, 1.0)])
 def test_lean_certificate_on_adversarial_pairs(pkg, oracle, seed, vscale):
     """Near-ties, near-contacts, grazing and nearly parallel pairs at relative

@@ -187,3 +187,25 @@ def test_oracle_thermostat_tick_matches_golden(oracle, name):
     assert_tick_close(got, g)
     e_after = 0.5 * (got["vx"] ** 2 + got["vy"] ** 2).sum()
     assert abs(e_after / c["n"] - float(g["T"])) < 1e-12          # the tick sets E/N = T
+
+
+def test_reference_grown_liquid_fixture_and_its_tiling(pkg, oracle):
+    """tests/golden/liquid_n10000_phi070.npz (the reference's own main() grew and
+    equilibrated it; make_liquid.py) is a periodic hard-disk liquid at phi = 0.70 whose
+    radii carry the growth phase's rounding; the k x k tiling keeps it overlap-free,
+    and the oracle's sweep on it finds a real collision for (nearly) every disk."""
+    from helpers import load_golden
+    base = load_golden("liquid_n10000_phi070")
+    n0, lx, ly = len(base["x"]), float(base["lx"]), float(base["ly"])
+    assert n0 == 10000 and abs(np.pi * np.sum(base["rad"] ** 2) / (lx * ly) - 0.70) < 1e-9
+    assert 1 < len(np.unique(base["rad"])) < 100 and np.abs(base["rad"] - 1).max() < 1e-12
+    c = pkg.synth.tiled_config(base, 2, seed=5)
+    assert c["n"] == 4 * n0 and (c["x"] < c["lx"]).all() and (c["y"] < c["ly"]).all()
+    assert abs(c["vx"].mean()) < 1e-12 and abs(c["vy"].mean()) < 1e-12
+    out = oracle.predict_all(c["n"], c["lx"], c["ly"], 0.0, c["x"], c["y"], c["vx"], c["vy"], c["rad"])
+    assert out["overlap"][0] < 0                      # no overlapping pair anywhere
+    assert (out["t_coll"] < 1e20).mean() > 0.95       # a dense liquid: nearly everyone has a partner
+    # the tiling is periodic with the base's period: pair counts of the tiling = 4 x the base's
+    pb = oracle.pcf(n0, lx, ly, base["x"], base["y"], 0.1, 8.0)
+    pt = oracle.pcf(c["n"], c["lx"], c["ly"], c["x"], c["y"], 0.1, 8.0)
+    assert np.array_equal(pt["counts"], 4 * pb["counts"])

@@ -437,11 +437,52 @@ struct F32Args {
     float lx32, ly32, hx32, hy32;   // fl32(L / dr) and exactly half of it
 };
 
-__device__ __forceinline__ float2 lds_float2(uint32_t addr)
+__device__ __forceinline__ float lds_float(uint32_t addr)
 {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
+}
+
+// ---- packed FP32 (sm_100: FADD2 / FFMA2, two lanes per instruction and per issue slot) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2_rd(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ void lds_2x64(uint32_t addr, f32x2 &a, f32x2 &b)
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
 
 __device__ __forceinline__ float4 lds_float4(uint32_t addr)
@@ -503,6 +544,35 @@ __device__ __forceinline__ float pair32(float bx, float by, float px, float py, 
     return frac;
 }
 
+// Two pairs (j, j+1) of one i at once with the packed instructions: lane for lane the same
+// round-to-nearest / round-down operations as pair32, so the same bits.  No wrap variant.
+struct Packed32 {
+    f32x2 px, py, neps, tiny, magic, nmagic;
+};
+// (Measured: doing the two subtractions as scalar FADDs, which either FMA pipe takes while the packed
+// forms only run on the heavy one, is slower -- 283 against 278 ms at N = 10^6.)
+template <bool INR>
+__device__ __forceinline__ void pair32x2(f32x2 bx, f32x2 by, const Packed32 &k, float tmax, uint32_t hbase,
+                                         float &f0, float &f1, uint32_t &t0, uint32_t &t1)
+{
+    const f32x2 dx = sub2(bx, k.px), dy = sub2(by, k.py);
+    const f32x2 s = fma2(dy, dy, fma2(dx, dx, k.tiny));
+    float s0, s1, y0, y1;
+    unpack2(s, s0, s1);
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(s0));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(s1));
+    const f32x2 qlo = fma2(s, pack2(y0, y1), k.neps);
+    const f32x2 t = add2_rd(qlo, k.magic);
+    const f32x2 frac = sub2(qlo, add2(t, k.nmagic));
+    float ta, tb;
+    unpack2(t, ta, tb);
+    unpack2(frac, f0, f1);
+    t0 = __float_as_uint(INR ? ta : fminf(ta, tmax));
+    t1 = __float_as_uint(INR ? tb : fminf(tb, tmax));
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hbase + (t0 << 2)), "r"(1u) : "memory");
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hbase + (t1 << 2)), "r"(1u) : "memory");
+}
+
 template <bool WX, bool WY, bool INR>
 __device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan &tp, float px, float py, int gi0,
                                             int gj0, uint32_t tile_addr, int jstart, int jcount, uint32_t hist_addr,
@@ -529,18 +599,55 @@ __device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan
     };
     int jj = jstart;
     uint32_t tb;
+    constexpr uint32_t kYOff = 4u * kTile;   // the tile is stored as x[kTile], y[kTile]
     for (; jj < jcount && (jj & 3); jj++) {
-        const float2 b = lds_float2(tile_addr + 8u * (uint32_t)jj);
-        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, tb) >= cth && (INR || tb != tmaxbits)) park(jj, tb);
+        const uint32_t ad = tile_addr + 4u * (uint32_t)jj;
+        if (pair32<WX, WY, INR>(lds_float(ad), lds_float(ad + kYOff), px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, tb) >= cth && (INR || tb != tmaxbits)) park(jj, tb);
     }
-    uint32_t addr = tile_addr + 8u * (uint32_t)jj;
-    for (; jj + 4 <= jcount; jj += 4, addr += 32u) {
-        const float4 b01 = lds_float4(addr), b23 = lds_float4(addr + 16u);
+    uint32_t addr = tile_addr + 4u * (uint32_t)jj;
+    Packed32 pk;
+    if (!WX && !WY) {
+        pk.px = pack2(px, px); pk.py = pack2(py, py);
+        pk.neps = pack2(-c, -c); pk.tiny = pack2(1e-30f, 1e-30f);
+        pk.magic = pack2(kMagic, kMagic); pk.nmagic = pack2(-kMagic, -kMagic);
+    }
+    // measured at N = 10^6: scalar 293 ms, packed four pairs per trip 278 ms, packed eight per trip 271 ms
+    if (!WX && !WY) {
+        for (; jj + 8 <= jcount; jj += 8, addr += 32u) {
+            uint32_t t[8];
+            float u[8];
+            f32x2 x01, x23, x45, x67, y01, y23, y45, y67;
+            lds_2x64(addr, x01, x23);
+            lds_2x64(addr + 16u, x45, x67);
+            lds_2x64(addr + kYOff, y01, y23);
+            lds_2x64(addr + kYOff + 16u, y45, y67);
+            pair32x2<INR>(x01, y01, pk, tmax, hbase, u[0], u[1], t[0], t[1]);
+            pair32x2<INR>(x23, y23, pk, tmax, hbase, u[2], u[3], t[2], t[3]);
+            pair32x2<INR>(x45, y45, pk, tmax, hbase, u[4], u[5], t[4], t[5]);
+            pair32x2<INR>(x67, y67, pk, tmax, hbase, u[6], u[7], t[6], t[7]);
+            if (fmaxf(fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3])), fmaxf(fmaxf(u[4], u[5]), fmaxf(u[6], u[7]))) >= cth) {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (u[q] >= cth && (INR || t[q] != tmaxbits)) park(jj + q, t[q]);
+            }
+        }
+    }
+    for (; jj + 4 <= jcount; jj += 4, addr += 16u) {
         uint32_t t0, t1, t2, t3;
-        const float u0 = pair32<WX, WY, INR>(b01.x, b01.y, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t0);
-        const float u1 = pair32<WX, WY, INR>(b01.z, b01.w, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t1);
-        const float u2 = pair32<WX, WY, INR>(b23.x, b23.y, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t2);
-        const float u3 = pair32<WX, WY, INR>(b23.z, b23.w, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t3);
+        float u0, u1, u2, u3;
+        if (!WX && !WY) {
+            f32x2 x01, x23, y01, y23;
+            lds_2x64(addr, x01, x23);
+            lds_2x64(addr + kYOff, y01, y23);
+            pair32x2<INR>(x01, y01, pk, tmax, hbase, u0, u1, t0, t1);
+            pair32x2<INR>(x23, y23, pk, tmax, hbase, u2, u3, t2, t3);
+        } else {
+            const float4 bx = lds_float4(addr), by = lds_float4(addr + kYOff);
+            u0 = pair32<WX, WY, INR>(bx.x, by.x, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t0);
+            u1 = pair32<WX, WY, INR>(bx.y, by.y, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t1);
+            u2 = pair32<WX, WY, INR>(bx.z, by.z, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t2);
+            u3 = pair32<WX, WY, INR>(bx.w, by.w, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, t3);
+        }
         if (fmaxf(fmaxf(u0, u1), fmaxf(u2, u3)) >= cth) {
             // (a pair clamped to the dummy word is certainly beyond the range: q* >= q_lo >= num_bins)
             if (u0 >= cth && (INR || t0 != tmaxbits)) park(jj, t0);
@@ -550,8 +657,8 @@ __device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan
         }
     }
     for (; jj < jcount; jj++) {
-        const float2 b = lds_float2(tile_addr + 8u * (uint32_t)jj);
-        if (pair32<WX, WY, INR>(b.x, b.y, px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, tb) >= cth && (INR || tb != tmaxbits)) park(jj, tb);
+        const uint32_t ad = tile_addr + 4u * (uint32_t)jj;
+        if (pair32<WX, WY, INR>(lds_float(ad), lds_float(ad + kYOff), px, py, c, tmax, lx32, ly32, hx32, hy32, hbase, tb) >= cth && (INR || tb != tmaxbits)) park(jj, tb);
     }
 }
 
@@ -579,116 +686,163 @@ __device__ __forceinline__ void plan_axis(double d0, double d1, double half, dou
     m_w = wrap ? fmax(half, m_un - len) : m_un;
 }
 
-__global__ void __launch_bounds__(kThreads)
+// The plan of tile pair w (one thread): skip / image shifts / eps / flags, see the header comment.
+__device__ __forceinline__ TilePairPlan make_plan(const F32Args &a, long long w, int nt, double rcut)
+{
+    const PcfArgs &p = a.p;
+    TilePairPlan tp;
+    // unrank w -> (ta, tb), ta <= tb, row-major over the upper triangle
+    const double fn = (double)nt + 0.5;
+    long long ta = (long long)(fn - sqrt(fn * fn - 2.0 * (double)w));
+    while (ta * nt - ta * (ta - 1) / 2 > w) ta--;
+    while ((ta + 1) * nt - (ta + 1) * ta / 2 <= w) ta++;
+    const long long tb = ta + (w - (ta * nt - ta * (ta - 1) / 2));
+    const double4 A = p.bbox[ta], B = p.bbox[tb];
+    double sx, sy, mxu, mxw, myu, myw, gx, gy;
+    bool wx, wy;
+    plan_axis(B.x - A.y, B.y - A.x, p.b.half_lx, p.b.lx, sx, wx, mxu, mxw, gx);
+    plan_axis(B.z - A.w, B.w - A.z, p.b.half_ly, p.b.ly, sy, wy, myu, myw, gy);
+    tp.ta = (int)ta;
+    tp.tb = (int)tb;
+    tp.eps = 0.0f;
+    tp.cth = 0.0f;
+    tp.cbs = make_double2(0.0, 0.0);
+    if (A.x != A.x || B.x != B.x) {
+        tp.flags = 16;   // a tile with non-finite or far-out coordinates (k_tile_bbox): FP64 for every pair
+        return tp;
+    }
+    if (gx * gx + gy * gy >= rcut * rcut) {
+        tp.flags = 8;
+        return tp;
+    }
+    const double u = 5.9604644775390625e-08 * 1.001;   // 2^-24, padded
+    const double id = a.inv_dr;
+    const double hbx = 0.5 * (B.y - B.x) * id, hby = 0.5 * (B.w - B.z) * id;
+    const double ex = u * (2.0 * hbx + 2.0 * mxu * id) + (wx ? u * p.b.lx * id : 0.0) + a.slack;
+    const double ey = u * (2.0 * hby + 2.0 * myu * id) + (wy ? u * p.b.ly * id : 0.0) + a.slack;
+    const double e = sqrt(ex * ex + ey * ey) * 1.001;
+    const double rmax = sqrt(mxw * mxw + myw * myw) * id * (1.0 + 1e-9);
+    // rsqrt.approx <= 2^-22.9 relative (PTX; measured 1.2467e-7 on B200, asserted by the GPU test);
+    // 1.01u from the two roundings of s under the square root, u from the fma of q_lo
+    const double rho = 1.28e-07 + 2.1 * u;
+    const double eps = ((rmax + e) * rho + e + 1e-12 + a.slack) * 1.001;
+    const float eps32 = __double2float_ru(eps);
+    tp.eps = eps32;
+    tp.cth = __double2float_rd(1.0 - 2.0 * (double)eps32 - 2.384185791015625e-07);
+    const bool inr = (rmax + e) * (1.0 + 1e-6) < (double)p.num_bins;   // every q_lo below num_bins
+    tp.flags = !(eps < 0.45) ? 16 : ((wx ? 1 : 0) | (wy ? 2 : 0) | ((inr && !wx && !wy) ? 4 : 0));
+    const double2 cb = a.ctr[tb];
+    tp.cbs = make_double2(cb.x + sx, cb.y + sy);
+    return tp;
+}
+
+constexpr int kPlanBatch = 64;   // tile pairs planned at once (one thread each)
+
+// A CTA takes the tile pairs w = first + k * stride.  Plans are made kPlanBatch at a time, one
+// thread each (the plan is a chain of ~60 dependent FP64 operations: made by one thread per tile pair
+// it was 4 % of the kernel and held eight warps at a barrier).  Per tile pair two barriers: the
+// drain of the previous pair's queue shares a phase with loading this pair's tile.
+__global__ void __launch_bounds__(kThreads, 4)   // 4 CTAs per SM by shared memory: 64 registers
 k_pcf_f32(const __grid_constant__ F32Args a)
 {
     extern __shared__ unsigned char smem_raw[];
-    float2 *tile = reinterpret_cast<float2 *>(smem_raw);
+    float *tile = reinterpret_cast<float *>(smem_raw);   // x[kTile], y[kTile]
     unsigned int *queue = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2));
     // [pad: 4 words][histogram][dummy words]: bin -1 (see pair32) lands in the pad, bins >= num_bins in hist[num_bins]
     unsigned int *hist = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2) + kQueue * sizeof(unsigned int)) + 4;
-    __shared__ TilePairPlan s_tp;
-    __shared__ int s_qn;
+    __shared__ TilePairPlan s_plans[kPlanBatch];
+    __shared__ int s_qn[2];
     const PcfArgs &p = a.p;
     for (int k = threadIdx.x; k < p.num_bins; k += kThreads) hist[k] = 0;
+    if (threadIdx.x < 2) s_qn[threadIdx.x] = 0;
     const int nt = (p.n + kTile - 1) / kTile;
     const long long npairs = (long long)nt * (nt + 1) / 2;
     unsigned int slow = 0;
     unsigned long long skipped = 0;
     const double rcut = p.max_r * (1.0 + 1e-12);
     const uint32_t tile_addr = smem_addr(tile), hist_addr = smem_addr(hist), queue_addr = smem_addr(queue);
-    // thread 0 walks this CTA's tile pairs w = first, first + stride, ... to the next one that is not
-    // skipped and leaves its plan in shared memory (flags 32: no tile pair left)
-    long long w = (long long)blockIdx.x * p.nparts + p.part;
     const long long wstride = (long long)gridDim.x * p.nparts;
-    for (;;) {
-        __syncthreads();   // previous tile pair drained, plan and tile consumed
-        if (threadIdx.x == 0) {
-            TilePairPlan tp;
-            tp.flags = 32;
-            for (; w < npairs; w += wstride) {
-                // unrank w -> (ta, tb), ta <= tb, row-major over the upper triangle
-                const double fn = (double)nt + 0.5;
-                long long ta = (long long)(fn - sqrt(fn * fn - 2.0 * (double)w));
-                while (ta * nt - ta * (ta - 1) / 2 > w) ta--;
-                while ((ta + 1) * nt - (ta + 1) * ta / 2 <= w) ta++;
-                const long long tb = ta + (w - (ta * nt - ta * (ta - 1) / 2));
-                const double4 A = p.bbox[ta], B = p.bbox[tb];
-                double sx, sy, mxu, mxw, myu, myw, gx, gy;
-                bool wx, wy;
-                plan_axis(B.x - A.y, B.y - A.x, p.b.half_lx, p.b.lx, sx, wx, mxu, mxw, gx);
-                plan_axis(B.z - A.w, B.w - A.z, p.b.half_ly, p.b.ly, sy, wy, myu, myw, gy);
-                tp.ta = (int)ta;
-                tp.tb = (int)tb;
-                if (A.x != A.x || B.x != B.x) {
-                    tp.flags = 16;   // a tile with non-finite or far-out coordinates (k_tile_bbox): FP64 for every pair
-                    break;
-                }
-                if (gx * gx + gy * gy >= rcut * rcut) {
-                    skipped++;
-                    continue;
-                }
-                const double u = 5.9604644775390625e-08 * 1.001;   // 2^-24, padded
-                const double id = a.inv_dr;
-                const double hbx = 0.5 * (B.y - B.x) * id, hby = 0.5 * (B.w - B.z) * id;
-                const double ex = u * (2.0 * hbx + 2.0 * mxu * id) + (wx ? u * p.b.lx * id : 0.0) + a.slack;
-                const double ey = u * (2.0 * hby + 2.0 * myu * id) + (wy ? u * p.b.ly * id : 0.0) + a.slack;
-                const double e = sqrt(ex * ex + ey * ey) * 1.001;
-                const double rmax = sqrt(mxw * mxw + myw * myw) * id * (1.0 + 1e-9);
-                // rsqrt.approx <= 2^-22.9 relative (PTX; measured 1.2467e-7 on B200, asserted by the GPU test);
-                // 1.01u from the two roundings of s under the square root, u from the fma of q_lo
-                const double rho = 1.28e-07 + 2.1 * u;
-                const double eps = ((rmax + e) * rho + e + 1e-12 + a.slack) * 1.001;
-                const float eps32 = __double2float_ru(eps);
-                tp.eps = eps32;
-                tp.cth = __double2float_rd(1.0 - 2.0 * (double)eps32 - 2.384185791015625e-07);
-                const bool inr = (rmax + e) * (1.0 + 1e-6) < (double)p.num_bins;   // every q_lo below num_bins
-                tp.flags = !(eps < 0.45) ? 16 : ((wx ? 1 : 0) | (wy ? 2 : 0) | ((inr && !wx && !wy) ? 4 : 0));
-                const double2 cb = a.ctr[tb];
-                tp.cbs = make_double2(cb.x + sx, cb.y + sy);
-                break;
-            }
-            w += wstride;
-            s_tp = tp;
-            s_qn = 0;
-        }
-        __syncthreads();
-        const int flags = s_tp.flags;
-        if (flags == 32) break;
-        const int ta = s_tp.ta, tb = s_tp.tb;
-        const int gi0 = (int)ta * kTile, gj0 = (int)tb * kTile;
-        if (gj0 + (int)threadIdx.x < p.n) tile[threadIdx.x] = a.rel[gj0 + threadIdx.x];
-        __syncthreads();
-        const int i = gi0 + threadIdx.x;
-        if (i < p.n) {
-            const double2 pi = p.sorted[i];
-            const double2 cbs = s_tp.cbs;
-            const float px = __double2float_rn((pi.x - cbs.x) * a.inv_dr);
-            const float py = __double2float_rn((pi.y - cbs.y) * a.inv_dr);
-            const int jcount = min(kTile, p.n - gj0);
-            const int jstart = (ta == tb) ? threadIdx.x + 1 : 0;
-            const uint32_t qn_addr = smem_addr(&s_qn);
-            switch (flags) {
-            case 16:
-                for (int jj = jstart; jj < jcount; jj++) exact_pair(p, i, gj0 + jj, hist_addr, kNotCounted);
-                slow += (unsigned int)max(jcount - jstart, 0);
-                break;
-            case 4: pair_loop32<false, false, true>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
-            case 0: pair_loop32<false, false, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
-            case 1: pair_loop32<true, false, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
-            case 2: pair_loop32<false, true, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
-            default: pair_loop32<true, true, false>(a, s_tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
-            }
-        }
-        __syncthreads();
-        // drain: the parked pairs with the reference's FP64 operations
-        const int qn = min(s_qn, kQueue);
+    long long wbase = (long long)blockIdx.x * p.nparts + p.part;
+    int par = 0;                 // which queue counter the next tile pair parks with
+    bool have_prev = false;      // a tile pair whose queue is not drained yet
+    int pgi0 = 0, pgj0 = 0;
+    // drain: the parked pairs of the previous tile pair with the reference's FP64 operations
+    auto drain = [&](int counter) {
+        const int qn = min(s_qn[counter], kQueue);
         for (int k = threadIdx.x; k < qn; k += kThreads) {
             const unsigned int e = queue[k];
-            exact_pair(p, gi0 + (int)((e >> 8) & 255u), gj0 + (int)(e & 255u), hist_addr, e >> 16);
+            exact_pair(p, pgi0 + (int)((e >> 8) & 255u), pgj0 + (int)(e & 255u), hist_addr, e >> 16);
             slow++;
         }
+    };
+    for (bool done = false; !done; wbase += (long long)kPlanBatch * wstride) {
+        if (have_prev) {
+            drain(par ^ 1);
+            have_prev = false;
+        }
+        __syncthreads();   // everybody is through with the previous batch of plans (and the drain)
+        if (threadIdx.x < kPlanBatch) {
+            const long long w = wbase + (long long)threadIdx.x * wstride;
+            TilePairPlan tp;
+            tp.flags = 32;   // no tile pair left
+            if (w < npairs) {
+                tp = make_plan(a, w, nt, rcut);
+                if (tp.flags == 8) skipped++;
+            }
+            s_plans[threadIdx.x] = tp;
+        }
+        __syncthreads();
+        for (int k = 0; k < kPlanBatch; k++) {
+            const TilePairPlan &tp = s_plans[k];
+            const int flags = tp.flags;
+            if (flags == 32) {
+                done = true;
+                break;
+            }
+            if (flags == 8) continue;
+            const int ta = tp.ta, tb = tp.tb;
+            const int gi0 = ta * kTile, gj0 = tb * kTile;
+            // phase 1: the previous pair's queue is drained while this pair's tile comes in
+            if (have_prev) drain(par ^ 1);
+            if (gj0 + (int)threadIdx.x < p.n) {
+                const float2 b = a.rel[gj0 + threadIdx.x];
+                tile[threadIdx.x] = b.x;
+                tile[kTile + threadIdx.x] = b.y;
+            }
+            const int i = gi0 + threadIdx.x;
+            float px = 0.0f, py = 0.0f;
+            if (i < p.n && flags != 16) {
+                const double2 pi = p.sorted[i];
+                px = __double2float_rn((pi.x - tp.cbs.x) * a.inv_dr);
+                py = __double2float_rn((pi.y - tp.cbs.y) * a.inv_dr);
+            }
+            __syncthreads();
+            // phase 2: the pairs of this tile pair
+            if (threadIdx.x == 0) s_qn[par ^ 1] = 0;   // drained in phase 1; next used by the next tile pair
+            if (i < p.n) {
+                const int jcount = min(kTile, p.n - gj0);
+                const int jstart = (ta == tb) ? threadIdx.x + 1 : 0;
+                const uint32_t qn_addr = smem_addr(&s_qn[par]);
+                switch (flags) {
+                case 16:
+                    for (int jj = jstart; jj < jcount; jj++) exact_pair(p, i, gj0 + jj, hist_addr, kNotCounted);
+                    slow += (unsigned int)max(jcount - jstart, 0);
+                    break;
+                case 4: pair_loop32<false, false, true>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
+                case 0: pair_loop32<false, false, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
+                case 1: pair_loop32<true, false, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
+                case 2: pair_loop32<false, true, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
+                default: pair_loop32<true, true, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
+                }
+            }
+            __syncthreads();
+            pgi0 = gi0;
+            pgj0 = gj0;
+            have_prev = true;
+            par ^= 1;
+        }
     }
+    if (have_prev) drain(par ^ 1);
     __syncthreads();
     for (int k = threadIdx.x; k < p.num_bins; k += kThreads) {
         const unsigned int v = hist[k];
@@ -696,7 +850,7 @@ k_pcf_f32(const __grid_constant__ F32Args a)
     }
     if (p.stats) {
         if (slow) atomicAdd(&p.stats[0], (unsigned long long)slow);
-        if (threadIdx.x == 0 && skipped) atomicAdd(&p.stats[1], skipped);
+        if (skipped) atomicAdd(&p.stats[1], skipped);
     }
 }
 

@@ -395,7 +395,9 @@ k_screen(const __grid_constant__ ScreenArgs a)
         if (blockIdx.x == 0 && threadIdx.x == 0) a.flags[kFlagLeanFail] = 1;
         return;
     }
-    if (classes == 1) screen_main<true>(a, K, lean_smem);
+    // the class bit is only looked at when a second class exists: one class with spread radii (a
+    // reference-grown monodisperse system) screens like one radius, with the inflated constant
+    if (classes == 1 && rad1 > 0.0) screen_main<true>(a, K, lean_smem);
     else screen_main<false>(a, K, lean_smem);
 }
 

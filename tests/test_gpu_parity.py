@@ -404,6 +404,33 @@ def test_pcf_points_on_bin_edges(pkg, oracle, dr, spacing, frac):
     assert exact > 0          # the edge pairs did go through the FP64 path
 
 
+def test_pcf_with_stray_and_non_finite_coordinates(pkg, oracle):
+    """edmd_cuda_pcf_device takes any device array.  A NaN coordinate (the reference's
+    `r < max_r` is false for it: the pairs are dropped) and coordinates outside the box
+    (the reference wraps once, src/EDMD.c:5896-5913) must come out as the reference's
+    arithmetic has them: tiles holding such a particle leave the FP32 path entirely."""
+    import torch
+    c = pkg.synth.lattice_config(20000, 0.70, 161)
+    x, y = c["x"].copy(), c["y"].copy()
+    x[17] = np.nan
+    x[4711] = c["lx"] + 3.0
+    y[9000] = -2.0 * c["ly"] - 1.0
+    x[15000], y[15000] = 40.0 * c["lx"], 0.5
+    dr, max_r = 0.1, 0.5 * min(c["lx"], c["ly"])
+    xy = torch.from_numpy(np.stack([x, y], axis=1).copy()).cuda()
+    nb = int(max_r / dr)
+    counts = torch.zeros(nb, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        assert ctx.pcf_device(xy.data_ptr(), c["n"], dr, max_r, 0, 1, counts.data_ptr()) == nb
+        exact = ctx.stat(pkg.binding.STAT_PCF_EXACT_PAIRS)
+    want = oracle.pcf(c["n"], c["lx"], c["ly"], x, y, dr, max_r)
+    assert np.array_equal(counts.cpu().numpy().astype(np.uint64), want["counts"])
+    # the tiles of the NaN and of the far-out particle went through FP64 whole (the two strays within
+    # 2 L of the box stay on the FP32 path: its error bound covers them)
+    assert exact > 256 * (c["n"] - 512)
+
+
 def test_pcf_fp32_decision_at_full_size(pkg):
     """N = 10^6 (BASELINE configs[2]) at a range the test can afford twice: the default
     kernel against the FP64-certified one, and the pair checksum."""

@@ -576,7 +576,7 @@ __device__ __forceinline__ void pair32x2(f32x2 bx, f32x2 by, const Packed32 &k, 
 template <bool WX, bool WY, bool INR>
 __device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan &tp, float px, float py, int gi0,
                                             int gj0, uint32_t tile_addr, int jstart, int jcount, uint32_t hist_addr,
-                                            uint32_t queue_addr, uint32_t qn, unsigned int &slow)
+                                            uint32_t queue_addr, uint32_t qn, unsigned int &slow, unsigned int tid)
 {
     const float c = tp.eps, cth = tp.cth, tmax = a.tmax;
     const float lx32 = a.lx32, ly32 = a.ly32, hx32 = a.hx32, hy32 = a.hy32;
@@ -590,10 +590,10 @@ __device__ __forceinline__ void pair_loop32(const F32Args &a, const TilePairPlan
         asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(qn + ((tbits >> 31) << 2)) : "memory");
         if (slot < (uint32_t)kQueue) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(queue_addr + 4u * (uint32_t)slot),
-                         "r"((counted << 16) | (threadIdx.x << 8) | (unsigned int)j)
+                         "r"((counted << 16) | (tid << 8) | (unsigned int)j)
                          : "memory");
         } else {
-            exact_pair(a.p, gi0 + (int)threadIdx.x, gj0 + j, hist_addr, counted);
+            exact_pair(a.p, gi0 + (int)tid, gj0 + j, hist_addr, counted);
             slow++;
         }
     };
@@ -737,39 +737,54 @@ __device__ __forceinline__ TilePairPlan make_plan(const F32Args &a, long long w,
 }
 
 constexpr int kPlanBatch = 64;   // tile pairs planned at once (one thread each)
+constexpr size_t kGroupSmem = kTile * sizeof(float2) + kQueue * sizeof(unsigned int);   // tile + queue of one group
 
-// A CTA takes the tile pairs w = first + k * stride.  Plans are made kPlanBatch at a time, one
-// thread each (the plan is a chain of ~60 dependent FP64 operations: made by one thread per tile pair
-// it was 4 % of the kernel and held eight warps at a barrier).  Per tile pair two barriers: the
-// drain of the previous pair's queue shares a phase with loading this pair's tile.
-__global__ void __launch_bounds__(kThreads, 4)   // 4 CTAs per SM by shared memory: 64 registers
+__device__ __forceinline__ void group_barrier(int group)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kThreads) : "memory");
+}
+
+// A CTA is G groups of 256 threads that share ONE histogram (the histogram is what limits the CTAs
+// per SM: 39 KB at N = 10^6, 79 KB at 4*10^6, 112 KB at 8*10^6 -- with G = 4 one resident CTA still
+// gives 32 warps).  Each group is what a CTA used to be: its own tile, queue, plans and named barrier,
+// and it takes the tile pairs w = first + k * stride of its virtual CTA id.  Plans are made kPlanBatch
+// at a time, one thread each (the plan is a chain of ~60 dependent FP64 operations: made by one thread
+// per tile pair it was 4 % of the kernel and held eight warps at a barrier).  Per tile pair two
+// barriers: the drain of the previous pair's queue shares a phase with loading this pair's tile.
+template <int G>
+__global__ void __launch_bounds__(kThreads * G, G == 1 ? 4 : (G == 2 ? 2 : 1))   // 64 registers
 k_pcf_f32(const __grid_constant__ F32Args a)
 {
     extern __shared__ unsigned char smem_raw[];
-    float *tile = reinterpret_cast<float *>(smem_raw);   // x[kTile], y[kTile]
-    unsigned int *queue = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2));
+    const int group = threadIdx.x / kThreads;
+    const unsigned int tid = threadIdx.x % kThreads;
+    float *tile = reinterpret_cast<float *>(smem_raw + group * kGroupSmem);   // x[kTile], y[kTile]
+    unsigned int *queue = reinterpret_cast<unsigned int *>(smem_raw + group * kGroupSmem + kTile * sizeof(float2));
     // [pad: 4 words][histogram][dummy words]: bin -1 (see pair32) lands in the pad, bins >= num_bins in hist[num_bins]
-    unsigned int *hist = reinterpret_cast<unsigned int *>(smem_raw + kTile * sizeof(float2) + kQueue * sizeof(unsigned int)) + 4;
-    __shared__ TilePairPlan s_plans[kPlanBatch];
-    __shared__ int s_qn[2];
+    unsigned int *hist = reinterpret_cast<unsigned int *>(smem_raw + G * kGroupSmem) + 4;
+    __shared__ TilePairPlan s_plans_all[G][kPlanBatch];
+    __shared__ int s_qn_all[G][2];
+    TilePairPlan *s_plans = s_plans_all[group];
+    int *s_qn = s_qn_all[group];
     const PcfArgs &p = a.p;
-    for (int k = threadIdx.x; k < p.num_bins; k += kThreads) hist[k] = 0;
-    if (threadIdx.x < 2) s_qn[threadIdx.x] = 0;
+    for (int k = threadIdx.x; k < p.num_bins; k += kThreads * G) hist[k] = 0;
+    if (tid < 2) s_qn[tid] = 0;
+    __syncthreads();
     const int nt = (p.n + kTile - 1) / kTile;
     const long long npairs = (long long)nt * (nt + 1) / 2;
     unsigned int slow = 0;
     unsigned long long skipped = 0;
     const double rcut = p.max_r * (1.0 + 1e-12);
     const uint32_t tile_addr = smem_addr(tile), hist_addr = smem_addr(hist), queue_addr = smem_addr(queue);
-    const long long wstride = (long long)gridDim.x * p.nparts;
-    long long wbase = (long long)blockIdx.x * p.nparts + p.part;
+    const long long wstride = (long long)gridDim.x * G * p.nparts;
+    long long wbase = ((long long)blockIdx.x * G + group) * p.nparts + p.part;
     int par = 0;                 // which queue counter the next tile pair parks with
     bool have_prev = false;      // a tile pair whose queue is not drained yet
     int pgi0 = 0, pgj0 = 0;
     // drain: the parked pairs of the previous tile pair with the reference's FP64 operations
     auto drain = [&](int counter) {
         const int qn = min(s_qn[counter], kQueue);
-        for (int k = threadIdx.x; k < qn; k += kThreads) {
+        for (int k = tid; k < qn; k += kThreads) {
             const unsigned int e = queue[k];
             exact_pair(p, pgi0 + (int)((e >> 8) & 255u), pgj0 + (int)(e & 255u), hist_addr, e >> 16);
             slow++;
@@ -780,18 +795,18 @@ k_pcf_f32(const __grid_constant__ F32Args a)
             drain(par ^ 1);
             have_prev = false;
         }
-        __syncthreads();   // everybody is through with the previous batch of plans (and the drain)
-        if (threadIdx.x < kPlanBatch) {
-            const long long w = wbase + (long long)threadIdx.x * wstride;
+        group_barrier(group);   // everybody is through with the previous batch of plans (and the drain)
+        if (tid < kPlanBatch) {
+            const long long w = wbase + (long long)tid * wstride;
             TilePairPlan tp;
             tp.flags = 32;   // no tile pair left
             if (w < npairs) {
                 tp = make_plan(a, w, nt, rcut);
                 if (tp.flags == 8) skipped++;
             }
-            s_plans[threadIdx.x] = tp;
+            s_plans[tid] = tp;
         }
-        __syncthreads();
+        group_barrier(group);
         for (int k = 0; k < kPlanBatch; k++) {
             const TilePairPlan &tp = s_plans[k];
             const int flags = tp.flags;
@@ -804,38 +819,38 @@ k_pcf_f32(const __grid_constant__ F32Args a)
             const int gi0 = ta * kTile, gj0 = tb * kTile;
             // phase 1: the previous pair's queue is drained while this pair's tile comes in
             if (have_prev) drain(par ^ 1);
-            if (gj0 + (int)threadIdx.x < p.n) {
-                const float2 b = a.rel[gj0 + threadIdx.x];
-                tile[threadIdx.x] = b.x;
-                tile[kTile + threadIdx.x] = b.y;
+            if (gj0 + (int)tid < p.n) {
+                const float2 b = a.rel[gj0 + tid];
+                tile[tid] = b.x;
+                tile[kTile + tid] = b.y;
             }
-            const int i = gi0 + threadIdx.x;
+            const int i = gi0 + tid;
             float px = 0.0f, py = 0.0f;
             if (i < p.n && flags != 16) {
                 const double2 pi = p.sorted[i];
                 px = __double2float_rn((pi.x - tp.cbs.x) * a.inv_dr);
                 py = __double2float_rn((pi.y - tp.cbs.y) * a.inv_dr);
             }
-            __syncthreads();
+            group_barrier(group);
             // phase 2: the pairs of this tile pair
-            if (threadIdx.x == 0) s_qn[par ^ 1] = 0;   // drained in phase 1; next used by the next tile pair
+            if (tid == 0) s_qn[par ^ 1] = 0;   // drained in phase 1; next used by the next tile pair
             if (i < p.n) {
                 const int jcount = min(kTile, p.n - gj0);
-                const int jstart = (ta == tb) ? threadIdx.x + 1 : 0;
+                const int jstart = (ta == tb) ? (int)tid + 1 : 0;
                 const uint32_t qn_addr = smem_addr(&s_qn[par]);
                 switch (flags) {
                 case 16:
                     for (int jj = jstart; jj < jcount; jj++) exact_pair(p, i, gj0 + jj, hist_addr, kNotCounted);
                     slow += (unsigned int)max(jcount - jstart, 0);
                     break;
-                case 4: pair_loop32<false, false, true>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
-                case 0: pair_loop32<false, false, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
-                case 1: pair_loop32<true, false, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
-                case 2: pair_loop32<false, true, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
-                default: pair_loop32<true, true, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow); break;
+                case 4: pair_loop32<false, false, true>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow, tid); break;
+                case 0: pair_loop32<false, false, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow, tid); break;
+                case 1: pair_loop32<true, false, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow, tid); break;
+                case 2: pair_loop32<false, true, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow, tid); break;
+                default: pair_loop32<true, true, false>(a, tp, px, py, gi0, gj0, tile_addr, jstart, jcount, hist_addr, queue_addr, qn_addr, slow, tid); break;
                 }
             }
-            __syncthreads();
+            group_barrier(group);
             pgi0 = gi0;
             pgj0 = gj0;
             have_prev = true;
@@ -844,7 +859,7 @@ k_pcf_f32(const __grid_constant__ F32Args a)
     }
     if (have_prev) drain(par ^ 1);
     __syncthreads();
-    for (int k = threadIdx.x; k < p.num_bins; k += kThreads) {
+    for (int k = threadIdx.x; k < p.num_bins; k += kThreads * G) {
         const unsigned int v = hist[k];
         if (v) atomicAdd(&p.counts[k], (unsigned long long)v);
     }
@@ -909,7 +924,8 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     // queue, q = r/dr stays far below 2^22 and the expected share of undecided pairs
     // (~2 q_max * 5.4e-7) is small; else bins certified in FP64 (k_pcf_sorted)
     const double lmax = c->box.lx > c->box.ly ? c->box.lx : c->box.ly;
-    const size_t f32_smem = kTile * sizeof(float2) + kQueue * sizeof(unsigned int) + ((size_t)num_bins + 4 + 32) * sizeof(unsigned int);
+    const size_t f32_hist = ((size_t)num_bins + 4 + 32) * sizeof(unsigned int);
+    const size_t f32_smem = kGroupSmem + f32_hist;   // with one group per CTA
     const bool f32 = c->pcf_mode == 0 && f32_smem <= 200 * 1024 && num_bins < 65535 && dr > 0.0 && max_r > 0.0 &&
                      num_bins <= (int)(max_r / dr) &&   // then `bin < num_bins` implies r < max_r (see pair32)
                      1.5 * lmax / dr < 2097152.0 && max_r / dr <= 60000.0 && lmax / dr <= 120000.0;
@@ -982,18 +998,42 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
         fa.ly32 = (float)(c->box.ly * inv_dr);
         fa.hx32 = 0.5f * fa.lx32;
         fa.hy32 = 0.5f * fa.ly32;
+        // groups of 256 threads per CTA (they share the histogram): the G with the most resident warps
         static bool attr32 = false;
         if (!attr32) {
-            cudaFuncSetAttribute(k_pcf_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+            cudaFuncSetAttribute(k_pcf_f32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+            cudaFuncSetAttribute(k_pcf_f32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+            cudaFuncSetAttribute(k_pcf_f32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
             attr32 = true;
         }
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_f32, kThreads, f32_smem);
-        if (per_sm < 1) per_sm = 1;
-        long long grid = sms * per_sm;
-        if (grid > npairs) grid = npairs;
+        int best_g = 1, best_warps = 0, best_per_sm = 1;
+        const char *force = getenv("EDMD_PCF_GROUPS");   // tests force the multi-group kernels at small sizes
+        for (int g = 1; g <= 4; g *= 2) {
+            const size_t sm = g * kGroupSmem + f32_hist;
+            if (sm > 208 * 1024) break;
+            int per_sm = 0;
+            if (g == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_f32<1>, kThreads, sm);
+            else if (g == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_f32<2>, 2 * kThreads, sm);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_f32<4>, 4 * kThreads, sm);
+            const int warps = per_sm * g * (kThreads / 32);
+            const bool forced = force && atoi(force) == g && per_sm > 0;
+            // ties go to the larger CTA (measured at N = 10^6, 32 warps each way: 274 / 267 / 256 ms for 1 / 2 / 4 groups;
+            // N = 2*10^6: 1240 / 1117 / 1071 ms)
+            if (warps >= best_warps || forced) {
+                best_warps = forced ? 1 << 20 : warps;
+                best_g = g;
+                best_per_sm = per_sm;
+            }
+        }
+        if (best_per_sm < 1) best_per_sm = 1;
+        const size_t smem = best_g * kGroupSmem + f32_hist;
+        long long grid = sms * best_per_sm;
+        const long long vctas = (npairs + best_g - 1) / best_g;
+        if (grid > vctas) grid = vctas;
         if (grid < 1) grid = 1;
-        k_pcf_f32<<<(int)grid, kThreads, f32_smem, c->stream>>>(fa);
+        if (best_g == 1) k_pcf_f32<1><<<(int)grid, kThreads, smem, c->stream>>>(fa);
+        else if (best_g == 2) k_pcf_f32<2><<<(int)grid, 2 * kThreads, smem, c->stream>>>(fa);
+        else k_pcf_f32<4><<<(int)grid, 4 * kThreads, smem, c->stream>>>(fa);
         return launched;
     }
     const size_t tile_bytes = kTile * sizeof(double2);

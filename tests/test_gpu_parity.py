@@ -404,6 +404,26 @@ def test_pcf_points_on_bin_edges(pkg, oracle, dr, spacing, frac):
     assert exact > 0          # the edge pairs did go through the FP64 path
 
 
+def test_pcf_groups_sharing_one_histogram(pkg, monkeypatch):
+    """Large histograms (N >= 2*10^6) leave room for one or two CTAs per SM only, so a CTA
+    then holds 2 or 4 groups of 256 threads that share the histogram, each with its own tile,
+    queue, plans and named barrier.  Forced here at a size the test can afford: same counts."""
+    c = pkg.synth.lattice_config(150000, 0.70, 171)
+    max_r = min(c["lx"], c["ly"]) / 2
+    got = {}
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        for g in (1, 2, 4):
+            monkeypatch.setenv("EDMD_PCF_GROUPS", str(g))
+            got[g] = ctx.pcf(0.1, max_r)["counts"]
+        monkeypatch.delenv("EDMD_PCF_GROUPS")
+        ctx.set_option(pkg.binding.OPT_PCF_LEGACY, 2)
+        ref = ctx.pcf(0.1, max_r)["counts"]
+    for g in (1, 2, 4):
+        assert np.array_equal(got[g], ref), g
+    assert int(ref.sum()) > 0
+
+
 def test_pcf_with_stray_and_non_finite_coordinates(pkg, oracle):
     """edmd_cuda_pcf_device takes any device array.  A NaN coordinate (the reference's
     `r < max_r` is false for it: the pairs are dropped) and coordinates outside the box

@@ -446,20 +446,21 @@ def run_ours(args, cfg):
             analysis["device_tick_ms"] = float(np.median(ticks) * 1e3)
         if args.analysis == "full":
             max_r = min(cfg["lx"], cfg["ly"]) / 2
-            pt, _ = ctx.bench(B.BENCH_PCF, dr=0.1, max_r=max_r, warmup=0, iters=1)
+            # one untimed frame first: the first call allocates the sort scratch and loads the kernels
+            pt, _ = ctx.bench(B.BENCH_PCF, dr=0.1, max_r=max_r, warmup=1, iters=2)
             pairs = n * (n - 1) / 2
-            analysis["gr_full_ms"] = float(pt[0])
+            analysis["gr_full_ms"] = float(np.mean(pt))
             analysis["gr_full_bins"] = int(max_r / 0.1)
-            analysis["gr_full_pairs_per_s"] = pairs / (pt[0] * 1e-3)
-            analysis["gr_full_fp64_tflops_9op"] = 9 * pairs / (pt[0] * 1e-3) / 1e12
-            analysis["frames_per_s_gr_full_plus_psi6"] = 1e3 / (pt[0] + np.mean(bt))
+            analysis["gr_full_pairs_per_s"] = pairs / (float(np.mean(pt)) * 1e-3)
+            analysis["gr_full_reference_op_rate_tflops_9op"] = 9 * pairs / (float(np.mean(pt)) * 1e-3) / 1e12
+            analysis["frames_per_s_gr_full_plus_psi6"] = 1e3 / (float(np.mean(pt)) + np.mean(bt))
             # the same frame with every bin certified in FP64 (the previous default kernel):
             # its time, and the two histograms compared bin by bin at full size
             e0 = ctx.stat(B.STAT_PCF_EXACT_PAIRS)
             fast = ctx.pcf(0.1, max_r)["counts"]
             analysis["gr_full_exact_path_share"] = (ctx.stat(B.STAT_PCF_EXACT_PAIRS) - e0) / pairs
             ctx.set_option(B.OPT_PCF_LEGACY, 2)
-            p64, _ = ctx.bench(B.BENCH_PCF, dr=0.1, max_r=max_r, warmup=0, iters=1)
+            p64, _ = ctx.bench(B.BENCH_PCF, dr=0.1, max_r=max_r, warmup=1, iters=1)
             slow = ctx.pcf(0.1, max_r)["counts"]
             ctx.set_option(B.OPT_PCF_LEGACY, 0)
             analysis["gr_full_ms_fp64_certified_kernel"] = float(p64[0])
@@ -489,7 +490,7 @@ def run_ours(args, cfg):
                 "k1_ms": float(np.mean(lmain)), "lean_path": bool(eligible and not declines),
             }
             if args.analysis == "full":
-                lp, _ = lctx.bench(B.BENCH_PCF, dr=0.1, max_r=min(lc["lx"], lc["ly"]) / 2, warmup=0, iters=1)
+                lp, _ = lctx.bench(B.BENCH_PCF, dr=0.1, max_r=min(lc["lx"], lc["ly"]) / 2, warmup=1, iters=1)
                 liquid["gr_full_ms"] = float(lp[0])
 
     cpu = cpu_baseline(cfg) if (rank == 0 and world == 1 and not args.no_cpu) else None

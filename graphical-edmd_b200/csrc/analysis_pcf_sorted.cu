@@ -1007,7 +1007,6 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
             attr32 = true;
         }
         int best_g = 1, best_warps = 0, best_per_sm = 1;
-        const char *force = getenv("EDMD_PCF_GROUPS");   // tests force the multi-group kernels at small sizes
         for (int g = 1; g <= 4; g *= 2) {
             const size_t sm = g * kGroupSmem + f32_hist;
             if (sm > 208 * 1024) break;
@@ -1016,7 +1015,7 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
             else if (g == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_f32<2>, 2 * kThreads, sm);
             else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_f32<4>, 4 * kThreads, sm);
             const int warps = per_sm * g * (kThreads / 32);
-            const bool forced = force && atoi(force) == g && per_sm > 0;
+            const bool forced = c->pcf_groups == g && per_sm > 0;   // EDMD_OPT_PCF_GROUPS
             // ties go to the larger CTA (measured at N = 10^6, 32 warps each way: 274 / 267 / 256 ms for 1 / 2 / 4 groups;
             // N = 2*10^6: 1240 / 1117 / 1071 ms)
             if (warps >= best_warps || forced) {

@@ -347,6 +347,11 @@ int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
         c->pcf_mode = (value == 1 || value == 2) ? value : 0;
         return 0;
     }
+    if (option == EDMD_OPT_PCF_GROUPS) {
+        if (value != 0 && value != 1 && value != 2 && value != 4) return fail(c, EDMD_EINVAL, "groups: 0, 1, 2 or 4");
+        c->pcf_groups = value;
+        return 0;
+    }
     if (option == EDMD_OPT_NO_PDL) {
         c->lean_pdl = value == 0;
         return 0;

@@ -223,6 +223,7 @@ struct edmd_ctx {
     char *pcfs_mem;                   // sorted-tile g(r) scratch (analysis_pcf_sorted.cu)
     size_t pcfs_bytes;
     unsigned long long *pcfs_stats;   // [0] pairs binned by the exact path, [1] tile pairs skipped
+    int pcf_groups;                   // EDMD_OPT_PCF_GROUPS: 0 automatic, else 1 / 2 / 4
     int pcf_mode;                     // EDMD_OPT_PCF_LEGACY: 0 FP32-decided sorted tiles, 1 plain kernel, 2 FP64-certified sorted tiles
     unsigned long long *pcf_wsum;     // weighted sums (2^-32 fixed point), capacity pcf_wcap bins
     int pcf_wcap;

@@ -96,6 +96,10 @@ uint64_t edmd_cuda_launch_count(const edmd_ctx *ctx);
  * sqrt and division per pair, id-ordered tiles); 2 = sorted tiles with every bin
  * certified in FP64.  Same integer counts; for cross-checking and timing. */
 #define EDMD_OPT_PCF_LEGACY 4
+/* EDMD_OPT_PCF_GROUPS: the default g(r) kernel runs CTAs of 1, 2 or 4 groups of 256 threads
+ * that share one shared-memory histogram; 0 (default) lets the library pick the count with the
+ * most resident warps, 1 / 2 / 4 force it (cross-checking and timing). */
+#define EDMD_OPT_PCF_GROUPS 5
 int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 /* Counters: EDMD_STAT_EXACT_RESCANS = particles the tiled sweep had to resolve
  * with the exact re-scan (near-ties, ill-conditioned pairs) since create. */

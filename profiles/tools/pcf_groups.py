@@ -9,7 +9,6 @@ max_r = min(c["lx"], c["ly"]) / 2
 with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
     ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
     for g in ("1", "2", "4", ""):
-        if g: os.environ["EDMD_PCF_GROUPS"] = g
-        else: os.environ.pop("EDMD_PCF_GROUPS", None)
+        ctx.set_option(B.OPT_PCF_GROUPS, int(g or 0))
         t = ctx.bench(B.BENCH_PCF, dr=0.1, max_r=max_r, warmup=0, iters=1)[0][0]
         print("N", c["n"], "bins", int(max_r / 0.1), "groups", g or "auto", "ms", float(t), flush=True)

@@ -404,7 +404,7 @@ def test_pcf_points_on_bin_edges(pkg, oracle, dr, spacing, frac):
     assert exact > 0          # the edge pairs did go through the FP64 path
 
 
-def test_pcf_groups_sharing_one_histogram(pkg, monkeypatch):
+def test_pcf_groups_sharing_one_histogram(pkg):
     """Large histograms (N >= 2*10^6) leave room for one or two CTAs per SM only, so a CTA
     then holds 2 or 4 groups of 256 threads that share the histogram, each with its own tile,
     queue, plans and named barrier.  Forced here at a size the test can afford: same counts."""
@@ -414,9 +414,9 @@ def test_pcf_groups_sharing_one_histogram(pkg, monkeypatch):
     with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
         ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
         for g in (1, 2, 4):
-            monkeypatch.setenv("EDMD_PCF_GROUPS", str(g))
+            ctx.set_option(pkg.binding.OPT_PCF_GROUPS, g)
             got[g] = ctx.pcf(0.1, max_r)["counts"]
-        monkeypatch.delenv("EDMD_PCF_GROUPS")
+        ctx.set_option(pkg.binding.OPT_PCF_GROUPS, 0)
         ctx.set_option(pkg.binding.OPT_PCF_LEGACY, 2)
         ref = ctx.pcf(0.1, max_r)["counts"]
     for g in (1, 2, 4):

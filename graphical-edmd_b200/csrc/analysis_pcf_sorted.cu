@@ -1,28 +1,28 @@
-// analysis_pcf_sorted.cu -- K3s: full-range g(r) (calculate_pcf, src/pcf.c:16-75)
-// over spatially sorted tiles, with the bin of a pair CERTIFIED instead of
-// computed by an IEEE square root and division.
+// analysis_pcf_sorted.cu -- K3: full-range g(r) (calculate_pcf, src/pcf.c:16-75) over
+// spatially sorted tiles.  The reference bins  bin = (int)(sqrt(dx^2 + dy^2) / dr)  for all
+// N(N-1)/2 pairs after the minimum-image adjustment (PBC, src/EDMD.c:5896-5913); the integer
+// counts must be the reference's.  Two kernels share the tiles:
 //
-// The reference bins  bin = (int)(sqrt(dx^2 + dy^2) / dr)  for all N(N-1)/2 pairs
-// after the minimum-image adjustment (PBC, src/EDMD.c:5896-5913).  The integer
-// counts must be the reference's.  Per pair this kernel computes only
-//     s = fl(fl(dx*dx) + fl(dy*dy))          exactly as the reference (unfused FP64)
-// and then
-//   * range test in s-space: r < max_r  <=>  s < S_max, with S_max the smallest
-//     double whose correctly rounded square root reaches max_r (found on the host);
-//   * an FP32 estimate k of the bin (float taken from the bits of s, MUFU rsqrt);
-//   * the certificate  (k dr)^2 (1 + 2^-48) <= s < ((k+1) dr)^2 (1 - 2^-48)  in FP64
-//     (5 multiplications, 2 additions, 2 compares): the two roundings of
-//     sqrt-then-divide move r/dr by at most 2^-52 relative, so inside that
-//     interval the reference's truncation gives k.  A pair that fails (the FP32
-//     estimate was off by one -- ~0.1-0.5 % of the pairs -- or s sits within
-//     2^-48 of an edge) takes the reference's sqrt and division.
-// 14 FP64 operations per pair instead of ~35.
+//   k_pcf_f32     (default, second half of this file) decides the bin of a pair in packed FP32
+//                 under a rigorous error bound and redoes the ~0.4 % of pairs FP32 cannot settle
+//                 with the reference's own FP64 operations; ~10 instructions per pair.
+//   k_pcf_sorted  (EDMD_OPT_PCF_LEGACY = 2; very fine bins) computes per pair only
+//                     s = fl(fl(dx*dx) + fl(dy*dy))      exactly as the reference (unfused FP64)
+//                 and then
+//                   * range test in s-space: r < max_r  <=>  s < S_max, with S_max the smallest
+//                     double whose correctly rounded square root reaches max_r (found on the host);
+//                   * an FP32 estimate k of the bin (float taken from the bits of s, MUFU rsqrt);
+//                   * the certificate  (k dr)^2 (1 + 2^-48) <= s < ((k+1) dr)^2 (1 - 2^-48)  in FP64
+//                     (5 multiplications, 2 additions, 2 compares): the two roundings of
+//                     sqrt-then-divide move r/dr by at most 2^-52 relative, so inside that
+//                     interval the reference's truncation gives k.  A pair that fails takes the
+//                     reference's sqrt and division.  14 FP64 operations per pair instead of ~35;
+//                     ~42 instructions per pair.
 //
-// Tiles are 256 consecutive particles of an array sorted by coarse cell
-// (row-major), with exact bounding boxes.  For a tile pair the boxes tell whether
-// any pair can need the periodic image in x / in y (else the adjustment is
-// skipped: identical result) and whether every pair is farther than max_r (the
-// tile pair is skipped: for max_r = L/2 that is ~20 % of them).
+// Tiles are 256 consecutive particles of an array sorted by coarse cell (row-major, alternate
+// rows reversed), with exact bounding boxes.  For a tile pair the boxes tell whether any pair can
+// need the periodic image in x / in y and whether every pair is farther than max_r (the tile pair
+// is skipped: for max_r = L/2 that is ~23 % of them).
 #include "edmd_internal.cuh"
 
 namespace {

@@ -110,11 +110,26 @@ def cpu_baseline(cfg, repeats=3):
         ref.predict_first()
         secs = [ref.repredict()["seconds"] for _ in range(repeats)]
         cal = ref.calendar_only()
+        # the frame analysis of the same snapshot with the reference's own functions:
+        # computeBOOPCutoff over all N; calculate_pcf (single-threaded, all pairs) on the first
+        # n_sub particles -- a bounded sample -- and extrapolated to N(N-1)/2 pairs
+        out = {"value": n / min(secs), "unit": UNIT, "cores": 1, "kind": "reference",
+               "sample": f"{repeats} full re-predict sweeps (reference addNoise loop incl. calendar "
+                         f"remove/insert) of the same N={n} snapshot, best of {repeats}",
+               "seconds_per_sweep": min(secs), "calendar_only_seconds": cal}
+        try:
+            out["psi6_seconds"] = float(ref.boop_cutoff(2.5)["seconds"])
+            out["psi6_particles_per_s"] = n / out["psi6_seconds"]
+            n_sub = min(n, 30000)
+            sec = float(ref.pcf(0.1, min(cfg["lx"], cfg["ly"]) / 2, n_sub)["seconds"])
+            rate = n_sub * (n_sub - 1) / 2 / sec
+            out["gr_sample"] = f"calculate_pcf on the first {n_sub} particles of the snapshot (same box, dr=0.1, max_r=min(L)/2)"
+            out["gr_pairs_per_s"] = rate
+            out["gr_full_seconds_extrapolated"] = n * (n - 1) / 2 / rate
+        except Exception as e:   # the analysis timings are extras of the baseline
+            out["analysis_error"] = str(e)[:200]
         ref.teardown()
-        return {"value": n / min(secs), "unit": UNIT, "cores": 1, "kind": "reference",
-                "sample": f"{repeats} full re-predict sweeps (reference addNoise loop incl. calendar "
-                          f"remove/insert) of the same N={n} snapshot, best of {repeats}",
-                "seconds_per_sweep": min(secs), "calendar_only_seconds": cal}
+        return out
     orc = Oracle()
     secs = []
     for _ in range(repeats):

@@ -48,7 +48,7 @@ SYMBOLS = [
     "edmd_cuda_calendar_plan", "edmd_cuda_pcf_bond_order", "edmd_cuda_bragg_peak",
     "edmd_cuda_boop_voronoi", "edmd_cuda_voronoi_cells", "edmd_cuda_g6_correlation",
     "edmd_cuda_structure_factor", "edmd_cuda_kinetic", "edmd_cuda_rescale_velocities",
-    "edmd_cuda_selftest_rsqrt",
+    "edmd_cuda_selftest_rsqrt", "edmd_cuda_langevin_kick",
 ]
 EVORONOI = 7
 HALO_RECORD_BYTES = 48
@@ -124,6 +124,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
                                             C.POINTER(C.c_int32)]
     lib.edmd_cuda_get_stat.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
     lib.edmd_cuda_selftest_rsqrt.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.edmd_cuda_langevin_kick.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32]
     lib.edmd_cuda_kinetic.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.edmd_cuda_rescale_velocities.argtypes = [vp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.edmd_cuda_boop_voronoi.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -307,6 +308,11 @@ class EdmdCuda:
         out = [np.empty(n, np.float64) for _ in range(5)]
         self._check(self.lib.edmd_cuda_download_state(self._h, *[_ptr(a) for a in out]))
         return dict(zip(("x", "y", "vx", "vy", "rad"), out))
+
+    def langevin_kick(self, T, gamma, dtnoise, seed, tick):
+        """Langevin kick on the resident velocities (edmd_cuda_langevin_kick)."""
+        self._check(self.lib.edmd_cuda_langevin_kick(self._h, float(T), float(gamma), float(dtnoise),
+                                                     int(seed) & 0xFFFFFFFF, int(tick) & 0xFFFFFFFF))
 
     def selftest_rsqrt(self) -> float:
         """Largest relative error of the hardware rsqrt over [2^-100, 2^64) (edmd_cuda_selftest_rsqrt)."""

@@ -1077,6 +1077,19 @@ int edmd_cuda_rescale_velocities(edmd_ctx *c, double T, double *E_before, double
     return 0;
 }
 
+int edmd_cuda_langevin_kick(edmd_ctx *c, double T, double gamma, double dtnoise, uint32_t seed, uint32_t tick)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "langevin_kick before upload");
+    if (!(T >= 0) || !(gamma >= 0) || !(dtnoise >= 0)) return fail(c, EDMD_EINVAL, "T, gamma, dtnoise must be >= 0");
+    CU(cudaSetDevice(c->device));
+    c->launches += edmd_launch_langevin(c, T, gamma, dtnoise, seed, tick);
+    CU(cudaGetLastError());
+    c->have_pred = false;
+    c->have_index = false;   // the cell-ordered records carry velocities
+    return check_flags(c);   // synchronises; refreshes vmax / lean eligibility
+}
+
 // ---- Voronoi family (analysis_voronoi.cu) -----------------------------------
 namespace {
 

@@ -90,7 +90,66 @@ k_rescale(int n, const double *__restrict__ red, double4 *__restrict__ xv, int32
     if ((threadIdx.x & 31) == 0 && vmb) atomicMax(reinterpret_cast<unsigned int *>(&flags[kFlagVmax]), vmb);
 }
 
+// ---- Langevin kick (addNoise with noise == 1: randomGaussian, src/EDMD.c:5802-5826) ----
+// Counter-based uniforms: the generator of graphical-edmd_b200/synth.py (splitmix64 finaliser over
+// (seed, id, stream)), so that numpy reproduces every draw.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ double uniform01(unsigned int seed, unsigned long long id, unsigned long long stream)
+{
+    unsigned long long z = (id + 1ull) * 0x9E3779B97F4A7C15ull;
+    z += (unsigned long long)seed * 0xD1B54A32D192ED03ull;
+    z += (stream + 1ull) * 0x8CB92BA72F3D8DD7ull;
+    z = mix64(mix64(z));
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// non-Euler branch, no damping, unit masses:
+//   c = exp(-gamm*dtnoise); std = sqrt(T*(1 - c*c)/m);
+//   vx = std*a*cos(b) + vx*c;  vy = std*a*sin(b) + vy*c;     a = sqrt(-2 log u1), b = 2 pi u2
+__global__ void __launch_bounds__(kThreads)
+k_langevin(int n, double std, double c, unsigned int seed, unsigned int tick, const int32_t *__restrict__ gid,
+           double4 *__restrict__ xv, int32_t *__restrict__ flags)
+{
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    float vm = 0.0f;
+    if (i < n) {
+        const unsigned long long id = (unsigned long long)(gid ? gid[i] : i);
+        const double u1 = 1.0 - uniform01(seed, id, 2ull * tick);        // (0, 1]: log is finite
+        const double u2 = uniform01(seed, id, 2ull * tick + 1ull);
+        const double a = sqrt(-2.0 * log(u1));
+        const double b = 2.0 * 3.14159265358979323846 * u2;
+        double sb, cb;
+        sincos(b, &sb, &cb);
+        double4 p = xv[i];
+        p.z = std * a * cb + p.z * c;
+        p.w = std * a * sb + p.w * c;
+        xv[i] = p;
+        vm = __double2float_ru(fmax(fabs(p.z), fabs(p.w)));
+        if (!(vm == vm)) vm = __int_as_float(0x7f800000);
+    }
+    const unsigned vmb = __reduce_max_sync(0xffffffffu, (unsigned)__float_as_int(vm));
+    if ((threadIdx.x & 31) == 0 && vmb) atomicMax(reinterpret_cast<unsigned int *>(&flags[kFlagVmax]), vmb);
+}
+
 }  // namespace
+
+int edmd_launch_langevin(edmd_ctx *c, double T, double gamma, double dtnoise, unsigned int seed, unsigned int tick)
+{
+    const int n = c->n_owned;
+    if (n == 0) return 0;
+    const double cc = exp(-gamma * dtnoise);
+    const double std = sqrt(T * (1.0 - cc * cc));
+    cudaMemsetAsync(c->flags + kFlagVmax, 0, sizeof(int32_t), c->stream);
+    k_langevin<<<(n + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(n, std, cc, seed, tick,
+                                                                      c->slab ? c->gid : nullptr, c->xv, c->flags);
+    return 1;
+}
 
 size_t edmd_thermostat_scratch_doubles() { return 3 * (size_t)kBlocks + 8; }
 

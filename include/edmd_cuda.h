@@ -307,6 +307,18 @@ int edmd_cuda_kinetic(edmd_ctx *ctx, double *E, double *px, double *py);
  * freeFly(p) of the same loop, :4893), this call, edmd_cuda_predict_device()
  * (the re-predict loop :4909-4915). */
 int edmd_cuda_rescale_velocities(edmd_ctx *ctx, double T, double *E_before, double *divisor);
+/* Replaces the Langevin branch of addNoise (noise == 1: randomGaussian, src/EDMD.c:5802-5826,
+ * the non-Euler form without damping, unit masses) on the resident velocities:
+ *     c = exp(-gamma dtnoise);  v <- sqrt(T (1 - c^2)) a (cos b, sin b) + c v,
+ * (a, b) the Box-Muller pair of two uniforms per particle.  The reference draws them from its
+ * sequential MT19937 stream (genrand_real3), which a parallel kernel cannot follow; here they come
+ * from a counter-based generator keyed on (seed, tick, particle id) -- the one of
+ * graphical-edmd_b200/synth.py, slab contexts key on the global id -- so a kick is reproducible
+ * and independent of the decomposition.  Parity with the reference is therefore STATISTICAL
+ * (<v^2> -> c^2 <v^2> + (1 - c^2) T per component); against a numpy restatement of the same
+ * generator and formula it is exact to rounding (tests).  Pass a new `tick` at every call. */
+int edmd_cuda_langevin_kick(edmd_ctx *ctx, double T, double gamma, double dtnoise, uint32_t seed,
+                            uint32_t tick);
 
 /* ---- per-frame structure analysis ----------------------------------- */
 

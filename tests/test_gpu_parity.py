@@ -1020,3 +1020,40 @@ def test_rescale_keeps_the_lean_path_and_the_sweep_exact(pkg, oracle):
     assert np.array_equal(s["vx"], c["vx"] * 7.0 / r["divisor"])
     want = oracle.predict_all(c["n"], c["lx"], c["ly"], 1.0, c["x"], c["y"], s["vx"], s["vy"], c["rad"])
     assert_events_equal(got, want)
+
+
+@pytest.mark.parametrize("n,phi,seed,T,gdt", [(200000, 0.70, 181, 1.0, 0.5), (50000, 0.55, 182, 0.25, 3.0)])
+def test_device_langevin_kick(pkg, oracle, n, phi, seed, T, gdt):
+    """edmd_cuda_langevin_kick = the Langevin branch of addNoise (randomGaussian,
+    src/EDMD.c:5802-5826) with a counter-based generator instead of the reference's
+    sequential MT19937.  (1) exact to rounding against the numpy restatement of the same
+    generator (synth.uniform01) and formula; (2) the reference's statistics: per kick
+    <v^2> -> c^2 <v^2> + (1 - c^2) T and no drift; (3) the re-predict sweep on the kicked,
+    resident state is the oracle's on the downloaded state, bit for bit."""
+    c = pkg.synth.lattice_config(n, phi, seed)
+    n = c["n"]
+    vx0, vy0 = 1.7 * c["vx"], 1.7 * c["vy"]            # start hot: T0 = 2.89
+    gamma, dt, tick = 2.0, gdt / 2.0, 7
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], vx0, vy0, c["rad"], t=0.0)
+        e0 = ctx.kinetic()["E"]
+        ctx.langevin_kick(T, gamma, dt, seed, tick)
+        e1 = ctx.kinetic()
+        ctx.predict_device()
+        got = ctx.fetch_predictions()
+        st = ctx.download_state()
+    ids = np.arange(n, dtype=np.int64)
+    u1 = 1.0 - pkg.synth.uniform01(seed, ids, 2 * tick)
+    u2 = pkg.synth.uniform01(seed, ids, 2 * tick + 1)
+    a, b = np.sqrt(-2.0 * np.log(u1)), 2.0 * np.pi * u2
+    cc = np.exp(-gamma * dt)
+    std = np.sqrt(T * (1.0 - cc * cc))
+    wx, wy = std * a * np.cos(b) + vx0 * cc, std * a * np.sin(b) + vy0 * cc
+    assert np.abs(st["vx"] - wx).max() <= 1e-13 and np.abs(st["vy"] - wy).max() <= 1e-13
+    assert np.array_equal(st["x"], c["x"]) and np.array_equal(st["y"], c["y"])
+    want_e = cc * cc * e0 / n + (1.0 - cc * cc) * T          # energy per particle = <vx^2> = T in 2-D, m = 1
+    assert abs(e1["E"] / n - want_e) <= 0.02 * want_e          # 1 / sqrt(n) = 0.2-0.5 %
+    drift = 5.0 * np.sqrt(want_e / n)                          # five standard errors of a mean velocity
+    assert abs(e1["px"]) / n < drift and abs(e1["py"]) / n < drift
+    want = oracle.predict_all(n, c["lx"], c["ly"], 0.0, st["x"], st["y"], st["vx"], st["vy"], c["rad"])
+    assert_events_equal(got, want)

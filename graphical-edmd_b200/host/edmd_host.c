@@ -49,7 +49,8 @@ enum { EV_CELLCROSS = 0, EV_COLLISION = 1, EV_SCREENSHOT = 2, EV_THERMO = 3, EV_
 static int N = 500;
 static double phi = 0.38, sizeratio = 0.4, fractionSmallN = 0.3, aspectRatio = 1.0;
 static double tmax = 4000, dtime = 100, dtimeThermo = 100, firstScreen = 1, firstThermo = 1;
-static double T = 1.0, dtnoise = 0.5;
+static double T = 1.0, dtnoise = 0.5, gamm = 0.02;   /* gamm: the reference's default, src/EDMD.c:382 */
+static unsigned noise_tick = 0;
 static int noise = 0, seed = 1, boopThermo = 0, pcfThermo = 0, verify = 0, quiet = 0;
 /* more of the reference's analysis switches (src/EDMD.c:223-231): areaThermo = Voronoi packing-fraction
  * column, strucThermo = S(q) mode (1 positions, 2.. = 0 velocity as saveStructureFactor's `mode`), pcfg6Thermo */
@@ -546,9 +547,25 @@ static void do_growstop(void)
 	gpu_predict_all(1);
 }
 
-/* thermostat tick = addNoise with noise == 2 (velocity rescale, :4899-4902) */
+/* thermostat tick = addNoise with noise == 2 (velocity rescale, :4899-4902) or noise == 1
+ * (Langevin kick, randomGaussian :5802-5826: done on the device with its counter-based
+ * generator, the new velocities come back for the event loop) */
 static void do_noise(void)
 {
+	if (noise == 1) {
+		for (int i = 0; i < N; i++) {
+			free_fly(i);
+			pcoll[i]++;
+		}
+		gpu_upload();
+		int rc = edmd_cuda_langevin_kick(gpu, T, gamm, dtnoise, (uint32_t)seed, noise_tick++);
+		if (rc) die_gpu(rc, "edmd_cuda_langevin_kick");
+		rc = edmd_cuda_download_state(gpu, NULL, NULL, pvx, pvy, NULL);
+		if (rc) die_gpu(rc, "edmd_cuda_download_state");
+		gpu_predict_all(1);
+		schedule_special(2, EV_NOISE, t + dtnoise);
+		return;
+	}
 	double E = kinetic_energy();
 	double s = sqrt(E / N / T);
 	for (int i = 0; i < N; i++) {
@@ -754,7 +771,7 @@ int main(int argc, char **argv)
 		{"init", required_argument, NULL, 1009}, {"ingest", required_argument, NULL, 1010},
 		{"boop-voronoi", no_argument, NULL, 1011}, {"area", no_argument, NULL, 1012},
 		{"struc", required_argument, NULL, 1013}, {"qmax", required_argument, NULL, 1014},
-		{"pcfg6", no_argument, NULL, 1015},
+		{"pcfg6", no_argument, NULL, 1015}, {"gamma", required_argument, NULL, 1016},
 		{NULL, 0, NULL, 0}};
 	int c, device = 0;
 	while ((c = getopt_long(argc, argv, "N:p:x:q:a:t:D:o:T:v:", longopt, NULL)) != -1) {
@@ -784,12 +801,13 @@ int main(int argc, char **argv)
 		case 1013: strucThermo = atoi(optarg) == 0 ? 2 : 1; break; /* reference: mode 0 = velocity S(q), else positions */
 		case 1014: qmax = atof(optarg); break;
 		case 1015: pcfg6Thermo = 1; break;
+		case 1016: gamm = atof(optarg); break;
 		default: fprintf(stderr, "usage: edmd_host -N n --phi f [-x xs -q ratio -a aspect -t tmax -D dt -o dtThermo -T temp -v seed]\n"
-		                         "       [--init grow|lattice] [--ingest bulk|seq] [--noise 2 --dtnoise dt] [--boop | --boop-voronoi] [--area] [--pcf] [--pcfg6] [--struc mode --qmax q] [--verify] [--outdir dir] [--quiet]\n");
+		                         "       [--init grow|lattice] [--ingest bulk|seq] [--noise 1|2 --dtnoise dt --gamma g] [--boop | --boop-voronoi] [--area] [--pcf] [--pcfg6] [--struc mode --qmax q] [--verify] [--outdir dir] [--quiet]\n");
 			return 2;
 		}
 	}
-	if (noise != 0 && noise != 2) { fprintf(stderr, "edmd_host: only --noise 0 (none) and 2 (velocity rescale) are implemented\n"); return 2; }
+	if (noise != 0 && noise != 1 && noise != 2) { fprintf(stderr, "edmd_host: --noise 0 (none), 1 (Langevin kick, --gamma) and 2 (velocity rescale) are implemented\n"); return 2; }
 	rng_state = 0x1234567ull * (uint64_t)(seed + 1);
 
 	/* the pinned allocator needs the CUDA runtime: touch the library first */

@@ -113,3 +113,17 @@ def test_host_voronoi_area_struc_and_g6_outputs(tmp_path):
     assert r[0] == 1.0 and len(g6) == 1 + frames
     c = np.array(g6[1].split(), float)
     assert len(c) == len(r) and np.abs(c).max() <= 1.0
+
+
+def test_host_langevin_thermostat_reaches_the_bath_temperature(tmp_path):
+    """--noise 1: the Langevin kick of addNoise (randomGaussian, src/EDMD.c:5802-5826) done on the
+    device (edmd_cuda_langevin_kick) every dtnoise; the velocities come back to the host's event
+    loop.  A fluid at the bath temperature T = 0.4 stays there under the kicks (no spurious heating)."""
+    out = run_host(tmp_path, "-N", 3000, "--phi", 0.5, "-x", 0, "-t", 40, "-D", 1000, "-o", 2, "--quiet",
+                   "--init", "lattice", "--noise", 1, "--gamma", 0.5, "--dtnoise", 0.25, "-T", 0.4)
+    th = np.loadtxt(next(tmp_path.glob("*.thermo")), skiprows=1)
+    late = th[th[:, 0] > 15][:, 2]                   # E/N column; exp(-2 gamma t) is gone by t = 15
+    assert len(late) >= 10
+    assert abs(late.mean() - 0.4) < 0.03, late.mean()   # 1/sqrt(N) = 1.8 % per sample
+    m = re.search(r"(\d+) collisions", out)
+    assert m and int(m.group(1)) > 50000

@@ -134,7 +134,10 @@ int check_flags(edmd_ctx *c)
     CU(cudaStreamSynchronize(c->stream));
     c->nghost = f[kFlagGhosts];
     memcpy(&c->vmax, &f[kFlagVmax], sizeof(float));
-    c->lean_ok = f[kFlagNotMono] <= 1 && f[kFlagInsane] == 0 && c->vmax >= 1e-12f && c->vmax <= 1e12f;
+    // radii_dirty: a GROW free flight changed the radii on the device after the radius classes
+    // (kFlagNotMono / kFlagRad1) were derived; only an upload that carries radii re-derives them
+    c->lean_ok = f[kFlagNotMono] <= 1 && f[kFlagInsane] == 0 && c->vmax >= 1e-12f && c->vmax <= 1e12f &&
+                 !c->radii_dirty;
     c->lean_two = f[kFlagNotMono] == 1;
     memcpy(&c->rad1, &f[kFlagRad1], sizeof(double));
     if (f[kFlagBadCell] & 2) {
@@ -270,6 +273,14 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
             if ((r = dev_alloc(c, &c->lwork, (size_t)c->lean_chunks + 8))) return r;
         }
     }
+    // tile sweep: fixed-capacity buckets of 32-byte records, one per tile of the cell grid
+    if (c->rowcap > 0 && c->dbox.nx >= 12 && c->dbox.nl >= 3 && N > 0 &&
+        edmd_tile_geometry(c->dbox.nx, c->dbox.nl, N, &c->tgeom)) {
+        const size_t nt = (size_t)c->tgeom.ntx * c->tgeom.nty;
+        CU(cudaMalloc((void **)&c->trec, (nt * c->tgeom.cap + 32) * 32));
+        if ((r = dev_alloc(c, &c->tcnt, nt * kCntStride + 8))) return r;
+        CU(cudaMemsetAsync(c->tcnt, 0, (nt * kCntStride + 8) * sizeof(int32_t), c->stream));
+    }
     if ((r = dev_alloc(c, &c->t_cross, N))) return r;
     if ((r = dev_alloc(c, &c->t_coll, N))) return r;
     if ((r = dev_alloc(c, &c->partner, N))) return r;
@@ -303,7 +314,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->gid, c->cell_cnt,
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
-                   c->lrec, c->lchunks, c->lres, c->lwork, c->cal_mem,
+                   c->lrec, c->lchunks, c->lres, c->lwork, c->trec, c->tcnt, c->cal_mem,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
                    c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->vor_mem, c->thermo_mem, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
@@ -350,6 +361,10 @@ int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
     if (option == EDMD_OPT_PCF_GROUPS) {
         if (value != 0 && value != 1 && value != 2 && value != 4) return fail(c, EDMD_EINVAL, "groups: 0, 1, 2 or 4");
         c->pcf_groups = value;
+        return 0;
+    }
+    if (option == EDMD_OPT_NO_TILE) {
+        c->tile_off = value != 0;
         return 0;
     }
     if (option == EDMD_OPT_NO_PDL) {
@@ -426,7 +441,10 @@ static int upload_impl(edmd_ctx *c, int n, const double *x, const double *y, con
     // ghosts, insane, vmax, notmono, leanfail; the second radius class
     CU(cudaMemsetAsync(c->flags + kFlagGhosts, 0, 5 * sizeof(int32_t), c->stream));
     CU(cudaMemsetAsync(c->flags + kFlagRad1, 0, 2 * sizeof(int32_t), c->stream));
-    if (!keep_rad) c->rad0 = n > 0 ? rad[0] : 1.0;
+    if (!keep_rad) {
+        c->rad0 = n > 0 ? rad[0] : 1.0;
+        c->radii_dirty = false;
+    }
     c->nghost = 0;
     c->n = n;
     c->n_owned = n;
@@ -628,7 +646,13 @@ static int lean_fallback(edmd_ctx *c);
 static int sweep_launch(edmd_ctx *c, int mode)
 {
     int launched = 0;
-    if (edmd_lean_eligible(c, mode)) {
+    c->index_tile = false;
+    if (edmd_tile_eligible(c, mode)) {
+        launched += edmd_launch_tile_sweep(c, nullptr);
+        c->index_lean = true;
+        c->index_tile = true;
+        c->lean_pending = true;
+    } else if (edmd_lean_eligible(c, mode)) {
         launched += edmd_launch_lean_index(c);
         launched += edmd_launch_predict_lean(c);
         c->index_lean = true;
@@ -662,12 +686,14 @@ int edmd_cuda_predict_device(edmd_ctx *c, int mode)
 // Redo the sweep with the full path then, and stay on it until the next upload.
 static int lean_fallback(edmd_ctx *c)
 {
-    if (!c->index_lean) return 0;
+    // keyed on lean_pending (set by the launch), not on index_lean: an analysis call may have
+    // rebuilt the full index in between without consuming a pending decline
+    if (!c->lean_pending) return 0;
     int32_t f = 0;
     CU(cudaMemcpyAsync(&f, c->flags + kFlagLeanFail, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (!f) {
-        if (c->lean_pending) c->lean_sweeps++;
+        c->lean_sweeps++;
         c->lean_pending = false;
         return 0;
     }
@@ -780,7 +806,10 @@ int edmd_cuda_free_fly(edmd_ctx *c, int mode, double t_new)
     double dt = t_new - c->t;  // `double dt = t - p->t;` src/EDMD.c:4955
     c->launches += edmd_launch_free_fly(c, mode, dt);
     CU(cudaGetLastError());
-    if (mode == EDMD_MODE_GROW) c->lean_ok = false;   // radii changed on the device: no longer known to be equal
+    if (mode == EDMD_MODE_GROW) {   // radii changed on the device: no longer known to be equal
+        c->lean_ok = false;
+        c->radii_dirty = true;      // sticky until an upload with radii (check_flags must not re-enable the lean path)
+    }
     c->t = t_new;
     c->have_pred = false;
     c->have_index = false;
@@ -815,6 +844,8 @@ int edmd_cuda_download_state(edmd_ctx *c, double *x, double *y, double *vx, doub
 
 static int ensure_index(edmd_ctx *c)
 {
+    int r0 = lean_fallback(c);   // a pending decline of the last sweep is resolved before the index is replaced
+    if (r0) return r0;
     if (c->have_index && !c->index_lean) return 0;   // analysis kernels read the full records
     if (c->n == 0) { c->have_index = true; c->index_lean = false; return 0; }
     c->launches += edmd_launch_cell_index(c, EDMD_MODE_NORMAL);
@@ -1060,6 +1091,9 @@ int edmd_cuda_rescale_velocities(edmd_ctx *c, double T, double *E_before, double
 {
     if (!c) return EDMD_EINVAL;
     if (!c->have_state) return fail(c, EDMD_ESTATE, "rescale before upload");
+    // the divisor is sqrt(E/N/T) of the WHOLE system (addNoise, src/EDMD.c:4899): a slab only knows its own sums
+    if (c->slab)
+        return fail(c, EDMD_ESTATE, "slab contexts: all-reduce edmd_cuda_kinetic's sums, then edmd_cuda_shift_scale_velocities");
     if (!(T > 0)) return fail(c, EDMD_EINVAL, "temperature must be positive");
     CU(cudaSetDevice(c->device));
     double *red = nullptr, h[4] = {0, 0, 0, 0};
@@ -1393,7 +1427,12 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
                 c->n = c->n_owned + 2 * c->halo_cap;
                 c->nghost_extra = 2 * c->halo_cap;
             }
-            if (edmd_lean_eligible(c, mode)) {
+            c->index_tile = false;
+            if (edmd_tile_eligible(c, mode)) {
+                c->launches += edmd_launch_tile_sweep(c, e ? e[1] : nullptr);
+                c->index_lean = true;
+                c->index_tile = true;
+            } else if (edmd_lean_eligible(c, mode)) {
                 c->launches += edmd_launch_lean_index(c);
                 if (e) CU(cudaEventRecord(e[1], c->stream));
                 c->launches += edmd_launch_predict_lean(c);

@@ -126,6 +126,20 @@ enum {
     kFlagCount = 16
 };
 
+// ---- tile sweep (tile_sweep.cu): the cell grid cut into tiles of kTX x kTY cells ----------
+constexpr int kTX = 32, kTY = 16;                                // cells per tile
+constexpr int kFW = kTX + 2, kFH = kTY + 2, kFC = kFW * kFH;     // a tile's frame: the tile + a one-cell ring
+constexpr int kTileThreads = 128;
+constexpr int kTileCtas = 8;                                     // per SM (64 registers per thread)
+constexpr int kTileK = 10;                                       // bucket records per thread at most
+constexpr int kCntStride = 32, kCntHalo = 8;                     // one 128-byte line of cursors per tile
+struct TileGeom {
+    int ntx, nty;            // tiles per row of tiles / rows of tiles
+    int wlast, hlast;        // width of the last tile column, height of the last tile row
+    int cap_own, cap_halo;   // bucket capacity: particles of the tile / of its ring
+    int cap;                 // cap_own + cap_halo
+};
+
 struct edmd_ctx {
     int device;
     int n;               // particles currently held (slab: owned + halo)
@@ -147,6 +161,7 @@ struct edmd_ctx {
     bool index_has_vr;   // ... and carries growth rates
     bool index_lean;     // ... but is the LEAN index (lean.cuh): no spos / saux records
     bool lean_ok;        // resident state is eligible for the lean sweep (monodisperse, sane speeds)
+    bool radii_dirty;    // a GROW free flight changed the resident radii since the classes were derived
     bool lean_off;       // EDMD_OPT_NO_LEAN
     bool lean_pdl;       // launch the lean chain with programmatic dependent launch (default on)
     double rad0;         // radius of the first particle = radius class 0 of the lean sweep
@@ -204,6 +219,12 @@ struct edmd_ctx {
     int32_t *lwork;                  // chunk ids that hold particles, any order (kFlagWork entries)
     int4 *lchunks;
     int2 *lres;                      // k_screen -> k_resolve: (winner slot, second bound) per slot
+    // tile sweep (tile_sweep.cu)
+    TileGeom tgeom;
+    struct LeanRec *trec;            // tile buckets: ntx * nty * cap records of 32 bytes
+    int32_t *tcnt;                   // per-tile cursors, kCntStride ints per tile
+    bool tile_off;                   // EDMD_OPT_NO_TILE
+    bool index_tile;                 // the last sweep ran on the tile path (no global cell index exists)
 
     // outputs
     double *t_cross, *t_coll;
@@ -284,6 +305,9 @@ int edmd_launch_calendar_plan(edmd_ctx *c, double paul_time, double dt_paul, int
 int edmd_launch_lean_index(edmd_ctx *c);
 int edmd_launch_predict_lean(edmd_ctx *c);
 bool edmd_lean_eligible(const edmd_ctx *c, int mode);
+bool edmd_tile_eligible(const edmd_ctx *c, int mode);
+bool edmd_tile_geometry(int nx, int nl, size_t n, TileGeom *out);
+int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between);
 int edmd_launch_boop(edmd_ctx *c, double r_c);
 int edmd_launch_mean(edmd_ctx *c, const double *v, int n, double *out_dev);
 int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bins, double kx, double ky,

@@ -90,59 +90,6 @@ struct ScreenArgs {
     int2 *res;
 };
 
-__device__ __forceinline__ LeanConsts make_consts(const edmd_dev_box &b, double rad0, double rad1, bool two,
-                                                   float vmaxf)
-{
-    LeanConsts K;
-    const double V = (double)vmaxf;
-    K.ok = (V >= 1e-12 && V <= 1e12) ? 1 : 0;   // NaN fails too
-    const double u = 5.9604644775390625e-08;    // 2^-24
-    const double cs = fmax(b.csx, b.csy);
-    const double Rm = 1.5 * cs, rho = cs, om = 0.5 * V;
-    // two classes: the class radii, inflated by the class tolerance (every disk of a class is at most
-    // that large: Cc stays an upper bound of 4 r_i r_j); no second class seen: class 1 is empty
-    if (two) {
-        rad1 = (rad1 > 0.0 ? rad1 : rad0) * (1.0 + kRadClassTol);
-        rad0 = rad0 * (1.0 + kRadClassTol);
-    }
-    const double rmax = two ? fmax(rad0, rad1) : rad0;
-    const double s2 = 4.0 * rmax * rmax;        // the error terms take the largest contact distance
-    // two radii: the class bit in the last mantissa bit of vy costs one more ulp per particle
-    const double ed = 8.0 * Rm, ew = (two ? 8.0 : 4.0) * V;   // e_d / u, e_w / u
-    const double kb = 0.7072 * (rho * ew + om * ed) + rho * om;
-    const double kv = 1.4143 * om * ew + 2.0 * om * om;
-    const double kdet = rho * om * kb + (rho * rho + s2) * kv + om * om * (4.0 * rho * rho + s2);
-    const double k4 = 1.5 * u * (1.4143 * ed / rho + 4.0);
-    const double k5 = 1.5 * u * (1.4143 * ed * rho) + 4.0 * u * s2 + 1e-10;
-    K.csx = __double2float_rn(b.csx);
-    K.csy = __double2float_rn(b.csy);
-    K.inv_rho2 = __double2float_rn(1.0 / (rho * rho));
-    K.inv_om2 = __double2float_rn(1.0 / (om * om));
-    K.A = __double2float_rd(1.0 - k4);
-    // 4 r1 r2 of the reference (src/EDMD.c:2700) per pair of classes
-    const double r1 = two ? rad1 : rad0;
-    K.Cc00 = __double2float_ru(4.0 * rad0 * rad0 + k5);
-    K.Cc01 = __double2float_ru(4.0 * rad0 * r1 + k5);
-    K.Cc11 = __double2float_ru(4.0 * r1 * r1 + k5);
-    K.Kb = __double2float_ru(1.5 * u * kb + 1.9073486328125e-06 * rho * om);   // + 2^-19 rho om
-    K.Kdet = __double2float_ru(1.5 * u * kdet);
-    return K;
-}
-
-__device__ __forceinline__ float rsqrt_f32(float x)
-{
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-__device__ __forceinline__ float rcp_f32(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
 __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");

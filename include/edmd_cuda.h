@@ -100,6 +100,9 @@ uint64_t edmd_cuda_launch_count(const edmd_ctx *ctx);
  * that share one shared-memory histogram; 0 (default) lets the library pick the count with the
  * most resident warps, 1 / 2 / 4 force it (cross-checking and timing). */
 #define EDMD_OPT_PCF_GROUPS 5
+/* EDMD_OPT_NO_TILE = 1 keeps eligible sweeps off the two-kernel tile sweep (tile_sweep.cu)
+ * and on the older five-kernel lean chain (cross-checking and timing). */
+#define EDMD_OPT_NO_TILE 6
 int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 /* Counters: EDMD_STAT_EXACT_RESCANS = particles the tiled sweep had to resolve
  * with the exact re-scan (near-ties, ill-conditioned pairs) since create. */

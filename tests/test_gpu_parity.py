@@ -786,6 +786,97 @@ def test_normal_sweep_after_growth_free_flight(pkg, oracle):
     assert_events_equal(got, want)
 
 
+@pytest.mark.parametrize("n,phi,seed,sf,vscale", [(300000, 0.70, 241, 0.0, 1.0), (300000, 0.85, 242, 0.0, 1e-4),
+                                                  (200000, 0.70, 243, 0.3, 1.0), (50000, 0.40, 244, 0.0, 300.0),
+                                                  (2700, 0.70, 245, 0.3, 1.0), (1000000, 0.70, 246, 0.0, 1.0)])
+def test_tile_sweep_equals_lean_chain_and_full_path(pkg, n, phi, seed, sf, vscale):
+    """The two-kernel tile sweep (tile_sweep.cu), the five-kernel lean chain and the full
+    FP64 path produce the same bits (one and two radius classes, tiles narrower than a
+    full tile at the grid edge, grids of a single tile)."""
+    c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf, shuffle=True)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"] * vscale, c["vy"] * vscale, c["rad"], t=1.25)
+        a = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 1
+        a2 = ctx.predict_all()          # the per-tile cursors clean themselves
+        ctx.set_option(pkg.binding.OPT_NO_TILE, 1)
+        b = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 3
+        ctx.set_option(pkg.binding.OPT_NO_LEAN, 1)
+        d = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 3
+    for k in ("t_cross", "dir", "t_coll", "partner", "ctype"):
+        assert np.array_equal(a[k], d[k]), k
+        assert np.array_equal(a2[k], d[k]), k
+        assert np.array_equal(b[k], d[k]), k
+
+
+def test_tile_sweep_declines_when_a_bucket_overflows(pkg, oracle):
+    """All particles of a dilute system crowded into one corner of the box: the bucket of
+    that tile overflows its fixed capacity, the sweep declines on the device and the call
+    re-runs on the full path."""
+    rng = np.random.default_rng(77)
+    lx, ly, n = 400.0, 300.0, 6000
+    side = int(np.ceil(np.sqrt(n)))
+    k = np.arange(n)
+    x = 1.0 + 2.05 * (k % side) + 0.02 * rng.random(n)
+    y = 1.0 + 2.05 * (k // side) + 0.02 * rng.random(n)
+    vx, vy = rng.standard_normal(n), rng.standard_normal(n)
+    c = dict(n=n, lx=lx, ly=ly, x=x, y=y, vx=vx, vy=vy, rad=np.ones(n))
+    with pkg.EdmdCuda(n, lx, ly) as ctx:
+        ctx.upload(x, y, vx, vy, c["rad"], t=0.5)
+        got = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_DECLINES) >= 1
+        got2 = ctx.predict_all()
+    want = oracle_sweep(oracle, c, t=0.5)
+    assert_events_equal(got, want)
+    assert_events_equal(got2, want)
+
+
+def test_rescale_after_growth_free_flight_stays_off_the_lean_path(pkg, oracle):
+    """free_fly(GROW) changes the radii on the device; a velocity rescale afterwards
+    refreshes the lean facts from flags that predate the growth -- it must not put the
+    sweep back on the equal-radii path (the device-resident stopGrow tick)."""
+    c = pkg.synth.lattice_config(30000, 0.55, seed=148)
+    rng = np.random.default_rng(148)
+    vr = 0.02 * rng.random(c["n"])
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        ctx.set_growth(vr)
+        ctx.free_fly(0.125, mode=1)
+        ctx.rescale_velocities(1.0)
+        s = ctx.download_state()
+        cells = oracle.cells(c["n"], c["lx"], c["ly"], c["x"], c["y"]).reshape(c["n"], 2)
+        got = ctx.predict_all(allow_overlap=True)
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 0
+        # an upload that carries radii re-derives the classes: eligible again
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 1
+    c2 = dict(c, x=s["x"], y=s["y"], vx=s["vx"], vy=s["vy"], rad=s["rad"])
+    want = oracle_sweep(oracle, c2, t=0.125, cells=cells)
+    assert_events_equal(got, want)
+
+
+def test_analysis_between_a_declined_lean_sweep_and_its_fetch(pkg, oracle):
+    """predict_device on the lean path that declines on the device, then an analysis call
+    (which rebuilds the full index), then the fetch: the pending decline must still be
+    resolved -- no stale predictions with return code 0."""
+    c = pkg.synth.lattice_config(20000, 0.30, seed=147)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        ctx.free_fly(1.5)
+        s = ctx.download_state()
+        cells = oracle.cells(c["n"], c["lx"], c["ly"], c["x"], c["y"]).reshape(c["n"], 2)
+        ctx.predict_device()
+        ctx.boop_cutoff(2.5)
+        got = ctx.fetch_predictions(allow_overlap=True)
+        assert ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 0
+    c2 = dict(c, x=s["x"], y=s["y"])
+    want = oracle_sweep(oracle, c2, t=1.5, cells=cells)
+    assert_events_equal(got, want)
+
+
 def test_lean_declines_after_free_flight_out_of_the_cells(pkg, oracle):
     """Free flight moves particles but not their (host-owned) cells; once some
     particle is more than a cell away from where it is filed the lean sweep

@@ -273,19 +273,24 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
             if ((r = dev_alloc(c, &c->lwork, (size_t)c->lean_chunks + 8))) return r;
         }
     }
-    // tile sweep: fixed-capacity buckets of 32-byte records, one per tile of the cell grid
+    // tile sweep: one bucket per tile of the cell grid = kFH runs (frame rows) of kRunCap records (32-byte FP64
+    // state + 16-byte tag), one cursor per run in its own 32-byte sector; one 32-byte event record per particle
     if (c->rowcap > 0 && c->dbox.nx >= 12 && c->dbox.nl >= 3 && N > 0 &&
         edmd_tile_geometry(c->dbox.nx, c->dbox.nl, N, &c->tgeom)) {
-        const size_t nt = (size_t)c->tgeom.ntx * c->tgeom.nty;
-        CU(cudaMalloc((void **)&c->trec, (nt * c->tgeom.cap + 32) * 32));
-        if ((r = dev_alloc(c, &c->tcnt, nt * kCntStride + 8))) return r;
-        CU(cudaMemsetAsync(c->tcnt, 0, (nt * kCntStride + 8) * sizeof(int32_t), c->stream));
+        const size_t runs = (size_t)c->tgeom.ntx * c->tgeom.nty * kFH;
+        if ((r = dev_alloc(c, &c->tst, runs * kRunCap + 32))) return r;
+        if ((r = dev_alloc(c, &c->ttag, runs * kRunCap + 32))) return r;
+        if ((r = dev_alloc(c, &c->trad, runs * kRunCap + 32))) return r;
+        if ((r = dev_alloc(c, &c->tcnt, runs * kCurStride + 8))) return r;
+        if ((r = dev_alloc(c, &c->evrec, N + 32))) return r;
+        CU(cudaMemsetAsync(c->tcnt, 0, (runs * kCurStride + 8) * sizeof(int32_t), c->stream));
     }
     if ((r = dev_alloc(c, &c->t_cross, N))) return r;
     if ((r = dev_alloc(c, &c->t_coll, N))) return r;
     if ((r = dev_alloc(c, &c->partner, N))) return r;
     if ((r = dev_alloc(c, &c->dir, N))) return r;
     if ((r = dev_alloc(c, &c->ctype, N))) return r;
+    CU(cudaMemsetAsync(c->ctype, EDMD_EV_COLLISION, N ? N : 1, c->stream));   // the constant COLLISION (src/EDMD.h:19-34)
     if ((r = dev_alloc(c, &c->overlap_key, 1))) return r;
     if ((r = dev_alloc(c, &c->flags, kFlagCount))) return r;
     CU(cudaMemsetAsync(c->flags, 0, kFlagCount * sizeof(int32_t), c->stream));
@@ -314,7 +319,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->gid, c->cell_cnt,
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
-                   c->lrec, c->lchunks, c->lres, c->lwork, c->trec, c->tcnt, c->cal_mem,
+                   c->lrec, c->lchunks, c->lres, c->lwork, c->tst, c->ttag, c->trad, c->tcnt, c->evrec, c->cal_mem,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
                    c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->vor_mem, c->thermo_mem, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
@@ -365,6 +370,10 @@ int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
     }
     if (option == EDMD_OPT_NO_TILE) {
         c->tile_off = value != 0;
+        return 0;
+    }
+    if (option == 100) {   // internal: timing experiments
+        c->tile_dbg = value;
         return 0;
     }
     if (option == EDMD_OPT_NO_PDL) {
@@ -647,6 +656,7 @@ static int sweep_launch(edmd_ctx *c, int mode)
 {
     int launched = 0;
     c->index_tile = false;
+    c->pred_packed = false;
     if (edmd_tile_eligible(c, mode)) {
         launched += edmd_launch_tile_sweep(c, nullptr);
         c->index_lean = true;
@@ -709,6 +719,16 @@ static int lean_fallback(edmd_ctx *c)
     return 0;
 }
 
+// the tile sweep leaves one event record per particle; the ABI's arrays are filled on demand
+static int ensure_unpacked(edmd_ctx *c)
+{
+    if (!c->pred_packed) return 0;
+    c->launches += edmd_launch_unpack_events(c);
+    CU(cudaGetLastError());
+    c->pred_packed = false;
+    return 0;
+}
+
 int edmd_cuda_fetch_predictions(edmd_ctx *c, double *t_cross, uint8_t *dir, double *t_coll,
                                 int32_t *partner, uint8_t *ctype, int32_t *overlap_pair)
 {
@@ -718,6 +738,7 @@ int edmd_cuda_fetch_predictions(edmd_ctx *c, double *t_cross, uint8_t *dir, doub
     size_t N = (size_t)c->n_owned;
     int r;
     if ((r = lean_fallback(c))) return r;
+    if ((r = ensure_unpacked(c))) return r;
     if (t_cross && (r = d2h(c, t_cross, c->t_cross, N * sizeof(double)))) return r;
     if (t_coll && (r = d2h(c, t_coll, c->t_coll, N * sizeof(double)))) return r;
     if (partner && (r = d2h(c, partner, c->partner, N * sizeof(int32_t)))) return r;
@@ -762,6 +783,7 @@ int edmd_cuda_calendar_plan(edmd_ctx *c, double paul_time, double dt_paul, int p
     CU(cudaSetDevice(c->device));
     int r;
     if ((r = lean_fallback(c))) return r;   // the predictions must be final
+    if ((r = ensure_unpacked(c))) return r;
     const size_t e2 = 2 * (size_t)c->n_owned, pn1 = (size_t)paul_n + 1;
     const size_t nsum = (e2 > pn1 ? e2 : pn1) / 1024 + 2;
     const size_t scratch = 4 * e2 + 3 * pn1 + nsum + 8;
@@ -1419,7 +1441,9 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
         if (e) CU(cudaEventRecord(e[0], c->stream));
         switch (what) {
         case EDMD_BENCH_SWEEP:
-            CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));
+            // (the tile sweep's first kernel resets the overlap report itself)
+            if (!edmd_tile_eligible(c, mode))
+                CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));
             if (c->slab && c->peer_mem[0] && c->peer_mem[1]) {
                 // multi-GPU step: the halo exchange (peer stores over NVLink) is part of it;
                 // every rank runs the same number of iterations, epochs advance in lockstep
@@ -1428,6 +1452,7 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
                 c->nghost_extra = 2 * c->halo_cap;
             }
             c->index_tile = false;
+            c->pred_packed = false;
             if (edmd_tile_eligible(c, mode)) {
                 c->launches += edmd_launch_tile_sweep(c, e ? e[1] : nullptr);
                 c->index_lean = true;

@@ -129,15 +129,16 @@ enum {
 // ---- tile sweep (tile_sweep.cu): the cell grid cut into tiles of kTX x kTY cells ----------
 constexpr int kTX = 32, kTY = 16;                                // cells per tile
 constexpr int kFW = kTX + 2, kFH = kTY + 2, kFC = kFW * kFH;     // a tile's frame: the tile + a one-cell ring
-constexpr int kTileThreads = 128;
-constexpr int kTileCtas = 8;                                     // per SM (64 registers per thread)
-constexpr int kTileK = 10;                                       // bucket records per thread at most
-constexpr int kCntStride = 32, kCntHalo = 8;                     // one 128-byte line of cursors per tile
+constexpr int kTileThreads = 192;
+constexpr int kTileWarps = kTileThreads / 32;
+constexpr int kTileCtas = 4;                                     // per SM (64 registers per thread)
+constexpr int kRunCap = 96;                                      // records per RUN = one frame row of one tile
+constexpr int kRunsPerWarp = (kFH + kTileWarps - 1) / kTileWarps;
+constexpr int kCurStride = 8;                                    // ints between cursors: one 32-byte sector each
 struct TileGeom {
     int ntx, nty;            // tiles per row of tiles / rows of tiles
     int wlast, hlast;        // width of the last tile column, height of the last tile row
-    int cap_own, cap_halo;   // bucket capacity: particles of the tile / of its ring
-    int cap;                 // cap_own + cap_halo
+    int smem_cap;            // records one CTA can bin (its shared memory is sized for this)
 };
 
 struct edmd_ctx {
@@ -221,9 +222,14 @@ struct edmd_ctx {
     int2 *lres;                      // k_screen -> k_resolve: (winner slot, second bound) per slot
     // tile sweep (tile_sweep.cu)
     TileGeom tgeom;
-    struct LeanRec *trec;            // tile buckets: ntx * nty * cap records of 32 bytes
-    int32_t *tcnt;                   // per-tile cursors, kCntStride ints per tile
+    double4 *tst;                    // tile buckets: ntx * nty tiles x kFH runs x kRunCap FP64 states (32 bytes each)
+    int2 *ttag;                      // ... their 8-byte tags (id, frame cell)
+    double *trad;                    // ... and radii (written only when the radii are not all exactly rad0)
+    int32_t *tcnt;                   // one cursor per run, kCurStride ints apart
+    edmd_ev32 *evrec;                 // event records of the last tile sweep, by particle id
+    bool pred_packed;                // the predictions of the last sweep are in ev[], not yet in the five arrays
     bool tile_off;                   // EDMD_OPT_NO_TILE
+    int tile_dbg;                    // timing experiments (internal option 100): skip parts of k_tile_sweep
     bool index_tile;                 // the last sweep ran on the tile path (no global cell index exists)
 
     // outputs
@@ -308,6 +314,7 @@ bool edmd_lean_eligible(const edmd_ctx *c, int mode);
 bool edmd_tile_eligible(const edmd_ctx *c, int mode);
 bool edmd_tile_geometry(int nx, int nl, size_t n, TileGeom *out);
 int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between);
+int edmd_launch_unpack_events(edmd_ctx *c);
 int edmd_launch_boop(edmd_ctx *c, double r_c);
 int edmd_launch_mean(edmd_ctx *c, const double *v, int n, double *out_dev);
 int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bins, double kx, double ky,

@@ -11,24 +11,31 @@
 // src/EDMD.c:2110-2124: the ring of an edge tile is the opposite edge of the grid).
 //
 //   P1  k_tile_partition   one thread per particle (memory order = particle id):
-//       the particle's 32-byte record -- FP32 screening half relative to the centre
-//       of the cell it is filed under, particle id, cell inside the destination
-//       frame -- is appended to the bucket of its tile, and, when it sits in an
-//       edge cell of the tile, to the halo region of the neighbouring tiles'
-//       buckets (13 % of the particles once, 0.4 % three times).  One returning
-//       atomic per append on a per-tile cursor (one 128-byte line per tile: the
-//       cursors of ~2000 tiles stay hot in L2, unlike a per-cell histogram), one
-//       full-sector 256-bit store per record.  No histogram pass, no scan, no
-//       work list.
+//       the particle's record -- its FP64 state (x, y, vx, vy: one 32-byte sector, one
+//       256-bit store) and a 16-byte tag (radius, particle id, cell inside the
+//       destination frame) -- is appended to the bucket of its tile, and, when it sits in an
+//       edge cell of the tile, to the buckets of the neighbouring tiles whose ring
+//       holds that cell (19 % of the particles once, 0.6 % three times).  A bucket
+//       is kFH RUNS, one per frame row, each with its own cursor in its own 32-byte
+//       sector: one returning atomic per append, ~30 appends per cursor per sweep
+//       (measured: ONE cursor per tile serialises its ~460 atomics at ~60 ns each,
+//       31 us for the kernel).  No histogram pass, no scan, no work list.
 //   P2  k_tile_sweep       one CTA per tile: the bucket (contiguous, coalesced) is
-//       binned by frame cell IN SHARED MEMORY (count -> scan -> place), then every
-//       particle of the tile, in cell order, screens its 3 x 3 neighbourhood in
-//       FP32 out of shared memory (the certified lower bounds of lean.cuh /
-//       predict_lean.cu: same arithmetic, same error model), gathers the winner's
-//       FP64 state by particle id, evaluates crossingEventNormal and the winner's
-//       collisionTimeNormal exactly as the reference does, certifies the winner
-//       against the second-smallest bound or re-scans the neighbourhood in FP64
-//       in the reference's order, and writes the five outputs by particle id.
+//       binned by frame cell IN SHARED MEMORY (count -> scan -> place: FP64 state,
+//       the FP32 screening record derived from it, id), then every particle of the
+//       tile, in cell order, screens its 3 x 3 neighbourhood in FP32 (the certified
+//       lower bounds of lean.cuh / predict_lean.cu: same arithmetic, same error
+//       model), evaluates crossingEventNormal and the winner's collisionTimeNormal
+//       exactly as the reference does from the FP64 states in shared memory,
+//       certifies the winner against the second-smallest bound or re-scans the
+//       neighbourhood in FP64 in the reference's order, and writes ONE 32-byte event
+//       record per particle (edmd_ev32: both event times, partner, direction) by
+//       particle id -- the only access of the kernel that is not contiguous.
+//       Measured on B200 (profiles/r2b_tile_phases.log): a random 32-byte gather or a
+//       scattered partial-sector store costs ~12 us per million, more than the whole
+//       screening arithmetic; hence the FP64 state travels with the record and the
+//       outputs leave as one full sector.  k_unpack_events turns the records into
+//       the ABI's five arrays when a caller fetches them.
 //
 // Everything the old five-kernel chain kept in global memory between kernels
 // (histogram, offsets, chunk plans, work list, cell-ordered records, per-particle
@@ -45,7 +52,7 @@ namespace {
 constexpr int kPartThreads = 256;
 
 struct PartArgs {
-    int first, n, ps, slab;
+    int first, n, ps, slab, dbg;
     TileGeom tg;
     edmd_dev_box b;
     const int32_t *cid;
@@ -54,77 +61,95 @@ struct PartArgs {
     double rad0;
     int32_t *flags;
     int32_t *tcnt;
-    LeanRec *trec;
+    double4 *tst;
+    int2 *ttag;
+    double *trad;
+    unsigned long long *overlap_key;
 };
-
-// one full 32-byte sector with a single 256-bit store
-__device__ __forceinline__ void put_rec(LeanRec *dst, const float4 &r, int id, int lcell)
-{
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst),
-                 "r"(__float_as_int(r.x)), "r"(__float_as_int(r.y)), "r"(__float_as_int(r.z)),
-                 "r"(__float_as_int(r.w)), "r"(id), "r"(lcell), "r"(0), "r"(0)
-                 : "memory");
-}
 
 __global__ void __launch_bounds__(kPartThreads)
 k_tile_partition(const __grid_constant__ PartArgs a)
 {
     const int i = a.first + blockIdx.x * blockDim.x + threadIdx.x;
     edmd_pdl_wait();
+    if (i == a.first) *a.overlap_key = ~0ull;   // the sweep's overlap report starts empty
     if (i >= a.first + a.n) return;
     const int pc = a.cid[i];
     const double4 p = ld_sector(a.xv + i);
     if (pc < 0) return;   // unused halo slot of a slab context
-    const bool two = a.flags[kFlagNotMono] == 1;
+    // radii matter only when they are not all exactly rad0 (two classes / spread inside a class)
+    const bool radii = a.flags[kFlagNotMono] != 0;
+    const double rad = radii ? a.rad[i] : a.rad0;
     const TileGeom &tg = a.tg;
     const int Yl = pc / a.ps;
     const int X = pc - Yl * a.ps - 1;
     const int tx = X / kTX, ty = Yl / kTY;
     const int lx = X - tx * kTX, ly = Yl - ty * kTY;
     const int w = tx == tg.ntx - 1 ? tg.wlast : kTX, h = ty == tg.nty - 1 ? tg.hlast : kTY;
-    // screening record, relative to the centre of the FILED cell (lean.cuh)
-    float4 r;
-    r.x = __double2float_rn(__dsub_rn(p.x, __dmul_rn((double)X + 0.5, a.b.csx)));
-    r.y = __double2float_rn(__dsub_rn(p.y, __dmul_rn((double)edmd_global_row(a.b, Yl) + 0.5, a.b.csy)));
-    r.z = __double2float_rn(p.z);
-    r.w = __double2float_rn(p.w);
-    if (two) r.w = __int_as_float((__float_as_int(r.w) & ~1) | (edmd_same_class(a.rad[i], a.rad0) ? 0 : 1));
-    bool fail = false;
-    {
-        const int t = ty * tg.ntx + tx;
-        const int k = atomicAdd(&a.tcnt[(size_t)t * kCntStride], 1);
-        if (k < tg.cap_own) put_rec(a.trec + (size_t)t * tg.cap + k, r, i, (ly + 1) * kFW + lx + 1);
-        else fail = true;
-    }
-    // edge cells also belong to the frames of the neighbouring tiles (periodic: the
-    // neighbour of the last tile column is the first; a tile one cell wide feeds both sides)
+    // Destinations: the particle's own tile, and -- for a particle in an edge cell of its tile --
+    // the neighbouring tiles whose ring holds that cell (periodic: the neighbour of the last tile
+    // column is the first).  run = tile * kFH + frame row, cell = frame row * kFW + frame column.
+    // All cursors are bumped before the first store: ONE atomic round trip per particle.
+    int run[4], cell[4];
+    run[0] = (ty * tg.ntx + tx) * kFH + ly + 1;
+    cell[0] = (ly + 1) * kFW + lx + 1;
+    run[1] = run[2] = run[3] = -1;
     const bool ex0 = lx == 0, ex1 = lx == w - 1, ey0 = ly == 0, ey1 = ly == h - 1;
-    if (ex0 || ex1 || ey0 || ey1) {
+    const bool degenerate = (ex0 && ex1) || (ey0 && ey1);   // a tile one cell wide / high feeds both sides
+    auto target = [&](int sx, int sy, int &r, int &c) {
+        int tx2 = tx + sx, ty2 = ty + sy;
+        if (tx2 < 0) tx2 = tg.ntx - 1;
+        if (tx2 >= tg.ntx) tx2 = 0;
+        r = -1;
+        if (ty2 < 0 || ty2 >= tg.nty) {
+            if (a.slab) return;   // a slab's rows are not periodic: rows 0 and nl-1 ARE the halo
+            ty2 = ty2 < 0 ? tg.nty - 1 : 0;
+        }
+        const int w2 = tx2 == tg.ntx - 1 ? tg.wlast : kTX, h2 = ty2 == tg.nty - 1 ? tg.hlast : kTY;
+        const int fx = sx < 0 ? w2 + 1 : (sx > 0 ? 0 : lx + 1);
+        const int fy = sy < 0 ? h2 + 1 : (sy > 0 ? 0 : ly + 1);
+        r = (ty2 * tg.ntx + tx2) * kFH + fy;
+        c = fy * kFW + fx;
+    };
+    if (!degenerate) {
+        const int sx = ex0 ? -1 : 1, sy = ey0 ? -1 : 1;
+        if (ex0 || ex1) target(sx, 0, run[1], cell[1]);
+        if (ey0 || ey1) target(0, sy, run[2], cell[2]);
+        if ((ex0 || ex1) && (ey0 || ey1)) target(sx, sy, run[3], cell[3]);
+    }
+    int k[4];
 #pragma unroll
-        for (int sy = -1; sy <= 1; sy++) {
+    for (int d = 0; d < 4; d++)
+        k[d] = run[d] >= 0 ? ((a.dbg & 16) ? (i & 31) : atomicAdd(&a.tcnt[(size_t)run[d] * kCurStride], 1)) : 0;
+    auto put = [&](int rr, int kk, int cc) {
+        const size_t slot = (size_t)rr * kRunCap + kk;
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(a.tst + slot), "d"(p.x), "d"(p.y), "d"(p.z), "d"(p.w)
+                     : "memory");
+        a.ttag[slot] = make_int2(i, cc);
+        if (radii) a.trad[slot] = rad;
+    };
+    bool ok = true;
 #pragma unroll
+    for (int d = 0; d < 4; d++) {
+        if (run[d] < 0) continue;
+        if (a.dbg & 8) { ok &= k[d] != 12345; continue; }
+        if (k[d] < kRunCap) put(run[d], k[d], cell[d]);
+        else ok = false;
+    }
+    if (degenerate) {   // rare: the last tile column / row of the grid is one cell wide / high
+        for (int sy = -1; sy <= 1; sy++)
             for (int sx = -1; sx <= 1; sx++) {
                 if (sx == 0 && sy == 0) continue;
-                const bool need = (sx < 0 ? ex0 : (sx > 0 ? ex1 : true)) && (sy < 0 ? ey0 : (sy > 0 ? ey1 : true));
-                if (!need) continue;
-                int tx2 = tx + sx, ty2 = ty + sy;
-                if (tx2 < 0) tx2 = tg.ntx - 1;
-                if (tx2 >= tg.ntx) tx2 = 0;
-                if (ty2 < 0 || ty2 >= tg.nty) {
-                    if (a.slab) continue;   // a slab's rows are not periodic: rows 0 and nl-1 ARE the halo
-                    ty2 = ty2 < 0 ? tg.nty - 1 : 0;
-                }
-                const int w2 = tx2 == tg.ntx - 1 ? tg.wlast : kTX, h2 = ty2 == tg.nty - 1 ? tg.hlast : kTY;
-                const int fx = sx < 0 ? w2 + 1 : (sx > 0 ? 0 : lx + 1);
-                const int fy = sy < 0 ? h2 + 1 : (sy > 0 ? 0 : ly + 1);
-                const int t2 = ty2 * tg.ntx + tx2;
-                const int k = atomicAdd(&a.tcnt[(size_t)t2 * kCntStride + kCntHalo], 1);
-                if (k < tg.cap_halo) put_rec(a.trec + (size_t)t2 * tg.cap + tg.cap_own + k, r, i, fy * kFW + fx);
-                else fail = true;
+                if (!((sx < 0 ? ex0 : (sx > 0 ? ex1 : true)) && (sy < 0 ? ey0 : (sy > 0 ? ey1 : true)))) continue;
+                int rr, cc;
+                target(sx, sy, rr, cc);
+                if (rr < 0) continue;
+                const int kk = atomicAdd(&a.tcnt[(size_t)rr * kCurStride], 1);
+                if (kk < kRunCap) put(rr, kk, cc);
+                else ok = false;
             }
-        }
     }
-    if (fail) atomicOr(&a.flags[kFlagLeanFail], 1);   // a bucket is full: the sweep declines
+    if (!ok) atomicOr(&a.flags[kFlagLeanFail], 1);   // a run is full: the sweep declines
 }
 
 // ---- P2 ---------------------------------------------------------------------------
@@ -132,66 +157,133 @@ struct SweepArgs {
     TileGeom tg;
     edmd_dev_box b;
     double t, rad0;
-    int n_owned;
+    int n_owned, dbg, rad_smem;
     const int32_t *tiles;   // tile list (nullptr: blockIdx.x is the tile)
-    const double4 *xv;
-    const double *rad;
     const int32_t *gid;
     int32_t *flags;
     int32_t *tcnt;
-    const LeanRec *trec;
-    double *t_cross;
-    uint8_t *dir;
-    double *t_coll;
-    int32_t *partner;
-    uint8_t *ctype;
+    const double4 *tst;
+    const int2 *ttag;
+    const double *trad;
+    edmd_ev32 *ev;
     unsigned long long *overlap_key;
 };
 
-__device__ __forceinline__ int gid_of(const SweepArgs &a, int id) { return a.gid ? a.gid[id] : id; }
-
-// shared memory of one CTA: [scr float4 x cap][id int x cap][lc u16 x cap (padded)][off int x kFC+1 ...]
+// Shared memory of one CTA (cap = tg.smem_cap records):
+//   xy   double2[cap]  FP64 positions in cell order   (two 16-byte arrays instead of one 32-byte
+//   vv   double2[cap]  FP64 velocities in cell order   record: 128-bit accesses stay conflict-free)
+//   scr  float4[cap]   screening records in cell order
+//   pk   uint2[kFC]    per frame cell c: off[c-1], off[c], off[c+1], off[c+2] as 4 x u16
+//   rad  double[cap]   radii in cell order (only when the radii are not all exactly rad0)
+//   id   int[cap]      particle ids in cell order (global ids in a slab context)
+//   off  int[kFC + 1]  cell counters, then their exclusive scan; dead once pk is built, and
+//   own  uint[cap]     ALIASES off: k-th owned particle in cell order -> position | frame cell << 16
+//   misc                warp sums, run counts, the screening constants
 struct TileSmem {
+    double2 *xy, *vv;
     float4 *scr;
+    uint2 *pk;
+    double *rad;
     int *id;
-    unsigned short *lc;
     int *off;
-    int *rowpre;   // [kTY + 1] owned particles before frame row y+1
-    int *misc;     // [0..3] warp sums, [4] n_own, [5] n_halo
+    unsigned int *own;
+    int *wsum;   // [kTileWarps]
+    int *cnt;    // [kFH] records per run, [kFH] = owned total, [kFH + 1] = records
+    LeanConsts *K;
 };
 
-__device__ __forceinline__ TileSmem carve(unsigned char *base, int cap)
+__host__ __device__ inline size_t tile_aliased_bytes(int cap)
+{
+    const size_t a = (size_t)cap * 4, b = sizeof(int) * (kFC + 4);
+    return ((a > b ? a : b) + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ TileSmem carve(unsigned char *base, int cap, int rad_smem)
 {
     TileSmem s;
+    s.xy = reinterpret_cast<double2 *>(base);
+    base += (size_t)cap * 16;
+    s.vv = reinterpret_cast<double2 *>(base);
+    base += (size_t)cap * 16;
     s.scr = reinterpret_cast<float4 *>(base);
-    s.id = reinterpret_cast<int *>(base + (size_t)cap * 16);
-    s.lc = reinterpret_cast<unsigned short *>(base + (size_t)cap * 20);
-    s.off = reinterpret_cast<int *>(base + (size_t)cap * 22 + ((cap & 1) ? 2 : 0));
-    s.rowpre = s.off + kFC + 4;
-    s.misc = s.rowpre + kTY + 4;
+    base += (size_t)cap * 16;
+    s.pk = reinterpret_cast<uint2 *>(base);
+    base += sizeof(uint2) * kFC;
+    s.rad = reinterpret_cast<double *>(base);
+    base += rad_smem ? (size_t)cap * 8 : 0;
+    s.id = reinterpret_cast<int *>(base);
+    base += (size_t)cap * 4;
+    s.off = reinterpret_cast<int *>(base);
+    s.own = reinterpret_cast<unsigned int *>(base);
+    base += tile_aliased_bytes(cap);
+    s.wsum = reinterpret_cast<int *>(base);
+    s.cnt = s.wsum + kTileWarps;
+    s.K = reinterpret_cast<LeanConsts *>(s.cnt + kFH + 4);
     return s;
 }
 
+struct Held {
+    double4 st;
+    double rad;
+    int id, key;   // key = frame cell | rank << 16, -1: none
+};
+
+__device__ __forceinline__ void st_ev(edmd_ev32 *dst, double t_cross, double t_coll, int partner, int dir)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst),
+                 "r"(__double2loint(t_cross)), "r"(__double2hiint(t_cross)), "r"(__double2loint(t_coll)),
+                 "r"(__double2hiint(t_coll)), "r"(partner), "r"(dir | (EDMD_EV_COLLISION << 8)), "r"(0), "r"(0)
+                 : "memory");
+}
+
 template <bool TWO>
-__device__ __forceinline__ void tile_main(const SweepArgs &a, const LeanConsts &K, const TileSmem &s, int tile,
-                                          int n_own, int n_halo)
+__device__ __forceinline__ void tile_main(const SweepArgs &a, const TileSmem &s, int tile, const bool radii)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileGeom &tg = a.tg;
-    const LeanRec *bucket = a.trec + (size_t)tile * tg.cap;
-    const int R = n_own + n_halo;
+    const size_t slot0 = (size_t)tile * kFH * kRunCap;
+    const double4 *bst = a.tst + slot0;
+    const int2 *btag = a.ttag + slot0;
+    const double *brad = a.trad + slot0;
+    const int tyi = tile / tg.ntx, txi = tile - tyi * tg.ntx;
+    const int tw = txi == tg.ntx - 1 ? tg.wlast : kTX, th = tyi == tg.nty - 1 ? tg.hlast : kTY;
 
-    // ---- count: rank of every record inside its frame cell (shared-memory atomics) ----
-    int keep[kTileK];   // frame cell | rank << 16
+    // ---- count: rank of every record inside its frame cell (shared-memory atomics).  Warp w takes
+    // the runs (frame rows) w, w + kTileWarps, ...; all loads go out before the first atomic --------
+    Held held[kRunsPerWarp];
+    int key2[kRunsPerWarp][2];   // records 32.. of a run longer than 32 (dense systems only)
+    {
+        int2 tg2[kRunsPerWarp];
 #pragma unroll
-    for (int k = 0; k < kTileK; k++) {
-        const int r = tid + k * kTileThreads;
-        keep[k] = -1;
-        if (r < R) {
-            const int src = r < n_own ? r : tg.cap_own + (r - n_own);
-            int lc = bucket[src].pc;
-            lc = min(max(lc, 0), kFC - 1);
-            keep[k] = lc | (atomicAdd(&s.off[lc], 1) << 16);
+        for (int q = 0; q < kRunsPerWarp; q++) {
+            const int fy = warp + kTileWarps * q;
+            const int n = fy < kFH ? s.cnt[fy] : 0;
+            tg2[q] = make_int2(0, 0);
+            held[q].st = make_double4(0, 0, 0, 0);
+            held[q].rad = a.rad0;
+            if (lane < n) {
+                tg2[q] = btag[fy * kRunCap + lane];
+                held[q].st = ld_sector(bst + fy * kRunCap + lane);
+                if (radii) held[q].rad = brad[fy * kRunCap + lane];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kRunsPerWarp; q++) {
+            const int fy = warp + kTileWarps * q;
+            const int n = fy < kFH ? s.cnt[fy] : 0;
+            held[q].key = -1;
+            key2[q][0] = key2[q][1] = -1;
+            if (lane < n) {
+                const int lc = min(max(tg2[q].y, 0), kFC - 1);
+                held[q].id = tg2[q].x;
+                held[q].key = lc | (atomicAdd(&s.off[lc], 1) << 16);
+            }
+#pragma unroll
+            for (int h = 1; h <= 2; h++)
+                if (n > 32 * h && lane + 32 * h < n) {
+                    const int lc = min(max(btag[fy * kRunCap + lane + 32 * h].y, 0), kFC - 1);
+                    key2[q][h - 1] = lc | (atomicAdd(&s.off[lc], 1) << 16);
+                }
         }
     }
     __syncthreads();
@@ -211,12 +303,12 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const LeanConsts &
             const int o = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += o;
         }
-        if (lane == 31) s.misc[warp] = incl;
+        if (lane == 31) s.wsum[warp] = incl;
         __syncthreads();
         int ex = incl - sum;
 #pragma unroll
-        for (int w = 0; w < kTileThreads / 32; w++)
-            if (w < warp) ex += s.misc[w];
+        for (int w = 0; w < kTileWarps; w++)
+            if (w < warp) ex += s.wsum[w];
 #pragma unroll
         for (int q = 0; q < kCpt; q++) {
             if (c0 + q <= kFC) s.off[c0 + q] = ex;
@@ -224,59 +316,120 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const LeanConsts &
         }
     }
     __syncthreads();
-    // ---- place: records into cell order; owned particles per frame row ------------------
+    // ---- tables: packed offsets per cell, owned particles per frame row ------------------
+    constexpr int kPkPt = (kFC + kTileThreads - 1) / kTileThreads;
+    uint2 mypk[kPkPt];
 #pragma unroll
-    for (int k = 0; k < kTileK; k++) {
-        if (keep[k] < 0) continue;
-        const int r = tid + k * kTileThreads;
-        const int src = r < n_own ? r : tg.cap_own + (r - n_own);
-        const int lc = keep[k] & 0xffff;
-        const int pos = s.off[lc] + (keep[k] >> 16);
-        const float4 q = *reinterpret_cast<const float4 *>(bucket + src);
-        s.scr[pos] = q;
-        s.id[pos] = bucket[src].id;
-        s.lc[pos] = (unsigned short)lc;
+    for (int q = 0; q < kPkPt; q++) {
+        const int c = tid + q * kTileThreads;
+        if (c < kFC) {
+            const unsigned o0 = s.off[max(c - 1, 0)], o1 = s.off[c], o2 = s.off[c + 1], o3 = s.off[min(c + 2, kFC)];
+            mypk[q] = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+        }
     }
-    if (warp == 0) {
-        // owned particles of frame row y+1 = its cells 1 .. kTX (cells 0 and kTX+1 are the ring)
-        int len = 0;
-        if (lane < kTY) len = s.off[(lane + 1) * kFW + kTX + 1] - s.off[(lane + 1) * kFW + 1];
+    // Owned particles of frame row y = its cells 1 .. tw (cells 0 and tw+1 are the ring; tw x th is this
+    // tile's size: the last tile column / row of the grid may be smaller), rows 1 .. th.  Every warp derives
+    // the row table for itself (lane y holds row y): rb = sorted start of cell (y, 1) minus the owned
+    // particles before row y, so that position - rb = rank among the owned particles.
+    int rb;
+    {
+        int len = 0, start = 0;
+        if (lane >= 1 && lane <= th) {
+            start = s.off[lane * kFW + 1];
+            len = s.off[lane * kFW + tw + 1] - start;
+        }
         int incl = len;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int o = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += o;
         }
-        if (lane <= kTY) s.rowpre[lane] = incl - len;   // lane == kTY: the total
+        rb = start - (incl - len);
+        if (tid == 31) s.cnt[kFH] = incl;   // owned particles of the tile
+    }
+    __syncthreads();   // every read of off[] is done: own[] may overwrite it
+#pragma unroll
+    for (int q = 0; q < kPkPt; q++) {
+        const int c = tid + q * kTileThreads;
+        if (c < kFC) s.pk[c] = mypk[q];
+    }
+    __syncthreads();
+    // ---- place: records into cell order; the list of owned particles -----------------------
+    const int nx = a.b.nx, nl = a.b.nl;
+    auto place = [&](int key, const double4 &st, double rad, int id) -> int {
+        const int lc = key & 0xffff;
+        const int pos = (int)(s.pk[lc].x >> 16) + (key >> 16);
+        const int lcy = lc / kFW, lcx = lc - lcy * kFW;
+        // the FILED cell of the record (a ring cell at the periodic edge is the opposite edge of the grid)
+        int X = txi * kTX + lcx - 1, Yl = tyi * kTY + lcy - 1;
+        X = X < 0 ? X + nx : (X >= nx ? X - nx : X);
+        Yl = Yl < 0 ? Yl + nl : (Yl >= nl ? Yl - nl : Yl);
+        // screening record, relative to the centre of the filed cell (lean.cuh)
+        float4 r;
+        r.x = __double2float_rn(__dsub_rn(st.x, __dmul_rn((double)X + 0.5, a.b.csx)));
+        r.y = __double2float_rn(__dsub_rn(st.y, __dmul_rn((double)edmd_global_row(a.b, Yl) + 0.5, a.b.csy)));
+        r.z = __double2float_rn(st.z);
+        r.w = __double2float_rn(st.w);
+        if (TWO) r.w = __int_as_float((__float_as_int(r.w) & ~1) | (edmd_same_class(rad, a.rad0) ? 0 : 1));
+        s.xy[pos] = make_double2(st.x, st.y);
+        s.vv[pos] = make_double2(st.z, st.w);
+        s.scr[pos] = r;
+        s.id[pos] = id;
+        if (radii) s.rad[pos] = rad;
+        return (lcx >= 1 && lcx <= tw && lcy >= 1 && lcy <= th) ? lcy : -1;
+    };
+    // (the shuffle that fetches a row's rb runs with the whole warp converged)
+    auto place_own = [&](bool active, int key, const double4 &st, double rad, int id) {
+        int lcy = -1;
+        if (active) lcy = place(key, st, rad, id);
+        const int r = __shfl_sync(0xffffffffu, rb, lcy >= 0 ? lcy : 0);
+        if (lcy >= 0) {
+            const int lc = key & 0xffff;
+            const int pos = (int)(s.pk[lc].x >> 16) + (key >> 16);
+            s.own[pos - r] = (unsigned)pos | ((unsigned)lc << 16);
+        }
+    };
+#pragma unroll
+    for (int q = 0; q < kRunsPerWarp; q++) {
+        place_own(held[q].key >= 0, held[q].key, held[q].st, held[q].rad, held[q].id);
+#pragma unroll
+        for (int h = 1; h <= 2; h++) {
+            const int fy = warp + kTileWarps * q;
+            if ((fy < kFH ? s.cnt[fy] : 0) <= 32 * h) continue;   // warp-uniform
+            const bool act = key2[q][h - 1] >= 0;
+            const int slot = fy * kRunCap + lane + 32 * h;
+            double4 st2 = make_double4(0, 0, 0, 0);
+            double rad2 = a.rad0;
+            int id2 = 0;
+            if (act) {
+                st2 = ld_sector(bst + slot);
+                id2 = btag[slot].x;
+                if (radii) rad2 = brad[slot];
+            }
+            place_own(act, key2[q][h - 1], st2, rad2, id2);
+        }
     }
     __syncthreads();
 
     // ---- sweep: every owned particle of the tile, in cell order ---------------------------
-    const int nown = s.rowpre[kTY];
-    const int tyi = tile / tg.ntx, txi = tile - tyi * tg.ntx;
+    const int nown = (a.dbg & 4) ? 0 : s.cnt[kFH];
+    const LeanConsts K = *s.K;
     const float fnan = __int_as_float(0x7fffffff);
 #pragma unroll 1
     for (int k = tid; k < nown; k += kTileThreads) {
-        // frame row of the k-th owned particle: largest y with rowpre[y] <= k
-        int y = 0;
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1)
-            if (y + step < kTY && s.rowpre[y + step] <= k) y += step;
-        const int self = s.off[(y + 1) * kFW + 1] + (k - s.rowpre[y]);
+        const unsigned u = s.own[k];
+        const int self = u & 0xffff, lc = u >> 16;
         const int id = s.id[self];
+        const float4 own = s.scr[self];
+        const uint2 pkr[3] = {s.pk[lc - kFW], s.pk[lc], s.pk[lc + kFW]};
         if (id >= a.n_owned) continue;   // halo copy from a neighbouring slab: never predicted
-        const double4 me = ld_sector(a.xv + id);
-        const double rad_i = TWO ? a.rad[id] : a.rad0;
-        const int lc = s.lc[self];
-        const int lcx = lc - (y + 1) * kFW;   // frame column 1 .. kTX
+        const int lcy = lc / kFW, lcx = lc - lcy * kFW;
 
         int lo[3], t1[3], t2[3], hi[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            const int *o = s.off + (y + j) * kFW + lcx - 1;
-            lo[j] = o[0]; t1[j] = o[1]; t2[j] = o[2]; hi[j] = o[3];
+            lo[j] = pkr[j].x & 0xffff; t1[j] = pkr[j].x >> 16; t2[j] = pkr[j].y & 0xffff; hi[j] = pkr[j].y >> 16;
         }
-        const float4 own = s.scr[self];
         // dx = rx_j - (rx_i - k csx), k = column(j) - column(i) in {-1, 0, 1}
         const float pxm = __fadd_rn(own.x, K.csx), px0 = own.x, pxp = __fsub_rn(own.x, K.csx);
         const bool own1 = TWO && (__float_as_int(own.w) & 1);
@@ -306,6 +459,7 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const LeanConsts &
             lo2 = fmaxf(lo1, fminf(lo2, tl));
             lo1 = fminf(lo1, tl);
         };
+        if (!(a.dbg & 1))
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             const float py = j == 0 ? __fadd_rn(own.y, K.csy) : (j == 1 ? own.y : __fsub_rn(own.y, K.csy));
@@ -318,35 +472,32 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const LeanConsts &
             }
             if (p < pe) screen(j, p, py);
         }
-        const int wid = idx >= 0 ? s.id[idx] : -1;
-        double4 wq = make_double4(0, 0, 0, 0);
-        double rad_w = a.rad0;
-        if (wid >= 0) {
-            wq = ld_sector(a.xv + wid);
-            if (TWO) rad_w = a.rad[wid];
-        }
         const float second = lo1 > 0.0f ? lo2 : fnan;   // a non-positive smallest bound is never certifiable
-
+        const double2 mexy = s.xy[self], mev = s.vv[self];
+        const double4 me = make_double4(mexy.x, mexy.y, mev.x, mev.y);
+        const double rad_i = radii ? s.rad[self] : a.rad0;
+        if (a.dbg & 2) {
+            st_ev(a.ev + id, (double)second + me.x, 0.0, idx, 0);
+            continue;
+        }
         // ---- exact: crossing + the winner's pair time, as the reference computes them ----
-        const int X = txi * kTX + lcx - 1, Yl = tyi * kTY + y;
+        const int X = txi * kTX + lcx - 1, Yl = tyi * kTY + lcy - 1;
         SRec p1;
         p1.x = me.x; p1.y = me.y; p1.vx = me.z; p1.vy = me.w;
         p1.rad = rad_i; p1.id = id; p1.pc = 0;
         const double four_r1 = __dmul_rn(4.0, p1.rad);
-        {
-            double dtc;
-            int d;
-            crossing_fast<true>(a.b, p1, X, edmd_global_row(a.b, Yl), dtc, d);
-            a.t_cross[id] = __dadd_rn(a.t, dtc);
-            a.dir[id] = (uint8_t)d;
-        }
+        double dtc;
+        int dirc;
+        crossing_fast<true>(a.b, p1, X, edmd_global_row(a.b, Yl), dtc, dirc);
         double best = EDMD_NEVER;
         int best_id = -1, best_pc = -1, ov_id = -1, ov_pc = -1;
-        bool certified = wid < 0;   // no candidate can collide: partner 0 at t + 1e26
-        if (wid >= 0) {
+        bool certified = idx < 0;   // no candidate can collide: partner 0 at t + 1e26
+        if (idx >= 0) {
+            const double2 wxy = s.xy[idx], wv = s.vv[idx];
+            const double4 wq = make_double4(wxy.x, wxy.y, wv.x, wv.y);
             SRec p2;
             p2.x = wq.x; p2.y = wq.y; p2.vx = wq.z; p2.vy = wq.w;
-            p2.rad = rad_w; p2.id = wid; p2.pc = 0;
+            p2.rad = radii ? s.rad[idx] : a.rad0; p2.id = s.id[idx]; p2.pc = 0;
             double bb, v2, cc, b2, vc;
             pair_terms<true>(a.b, p1, four_r1, p2, bb, v2, cc, b2, vc);
             const double det = __dsub_rn(b2, vc);
@@ -355,8 +506,9 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const LeanConsts &
             // bound above the exact time (a NaN bound or time fails the test)
             certified = !(bb > 0) && (det >= 0) && ((double)second > T);
             best = T;
-            best_id = wid;
+            best_id = p2.id;
         }
+        auto gidx = [&](int q) { return a.gid ? a.gid[q] : q; };   // the caller's (global) id of a local one
         if (!certified) {
             // the plain FP64 loop in the reference's order with its tie rule (first in scan
             // order = earlier cell, then larger id = its linked-list order after cellListInit)
@@ -367,21 +519,20 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const LeanConsts &
             for (int j = 0; j < 3; j++) {
 #pragma unroll 1
                 for (int p = lo[j]; p < hi[j]; p++) {
-                    const int id2 = s.id[p];
-                    if (id2 == id) continue;   // `p1 != p2` is identity (periodic copies included)
-                    const double4 q = ld_sector(a.xv + id2);
+                    if (p == self) continue;   // `p1 != p2` is identity
+                    const double2 qxy = s.xy[p], qv = s.vv[p];
+                    const double4 q = make_double4(qxy.x, qxy.y, qv.x, qv.y);
                     SRec p2;
                     p2.x = q.x; p2.y = q.y; p2.vx = q.z; p2.vy = q.w;
-                    p2.rad = TWO ? a.rad[id2] : a.rad0; p2.id = id2;
+                    p2.rad = radii ? s.rad[p] : a.rad0; p2.id = s.id[p];
                     p2.pc = 3 * j + (p < t1[j] ? 0 : (p < t2[j] ? 1 : 2));   // scan-order cell
                     bool ov = false;
                     const double dt = pair_time_normal<true>(a.b, p1, four_r1, p2, ov);
-                    if (ov && (ov_id < 0 || (p2.pc == ov_pc && gid_of(a, p2.id) > gid_of(a, ov_id)))) {
+                    if (ov && (ov_id < 0 || (p2.pc == ov_pc && gidx(p2.id) > gidx(ov_id)))) {
                         ov_id = p2.id;
                         ov_pc = p2.pc;
                     }
-                    if (best > dt || (best == dt && best_id >= 0 && p2.pc == best_pc &&
-                                      gid_of(a, p2.id) > gid_of(a, best_id))) {
+                    if (best > dt || (best == dt && best_id >= 0 && p2.pc == best_pc && gidx(p2.id) > gidx(best_id))) {
                         best = dt;
                         best_id = p2.id;
                         best_pc = p2.pc;
@@ -389,12 +540,12 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const LeanConsts &
                 }
             }
         }
-        a.t_coll[id] = __dadd_rn(a.t, best);
-        a.partner[id] = best_id >= 0 ? gid_of(a, best_id) : 0;
-        a.ctype[id] = EDMD_EV_COLLISION;
+        // ids in shared memory are LOCAL; partners and the overlap report carry the caller's ids
+        const int partner = best_id >= 0 ? (a.gid ? a.gid[best_id] : best_id) : 0;
+        st_ev(a.ev + id, __dadd_rn(a.t, dtc), __dadd_rn(a.t, best), partner, dirc);
         if (ov_id >= 0) {
-            unsigned long long key = ((unsigned long long)(uint32_t)gid_of(a, id) << 32) |
-                                     (uint32_t)gid_of(a, ov_id);
+            const unsigned long long key = ((unsigned long long)(uint32_t)(a.gid ? a.gid[id] : id) << 32) |
+                                           (uint32_t)(a.gid ? a.gid[ov_id] : ov_id);
             atomicMin(a.overlap_key, key);
         }
     }
@@ -404,47 +555,68 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtas)
 k_tile_sweep(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    const TileSmem s = carve(tile_smem, a.tg.cap);
+    const TileSmem s = carve(tile_smem, a.tg.smem_cap, a.rad_smem);
     const int tid = threadIdx.x;
     // zero the cell counters while the previous kernel drains
     for (int c = tid; c <= kFC; c += kTileThreads) s.off[c] = 0;
     edmd_pdl_wait();
     const int tile = a.tiles ? a.tiles[blockIdx.x] : blockIdx.x;
-    int32_t *cnt = a.tcnt + (size_t)tile * kCntStride;
-    if (tid == 0) {
-        s.misc[4] = min(cnt[0], a.tg.cap_own);
-        s.misc[5] = min(cnt[kCntHalo], a.tg.cap_halo);
-        // cursors back to zero for the next sweep (this CTA is their only reader)
-        cnt[0] = 0;
-        cnt[kCntHalo] = 0;
-    }
     const int classes = a.flags[kFlagNotMono];   // 0: one radius, 1: two classes, more: not eligible
     const double rad1 = __longlong_as_double(*reinterpret_cast<const long long *>(a.flags + kFlagRad1));
-    const LeanConsts K = make_consts(a.b, a.rad0, rad1, classes == 1, __int_as_float(a.flags[kFlagVmax]));
+    if (tid < 32) {
+        // run lengths; cursors back to zero for the next sweep (this CTA is their only reader)
+        int n = 0;
+        if (tid < kFH) {
+            int32_t *cur = a.tcnt + ((size_t)tile * kFH + tid) * kCurStride;
+            n = min(*cur, kRunCap);
+            *cur = 0;
+            s.cnt[tid] = n;
+        }
+        const int total = __reduce_add_sync(0xffffffffu, n);
+        if (tid == 0) s.cnt[kFH + 1] = total;
+    } else if (tid == 32) {
+        *s.K = make_consts(a.b, a.rad0, rad1, classes == 1, __int_as_float(a.flags[kFlagVmax]));
+    }
     const bool declined = a.flags[kFlagLeanFail] != 0;
-    const bool bad = a.flags[kFlagInsane] != 0 || classes > 1 || !K.ok;
+    const bool bad = a.flags[kFlagInsane] != 0 || classes > 1 || (classes == 1 && !a.rad_smem);
     __syncthreads();
-    if (declined) return;   // a bucket overflowed: the host re-runs the sweep on the full path
-    if (bad) {
-        if (blockIdx.x == 0 && tid == 0) a.flags[kFlagLeanFail] = 1;
+    if (declined) return;   // a run overflowed: the host re-runs the sweep on the full path
+    if (bad || !s.K->ok || s.cnt[kFH + 1] > a.tg.smem_cap) {
+        // not eligible, or more records than this CTA's shared memory holds: decline
+        if (tid == 0) atomicOr(&a.flags[kFlagLeanFail], 1);
         return;
     }
-    const int n_own = s.misc[4], n_halo = s.misc[5];
-    __syncthreads();   // misc[] is reused by the scan
-    if (classes == 1 && rad1 > 0.0) tile_main<true>(a, K, s, tile, n_own, n_halo);
-    else tile_main<false>(a, K, s, tile, n_own, n_halo);
+    // classes == 1: the radii are spread inside their classes (a reference-grown system): the exact
+    // stage takes every disk's own FP64 radius; the class bit is only looked at when a second class exists
+    if (classes == 1 && rad1 > 0.0) tile_main<true>(a, s, tile, true);
+    else tile_main<false>(a, s, tile, classes == 1);
+}
+
+// the ABI's five prediction arrays from the event records (one coalesced pass)
+__global__ void __launch_bounds__(256)
+k_unpack_events(int n, const edmd_ev32 *__restrict__ ev, double *__restrict__ t_cross, uint8_t *__restrict__ dir,
+                double *__restrict__ t_coll, int32_t *__restrict__ partner)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 v = ld_sector(reinterpret_cast<const double4 *>(ev + i));
+    t_cross[i] = v.x;
+    t_coll[i] = v.y;
+    partner[i] = __double2loint(v.z);
+    dir[i] = (uint8_t)(__double2hiint(v.z) & 0xff);
 }
 
 }  // namespace
 
 bool edmd_tile_eligible(const edmd_ctx *c, int mode)
 {
-    return edmd_lean_eligible(c, mode) && !c->tile_off && c->trec != nullptr;
+    return edmd_lean_eligible(c, mode) && !c->tile_off && c->tst != nullptr;
 }
 
-size_t edmd_tile_smem_bytes(const TileGeom &tg)
+static size_t tile_smem_bytes(const TileGeom &tg, int rad_smem)
 {
-    return (size_t)tg.cap * 22 + 4 + sizeof(int) * (kFC + 4 + kTY + 4 + 8);
+    return (size_t)tg.smem_cap * (32 + 16 + 4 + (rad_smem ? 8 : 0)) + sizeof(uint2) * kFC +
+           tile_aliased_bytes(tg.smem_cap) + sizeof(int) * (kTileWarps + kFH + 4) + sizeof(LeanConsts) + 16;
 }
 
 // geometry + capacities of the tile buckets for a context (nx x nl cells, n particles)
@@ -456,17 +628,22 @@ bool edmd_tile_geometry(int nx, int nl, size_t n, TileGeom *out)
     tg.wlast = nx - (tg.ntx - 1) * kTX;
     tg.hlast = nl - (tg.nty - 1) * kTY;
     const double dens = (double)n / ((double)nx * (double)nl);   // particles per cell
-    long long own = (long long)(1.35 * dens * kTX * kTY) + 96;
-    long long halo = (long long)(1.6 * dens * (2 * (kTX + kTY) + 4)) + 64;
-    own = (own + 31) & ~31ll;
-    halo = (halo + 31) & ~31ll;
-    if (own + halo > (long long)kTileK * kTileThreads) return false;   // denser than a CTA's registers provide for
-    tg.cap_own = (int)own;
-    tg.cap_halo = (int)halo;
-    tg.cap = (int)(own + halo);
-    if ((long long)tg.ntx * tg.nty * tg.cap >= (1ll << 31)) return false;
+    long long cap = (long long)(1.25 * dens * kFC) + 96;
+    cap = (cap + 31) & ~31ll;
+    if (cap > (long long)kFH * kRunCap) cap = (long long)kFH * kRunCap;
+    tg.smem_cap = (int)cap;
+    if (tile_smem_bytes(tg, 1) > 200 * 1024) return false;   // denser than a CTA's shared memory provides for
+    if ((long long)tg.ntx * tg.nty * kFH * kRunCap >= (1ll << 31)) return false;
     *out = tg;
     return true;
+}
+
+int edmd_launch_unpack_events(edmd_ctx *c)
+{
+    const int n = c->n_owned;
+    if (n == 0) return 0;
+    k_unpack_events<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->evrec, c->t_cross, c->dir, c->t_coll, c->partner);
+    return 1;
 }
 
 int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between)
@@ -474,10 +651,11 @@ int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between)
     if (c->n == 0) return 0;
     const TileGeom &tg = c->tgeom;
     PartArgs pa;
-    pa.first = 0; pa.n = c->n; pa.ps = c->ps; pa.slab = c->slab ? 1 : 0;
+    pa.first = 0; pa.n = c->n; pa.ps = c->ps; pa.slab = c->slab ? 1 : 0; pa.dbg = c->tile_dbg;
     pa.tg = tg; pa.b = c->dbox;
     pa.cid = c->cid; pa.xv = c->xv; pa.rad = c->rad; pa.rad0 = c->rad0;
-    pa.flags = c->flags; pa.tcnt = c->tcnt; pa.trec = c->trec;
+    pa.flags = c->flags; pa.tcnt = c->tcnt; pa.tst = c->tst; pa.ttag = c->ttag; pa.trad = c->trad;
+    pa.overlap_key = c->overlap_key;
     // the first kernel of the chain is launched plainly: whatever precedes it on the stream completes first
     edmd_launch(k_tile_partition, dim3((c->n + kPartThreads - 1) / kPartThreads), dim3(kPartThreads), 0, c->stream,
                 false, pa);
@@ -485,17 +663,20 @@ int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between)
     SweepArgs sa;
     sa.tg = tg; sa.b = c->dbox; sa.t = c->t; sa.rad0 = c->rad0; sa.n_owned = c->n_owned;
     sa.tiles = nullptr;
-    sa.xv = c->xv; sa.rad = c->rad; sa.gid = c->slab ? c->gid : nullptr;
-    sa.flags = c->flags; sa.tcnt = c->tcnt; sa.trec = c->trec;
-    sa.t_cross = c->t_cross; sa.dir = c->dir; sa.t_coll = c->t_coll; sa.partner = c->partner; sa.ctype = c->ctype;
+    sa.dbg = c->tile_dbg;
+    sa.rad_smem = c->lean_two ? 1 : 0;   // the host's knowledge; the kernel declines if the device knows better
+    sa.gid = c->slab ? c->gid : nullptr;
+    sa.flags = c->flags; sa.tcnt = c->tcnt; sa.tst = c->tst; sa.ttag = c->ttag; sa.trad = c->trad;
+    sa.ev = c->evrec;
     sa.overlap_key = c->overlap_key;
-    const size_t smem = edmd_tile_smem_bytes(tg);
+    const size_t smem = tile_smem_bytes(tg, sa.rad_smem);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr = true;
     }
     edmd_launch(k_tile_sweep, dim3(tg.ntx * tg.nty), dim3(kTileThreads), smem, c->stream, c->lean_pdl, sa);
+    c->pred_packed = true;
     return 2;
 }

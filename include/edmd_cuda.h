@@ -103,6 +103,16 @@ uint64_t edmd_cuda_launch_count(const edmd_ctx *ctx);
 /* EDMD_OPT_NO_TILE = 1 keeps eligible sweeps off the two-kernel tile sweep (tile_sweep.cu)
  * and on the older five-kernel lean chain (cross-checking and timing). */
 #define EDMD_OPT_NO_TILE 6
+/* One particle's two scheduled events as the tile sweep leaves them on the device: exactly what
+ * addCrossingEvent / addCollisionEvent store into eventList[i] / eventList[N+i]
+ * (src/EDMD.c:2487-2496, 3286-3297), one 32-byte record per particle. */
+typedef struct edmd_ev32 {
+    double t_cross, t_coll;   /* absolute event times */
+    int32_t partner;          /* collision partner (caller's particle id) */
+    uint8_t dir;              /* crossing direction 1..4 */
+    uint8_t ctype;            /* EDMD_EV_COLLISION */
+    uint8_t pad[10];
+} edmd_ev32;
 int edmd_cuda_set_option(edmd_ctx *ctx, int option, int value);
 /* Counters: EDMD_STAT_EXACT_RESCANS = particles the tiled sweep had to resolve
  * with the exact re-scan (near-ties, ill-conditioned pairs) since create. */

@@ -26,6 +26,7 @@ OPT_NO_PDL = 3
 OPT_PCF_LEGACY = 4
 OPT_PCF_GROUPS = 5
 OPT_NO_TILE = 6
+OPT_NO_TILE_BOOP = 7
 EPLAN = 6
 STAT_EXACT_RESCANS = 1
 STAT_LEAN_SWEEPS = 2

@@ -282,6 +282,8 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
         if ((r = dev_alloc(c, &c->ttag, runs * kRunCap + 32))) return r;
         if ((r = dev_alloc(c, &c->trad, runs * kRunCap + 32))) return r;
         if ((r = dev_alloc(c, &c->tcnt, runs * kCurStride + 8))) return r;
+        if ((r = dev_alloc(c, &c->tkeep, runs + 8))) return r;
+        if ((r = dev_alloc(c, &c->boop_rec, 2 * N + 8))) return r;
         if ((r = dev_alloc(c, &c->evrec, N + 32))) return r;
         CU(cudaMemsetAsync(c->tcnt, 0, (runs * kCurStride + 8) * sizeof(int32_t), c->stream));
     }
@@ -319,7 +321,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->gid, c->cell_cnt,
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
-                   c->lrec, c->lchunks, c->lres, c->lwork, c->tst, c->ttag, c->trad, c->tcnt, c->evrec, c->cal_mem,
+                   c->lrec, c->lchunks, c->lres, c->lwork, c->tst, c->ttag, c->trad, c->tcnt, c->tkeep, c->boop_rec, c->evrec, c->cal_mem,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
                    c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->vor_mem, c->thermo_mem, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
@@ -370,6 +372,10 @@ int edmd_cuda_set_option(edmd_ctx *c, int option, int value)
     }
     if (option == EDMD_OPT_NO_TILE) {
         c->tile_off = value != 0;
+        return 0;
+    }
+    if (option == EDMD_OPT_NO_TILE_BOOP) {
+        c->boop_tile_off = value != 0;
         return 0;
     }
     if (option == 100) {   // internal: timing experiments
@@ -877,6 +883,58 @@ static int ensure_index(edmd_ctx *c)
     return 0;
 }
 
+// K4 on the device: the tile kernel (tile_sweep.cu) over the buckets of the last sweep when they still
+// match the state, else after a fresh partition; the row kernel over the full cell index when the tile
+// path does not apply or declines.
+static bool boop_tile_ok(const edmd_ctx *c)
+{
+    return c->tst != nullptr && !c->tile_off && !c->boop_tile_off && !c->force_generic && c->n > 0;
+}
+
+static int boop_launch(edmd_ctx *c, double r_c, bool *used_tile)
+{
+    int r;
+    *used_tile = false;
+    if ((r = lean_fallback(c))) return r;   // a pending decline of the last sweep is resolved first
+    if (boop_tile_ok(c)) {
+        const bool fresh = c->have_index && c->index_tile;   // buckets (and tkeep) match the resident state
+        if (!fresh) c->launches += edmd_launch_tile_partition(c);
+        c->launches += edmd_launch_tile_boop(c, r_c, fresh);
+        CU(cudaGetLastError());
+        if (!fresh) {
+            c->have_index = true;
+            c->index_lean = true;
+            c->index_tile = true;
+        }
+        *used_tile = true;
+        return 0;
+    }
+    if ((r = ensure_index(c))) return r;
+    c->launches += edmd_launch_boop(c, r_c);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// after a synchronisation point: did the tile psi6 pass decline?  Then redo it with the row kernel.
+static int boop_tile_confirm(edmd_ctx *c, double r_c, bool *redone)
+{
+    int32_t f[kFlagCount];
+    *redone = false;
+    CU(cudaMemcpyAsync(f, c->flags, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (!f[kFlagBoopFail] && !f[kFlagLeanFail]) return 0;
+    CU(cudaMemsetAsync(c->flags + kFlagBoopFail, 0, sizeof(int32_t), c->stream));
+    CU(cudaMemsetAsync(c->flags + kFlagLeanFail, 0, sizeof(int32_t), c->stream));
+    c->boop_tile_off = true;   // this system does not fit the tile buckets: stop trying
+    c->have_index = false;
+    int r = ensure_index(c);
+    if (r) return r;
+    c->launches += edmd_launch_boop(c, r_c);
+    CU(cudaGetLastError());
+    *redone = true;
+    return 0;
+}
+
 int edmd_cuda_boop_cutoff(edmd_ctx *c, double r_c, double *q5, double *q6, double *q7,
                           double *q6_arg, int32_t *neighbors, double *mean_q6)
 {
@@ -884,8 +942,9 @@ int edmd_cuda_boop_cutoff(edmd_ctx *c, double r_c, double *q5, double *q6, doubl
     if (!c->have_state) return fail(c, EDMD_ESTATE, "boop before upload");
     CU(cudaSetDevice(c->device));
     int r;
-    if ((r = ensure_index(c))) return r;
-    c->launches += edmd_launch_boop(c, r_c);
+    bool tile = false, redone = false;
+    if ((r = boop_launch(c, r_c, &tile))) return r;
+    if (tile && (r = boop_tile_confirm(c, r_c, &redone))) return r;
     size_t N = (size_t)c->n, B = N * sizeof(double);
     if (mean_q6) c->launches += edmd_launch_mean(c, c->boop + N, c->n, c->red_partial + c->red_cap);
     CU(cudaGetLastError());
@@ -1414,9 +1473,12 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
             c->pcf_cap = nb;
         }
     }
+    bool boop_tile = false;
     if (what == EDMD_BENCH_BOOP) {
-        int r = ensure_index(c);
+        int r = lean_fallback(c);
         if (r) return r;
+        boop_tile = boop_tile_ok(c);
+        if (!boop_tile && (r = ensure_index(c))) return r;
     }
     char *vgrid = nullptr;
     double2 *vpsi = nullptr;
@@ -1477,8 +1539,18 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
             c->launches += edmd_launch_free_fly(c, mode, 0.0);  // dt = 0: state unchanged
             break;
         case EDMD_BENCH_BOOP:
-            if (e) CU(cudaEventRecord(e[1], c->stream));
-            c->launches += edmd_launch_boop(c, dr > 0 ? dr : 2.5);
+            if (boop_tile) {
+                // a frame after a snapshot re-sync: partition (ms_total includes it) + the tile kernel (ms_main)
+                c->launches += edmd_launch_tile_partition(c);
+                if (e) CU(cudaEventRecord(e[1], c->stream));
+                c->launches += edmd_launch_tile_boop(c, dr > 0 ? dr : 2.5, false);
+                c->have_index = true;
+                c->index_lean = true;
+                c->index_tile = true;
+            } else {
+                if (e) CU(cudaEventRecord(e[1], c->stream));
+                c->launches += edmd_launch_boop(c, dr > 0 ? dr : 2.5);
+            }
             break;
         case EDMD_BENCH_PCF:
             CU(cudaMemsetAsync(c->pcf_counts, 0, (size_t)(nb > 0 ? nb : 1) * sizeof(unsigned long long), c->stream));
@@ -1500,6 +1572,16 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
     }
     CU(cudaStreamSynchronize(c->stream));
     c->t = t_keep;
+    if (what == EDMD_BENCH_BOOP && boop_tile) {
+        int32_t f[kFlagCount];
+        CU(cudaMemcpy(f, c->flags, sizeof(f), cudaMemcpyDeviceToHost));
+        if (f[kFlagBoopFail] || f[kFlagLeanFail]) {
+            CU(cudaMemset(c->flags + kFlagBoopFail, 0, sizeof(int32_t)));
+            CU(cudaMemset(c->flags + kFlagLeanFail, 0, sizeof(int32_t)));
+            c->have_index = false;
+            return fail(c, EDMD_ESTATE, "bench: the tile psi6 kernel declined (buckets too small for this system)");
+        }
+    }
     if (what == EDMD_BENCH_SWEEP && c->index_lean) {
         int32_t f = 0;
         CU(cudaMemcpy(&f, c->flags + kFlagLeanFail, sizeof(f), cudaMemcpyDeviceToHost));

@@ -122,6 +122,7 @@ enum {
     kFlagNotMono = 5,    // radii: 0 all EXACTLY rad0, 1 at most two classes (rad0's and kFlagRad1's, see edmd_note_radius), >= 2 more
     kFlagLeanFail = 6,   // the lean sweep declined (state not eligible): redo with the full path
     kFlagWork = 7,       // number of entries in the lean work list (chunks that hold particles)
+    kFlagBoopFail = 10,  // the tile psi6 kernel declined (a bucket beyond a CTA's shared memory)
     kFlagRad1 = 8,       // (two words, 8-byte aligned) bits of the first radius seen outside rad0's class, 0 = none
     kFlagCount = 16
 };
@@ -226,6 +227,9 @@ struct edmd_ctx {
     int2 *ttag;                      // ... their 8-byte tags (id, frame cell)
     double *trad;                    // ... and radii (written only when the radii are not all exactly rad0)
     int32_t *tcnt;                   // one cursor per run, kCurStride ints apart
+    int32_t *tkeep;                  // run lengths of the last partition (dense), for later passes over the buckets
+    bool boop_tile_off;              // EDMD_OPT_NO_TILE_BOOP
+    double4 *boop_rec;               // psi6 records of the tile kernel: two sectors per particle id
     edmd_ev32 *evrec;                 // event records of the last tile sweep, by particle id
     bool pred_packed;                // the predictions of the last sweep are in ev[], not yet in the five arrays
     bool tile_off;                   // EDMD_OPT_NO_TILE
@@ -315,6 +319,8 @@ bool edmd_tile_eligible(const edmd_ctx *c, int mode);
 bool edmd_tile_geometry(int nx, int nl, size_t n, TileGeom *out);
 int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between);
 int edmd_launch_unpack_events(edmd_ctx *c);
+int edmd_launch_tile_partition(edmd_ctx *c);
+int edmd_launch_tile_boop(edmd_ctx *c, double r_c, bool from_keep);
 int edmd_launch_boop(edmd_ctx *c, double r_c);
 int edmd_launch_mean(edmd_ctx *c, const double *v, int n, double *out_dev);
 int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bins, double kx, double ky,

@@ -162,6 +162,7 @@ struct SweepArgs {
     const int32_t *gid;
     int32_t *flags;
     int32_t *tcnt;
+    int32_t *tkeep;   // run lengths of the last partition (kept when the cursors are zeroed)
     const double4 *tst;
     const int2 *ttag;
     const double *trad;
@@ -222,6 +223,29 @@ __device__ __forceinline__ TileSmem carve(unsigned char *base, int cap, int rad_
     return s;
 }
 
+// the psi6 kernel keeps positions and ids only: half the shared memory, twice the resident CTAs
+__device__ __forceinline__ TileSmem carve_boop(unsigned char *base, int cap)
+{
+    TileSmem s;
+    s.xy = reinterpret_cast<double2 *>(base);
+    base += (size_t)cap * 16;
+    s.vv = nullptr;
+    s.scr = nullptr;
+    s.rad = nullptr;
+    s.K = nullptr;
+    s.pk = reinterpret_cast<uint2 *>(base);
+    base += sizeof(uint2) * kFC;
+    s.id = reinterpret_cast<int *>(base);
+    base += (size_t)cap * 4;
+    s.off = reinterpret_cast<int *>(base);
+    s.own = reinterpret_cast<unsigned int *>(base);
+    base += tile_aliased_bytes(cap);
+    s.wsum = reinterpret_cast<int *>(base);
+    s.cnt = s.wsum + kTileWarps;
+    return s;
+}
+constexpr int kBoopCtas = 6;   // per SM
+
 struct Held {
     double4 st;
     double rad;
@@ -236,17 +260,35 @@ __device__ __forceinline__ void st_ev(edmd_ev32 *dst, double t_cross, double t_c
                  : "memory");
 }
 
-template <bool TWO>
-__device__ __forceinline__ void tile_main(const SweepArgs &a, const TileSmem &s, int tile, const bool radii)
+// where a tile sits in the grid
+struct TilePos {
+    int txi, tyi;   // tile column / row
+    int tw, th;     // its size in cells (the last tile column / row of the grid may be smaller)
+};
+__device__ __forceinline__ TilePos tile_pos(const TileGeom &tg, int tile)
+{
+    TilePos t;
+    t.tyi = tile / tg.ntx;
+    t.txi = tile - t.tyi * tg.ntx;
+    t.tw = t.txi == tg.ntx - 1 ? tg.wlast : kTX;
+    t.th = t.tyi == tg.nty - 1 ? tg.hlast : kTY;
+    return t;
+}
+
+// Bin the bucket of one tile by frame cell in shared memory: count -> scan -> place.  Leaves
+// s.pk (packed cell offsets), s.own (the owned particles in cell order), s.cnt[kFH] (their number);
+// `store(pos, lcx, lcy, state, radius, id)` writes one record to its sorted position.  Ends with a
+// barrier: everything is visible to the whole CTA.
+template <class Store>
+__device__ __forceinline__ void tile_bin(const SweepArgs &a, const TileSmem &s, int tile, const TilePos &tp,
+                                         const bool radii, Store store)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TileGeom &tg = a.tg;
     const size_t slot0 = (size_t)tile * kFH * kRunCap;
     const double4 *bst = a.tst + slot0;
     const int2 *btag = a.ttag + slot0;
     const double *brad = a.trad + slot0;
-    const int tyi = tile / tg.ntx, txi = tile - tyi * tg.ntx;
-    const int tw = txi == tg.ntx - 1 ? tg.wlast : kTX, th = tyi == tg.nty - 1 ? tg.hlast : kTY;
+    const int tw = tp.tw, th = tp.th;
 
     // ---- count: rank of every record inside its frame cell (shared-memory atomics).  Warp w takes
     // the runs (frame rows) w, w + kTileWarps, ...; all loads go out before the first atomic --------
@@ -355,27 +397,11 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const TileSmem &s,
     }
     __syncthreads();
     // ---- place: records into cell order; the list of owned particles -----------------------
-    const int nx = a.b.nx, nl = a.b.nl;
     auto place = [&](int key, const double4 &st, double rad, int id) -> int {
         const int lc = key & 0xffff;
         const int pos = (int)(s.pk[lc].x >> 16) + (key >> 16);
         const int lcy = lc / kFW, lcx = lc - lcy * kFW;
-        // the FILED cell of the record (a ring cell at the periodic edge is the opposite edge of the grid)
-        int X = txi * kTX + lcx - 1, Yl = tyi * kTY + lcy - 1;
-        X = X < 0 ? X + nx : (X >= nx ? X - nx : X);
-        Yl = Yl < 0 ? Yl + nl : (Yl >= nl ? Yl - nl : Yl);
-        // screening record, relative to the centre of the filed cell (lean.cuh)
-        float4 r;
-        r.x = __double2float_rn(__dsub_rn(st.x, __dmul_rn((double)X + 0.5, a.b.csx)));
-        r.y = __double2float_rn(__dsub_rn(st.y, __dmul_rn((double)edmd_global_row(a.b, Yl) + 0.5, a.b.csy)));
-        r.z = __double2float_rn(st.z);
-        r.w = __double2float_rn(st.w);
-        if (TWO) r.w = __int_as_float((__float_as_int(r.w) & ~1) | (edmd_same_class(rad, a.rad0) ? 0 : 1));
-        s.xy[pos] = make_double2(st.x, st.y);
-        s.vv[pos] = make_double2(st.z, st.w);
-        s.scr[pos] = r;
-        s.id[pos] = id;
-        if (radii) s.rad[pos] = rad;
+        store(pos, lcx, lcy, st, rad, id);
         return (lcx >= 1 && lcx <= tw && lcy >= 1 && lcy <= th) ? lcy : -1;
     };
     // (the shuffle that fetches a row's rb runs with the whole warp converged)
@@ -410,8 +436,34 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const TileSmem &s,
         }
     }
     __syncthreads();
+}
 
-    // ---- sweep: every owned particle of the tile, in cell order ---------------------------
+// ---- sweep: every owned particle of the tile, in cell order ---------------------------
+template <bool TWO>
+__device__ __forceinline__ void tile_main(const SweepArgs &a, const TileSmem &s, int tile, const bool radii)
+{
+    const int tid = threadIdx.x;
+    const TilePos tp = tile_pos(a.tg, tile);
+    const int txi = tp.txi, tyi = tp.tyi;
+    const int nx = a.b.nx, nl = a.b.nl;
+    tile_bin(a, s, tile, tp, radii, [&](int pos, int lcx, int lcy, const double4 &st, double rad, int id) {
+        // the FILED cell of the record (a ring cell at the periodic edge is the opposite edge of the grid)
+        int X = txi * kTX + lcx - 1, Yl = tyi * kTY + lcy - 1;
+        X = X < 0 ? X + nx : (X >= nx ? X - nx : X);
+        Yl = Yl < 0 ? Yl + nl : (Yl >= nl ? Yl - nl : Yl);
+        // screening record, relative to the centre of the filed cell (lean.cuh)
+        float4 r;
+        r.x = __double2float_rn(__dsub_rn(st.x, __dmul_rn((double)X + 0.5, a.b.csx)));
+        r.y = __double2float_rn(__dsub_rn(st.y, __dmul_rn((double)edmd_global_row(a.b, Yl) + 0.5, a.b.csy)));
+        r.z = __double2float_rn(st.z);
+        r.w = __double2float_rn(st.w);
+        if (TWO) r.w = __int_as_float((__float_as_int(r.w) & ~1) | (edmd_same_class(rad, a.rad0) ? 0 : 1));
+        s.xy[pos] = make_double2(st.x, st.y);
+        s.vv[pos] = make_double2(st.z, st.w);
+        s.scr[pos] = r;
+        s.id[pos] = id;
+        if (radii) s.rad[pos] = rad;
+    });
     const int nown = (a.dbg & 4) ? 0 : s.cnt[kFH];
     const LeanConsts K = *s.K;
     const float fnan = __int_as_float(0x7fffffff);
@@ -551,6 +603,32 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const TileSmem &s,
     }
 }
 
+// Common prologue of the tile kernels: the run lengths of the tile (from the live cursors, which go back
+// to zero for the next partition -- this CTA is their only reader -- and are kept in tkeep[] for later
+// passes over the same buckets; or from tkeep[] when `from_keep`).  Returns the number of records.
+__device__ __forceinline__ int tile_prologue(const SweepArgs &a, const TileSmem &s, int tile, bool from_keep)
+{
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        int n = 0;
+        if (tid < kFH) {
+            const size_t run = (size_t)tile * kFH + tid;
+            if (from_keep) {
+                n = a.tkeep[run];
+            } else {
+                int32_t *cur = a.tcnt + run * kCurStride;
+                n = min(*cur, kRunCap);
+                *cur = 0;
+                a.tkeep[run] = n;
+            }
+            s.cnt[tid] = n;
+        }
+        const int total = __reduce_add_sync(0xffffffffu, n);
+        if (tid == 0) s.cnt[kFH + 1] = total;
+    }
+    return 0;
+}
+
 __global__ void __launch_bounds__(kTileThreads, kTileCtas)
 k_tile_sweep(const __grid_constant__ SweepArgs a)
 {
@@ -563,20 +641,8 @@ k_tile_sweep(const __grid_constant__ SweepArgs a)
     const int tile = a.tiles ? a.tiles[blockIdx.x] : blockIdx.x;
     const int classes = a.flags[kFlagNotMono];   // 0: one radius, 1: two classes, more: not eligible
     const double rad1 = __longlong_as_double(*reinterpret_cast<const long long *>(a.flags + kFlagRad1));
-    if (tid < 32) {
-        // run lengths; cursors back to zero for the next sweep (this CTA is their only reader)
-        int n = 0;
-        if (tid < kFH) {
-            int32_t *cur = a.tcnt + ((size_t)tile * kFH + tid) * kCurStride;
-            n = min(*cur, kRunCap);
-            *cur = 0;
-            s.cnt[tid] = n;
-        }
-        const int total = __reduce_add_sync(0xffffffffu, n);
-        if (tid == 0) s.cnt[kFH + 1] = total;
-    } else if (tid == 32) {
-        *s.K = make_consts(a.b, a.rad0, rad1, classes == 1, __int_as_float(a.flags[kFlagVmax]));
-    }
+    tile_prologue(a, s, tile, false);
+    if (tid == 32) *s.K = make_consts(a.b, a.rad0, rad1, classes == 1, __int_as_float(a.flags[kFlagVmax]));
     const bool declined = a.flags[kFlagLeanFail] != 0;
     const bool bad = a.flags[kFlagInsane] != 0 || classes > 1 || (classes == 1 && !a.rad_smem);
     __syncthreads();
@@ -590,6 +656,154 @@ k_tile_sweep(const __grid_constant__ SweepArgs a)
     // stage takes every disk's own FP64 radius; the class bit is only looked at when a second class exists
     if (classes == 1 && rad1 > 0.0) tile_main<true>(a, s, tile, true);
     else tile_main<false>(a, s, tile, classes == 1);
+}
+
+// ---- K4 on the tile buckets: computeBOOPCutoff, src/boop.c:61-107 ---------------------------
+// Same binning; positions only.  Per owned particle the reference's 3 x 3 scan with its own
+// arithmetic (FP64 differences, PBC, r2 < r_c^2: neighbour counts are integers identical to the
+// reference's; the same truncation: cells are ~2.0 wide, r_c = 2.5, neighbours two cells away are
+// never seen).  e^{ik theta} by complex powers, sums in 2^-48 fixed point (order-independent), as
+// k_boop_rows (analysis.cu).  Works for any radii; a bucket overflow sets kFlagBoopFail and the host
+// falls back to the row kernel.
+struct BoopTileArgs {
+    SweepArgs s;
+    int from_keep;
+    double rc2;
+    double4 *rec;   // two 32-byte sectors per particle id: (q5, q6, q7, q6_arg), (neighbours, 0, 0, 0)
+};
+
+__global__ void __launch_bounds__(kTileThreads, kBoopCtas)
+k_tile_boop(const __grid_constant__ BoopTileArgs ba)
+{
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    const SweepArgs &a = ba.s;
+    const TileSmem s = carve_boop(tile_smem, a.tg.smem_cap);
+    const int tid = threadIdx.x;
+    for (int c = tid; c <= kFC; c += kTileThreads) s.off[c] = 0;
+    edmd_pdl_wait();
+    const int tile = blockIdx.x;
+    tile_prologue(a, s, tile, ba.from_keep != 0);
+    const bool declined = a.flags[kFlagBoopFail] != 0;
+    __syncthreads();
+    if (declined) return;
+    if (s.cnt[kFH + 1] > a.tg.smem_cap) {
+        if (tid == 0) atomicOr(&a.flags[kFlagBoopFail], 1);
+        return;
+    }
+    const TilePos tp = tile_pos(a.tg, tile);
+    tile_bin(a, s, tile, tp, false, [&](int pos, int, int, const double4 &st, double, int id) {
+        s.xy[pos] = make_double2(st.x, st.y);
+        s.id[pos] = id;
+    });
+    // Records inside a cell sit in arrival order (atomics).  Sort every cell by particle id: the FP64
+    // sums below then run in one fixed order (rows, cells, ids) and every output bit is reproducible.
+    for (int c = tid; c < kFC; c += kTileThreads) {
+        const uint2 pk = s.pk[c];
+        const int lo = pk.x >> 16, hi = pk.y & 0xffff;
+        for (int i = lo + 1; i < hi; i++) {
+            const int idi = s.id[i];
+            const double2 xi = s.xy[i];
+            int j = i - 1;
+            for (; j >= lo && s.id[j] > idi; j--) {
+                s.id[j + 1] = s.id[j];
+                s.xy[j + 1] = s.xy[j];
+            }
+            s.id[j + 1] = idi;
+            s.xy[j + 1] = xi;
+        }
+    }
+    __syncthreads();
+    const int nown = s.cnt[kFH];
+    const double half_lx = a.b.half_lx, half_ly = a.b.half_ly, lx = a.b.lx, ly = a.b.ly, rc2 = ba.rc2;
+    // a tile away from the edges of the grid never sees the periodic image (every particle lies within
+    // 1.5 cells of the cell it is filed under -- kFlagInsane -- so |d| <= 4 cells < L/2): PBC() is the identity
+    const bool wrap = a.flags[kFlagInsane] != 0 || tp.txi == 0 || tp.txi == a.tg.ntx - 1 || tp.tyi == 0 ||
+                      tp.tyi == a.tg.nty - 1 || a.b.nx < 12 || a.b.ny < 12;
+#pragma unroll 1
+    for (int k = tid; k < nown; k += kTileThreads) {
+        const unsigned u = s.own[k];
+        const int self = u & 0xffff, lc = u >> 16;
+        const int id = s.id[self];
+        if (id >= a.n_owned) continue;   // halo copy from a neighbouring slab
+        const double2 me = s.xy[self];
+        const uint2 pkr[3] = {s.pk[lc - kFW], s.pk[lc], s.pk[lc + kFW]};
+        double s5r = 0, s5i = 0, s6r = 0, s6i = 0, s7r = 0, s7i = 0;
+        int nb = 0;
+#pragma unroll 1
+        for (int j = 0; j < 3; j++) {
+            const int lo = pkr[j].x & 0xffff, hi = pkr[j].y >> 16;
+#pragma unroll 1
+            for (int p = lo; p < hi; p++) {
+                if (p == self) continue;   // `p2->num != p1->num`
+                const double2 q = s.xy[p];
+                // the reference's own operations decide who is a neighbour (src/boop.c:78-84)
+                double dx = __dsub_rn(q.x, me.x), dy = __dsub_rn(q.y, me.y);
+                if (wrap) {
+                    dx = min_image(dx, half_lx, lx);
+                    dy = min_image(dy, half_ly, ly);
+                }
+                const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (r2 < rc2) {
+                    nb++;
+                    // e^{ik theta} = ((dx + i dy)/r)^k, k = 5, 6, 7, by complex powers (fused multiply-adds:
+                    // not parity-critical, gate 1e-10); 1/r from the MUFU seed + two Newton steps
+                    double zr = 1.0, zi = 0.0;   // atan2(0,0) = 0 in the reference
+                    if (r2 > 0) {
+                        double y = rsqrt_seed(r2);
+                        double e = __fma_rn(-__dmul_rn(r2, y), y, 1.0);
+                        y = __fma_rn(__dmul_rn(0.5, y), e, y);
+                        e = __fma_rn(-__dmul_rn(r2, y), y, 1.0);
+                        y = __fma_rn(__dmul_rn(0.5, y), e, y);
+                        zr = __dmul_rn(dx, y);
+                        zi = __dmul_rn(dy, y);
+                    }
+                    const double z2r = __fma_rn(zr, zr, -__dmul_rn(zi, zi)), z2i = __dmul_rn(__dadd_rn(zr, zr), zi);
+                    const double z4r = __fma_rn(z2r, z2r, -__dmul_rn(z2i, z2i)), z4i = __dmul_rn(__dadd_rn(z2r, z2r), z2i);
+                    const double z6r = __fma_rn(z4r, z2r, -__dmul_rn(z4i, z2i)), z6i = __fma_rn(z4r, z2i, __dmul_rn(z4i, z2r));
+                    // |z| = 1: z^5 = z^6 conj(z), z^7 = z^6 z
+                    s5r += __fma_rn(z6r, zr, __dmul_rn(z6i, zi));
+                    s5i += __fma_rn(z6i, zr, -__dmul_rn(z6r, zi));
+                    s6r += z6r;
+                    s6i += z6i;
+                    s7r += __fma_rn(z6r, zr, -__dmul_rn(z6i, zi));
+                    s7i += __fma_rn(z6r, zi, __dmul_rn(z6i, zr));
+                }
+            }
+        }
+        double q5 = 0.0, q6 = 0.0, q7 = 0.0, arg = 0.0;
+        if (nb > 0) {
+            const double inv_n = 1.0 / (double)nb;
+            auto modulus = [&](double re, double im) {   // |re + i im| / n  (no overflow: |sum| <= n)
+                const double m2 = __fma_rn(re, re, __dmul_rn(im, im));
+                return __dmul_rn(__dsqrt_rn(m2), inv_n);
+            };
+            q5 = modulus(s5r, s5i);
+            q6 = modulus(s6r, s6i);
+            q7 = modulus(s7r, s7i);
+            arg = atan2(s6i, s6r);
+        }
+        // Two FULL-sector stores by particle id.  (Five scattered 8-/4-byte stores cost 60 us at N = 10^6:
+        // a partial write to a sector that is not in L2 makes L2 fetch it from DRAM first.)
+        double4 *dst = ba.rec + 2 * (size_t)id;
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(q5), "d"(q6), "d"(q7), "d"(arg) : "memory");
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%2,%2,%2,%2,%2,%2};" ::"l"(dst + 1), "r"(nb), "r"(0) : "memory");
+    }
+}
+
+// the ABI's five psi6 arrays from the records (one coalesced pass)
+__global__ void __launch_bounds__(256)
+k_unpack_boop(int n, const double4 *__restrict__ rec, double *__restrict__ q5, double *__restrict__ q6,
+              double *__restrict__ q7, double *__restrict__ q6arg, int32_t *__restrict__ nbr)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 v = ld_sector(rec + 2 * (size_t)i);
+    const int nb = *reinterpret_cast<const int *>(rec + 2 * (size_t)i + 1);
+    q5[i] = v.x;
+    q6[i] = v.y;
+    q7[i] = v.z;
+    q6arg[i] = v.w;
+    nbr[i] = nb;
 }
 
 // the ABI's five prediction arrays from the event records (one coalesced pass)
@@ -646,37 +860,78 @@ int edmd_launch_unpack_events(edmd_ctx *c)
     return 1;
 }
 
-int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between)
+// P1 alone: (re)build the tile buckets of the resident state
+int edmd_launch_tile_partition(edmd_ctx *c)
 {
     if (c->n == 0) return 0;
-    const TileGeom &tg = c->tgeom;
     PartArgs pa;
     pa.first = 0; pa.n = c->n; pa.ps = c->ps; pa.slab = c->slab ? 1 : 0; pa.dbg = c->tile_dbg;
-    pa.tg = tg; pa.b = c->dbox;
+    pa.tg = c->tgeom; pa.b = c->dbox;
     pa.cid = c->cid; pa.xv = c->xv; pa.rad = c->rad; pa.rad0 = c->rad0;
     pa.flags = c->flags; pa.tcnt = c->tcnt; pa.tst = c->tst; pa.ttag = c->ttag; pa.trad = c->trad;
     pa.overlap_key = c->overlap_key;
     // the first kernel of the chain is launched plainly: whatever precedes it on the stream completes first
     edmd_launch(k_tile_partition, dim3((c->n + kPartThreads - 1) / kPartThreads), dim3(kPartThreads), 0, c->stream,
                 false, pa);
-    if (between) cudaEventRecord(between, c->stream);
+    return 1;
+}
+
+static SweepArgs sweep_args(edmd_ctx *c)
+{
     SweepArgs sa;
-    sa.tg = tg; sa.b = c->dbox; sa.t = c->t; sa.rad0 = c->rad0; sa.n_owned = c->n_owned;
+    sa.tg = c->tgeom; sa.b = c->dbox; sa.t = c->t; sa.rad0 = c->rad0; sa.n_owned = c->n_owned;
     sa.tiles = nullptr;
     sa.dbg = c->tile_dbg;
     sa.rad_smem = c->lean_two ? 1 : 0;   // the host's knowledge; the kernel declines if the device knows better
     sa.gid = c->slab ? c->gid : nullptr;
-    sa.flags = c->flags; sa.tcnt = c->tcnt; sa.tst = c->tst; sa.ttag = c->ttag; sa.trad = c->trad;
+    sa.flags = c->flags; sa.tcnt = c->tcnt; sa.tkeep = c->tkeep; sa.tst = c->tst; sa.ttag = c->ttag; sa.trad = c->trad;
     sa.ev = c->evrec;
     sa.overlap_key = c->overlap_key;
-    const size_t smem = tile_smem_bytes(tg, sa.rad_smem);
+    return sa;
+}
+
+static void tile_attrs()
+{
     static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr = true;
-    }
-    edmd_launch(k_tile_sweep, dim3(tg.ntx * tg.nty), dim3(kTileThreads), smem, c->stream, c->lean_pdl, sa);
+    if (attr) return;
+    cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_tile_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_tile_boop, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_tile_boop, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    attr = true;
+}
+
+int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between)
+{
+    if (c->n == 0) return 0;
+    edmd_launch_tile_partition(c);
+    if (between) cudaEventRecord(between, c->stream);
+    const SweepArgs sa = sweep_args(c);
+    tile_attrs();
+    edmd_launch(k_tile_sweep, dim3(c->tgeom.ntx * c->tgeom.nty), dim3(kTileThreads), tile_smem_bytes(c->tgeom, sa.rad_smem),
+                c->stream, c->lean_pdl, sa);
     c->pred_packed = true;
+    return 2;
+}
+
+// K4 on the tile buckets; from_keep: the buckets were consumed once already (run lengths in tkeep[])
+int edmd_launch_tile_boop(edmd_ctx *c, double r_c, bool from_keep)
+{
+    if (c->n == 0) return 0;
+    const size_t N = (size_t)c->n;
+    BoopTileArgs ba;
+    ba.s = sweep_args(c);
+    ba.from_keep = from_keep ? 1 : 0;
+    ba.rc2 = r_c * r_c;   // `r_c*r_c`, a single rounded product
+    ba.rec = c->boop_rec;
+    tile_attrs();
+    const size_t smem = (size_t)c->tgeom.smem_cap * 20 + sizeof(uint2) * kFC + tile_aliased_bytes(c->tgeom.smem_cap) +
+                        sizeof(int) * (kTileWarps + kFH + 4) + 16;
+    edmd_launch(k_tile_boop, dim3(c->tgeom.ntx * c->tgeom.nty), dim3(kTileThreads), smem, c->stream,
+                c->lean_pdl && !from_keep, ba);
+    // halo copies of a slab context are not computed: the unpack covers the owned particles
+    const int no = c->n_owned;
+    k_unpack_boop<<<(no + 255) / 256, 256, 0, c->stream>>>(no, c->boop_rec, c->boop, c->boop + N, c->boop + 2 * N,
+                                                           c->boop + 3 * N, c->boop_nb);
     return 2;
 }

@@ -103,6 +103,8 @@ uint64_t edmd_cuda_launch_count(const edmd_ctx *ctx);
 /* EDMD_OPT_NO_TILE = 1 keeps eligible sweeps off the two-kernel tile sweep (tile_sweep.cu)
  * and on the older five-kernel lean chain (cross-checking and timing). */
 #define EDMD_OPT_NO_TILE 6
+/* EDMD_OPT_NO_TILE_BOOP = 1 keeps psi6 (edmd_cuda_boop_cutoff) on the row kernel over the full cell index. */
+#define EDMD_OPT_NO_TILE_BOOP 7
 /* One particle's two scheduled events as the tile sweep leaves them on the device: exactly what
  * addCrossingEvent / addCollisionEvent store into eventList[i] / eventList[N+i]
  * (src/EDMD.c:2487-2496, 3286-3297), one 32-byte record per particle. */

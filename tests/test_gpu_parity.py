@@ -811,6 +811,31 @@ def test_tile_sweep_equals_lean_chain_and_full_path(pkg, n, phi, seed, sf, vscal
         assert np.array_equal(b[k], d[k]), k
 
 
+@pytest.mark.parametrize("n,phi,seed,sf", [(300000, 0.70, 251, 0.0), (200000, 0.85, 252, 0.0), (100000, 0.72, 253, 0.3)])
+def test_tile_psi6_equals_row_kernel(pkg, oracle, n, phi, seed, sf):
+    """psi6 on the tile buckets (fresh partition, and re-using the buckets of a sweep) gives the
+    same values as the row kernel over the full cell index (to 1e-13), and the oracle's."""
+    c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf, shuffle=True)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        a = ctx.boop_cutoff(2.5)              # partition + tile kernel
+        ctx.predict_all()
+        b = ctx.boop_cutoff(2.5)              # buckets of the sweep, run lengths from the kept copy
+        b2 = ctx.boop_cutoff(2.5)
+        ctx.set_option(pkg.binding.OPT_NO_TILE_BOOP, 1)
+        d = ctx.boop_cutoff(2.5)              # row kernel
+    # the tile kernel is reproducible bit for bit (cells sorted by id, fixed summation order) ...
+    for k in ("q5", "q6", "q7", "q6_arg", "neighbors"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], b2[k]), k
+    # ... and agrees with the row kernel (2^-48 fixed-point sums) far inside the 1e-10 gate
+    assert np.array_equal(a["neighbors"], d["neighbors"])
+    for k in ("q5", "q6", "q7"):
+        assert np.abs(a[k] - d[k]).max() < 1e-13, k
+    assert_boop_close(a, d)
+    assert_boop_close(a, oracle.boop_cutoff(c["n"], c["lx"], c["ly"], c["x"], c["y"], 2.5))
+
+
 def test_tile_sweep_declines_when_a_bucket_overflows(pkg, oracle):
     """All particles of a dilute system crowded into one corner of the box: the bucket of
     that tile overflows its fixed capacity, the sweep declines on the device and the call

@@ -18,6 +18,7 @@ to the oracle port when _ref is absent) on the host cores.
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -219,7 +220,7 @@ def run_reference(args, cfg):
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": workload_config(cfg),
+        "config": workload_config(cfg, args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
                          "sample": f"{steps} full re-predict sweeps of the N={n} snapshot "
                                    "(single-threaded, as the reference ships)"},
@@ -228,9 +229,11 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
-def workload_config(cfg):
+def workload_config(cfg, gpus=1):
+    which = "BASELINE configs[2]" if gpus == 1 else \
+        f"{gpus} x BASELINE configs[2] in one periodic box (configs[3] at 4 GPUs)"
     return {"workload": f"N={cfg['n']} phi={PHI} monodisperse liquid-density jittered-lattice "
-                        f"snapshot, {cfg.get('order', 'shuffled')} ids, full re-predict sweep (BASELINE configs[2])",
+                        f"snapshot, {cfg.get('order', 'shuffled')} ids, full re-predict sweep ({which})",
             "n_particles": cfg["n"], "phi": PHI, "seed": SEED,
             "box": [cfg["lx"], cfg["ly"]],
             "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB written then {L2_FLUSH_BYTES >> 20} MiB "
@@ -248,78 +251,119 @@ def profile_traffic():
     return None
 
 
+def slab_sweep_ms(pkg, dist, torch, cfg, rank, world, local, steps, warm):
+    """Device-resident multi-GPU step of one system: ms per step (max over ranks), K1 part, n_owned."""
+    slab = pkg.slab
+    N, lx, ly = cfg["n"], cfg["lx"], cfg["ly"]
+    fx, fy = 1.0 / (lx / int(lx / 2)), 1.0 / (ly / int(ly / 2))     # cellxFac, cellyFac (src/EDMD.c:694-706)
+    cells = np.stack([(cfg["x"] * fx).astype(np.int32), (cfg["y"] * fy).astype(np.int32)], 1)
+    sr = slab.SlabRank(pkg, N, lx, ly, rank, world, local)
+    sr.connect_p2p(dist)   # halo = peer stores over NVLink (csrc/halo.cu)
+    gid = sr.load_owned(cfg, cells, 0.0)
+    sr.exchange(dist)
+    dist.barrier()
+    torch.cuda.synchronize()
+    tot, main = sr.ctx.bench(pkg.binding.BENCH_SWEEP, warmup=warm, iters=steps, flush_bytes=L2_FLUSH_BYTES)
+    return sr, gid, cells, tot, main
+
+
 def run_slabs(args, pkg, rank, world, local):
     """N > 1: weak scaling -- the system is N x 1M disks in one periodic box, cut
     into N row slabs of the cell grid (one per GPU).  A step = halo exchange
-    (boundary rows packed and stored straight into the neighbours' memory over
-    NVLink) + K0 + K1 on every rank, all inside the CUDA-event bracket; outputs
-    are disjoint, no collective on the data path."""
+    (boundary rows stored straight into the neighbours' memory over NVLink, on a
+    second stream beside the partition of the owned particles) + K0 + K1 on every
+    rank, all inside the CUDA-event bracket; outputs are disjoint, no collective
+    on the data path.  Plus: psi6 per slab with the mean q6 all-reduced, g(r)
+    split over the ranks, and the STRONG-scaling point of BASELINE configs[3]
+    (N = 4*10^6 fixed, on this many GPUs)."""
     import torch
     import torch.distributed as dist
 
-    slab = pkg.slab
     B = pkg.binding
     n_total = args.n * world
     cfg = pkg.synth.lattice_config(n_total, PHI, SEED, shuffle=(args.order == "shuffled"))
     N, lx, ly = cfg["n"], cfg["lx"], cfg["ly"]
-    fx, fy = 1.0 / (lx / int(lx / 2)), 1.0 / (ly / int(ly / 2))     # cellxFac, cellyFac (src/EDMD.c:694-706)
-    cells = np.stack([(cfg["x"] * fx).astype(np.int32), (cfg["y"] * fy).astype(np.int32)], 1)
     steps, warm = args.steps, max(args.warmup, 3)
-    sr = slab.SlabRank(pkg, N, lx, ly, rank, world, local)
-    sr.connect_p2p(dist)   # halo = peer stores over NVLink from the pack kernel (csrc/halo.cu)
 
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
 
-    gid = sr.load_owned(cfg, cells, 0.0)
-    n_owned = len(gid)
-    halo_bytes = sr.exchange(dist)
-    _, n_local = sr.ctx.counts()
-    barrier()
-    l0 = sr.ctx.launches
     with ClockSampler(local) as clk:
-        tot, main = sr.ctx.bench(B.BENCH_SWEEP, warmup=warm, iters=steps, flush_bytes=L2_FLUSH_BYTES)
-        launches_timed = (sr.ctx.launches - l0) * steps // (steps + warm)
-        own = {}
-        keep = []
+        sr, gid, cells, tot, main = slab_sweep_ms(pkg, dist, torch, cfg, rank, world, local, steps, warm)
+        n_owned = len(gid)
+        halo_bytes = 2 * sr.halo_capacity * 48
+        _, n_local = sr.ctx.counts()
+        l0 = sr.ctx.launches
+        sr.ctx.bench(B.BENCH_SWEEP, warmup=0, iters=1, flush_bytes=0)
+        launches_per_step = sr.ctx.launches - l0
+        # ---- end to end: pinned host buffers -> upload owned, exchange + sweep (one device sequence),
+        # results into pinned host buffers; every call goes through the C ABI
+        keep, own = [], {}
         for k in ("x", "y", "vx", "vy", "rad"):
             tpin = torch.from_numpy(np.ascontiguousarray(cfg[k][gid])).pin_memory()
             keep.append(tpin)
             own[k] = tpin.numpy()
-        tpin = torch.from_numpy(np.ascontiguousarray(cells[gid])).pin_memory()
-        keep.append(tpin)
-        own_cells = tpin.numpy()
-        barrier()
-        # end to end: host buffers -> upload owned, exchange, sweep, results back on the host
+        for k, a in (("cells", cells[gid]), ("gid", gid.astype(np.int32))):
+            tpin = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            keep.append(tpin)
+            own[k] = tpin.numpy()
+        outs = {}
+        for k, dt in (("t_cross", torch.float64), ("dir", torch.uint8), ("t_coll", torch.float64), ("partner", torch.int32)):
+            tpin = torch.empty(n_owned, dtype=dt).pin_memory()
+            keep.append(tpin)
+            outs[k] = tpin.numpy()
+        ov = np.zeros(2, np.int32)
+        lib, h, P = sr.ctx.lib, sr.ctx._h, B._ptr
+
+        def e2e_step():
+            rc = lib.edmd_cuda_upload_owned(h, n_owned, P(own["x"]), P(own["y"]), P(own["vx"]), P(own["vy"]),
+                                            P(own["rad"]), P(own["cells"]), P(own["gid"]), 0.0)
+            assert rc == 0, lib.edmd_cuda_last_error(h)
+            rc = lib.edmd_cuda_exchange_predict_device(h, B.MODE_NORMAL)
+            assert rc == 0, lib.edmd_cuda_last_error(h)
+            rc = lib.edmd_cuda_fetch_predictions(h, P(outs["t_cross"]), P(outs["dir"]), P(outs["t_coll"]),
+                                                 P(outs["partner"]), None, P(ov))
+            assert rc == 0, lib.edmd_cuda_last_error(h)
+
         e2e = []
         for it in range(3 + steps):
             barrier()
             t0 = time.perf_counter()
-            sr.ctx.upload_owned(own["x"], own["y"], own["vx"], own["vy"], own["rad"], own_cells, gid, t=0.0)
-            sr.exchange(dist)
-            sr.predict()
+            e2e_step()
             if it >= 3:
                 e2e.append(time.perf_counter() - t0)
         barrier()
+        # ---- psi6 of every slab (halo rows of the last exchange supply the cross-boundary neighbours)
+        bt, bm = sr.ctx.bench(B.BENCH_BOOP, dr=2.5, warmup=3, iters=10, flush_bytes=L2_FLUSH_BYTES)
+        bo = sr.boop(dist, N)
     clocks = clk.summary()
     ms_step, ms_k1, ms_e2e = float(np.mean(tot)), float(np.mean(main)), 1e3 * float(np.mean(e2e))
+    ms_psi6 = float(np.mean(bt))
     # BASELINE configs[3] second half: g(r) of the whole N-GPU system, pairs split over the ranks
     ms_gr, gr_pairs = 0.0, 0
     if args.analysis == "full":
         max_r = min(lx, ly) / 2
         counts, ms_gr = sr.pcf(dist, cfg["x"][gid], cfg["y"][gid], N, 0.1, max_r)
         gr_pairs = int(counts.sum())
-    tt = torch.tensor([ms_step, ms_k1, ms_e2e, float(n_local), ms_gr], device="cuda", dtype=torch.float64)
+    sr.close()
+    # ---- strong scaling of BASELINE configs[3]: N = 4*10^6 fixed on `world` GPUs
+    n_strong = 4 * args.n
+    cfg4 = cfg if world == 4 else pkg.synth.lattice_config(n_strong, PHI, SEED, shuffle=(args.order == "shuffled"))
+    sr4, gid4, _, tot4, main4 = slab_sweep_ms(pkg, dist, torch, cfg4, rank, world, local, steps, warm)
+    sr4.close()
+    ms_strong = float(np.mean(tot4))
+    tt = torch.tensor([ms_step, ms_k1, ms_e2e, float(n_local), ms_gr, ms_psi6, ms_strong], device="cuda",
+                      dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_step, ms_k1, ms_e2e, n_local_max, ms_gr = tt.tolist()
+    ms_step, ms_k1, ms_e2e, n_local_max, ms_gr, ms_psi6, ms_strong = tt.tolist()
     if rank == 0:
         peak, how = peaks()
         achieved = BYTES_PER_PARTICLE * n_owned / (ms_k1 * 1e-3) / 1e9
-        wc = workload_config({**cfg, "order": args.order})
-        wc["workload"] = (f"N={N} phi={PHI} ({world} x {args.n} disks, one periodic box), row slabs of the cell grid, "
-                          f"one-cell-row halo by peer stores over NVLink, full re-predict sweep (BASELINE configs[3] at 4 GPUs)")
-        wc["parallelism"] = f"{world} row slabs, halo {halo_bytes} B/rank/step, no data-path collective"
+        wc = workload_config({**cfg, "order": args.order}, world)
+        wc["parallelism"] = (f"{world} row slabs of the cell grid, one-cell-row halo by peer stores over NVLink "
+                             f"({halo_bytes} B/rank/step inbox capacity) on a second stream beside the partition, "
+                             f"no data-path collective")
         wc["step_breakdown_ms"] = {"halo_exchange_plus_K0": ms_step - ms_k1, "K1": ms_k1}
         line = {
             "metric": METRIC, "value": N / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -327,23 +371,54 @@ def run_slabs(args, pkg, rank, world, local):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wc,
             "clocks": clocks,
             "e2e": {"value": N / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 52 * n_owned, "d2h_bytes_per_step": 22 * n_owned,
-                    "api": "edmd_cuda_upload_owned + halo exchange + edmd_cuda_predict_all per rank"},
-            "gpu_launches": int(launches_timed) * world,
-            "roofline": {"bound": "hbm", "kernel": "k_predict_rows (K1), rank 0", "achieved": achieved,
+                    "h2d_bytes_per_step": 52 * n_owned, "d2h_bytes_per_step": 21 * n_owned,
+                    "api": "per rank, pinned host buffers: edmd_cuda_upload_owned(x,y,vx,vy,rad,cells,ids) + "
+                           "edmd_cuda_exchange_predict_device + edmd_cuda_fetch_predictions(t_cross,dir,t_coll,partner)"},
+            "gpu_launches": int(launches_per_step) * steps * world,
+            "roofline": {"bound": "hbm", "kernel": "k_tile_sweep (K1 of the tile sweep), rank 0", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": how + " (burst copy)", "traffic": profile_traffic(),
+                         "peak_source": how + " (burst copy)", "traffic": None,
                          "ms_kernel": ms_k1, "bytes_per_particle": BYTES_PER_PARTICLE},
+            "strong_scaling_4M": {"n_particles": cfg4["n"], "n_gpus": world, "ms_per_step": ms_strong,
+                                  "particles_per_s": cfg4["n"] / (ms_strong * 1e-3),
+                                  "note": "BASELINE configs[3]: the same N = 4*10^6 phi = 0.70 system on 1/2/4/8 GPUs; "
+                                          "efficiency = t(1 GPU) / (n_gpus * t(n_gpus)) across the lines of the scaling run"},
+            "analysis": {"psi6_ms": ms_psi6, "psi6_particles_per_s": N / (ms_psi6 * 1e-3),
+                         "mean_q6_all_reduced": bo["mean_q6_global"],
+                         "psi6_note": "computeBOOPCutoff per slab (partition + tile kernel + unpack, max over ranks); "
+                                      "the per-rank q6 sums are all-reduced (NCCL) into the thermo column's mean q6"},
         }
         if args.analysis == "full":
-            line["analysis"] = {
+            line["analysis"].update({
                 "gr_full_ms": ms_gr, "gr_full_bins": int(min(lx, ly) / 2 / 0.1),
                 "gr_full_pairs_per_s": N * (N - 1) / 2 / (ms_gr * 1e-3), "gr_pairs_binned": gr_pairs,
                 "note": "calculate_pcf dr=0.1 max_r=min(L)/2 of the whole system: all-gather of the positions "
                         "(NCCL) + sorted-tile kernel on the tile pairs w = rank (mod N) + all-reduce of the "
-                        "counts, CUDA events, max over ranks"}
+                        "counts, CUDA events, max over ranks"})
         print(json.dumps(line, default=float))
-    sr.close()
+
+
+def bench_config(pkg, local, name, n, phi, sf, steps, warm, with_psi6=True):
+    """Sweep (+ psi6) timing of one more BASELINE configuration on one GPU."""
+    B = pkg.binding
+    c = pkg.synth.lattice_config(n, phi, SEED, small_fraction=sf, shuffle=True)
+    peak, _ = peaks()
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"], device=local) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        r0 = ctx.stat(B.STAT_EXACT_RESCANS)
+        tot, main = ctx.bench(B.BENCH_SWEEP, warmup=warm, iters=steps, flush_bytes=L2_FLUSH_BYTES)
+        rescans = (ctx.stat(B.STAT_EXACT_RESCANS) - r0) / (steps + warm)
+        out = {"config": name, "n_particles": c["n"], "phi": phi, "small_fraction": sf,
+               "ms_per_step": float(np.mean(tot)), "particles_per_s": c["n"] / (float(np.mean(tot)) * 1e-3),
+               "k1_ms": float(np.mean(main)),
+               "k1_hbm_frac": BYTES_PER_PARTICLE * c["n"] / (float(np.mean(main)) * 1e-3) / 1e9 / peak,
+               "exact_rescans_per_sweep": rescans,
+               "tile_sweep": bool(ctx.stat(B.STAT_LEAN_ELIGIBLE) and not ctx.stat(B.STAT_LEAN_DECLINES))}
+        if with_psi6:
+            bt, bm = ctx.bench(B.BENCH_BOOP, dr=2.5, warmup=2, iters=5, flush_bytes=L2_FLUSH_BYTES)
+            out["psi6_ms"] = float(np.mean(bt))
+            out["psi6_kernel_ms"] = float(np.mean(bm))
+    return out
 
 
 def run_ours(args, cfg):
@@ -392,15 +467,33 @@ def run_ours(args, cfg):
     ov = np.zeros(2, np.int32)
     lib, h = ctx.lib, ctx._h
     P = B._ptr
+    # the host's cell[2] of every particle (the mid-run form of the upload: include/edmd_cuda.h)
+    fx, fy = 1.0 / (cfg["lx"] / int(cfg["lx"] / 2)), 1.0 / (cfg["ly"] / int(cfg["ly"] / 2))
+    t, host["cells"] = pinned(np.stack([(cfg["x"] * fx).astype(np.int32), (cfg["y"] * fy).astype(np.int32)], 1))
+    keep.append(t)
+    # calendar geometry of the reference (boxConstantHelper: dtPaul = 5/N, paulListN = N)
+    cal = {}
+    for k, m in (("bucket", 2 * n), ("next", 2 * n), ("prev", 2 * n), ("head", n + 1)):
+        t = torch.empty(m, dtype=torch.int32).pin_memory()
+        keep.append(t)
+        cal[k] = t.numpy()
+    n_tree = C.c_int32(0)
 
     def e2e_step():
-        # a thermostat tick: positions and velocities up (radii are unchanged: rad = NULL),
-        # crossing + collision events down (ctype is the constant COLLISION: not fetched)
+        # a thermostat tick: positions, velocities and the host's cells up (radii are unchanged:
+        # rad = NULL), crossing + collision events down (ctype is the constant COLLISION: not fetched)
         rc = lib.edmd_cuda_upload(h, P(host["x"]), P(host["y"]), P(host["vx"]), P(host["vy"]),
-                                  None, None, 0.0)
+                                  None, P(host["cells"]), 0.0)
         assert rc == 0, lib.edmd_cuda_last_error(h)
         rc = lib.edmd_cuda_predict_all(h, B.MODE_NORMAL, None, P(outs["t_cross"]), P(outs["dir"]),
                                        P(outs["t_coll"]), P(outs["partner"]), None, P(ov))
+        assert rc == 0, lib.edmd_cuda_last_error(h)
+
+    def plan_step():
+        # the calendar ingest plan of those events (edmd_cuda_calendar_plan), downloaded: what the host
+        # needs to rebuild its calendar in one streaming pass instead of 2N addEventToQueue calls
+        rc = lib.edmd_cuda_calendar_plan(h, C.c_double(0.0), C.c_double(5.0 / n), n, 17, P(cal["bucket"]),
+                                         P(cal["next"]), P(cal["prev"]), P(cal["head"]), C.byref(n_tree))
         assert rc == 0, lib.edmd_cuda_last_error(h)
 
     ctx.upload(host["x"], host["y"], host["vx"], host["vy"], host["rad"], t=0.0)
@@ -415,12 +508,16 @@ def run_ours(args, cfg):
         # ---- end to end through the C ABI, host buffers ------------------
         for _ in range(3):
             e2e_step()
+            plan_step()
         barrier()
-        e2e_times = []
+        e2e_times, plan_times = [], []
         for _ in range(steps):
             t0 = time.perf_counter()
             e2e_step()
-            e2e_times.append(time.perf_counter() - t0)
+            t1 = time.perf_counter()
+            plan_step()
+            e2e_times.append(t1 - t0)
+            plan_times.append(time.perf_counter() - t1)
         barrier()
     clocks = clk.summary()
 
@@ -435,10 +532,26 @@ def run_ours(args, cfg):
     # ---- per-frame analysis (rank-local; reported, not the headline) -----
     analysis = {}
     if args.analysis != "none" and rank == 0:
-        bt, _ = ctx.bench(B.BENCH_BOOP, dr=2.5, warmup=3, iters=10, flush_bytes=L2_FLUSH_BYTES)
+        bt, bm = ctx.bench(B.BENCH_BOOP, dr=2.5, warmup=3, iters=10, flush_bytes=L2_FLUSH_BYTES)
         analysis["psi6_ms"] = float(np.mean(bt))
+        analysis["psi6_kernel_ms"] = float(np.mean(bm))
         analysis["psi6_particles_per_s"] = float(n / (np.mean(bt) * 1e-3))
         analysis["psi6_hbm_frac"] = 56.0 * n / (np.mean(bt) * 1e-3) / 1e9 / peaks()[0]
+        # the same frame right after a sweep: the tile buckets are re-used, no partition, no re-index
+        ctx.predict_device()
+        ctx.stat(B.STAT_EXACT_RESCANS)
+        torch.cuda.synchronize()
+        reuse = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            lib.edmd_cuda_boop_cutoff(h, C.c_double(2.5), None, None, None, None, None, None)
+            reuse.append(time.perf_counter() - t0)
+        analysis["psi6_after_sweep_wall_ms"] = float(np.median(reuse) * 1e3)
+        analysis["psi6_roofline"] = {
+            "bound": "fp64 pipe (not HBM: 56 B/particle is 0.06 % of a millisecond of HBM traffic)",
+            "fp64_ops_per_particle": "~6 neighbours x ~40 (distance, 1/r by Newton, z^2 z^4 z^6, z^5 z^7, six sums) "
+                                     "+ ~2.3 rejected candidates x 8 + ~150 (three moduli, atan2)",
+            "hbm_frac": analysis["psi6_hbm_frac"]}
         max_r_cut = 12.0
         if world == 1:
             # K5: Voronoi psi6 + cell area / perimeter (computeBOOPVoronoi, get_particle_voronoi_area)
@@ -469,6 +582,14 @@ def run_ours(args, cfg):
             analysis["gr_full_pairs_per_s"] = pairs / (float(np.mean(pt)) * 1e-3)
             analysis["gr_full_reference_op_rate_tflops_9op"] = 9 * pairs / (float(np.mean(pt)) * 1e-3) / 1e12
             analysis["frames_per_s_gr_full_plus_psi6"] = 1e3 / (float(np.mean(pt)) + np.mean(bt))
+            analysis["gr_roofline"] = {
+                "bound": "instruction issue + shared-memory atomics (positions fit L2; bytes negligible)",
+                "pairs": pairs, "instructions_per_pair": 10,
+                "fp64_equivalent_tflops_9op": 9 * pairs / (float(np.mean(pt)) * 1e-3) / 1e12,
+                "fp64_peak_tflops_nominal": 37.0,
+                "frac_of_nominal_fp64_peak": 9 * pairs / (float(np.mean(pt)) * 1e-3) / 1e12 / 37.0,
+                "note": "SURVEY 8d counts 9 FP64 operations per pair for the reference's arithmetic; the kernel decides "
+                        "99.6 % of the pairs in FP32 (certified), so the FP64 pipe itself is ~1 % busy"}
             # the same frame with every bin certified in FP64 (the previous default kernel):
             # its time, and the two histograms compared bin by bin at full size
             e0 = ctx.stat(B.STAT_PCF_EXACT_PAIRS)
@@ -508,6 +629,21 @@ def run_ours(args, cfg):
                 lp, _ = lctx.bench(B.BENCH_PCF, dr=0.1, max_r=min(lc["lx"], lc["ly"]) / 2, warmup=1, iters=1)
                 liquid["gr_full_ms"] = float(lp[0])
 
+    # ---- the other BASELINE configurations + the strong-scaling point of configs[3] on this one GPU ----
+    others, strong = [], None
+    if rank == 0 and world == 1 and args.analysis != "none":
+        ctx.close()
+        ctx = None
+        for name, nn, phi, sf in (("configs[1]: N=100000 phi=0.72 near liquid-hexatic", 100000, 0.72, 0.0),
+                                  ("configs[4]: N=1000000 phi=0.85 dense crystal", n, 0.85, 0.0),
+                                  ("reference CLI default mixture (30 % of radius 0.4) at N=1000000 phi=0.70", n, 0.70, 0.3)):
+            others.append(bench_config(pkg, local, name, nn, phi, sf, steps, warm))
+        st = bench_config(pkg, local, "configs[3] on one GPU", 4 * n, PHI, 0.0, steps, warm, with_psi6=False)
+        strong = {"n_particles": st["n_particles"], "n_gpus": 1, "ms_per_step": st["ms_per_step"],
+                  "particles_per_s": st["particles_per_s"],
+                  "note": "BASELINE configs[3]: the same N = 4*10^6 phi = 0.70 system on 1/2/4/8 GPUs; "
+                          "efficiency = t(1 GPU) / (n_gpus * t(n_gpus)) across the lines of the scaling run"}
+
     cpu = cpu_baseline(cfg) if (rank == 0 and world == 1 and not args.no_cpu) else None
 
     if rank == 0:
@@ -520,11 +656,20 @@ def run_ours(args, cfg):
             "dtype": "f64", "data": "synthetic", "config": workload_config(cfg),
             "clocks": clocks,
             "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 21 * n,
-                    "api": "edmd_cuda_upload(x,y,vx,vy; radii resident) + edmd_cuda_predict_all"
-                           "(t_cross,dir,t_coll,partner), pinned host buffers"},
+                    "h2d_bytes_per_step": 40 * n, "d2h_bytes_per_step": 21 * n,
+                    "api": "edmd_cuda_upload(x,y,vx,vy,cell_xy; radii resident) + edmd_cuda_predict_all"
+                           "(t_cross,dir,t_coll,partner), pinned host buffers",
+                    "pcie_gb_per_s": 61 * n / (e2e_ms * 1e-3) / 1e9,
+                    "calendar_plan_ms": float(np.mean(plan_times)) * 1e3,
+                    "calendar_plan_d2h_bytes": 4 * (6 * n + n + 1),
+                    "ms_per_tick_with_calendar_plan": e2e_ms + float(np.mean(plan_times)) * 1e3,
+                    "note": "a tick = upload (40 B/particle incl. the host's cells) + sweep + download (21 B/particle); "
+                            "upload and download cannot overlap (the results depend on every particle), so the tick is "
+                            "PCIe-serial: pcie_gb_per_s is the link rate it achieves.  calendar_plan_ms = the device's "
+                            "ingest plan + its 28 B/particle download, timed next to it (the reference arm's loop "
+                            "includes its calendar remove/insert)"},
             "gpu_launches": int(launches_timed),
-            "roofline": {"bound": "hbm", "kernel": "K1 = k_screen + k_resolve (lean sweep)",
+            "roofline": {"bound": "hbm", "kernel": "K1 = k_tile_sweep (bin + screen + resolve, one CTA per tile)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": how + " (burst copy)",
                          "traffic": profile_traffic(),
@@ -535,12 +680,17 @@ def run_ours(args, cfg):
             line["config"]["parallelism"] = f"{world} independent replicas (slab path: see DESIGN.md)"
         if liquid:
             line["liquid_input"] = liquid
+        if others:
+            line["configs"] = others
+        if strong:
+            line["strong_scaling_4M"] = strong
         if cpu:
             line["cpu_baseline"] = cpu
         if world == 1 and not args.no_cpu:
             line["end_to_end"] = end_to_end_coll_rate()
         print(json.dumps(line, default=float))
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -565,7 +715,9 @@ def main():
     if args.impl != "reference" and world > 1:
         run_ours(args, None)
         return
-    cfg = pkg.synth.lattice_config(args.n, PHI, SEED, shuffle=(args.order == "shuffled"))
+    # the reference arm sweeps the SAME system as our arm: N x 10^6 disks in one box at --gpus N
+    n_sys = args.n * (args.gpus if args.impl == "reference" else 1)
+    cfg = pkg.synth.lattice_config(n_sys, PHI, SEED, shuffle=(args.order == "shuffled"))
     cfg["order"] = args.order
     if args.impl == "reference":
         run_reference(args, cfg)

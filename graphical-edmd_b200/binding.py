@@ -47,6 +47,7 @@ SYMBOLS = [
     "edmd_cuda_create_slab", "edmd_cuda_upload_owned", "edmd_cuda_halo_pack",
     "edmd_cuda_halo_append", "edmd_cuda_get_counts", "edmd_cuda_pcf_device",
     "edmd_cuda_halo_export", "edmd_cuda_halo_connect", "edmd_cuda_halo_exchange",
+    "edmd_cuda_exchange_predict_device",
     "edmd_cuda_calendar_plan", "edmd_cuda_pcf_bond_order", "edmd_cuda_bragg_peak",
     "edmd_cuda_boop_voronoi", "edmd_cuda_voronoi_cells", "edmd_cuda_g6_correlation",
     "edmd_cuda_structure_factor", "edmd_cuda_kinetic", "edmd_cuda_rescale_velocities",
@@ -114,6 +115,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_halo_export.argtypes = [vp, C.c_int, C.c_char_p]
     lib.edmd_cuda_halo_connect.argtypes = [vp, C.c_char_p, C.c_char_p]
     lib.edmd_cuda_halo_exchange.argtypes = [vp]
+    lib.edmd_cuda_exchange_predict_device.argtypes = [vp, C.c_int]
     lib.edmd_cuda_pcf_device.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, vp,
                                          C.POINTER(C.c_int)]
     lib.edmd_cuda_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -254,6 +256,10 @@ class EdmdCuda:
 
     def halo_exchange(self):
         self._check(self.lib.edmd_cuda_halo_exchange(self._h))
+
+    def exchange_predict_device(self, mode=MODE_NORMAL):
+        """Halo exchange + sweep as one stream-ordered sequence (transfer hidden behind the partition)."""
+        self._check(self.lib.edmd_cuda_exchange_predict_device(self._h, mode))
 
     def counts(self):
         a, b = C.c_int(0), C.c_int(0)

@@ -245,7 +245,7 @@ int edmd_launch_boop(edmd_ctx *c, double r_c)
 {
     int n = c->n;
     if (n == 0) return 0;
-    size_t N = (size_t)n;
+    size_t N = (size_t)c->n_cap;   // the four psi6 arrays lie n_cap apart
     BoopArgs a;
     a.b = c->dbox;
     a.g = edmd_cell_index(c);

@@ -226,6 +226,11 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int k = 0; k < 4; k++) CU(cudaEventCreateWithFlags(&c->ev[k], cudaEventDisableTiming));
+    if (slab) {
+        CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
     size_t N = (size_t)n;
     int r;
     if ((r = dev_alloc(c, &c->in_soa, 5 * N))) return r;
@@ -318,6 +323,7 @@ int edmd_cuda_create_slab(int device, int n_capacity, double lx, double ly, int 
 void edmd_cuda_destroy(edmd_ctx *c)
 {
     if (!c) return;
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->gid, c->cell_cnt,
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
@@ -335,6 +341,9 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (int k = 0; k < 4; k++)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -596,6 +605,67 @@ int edmd_cuda_halo_exchange(edmd_ctx *c)
     c->have_index = false;
     c->have_pred = false;
     return 0;
+}
+
+// Halo exchange + sweep of a slab context as ONE stream-ordered sequence with the transfer hidden:
+//   send (peer stores over NVLink)  ->  partition of the owned particles  ->  receive + partition of the
+//   neighbours' rows (their send was issued a partition ago)  ->  sweep kernel.
+// Falls back to exchange-then-predict when the state is not eligible for the tile sweep.
+static int exchange_predict_launch(edmd_ctx *c, int mode, cudaEvent_t between)
+{
+    const int H2 = 2 * c->halo_cap;
+    c->n = c->n_owned + H2;       // fixed halo region; unused slots carry cell id -1
+    c->nghost_extra = H2;         // bound: every halo particle could sit in an edge cell
+    c->index_tile = false;
+    c->pred_packed = false;
+    if (edmd_tile_eligible(c, mode)) {
+        // fork: send + receive (a few small blocks, mostly waiting on NVLink) on the second stream, the
+        // partition of the owned particles on the first; both append to the same buckets (atomic cursors)
+        CU(cudaEventRecord(c->ev_fork, c->stream));
+        CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        c->launches += edmd_launch_halo_send(c, c->stream2);
+        c->launches += edmd_launch_halo_recv_partition(c, c->stream2);
+        CU(cudaEventRecord(c->ev_join, c->stream2));
+        c->launches += edmd_launch_tile_partition_range(c, 0, c->n_owned);
+        CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        if (between) CU(cudaEventRecord(between, c->stream));
+        c->launches += edmd_launch_tile_sweep_only(c);
+        c->index_lean = true;
+        c->index_tile = true;
+        c->lean_pending = true;
+    } else {
+        CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));
+        c->launches += edmd_launch_halo_p2p(c);
+        if (edmd_lean_eligible(c, mode)) {
+            c->launches += edmd_launch_lean_index(c);
+            if (between) CU(cudaEventRecord(between, c->stream));
+            c->launches += edmd_launch_predict_lean(c);
+            c->index_lean = true;
+            c->lean_pending = true;
+        } else {
+            c->launches += edmd_launch_cell_index(c, mode);
+            if (between) CU(cudaEventRecord(between, c->stream));
+            c->launches += edmd_launch_predict(c, mode);
+            c->index_lean = false;
+        }
+    }
+    CU(cudaGetLastError());
+    c->have_index = true;
+    c->have_pred = true;
+    c->pred_mode = mode;
+    return 0;
+}
+
+int edmd_cuda_exchange_predict_device(edmd_ctx *c, int mode)
+{
+    if (!c) return EDMD_EINVAL;
+    if (mode != EDMD_MODE_NORMAL && mode != EDMD_MODE_GROW) return fail(c, EDMD_EINVAL, "bad mode");
+    if (!c->slab || !c->have_state) return fail(c, EDMD_ESTATE, "exchange_predict needs an uploaded slab");
+    if (!c->peer_mem[0] || !c->peer_mem[1]) return fail(c, EDMD_ESTATE, "halo_connect first");
+    if (c->n_owned + 2 * c->halo_cap > c->n_cap) return fail(c, EDMD_EINVAL, "halo does not fit the slab capacity");
+    if (mode == EDMD_MODE_GROW && !c->have_vr) return fail(c, EDMD_ESTATE, "GROW mode needs growth rates");
+    CU(cudaSetDevice(c->device));
+    return exchange_predict_launch(c, mode, nullptr);
 }
 
 int edmd_cuda_get_counts(const edmd_ctx *c, int *n_owned, int *n_total)
@@ -945,14 +1015,16 @@ int edmd_cuda_boop_cutoff(edmd_ctx *c, double r_c, double *q5, double *q6, doubl
     bool tile = false, redone = false;
     if ((r = boop_launch(c, r_c, &tile))) return r;
     if (tile && (r = boop_tile_confirm(c, r_c, &redone))) return r;
-    size_t N = (size_t)c->n, B = N * sizeof(double);
-    if (mean_q6) c->launches += edmd_launch_mean(c, c->boop + N, c->n, c->red_partial + c->red_cap);
+    // outputs cover the particles this context predicts (a slab's halo copies belong to its neighbours);
+    // mean_q6 of a slab is the mean over ITS particles: weight by n_owned when combining ranks
+    size_t N = (size_t)c->n_cap, B = (size_t)c->n_owned * sizeof(double);
+    if (mean_q6) c->launches += edmd_launch_mean(c, c->boop + N, c->n_owned, c->red_partial + c->red_cap);
     CU(cudaGetLastError());
     if (q5 && (r = d2h(c, q5, c->boop, B))) return r;
     if (q6 && (r = d2h(c, q6, c->boop + N, B))) return r;
     if (q7 && (r = d2h(c, q7, c->boop + 2 * N, B))) return r;
     if (q6_arg && (r = d2h(c, q6_arg, c->boop + 3 * N, B))) return r;
-    if (neighbors && (r = d2h(c, neighbors, c->boop_nb, N * sizeof(int32_t)))) return r;
+    if (neighbors && (r = d2h(c, neighbors, c->boop_nb, (size_t)c->n_owned * sizeof(int32_t)))) return r;
     if (mean_q6)
         CU(cudaMemcpyAsync(mean_q6, c->red_partial + c->red_cap, sizeof(double),
                            cudaMemcpyDeviceToHost, c->stream));
@@ -1269,14 +1341,16 @@ int edmd_cuda_boop_voronoi(edmd_ctx *c, double *q5, double *q6, double *q7, doub
     CU(cudaSetDevice(c->device));
     int r;
     if ((r = voronoi_run(c, true, false, nullptr, nullptr, nullptr))) return r;
-    size_t N = (size_t)c->n, B = N * sizeof(double);
-    if (mean_q6) c->launches += edmd_launch_mean(c, c->boop + N, c->n, c->red_partial + c->red_cap);
+    // outputs cover the particles this context predicts (a slab's halo copies belong to its neighbours);
+    // mean_q6 of a slab is the mean over ITS particles: weight by n_owned when combining ranks
+    size_t N = (size_t)c->n_cap, B = (size_t)c->n_owned * sizeof(double);
+    if (mean_q6) c->launches += edmd_launch_mean(c, c->boop + N, c->n_owned, c->red_partial + c->red_cap);
     CU(cudaGetLastError());
     if (q5 && (r = d2h(c, q5, c->boop, B))) return r;
     if (q6 && (r = d2h(c, q6, c->boop + N, B))) return r;
     if (q7 && (r = d2h(c, q7, c->boop + 2 * N, B))) return r;
     if (q6_arg && (r = d2h(c, q6_arg, c->boop + 3 * N, B))) return r;
-    if (neighbors && (r = d2h(c, neighbors, c->boop_nb, N * sizeof(int32_t)))) return r;
+    if (neighbors && (r = d2h(c, neighbors, c->boop_nb, (size_t)c->n_owned * sizeof(int32_t)))) return r;
     if (mean_q6)
         CU(cudaMemcpyAsync(mean_q6, c->red_partial + c->red_cap, sizeof(double),
                            cudaMemcpyDeviceToHost, c->stream));
@@ -1507,11 +1581,12 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
             if (!edmd_tile_eligible(c, mode))
                 CU(cudaMemsetAsync(c->overlap_key, 0xff, sizeof(unsigned long long), c->stream));
             if (c->slab && c->peer_mem[0] && c->peer_mem[1]) {
-                // multi-GPU step: the halo exchange (peer stores over NVLink) is part of it;
-                // every rank runs the same number of iterations, epochs advance in lockstep
-                c->launches += edmd_launch_halo_p2p(c);
-                c->n = c->n_owned + 2 * c->halo_cap;
-                c->nghost_extra = 2 * c->halo_cap;
+                // multi-GPU step: the halo exchange (peer stores over NVLink) is part of it, hidden behind
+                // the partition of the owned particles; every rank runs the same number of iterations,
+                // epochs advance in lockstep
+                int r = exchange_predict_launch(c, mode, e ? e[1] : nullptr);
+                if (r) return r;
+                break;
             }
             c->index_tile = false;
             c->pred_packed = false;

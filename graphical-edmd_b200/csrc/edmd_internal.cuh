@@ -151,7 +151,9 @@ struct edmd_ctx {
     edmd_box box;
     edmd_dev_box dbox;
     cudaStream_t stream;
+    cudaStream_t stream2;   // the halo exchange of a slab context runs beside the partition of the owned particles
     cudaEvent_t ev[4];
+    cudaEvent_t ev_fork, ev_join;
     char err[512];
     uint64_t launches;
     bool force_generic;  // EDMD_OPT_FORCE_GENERIC: global-memory exact kernel only
@@ -306,6 +308,11 @@ int edmd_launch_halo_pack(edmd_ctx *c, int side, void *out, int cap, int32_t *co
 int edmd_launch_halo_append_row(edmd_ctx *c, const void *in, int count, int row);
 size_t edmd_halo_mem_bytes(int halo_cap);
 int edmd_launch_halo_p2p(edmd_ctx *c);
+int edmd_launch_halo_send(edmd_ctx *c, cudaStream_t st);
+int edmd_launch_halo_recv(edmd_ctx *c);
+int edmd_launch_halo_recv_partition(edmd_ctx *c, cudaStream_t st);
+int edmd_launch_tile_partition_range(edmd_ctx *c, int first, int n);
+int edmd_launch_tile_sweep_only(edmd_ctx *c);
 int edmd_launch_cell_index(edmd_ctx *c, int mode);
 int edmd_launch_predict(edmd_ctx *c, int mode);
 int edmd_launch_free_fly(edmd_ctx *c, int mode, double dt);

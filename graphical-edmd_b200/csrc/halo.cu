@@ -19,36 +19,11 @@
 // slots get cell id -1 and are skipped by the cell index), and acks.  A sender
 // may run at most two exchanges ahead of its receiver (ack check).
 #include "edmd_internal.cuh"
+#include "halo.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-
-struct __align__(16) HaloRec {
-    double x, y, vx, vy, rad;
-    int gid;
-    int cell;   // padded column 1..nx (the row is implied by which neighbour sent it)
-};
-static_assert(sizeof(HaloRec) == 48, "halo record");
-
-struct __align__(16) InboxHeader {
-    int count, epoch, pad[2];
-};
-
-__host__ __device__ inline size_t inbox_bytes(int H)
-{
-    return (sizeof(InboxHeader) + sizeof(HaloRec) * (size_t)H + 255) & ~(size_t)255;
-}
-__host__ __device__ inline size_t inbox_offset(int H, int from, int parity)
-{
-    return inbox_bytes(H) * (size_t)(2 * from + parity);
-}
-__host__ __device__ inline size_t ack_offset(int H) { return inbox_bytes(H) * 4; }
-
-__device__ __forceinline__ int ld_volatile(const int *p)
-{
-    return *reinterpret_cast<const volatile int *>(p);
-}
 
 // Sending is two steps.  The indices of the owned particles in the two boundary
 // rows are listed once per upload (by the pack kernel, or by k_halo_collect if the
@@ -204,9 +179,12 @@ k_halo_recv(const __grid_constant__ RecvArgs a)
 
 size_t edmd_halo_mem_bytes(int halo_cap) { return ack_offset(halo_cap) + 256; }
 
-// Launches one send and one recv kernel on the context's stream.
-int edmd_launch_halo_p2p(edmd_ctx *c)
+// The exchange is two launches on the context's stream: send (peer stores into the neighbours'
+// inboxes; starts a new epoch) and receive (waits for the neighbours' epoch, unpacks, acks).  Work that
+// does not need the halo may be launched between the two (edmd_cuda_exchange_predict_device).
+int edmd_launch_halo_send(edmd_ctx *c, cudaStream_t st)
 {
+    if (!st) st = c->stream;
     const int H = c->halo_cap;
     const int e = ++c->halo_epoch;
     const int par = e & 1;
@@ -220,8 +198,8 @@ int edmd_launch_halo_p2p(edmd_ctx *c)
     ca.cid = c->cid; ca.list = c->halo_list; ca.cnt = cnt; ca.flags = c->flags;
     const bool collect = n > 0 && !c->halo_list_valid;   // else the upload's pack kernel listed them
     if (collect) {
-        cudaMemsetAsync(cnt, 0, 2 * sizeof(int32_t), c->stream);
-        k_halo_collect<<<(n + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(ca);
+        cudaMemsetAsync(cnt, 0, 2 * sizeof(int32_t), st);
+        k_halo_collect<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(ca);
         c->halo_list_valid = true;
     }
     SendArgs sa;
@@ -231,9 +209,18 @@ int edmd_launch_halo_p2p(edmd_ctx *c)
     sa.peer_inbox[1] = c->peer_mem[1] + inbox_offset(H, 0, par);
     sa.ack = reinterpret_cast<const int *>(c->halo_mem + ack_offset(H));
     sa.cnt = cnt; sa.done = cnt + 2;
-    k_halo_send<<<dim3((H + kThreads - 1) / kThreads, 2), kThreads, 0, c->stream>>>(sa);
+    k_halo_send<<<dim3((H + kThreads - 1) / kThreads, 2), kThreads, 0, st>>>(sa);
+    return collect ? 2 : 1;
+}
+
+int edmd_launch_halo_recv(edmd_ctx *c)
+{
+    const int H = c->halo_cap;
+    const int e = c->halo_epoch, par = e & 1;
+    const int nl = c->dbox.nl;
+    int32_t *cnt = c->halo_cnt;
     RecvArgs ra;
-    ra.H = H; ra.first = n; ra.ps = c->ps; ra.epoch = e;
+    ra.H = H; ra.first = c->n_owned; ra.ps = c->ps; ra.epoch = e;
     ra.row[0] = 0; ra.row[1] = nl - 1;
     ra.inbox[0] = c->halo_mem + inbox_offset(H, 0, par);
     ra.inbox[1] = c->halo_mem + inbox_offset(H, 1, par);
@@ -246,5 +233,11 @@ int edmd_launch_halo_p2p(edmd_ctx *c)
     ra.rad0 = c->rad0;
     dim3 rgrid((H + kThreads - 1) / kThreads, 2);
     k_halo_recv<<<rgrid, kThreads, 0, c->stream>>>(ra);
-    return collect ? 3 : 2;
+    return 1;
+}
+
+int edmd_launch_halo_p2p(edmd_ctx *c)
+{
+    int launched = edmd_launch_halo_send(c, nullptr);
+    return launched + edmd_launch_halo_recv(c);
 }

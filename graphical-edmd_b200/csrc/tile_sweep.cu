@@ -46,6 +46,7 @@
 // through kFlagLeanFail and the host re-runs it on the full FP64 path.
 #include "lean.cuh"
 #include "pairmath.cuh"
+#include "halo.cuh"
 
 namespace {
 
@@ -67,19 +68,11 @@ struct PartArgs {
     unsigned long long *overlap_key;
 };
 
-__global__ void __launch_bounds__(kPartThreads)
-k_tile_partition(const __grid_constant__ PartArgs a)
+// Append particle i (padded cell id pc, state p, radius rad) to the bucket of its tile and, when it sits
+// in an edge cell of the tile, to the buckets of the neighbouring tiles whose ring holds that cell.
+__device__ __forceinline__ void partition_one(const PartArgs &a, int i, int pc, const double4 &p, double rad,
+                                              const bool radii)
 {
-    const int i = a.first + blockIdx.x * blockDim.x + threadIdx.x;
-    edmd_pdl_wait();
-    if (i == a.first) *a.overlap_key = ~0ull;   // the sweep's overlap report starts empty
-    if (i >= a.first + a.n) return;
-    const int pc = a.cid[i];
-    const double4 p = ld_sector(a.xv + i);
-    if (pc < 0) return;   // unused halo slot of a slab context
-    // radii matter only when they are not all exactly rad0 (two classes / spread inside a class)
-    const bool radii = a.flags[kFlagNotMono] != 0;
-    const double rad = radii ? a.rad[i] : a.rad0;
     const TileGeom &tg = a.tg;
     const int Yl = pc / a.ps;
     const int X = pc - Yl * a.ps - 1;
@@ -150,6 +143,88 @@ k_tile_partition(const __grid_constant__ PartArgs a)
             }
     }
     if (!ok) atomicOr(&a.flags[kFlagLeanFail], 1);   // a run is full: the sweep declines
+}
+
+__global__ void __launch_bounds__(kPartThreads)
+k_tile_partition(const __grid_constant__ PartArgs a)
+{
+    const int i = a.first + blockIdx.x * blockDim.x + threadIdx.x;
+    edmd_pdl_wait();
+    if (i == a.first && a.overlap_key) *a.overlap_key = ~0ull;   // the sweep's overlap report starts empty
+    if (i >= a.first + a.n) return;
+    const int pc = a.cid[i];
+    const double4 p = ld_sector(a.xv + i);
+    if (pc < 0) return;   // unused halo slot of a slab context
+    // radii matter only when they are not all exactly rad0 (two classes / spread inside a class)
+    const bool radii = a.flags[kFlagNotMono] != 0;
+    const double rad = radii ? a.rad[i] : a.rad0;
+    partition_one(a, i, pc, p, rad, radii);
+}
+
+// Slab contexts, peer-to-peer halo: receive + partition in one kernel.  Waits for the neighbours'
+// epoch (their k_halo_send wrote the records into my inbox over NVLink), unpacks each record into the
+// fixed halo region of the resident arrays -- exactly what k_halo_recv (halo.cu) does -- and appends
+// it to the tile buckets right away; acks back.  blockIdx.y = from (0: lower neighbour's records ->
+// local row 0, 1: upper -> row nl-1).
+struct RecvPartArgs {
+    PartArgs p;
+    int H, epoch, row[2];
+    const char *inbox[2];
+    double4 *xv;
+    double *rad;
+    int32_t *cid, *gid;
+    int *peer_ack[2];
+    int32_t *done;
+};
+
+__global__ void __launch_bounds__(kPartThreads)
+k_halo_recv_partition(const __grid_constant__ RecvPartArgs a)
+{
+    __shared__ bool last;
+    const int from = blockIdx.y;
+    const InboxHeader *hdr = reinterpret_cast<const InboxHeader *>(a.inbox[from]);
+    const HaloRec *rec = reinterpret_cast<const HaloRec *>(a.inbox[from] + sizeof(InboxHeader));
+    if (threadIdx.x == 0)
+        while (ld_volatile(&hdr->epoch) != a.epoch) __nanosleep(50);
+    __syncthreads();
+    const int count = ld_volatile(&hdr->count);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < a.H) {
+        const int i = a.p.first + from * a.H + k;
+        if (k < count) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(rec + k);
+            HaloRec r;
+            uint4 *dst = reinterpret_cast<uint4 *>(&r);
+            dst[0] = __ldcv(src); dst[1] = __ldcv(src + 1); dst[2] = __ldcv(src + 2);
+            const double4 p = make_double4(r.x, r.y, r.vx, r.vy);
+            const int pc = a.row[from] * a.p.ps + r.cell;
+            a.xv[i] = p;
+            a.rad[i] = r.rad;
+            a.gid[i] = r.gid;
+            a.cid[i] = pc;
+            // keep the sweep's eligibility facts current (lean.cuh)
+            edmd_note_radius(a.p.flags, r.rad, a.p.rad0);
+            float vm = __double2float_ru(fmax(fabs(r.vx), fabs(r.vy)));
+            if (!(vm == vm)) vm = __int_as_float(0x7f800000);
+            if (__float_as_int(vm) > a.p.flags[kFlagVmax])
+                atomicMax(reinterpret_cast<unsigned int *>(&a.p.flags[kFlagVmax]), (unsigned)__float_as_int(vm));
+            // the owned particles were partitioned with the radius facts of the upload; a halo disk of
+            // another radius class raises kFlagNotMono now and the sweep kernel declines (rad_smem)
+            partition_one(a.p, i, pc, p, r.rad, true);
+        } else {
+            a.cid[i] = -1;   // unused slot
+            a.gid[i] = -1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(a.done + from, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(a.peer_ack[from]) = a.epoch;   // "consumed", peer store
+        __threadfence_system();
+        a.done[from] = 0;
+    }
 }
 
 // ---- P2 ---------------------------------------------------------------------------
@@ -717,8 +792,11 @@ k_tile_boop(const __grid_constant__ BoopTileArgs ba)
     const double half_lx = a.b.half_lx, half_ly = a.b.half_ly, lx = a.b.lx, ly = a.b.ly, rc2 = ba.rc2;
     // a tile away from the edges of the grid never sees the periodic image (every particle lies within
     // 1.5 cells of the cell it is filed under -- kFlagInsane -- so |d| <= 4 cells < L/2): PBC() is the identity
-    const bool wrap = a.flags[kFlagInsane] != 0 || tp.txi == 0 || tp.txi == a.tg.ntx - 1 || tp.tyi == 0 ||
-                      tp.tyi == a.tg.nty - 1 || a.b.nx < 12 || a.b.ny < 12;
+    // (frame rows lo .. hi in local rows; in a slab the global row yoff + l wraps somewhere inside the slab)
+    const int fr_lo = tp.tyi * kTY - 1, fr_hi = tp.tyi * kTY + tp.th;
+    const bool wrap_y = fr_lo < 0 || fr_hi >= a.b.nl || (a.b.yoff + fr_lo < a.b.ny && a.b.yoff + fr_hi >= a.b.ny);
+    const bool wrap = a.flags[kFlagInsane] != 0 || tp.txi == 0 || tp.txi == a.tg.ntx - 1 || wrap_y ||
+                      a.b.nx < 12 || a.b.ny < 12;
 #pragma unroll 1
     for (int k = tid; k < nown; k += kTileThreads) {
         const unsigned u = s.own[k];
@@ -860,19 +938,50 @@ int edmd_launch_unpack_events(edmd_ctx *c)
     return 1;
 }
 
-// P1 alone: (re)build the tile buckets of the resident state
-int edmd_launch_tile_partition(edmd_ctx *c)
+static PartArgs part_args(edmd_ctx *c, int first, int n)
 {
-    if (c->n == 0) return 0;
     PartArgs pa;
-    pa.first = 0; pa.n = c->n; pa.ps = c->ps; pa.slab = c->slab ? 1 : 0; pa.dbg = c->tile_dbg;
+    pa.first = first; pa.n = n; pa.ps = c->ps; pa.slab = c->slab ? 1 : 0; pa.dbg = c->tile_dbg;
     pa.tg = c->tgeom; pa.b = c->dbox;
     pa.cid = c->cid; pa.xv = c->xv; pa.rad = c->rad; pa.rad0 = c->rad0;
     pa.flags = c->flags; pa.tcnt = c->tcnt; pa.tst = c->tst; pa.ttag = c->ttag; pa.trad = c->trad;
     pa.overlap_key = c->overlap_key;
+    return pa;
+}
+
+// P1 alone: (re)build the tile buckets of the resident state (particles [first, first + n))
+int edmd_launch_tile_partition_range(edmd_ctx *c, int first, int n)
+{
+    if (n <= 0) return 0;
+    const PartArgs pa = part_args(c, first, n);
     // the first kernel of the chain is launched plainly: whatever precedes it on the stream completes first
-    edmd_launch(k_tile_partition, dim3((c->n + kPartThreads - 1) / kPartThreads), dim3(kPartThreads), 0, c->stream,
+    edmd_launch(k_tile_partition, dim3((n + kPartThreads - 1) / kPartThreads), dim3(kPartThreads), 0, c->stream,
                 false, pa);
+    return 1;
+}
+
+int edmd_launch_tile_partition(edmd_ctx *c) { return edmd_launch_tile_partition_range(c, 0, c->n); }
+
+// slab contexts with the peer-to-peer halo: receive the neighbours' boundary rows (sent by
+// edmd_launch_halo_send) and append them to the tile buckets in the same kernel
+int edmd_launch_halo_recv_partition(edmd_ctx *c, cudaStream_t st)
+{
+    if (!st) st = c->stream;
+    const int H = c->halo_cap;
+    const int e = c->halo_epoch, par = e & 1;
+    RecvPartArgs ra;
+    ra.p = part_args(c, c->n_owned, 2 * H);
+    ra.p.overlap_key = nullptr;
+    ra.H = H; ra.epoch = e;
+    ra.row[0] = 0; ra.row[1] = c->dbox.nl - 1;
+    ra.inbox[0] = c->halo_mem + inbox_offset(H, 0, par);
+    ra.inbox[1] = c->halo_mem + inbox_offset(H, 1, par);
+    ra.xv = c->xv; ra.rad = c->rad; ra.cid = c->cid; ra.gid = c->gid;
+    // consuming the lower neighbour's records: I am its UPPER neighbour -> its ack[1]; and vice versa
+    ra.peer_ack[0] = reinterpret_cast<int *>(c->peer_mem[0] + ack_offset(H)) + 1;
+    ra.peer_ack[1] = reinterpret_cast<int *>(c->peer_mem[1] + ack_offset(H)) + 0;
+    ra.done = c->halo_cnt + 4;
+    k_halo_recv_partition<<<dim3((H + kPartThreads - 1) / kPartThreads, 2), kPartThreads, 0, st>>>(ra);
     return 1;
 }
 
@@ -901,6 +1010,17 @@ static void tile_attrs()
     attr = true;
 }
 
+// the sweep kernel over the buckets (P2)
+int edmd_launch_tile_sweep_only(edmd_ctx *c)
+{
+    const SweepArgs sa = sweep_args(c);
+    tile_attrs();
+    edmd_launch(k_tile_sweep, dim3(c->tgeom.ntx * c->tgeom.nty), dim3(kTileThreads), tile_smem_bytes(c->tgeom, sa.rad_smem),
+                c->stream, false, sa);
+    c->pred_packed = true;
+    return 1;
+}
+
 int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between)
 {
     if (c->n == 0) return 0;
@@ -918,7 +1038,7 @@ int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between)
 int edmd_launch_tile_boop(edmd_ctx *c, double r_c, bool from_keep)
 {
     if (c->n == 0) return 0;
-    const size_t N = (size_t)c->n;
+    const size_t N = (size_t)c->n_cap;   // the four psi6 arrays lie n_cap apart
     BoopTileArgs ba;
     ba.s = sweep_args(c);
     ba.from_keep = from_keep ? 1 : 0;

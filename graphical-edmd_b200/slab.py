@@ -167,6 +167,32 @@ class SlabRank:
     def predict(self):
         return self.ctx.predict_all()
 
+    def exchange_predict(self, dist=None):
+        """Halo exchange + sweep.  With the peer-to-peer halo this is ONE stream-ordered sequence on
+        the device (edmd_cuda_exchange_predict_device): send, partition of the owned particles,
+        receive + partition of the neighbours' rows, sweep kernel."""
+        if self.p2p:
+            self.ctx.exchange_predict_device()
+            return self.ctx.fetch_predictions()
+        self.exchange(dist)
+        return self.predict()
+
+    def boop(self, dist, n_total: int, r_c: float = 2.5):
+        """psi6 of this rank's particles (computeBOOPCutoff, src/boop.c:61-107; the halo rows of the
+        last exchange supply the neighbours across the slab boundary) and the mean q6 of the WHOLE
+        system (the thermo column, src/EDMD.c:5521-5536): the per-rank sums are all-reduced."""
+        torch = self.torch
+        b = self.ctx.boop_cutoff(r_c)
+        n_own = len(b["q6"])
+        part = torch.tensor([b["mean_q6"] * n_own, float(n_own)], dtype=torch.float64,
+                            device=torch.device("cuda", self.device))
+        if self.world > 1:
+            dist.all_reduce(part)
+        tot = part.cpu().numpy()
+        assert int(round(tot[1])) == n_total
+        b["mean_q6_global"] = float(tot[0] / tot[1])
+        return b
+
     def pcf(self, dist, x_owned, y_owned, n_total: int, dr: float, max_r: float):
         """g(r) of the whole system across the ranks (calculate_pcf, src/pcf.c:16-75):
         the owned positions are all-gathered (NCCL), every rank sorts them into the

@@ -231,6 +231,12 @@ int edmd_cuda_halo_append(edmd_ctx *ctx, int side, const void *dev_records, int 
 int edmd_cuda_halo_export(edmd_ctx *ctx, int halo_capacity, void *handle64);
 int edmd_cuda_halo_connect(edmd_ctx *ctx, const void *lower_handle64, const void *upper_handle64);
 int edmd_cuda_halo_exchange(edmd_ctx *ctx);
+/* Halo exchange + sweep of a slab context as ONE stream-ordered sequence that hides the transfer:
+ * send (peer stores over NVLink) -> partition of the owned particles -> receive + partition of the
+ * neighbours' boundary rows -> sweep kernel.  Asynchronous like edmd_cuda_predict_device; every rank
+ * of the decomposition must call it the same number of times (the exchange counts epochs).  Replaces
+ * edmd_cuda_halo_exchange + edmd_cuda_predict_device; results through edmd_cuda_fetch_predictions. */
+int edmd_cuda_exchange_predict_device(edmd_ctx *ctx, int mode);
 int edmd_cuda_get_counts(const edmd_ctx *ctx, int *n_owned, int *n_total);
 /* g(r) share of one rank: positions of ALL particles as (x,y) pairs in device
  * memory (e.g. after an all-gather), tile pairs part (mod nparts); ADDS into

@@ -31,9 +31,12 @@ def main():
     slab = pkg.slab
     orc = Oracle()
     ok = True
-    for (n, phi, seed, sf, p2p) in [(200000, 0.70, 5, 0.3, False), (200000, 0.70, 5, 0.3, True),
-                                    (60000, 0.85, 6, 0.0, True), (150000, 0.70, 7, 0.0, False),
-                                    (150000, 0.72, 8, 0.0, True)]:   # monodisperse: the lean sweep
+    cases = [(200000, 0.70, 5, 0.3, False), (200000, 0.70, 5, 0.3, True),
+             (60000, 0.85, 6, 0.0, True), (150000, 0.70, 7, 0.0, False),
+             (150000, 0.72, 8, 0.0, True)]
+    if "--big" in sys.argv:   # BASELINE configs[3]: N = 4*10^6, phi = 0.70 (the configuration SCALE times)
+        cases += [(4000000, 0.70, 12345, 0.0, True)]
+    for (n, phi, seed, sf, p2p) in cases:
         cfg = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf)
         N, lx, ly, t = cfg["n"], cfg["lx"], cfg["ly"], 1.25
         cells = orc.cells(N, lx, ly, cfg["x"], cfg["y"]).reshape(N, 2)
@@ -41,21 +44,34 @@ def main():
         if p2p:
             sr.connect_p2p(dist)
         gid = sr.load_owned(cfg, cells, t)
-        sr.exchange(dist)
-        out = sr.predict()
-        if p2p:   # a second and third exchange on fresh uploads: epochs / parities / acks
-            for _ in range(2):
-                sr.load_owned(cfg, cells, t)
-                sr.exchange(dist)
-                out = sr.predict()
+        if p2p:
+            # send -> partition(owned) -> receive + partition(halo) -> sweep, one sequence on the device
+            out = sr.exchange_predict(dist)
+            # a second and third exchange on fresh uploads (epochs / parities / acks), once through the
+            # separate calls (exchange, then predict) and once fused
+            sr.load_owned(cfg, cells, t)
+            sr.exchange(dist)
+            out2 = sr.predict()
+            sr.load_owned(cfg, cells, t)
+            out = sr.exchange_predict(dist)
+            for k in ("t_cross", "dir", "t_coll", "partner", "ctype"):
+                if not np.array_equal(out[k], out2[k]):
+                    ok = False
+                    print(f"rank {rank}: fused exchange+sweep differs from exchange, then sweep ({k})")
+        else:
+            sr.exchange(dist)
+            out = sr.predict()
+        # psi6 of the owned particles (halo rows supply the neighbours across the boundary) + global mean q6
+        bo = sr.boop(dist, N)
         gathered = [None] * world
-        dist.all_gather_object(gathered, {"gid": gid, **{k: out[k] for k in ("t_cross", "dir", "t_coll", "partner", "ctype")}})
+        dist.all_gather_object(gathered, {"gid": gid, **{k: out[k] for k in ("t_cross", "dir", "t_coll", "partner", "ctype")},
+                                          "nb": bo["neighbors"], "q6": bo["q6"], "mq6": bo["mean_q6_global"]})
         # g(r): all-gather owned positions, bin my share of the tile pairs, all-reduce the counts
         dr, max_r = 0.1, 15.0
         counts, _ = sr.pcf(dist, cfg["x"][gid], cfg["y"][gid], N, dr, max_r)
         # full range on the larger system: the sorted-tile kernel, tiles cut identically on every rank
         counts_full = None
-        if N >= 8192:
+        if 8192 <= N <= 1000000:
             counts_full, _ = sr.pcf(dist, cfg["x"][gid], cfg["y"][gid], N, 0.25, min(lx, ly) / 2)
         if rank == 0:
             want = orc.predict_all(N, lx, ly, t, cfg["x"], cfg["y"], cfg["vx"], cfg["vy"], cfg["rad"])
@@ -67,6 +83,12 @@ def main():
                         ok = False
                         print(f"MISMATCH N={N} {k}: {(g[k] != want[k][g['gid']]).sum()}")
             ok = ok and bool(seen.all())
+            wb = orc.boop_cutoff(N, lx, ly, cfg["x"], cfg["y"], 2.5)
+            for g in gathered:
+                if not np.array_equal(g["nb"], wb["neighbors"][g["gid"]]) or \
+                        np.abs(g["q6"] - wb["q6"][g["gid"]]).max() > 1e-10 or abs(g["mq6"] - wb["q6"].mean()) > 1e-12:
+                    ok = False
+                    print(f"MISMATCH N={N} psi6")
             if N < 100000:   # the oracle's g(r) is O(N^2)
                 wp = orc.pcf(N, lx, ly, cfg["x"], cfg["y"], dr, max_r)
                 if not np.array_equal(counts, wp["counts"]):
@@ -78,7 +100,7 @@ def main():
                         ok = False
                         print("MISMATCH full-range g(r) counts (sorted tiles)")
             print(f"slab check N={N} phi={phi} world={world} halo={'NVLink peer stores' if p2p else 'NCCL send/recv'}: "
-                  f"sweep + g(r) {'bit-exact' if ok else 'FAILED'}")
+                  f"sweep bit-exact, psi6 <= 1e-10, mean q6 all-reduced, g(r) counts exact: {'OK' if ok else 'FAILED'}")
         sr.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -1173,3 +1173,53 @@ def test_device_langevin_kick(pkg, oracle, n, phi, seed, T, gdt):
     assert abs(e1["px"]) / n < drift and abs(e1["py"]) / n < drift
     want = oracle.predict_all(n, c["lx"], c["ly"], 0.0, st["x"], st["y"], st["vx"], st["vy"], c["rad"])
     assert_events_equal(got, want)
+
+
+# ------------------------------------------------- slabs on ONE GPU (no IPC, no NCCL) ----
+@pytest.mark.parametrize("n,phi,seed,sf,nslabs", [(1000000, 0.70, 301, 0.0, 4), (1000000, 0.85, 302, 0.0, 2),
+                                                  (300000, 0.70, 303, 0.3, 3), (60000, 0.72, 304, 0.0, 8)])
+def test_slab_decomposition_on_one_gpu_matches_oracle(pkg, oracle, n, phi, seed, sf, nslabs):
+    """The multi-GPU path with every slab context on the same device: ownership by cell row, the
+    one-row halo through edmd_cuda_halo_pack / edmd_cuda_halo_append (device buffers, no IPC), the
+    sweep (tile path) and psi6 of every slab against the whole-system oracle, bit for bit; the
+    weighted mean of the per-slab mean q6 is the whole system's."""
+    import torch
+    slab = pkg.slab
+    c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf, shuffle=True)
+    N, lx, ly, t = c["n"], c["lx"], c["ly"], 0.75
+    cells = oracle.cells(N, lx, ly, c["x"], c["y"]).reshape(N, 2)
+    want = oracle_sweep(oracle, c, t=t)
+    wb = oracle.boop_cutoff(N, lx, ly, c["x"], c["y"], 2.5)
+    ranks = [slab.SlabRank(pkg, N, lx, ly, r, nslabs, 0) for r in range(nslabs)]
+    try:
+        gids = [sr.load_owned(c, cells, t) for sr in ranks]
+        rec = slab.HALO_REC.itemsize
+        packed = []
+        for sr in ranks:
+            n_lo = sr.ctx.halo_pack(0, sr.send[0].data_ptr(), sr.halo_capacity)
+            n_hi = sr.ctx.halo_pack(1, sr.send[1].data_ptr(), sr.halo_capacity)
+            packed.append((n_lo, n_hi))
+        torch.cuda.synchronize()
+        for r, sr in enumerate(ranks):
+            lower, upper = slab.neighbours(r, nslabs)
+            # my local row 0 is the lower neighbour's LAST row (its side 1); my last row its upper's FIRST
+            sr.ctx.halo_append(0, ranks[lower].send[1].data_ptr(), packed[lower][1])
+            sr.ctx.halo_append(1, ranks[upper].send[0].data_ptr(), packed[upper][0])
+        seen = np.zeros(N, bool)
+        q6sum = 0.0
+        for sr, gid in zip(ranks, gids):
+            got = sr.predict()
+            assert sr.ctx.stat(pkg.binding.STAT_LEAN_SWEEPS) == 1
+            for k in ("t_cross", "dir", "t_coll", "partner", "ctype"):
+                assert np.array_equal(got[k], want[k][gid]), (k, sr.rank)
+            b = sr.ctx.boop_cutoff(2.5)
+            assert np.array_equal(b["neighbors"], wb["neighbors"][gid])
+            for k in ("q5", "q6", "q7"):
+                assert np.abs(b[k] - wb[k][gid]).max() <= 1e-10, k
+            q6sum += b["mean_q6"] * len(gid)
+            seen[gid] = True
+        assert seen.all()
+        assert abs(q6sum / N - wb["q6"].mean()) < 1e-12
+    finally:
+        for sr in ranks:
+            sr.close()

@@ -226,11 +226,7 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int k = 0; k < 4; k++) CU(cudaEventCreateWithFlags(&c->ev[k], cudaEventDisableTiming));
-    if (slab) {
-        CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    }
+
     size_t N = (size_t)n;
     int r;
     if ((r = dev_alloc(c, &c->in_soa, 5 * N))) return r;
@@ -300,6 +296,8 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
     CU(cudaMemsetAsync(c->ctype, EDMD_EV_COLLISION, N ? N : 1, c->stream));   // the constant COLLISION (src/EDMD.h:19-34)
     if ((r = dev_alloc(c, &c->overlap_key, 1))) return r;
     if ((r = dev_alloc(c, &c->flags, kFlagCount))) return r;
+    if ((r = dev_alloc(c, &c->dbg_ts, 16))) return r;
+    CU(cudaMemsetAsync(c->dbg_ts, 0, 16 * sizeof(unsigned long long), c->stream));
     CU(cudaMemsetAsync(c->flags, 0, kFlagCount * sizeof(int32_t), c->stream));
     if ((r = dev_alloc(c, &c->boop, 4 * N))) return r;
     if ((r = dev_alloc(c, &c->boop_nb, N))) return r;
@@ -323,13 +321,12 @@ int edmd_cuda_create_slab(int device, int n_capacity, double lx, double ly, int 
 void edmd_cuda_destroy(edmd_ctx *c)
 {
     if (!c) return;
-    if (c->stream2) cudaStreamSynchronize(c->stream2);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->gid, c->cell_cnt,
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
                    c->lrec, c->lchunks, c->lres, c->lwork, c->tst, c->ttag, c->trad, c->tcnt, c->tkeep, c->boop_rec, c->evrec, c->cal_mem,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
-                   c->overlap_key, c->flags, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->vor_mem, c->thermo_mem, c->boop, c->boop_nb,
+                   c->overlap_key, c->flags, c->dbg_ts, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->vor_mem, c->thermo_mem, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
     for (void *p : dev)
         if (p) cudaFree(p);
@@ -341,9 +338,6 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (int k = 0; k < 4; k++)
         if (c->ev[k]) cudaEventDestroy(c->ev[k]);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -421,6 +415,14 @@ int edmd_cuda_get_stat(edmd_ctx *c, int stat, uint64_t *value)
     }
     if (stat == EDMD_STAT_LEAN_ELIGIBLE) {
         *value = edmd_lean_eligible(c, EDMD_MODE_NORMAL) ? 1 : 0;
+        return 0;
+    }
+    if (stat >= 100 && stat < 116) {   // internal: timing experiments
+        CU(cudaSetDevice(c->device));
+        unsigned long long v = 0;
+        CU(cudaMemcpyAsync(&v, c->dbg_ts + (stat - 100), sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        *value = v;
         return 0;
     }
     if (stat != EDMD_STAT_EXACT_RESCANS) return fail(c, EDMD_EINVAL, "unknown stat");
@@ -619,15 +621,17 @@ static int exchange_predict_launch(edmd_ctx *c, int mode, cudaEvent_t between)
     c->index_tile = false;
     c->pred_packed = false;
     if (edmd_tile_eligible(c, mode)) {
-        // fork: send + receive (a few small blocks, mostly waiting on NVLink) on the second stream, the
-        // partition of the owned particles on the first; both append to the same buckets (atomic cursors)
-        CU(cudaEventRecord(c->ev_fork, c->stream));
-        CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-        c->launches += edmd_launch_halo_send(c, c->stream2);
-        c->launches += edmd_launch_halo_recv_partition(c, c->stream2);
-        CU(cudaEventRecord(c->ev_join, c->stream2));
-        c->launches += edmd_launch_tile_partition_range(c, 0, c->n_owned);
-        CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        // One chain on one stream, no host or cross-stream synchronisation:
+        //   send      (first, plain launch; a few small blocks: peer stores over NVLink) lets
+        //   receive   start at once (waits for the neighbours' epoch, appends their rows to the buckets), which lets
+        //   partition (the owned particles; thousands of blocks) start beside the two -- all three append through the
+        //             same atomic cursors; receive waits for send and the partition for receive before they exit, so
+        //   sweep     which waits for the partition, sees every append of the step.
+        // (Launching the halo kernels BEHIND the partition, or on a second stream, hid nothing: the block
+        // scheduler only gets to them once the partition's last wave of blocks has been dispatched.)
+        c->launches += edmd_launch_halo_send(c, false);
+        c->launches += edmd_launch_halo_recv_partition(c);
+        c->launches += edmd_launch_tile_partition_range(c, 0, c->n_owned, c->lean_pdl);
         if (between) CU(cudaEventRecord(between, c->stream));
         c->launches += edmd_launch_tile_sweep_only(c);
         c->index_lean = true;

@@ -151,9 +151,7 @@ struct edmd_ctx {
     edmd_box box;
     edmd_dev_box dbox;
     cudaStream_t stream;
-    cudaStream_t stream2;   // the halo exchange of a slab context runs beside the partition of the owned particles
     cudaEvent_t ev[4];
-    cudaEvent_t ev_fork, ev_join;
     char err[512];
     uint64_t launches;
     bool force_generic;  // EDMD_OPT_FORCE_GENERIC: global-memory exact kernel only
@@ -235,6 +233,7 @@ struct edmd_ctx {
     edmd_ev32 *evrec;                 // event records of the last tile sweep, by particle id
     bool pred_packed;                // the predictions of the last sweep are in ev[], not yet in the five arrays
     bool tile_off;                   // EDMD_OPT_NO_TILE
+    unsigned long long *dbg_ts;      // [16] %globaltimer stamps of the fused exchange chain (timing experiments)
     int tile_dbg;                    // timing experiments (internal option 100): skip parts of k_tile_sweep
     bool index_tile;                 // the last sweep ran on the tile path (no global cell index exists)
 
@@ -308,10 +307,10 @@ int edmd_launch_halo_pack(edmd_ctx *c, int side, void *out, int cap, int32_t *co
 int edmd_launch_halo_append_row(edmd_ctx *c, const void *in, int count, int row);
 size_t edmd_halo_mem_bytes(int halo_cap);
 int edmd_launch_halo_p2p(edmd_ctx *c);
-int edmd_launch_halo_send(edmd_ctx *c, cudaStream_t st);
+int edmd_launch_halo_send(edmd_ctx *c, bool chained);
 int edmd_launch_halo_recv(edmd_ctx *c);
-int edmd_launch_halo_recv_partition(edmd_ctx *c, cudaStream_t st);
-int edmd_launch_tile_partition_range(edmd_ctx *c, int first, int n);
+int edmd_launch_halo_recv_partition(edmd_ctx *c);
+int edmd_launch_tile_partition_range(edmd_ctx *c, int first, int n, bool early);
 int edmd_launch_tile_sweep_only(edmd_ctx *c);
 int edmd_launch_cell_index(edmd_ctx *c, int mode);
 int edmd_launch_predict(edmd_ctx *c, int mode);
@@ -396,6 +395,22 @@ __device__ __forceinline__ void edmd_pdl_wait()
 {
 #if __CUDA_ARCH__ >= 900
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+__device__ __forceinline__ void edmd_stamp(unsigned long long *ts, int k)
+{
+    if (!ts) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    ts[k] = t;
+}
+
+// lets the NEXT kernel of the chain (launched with the programmatic attribute) start now
+__device__ __forceinline__ void edmd_pdl_trigger()
+{
+#if __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
 

@@ -67,6 +67,7 @@ struct SendArgs {
     const int *ack;     // [2]
     int32_t *cnt;       // [2] records listed per side
     int32_t *done;      // finished blocks
+    unsigned long long *ts;
 };
 
 // blockIdx.y = side
@@ -75,6 +76,11 @@ k_halo_send(const __grid_constant__ SendArgs a)
 {
     __shared__ bool last;
     const int side = blockIdx.y;
+    // In the fused exchange + sweep chain (edmd_cuda_exchange_predict_device) this kernel comes FIRST and
+    // lets the rest of the chain (receive, partition: launched with the programmatic attribute) start at
+    // once: a handful of small blocks here, mostly waiting on NVLink, beside the partition's thousands.
+    edmd_pdl_trigger();
+    if (blockIdx.x == 0 && side == 0 && threadIdx.x == 0) edmd_stamp(a.ts, 0);
     // do not overwrite a buffer the neighbour may still be reading
     if (threadIdx.x == 0)
         while (ld_volatile(a.ack + side) < a.epoch - 2) __nanosleep(50);
@@ -114,7 +120,10 @@ k_halo_send(const __grid_constant__ SendArgs a)
         __threadfence_system();
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) *a.done = 0;   // cnt / list stay valid until the next upload
+    if (last && threadIdx.x == 0) {
+        *a.done = 0;   // cnt / list stay valid until the next upload
+        edmd_stamp(a.ts, 1);
+    }
 }
 
 struct RecvArgs {
@@ -182,9 +191,9 @@ size_t edmd_halo_mem_bytes(int halo_cap) { return ack_offset(halo_cap) + 256; }
 // The exchange is two launches on the context's stream: send (peer stores into the neighbours'
 // inboxes; starts a new epoch) and receive (waits for the neighbours' epoch, unpacks, acks).  Work that
 // does not need the halo may be launched between the two (edmd_cuda_exchange_predict_device).
-int edmd_launch_halo_send(edmd_ctx *c, cudaStream_t st)
+int edmd_launch_halo_send(edmd_ctx *c, bool chained)
 {
-    if (!st) st = c->stream;
+    cudaStream_t st = c->stream;
     const int H = c->halo_cap;
     const int e = ++c->halo_epoch;
     const int par = e & 1;
@@ -209,7 +218,9 @@ int edmd_launch_halo_send(edmd_ctx *c, cudaStream_t st)
     sa.peer_inbox[1] = c->peer_mem[1] + inbox_offset(H, 0, par);
     sa.ack = reinterpret_cast<const int *>(c->halo_mem + ack_offset(H));
     sa.cnt = cnt; sa.done = cnt + 2;
-    k_halo_send<<<dim3((H + kThreads - 1) / kThreads, 2), kThreads, 0, st>>>(sa);
+    sa.ts = c->tile_dbg & 32 ? c->dbg_ts : nullptr;
+    (void)chained;   // always the first kernel of its chain: plain launch
+    edmd_launch(k_halo_send, dim3((H + kThreads - 1) / kThreads, 2), dim3(kThreads), 0, st, false, sa);
     return collect ? 2 : 1;
 }
 
@@ -238,6 +249,6 @@ int edmd_launch_halo_recv(edmd_ctx *c)
 
 int edmd_launch_halo_p2p(edmd_ctx *c)
 {
-    int launched = edmd_launch_halo_send(c, nullptr);
+    int launched = edmd_launch_halo_send(c, false);
     return launched + edmd_launch_halo_recv(c);
 }

@@ -54,6 +54,7 @@ constexpr int kPartThreads = 256;
 
 struct PartArgs {
     int first, n, ps, slab, dbg;
+    int late_wait;   // fused halo exchange: run BESIDE the preceding kernels of the chain, wait for them at the end
     TileGeom tg;
     edmd_dev_box b;
     const int32_t *cid;
@@ -66,6 +67,7 @@ struct PartArgs {
     int2 *ttag;
     double *trad;
     unsigned long long *overlap_key;
+    unsigned long long *ts;
 };
 
 // Append particle i (padded cell id pc, state p, radius rad) to the bucket of its tile and, when it sits
@@ -149,16 +151,26 @@ __global__ void __launch_bounds__(kPartThreads)
 k_tile_partition(const __grid_constant__ PartArgs a)
 {
     const int i = a.first + blockIdx.x * blockDim.x + threadIdx.x;
-    edmd_pdl_wait();
+    if (!a.late_wait) edmd_pdl_wait();
+    if (i == a.first) edmd_stamp(a.ts, 4);
+    if (i == a.first + a.n - 1) edmd_stamp(a.ts, 5);
     if (i == a.first && a.overlap_key) *a.overlap_key = ~0ull;   // the sweep's overlap report starts empty
-    if (i >= a.first + a.n) return;
-    const int pc = a.cid[i];
-    const double4 p = ld_sector(a.xv + i);
-    if (pc < 0) return;   // unused halo slot of a slab context
-    // radii matter only when they are not all exactly rad0 (two classes / spread inside a class)
-    const bool radii = a.flags[kFlagNotMono] != 0;
-    const double rad = radii ? a.rad[i] : a.rad0;
-    partition_one(a, i, pc, p, rad, radii);
+    if (i < a.first + a.n) {
+        const int pc = a.cid[i];
+        const double4 p = ld_sector(a.xv + i);
+        if (pc >= 0) {   // < 0: unused halo slot of a slab context
+            // radii matter only when they are not all exactly rad0 (two classes / spread inside a class)
+            const bool radii = a.flags[kFlagNotMono] != 0;
+            const double rad = radii ? a.rad[i] : a.rad0;
+            partition_one(a, i, pc, p, rad, radii);
+        }
+    }
+    // fused halo exchange: the send and receive kernels run beside this one; "this kernel is complete"
+    // must imply "they are" for the sweep kernel that waits on it.  ONE block waits -- the last one
+    // dispatched: a grid is complete when all its blocks are.  (Every block waiting kept the first waves
+    // resident until the receive kernel was through, 16 us, and the partition made no progress.)
+    if (a.late_wait && blockIdx.x == gridDim.x - 1) edmd_pdl_wait();
+    if (i == a.first + a.n - 1) edmd_stamp(a.ts, 6);
 }
 
 // Slab contexts, peer-to-peer halo: receive + partition in one kernel.  Waits for the neighbours'
@@ -184,6 +196,8 @@ k_halo_recv_partition(const __grid_constant__ RecvPartArgs a)
     const int from = blockIdx.y;
     const InboxHeader *hdr = reinterpret_cast<const InboxHeader *>(a.inbox[from]);
     const HaloRec *rec = reinterpret_cast<const HaloRec *>(a.inbox[from] + sizeof(InboxHeader));
+    edmd_pdl_trigger();   // the partition of the owned particles starts beside this kernel
+    if (blockIdx.x == 0 && from == 0 && threadIdx.x == 0) edmd_stamp(a.p.ts, 2);
     if (threadIdx.x == 0)
         while (ld_volatile(&hdr->epoch) != a.epoch) __nanosleep(50);
     __syncthreads();
@@ -224,7 +238,10 @@ k_halo_recv_partition(const __grid_constant__ RecvPartArgs a)
         *reinterpret_cast<volatile int *>(a.peer_ack[from]) = a.epoch;   // "consumed", peer store
         __threadfence_system();
         a.done[from] = 0;
+        edmd_stamp(a.p.ts, 3);
     }
+    // chained behind the send kernel: "this kernel is complete" implies "my own send is"
+    edmd_pdl_wait();
 }
 
 // ---- P2 ---------------------------------------------------------------------------
@@ -243,6 +260,7 @@ struct SweepArgs {
     const double *trad;
     edmd_ev32 *ev;
     unsigned long long *overlap_key;
+    unsigned long long *ts;
 };
 
 // Shared memory of one CTA (cap = tg.smem_cap records):
@@ -600,6 +618,10 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const TileSmem &s,
             if (p < pe) screen(j, p, py);
         }
         const float second = lo1 > 0.0f ? lo2 : fnan;   // a non-positive smallest bound is never certifiable
+        // slab contexts: the partner leaves as the caller's (global) id; fetch the winner's now, the load
+        // flies while the exact stage computes
+        const int wloc = idx >= 0 ? s.id[idx] : -1;
+        const int wglob = (wloc >= 0 && a.gid) ? a.gid[wloc] : wloc;
         const double2 mexy = s.xy[self], mev = s.vv[self];
         const double4 me = make_double4(mexy.x, mexy.y, mev.x, mev.y);
         const double rad_i = radii ? s.rad[self] : a.rad0;
@@ -668,7 +690,7 @@ __device__ __forceinline__ void tile_main(const SweepArgs &a, const TileSmem &s,
             }
         }
         // ids in shared memory are LOCAL; partners and the overlap report carry the caller's ids
-        const int partner = best_id >= 0 ? (a.gid ? a.gid[best_id] : best_id) : 0;
+        const int partner = best_id >= 0 ? (best_id == wloc ? wglob : (a.gid ? a.gid[best_id] : best_id)) : 0;
         st_ev(a.ev + id, __dadd_rn(a.t, dtc), __dadd_rn(a.t, best), partner, dirc);
         if (ov_id >= 0) {
             const unsigned long long key = ((unsigned long long)(uint32_t)(a.gid ? a.gid[id] : id) << 32) |
@@ -714,6 +736,7 @@ k_tile_sweep(const __grid_constant__ SweepArgs a)
     for (int c = tid; c <= kFC; c += kTileThreads) s.off[c] = 0;
     edmd_pdl_wait();
     const int tile = a.tiles ? a.tiles[blockIdx.x] : blockIdx.x;
+    if (blockIdx.x == 0 && tid == 0) edmd_stamp(a.ts, 7);
     const int classes = a.flags[kFlagNotMono];   // 0: one radius, 1: two classes, more: not eligible
     const double rad1 = __longlong_as_double(*reinterpret_cast<const long long *>(a.flags + kFlagRad1));
     tile_prologue(a, s, tile, false);
@@ -942,31 +965,34 @@ static PartArgs part_args(edmd_ctx *c, int first, int n)
 {
     PartArgs pa;
     pa.first = first; pa.n = n; pa.ps = c->ps; pa.slab = c->slab ? 1 : 0; pa.dbg = c->tile_dbg;
+    pa.late_wait = 0;
     pa.tg = c->tgeom; pa.b = c->dbox;
     pa.cid = c->cid; pa.xv = c->xv; pa.rad = c->rad; pa.rad0 = c->rad0;
     pa.flags = c->flags; pa.tcnt = c->tcnt; pa.tst = c->tst; pa.ttag = c->ttag; pa.trad = c->trad;
     pa.overlap_key = c->overlap_key;
+    pa.ts = c->tile_dbg & 32 ? c->dbg_ts : nullptr;
     return pa;
 }
 
 // P1 alone: (re)build the tile buckets of the resident state (particles [first, first + n))
-int edmd_launch_tile_partition_range(edmd_ctx *c, int first, int n)
+int edmd_launch_tile_partition_range(edmd_ctx *c, int first, int n, bool beside)
 {
     if (n <= 0) return 0;
-    const PartArgs pa = part_args(c, first, n);
-    // the first kernel of the chain is launched plainly: whatever precedes it on the stream completes first
+    PartArgs pa = part_args(c, first, n);
+    pa.late_wait = beside ? 1 : 0;
+    // normally the first kernel of its chain, launched plainly: whatever precedes it on the stream completes
+    // first.  `beside`: behind the halo kernels of the fused exchange, with the programmatic attribute
     edmd_launch(k_tile_partition, dim3((n + kPartThreads - 1) / kPartThreads), dim3(kPartThreads), 0, c->stream,
-                false, pa);
+                beside, pa);
     return 1;
 }
 
-int edmd_launch_tile_partition(edmd_ctx *c) { return edmd_launch_tile_partition_range(c, 0, c->n); }
+int edmd_launch_tile_partition(edmd_ctx *c) { return edmd_launch_tile_partition_range(c, 0, c->n, false); }
 
 // slab contexts with the peer-to-peer halo: receive the neighbours' boundary rows (sent by
 // edmd_launch_halo_send) and append them to the tile buckets in the same kernel
-int edmd_launch_halo_recv_partition(edmd_ctx *c, cudaStream_t st)
+int edmd_launch_halo_recv_partition(edmd_ctx *c)
 {
-    if (!st) st = c->stream;
     const int H = c->halo_cap;
     const int e = c->halo_epoch, par = e & 1;
     RecvPartArgs ra;
@@ -981,7 +1007,8 @@ int edmd_launch_halo_recv_partition(edmd_ctx *c, cudaStream_t st)
     ra.peer_ack[0] = reinterpret_cast<int *>(c->peer_mem[0] + ack_offset(H)) + 1;
     ra.peer_ack[1] = reinterpret_cast<int *>(c->peer_mem[1] + ack_offset(H)) + 0;
     ra.done = c->halo_cnt + 4;
-    k_halo_recv_partition<<<dim3((H + kPartThreads - 1) / kPartThreads, 2), kPartThreads, 0, st>>>(ra);
+    edmd_launch(k_halo_recv_partition, dim3((H + kPartThreads - 1) / kPartThreads, 2), dim3(kPartThreads), 0, c->stream,
+                c->lean_pdl, ra);
     return 1;
 }
 
@@ -996,6 +1023,7 @@ static SweepArgs sweep_args(edmd_ctx *c)
     sa.flags = c->flags; sa.tcnt = c->tcnt; sa.tkeep = c->tkeep; sa.tst = c->tst; sa.ttag = c->ttag; sa.trad = c->trad;
     sa.ev = c->evrec;
     sa.overlap_key = c->overlap_key;
+    sa.ts = c->tile_dbg & 32 ? c->dbg_ts : nullptr;
     return sa;
 }
 
@@ -1016,7 +1044,7 @@ int edmd_launch_tile_sweep_only(edmd_ctx *c)
     const SweepArgs sa = sweep_args(c);
     tile_attrs();
     edmd_launch(k_tile_sweep, dim3(c->tgeom.ntx * c->tgeom.nty), dim3(kTileThreads), tile_smem_bytes(c->tgeom, sa.rad_smem),
-                c->stream, false, sa);
+                c->stream, c->lean_pdl, sa);
     c->pred_packed = true;
     return 1;
 }

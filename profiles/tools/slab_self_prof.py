@@ -27,4 +27,12 @@ sr.exchange(None)
 tot, main = sr.ctx.bench(B.BENCH_SWEEP, warmup=3, iters=int(sys.argv[1]) if len(sys.argv) > 1 else 5,
                          flush_bytes=256 << 20)
 print("slab self-exchange: step %.1f us, K1 %.1f us" % (1e3 * tot.mean(), 1e3 * main.mean()))
+# timeline of the last step (%globaltimer, ns): send start/end, receive start/end, partition first/last block start, end, sweep start
+sr.ctx.set_option(100, 32)
+sr.ctx.bench(B.BENCH_SWEEP, warmup=1, iters=1, flush_bytes=256 << 20)
+ts = [sr.ctx.stat(100 + k) for k in range(8)]
+t0 = min(t for t in ts if t)
+names = ["send start", "send end", "recv start", "recv end", "partition first block", "partition last block", "partition end", "sweep start"]
+for nme, t in zip(names, ts):
+    print("  %-24s %8.1f us" % (nme, (t - t0) / 1e3))
 sr.close()

@@ -251,6 +251,24 @@ def profile_traffic():
     return None
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this rank's host thread (and so its pinned staging buffers, first-touch) on the CPUs next to
+    its GPU (NVML's CPU affinity of the device) when the box exposes more than one NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hdl, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def slab_sweep_ms(pkg, dist, torch, cfg, rank, world, local, steps, warm):
     """Device-resident multi-GPU step of one system: ms per step (max over ranks), K1 part, n_owned."""
     slab = pkg.slab
@@ -280,6 +298,7 @@ def run_slabs(args, pkg, rank, world, local):
     import torch.distributed as dist
 
     B = pkg.binding
+    ncpu_bound = bind_to_gpu_numa_node(local)
     n_total = args.n * world
     cfg = pkg.synth.lattice_config(n_total, PHI, SEED, shuffle=(args.order == "shuffled"))
     N, lx, ly = cfg["n"], cfg["lx"], cfg["ly"]
@@ -317,8 +336,9 @@ def run_slabs(args, pkg, rank, world, local):
         lib, h, P = sr.ctx.lib, sr.ctx._h, B._ptr
 
         def e2e_step():
+            # a thermostat tick: positions, velocities and the host's cells (radii and ids are resident)
             rc = lib.edmd_cuda_upload_owned(h, n_owned, P(own["x"]), P(own["y"]), P(own["vx"]), P(own["vy"]),
-                                            P(own["rad"]), P(own["cells"]), P(own["gid"]), 0.0)
+                                            None, P(own["cells"]), None, 0.0)
             assert rc == 0, lib.edmd_cuda_last_error(h)
             rc = lib.edmd_cuda_exchange_predict_device(h, B.MODE_NORMAL)
             assert rc == 0, lib.edmd_cuda_last_error(h)
@@ -371,9 +391,13 @@ def run_slabs(args, pkg, rank, world, local):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wc,
             "clocks": clocks,
             "e2e": {"value": N / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 52 * n_owned, "d2h_bytes_per_step": 21 * n_owned,
-                    "api": "per rank, pinned host buffers: edmd_cuda_upload_owned(x,y,vx,vy,rad,cells,ids) + "
-                           "edmd_cuda_exchange_predict_device + edmd_cuda_fetch_predictions(t_cross,dir,t_coll,partner)"},
+                    "h2d_bytes_per_step": 40 * n_owned, "d2h_bytes_per_step": 21 * n_owned,
+                    "api": "per rank, pinned host buffers: edmd_cuda_upload_owned(x,y,vx,vy,cell_xy; radii and ids resident) + "
+                           "edmd_cuda_exchange_predict_device + edmd_cuda_fetch_predictions(t_cross,dir,t_coll,partner)",
+                    "pcie_gb_per_s_per_rank": 61 * n_owned / (ms_e2e * 1e-3) / 1e9,
+                    "host_cpus_bound_per_rank": ncpu_bound,
+                    "note": "every rank moves 61 B/particle over its own PCIe link at the same time; the per-rank "
+                            "rate falls when the ranks share the host's memory system"},
             "gpu_launches": int(launches_per_step) * steps * world,
             "roofline": {"bound": "hbm", "kernel": "k_tile_sweep (K1 of the tile sweep), rank 0", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -505,7 +505,9 @@ int edmd_cuda_upload_owned(edmd_ctx *c, int n_owned, const double *x, const doub
     if (!c) return EDMD_EINVAL;
     if (!c->slab) return fail(c, EDMD_ESTATE, "not a slab context");
     if (n_owned < 0 || n_owned > c->n_cap) return fail(c, EDMD_EINVAL, "n_owned exceeds the slab capacity");
-    if (n_owned > 0 && !global_id) return fail(c, EDMD_EINVAL, "slab upload needs global ids");
+    // global_id == NULL keeps the resident ids (a tick: the same particles with new positions and velocities)
+    if (n_owned > 0 && !global_id && (!c->have_rad || n_owned != c->n_owned))
+        return fail(c, EDMD_EINVAL, "slab upload needs global ids (NULL only after an upload of the same particles)");
     return upload_impl(c, n_owned, x, y, vx, vy, rad, cell_xy, global_id, t);
 }
 

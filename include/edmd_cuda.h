@@ -209,7 +209,9 @@ int edmd_cuda_create_slab(int device, int n_capacity, double lx, double ly, int 
                           edmd_ctx **out);
 /* Owned particles of this slab (all in rows [row_lo,row_hi)); global_id[i] is
  * the id the caller knows the particle by: partner[] outputs carry global ids,
- * outputs are indexed by the LOCAL index 0..n_owned-1. */
+ * outputs are indexed by the LOCAL index 0..n_owned-1.  rad == NULL / global_id == NULL
+ * keep the resident radii / ids (a thermostat tick: the same n_owned particles with new
+ * positions and velocities). */
 int edmd_cuda_upload_owned(edmd_ctx *ctx, int n_owned, const double *x, const double *y,
                            const double *vx, const double *vy, const double *rad,
                            const int32_t *cell_xy, const int32_t *global_id, double t);

@@ -35,7 +35,7 @@ STAT_PCF_SKIPPED_TILE_PAIRS = 4
 STAT_LEAN_DECLINES = 5
 STAT_LEAN_ELIGIBLE = 6
 
-# every symbol include/edmd_cuda.h declares
+# every symbol include/edmd_cuda.h declares (+ edmd_cuda_bench from the bench-only header)
 SYMBOLS = [
     "edmd_cuda_create", "edmd_cuda_destroy", "edmd_cuda_last_error",
     "edmd_cuda_get_box", "edmd_cuda_launch_count", "edmd_cuda_upload",

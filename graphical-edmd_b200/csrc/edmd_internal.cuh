@@ -41,6 +41,7 @@
 #include <stdint.h>
 
 #include "edmd_cuda.h"
+#include "edmd_cuda_bench.h"
 
 struct edmd_dev_box {
     int n, nx, ny, nc;     // ny = rows of the GLOBAL cell grid

@@ -377,24 +377,6 @@ int edmd_cuda_boop_voronoi(edmd_ctx *ctx, double *q5, double *q6, double *q7, do
  * its number of edges.  Any output may be NULL. */
 int edmd_cuda_voronoi_cells(edmd_ctx *ctx, double *area, double *perimeter, int32_t *neighbors);
 
-/* ---- measurement helpers (used by bench.py; timed with CUDA events on the
- * context's own stream, inputs resident in HBM) ------------------------ */
-
-/* kernel ids for edmd_cuda_bench */
-#define EDMD_BENCH_SWEEP 0  /* K0 (cell index) + K1 (predict) */
-#define EDMD_BENCH_FREEFLY 1
-#define EDMD_BENCH_BOOP 2
-#define EDMD_BENCH_PCF 3    /* uses dr / max_r arguments */
-#define EDMD_BENCH_VORONOI 4 /* K5: grid sort + one Voronoi cell per particle (psi, area, perimeter) */
-
-/* Runs `warmup` untimed and `iters` timed passes of the chosen device path,
- * writing `flush_bytes` of scratch between passes (L2 flush, outside the timed
- * events) when flush_bytes > 0.  ms_total[iters] = whole pass,
- * ms_main[iters] = the dominant kernel alone (K1 for the sweep). */
-int edmd_cuda_bench(edmd_ctx *ctx, int what, int mode, double dr, double max_r,
-                    int warmup, int iters, size_t flush_bytes, float *ms_total,
-                    float *ms_main);
-
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,8 @@ from conftest import ROOT, has_gpu
 
 
 def header_symbols():
-    text = (ROOT / "include" / "edmd_cuda.h").read_text()
+    # the drop-in header and the bench-only header (edmd_cuda_bench.h: not part of the interface)
+    text = "".join(p.read_text() for p in sorted((ROOT / "include").glob("*.h")))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(edmd_cuda_\w+)\s*\(", text)))
 
@@ -59,3 +60,7 @@ def test_synth_is_deterministic_and_non_overlapping(pkg):
     dy -= ly * np.rint(dy / ly)
     d2 = dx * dx + dy * dy + 1e9 * np.eye(n)
     assert (d2 >= 4 * a["rad"][:, None] * a["rad"][None, :]).all()
+
+
+def test_bench_helper_is_not_in_the_drop_in_header():
+    assert "edmd_cuda_bench" not in (ROOT / "include" / "edmd_cuda.h").read_text()

@@ -13,7 +13,7 @@ ARCH       = -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS  = $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Iinclude -I$(CSRC) \
              -Xcompiler -fPIC,-Wall,-Wno-unused-function
 CU_SRCS    = $(CSRC)/edmd_cuda.cu $(CSRC)/cell_index.cu $(CSRC)/predict.cu $(CSRC)/analysis.cu $(CSRC)/halo.cu \
-             $(CSRC)/lean_index.cu $(CSRC)/predict_lean.cu $(CSRC)/tile_sweep.cu $(CSRC)/calendar.cu $(CSRC)/analysis_weighted.cu $(CSRC)/analysis_pcf_sorted.cu $(CSRC)/analysis_voronoi.cu $(CSRC)/thermostat.cu
+             $(CSRC)/lean_index.cu $(CSRC)/predict_lean.cu $(CSRC)/cell_sweep.cu $(CSRC)/calendar.cu $(CSRC)/analysis_weighted.cu $(CSRC)/analysis_pcf_sorted.cu $(CSRC)/analysis_voronoi.cu $(CSRC)/thermostat.cu
 CU_OBJS    = $(CU_SRCS:.cu=.o)
 LIB        = $(PKG)/libedmd_cuda.so
 

@@ -1,0 +1,962 @@
+// cell_sweep.cu -- the whole-system prediction sweep (NORMAL mode, one or two
+// radius classes) in TWO kernels over FIXED-CAPACITY CELL SLOTS.  Replaces, bit for bit,
+//   cellListInit / addToCell   src/EDMD.c:1906-1920, 2053-2078   (the cell index)
+//   crossingEventNormal        src/EDMD.c:2405-2482
+//   collisionEventNormal       src/EDMD.c:2829-3102   (scan 2959-3003, select 2991-2995)
+//   collisionTimeNormal        src/EDMD.c:2661-2723
+//
+// The reference's cells are at least one disk diameter wide, so a cell holds ONE disk
+// nearly always (jittered lattice at phi = 0.70: 12.5 % empty, 85.8 % one, 1.8 % two;
+// reference-grown liquid: 15.0 / 80.6 / 4.4 %; phi = 0.85: 2.7 / 86.2 / 11.1 %).  The cell
+// index is therefore kSlotK PLANES over the padded cell grid: plane s holds the s-th
+// arrival of every cell.  Plane 0 is dense (what the sweep streams), planes 1.. are
+// sparse (read only where a cell's counter says so).
+//
+//   P1  k_cell_partition   one thread per particle (memory order = particle id):
+//       slot = atomicAdd(count[cell]); the FP64 state (x, y, vx, vy = one 32-byte sector,
+//       one 256-bit store) goes to plane `slot` at the cell's index, the particle id (and
+//       the radius when the radii are not all exactly rad0) beside it.  No histogram pass,
+//       no scan, no tiles, no copies for neighbouring tiles, no tag: the cell IS the address.
+//   P2  k_cell_sweep       one CTA per TILE of kTX x kTY cells.  It streams the counters
+//       and plane 0 of its FRAME (the tile + a one-cell ring: everything the reference's
+//       3 x 3 scan of the tile's particles touches; the ring of an edge tile is the
+//       opposite edge of the grid, PBCcellX/Y src/EDMD.c:2110-2124) into shared memory IN
+//       FRAME-CELL ORDER -- no binning, no compaction: an empty cell is a NaN record that the
+//       screening drops by itself -- and the few disks of planes 1.. into a short list behind
+//       it.  Every particle of the tile then screens its 3 x 3 neighbourhood, fully unrolled
+//       (nine plane-0 records at fixed offsets + the listed extras), in FP32 (the certified
+//       lower bounds of lean.cuh / predict_lean.cu: same arithmetic, same error model),
+//       evaluates crossingEventNormal and the winner's collisionTimeNormal exactly as the
+//       reference does from the FP64 states in shared memory, certifies the winner against
+//       the second-smallest bound or re-scans the neighbourhood in FP64 in the reference's
+//       order, and writes ONE 32-byte event record per particle (edmd_ev32) by particle id.
+//       k_unpack_events turns the records into the ABI's five arrays when a caller fetches them.
+//
+// The counters are double-buffered: a consumer kernel (sweep or psi6) zeroes the OTHER
+// buffer's cells of its tile, so the next partition finds zeros without a memset kernel and
+// the counters of the current partition stay valid for later passes (psi6 after a sweep).
+//
+// The state must be eligible exactly as for the lean sweep (lean.cuh); a cell with more
+// than kSlotK disks, or a tile with more extras than its shared memory provides for
+// (clustered tiny disks), makes the sweep DECLINE through kFlagLeanFail and the host
+// re-runs it on the five-kernel lean chain / the full FP64 path.
+#include "lean.cuh"
+#include "pairmath.cuh"
+#include "halo.cuh"
+
+namespace {
+
+constexpr int kPartThreads = 256;
+
+struct PartArgs {
+    int first, n, ncp, dbg;
+    int late_wait;   // fused halo exchange: run BESIDE the preceding kernels of the chain, wait for them at the end
+    const int32_t *cid;
+    const double4 *xv;
+    const double *rad;
+    double rad0;
+    int32_t *flags;
+    int32_t *ccnt;   // counters of the partition being built (zero on entry)
+    double4 *pst;    // [kSlotK][ncp] FP64 states
+    int32_t *pid;    // [kSlotK][ncp] particle ids
+    double *prad;    // [kSlotK][ncp] radii (written only when the radii are not all exactly rad0)
+    unsigned long long *overlap_key;
+    unsigned long long *ts;
+};
+
+// File particle i (padded cell id pc, state p, radius rad) in the next free slot of its cell.
+__device__ __forceinline__ void partition_one(const PartArgs &a, int i, int pc, const double4 &p, double rad,
+                                              const bool radii)
+{
+    const int s = (a.dbg & 16) ? 0 : atomicAdd(&a.ccnt[pc], 1);   // (dbg: timing experiments, option 100)
+    if (a.dbg & 8) return;
+    if (s < kSlotK) {
+        const size_t slot = (size_t)s * a.ncp + pc;
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(a.pst + slot), "d"(p.x), "d"(p.y), "d"(p.z), "d"(p.w)
+                     : "memory");
+        a.pid[slot] = i;
+        if (radii) a.prad[slot] = rad;
+    } else {
+        atomicOr(&a.flags[kFlagLeanFail], 1);   // a cell is full: the sweep declines
+    }
+}
+
+__global__ void __launch_bounds__(kPartThreads)
+k_cell_partition(const __grid_constant__ PartArgs a)
+{
+    const int i = a.first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (!a.late_wait) edmd_pdl_wait();
+    if (i == a.first) edmd_stamp(a.ts, 4);
+    if (i == a.first + a.n - 1) edmd_stamp(a.ts, 5);
+    if (i == a.first && a.overlap_key) *a.overlap_key = ~0ull;   // the sweep's overlap report starts empty
+    if (i < a.first + a.n) {
+        const int pc = a.cid[i];
+        const double4 p = ld_sector(a.xv + i);
+        if (pc >= 0) {   // < 0: unused halo slot of a slab context
+            // radii matter only when they are not all exactly rad0 (two classes / spread inside a class)
+            const bool radii = a.flags[kFlagNotMono] != 0;
+            const double rad = radii ? a.rad[i] : a.rad0;
+            partition_one(a, i, pc, p, rad, radii);
+        }
+    }
+    // fused halo exchange: the send and receive kernels run beside this one; "this kernel is complete"
+    // must imply "they are" for the sweep kernel that waits on it.  ONE block waits -- the last one
+    // dispatched: a grid is complete when all its blocks are.  (Every block waiting kept the first waves
+    // resident until the receive kernel was through, 16 us, and the partition made no progress.)
+    if (a.late_wait && blockIdx.x == gridDim.x - 1) edmd_pdl_wait();
+    if (i == a.first + a.n - 1) edmd_stamp(a.ts, 6);
+}
+
+// Slab contexts, peer-to-peer halo: receive + partition in one kernel.  Waits for the neighbours'
+// epoch (their k_halo_send wrote the records into my inbox over NVLink), unpacks each record into the
+// fixed halo region of the resident arrays -- exactly what k_halo_recv (halo.cu) does -- and files
+// it in the cell slots right away; acks back.  blockIdx.y = from (0: lower neighbour's records ->
+// local row 0, 1: upper -> row nl-1).
+struct RecvPartArgs {
+    PartArgs p;
+    int H, epoch, ps, row[2];
+    const char *inbox[2];
+    double4 *xv;
+    double *rad;
+    int32_t *cid, *gid;
+    int *peer_ack[2];
+    int32_t *done;
+};
+
+__global__ void __launch_bounds__(kPartThreads)
+k_halo_recv_partition(const __grid_constant__ RecvPartArgs a)
+{
+    __shared__ bool last;
+    const int from = blockIdx.y;
+    const InboxHeader *hdr = reinterpret_cast<const InboxHeader *>(a.inbox[from]);
+    const HaloRec *rec = reinterpret_cast<const HaloRec *>(a.inbox[from] + sizeof(InboxHeader));
+    edmd_pdl_trigger();   // the partition of the owned particles starts beside this kernel
+    if (blockIdx.x == 0 && from == 0 && threadIdx.x == 0) edmd_stamp(a.p.ts, 2);
+    if (threadIdx.x == 0)
+        while (ld_volatile(&hdr->epoch) != a.epoch) __nanosleep(50);
+    __syncthreads();
+    const int count = ld_volatile(&hdr->count);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < a.H) {
+        const int i = a.p.first + from * a.H + k;
+        if (k < count) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(rec + k);
+            HaloRec r;
+            uint4 *dst = reinterpret_cast<uint4 *>(&r);
+            dst[0] = __ldcv(src); dst[1] = __ldcv(src + 1); dst[2] = __ldcv(src + 2);
+            const double4 p = make_double4(r.x, r.y, r.vx, r.vy);
+            const int pc = a.row[from] * a.ps + r.cell;
+            a.xv[i] = p;
+            a.rad[i] = r.rad;
+            a.gid[i] = r.gid;
+            a.cid[i] = pc;
+            // keep the sweep's eligibility facts current (lean.cuh)
+            edmd_note_radius(a.p.flags, r.rad, a.p.rad0);
+            float vm = __double2float_ru(fmax(fabs(r.vx), fabs(r.vy)));
+            if (!(vm == vm)) vm = __int_as_float(0x7f800000);
+            if (__float_as_int(vm) > a.p.flags[kFlagVmax])
+                atomicMax(reinterpret_cast<unsigned int *>(&a.p.flags[kFlagVmax]), (unsigned)__float_as_int(vm));
+            // the owned particles were partitioned with the radius facts of the upload; a halo disk of
+            // another radius class raises kFlagNotMono now and the sweep kernel declines (rad_smem)
+            partition_one(a.p, i, pc, p, r.rad, true);
+        } else {
+            a.cid[i] = -1;   // unused slot
+            a.gid[i] = -1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(a.done + from, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(a.peer_ack[from]) = a.epoch;   // "consumed", peer store
+        __threadfence_system();
+        a.done[from] = 0;
+        edmd_stamp(a.p.ts, 3);
+    }
+    // chained behind the send kernel: "this kernel is complete" implies "my own send is"
+    edmd_pdl_wait();
+}
+
+// ---- P2 ---------------------------------------------------------------------------
+struct SweepArgs {
+    TileGeom tg;
+    edmd_dev_box b;
+    double t, rad0;
+    int n_owned, dbg, rad_smem, ps, ncp, slab;
+    const int32_t *gid;
+    int32_t *flags;
+    const int32_t *ccnt;   // counters of the current partition
+    int32_t *czero;        // the other counter buffer: this kernel zeroes the cells of its tile
+    const double4 *pst;
+    const int32_t *pid;
+    const double *prad;
+    edmd_ev32 *ev;
+    unsigned long long *overlap_key;
+    unsigned long long *ts;
+};
+
+// Shared memory of one CTA.  Index p < kFC = the plane-0 record of frame cell p; p >= kFC = extra
+// number p - kFC (a disk of planes 1..).  cap = kFC + tg.ecap.
+//   xy    double2[cap]  FP64 positions              (two 16-byte arrays instead of one 32-byte
+//   vv    double2[cap]  FP64 velocities              record: 128-bit accesses stay conflict-free)
+//   scr   float4[cap]   screening records (NaN: empty cell)
+//   rad   double[cap]   radii (only when the radii are not all exactly rad0)
+//   id    int[cap]      particle ids, -1: empty (local ids in a slab context)
+//   bits  u64[kFH]      per frame row: bit fx set = cell (fx, fy) has extras
+//   xinfo u16[kFC]      first extra | (number of extras << 12) of a cell whose bit is set
+//   ecell u16[ecap]     home frame cell of every extra
+struct CellSmem {
+    double2 *xy, *vv;
+    float4 *scr;
+    double *rad;
+    int *id;
+    unsigned long long *bits;
+    unsigned short *xinfo, *ecell;
+    int *misc;   // [0] extras listed, [1] decline
+    LeanConsts *K;
+};
+
+__host__ __device__ inline size_t cell_smem_bytes(int ecap, int rad_smem, bool boop)
+{
+    const size_t cap = (size_t)kFC + ecap;
+    size_t b = cap * 16;                        // xy
+    if (!boop) b += cap * 32;                   // vv, scr
+    if (!boop && rad_smem) b += cap * 8;        // rad
+    b += sizeof(unsigned long long) * kFH;      // bits
+    b += cap * 4;                               // id
+    b += 16;                                    // misc
+    b += (sizeof(LeanConsts) + 15) & ~(size_t)15;
+    b += sizeof(unsigned short) * (kFC + ecap); // xinfo, ecell
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ CellSmem carve(unsigned char *base, int ecap, int rad_smem, bool boop)
+{
+    const size_t cap = (size_t)kFC + ecap;
+    CellSmem s;
+    s.xy = reinterpret_cast<double2 *>(base);
+    base += cap * 16;
+    s.vv = nullptr;
+    s.scr = nullptr;
+    s.rad = nullptr;
+    if (!boop) {
+        s.vv = reinterpret_cast<double2 *>(base);
+        base += cap * 16;
+        s.scr = reinterpret_cast<float4 *>(base);
+        base += cap * 16;
+        if (rad_smem) {
+            s.rad = reinterpret_cast<double *>(base);
+            base += cap * 8;
+        }
+    }
+    s.bits = reinterpret_cast<unsigned long long *>(base);
+    base += sizeof(unsigned long long) * kFH;
+    s.id = reinterpret_cast<int *>(base);
+    base += cap * 4;
+    s.misc = reinterpret_cast<int *>(base);
+    base += 16;
+    s.K = reinterpret_cast<LeanConsts *>(base);
+    base += (sizeof(LeanConsts) + 15) & ~(size_t)15;
+    s.xinfo = reinterpret_cast<unsigned short *>(base);
+    s.ecell = s.xinfo + kFC;
+    return s;
+}
+
+__device__ __forceinline__ void st_ev(edmd_ev32 *dst, double t_cross, double t_coll, int partner, int dir)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst),
+                 "r"(__double2loint(t_cross)), "r"(__double2hiint(t_cross)), "r"(__double2loint(t_coll)),
+                 "r"(__double2hiint(t_coll)), "r"(partner), "r"(dir | (EDMD_EV_COLLISION << 8)), "r"(0), "r"(0)
+                 : "memory");
+}
+
+// where a tile sits in the grid
+struct TilePos {
+    int txi, tyi;   // tile column / row
+    int tw, th;     // its size in cells (the last tile column / row of the grid may be smaller)
+    int x0, y0;     // its first cell column / local row
+};
+__device__ __forceinline__ TilePos tile_pos(const TileGeom &tg, int tile)
+{
+    TilePos t;
+    t.tyi = tile / tg.ntx;
+    t.txi = tile - t.tyi * tg.ntx;
+    t.tw = t.txi == tg.ntx - 1 ? tg.wlast : kTX;
+    t.th = t.tyi == tg.nty - 1 ? tg.hlast : kTY;
+    t.x0 = t.txi * kTX;
+    t.y0 = t.tyi * kTY;
+    return t;
+}
+
+// The other counter buffer goes back to zero for the cells of this tile (nobody reads it: its last
+// consumer completed before the chain of this sweep began).
+__device__ __forceinline__ void zero_other_counters(const SweepArgs &a, const TilePos &tp)
+{
+    for (int k = threadIdx.x; k < kTX * kTY; k += kTileThreads) {
+        const int r = k / kTX, x = k - r * kTX;
+        if (r < tp.th && x < tp.tw) a.czero[(tp.y0 + r) * a.ps + tp.x0 + x + 1] = 0;
+    }
+}
+
+// Stream the frame of one tile into shared memory: counters + plane 0 in frame-cell order, the disks of
+// planes 1.. into the extras list.  `store(pos, X, Yl, state, radius, id)` writes one record (X, Yl = the
+// cell it is FILED under, a ring cell at the periodic edge being the opposite edge of the grid),
+// `store_empty(pos)` marks a cell without a disk.  SORT: the disks of a cell are placed in ascending
+// particle id (plane 0 = the smallest), so that sums over a neighbourhood run in one fixed order.
+// Ends with a barrier; returns false (for the whole CTA) when the extras do not fit.
+template <bool SORT, class Store, class Empty>
+__device__ __forceinline__ bool frame_load(const SweepArgs &a, const CellSmem &s, const TilePos &tp, const bool radii,
+                                           Store store, Empty store_empty)
+{
+    const int tid = threadIdx.x;
+    const int nx = a.b.nx, nl = a.b.nl;
+    constexpr int kLoads = (kFC + kTileThreads - 1) / kTileThreads;
+    int pc[kLoads], n[kLoads], id0[kLoads];
+    short Xs[kLoads], Ys[kLoads];
+    double4 st0[kLoads];
+    double rad0[kLoads];
+#pragma unroll
+    for (int q = 0; q < kLoads; q++) {
+        const int fc = tid + q * kTileThreads;
+        pc[q] = -1;
+        n[q] = 0;
+        id0[q] = -1;
+        Xs[q] = Ys[q] = 0;
+        st0[q] = make_double4(0, 0, 0, 0);
+        rad0[q] = a.rad0;
+        if (fc < kFC) {
+            const int fy = fc / kFW, fx = fc - fy * kFW;
+            int X = tp.x0 + fx - 1, Yl = tp.y0 + fy - 1;
+            bool valid = fx <= tp.tw + 1 && fy <= tp.th + 1;
+            X = X < 0 ? X + nx : (X >= nx ? X - nx : X);
+            if (Yl < 0 || Yl >= nl) {
+                if (a.slab) valid = false;   // a slab's rows are not periodic: rows 0 and nl-1 ARE the halo
+                Yl = Yl < 0 ? Yl + nl : Yl - nl;
+            }
+            if (valid) {
+                const int c = Yl * a.ps + X + 1;
+                pc[q] = c;
+                Xs[q] = (short)X;
+                Ys[q] = (short)Yl;
+                n[q] = a.ccnt[c];
+                st0[q] = ld_sector(a.pst + c);
+                id0[q] = a.pid[c];
+                if (radii) rad0[q] = a.prad[c];
+            }
+        }
+    }
+    // the loads are in flight; the list head, the row bits (zeroed by the caller) and whatever else the
+    // caller prepared become visible to the CTA meanwhile
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kLoads; q++) {
+        const int fc = tid + q * kTileThreads;
+        if (fc >= kFC) continue;
+        const int nn = min(n[q], kSlotK);
+        if (nn == 0) {
+            store_empty(fc);
+            continue;
+        }
+        const int c = pc[q];
+        const int X = Xs[q], Yl = Ys[q];
+        if (nn == 1) {
+            store(fc, X, Yl, st0[q], rad0[q], id0[q]);
+            continue;
+        }
+        // more than one disk in the cell: the others go to the extras list, contiguously
+        const int m = nn - 1;
+        const int e0 = atomicAdd(&s.misc[0], m);
+        if (e0 + m > a.tg.ecap) {
+            s.misc[1] = 1;
+            store_empty(fc);
+            continue;
+        }
+        const int fy = fc / kFW, fx = fc - fy * kFW;
+        s.xinfo[fc] = (unsigned short)(e0 | (m << 12));
+        atomicOr(&s.bits[fy], 1ull << fx);
+        for (int k = 0; k < nn; k++) {
+            const size_t slot = (size_t)k * a.ncp + c;
+            const int idk = k == 0 ? id0[q] : a.pid[slot];
+            int rank = k;
+            if (SORT) {
+                rank = 0;
+                for (int k2 = 0; k2 < nn; k2++) rank += a.pid[(size_t)k2 * a.ncp + c] < idk ? 1 : 0;
+            }
+            const double4 stk = k == 0 ? st0[q] : ld_sector(a.pst + slot);
+            const double radk = k == 0 ? rad0[q] : (radii ? a.prad[slot] : a.rad0);
+            const int pos = rank == 0 ? fc : kFC + e0 + rank - 1;
+            store(pos, X, Yl, stk, radk, idk);
+            if (rank > 0) s.ecell[e0 + rank - 1] = (unsigned short)fc;
+        }
+    }
+    __syncthreads();
+    return s.misc[1] == 0;
+}
+
+// ---- sweep: every particle of the tile ---------------------------------------------
+template <bool TWO>
+__device__ __forceinline__ void cell_main(const SweepArgs &a, const CellSmem &s, const TilePos &tp, const bool radii)
+{
+    const int tid = threadIdx.x;
+    const float fnan = __int_as_float(0x7fffffff);
+    const bool fits = frame_load<false>(
+        a, s, tp, radii,
+        [&](int pos, int X, int Yl, const double4 &st, double rad, int id) {
+            // screening record, relative to the centre of the filed cell (lean.cuh)
+            float4 r;
+            r.x = __double2float_rn(__dsub_rn(st.x, __dmul_rn((double)X + 0.5, a.b.csx)));
+            r.y = __double2float_rn(__dsub_rn(st.y, __dmul_rn((double)edmd_global_row(a.b, Yl) + 0.5, a.b.csy)));
+            r.z = __double2float_rn(st.z);
+            r.w = __double2float_rn(st.w);
+            if (TWO) r.w = __int_as_float((__float_as_int(r.w) & ~1) | (edmd_same_class(rad, a.rad0) ? 0 : 1));
+            s.xy[pos] = make_double2(st.x, st.y);
+            s.vv[pos] = make_double2(st.z, st.w);
+            s.scr[pos] = r;
+            s.id[pos] = id;
+            if (radii) s.rad[pos] = rad;
+        },
+        [&](int pos) {
+            s.scr[pos] = make_float4(fnan, fnan, fnan, fnan);
+            s.id[pos] = -1;
+        });
+    if (!fits || !s.K->ok) {   // extras beyond the frame's list, or a velocity scale outside the FP32-safe range
+        if (tid == 0) atomicOr(&a.flags[kFlagLeanFail], 1);
+        return;
+    }
+    const int tw = tp.tw, th = tp.th;
+    const int ne = s.misc[0];
+    const int nrow_items = th * 32;
+    const int nitems = (a.dbg & 4) ? 0 : nrow_items + ne;
+    const LeanConsts K = *s.K;
+#pragma unroll 1
+    for (int w = tid; w < nitems; w += kTileThreads) {
+        // work item: a cell of the tile (its plane-0 disk), then the extras
+        int p, c, fx, fy;
+        if (w < nrow_items) {
+            fy = (w >> 5) + 1;
+            fx = (w & 31) + 1;
+            c = fy * kFW + fx;
+            p = c;
+            if (fx > tw) continue;
+        } else {
+            const int e = w - nrow_items;
+            c = s.ecell[e];
+            fy = c / kFW;
+            fx = c - fy * kFW;
+            p = kFC + e;
+            if (fx < 1 || fx > tw || fy < 1 || fy > th) continue;   // an extra of the ring
+        }
+        const int id = s.id[p];
+        if (id < 0 || id >= a.n_owned) continue;   // empty cell; halo copy from a neighbouring slab: never predicted
+        const float4 own = s.scr[p];
+        // dx = rx_j - (rx_i - k csx), k = column(j) - column(i) in {-1, 0, 1}
+        const float pxs[3] = {__fadd_rn(own.x, K.csx), own.x, __fsub_rn(own.x, K.csx)};
+        const float pys[3] = {__fadd_rn(own.y, K.csy), own.y, __fsub_rn(own.y, K.csy)};
+        const bool own1 = TWO && (__float_as_int(own.w) & 1);
+        const float cc_a = own1 ? K.Cc01 : K.Cc00, cc_b = own1 ? K.Cc11 : K.Cc01;
+        float lo1 = __int_as_float(0x7f800000), lo2 = __int_as_float(0x7f800000);   // two smallest bounds
+        int idx = -1;
+        auto screen = [&](int q, float px, float py, bool maybe_self) {
+            const float4 qq = s.scr[q];
+            const float dx = __fsub_rn(qq.x, px), dy = __fsub_rn(qq.y, py);
+            const float dvx = __fsub_rn(qq.z, own.z), dvy = __fsub_rn(qq.w, own.w);
+            const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+            const float v2 = __fmaf_rn(dvy, dvy, __fmul_rn(dvx, dvx));
+            const float bb = __fmaf_rn(dy, dvy, __fmul_rn(dx, dvx));
+            const float psi = __fmaf_rn(d2, K.inv_rho2, __fmaf_rn(v2, K.inv_om2, 1.0f));
+            const float clo = __fmaf_rn(d2, K.A, TWO ? ((__float_as_int(qq.w) & 1) ? -cc_b : -cc_a) : -cc_a);
+            const float det = __fmaf_rn(-v2, clo, __fmul_rn(bb, bb));
+            const float detu = __fmaf_rn(__fmul_rn(K.Kdet, psi), psi, det);
+            const float bup = __fmaf_rn(K.Kb, psi, -bb);
+            const float sq = __fmul_rn(detu, rsqrt_f32(detu));   // NaN when det_up <= 0: dropped below
+            const float den = __fadd_rn(sq, bup);
+            float tl = __fmul_rn(clo, rcp_f32(den));
+            // an empty cell is a NaN record: bup is NaN, the test fails, the candidate is dropped
+            const bool keepc = maybe_self ? ((bup > 0.0f) && (q != p)) : (bup > 0.0f);
+            tl = keepc ? tl : fnan;
+            // (lo1, lo2) <- two smallest of {lo1, lo2, tl}; min / max drop NaN operands
+            idx = tl < lo1 ? q : idx;
+            lo2 = fmaxf(lo1, fminf(lo2, tl));
+            lo1 = fminf(lo1, tl);
+        };
+        // extras in the 3 x 3 block: bit 3 j + k
+        unsigned xm = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) xm |= ((unsigned)(s.bits[fy + j - 1] >> (fx - 1)) & 7u) << (3 * j);
+        if (!(a.dbg & 1)) {
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) screen(c + (j - 1) * kFW + (k - 1), pxs[k], pys[j], j == 1 && k == 1);
+            unsigned m = xm;
+#pragma unroll 1
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int j = (b * 11) >> 5, k = b - 3 * j;
+                const unsigned info = s.xinfo[c + (j - 1) * kFW + (k - 1)];
+                const int q0 = kFC + (info & 0xfff), qn = info >> 12;
+                const float px = k == 0 ? pxs[0] : (k == 1 ? pxs[1] : pxs[2]);
+                const float py = j == 0 ? pys[0] : (j == 1 ? pys[1] : pys[2]);
+#pragma unroll 1
+                for (int q = q0; q < q0 + qn; q++) screen(q, px, py, true);
+            }
+        }
+        const float second = lo1 > 0.0f ? lo2 : fnan;   // a non-positive smallest bound is never certifiable
+        // slab contexts: the partner leaves as the caller's (global) id; fetch the winner's now, the load
+        // flies while the exact stage computes
+        const int wloc = idx >= 0 ? s.id[idx] : -1;
+        const int wglob = (wloc >= 0 && a.gid) ? a.gid[wloc] : wloc;
+        const double2 mexy = s.xy[p], mev = s.vv[p];
+        const double rad_i = radii ? s.rad[p] : a.rad0;
+        if (a.dbg & 2) {
+            st_ev(a.ev + id, (double)second + mexy.x, 0.0, idx, 0);
+            continue;
+        }
+        // ---- exact: crossing + the winner's pair time, as the reference computes them ----
+        const int X = tp.x0 + fx - 1, Yl = tp.y0 + fy - 1;
+        SRec p1;
+        p1.x = mexy.x; p1.y = mexy.y; p1.vx = mev.x; p1.vy = mev.y;
+        p1.rad = rad_i; p1.id = id; p1.pc = 0;
+        const double four_r1 = __dmul_rn(4.0, p1.rad);
+        double dtc;
+        int dirc;
+        crossing_fast<true>(a.b, p1, X, edmd_global_row(a.b, Yl), dtc, dirc);
+        double best = EDMD_NEVER;
+        int best_id = -1, best_pc = -1, ov_id = -1, ov_pc = -1;
+        bool certified = idx < 0;   // no candidate can collide: partner 0 at t + 1e26
+        if (idx >= 0) {
+            const double2 wxy = s.xy[idx], wv = s.vv[idx];
+            SRec p2;
+            p2.x = wxy.x; p2.y = wxy.y; p2.vx = wv.x; p2.vy = wv.y;
+            p2.rad = radii ? s.rad[idx] : a.rad0; p2.id = wloc; p2.pc = 0;
+            double bb, v2, cc, b2, vc;
+            pair_terms<true>(a.b, p1, four_r1, p2, bb, v2, cc, b2, vc);
+            const double det = __dsub_rn(b2, vc);
+            const double T = __ddiv_rn(__dsub_rn(-bb, __dsqrt_rn(det)), v2);
+            // a real collision (the reference's branches) and every other candidate's lower
+            // bound above the exact time (a NaN bound or time fails the test)
+            certified = !(bb > 0) && (det >= 0) && ((double)second > T);
+            best = T;
+            best_id = p2.id;
+        }
+        auto gidx = [&](int q) { return a.gid ? a.gid[q] : q; };   // the caller's (global) id of a local one
+        if (!certified) {
+            // the plain FP64 loop in the reference's order with its tie rule (first in scan
+            // order = earlier cell, then larger id = its linked-list order after cellListInit)
+            atomicAdd(reinterpret_cast<unsigned int *>(a.flags + kFlagRescans), 1u);
+            best = EDMD_NEVER;
+            best_id = -1;
+            auto cand = [&](int q, int scan_cell) {
+                SRec p2;
+                const double2 qxy = s.xy[q], qv = s.vv[q];
+                p2.x = qxy.x; p2.y = qxy.y; p2.vx = qv.x; p2.vy = qv.y;
+                p2.rad = radii ? s.rad[q] : a.rad0; p2.id = s.id[q];
+                p2.pc = scan_cell;
+                bool ov = false;
+                const double dt = pair_time_normal<true>(a.b, p1, four_r1, p2, ov);
+                if (ov && (ov_id < 0 || (p2.pc == ov_pc && gidx(p2.id) > gidx(ov_id)))) {
+                    ov_id = p2.id;
+                    ov_pc = p2.pc;
+                }
+                if (best > dt || (best == dt && best_id >= 0 && p2.pc == best_pc && gidx(p2.id) > gidx(best_id))) {
+                    best = dt;
+                    best_id = p2.id;
+                    best_pc = p2.pc;
+                }
+            };
+#pragma unroll 1
+            for (int b = 0; b < 9; b++) {
+                const int j = (b * 11) >> 5, k = b - 3 * j;
+                const int q = c + (j - 1) * kFW + (k - 1);
+                if (q != p && s.id[q] >= 0) cand(q, b);   // `p1 != p2` is identity
+                if ((xm >> b) & 1u) {
+                    const unsigned info = s.xinfo[q];
+                    const int q0 = kFC + (info & 0xfff), qn = info >> 12;
+#pragma unroll 1
+                    for (int e = q0; e < q0 + qn; e++)
+                        if (e != p) cand(e, b);
+                }
+            }
+        }
+        // ids in shared memory are LOCAL; partners and the overlap report carry the caller's ids
+        const int partner = best_id >= 0 ? (best_id == wloc ? wglob : (a.gid ? a.gid[best_id] : best_id)) : 0;
+        st_ev(a.ev + id, __dadd_rn(a.t, dtc), __dadd_rn(a.t, best), partner, dirc);
+        if (ov_id >= 0) {
+            const unsigned long long key = ((unsigned long long)(uint32_t)(a.gid ? a.gid[id] : id) << 32) |
+                                           (uint32_t)(a.gid ? a.gid[ov_id] : ov_id);
+            atomicMin(a.overlap_key, key);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads, kTileCtas)
+k_cell_sweep(const __grid_constant__ SweepArgs a)
+{
+    extern __shared__ __align__(128) unsigned char cell_smem[];
+    const CellSmem s = carve(cell_smem, a.tg.ecap, a.rad_smem, false);
+    const int tid = threadIdx.x;
+    const TilePos tp = tile_pos(a.tg, blockIdx.x);
+    // before the partition is complete: what does not depend on it
+    if (tid < kFH) s.bits[tid] = 0ull;
+    if (tid < 2) s.misc[tid] = 0;
+    zero_other_counters(a, tp);
+    edmd_pdl_wait();
+    if (blockIdx.x == 0 && tid == 0) edmd_stamp(a.ts, 7);
+    const int classes = a.flags[kFlagNotMono];   // 0: one radius, 1: two classes, more: not eligible
+    const double rad1 = __longlong_as_double(*reinterpret_cast<const long long *>(a.flags + kFlagRad1));
+    const bool declined = a.flags[kFlagLeanFail] != 0;
+    const bool bad = a.flags[kFlagInsane] != 0 || classes > 1 || (classes == 1 && !a.rad_smem);
+    // one thread derives the screening constants while the others have their frame loads in flight
+    if (tid == kTileThreads - 1) *s.K = make_consts(a.b, a.rad0, rad1, classes == 1, __int_as_float(a.flags[kFlagVmax]));
+    if (declined) return;   // a cell overflowed: the host re-runs the sweep on another path
+    if (bad) {
+        if (tid == 0) atomicOr(&a.flags[kFlagLeanFail], 1);   // not eligible: decline
+        return;
+    }
+    // classes == 1: the radii are spread inside their classes (a reference-grown system): the exact
+    // stage takes every disk's own FP64 radius; the class bit is only looked at when a second class exists
+    if (classes == 1 && rad1 > 0.0) cell_main<true>(a, s, tp, true);
+    else cell_main<false>(a, s, tp, classes == 1);
+}
+
+// ---- K4 on the cell slots: computeBOOPCutoff, src/boop.c:61-107 ---------------------------
+// Same frame; positions only.  Per particle the reference's 3 x 3 scan with its own arithmetic (FP64
+// differences, PBC, r2 < r_c^2: neighbour counts are integers identical to the reference's; the same
+// truncation: cells are ~2.0 wide, r_c = 2.5, neighbours two cells away are never seen).
+// e^{ik theta} by complex powers; the FP64 sums run in one fixed order (rows, cells, ascending particle
+// id inside a cell): every output bit is reproducible.  Works for any radii; a frame whose extras do
+// not fit sets kFlagBoopFail and the host falls back to the row kernel.
+struct BoopTileArgs {
+    SweepArgs s;
+    double rc2;
+    double4 *rec;   // two 32-byte sectors per particle id: (q5, q6, q7, q6_arg), (neighbours, 0, 0, 0)
+};
+constexpr int kBoopCtas = 4;   // per SM
+
+__global__ void __launch_bounds__(kTileThreads, kBoopCtas)
+k_cell_boop(const __grid_constant__ BoopTileArgs ba)
+{
+    extern __shared__ __align__(128) unsigned char cell_smem[];
+    const SweepArgs &a = ba.s;
+    const CellSmem s = carve(cell_smem, a.tg.ecap, 0, true);
+    const int tid = threadIdx.x;
+    const TilePos tp = tile_pos(a.tg, blockIdx.x);
+    if (tid < kFH) s.bits[tid] = 0ull;
+    if (tid < 2) s.misc[tid] = 0;
+    zero_other_counters(a, tp);
+    edmd_pdl_wait();
+    const bool declined = a.flags[kFlagBoopFail] != 0;
+    __syncthreads();
+    if (declined) return;
+    const bool fits = frame_load<true>(
+        a, s, tp, false,
+        [&](int pos, int, int, const double4 &st, double, int id) {
+            s.xy[pos] = make_double2(st.x, st.y);
+            s.id[pos] = id;
+        },
+        [&](int pos) { s.id[pos] = -1; });
+    if (!fits) {
+        if (tid == 0) atomicOr(&a.flags[kFlagBoopFail], 1);
+        return;
+    }
+    const int tw = tp.tw, th = tp.th;
+    const int ne = s.misc[0];
+    const int nrow_items = th * 32;
+    const int nitems = nrow_items + ne;
+    const double half_lx = a.b.half_lx, half_ly = a.b.half_ly, lx = a.b.lx, ly = a.b.ly, rc2 = ba.rc2;
+    // a tile away from the edges of the grid never sees the periodic image (every particle lies within
+    // 1.5 cells of the cell it is filed under -- kFlagInsane -- so |d| <= 4 cells < L/2): PBC() is the identity
+    // (frame rows lo .. hi in local rows; in a slab the global row yoff + l wraps somewhere inside the slab)
+    const int fr_lo = tp.y0 - 1, fr_hi = tp.y0 + tp.th;
+    const bool wrap_y = fr_lo < 0 || fr_hi >= a.b.nl || (a.b.yoff + fr_lo < a.b.ny && a.b.yoff + fr_hi >= a.b.ny);
+    const bool wrap = a.flags[kFlagInsane] != 0 || tp.txi == 0 || tp.txi == a.tg.ntx - 1 || wrap_y ||
+                      a.b.nx < 12 || a.b.ny < 12;
+#pragma unroll 1
+    for (int w = tid; w < nitems; w += kTileThreads) {
+        int p, c, fx, fy;
+        if (w < nrow_items) {
+            fy = (w >> 5) + 1;
+            fx = (w & 31) + 1;
+            c = fy * kFW + fx;
+            p = c;
+            if (fx > tw) continue;
+        } else {
+            const int e = w - nrow_items;
+            c = s.ecell[e];
+            fy = c / kFW;
+            fx = c - fy * kFW;
+            p = kFC + e;
+            if (fx < 1 || fx > tw || fy < 1 || fy > th) continue;
+        }
+        const int id = s.id[p];
+        if (id < 0 || id >= a.n_owned) continue;   // empty cell; halo copy from a neighbouring slab
+        const double2 me = s.xy[p];
+        double s5r = 0, s5i = 0, s6r = 0, s6i = 0, s7r = 0, s7i = 0;
+        int nb = 0;
+        auto visit = [&](int q) {
+            const double2 qq = s.xy[q];
+            // the reference's own operations decide who is a neighbour (src/boop.c:78-84)
+            double dx = __dsub_rn(qq.x, me.x), dy = __dsub_rn(qq.y, me.y);
+            if (wrap) {
+                dx = min_image(dx, half_lx, lx);
+                dy = min_image(dy, half_ly, ly);
+            }
+            const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (r2 < rc2) {
+                nb++;
+                // e^{ik theta} = ((dx + i dy)/r)^k, k = 5, 6, 7, by complex powers (fused multiply-adds:
+                // not parity-critical, gate 1e-10); 1/r from the MUFU seed + two Newton steps
+                double zr = 1.0, zi = 0.0;   // atan2(0,0) = 0 in the reference
+                if (r2 > 0) {
+                    double y = rsqrt_seed(r2);
+                    double e = __fma_rn(-__dmul_rn(r2, y), y, 1.0);
+                    y = __fma_rn(__dmul_rn(0.5, y), e, y);
+                    e = __fma_rn(-__dmul_rn(r2, y), y, 1.0);
+                    y = __fma_rn(__dmul_rn(0.5, y), e, y);
+                    zr = __dmul_rn(dx, y);
+                    zi = __dmul_rn(dy, y);
+                }
+                const double z2r = __fma_rn(zr, zr, -__dmul_rn(zi, zi)), z2i = __dmul_rn(__dadd_rn(zr, zr), zi);
+                const double z4r = __fma_rn(z2r, z2r, -__dmul_rn(z2i, z2i)), z4i = __dmul_rn(__dadd_rn(z2r, z2r), z2i);
+                const double z6r = __fma_rn(z4r, z2r, -__dmul_rn(z4i, z2i)), z6i = __fma_rn(z4r, z2i, __dmul_rn(z4i, z2r));
+                // |z| = 1: z^5 = z^6 conj(z), z^7 = z^6 z
+                s5r += __fma_rn(z6r, zr, __dmul_rn(z6i, zi));
+                s5i += __fma_rn(z6i, zr, -__dmul_rn(z6r, zi));
+                s6r += z6r;
+                s6i += z6i;
+                s7r += __fma_rn(z6r, zr, -__dmul_rn(z6i, zi));
+                s7i += __fma_rn(z6r, zi, __dmul_rn(z6i, zr));
+            }
+        };
+#pragma unroll 1
+        for (int j = 0; j < 3; j++) {
+            const unsigned rb = (unsigned)(s.bits[fy + j - 1] >> (fx - 1)) & 7u;
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                const int q = c + (j - 1) * kFW + (k - 1);
+                if (q != p && s.id[q] >= 0) visit(q);   // `p2->num != p1->num`
+                if ((rb >> k) & 1u) {
+                    const unsigned info = s.xinfo[q];
+                    const int q0 = kFC + (info & 0xfff), qn = info >> 12;
+#pragma unroll 1
+                    for (int e = q0; e < q0 + qn; e++)
+                        if (e != p) visit(e);
+                }
+            }
+        }
+        double q5 = 0.0, q6 = 0.0, q7 = 0.0, arg = 0.0;
+        if (nb > 0) {
+            const double inv_n = 1.0 / (double)nb;
+            auto modulus = [&](double re, double im) {   // |re + i im| / n  (no overflow: |sum| <= n)
+                const double m2 = __fma_rn(re, re, __dmul_rn(im, im));
+                return __dmul_rn(__dsqrt_rn(m2), inv_n);
+            };
+            q5 = modulus(s5r, s5i);
+            q6 = modulus(s6r, s6i);
+            q7 = modulus(s7r, s7i);
+            arg = atan2(s6i, s6r);
+        }
+        // Two FULL-sector stores by particle id.  (Five scattered 8-/4-byte stores cost 60 us at N = 10^6:
+        // a partial write to a sector that is not in L2 makes L2 fetch it from DRAM first.)
+        double4 *dst = ba.rec + 2 * (size_t)id;
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(q5), "d"(q6), "d"(q7), "d"(arg) : "memory");
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%2,%2,%2,%2,%2,%2};" ::"l"(dst + 1), "r"(nb), "r"(0) : "memory");
+    }
+}
+
+// the ABI's five psi6 arrays from the records (one coalesced pass)
+__global__ void __launch_bounds__(256)
+k_unpack_boop(int n, const double4 *__restrict__ rec, double *__restrict__ q5, double *__restrict__ q6,
+              double *__restrict__ q7, double *__restrict__ q6arg, int32_t *__restrict__ nbr)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 v = ld_sector(rec + 2 * (size_t)i);
+    const int nb = *reinterpret_cast<const int *>(rec + 2 * (size_t)i + 1);
+    q5[i] = v.x;
+    q6[i] = v.y;
+    q7[i] = v.z;
+    q6arg[i] = v.w;
+    nbr[i] = nb;
+}
+
+// the ABI's five prediction arrays from the event records (one coalesced pass)
+__global__ void __launch_bounds__(256)
+k_unpack_events(int n, const edmd_ev32 *__restrict__ ev, double *__restrict__ t_cross, uint8_t *__restrict__ dir,
+                double *__restrict__ t_coll, int32_t *__restrict__ partner)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 v = ld_sector(reinterpret_cast<const double4 *>(ev + i));
+    t_cross[i] = v.x;
+    t_coll[i] = v.y;
+    partner[i] = __double2loint(v.z);
+    dir[i] = (uint8_t)(__double2hiint(v.z) & 0xff);
+}
+
+}  // namespace
+
+bool edmd_tile_eligible(const edmd_ctx *c, int mode)
+{
+    return edmd_lean_eligible(c, mode) && !c->tile_off && c->pst != nullptr;
+}
+
+// geometry of the tiles + the extras a frame may hold, for a context of nx x nl cells and n particles
+bool edmd_tile_geometry(int nx, int nl, size_t n, TileGeom *out)
+{
+    TileGeom tg;
+    tg.ntx = (nx + kTX - 1) / kTX;
+    tg.nty = (nl + kTY - 1) / kTY;
+    tg.wlast = nx - (tg.ntx - 1) * kTX;
+    tg.hlast = nl - (tg.nty - 1) * kTY;
+    // Extras per cell = mean occupancy - P(occupied).  Hard disks in cells one diameter wide stay far below
+    // a Poisson process of the same density (1.8 - 11 % against 30 %), mixtures with small disks come close to it:
+    // the Poisson figure + a margin is provided for, and at least 30 % of the frame.
+    const double dens = (double)n / ((double)nx * (double)nl);   // particles per cell
+    const double poisson = dens - 1.0 + exp(-dens);
+    long long ecap = (long long)(kFC * fmax(0.30, 1.15 * poisson)) + 32;
+    ecap = (ecap + 31) & ~31ll;
+    if (ecap > 4064) return false;   // xinfo holds 12 bits of extras index
+    if (nx > 32000 || nl > 32000) return false;   // frame_load keeps cell coordinates in 16 bits
+    tg.ecap = (int)ecap;
+    if (cell_smem_bytes(tg.ecap, 1, false) > 200 * 1024) return false;   // denser than a CTA's shared memory provides for
+    *out = tg;
+    return true;
+}
+
+int edmd_launch_unpack_events(edmd_ctx *c)
+{
+    const int n = c->n_owned;
+    if (n == 0) return 0;
+    k_unpack_events<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->evrec, c->t_cross, c->dir, c->t_coll, c->partner);
+    return 1;
+}
+
+// A new partition goes to the other counter buffer (zeroed by the consumers of the current one).
+void edmd_tile_begin_partition(edmd_ctx *c) { c->cbuf ^= 1; }
+
+static PartArgs part_args(edmd_ctx *c, int first, int n)
+{
+    PartArgs pa;
+    pa.first = first; pa.n = n; pa.ncp = c->ncp; pa.dbg = c->tile_dbg;
+    pa.late_wait = 0;
+    pa.cid = c->cid; pa.xv = c->xv; pa.rad = c->rad; pa.rad0 = c->rad0;
+    pa.flags = c->flags;
+    pa.ccnt = c->ccnt + (size_t)c->cbuf * c->ncp;
+    pa.pst = c->pst; pa.pid = c->pid; pa.prad = c->prad;
+    pa.overlap_key = c->overlap_key;
+    pa.ts = c->tile_dbg & 32 ? c->dbg_ts : nullptr;
+    return pa;
+}
+
+// P1 alone: file the particles [first, first + n) of the resident state in the cell slots of the
+// partition begun with edmd_tile_begin_partition
+int edmd_launch_tile_partition_range(edmd_ctx *c, int first, int n, bool beside)
+{
+    if (n <= 0) return 0;
+    PartArgs pa = part_args(c, first, n);
+    pa.late_wait = beside ? 1 : 0;
+    // normally the first kernel of its chain, launched plainly: whatever precedes it on the stream completes
+    // first.  `beside`: behind the halo kernels of the fused exchange, with the programmatic attribute
+    edmd_launch(k_cell_partition, dim3((n + kPartThreads - 1) / kPartThreads), dim3(kPartThreads), 0, c->stream,
+                beside, pa);
+    return 1;
+}
+
+int edmd_launch_tile_partition(edmd_ctx *c)
+{
+    edmd_tile_begin_partition(c);
+    return edmd_launch_tile_partition_range(c, 0, c->n, false);
+}
+
+// slab contexts with the peer-to-peer halo: receive the neighbours' boundary rows (sent by
+// edmd_launch_halo_send) and file them in the cell slots in the same kernel
+int edmd_launch_halo_recv_partition(edmd_ctx *c)
+{
+    const int H = c->halo_cap;
+    const int e = c->halo_epoch, par = e & 1;
+    RecvPartArgs ra;
+    ra.p = part_args(c, c->n_owned, 2 * H);
+    ra.p.overlap_key = nullptr;
+    ra.H = H; ra.epoch = e; ra.ps = c->ps;
+    ra.row[0] = 0; ra.row[1] = c->dbox.nl - 1;
+    ra.inbox[0] = c->halo_mem + inbox_offset(H, 0, par);
+    ra.inbox[1] = c->halo_mem + inbox_offset(H, 1, par);
+    ra.xv = c->xv; ra.rad = c->rad; ra.cid = c->cid; ra.gid = c->gid;
+    // consuming the lower neighbour's records: I am its UPPER neighbour -> its ack[1]; and vice versa
+    ra.peer_ack[0] = reinterpret_cast<int *>(c->peer_mem[0] + ack_offset(H)) + 1;
+    ra.peer_ack[1] = reinterpret_cast<int *>(c->peer_mem[1] + ack_offset(H)) + 0;
+    ra.done = c->halo_cnt + 4;
+    edmd_launch(k_halo_recv_partition, dim3((H + kPartThreads - 1) / kPartThreads, 2), dim3(kPartThreads), 0, c->stream,
+                c->lean_pdl, ra);
+    return 1;
+}
+
+static SweepArgs sweep_args(edmd_ctx *c)
+{
+    SweepArgs sa;
+    sa.tg = c->tgeom; sa.b = c->dbox; sa.t = c->t; sa.rad0 = c->rad0; sa.n_owned = c->n_owned;
+    sa.dbg = c->tile_dbg;
+    sa.rad_smem = c->lean_two ? 1 : 0;   // the host's knowledge; the kernel declines if the device knows better
+    sa.ps = c->ps; sa.ncp = c->ncp; sa.slab = c->slab ? 1 : 0;
+    sa.gid = c->slab ? c->gid : nullptr;
+    sa.flags = c->flags;
+    sa.ccnt = c->ccnt + (size_t)c->cbuf * c->ncp;
+    sa.czero = c->ccnt + (size_t)(c->cbuf ^ 1) * c->ncp;
+    sa.pst = c->pst; sa.pid = c->pid; sa.prad = c->prad;
+    sa.ev = c->evrec;
+    sa.overlap_key = c->overlap_key;
+    sa.ts = c->tile_dbg & 32 ? c->dbg_ts : nullptr;
+    return sa;
+}
+
+static void tile_attrs()
+{
+    static bool attr = false;
+    if (attr) return;
+    cudaFuncSetAttribute(k_cell_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_cell_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_cell_boop, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_cell_boop, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    attr = true;
+}
+
+// the sweep kernel over the cell slots (P2)
+int edmd_launch_tile_sweep_only(edmd_ctx *c)
+{
+    const SweepArgs sa = sweep_args(c);
+    tile_attrs();
+    edmd_launch(k_cell_sweep, dim3(c->tgeom.ntx * c->tgeom.nty), dim3(kTileThreads),
+                cell_smem_bytes(c->tgeom.ecap, sa.rad_smem, false), c->stream, c->lean_pdl, sa);
+    c->pred_packed = true;
+    return 1;
+}
+
+int edmd_launch_tile_sweep(edmd_ctx *c, cudaEvent_t between)
+{
+    if (c->n == 0) return 0;
+    edmd_launch_tile_partition(c);
+    if (between) cudaEventRecord(between, c->stream);
+    return 1 + edmd_launch_tile_sweep_only(c);
+}
+
+// K4 on the cell slots; chained: launched right behind a partition (programmatic launch)
+int edmd_launch_tile_boop(edmd_ctx *c, double r_c, bool from_keep)
+{
+    if (c->n == 0) return 0;
+    const size_t N = (size_t)c->n_cap;   // the four psi6 arrays lie n_cap apart
+    BoopTileArgs ba;
+    ba.s = sweep_args(c);
+    ba.rc2 = r_c * r_c;   // `r_c*r_c`, a single rounded product
+    ba.rec = c->boop_rec;
+    tile_attrs();
+    edmd_launch(k_cell_boop, dim3(c->tgeom.ntx * c->tgeom.nty), dim3(kTileThreads),
+                cell_smem_bytes(c->tgeom.ecap, 0, true), c->stream, c->lean_pdl && !from_keep, ba);
+    // halo copies of a slab context are not computed: the unpack covers the owned particles
+    const int no = c->n_owned;
+    k_unpack_boop<<<(no + 255) / 256, 256, 0, c->stream>>>(no, c->boop_rec, c->boop, c->boop + N, c->boop + 2 * N,
+                                                           c->boop + 3 * N, c->boop_nb);
+    return 2;
+}

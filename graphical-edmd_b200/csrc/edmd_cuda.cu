@@ -274,19 +274,19 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
             if ((r = dev_alloc(c, &c->lwork, (size_t)c->lean_chunks + 8))) return r;
         }
     }
-    // tile sweep: one bucket per tile of the cell grid = kFH runs (frame rows) of kRunCap records (32-byte FP64
-    // state + 16-byte tag), one cursor per run in its own 32-byte sector; one 32-byte event record per particle
+    // cell-slot sweep (cell_sweep.cu): kSlotK planes over the padded cell grid (plane s = the s-th arrival of
+    // every cell: FP64 state, id, radius), two counter buffers; one 32-byte event record per particle
     if (c->rowcap > 0 && c->dbox.nx >= 12 && c->dbox.nl >= 3 && N > 0 &&
         edmd_tile_geometry(c->dbox.nx, c->dbox.nl, N, &c->tgeom)) {
-        const size_t runs = (size_t)c->tgeom.ntx * c->tgeom.nty * kFH;
-        if ((r = dev_alloc(c, &c->tst, runs * kRunCap + 32))) return r;
-        if ((r = dev_alloc(c, &c->ttag, runs * kRunCap + 32))) return r;
-        if ((r = dev_alloc(c, &c->trad, runs * kRunCap + 32))) return r;
-        if ((r = dev_alloc(c, &c->tcnt, runs * kCurStride + 8))) return r;
-        if ((r = dev_alloc(c, &c->tkeep, runs + 8))) return r;
+        const size_t ncp = (size_t)c->ncp;
+        if ((r = dev_alloc(c, &c->pst, kSlotK * ncp + 32))) return r;
+        if ((r = dev_alloc(c, &c->pid, kSlotK * ncp + 32))) return r;
+        if ((r = dev_alloc(c, &c->prad, kSlotK * ncp + 32))) return r;
+        if ((r = dev_alloc(c, &c->ccnt, 2 * ncp + 32))) return r;
         if ((r = dev_alloc(c, &c->boop_rec, 2 * N + 8))) return r;
         if ((r = dev_alloc(c, &c->evrec, N + 32))) return r;
-        CU(cudaMemsetAsync(c->tcnt, 0, (runs * kCurStride + 8) * sizeof(int32_t), c->stream));
+        CU(cudaMemsetAsync(c->ccnt, 0, (2 * ncp + 32) * sizeof(int32_t), c->stream));
+        c->cbuf = 0;
     }
     if ((r = dev_alloc(c, &c->t_cross, N))) return r;
     if ((r = dev_alloc(c, &c->t_coll, N))) return r;
@@ -324,7 +324,7 @@ void edmd_cuda_destroy(edmd_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *dev[] = {c->in_soa, c->in_cell, c->xv, c->rad, c->vr, c->cid, c->gid, c->cell_cnt,
                    c->off, c->cstart, c->rank, c->row_total, c->row_base, c->meta, c->spos, c->saux, c->svr,
-                   c->lrec, c->lchunks, c->lres, c->lwork, c->tst, c->ttag, c->trad, c->tcnt, c->tkeep, c->boop_rec, c->evrec, c->cal_mem,
+                   c->lrec, c->lchunks, c->lres, c->lwork, c->pst, c->pid, c->prad, c->ccnt, c->boop_rec, c->evrec, c->cal_mem,
                    c->t_cross, c->t_coll, c->partner, c->dir, c->ctype,
                    c->overlap_key, c->flags, c->dbg_ts, c->pcf_counts, c->pcf_wsum, c->pcfs_mem, c->pcfs_stats, c->vor_mem, c->thermo_mem, c->boop, c->boop_nb,
                    c->red_partial, c->flush_buf};
@@ -631,6 +631,7 @@ static int exchange_predict_launch(edmd_ctx *c, int mode, cudaEvent_t between)
         //   sweep     which waits for the partition, sees every append of the step.
         // (Launching the halo kernels BEHIND the partition, or on a second stream, hid nothing: the block
         // scheduler only gets to them once the partition's last wave of blocks has been dispatched.)
+        edmd_tile_begin_partition(c);
         c->launches += edmd_launch_halo_send(c, false);
         c->launches += edmd_launch_halo_recv_partition(c);
         c->launches += edmd_launch_tile_partition_range(c, 0, c->n_owned, c->lean_pdl);
@@ -964,7 +965,7 @@ static int ensure_index(edmd_ctx *c)
 // path does not apply or declines.
 static bool boop_tile_ok(const edmd_ctx *c)
 {
-    return c->tst != nullptr && !c->tile_off && !c->boop_tile_off && !c->force_generic && c->n > 0;
+    return c->pst != nullptr && !c->tile_off && !c->boop_tile_off && !c->force_generic && c->n > 0;
 }
 
 static int boop_launch(edmd_ctx *c, double r_c, bool *used_tile)

@@ -128,19 +128,17 @@ enum {
     kFlagCount = 16
 };
 
-// ---- tile sweep (tile_sweep.cu): the cell grid cut into tiles of kTX x kTY cells ----------
+// ---- cell-slot sweep (cell_sweep.cu): kSlotK planes over the padded cell grid, tiles of kTX x kTY cells ----
 constexpr int kTX = 32, kTY = 16;                                // cells per tile
 constexpr int kFW = kTX + 2, kFH = kTY + 2, kFC = kFW * kFH;     // a tile's frame: the tile + a one-cell ring
-constexpr int kTileThreads = 192;
+constexpr int kTileThreads = 256;
 constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kTileCtas = 4;                                     // per SM (64 registers per thread)
-constexpr int kRunCap = 96;                                      // records per RUN = one frame row of one tile
-constexpr int kRunsPerWarp = (kFH + kTileWarps - 1) / kTileWarps;
-constexpr int kCurStride = 8;                                    // ints between cursors: one 32-byte sector each
+constexpr int kTileCtas = 3;                                     // per SM (<= 85 registers per thread)
+constexpr int kSlotK = 8;                                        // disks one cell can hold (plane s = s-th arrival)
 struct TileGeom {
     int ntx, nty;            // tiles per row of tiles / rows of tiles
     int wlast, hlast;        // width of the last tile column, height of the last tile row
-    int smem_cap;            // records one CTA can bin (its shared memory is sized for this)
+    int ecap;                // extras (disks of planes 1..) one frame can list in shared memory
 };
 
 struct edmd_ctx {
@@ -222,13 +220,13 @@ struct edmd_ctx {
     int32_t *lwork;                  // chunk ids that hold particles, any order (kFlagWork entries)
     int4 *lchunks;
     int2 *lres;                      // k_screen -> k_resolve: (winner slot, second bound) per slot
-    // tile sweep (tile_sweep.cu)
+    // cell-slot sweep (cell_sweep.cu)
     TileGeom tgeom;
-    double4 *tst;                    // tile buckets: ntx * nty tiles x kFH runs x kRunCap FP64 states (32 bytes each)
-    int2 *ttag;                      // ... their 8-byte tags (id, frame cell)
-    double *trad;                    // ... and radii (written only when the radii are not all exactly rad0)
-    int32_t *tcnt;                   // one cursor per run, kCurStride ints apart
-    int32_t *tkeep;                  // run lengths of the last partition (dense), for later passes over the buckets
+    double4 *pst;                    // [kSlotK][ncp] FP64 states: plane s = the s-th arrival of every padded cell
+    int32_t *pid;                    // ... their particle ids
+    double *prad;                    // ... and radii (written only when the radii are not all exactly rad0)
+    int32_t *ccnt;                   // [2][ncp] disks per cell, double-buffered (consumers zero the other buffer)
+    int cbuf;                        // the buffer of the current partition
     bool boop_tile_off;              // EDMD_OPT_NO_TILE_BOOP
     double4 *boop_rec;               // psi6 records of the tile kernel: two sectors per particle id
     edmd_ev32 *evrec;                 // event records of the last tile sweep, by particle id
@@ -311,6 +309,7 @@ int edmd_launch_halo_p2p(edmd_ctx *c);
 int edmd_launch_halo_send(edmd_ctx *c, bool chained);
 int edmd_launch_halo_recv(edmd_ctx *c);
 int edmd_launch_halo_recv_partition(edmd_ctx *c);
+void edmd_tile_begin_partition(edmd_ctx *c);
 int edmd_launch_tile_partition_range(edmd_ctx *c, int first, int n, bool early);
 int edmd_launch_tile_sweep_only(edmd_ctx *c);
 int edmd_launch_cell_index(edmd_ctx *c, int mode);

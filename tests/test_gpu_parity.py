@@ -836,11 +836,34 @@ def test_tile_psi6_equals_row_kernel(pkg, oracle, n, phi, seed, sf):
     assert_boop_close(a, oracle.boop_cutoff(c["n"], c["lx"], c["ly"], c["x"], c["y"], 2.5))
 
 
-def test_tile_sweep_declines_when_a_bucket_overflows(pkg, oracle):
-    """All particles of a dilute system crowded into one corner of the box: the bucket of
-    that tile overflows its fixed capacity, the sweep declines on the device and the call
-    re-runs on the full path."""
+@pytest.mark.parametrize("rad,spacing", [(0.1, 0.3), (0.3, 0.95)])
+def test_cell_slot_sweep_declines_when_cells_overflow(pkg, oracle, rad, spacing):
+    """Tiny disks crowded into one corner of a dilute box (cells are ~2 wide whatever the radius):
+    spacing 0.3 puts ~40 disks in a cell -- more than the kSlotK slots a cell has --, spacing 0.95 about
+    four -- more extras than a frame's list holds.  The sweep declines on the device and the call
+    re-runs on the full path; the results are the reference's either way."""
     rng = np.random.default_rng(77)
+    lx, ly, n = 400.0, 300.0, 6000
+    side = int(np.ceil(np.sqrt(n)))
+    k = np.arange(n)
+    x = 1.0 + spacing * (k % side) + 0.02 * rng.random(n)
+    y = 1.0 + spacing * (k // side) + 0.02 * rng.random(n)
+    vx, vy = rng.standard_normal(n), rng.standard_normal(n)
+    c = dict(n=n, lx=lx, ly=ly, x=x, y=y, vx=vx, vy=vy, rad=np.full(n, rad))
+    with pkg.EdmdCuda(n, lx, ly) as ctx:
+        ctx.upload(x, y, vx, vy, c["rad"], t=0.5)
+        got = ctx.predict_all()
+        assert ctx.stat(pkg.binding.STAT_LEAN_DECLINES) >= 1
+        got2 = ctx.predict_all()
+    want = oracle_sweep(oracle, c, t=0.5)
+    assert_events_equal(got, want)
+    assert_events_equal(got2, want)
+
+
+def test_cell_slot_sweep_takes_a_crowded_corner(pkg, oracle):
+    """One disk per cell, all in one corner of the box (the tile buckets of round 2's first sweep
+    overflowed on this): the cell slots take it."""
+    rng = np.random.default_rng(78)
     lx, ly, n = 400.0, 300.0, 6000
     side = int(np.ceil(np.sqrt(n)))
     k = np.arange(n)
@@ -851,11 +874,8 @@ def test_tile_sweep_declines_when_a_bucket_overflows(pkg, oracle):
     with pkg.EdmdCuda(n, lx, ly) as ctx:
         ctx.upload(x, y, vx, vy, c["rad"], t=0.5)
         got = ctx.predict_all()
-        assert ctx.stat(pkg.binding.STAT_LEAN_DECLINES) >= 1
-        got2 = ctx.predict_all()
-    want = oracle_sweep(oracle, c, t=0.5)
-    assert_events_equal(got, want)
-    assert_events_equal(got2, want)
+        assert ctx.stat(pkg.binding.STAT_LEAN_DECLINES) == 0
+    assert_events_equal(got, oracle_sweep(oracle, c, t=0.5))
 
 
 def test_rescale_after_growth_free_flight_stays_off_the_lean_path(pkg, oracle):

@@ -10,7 +10,8 @@ CSRC       = $(PKG)/csrc
 ARCH       = -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: no implicit multiply-add contraction anywhere in the library; the
 # parity-critical arithmetic additionally uses explicit __d*_rn intrinsics.
-NVCCFLAGS  = $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Iinclude -I$(CSRC) \
+TILE_ROWS ?= 8
+NVCCFLAGS  = -DEDMD_TILE_ROWS=$(TILE_ROWS) $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Iinclude -I$(CSRC) \
              -Xcompiler -fPIC,-Wall,-Wno-unused-function
 CU_SRCS    = $(CSRC)/edmd_cuda.cu $(CSRC)/cell_index.cu $(CSRC)/predict.cu $(CSRC)/analysis.cu $(CSRC)/halo.cu \
              $(CSRC)/lean_index.cu $(CSRC)/predict_lean.cu $(CSRC)/cell_sweep.cu $(CSRC)/calendar.cu $(CSRC)/analysis_weighted.cu $(CSRC)/analysis_pcf_sorted.cu $(CSRC)/analysis_voronoi.cu $(CSRC)/thermostat.cu

@@ -443,9 +443,11 @@ class EdmdCuda:
         return dict(rc=rc, bucket=bucket, next=nxt, prev=prv, head=head, n_tree=n_tree.value)
 
     def bench(self, what, mode=MODE_NORMAL, dr=0.0, max_r=0.0, warmup=3, iters=10,
-              flush_bytes=0):
+              flush_bytes=0, split=True):
+        """split=False (sweep only): no event between K0 and K1 -- the chain as the product launches it;
+        returns (ms_total, None)."""
         tot = np.zeros(iters, np.float32)
-        main = np.zeros(iters, np.float32)
+        main = np.zeros(iters, np.float32) if split else None
         self._check(self.lib.edmd_cuda_bench(self._h, what, mode, dr, max_r, warmup, iters,
-                                             flush_bytes, _ptr(tot), _ptr(main)))
+                                             flush_bytes, _ptr(tot), _ptr(main) if split else None))
         return tot, main

@@ -43,20 +43,24 @@
 #include "lean.cuh"
 #include "pairmath.cuh"
 #include "halo.cuh"
+#include "rowstage.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int kPartThreads = 256;
 
 struct PartArgs {
-    int first, n, ncp, dbg;
+    int first, n, ncp, dbg, ps, nx;
+    int workers;     // CTAs of the sweep kernel that follows: its tile counter starts there
     int late_wait;   // fused halo exchange: run BESIDE the preceding kernels of the chain, wait for them at the end
     const int32_t *cid;
     const double4 *xv;
     const double *rad;
     double rad0;
     int32_t *flags;
-    int32_t *ccnt;   // counters of the partition being built (zero on entry)
+    unsigned long long *ccnt;   // cell words of the partition being built (zero on entry): count << 32 | sum of ids
     double4 *pst;    // [kSlotK][ncp] FP64 states
     int32_t *pid;    // [kSlotK][ncp] particle ids
     double *prad;    // [kSlotK][ncp] radii (written only when the radii are not all exactly rad0)
@@ -64,21 +68,36 @@ struct PartArgs {
     unsigned long long *ts;
 };
 
-// File particle i (padded cell id pc, state p, radius rad) in the next free slot of its cell.
-__device__ __forceinline__ void partition_one(const PartArgs &a, int i, int pc, const double4 &p, double rad,
-                                              const bool radii)
+// File particle i (padded cell id pc, state p, radius rad) in the next free slot of its cell -- and, when the cell
+// is the first / last of its row, of the row's GHOST cell on the other side (padded column nx + 1 / 0, the
+// periodic neighbour PBCcellX wraps to, src/EDMD.c:2110-2116): with the ghosts every frame row of the sweep
+// is ONE contiguous run of the planes, periodic edge included, and can be fetched by a single bulk copy.
+__device__ __forceinline__ void file_one(const PartArgs &a, int i, int pc, const double4 &p, double rad, const bool radii)
 {
-    const int s = (a.dbg & 16) ? 0 : atomicAdd(&a.ccnt[pc], 1);   // (dbg: timing experiments, option 100)
+    // ONE atomic claims the slot AND leaves the id: the cell word is count << 32 | (sum of the ids filed so far,
+    // mod 2^32).  A cell with one disk -- nearly all of them -- needs no id store at all (the partition kernel
+    // is bound by the number of scattered L2 requests: atomic + state + id were three per particle); the
+    // disks of planes 1.. store theirs, the sum gives back plane 0's.
+    const int s = (a.dbg & 16) ? 0 : (int)(atomicAdd(&a.ccnt[pc], (1ull << 32) | (unsigned int)i) >> 32);   // (dbg: timing experiments)
     if (a.dbg & 8) return;
     if (s < kSlotK) {
         const size_t slot = (size_t)s * a.ncp + pc;
         asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(a.pst + slot), "d"(p.x), "d"(p.y), "d"(p.z), "d"(p.w)
                      : "memory");
-        a.pid[slot] = i;
+        if (s > 0) a.pid[slot] = i;
         if (radii) a.prad[slot] = rad;
     } else {
         atomicOr(&a.flags[kFlagLeanFail], 1);   // a cell is full: the sweep declines
     }
+}
+
+__device__ __forceinline__ void partition_one(const PartArgs &a, int i, int pc, const double4 &p, double rad,
+                                              const bool radii)
+{
+    file_one(a, i, pc, p, rad, radii);
+    const int col = pc - (pc / a.ps) * a.ps;   // padded column 1 .. nx
+    if (col == 1) file_one(a, i, pc + a.nx, p, rad, radii);        // cell 0 -> right ghost (column nx + 1)
+    else if (col == a.nx) file_one(a, i, pc - a.nx, p, rad, radii);   // cell nx-1 -> left ghost (column 0)
 }
 
 __global__ void __launch_bounds__(kPartThreads)
@@ -88,7 +107,10 @@ k_cell_partition(const __grid_constant__ PartArgs a)
     if (!a.late_wait) edmd_pdl_wait();
     if (i == a.first) edmd_stamp(a.ts, 4);
     if (i == a.first + a.n - 1) edmd_stamp(a.ts, 5);
-    if (i == a.first && a.overlap_key) *a.overlap_key = ~0ull;   // the sweep's overlap report starts empty
+    if (i == a.first && a.overlap_key) {
+        *a.overlap_key = ~0ull;                 // the sweep's overlap report starts empty
+        a.flags[kFlagTileCtr] = a.workers;      // ... and its workers take the tiles from here on dynamically
+    }
     if (i < a.first + a.n) {
         const int pc = a.cid[i];
         const double4 p = ld_sector(a.xv + i);
@@ -186,8 +208,8 @@ struct SweepArgs {
     int n_owned, dbg, rad_smem, ps, ncp, slab;
     const int32_t *gid;
     int32_t *flags;
-    const int32_t *ccnt;   // counters of the current partition
-    int32_t *czero;        // the other counter buffer: this kernel zeroes the cells of its tile
+    const unsigned long long *ccnt;   // cell words (count << 32 | sum of ids) of the current partition
+    unsigned long long *czero;        // the other buffer: this kernel zeroes the cells of its tile
     const double4 *pst;
     const int32_t *pid;
     const double *prad;
@@ -289,13 +311,14 @@ __device__ __forceinline__ TilePos tile_pos(const TileGeom &tg, int tile)
     return t;
 }
 
-// The other counter buffer goes back to zero for the cells of this tile (nobody reads it: its last
-// consumer completed before the chain of this sweep began).
+// The other counter buffer goes back to zero for the cells of this tile -- and the ghost cells beside the first /
+// last tile column -- (nobody reads it: its last consumer completed before the chain of this sweep began).
 __device__ __forceinline__ void zero_other_counters(const SweepArgs &a, const TilePos &tp)
 {
-    for (int k = threadIdx.x; k < kTX * kTY; k += kTileThreads) {
-        const int r = k / kTX, x = k - r * kTX;
-        if (r < tp.th && x < tp.tw) a.czero[(tp.y0 + r) * a.ps + tp.x0 + x + 1] = 0;
+    const int lo = tp.txi == 0 ? -1 : 0, hi = tp.tw + (tp.txi == a.tg.ntx - 1 ? 1 : 0);
+    for (int k = threadIdx.x; k < kFW * kTY; k += kTileThreads) {
+        const int r = k / kFW, x = k - r * kFW - 1;
+        if (r < tp.th && x >= lo && x < hi) a.czero[(tp.y0 + r) * a.ps + tp.x0 + x + 1] = 0ull;
     }
 }
 
@@ -339,9 +362,10 @@ __device__ __forceinline__ bool frame_load(const SweepArgs &a, const CellSmem &s
                 pc[q] = c;
                 Xs[q] = (short)X;
                 Ys[q] = (short)Yl;
-                n[q] = a.ccnt[c];
+                const unsigned long long word = a.ccnt[c];
+                n[q] = (int)(word >> 32);
                 st0[q] = ld_sector(a.pst + c);
-                id0[q] = a.pid[c];
+                id0[q] = (int)(unsigned int)word;   // one disk: its id; more: the sum of their ids
                 if (radii) rad0[q] = a.prad[c];
             }
         }
@@ -375,13 +399,15 @@ __device__ __forceinline__ bool frame_load(const SweepArgs &a, const CellSmem &s
         const int fy = fc / kFW, fx = fc - fy * kFW;
         s.xinfo[fc] = (unsigned short)(e0 | (m << 12));
         atomicOr(&s.bits[fy], 1ull << fx);
+        unsigned int idp0 = (unsigned int)id0[q];   // plane 0's id = the sum - the ids of planes 1..
+        for (int k = 1; k < nn; k++) idp0 -= (unsigned int)a.pid[(size_t)k * a.ncp + c];
         for (int k = 0; k < nn; k++) {
             const size_t slot = (size_t)k * a.ncp + c;
-            const int idk = k == 0 ? id0[q] : a.pid[slot];
+            const int idk = k == 0 ? (int)idp0 : a.pid[slot];
             int rank = k;
             if (SORT) {
                 rank = 0;
-                for (int k2 = 0; k2 < nn; k2++) rank += a.pid[(size_t)k2 * a.ncp + c] < idk ? 1 : 0;
+                for (int k2 = 0; k2 < nn; k2++) rank += (k2 == 0 ? (int)idp0 : a.pid[(size_t)k2 * a.ncp + c]) < idk ? 1 : 0;
             }
             const double4 stk = k == 0 ? st0[q] : ld_sector(a.pst + slot);
             const double radk = k == 0 ? rad0[q] : (radii ? a.prad[slot] : a.rad0);
@@ -394,41 +420,234 @@ __device__ __forceinline__ bool frame_load(const SweepArgs &a, const CellSmem &s
     return s.misc[1] == 0;
 }
 
-// ---- sweep: every particle of the tile ---------------------------------------------
+// ---- P2, persistent: frames prefetched by TMA bulk copies one tile ahead -------------------------
+// Shared memory of one CTA of k_cell_sweep.  Index p < kFC = the plane-0 disk of frame cell p,
+// p >= kFC = extra number p - kFC (a disk of planes 1..); cap = kFC + tg.ecap.
+//   st[2]   double4[kFC]     FP64 states of plane 0, frame-cell order, DOUBLE-BUFFERED: the bulk copies of
+//                            the next tile land while this one is swept (read in place by the exact stage)
+//   rrad[2] double[kFC]      radii of plane 0 (only when the radii are not all exactly rad0)
+//   rcnt    u64[kFC]         cell words (count << 32 | sum of ids) of the frame as copied (consumed by the convert pass)
+//   scr     float4[cap]      screening records (NaN: empty cell)
+//   id      int[cap]         particle ids, -1: empty (local ids in a slab context)
+//   xst     double4[ecap], xrad double[ecap]   FP64 states / radii of the extras
+//   bits, xinfo, ecell       as CellSmem
+static_assert((kFW * 8) % 16 == 0, "bulk copies move 16-byte granules");
+static_assert(kFW + kFH <= kTileThreads && 32 + kFH <= 62, "frame_tables / the list reset spread their work over the first 64 threads");
+static_assert(kFW == 34, "frame_convert divides by 34 with a multiply-shift");
+struct SweepSmem {
+    double4 *st;    // buffer b at st + b * kFC
+    double *rrad;   // buffer b at rrad + b * kFC
+    unsigned long long *rcnt;
+    float4 *scr;
+    int *id;
+    double4 *xst;
+    double *xrad;
+    unsigned long long *bits;   // [2][kFH]: the set of tile k is cleared while tile k+1 uses the other
+    unsigned short *xinfo, *ecell;
+    int *misc;   // per set (4 ints each): [0] extras listed, [1] decline, [2] the tile after the next one
+    double *ctr; // [kFW] x of the centre of the cell frame column fx is FILED under, [kFH] y of frame row fy's
+    int *rowl;   // [kFH] local row of frame row fy, -1: none
+    LeanConsts *K;
+    uint64_t *mbar;   // [2]
+};
+
+__host__ __device__ inline size_t sweep_smem_bytes(int ecap, int rad_smem)
+{
+    const size_t cap = (size_t)kFC + ecap;
+    size_t b = 2 * (size_t)kFC * 32;                       // st
+    b += (size_t)ecap * 32;                                // xst
+    b += cap * 16;                                         // scr
+    if (rad_smem) b += 2 * (size_t)kFC * 8 + (size_t)ecap * 8 + 16;   // rrad, xrad
+    b += 2 * sizeof(unsigned long long) * kFH + 16;        // bits, mbar
+    b += sizeof(double) * (kFW + kFH) + 16;                // ctr
+    b += sizeof(int) * kFH + 16;                           // rowl
+    b += (size_t)kFC * 8;                                  // rcnt
+    b += cap * 4 + 16;                                     // id
+    b += 32;                                               // misc
+    b += (sizeof(LeanConsts) + 15) & ~(size_t)15;
+    b += sizeof(unsigned short) * (kFC + ecap);            // xinfo, ecell
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ SweepSmem carve_sweep(unsigned char *base, int ecap, int rad_smem)
+{
+    const size_t cap = (size_t)kFC + ecap;
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    SweepSmem s;
+    s.st = reinterpret_cast<double4 *>(base);
+    base += 2 * (size_t)kFC * 32;
+    s.xst = reinterpret_cast<double4 *>(base);
+    base += (size_t)ecap * 32;
+    s.scr = reinterpret_cast<float4 *>(base);
+    base += cap * 16;
+    s.rrad = s.xrad = nullptr;
+    if (rad_smem) {
+        s.rrad = reinterpret_cast<double *>(base);
+        base += 2 * (size_t)kFC * 8;
+        s.xrad = reinterpret_cast<double *>(base);
+        base += up16((size_t)ecap * 8);
+    }
+    s.bits = reinterpret_cast<unsigned long long *>(base);
+    base += 2 * sizeof(unsigned long long) * kFH;
+    s.mbar = reinterpret_cast<uint64_t *>(base);
+    base += 16;
+    s.ctr = reinterpret_cast<double *>(base);
+    base += up16(sizeof(double) * (kFW + kFH));
+    s.rowl = reinterpret_cast<int *>(base);
+    base += up16(sizeof(int) * kFH);
+    s.rcnt = reinterpret_cast<unsigned long long *>(base);
+    base += (size_t)kFC * 8;
+    s.id = reinterpret_cast<int *>(base);
+    base += up16(cap * 4);
+    s.misc = reinterpret_cast<int *>(base);
+    base += 32;
+    s.K = reinterpret_cast<LeanConsts *>(base);
+    base += (sizeof(LeanConsts) + 15) & ~(size_t)15;
+    s.xinfo = reinterpret_cast<unsigned short *>(base);
+    s.ecell = s.xinfo + kFC;
+    return s;
+}
+
+// local row of frame row fy, -1: no such row (beyond the tile's frame, or outside a slab's rows: a slab's
+// rows are not periodic, rows 0 and nl-1 ARE the halo)
+__device__ __forceinline__ int frame_row(const SweepArgs &a, const TilePos &tp, int fy)
+{
+    if (fy > tp.th + 1) return -1;
+    int Yl = tp.y0 + fy - 1;
+    if (Yl < 0 || Yl >= a.b.nl) {
+        if (a.slab) return -1;
+        Yl = Yl < 0 ? Yl + a.b.nl : Yl - a.b.nl;
+    }
+    return Yl;
+}
+
+// Fire the bulk copies of one tile's frame (warp 0, converged): lane fy copies frame row fy -- with the
+// ghost columns of the planes a row is ONE contiguous run starting at padded column x0, periodic edge
+// included: kFW states, kFW cell words (and kFW radii).  Completion is counted in bytes on mbar[buf].
+__device__ __forceinline__ void frame_issue(const SweepArgs &a, const SweepSmem &s, const TilePos &tp, int buf,
+                                            const bool radii)
+{
+    const int lane = threadIdx.x & 31;
+    const int Yl = lane < kFH ? frame_row(a, tp, lane) : -1;
+    const int nrows = __popc(__ballot_sync(0xffffffffu, Yl >= 0));
+    const uint32_t per_row = kFW * 32u + kFW * 8u + (radii ? kFW * 8u : 0u);
+    if (lane == 0) mbar_expect_tx(&s.mbar[buf], (uint32_t)nrows * per_row);
+    __syncwarp();
+    if (Yl >= 0) {
+        const size_t base = (size_t)Yl * a.ps + tp.x0;
+        bulk_g2s(s.st + buf * kFC + lane * kFW, a.pst + base, kFW * 32u, &s.mbar[buf]);
+        bulk_g2s(s.rcnt + lane * kFW, a.ccnt + base, kFW * 8u, &s.mbar[buf]);
+        if (radii) bulk_g2s(s.rrad + buf * kFC + lane * kFW, a.prad + base, kFW * 8u, &s.mbar[buf]);
+    }
+}
+
+// Per tile, before the convert pass: the centre of the cell every frame column / row is filed under (a ghost
+// column is the opposite edge of the grid), the local row of every frame row.  (Once per column instead of
+// once per record: the int -> FP64 conversion, the + 0.5 and the product are 3 of the 5 FP64 operations a
+// screening coordinate costs.)
+__device__ __forceinline__ void frame_tables(const SweepArgs &a, const SweepSmem &s, const TilePos &tp)
+{
+    const int t = threadIdx.x;
+    if (t < kFW) {
+        int X = tp.x0 + t - 1;
+        X = X < 0 ? X + a.b.nx : (X >= a.b.nx ? X - a.b.nx : X);
+        s.ctr[t] = __dmul_rn((double)X + 0.5, a.b.csx);
+    } else if (t < kFW + kFH) {
+        const int fy = t - kFW;
+        const int Yl = frame_row(a, tp, fy);
+        s.rowl[fy] = Yl;
+        s.ctr[kFW + fy] = __dmul_rn((double)edmd_global_row(a.b, Yl < 0 ? 0 : Yl) + 0.5, a.b.csy);
+    }
+}
+
+// The frame has landed: derive the screening records of plane 0 (in place order), list the extras (sets
+// bits / misc of set `buf`).  Ends with a barrier; returns false (for the whole CTA) when the extras do not fit.
 template <bool TWO>
-__device__ __forceinline__ void cell_main(const SweepArgs &a, const CellSmem &s, const TilePos &tp, const bool radii)
+__device__ __forceinline__ bool frame_convert(const SweepArgs &a, const SweepSmem &s, const TilePos &tp, int buf,
+                                              const bool radii)
 {
     const int tid = threadIdx.x;
     const float fnan = __int_as_float(0x7fffffff);
-    const bool fits = frame_load<false>(
-        a, s, tp, radii,
-        [&](int pos, int X, int Yl, const double4 &st, double rad, int id) {
-            // screening record, relative to the centre of the filed cell (lean.cuh)
-            float4 r;
-            r.x = __double2float_rn(__dsub_rn(st.x, __dmul_rn((double)X + 0.5, a.b.csx)));
-            r.y = __double2float_rn(__dsub_rn(st.y, __dmul_rn((double)edmd_global_row(a.b, Yl) + 0.5, a.b.csy)));
-            r.z = __double2float_rn(st.z);
-            r.w = __double2float_rn(st.w);
-            if (TWO) r.w = __int_as_float((__float_as_int(r.w) & ~1) | (edmd_same_class(rad, a.rad0) ? 0 : 1));
-            s.xy[pos] = make_double2(st.x, st.y);
-            s.vv[pos] = make_double2(st.z, st.w);
-            s.scr[pos] = r;
-            s.id[pos] = id;
-            if (radii) s.rad[pos] = rad;
-        },
-        [&](int pos) {
-            s.scr[pos] = make_float4(fnan, fnan, fnan, fnan);
-            s.id[pos] = -1;
-        });
-    if (!fits || !s.K->ok) {   // extras beyond the frame's list, or a velocity scale outside the FP32-safe range
-        if (tid == 0) atomicOr(&a.flags[kFlagLeanFail], 1);
-        return;
+    const double4 *st0 = s.st + buf * kFC;
+    unsigned long long *bits = s.bits + buf * kFH;
+    int *misc = s.misc + buf * 4;
+    auto record = [&](int fx, int fy, const double2 &xy, const double2 &vv, double rad) {
+        // screening record, relative to the centre of the filed cell (lean.cuh)
+        float4 r;
+        r.x = __double2float_rn(__dsub_rn(xy.x, s.ctr[fx]));
+        r.y = __double2float_rn(__dsub_rn(xy.y, s.ctr[kFW + fy]));
+        r.z = __double2float_rn(vv.x);
+        r.w = __double2float_rn(vv.y);
+        if (TWO) r.w = __int_as_float((__float_as_int(r.w) & ~1) | (edmd_same_class(rad, a.rad0) ? 0 : 1));
+        return r;
+    };
+#pragma unroll 1
+    for (int fc = tid; fc < kFC; fc += kTileThreads) {
+        const int fy = (fc * 241) >> 13, fx = fc - fy * kFW;   // fc / kFW for fc < 4096 (kFW = 34)
+        const int Yl = s.rowl[fy];
+        const unsigned long long word = s.rcnt[fc];
+        const int nn = (Yl >= 0 && fx <= tp.tw + 1) ? min((int)(word >> 32), kSlotK) : 0;
+        if (nn == 0) {
+            s.scr[fc] = make_float4(fnan, fnan, fnan, fnan);
+            s.id[fc] = -1;
+            continue;
+        }
+        const double2 xy = reinterpret_cast<const double2 *>(st0 + fc)[0];
+        const double2 vv = reinterpret_cast<const double2 *>(st0 + fc)[1];
+        s.scr[fc] = record(fx, fy, xy, vv, radii ? s.rrad[buf * kFC + fc] : a.rad0);
+        if (nn == 1) {
+            s.id[fc] = (int)(unsigned int)word;   // one disk: the sum of ids is its id
+            continue;
+        }
+        // more than one disk in the cell: the others go to the extras list, contiguously
+        const int m = nn - 1;
+        const int e0 = atomicAdd(&misc[0], m);
+        if (e0 + m > a.tg.ecap) {
+            misc[1] = 1;
+            continue;
+        }
+        s.xinfo[fc] = (unsigned short)(e0 | (m << 12));
+        atomicOr(&bits[fy], 1ull << fx);
+        const int c = Yl * a.ps + tp.x0 + fx;   // padded cell id (ghost columns included)
+        unsigned int idp0 = (unsigned int)word;   // plane 0's id = the sum - the ids of planes 1..
+        for (int k = 1; k < nn; k++) {
+            const size_t slot = (size_t)k * a.ncp + c;
+            const double4 stk = ld_sector(a.pst + slot);
+            const double radk = radii ? a.prad[slot] : a.rad0;
+            const int idk = a.pid[slot];
+            const int e = e0 + k - 1;
+            s.xst[e] = stk;
+            if (radii) s.xrad[e] = radk;
+            s.scr[kFC + e] = record(fx, fy, make_double2(stk.x, stk.y), make_double2(stk.z, stk.w), radk);
+            s.id[kFC + e] = idk;
+            s.ecell[e] = (unsigned short)fc;
+            idp0 -= (unsigned int)idk;
+        }
+        s.id[fc] = (int)idp0;
     }
+    zero_other_counters(a, tp);
+    __syncthreads();
+    return misc[1] == 0;
+}
+
+// ---- sweep: every particle of the tile ---------------------------------------------
+template <bool TWO>
+__device__ __forceinline__ void cell_tile(const SweepArgs &a, const SweepSmem &s, const TilePos &tp, int buf,
+                                          const bool radii, const LeanConsts &K)
+{
+    const int tid = threadIdx.x;
+    const float fnan = __int_as_float(0x7fffffff);
     const int tw = tp.tw, th = tp.th;
-    const int ne = s.misc[0];
+    const int ne = s.misc[buf * 4];
+    const unsigned long long *bits = s.bits + buf * kFH;
     const int nrow_items = th * 32;
     const int nitems = (a.dbg & 4) ? 0 : nrow_items + ne;
-    const LeanConsts K = *s.K;
+    const double4 *st0 = s.st + buf * kFC;
+    const double *rad0p = s.rrad + buf * kFC;
+    // FP64 state / radius of record p: plane 0 in the copied frame, extras in their list
+    auto xy_of = [&](int p) { return reinterpret_cast<const double2 *>(p < kFC ? st0 + p : s.xst + (p - kFC))[0]; };
+    auto vv_of = [&](int p) { return reinterpret_cast<const double2 *>(p < kFC ? st0 + p : s.xst + (p - kFC))[1]; };
+    auto rad_of = [&](int p) { return radii ? (p < kFC ? rad0p[p] : s.xrad[p - kFC]) : a.rad0; };
 #pragma unroll 1
     for (int w = tid; w < nitems; w += kTileThreads) {
         // work item: a cell of the tile (its plane-0 disk), then the extras
@@ -483,7 +702,7 @@ __device__ __forceinline__ void cell_main(const SweepArgs &a, const CellSmem &s,
         // extras in the 3 x 3 block: bit 3 j + k
         unsigned xm = 0;
 #pragma unroll
-        for (int j = 0; j < 3; j++) xm |= ((unsigned)(s.bits[fy + j - 1] >> (fx - 1)) & 7u) << (3 * j);
+        for (int j = 0; j < 3; j++) xm |= ((unsigned)(bits[fy + j - 1] >> (fx - 1)) & 7u) << (3 * j);
         if (!(a.dbg & 1)) {
 #pragma unroll
             for (int j = 0; j < 3; j++)
@@ -508,8 +727,8 @@ __device__ __forceinline__ void cell_main(const SweepArgs &a, const CellSmem &s,
         // flies while the exact stage computes
         const int wloc = idx >= 0 ? s.id[idx] : -1;
         const int wglob = (wloc >= 0 && a.gid) ? a.gid[wloc] : wloc;
-        const double2 mexy = s.xy[p], mev = s.vv[p];
-        const double rad_i = radii ? s.rad[p] : a.rad0;
+        const double2 mexy = xy_of(p), mev = vv_of(p);
+        const double rad_i = rad_of(p);
         if (a.dbg & 2) {
             st_ev(a.ev + id, (double)second + mexy.x, 0.0, idx, 0);
             continue;
@@ -527,10 +746,10 @@ __device__ __forceinline__ void cell_main(const SweepArgs &a, const CellSmem &s,
         int best_id = -1, best_pc = -1, ov_id = -1, ov_pc = -1;
         bool certified = idx < 0;   // no candidate can collide: partner 0 at t + 1e26
         if (idx >= 0) {
-            const double2 wxy = s.xy[idx], wv = s.vv[idx];
+            const double2 wxy = xy_of(idx), wv = vv_of(idx);
             SRec p2;
             p2.x = wxy.x; p2.y = wxy.y; p2.vx = wv.x; p2.vy = wv.y;
-            p2.rad = radii ? s.rad[idx] : a.rad0; p2.id = wloc; p2.pc = 0;
+            p2.rad = rad_of(idx); p2.id = wloc; p2.pc = 0;
             double bb, v2, cc, b2, vc;
             pair_terms<true>(a.b, p1, four_r1, p2, bb, v2, cc, b2, vc);
             const double det = __dsub_rn(b2, vc);
@@ -550,9 +769,9 @@ __device__ __forceinline__ void cell_main(const SweepArgs &a, const CellSmem &s,
             best_id = -1;
             auto cand = [&](int q, int scan_cell) {
                 SRec p2;
-                const double2 qxy = s.xy[q], qv = s.vv[q];
+                const double2 qxy = xy_of(q), qv = vv_of(q);
                 p2.x = qxy.x; p2.y = qxy.y; p2.vx = qv.x; p2.vy = qv.y;
-                p2.rad = radii ? s.rad[q] : a.rad0; p2.id = s.id[q];
+                p2.rad = rad_of(q); p2.id = s.id[q];
                 p2.pc = scan_cell;
                 bool ov = false;
                 const double dt = pair_time_normal<true>(a.b, p1, four_r1, p2, ov);
@@ -591,34 +810,111 @@ __device__ __forceinline__ void cell_main(const SweepArgs &a, const CellSmem &s,
     }
 }
 
+// One CTA = a persistent worker.  While it sweeps tile k the bulk copies of tile k+1's frame land in the other
+// state buffer, so the memory latency of a frame hides behind the arithmetic of the previous one.  Tiles are
+// handed out dynamically (one global counter, reset by the partition kernel; the first gridDim.x tiles are
+// taken statically): a static round-robin leaves most SMs idle for the last tile of the slowest workers
+// (2232 tiles over 444 workers: six rounds for 5.03 rounds of work, measured +20 %).
+template <bool TWO>
+__device__ __forceinline__ void cell_worker(const SweepArgs &a, const SweepSmem &s, const bool radii)
+{
+    const int tid = threadIdx.x;
+    const int ntiles = a.tg.ntiles;
+    const LeanConsts K = *s.K;
+    int buf = 0;
+    unsigned phases = 0u;   // bit b = parity of the next completion of mbar[b]
+    int tile = blockIdx.x;
+    int it = 0;
+    const bool stamp = a.ts && blockIdx.x == 0 && tid == 0;   // timing experiments (option 100, bit 32)
+#pragma unroll 1
+    while (tile < ntiles) {
+        const TilePos tp = tile_pos(a.tg, tile);
+        if (stamp && it < 6) edmd_stamp(a.ts, 16 + 4 * it);
+        // the next tile: asked for now (the round trip hides behind the convert pass), fetched while this
+        // one is swept.  ONE tile ahead, not two: what a worker holds when the counter runs out is the tail
+        // of the kernel (two tiles held: workers ended over a span of 25 us, measured).
+        int next = ntiles;
+        if (tid == 0) next = atomicAdd(a.flags + kFlagTileCtr, 1);
+        frame_tables(a, s, tp);
+        __syncthreads();
+        mbar_wait(&s.mbar[buf], (phases >> buf) & 1u);
+        phases ^= 1u << buf;
+        if (stamp && it < 6) edmd_stamp(a.ts, 17 + 4 * it);
+        if (tid == 0) s.misc[buf * 4 + 2] = next;
+        const bool fits = frame_convert<TWO>(a, s, tp, buf, radii);
+        if (stamp && it < 6) edmd_stamp(a.ts, 18 + 4 * it);
+        if (!fits) {   // more extras than the frame's list holds: decline (no copy is in flight here)
+            if (tid == 0) atomicOr(&a.flags[kFlagLeanFail], 1);
+            return;
+        }
+        next = s.misc[buf * 4 + 2];
+        if (next < ntiles && tid < 32) frame_issue(a, s, tile_pos(a.tg, next), buf ^ 1, radii);
+        // the other set of lists (of the previous tile) goes back to empty for the next one
+        if (tid >= 32 && tid < 32 + kFH) s.bits[(buf ^ 1) * kFH + tid - 32] = 0ull;
+        if (tid >= 62 && tid < 64) s.misc[(buf ^ 1) * 4 + tid - 62] = 0;
+        cell_tile<TWO>(a, s, tp, buf, radii, K);
+        if (stamp && it < 6) edmd_stamp(a.ts, 19 + 4 * it);
+        it++;
+        __syncthreads();   // the records of this tile are dead (the other state buffer has been filling meanwhile)
+        tile = next;
+        buf ^= 1;
+    }
+    if (stamp) edmd_stamp(a.ts, 15);
+    if (a.ts && tid == 0) {   // timing experiments: the last worker's end, the largest number of tiles per worker
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(a.ts + 14, t);
+        atomicMax(a.ts + 13, (unsigned long long)it);
+        atomicAdd(a.ts + 12, (unsigned long long)it);
+        // histogram of the workers' end times, 2 us bins from the first thread of the partition kernel
+        const unsigned long long t4 = *reinterpret_cast<volatile unsigned long long *>(a.ts + 4);
+        long long bin = t > t4 ? (long long)((t - t4) / 2000ull) - 16 : 0;
+        bin = bin < 0 ? 0 : (bin > 23 ? 23 : bin);
+        atomicAdd(a.ts + 40 + bin, 1ull);
+    }
+}
+
 __global__ void __launch_bounds__(kTileThreads, kTileCtas)
 k_cell_sweep(const __grid_constant__ SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char cell_smem[];
-    const CellSmem s = carve(cell_smem, a.tg.ecap, a.rad_smem, false);
+    const SweepSmem s = carve_sweep(cell_smem, a.tg.ecap, a.rad_smem);
     const int tid = threadIdx.x;
-    const TilePos tp = tile_pos(a.tg, blockIdx.x);
     // before the partition is complete: what does not depend on it
-    if (tid < kFH) s.bits[tid] = 0ull;
-    if (tid < 2) s.misc[tid] = 0;
-    zero_other_counters(a, tp);
+    if (tid < 2 * kFH) s.bits[tid] = 0ull;
+    if (tid < 8) s.misc[tid] = 0;
+    if (tid == 0) {
+        mbar_init(&s.mbar[0], 1);
+        mbar_init(&s.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     edmd_pdl_wait();
     if (blockIdx.x == 0 && tid == 0) edmd_stamp(a.ts, 7);
     const int classes = a.flags[kFlagNotMono];   // 0: one radius, 1: two classes, more: not eligible
     const double rad1 = __longlong_as_double(*reinterpret_cast<const long long *>(a.flags + kFlagRad1));
     const bool declined = a.flags[kFlagLeanFail] != 0;
     const bool bad = a.flags[kFlagInsane] != 0 || classes > 1 || (classes == 1 && !a.rad_smem);
-    // one thread derives the screening constants while the others have their frame loads in flight
-    if (tid == kTileThreads - 1) *s.K = make_consts(a.b, a.rad0, rad1, classes == 1, __int_as_float(a.flags[kFlagVmax]));
+    if (blockIdx.x == 0 && tid == 0) edmd_stamp(a.ts, 8);
     if (declined) return;   // a cell overflowed: the host re-runs the sweep on another path
     if (bad) {
         if (tid == 0) atomicOr(&a.flags[kFlagLeanFail], 1);   // not eligible: decline
         return;
     }
+    const bool radii = classes == 1;
+    // the first frame is on its way while one thread derives the screening constants
+    if (tid < 32) frame_issue(a, s, tile_pos(a.tg, blockIdx.x), 0, radii);
+    if (tid == kTileThreads - 1) *s.K = make_consts(a.b, a.rad0, rad1, classes == 1, __int_as_float(a.flags[kFlagVmax]));
+    __syncthreads();
+    if (!s.K->ok) {   // a velocity scale outside the FP32-safe range: decline -- once the copy in flight has landed
+        mbar_wait(&s.mbar[0], 0u);
+        if (tid == 0) atomicOr(&a.flags[kFlagLeanFail], 1);
+        return;
+    }
     // classes == 1: the radii are spread inside their classes (a reference-grown system): the exact
     // stage takes every disk's own FP64 radius; the class bit is only looked at when a second class exists
-    if (classes == 1 && rad1 > 0.0) cell_main<true>(a, s, tp, true);
-    else cell_main<false>(a, s, tp, classes == 1);
+    if (classes == 1 && rad1 > 0.0) cell_worker<true>(a, s, true);
+    else cell_worker<false>(a, s, radii);
 }
 
 // ---- K4 on the cell slots: computeBOOPCutoff, src/boop.c:61-107 ---------------------------
@@ -803,7 +1099,9 @@ bool edmd_tile_eligible(const edmd_ctx *c, int mode)
     return edmd_lean_eligible(c, mode) && !c->tile_off && c->pst != nullptr;
 }
 
-// geometry of the tiles + the extras a frame may hold, for a context of nx x nl cells and n particles
+// Geometry of the tiles + the extras a frame may hold, for a context of nx x nl cells and n particles.
+// (Measured and not kept: half-height tiles for half of the workers at the start and for everybody's last
+// tiles, to break the workers' lock-step and shorten the tail: 63.5 us against 61.5 us for equal tiles.)
 bool edmd_tile_geometry(int nx, int nl, size_t n, TileGeom *out)
 {
     TileGeom tg;
@@ -811,17 +1109,18 @@ bool edmd_tile_geometry(int nx, int nl, size_t n, TileGeom *out)
     tg.nty = (nl + kTY - 1) / kTY;
     tg.wlast = nx - (tg.ntx - 1) * kTX;
     tg.hlast = nl - (tg.nty - 1) * kTY;
+    tg.ntiles = tg.ntx * tg.nty;
     // Extras per cell = mean occupancy - P(occupied).  Hard disks in cells one diameter wide stay far below
     // a Poisson process of the same density (1.8 - 11 % against 30 %), mixtures with small disks come close to it:
-    // the Poisson figure + a margin is provided for, and at least 30 % of the frame.
+    // the Poisson figure + a margin is provided for, and at least 22 % of the frame.
     const double dens = (double)n / ((double)nx * (double)nl);   // particles per cell
     const double poisson = dens - 1.0 + exp(-dens);
-    long long ecap = (long long)(kFC * fmax(0.30, 1.15 * poisson)) + 32;
+    long long ecap = (long long)(kFC * fmax(0.22, 1.15 * poisson)) + 32;
     ecap = (ecap + 31) & ~31ll;
     if (ecap > 4064) return false;   // xinfo holds 12 bits of extras index
     if (nx > 32000 || nl > 32000) return false;   // frame_load keeps cell coordinates in 16 bits
     tg.ecap = (int)ecap;
-    if (cell_smem_bytes(tg.ecap, 1, false) > 200 * 1024) return false;   // denser than a CTA's shared memory provides for
+    if (sweep_smem_bytes(tg.ecap, 1) > 200 * 1024) return false;   // denser than a CTA's shared memory provides for
     *out = tg;
     return true;
 }
@@ -837,10 +1136,36 @@ int edmd_launch_unpack_events(edmd_ctx *c)
 // A new partition goes to the other counter buffer (zeroed by the consumers of the current one).
 void edmd_tile_begin_partition(edmd_ctx *c) { c->cbuf ^= 1; }
 
+// Extras a frame of the sweep kernel lists.  tgeom.ecap provides for a Poisson process of the system's density
+// (mixtures with small disks come close to it); disks of ONE radius class in cells one diameter wide stay far
+// below (1.8 - 11 % of the cells hold a second disk): 23.5 % of the frame then, which lets one more CTA fit an SM.
+static int sweep_ecap(const edmd_ctx *c)
+{
+    const int mono = ((int)(0.235 * kFC) + 15) & ~15;
+    return (!c->lean_two && mono < c->tgeom.ecap) ? mono : c->tgeom.ecap;
+}
+
+// CTAs of the persistent sweep kernel: as many as are resident at once (asked of the runtime: a worker that
+// had to wait for a free slot would begin its first tile when the others are through), at most one per tile
+static void tile_attrs();
+static int sweep_workers(const edmd_ctx *c)
+{
+    const int ntiles = c->tgeom.ntiles;
+    const size_t smem = sweep_smem_bytes(sweep_ecap(c), c->lean_two ? 1 : 0);
+    tile_attrs();
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cell_sweep, kTileThreads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    if (getenv("EDMD_DEBUG_WORKERS")) fprintf(stderr, "k_cell_sweep: %zu bytes of shared memory, %d CTAs per SM\n", smem, per_sm);
+    const int sms = c->sm_count > 0 ? c->sm_count : 148;
+    return ntiles < sms * per_sm ? ntiles : sms * per_sm;
+}
+
 static PartArgs part_args(edmd_ctx *c, int first, int n)
 {
     PartArgs pa;
-    pa.first = first; pa.n = n; pa.ncp = c->ncp; pa.dbg = c->tile_dbg;
+    pa.first = first; pa.n = n; pa.ncp = c->ncp; pa.dbg = c->tile_dbg; pa.ps = c->ps; pa.nx = c->dbox.nx;
+    pa.workers = sweep_workers(c);
     pa.late_wait = 0;
     pa.cid = c->cid; pa.xv = c->xv; pa.rad = c->rad; pa.rad0 = c->rad0;
     pa.flags = c->flags;
@@ -923,13 +1248,15 @@ static void tile_attrs()
     attr = true;
 }
 
-// the sweep kernel over the cell slots (P2)
+// the sweep kernel over the cell slots (P2): persistent CTAs, kTileCtas per SM
 int edmd_launch_tile_sweep_only(edmd_ctx *c)
 {
-    const SweepArgs sa = sweep_args(c);
+    SweepArgs sa = sweep_args(c);
     tile_attrs();
-    edmd_launch(k_cell_sweep, dim3(c->tgeom.ntx * c->tgeom.nty), dim3(kTileThreads),
-                cell_smem_bytes(c->tgeom.ecap, sa.rad_smem, false), c->stream, c->lean_pdl, sa);
+    sa.tg.ecap = sweep_ecap(c);
+    const size_t smem = sweep_smem_bytes(sa.tg.ecap, sa.rad_smem);
+    const int grid = sweep_workers(c);
+    edmd_launch(k_cell_sweep, dim3(grid), dim3(kTileThreads), smem, c->stream, c->lean_pdl, sa);
     c->pred_packed = true;
     return 1;
 }
@@ -952,7 +1279,7 @@ int edmd_launch_tile_boop(edmd_ctx *c, double r_c, bool from_keep)
     ba.rc2 = r_c * r_c;   // `r_c*r_c`, a single rounded product
     ba.rec = c->boop_rec;
     tile_attrs();
-    edmd_launch(k_cell_boop, dim3(c->tgeom.ntx * c->tgeom.nty), dim3(kTileThreads),
+    edmd_launch(k_cell_boop, dim3(c->tgeom.ntiles), dim3(kTileThreads),
                 cell_smem_bytes(c->tgeom.ecap, 0, true), c->stream, c->lean_pdl && !from_keep, ba);
     // halo copies of a slab context are not computed: the unpack covers the owned particles
     const int no = c->n_owned;

@@ -285,7 +285,7 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
         if ((r = dev_alloc(c, &c->ccnt, 2 * ncp + 32))) return r;
         if ((r = dev_alloc(c, &c->boop_rec, 2 * N + 8))) return r;
         if ((r = dev_alloc(c, &c->evrec, N + 32))) return r;
-        CU(cudaMemsetAsync(c->ccnt, 0, (2 * ncp + 32) * sizeof(int32_t), c->stream));
+        CU(cudaMemsetAsync(c->ccnt, 0, (2 * ncp + 32) * sizeof(unsigned long long), c->stream));
         c->cbuf = 0;
     }
     if ((r = dev_alloc(c, &c->t_cross, N))) return r;
@@ -296,8 +296,8 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
     CU(cudaMemsetAsync(c->ctype, EDMD_EV_COLLISION, N ? N : 1, c->stream));   // the constant COLLISION (src/EDMD.h:19-34)
     if ((r = dev_alloc(c, &c->overlap_key, 1))) return r;
     if ((r = dev_alloc(c, &c->flags, kFlagCount))) return r;
-    if ((r = dev_alloc(c, &c->dbg_ts, 16))) return r;
-    CU(cudaMemsetAsync(c->dbg_ts, 0, 16 * sizeof(unsigned long long), c->stream));
+    if ((r = dev_alloc(c, &c->dbg_ts, 64))) return r;
+    CU(cudaMemsetAsync(c->dbg_ts, 0, 64 * sizeof(unsigned long long), c->stream));
     CU(cudaMemsetAsync(c->flags, 0, kFlagCount * sizeof(int32_t), c->stream));
     if ((r = dev_alloc(c, &c->boop, 4 * N))) return r;
     if ((r = dev_alloc(c, &c->boop_nb, N))) return r;
@@ -417,7 +417,7 @@ int edmd_cuda_get_stat(edmd_ctx *c, int stat, uint64_t *value)
         *value = edmd_lean_eligible(c, EDMD_MODE_NORMAL) ? 1 : 0;
         return 0;
     }
-    if (stat >= 100 && stat < 116) {   // internal: timing experiments
+    if (stat >= 100 && stat < 164) {   // internal: timing experiments
         CU(cudaSetDevice(c->device));
         unsigned long long v = 0;
         CU(cudaMemcpyAsync(&v, c->dbg_ts + (stat - 100), sizeof(v), cudaMemcpyDeviceToHost, c->stream));
@@ -1582,6 +1582,10 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
         }
         cudaEvent_t *e = it >= 0 ? &evs[3 * (size_t)it] : nullptr;
         if (e) CU(cudaEventRecord(e[0], c->stream));
+        // ms_main == NULL: no event between the kernels of a sweep -- the chain runs as the product calls launch
+        // it (an event record between two kernels keeps the second one's programmatic launch from overlapping
+        // the first one's tail)
+        cudaEvent_t mid = (e && (ms_main || what != EDMD_BENCH_SWEEP)) ? e[1] : nullptr;
         switch (what) {
         case EDMD_BENCH_SWEEP:
             // (the tile sweep's first kernel resets the overlap report itself)
@@ -1591,24 +1595,24 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
                 // multi-GPU step: the halo exchange (peer stores over NVLink) is part of it, hidden behind
                 // the partition of the owned particles; every rank runs the same number of iterations,
                 // epochs advance in lockstep
-                int r = exchange_predict_launch(c, mode, e ? e[1] : nullptr);
+                int r = exchange_predict_launch(c, mode, mid);
                 if (r) return r;
                 break;
             }
             c->index_tile = false;
             c->pred_packed = false;
             if (edmd_tile_eligible(c, mode)) {
-                c->launches += edmd_launch_tile_sweep(c, e ? e[1] : nullptr);
+                c->launches += edmd_launch_tile_sweep(c, mid);
                 c->index_lean = true;
                 c->index_tile = true;
             } else if (edmd_lean_eligible(c, mode)) {
                 c->launches += edmd_launch_lean_index(c);
-                if (e) CU(cudaEventRecord(e[1], c->stream));
+                if (mid) CU(cudaEventRecord(mid, c->stream));
                 c->launches += edmd_launch_predict_lean(c);
                 c->index_lean = true;
             } else {
                 c->launches += edmd_launch_cell_index(c, mode);
-                if (e) CU(cudaEventRecord(e[1], c->stream));
+                if (mid) CU(cudaEventRecord(mid, c->stream));
                 c->launches += edmd_launch_predict(c, mode);
                 c->index_lean = false;
             }
@@ -1672,7 +1676,7 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
     for (int it = 0; it < iters; it++) {
         float a = 0, b = 0;
         CU(cudaEventElapsedTime(&a, evs[3 * (size_t)it], evs[3 * (size_t)it + 2]));
-        CU(cudaEventElapsedTime(&b, evs[3 * (size_t)it + 1], evs[3 * (size_t)it + 2]));
+        if (ms_main || what != EDMD_BENCH_SWEEP) CU(cudaEventElapsedTime(&b, evs[3 * (size_t)it + 1], evs[3 * (size_t)it + 2]));
         if (ms_total) ms_total[it] = a;
         if (ms_main) ms_main[it] = b;
     }

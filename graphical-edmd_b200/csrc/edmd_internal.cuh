@@ -123,22 +123,27 @@ enum {
     kFlagNotMono = 5,    // radii: 0 all EXACTLY rad0, 1 at most two classes (rad0's and kFlagRad1's, see edmd_note_radius), >= 2 more
     kFlagLeanFail = 6,   // the lean sweep declined (state not eligible): redo with the full path
     kFlagWork = 7,       // number of entries in the lean work list (chunks that hold particles)
+    kFlagTileCtr = 11,   // next tile of the persistent sweep kernel (reset by the partition kernel)
     kFlagBoopFail = 10,  // the tile psi6 kernel declined (a bucket beyond a CTA's shared memory)
     kFlagRad1 = 8,       // (two words, 8-byte aligned) bits of the first radius seen outside rad0's class, 0 = none
     kFlagCount = 16
 };
 
 // ---- cell-slot sweep (cell_sweep.cu): kSlotK planes over the padded cell grid, tiles of kTX x kTY cells ----
-constexpr int kTX = 32, kTY = 16;                                // cells per tile
+#ifndef EDMD_TILE_ROWS
+#define EDMD_TILE_ROWS 8
+#endif
+constexpr int kTX = 32, kTY = EDMD_TILE_ROWS;                    // cells per tile
 constexpr int kFW = kTX + 2, kFH = kTY + 2, kFC = kFW * kFH;     // a tile's frame: the tile + a one-cell ring
-constexpr int kTileThreads = 256;
+constexpr int kTileThreads = 16 * kTY;                           // one warp per two tile rows
 constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kTileCtas = 3;                                     // per SM (<= 85 registers per thread)
+constexpr int kTileCtas = 768 / kTileThreads;                    // per SM: 24 warps at <= 85 registers per thread
 constexpr int kSlotK = 8;                                        // disks one cell can hold (plane s = s-th arrival)
 struct TileGeom {
     int ntx, nty;            // tiles per row of tiles / rows of tiles
     int wlast, hlast;        // width of the last tile column, height of the last tile row
     int ecap;                // extras (disks of planes 1..) one frame can list in shared memory
+    int ntiles;
 };
 
 struct edmd_ctx {
@@ -225,7 +230,7 @@ struct edmd_ctx {
     double4 *pst;                    // [kSlotK][ncp] FP64 states: plane s = the s-th arrival of every padded cell
     int32_t *pid;                    // ... their particle ids
     double *prad;                    // ... and radii (written only when the radii are not all exactly rad0)
-    int32_t *ccnt;                   // [2][ncp] disks per cell, double-buffered (consumers zero the other buffer)
+    unsigned long long *ccnt;        // [2][ncp] cell words (count << 32 | sum of ids), double-buffered (consumers zero the other buffer)
     int cbuf;                        // the buffer of the current partition
     bool boop_tile_off;              // EDMD_OPT_NO_TILE_BOOP
     double4 *boop_rec;               // psi6 records of the tile kernel: two sectors per particle id

@@ -19,7 +19,9 @@ extern "C" {
 /* Runs `warmup` untimed and `iters` timed passes of the chosen device path,
  * writing `flush_bytes` of scratch between passes (L2 flush, outside the timed
  * events) when flush_bytes > 0.  ms_total[iters] = whole pass,
- * ms_main[iters] = the dominant kernel alone (K1 for the sweep). */
+ * ms_main[iters] = the dominant kernel alone (K1 for the sweep).  EDMD_BENCH_SWEEP with ms_main == NULL: no
+ * event is recorded between K0 and K1, the two run as the product calls launch them (programmatic dependent
+ * launch: K1's launch latency and prologue overlap K0's tail) -- ms_total is then the step as shipped. */
 int edmd_cuda_bench(edmd_ctx *ctx, int what, int mode, double dr, double max_r,
                     int warmup, int iters, size_t flush_bytes, float *ms_total,
                     float *ms_main);

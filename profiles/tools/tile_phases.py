@@ -17,3 +17,5 @@ with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
         tot, main = ctx.bench(B.BENCH_SWEEP, warmup=3, iters=20, flush_bytes=256 << 20)
         print(f"{name:40s}: step {np.median(tot)*1e3:7.1f} us  P2 {np.median(main)*1e3:7.1f} us  P1 {np.median(tot-main)*1e3:6.1f} us", flush=True)
     ctx.set_option(100, 0)
+    tot, _ = ctx.bench(B.BENCH_SWEEP, warmup=3, iters=20, flush_bytes=256 << 20, split=False)
+    print(f"{'the chain as shipped (no event between)':40s}: step {np.median(tot)*1e3:7.1f} us (min {np.min(tot)*1e3:.1f})", flush=True)

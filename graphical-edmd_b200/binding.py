@@ -52,6 +52,7 @@ SYMBOLS = [
     "edmd_cuda_boop_voronoi", "edmd_cuda_voronoi_cells", "edmd_cuda_g6_correlation",
     "edmd_cuda_structure_factor", "edmd_cuda_kinetic", "edmd_cuda_rescale_velocities",
     "edmd_cuda_selftest_rsqrt", "edmd_cuda_langevin_kick",
+    "edmd_cuda_normalize_velocities", "edmd_cuda_shift_scale_velocities",
 ]
 EVORONOI = 7
 HALO_RECORD_BYTES = 48
@@ -130,6 +131,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_selftest_rsqrt.argtypes = [vp, C.POINTER(C.c_double)]
     lib.edmd_cuda_langevin_kick.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32]
     lib.edmd_cuda_kinetic.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.edmd_cuda_normalize_velocities.argtypes = [vp, C.c_double] + [C.POINTER(C.c_double)] * 4
+    lib.edmd_cuda_shift_scale_velocities.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     lib.edmd_cuda_rescale_velocities.argtypes = [vp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.edmd_cuda_boop_voronoi.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.edmd_cuda_voronoi_cells.argtypes = [vp, vp, vp, vp]
@@ -321,6 +324,17 @@ class EdmdCuda:
         """Langevin kick on the resident velocities (edmd_cuda_langevin_kick)."""
         self._check(self.lib.edmd_cuda_langevin_kick(self._h, float(T), float(gamma), float(dtnoise),
                                                      int(seed) & 0xFFFFFFFF, int(tick) & 0xFFFFFFFF))
+
+    def normalize_velocities(self, e_init=1.0):
+        """normalizePhysicalQ on the resident velocities (edmd_cuda_normalize_velocities)."""
+        px, py, e, d = (C.c_double(0.0) for _ in range(4))
+        self._check(self.lib.edmd_cuda_normalize_velocities(self._h, float(e_init), C.byref(px), C.byref(py),
+                                                            C.byref(e), C.byref(d)))
+        return dict(px_before=px.value, py_before=py.value, E_shifted=e.value, divisor=d.value)
+
+    def shift_scale_velocities(self, dvx, dvy, divisor):
+        """v <- (v - (dvx, dvy)) / divisor (edmd_cuda_shift_scale_velocities)."""
+        self._check(self.lib.edmd_cuda_shift_scale_velocities(self._h, float(dvx), float(dvy), float(divisor)))
 
     def selftest_rsqrt(self) -> float:
         """Largest relative error of the hardware rsqrt over [2^-100, 2^64) (edmd_cuda_selftest_rsqrt)."""

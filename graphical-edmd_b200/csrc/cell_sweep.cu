@@ -929,7 +929,7 @@ struct BoopTileArgs {
     double rc2;
     double4 *rec;   // two 32-byte sectors per particle id: (q5, q6, q7, q6_arg), (neighbours, 0, 0, 0)
 };
-constexpr int kBoopCtas = 4;   // per SM
+constexpr int kBoopCtas = 1024 / kTileThreads;   // per SM: 32 warps at 64 registers per thread
 
 __global__ void __launch_bounds__(kTileThreads, kBoopCtas)
 k_cell_boop(const __grid_constant__ BoopTileArgs ba)
@@ -1142,7 +1142,8 @@ void edmd_tile_begin_partition(edmd_ctx *c) { c->cbuf ^= 1; }
 static int sweep_ecap(const edmd_ctx *c)
 {
     const int mono = ((int)(0.235 * kFC) + 15) & ~15;
-    return (!c->lean_two && mono < c->tgeom.ecap) ? mono : c->tgeom.ecap;
+    const bool one_class = !c->lean_two || !(c->rad1 > 0.0);   // (spread radii inside ONE class: a reference-grown system)
+    return (one_class && mono < c->tgeom.ecap) ? mono : c->tgeom.ecap;
 }
 
 // CTAs of the persistent sweep kernel: as many as are resident at once (asked of the runtime: a worker that

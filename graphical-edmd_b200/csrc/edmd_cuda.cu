@@ -1271,6 +1271,51 @@ int edmd_cuda_rescale_velocities(edmd_ctx *c, double T, double *E_before, double
     return 0;
 }
 
+int edmd_cuda_shift_scale_velocities(edmd_ctx *c, double dvx, double dvy, double divisor)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "shift_scale before upload");
+    if (!(divisor > 0) || !(dvx == dvx) || !(dvy == dvy)) return fail(c, EDMD_EINVAL, "shift_scale: the divisor must be positive, the shift a number");
+    CU(cudaSetDevice(c->device));
+    c->launches += edmd_launch_shift_scale(c, dvx, dvy, divisor, nullptr, false, c->n_owned, nullptr);
+    CU(cudaGetLastError());
+    c->have_pred = false;
+    c->have_index = false;   // the cell-ordered records carry velocities
+    return check_flags(c);   // synchronises; refreshes vmax / lean eligibility
+}
+
+int edmd_cuda_normalize_velocities(edmd_ctx *c, double Einit, double *px_before, double *py_before, double *E_shifted,
+                                   double *divisor)
+{
+    if (!c) return EDMD_EINVAL;
+    if (!c->have_state) return fail(c, EDMD_ESTATE, "normalize before upload");
+    // the sums are the WHOLE system's (normalizePhysicalQ, src/EDMD.c:5723-5764): a slab only knows its own
+    if (c->slab)
+        return fail(c, EDMD_ESTATE, "slab contexts: all-reduce edmd_cuda_kinetic's sums, then edmd_cuda_shift_scale_velocities");
+    if (!(Einit > 0)) return fail(c, EDMD_EINVAL, "Einit must be positive");
+    CU(cudaSetDevice(c->device));
+    double *red = nullptr, h1[4] = {0, 0, 0, 0}, h2[4] = {0, 0, 0, 0};
+    int r;
+    // physicalQ -> v -= p/(N m) (+ the sums of the shifted velocities in the same pass) -> v /= sqrt(E/N/Einit)
+    if ((r = kinetic_run(c, 0.0, &red))) return r;
+    CU(cudaMemcpyAsync(h1, red, sizeof(h1), cudaMemcpyDeviceToHost, c->stream));
+    c->launches += edmd_launch_shift_scale(c, 0.0, 0.0, 1.0, red, false, c->n_owned, c->thermo_mem);
+    red = edmd_launch_kinetic_final(c, Einit, c->thermo_mem, c->n_owned);
+    c->launches += 1;
+    CU(cudaMemcpyAsync(h2, red, sizeof(h2), cudaMemcpyDeviceToHost, c->stream));
+    c->launches += edmd_launch_shift_scale(c, 0.0, 0.0, 1.0, red, true, c->n_owned, nullptr);
+    CU(cudaGetLastError());
+    c->have_pred = false;
+    c->have_index = false;   // the cell-ordered records carry velocities
+    if ((r = check_flags(c))) return r;   // synchronises; refreshes vmax / lean eligibility
+    if (px_before) *px_before = h1[1];
+    if (py_before) *py_before = h1[2];
+    if (E_shifted) *E_shifted = h2[0];
+    if (divisor) *divisor = h2[3];
+    if (!(h2[3] > 0)) return fail(c, EDMD_EINVAL, "normalize: the system has no kinetic energy");
+    return 0;
+}
+
 int edmd_cuda_langevin_kick(edmd_ctx *c, double T, double gamma, double dtnoise, uint32_t seed, uint32_t tick)
 {
     if (!c) return EDMD_EINVAL;

@@ -345,6 +345,9 @@ int edmd_launch_psi6(edmd_ctx *c, const double *q6, const double *arg, double2 *
 size_t edmd_thermostat_scratch_doubles();
 double *edmd_launch_kinetic(edmd_ctx *c, double T, double *scratch, int *launched);
 int edmd_launch_rescale(edmd_ctx *c, const double *red);
+int edmd_launch_shift_scale(edmd_ctx *c, double dvx, double dvy, double divisor, const double *red, bool div_from_red,
+                            int n_total, double *sums);
+double *edmd_launch_kinetic_final(edmd_ctx *c, double T, double *scratch, int n_total);
 int edmd_launch_langevin(edmd_ctx *c, double T, double gamma, double dtnoise, unsigned int seed, unsigned int tick);
 int edmd_launch_bragg(edmd_ctx *c, int nk, const double2 *kvec, double *re, double *im, double *best_s,
                       int *best_i);

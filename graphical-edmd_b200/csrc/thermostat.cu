@@ -90,6 +90,51 @@ k_rescale(int n, const double *__restrict__ red, double4 *__restrict__ xv, int32
     if ((threadIdx.x & 31) == 0 && vmb) atomicMax(reinterpret_cast<unsigned int *>(&flags[kFlagVmax]), vmb);
 }
 
+// normalizePhysicalQ (src/EDMD.c:5723-5764, the branch without a circular wall; unit masses):
+//   `vx -= px/(N*m); vy -= py/(N*m);`  then, with the E of the shifted velocities,  `vx /= sqrt(E/N/Einit)`.
+// shift = (dvx, dvy) subtracted first, then -- when divisor != 1 -- the division: the reference's two
+// roundings.  `red` (nullable): take dvx = red[1]/n, dvy = red[2]/n from the device's sums instead.
+// Optionally accumulates the kinetic sums of the NEW velocities (partial != nullptr) for the step that follows.
+__global__ void __launch_bounds__(kThreads)
+k_shift_scale(int n, int n_total, double dvx, double dvy, double divisor, const double *__restrict__ red, int div_from_red,
+              double4 *__restrict__ xv, int32_t *__restrict__ flags, double *__restrict__ partial)
+{
+    if (red && !div_from_red) {
+        // `px/(N*particles[i].m)` with m == 1
+        dvx = __ddiv_rn(red[1], __dmul_rn((double)n_total, 1.0));
+        dvy = __ddiv_rn(red[2], __dmul_rn((double)n_total, 1.0));
+    }
+    if (red && div_from_red) divisor = red[3];
+    double e = 0, px = 0, py = 0;
+    float vm = 0.0f;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        double4 p = xv[i];
+        p.z = __dsub_rn(p.z, dvx);
+        p.w = __dsub_rn(p.w, dvy);
+        if (divisor != 1.0) {
+            p.z = __ddiv_rn(p.z, divisor);
+            p.w = __ddiv_rn(p.w, divisor);
+        }
+        xv[i] = p;
+        e += 0.5 * (p.z * p.z + p.w * p.w);
+        px += p.z;
+        py += p.w;
+        float v = __double2float_ru(fmax(fabs(p.z), fabs(p.w)));
+        if (!(v == v)) v = __int_as_float(0x7f800000);
+        vm = fmaxf(vm, v);
+    }
+    const unsigned vmb = __reduce_max_sync(0xffffffffu, (unsigned)__float_as_int(vm));
+    if ((threadIdx.x & 31) == 0 && vmb) atomicMax(reinterpret_cast<unsigned int *>(&flags[kFlagVmax]), vmb);
+    if (partial) {
+        block_sum3(e, px, py);
+        if (threadIdx.x == 0) {
+            partial[blockIdx.x] = e;
+            partial[kBlocks + blockIdx.x] = px;
+            partial[2 * kBlocks + blockIdx.x] = py;
+        }
+    }
+}
+
 // ---- Langevin kick (addNoise with noise == 1: randomGaussian, src/EDMD.c:5802-5826) ----
 // Counter-based uniforms: the generator of graphical-edmd_b200/synth.py (splitmix64 finaliser over
 // (seed, id, stream)), so that numpy reproduces every draw.
@@ -160,6 +205,29 @@ double *edmd_launch_kinetic(edmd_ctx *c, double T, double *scratch, int *launche
     k_kinetic_partial<<<kBlocks, kThreads, 0, c->stream>>>(c->n_owned, c->xv, scratch);
     k_kinetic_final<<<1, kThreads, 0, c->stream>>>(c->n_owned, T, scratch, out);
     *launched += 2;
+    return out;
+}
+
+// v <- (v - shift) / divisor on the owned particles.  red != nullptr: the shift is the centre-of-mass velocity
+// red[1..2] / n_total (normalizePhysicalQ's first loop), or -- div_from_red -- the divisor is red[3].
+// sums != nullptr: the kinetic sums of the new velocities go to sums (scratch of edmd_launch_kinetic's layout),
+// finished by edmd_launch_kinetic_final.
+int edmd_launch_shift_scale(edmd_ctx *c, double dvx, double dvy, double divisor, const double *red, bool div_from_red,
+                            int n_total, double *sums)
+{
+    const int n = c->n_owned;
+    if (n == 0) return 0;
+    cudaMemsetAsync(c->flags + kFlagVmax, 0, sizeof(int32_t), c->stream);
+    k_shift_scale<<<kBlocks, kThreads, 0, c->stream>>>(n, n_total, dvx, dvy, divisor, red, div_from_red ? 1 : 0, c->xv,
+                                                       c->flags, sums);
+    return 1;
+}
+
+// second half of edmd_launch_kinetic for sums accumulated elsewhere
+double *edmd_launch_kinetic_final(edmd_ctx *c, double T, double *scratch, int n_total)
+{
+    double *out = scratch + 3 * kBlocks;
+    k_kinetic_final<<<1, kThreads, 0, c->stream>>>(n_total, T, scratch, out);
     return out;
 }
 

@@ -39,6 +39,7 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "edmd_cuda.h"
 
@@ -71,7 +72,8 @@ static int32_t *pcell;                            /* interleaved X,Y */
 static unsigned long *pcoll;
 static int *ptype, *cnext, *cprev, *chead;
 static unsigned long ncol = 0, ncross = 0;
-static double collTermX = 0, collTermY = 0, lastThermoT = 0;
+static double collTermX = 0, collTermY = 0, collTermXY = 0, collTermYX = 0, lastThermoT = 0;
+static double Einit = 1;   /* the reference's --initial-energy / -E (src/EDMD.c:369, :847): E/N after normalizePhysicalQ */
 
 typedef struct node {
 	struct node *lft, *rgt, *top;
@@ -491,6 +493,8 @@ static void do_collision(node *ev)
 		double f = (dx * dvx + dy * dvy) / (4 * prad[i] * prad[j]);
 		collTermX += f * dx * dx;
 		collTermY += f * dy * dy;
+		collTermXY += f * dx * dy;   /* :3807-3813 */
+		collTermYX += f * dy * dx;
 		pvx[i] += f * dx; pvy[i] += f * dy;
 		pvx[j] -= f * dx; pvy[j] -= f * dy;
 	}
@@ -536,13 +540,18 @@ static void do_growstop(void)
 	for (int i = 0; i < N; i++) { free_fly(i); pcoll[i] = 0; }
 	ncol = ncross = 0;
 	growing = 0;
-	/* normalizePhysicalQ :5723-5764: remove the COM momentum, rescale to E/N = T */
-	double sx = 0, sy = 0;
-	for (int i = 0; i < N; i++) { sx += pvx[i]; sy += pvy[i]; }
-	for (int i = 0; i < N; i++) { pvx[i] -= sx / N; pvy[i] -= sy / N; }
-	double s = sqrt(kinetic_energy() / N / T);
-	for (int i = 0; i < N; i++) { pvx[i] /= s; pvy[i] /= s; pcoll[i]++; }
-	collTermX = collTermY = 0;
+	/* normalizePhysicalQ :5723-5764 on the device (edmd_cuda_normalize_velocities): the centre-of-mass
+	 * velocity removed, E/N set to Einit; the new velocities come back for the event loop.
+	 * (stopGrow re-inserts every particle's collision event before its crossing event, :4772-4778; the
+	 * sweep below inserts crossing first like the other three sites -- which of two events with EXACTLY
+	 * equal times pops first is the only thing that could differ.) */
+	gpu_upload();
+	int rc = edmd_cuda_normalize_velocities(gpu, Einit, NULL, NULL, NULL, NULL);
+	if (rc) die_gpu(rc, "edmd_cuda_normalize_velocities");
+	rc = edmd_cuda_download_state(gpu, NULL, NULL, pvx, pvy, NULL);
+	if (rc) die_gpu(rc, "edmd_cuda_download_state");
+	for (int i = 0; i < N; i++) pcoll[i]++;
+	collTermX = collTermY = collTermXY = collTermYX = 0;
 	lastThermoT = t;
 	gpu_predict_all(1);
 }
@@ -621,18 +630,54 @@ static void do_screenshot(void)
 
 static double last_pressure = 0;
 
+/* saveThermo, src/EDMD.c:5232-5609, for the reference's CLI build (Nthermo = 1: every call prints the
+ * interval since the last one): the columns and formats of :5407-5577 --
+ *   t Ncol E p px py pxy pyx [q6] a2
+ * virial pressure tensor :5299-5328, mean q6 :5521-5536 (on the device), Sonine coefficient :5377-5403. */
 static void do_thermo(void)
 {
 	schedule_special(3, EV_THERMO, t + dtimeThermo);
 	double E = kinetic_energy();
 	double area = Lx * Ly, dtm = t - lastThermoT;
-	/* virial pressure, src/EDMD.c:5324-5328 */
+	double eX = 0, eY = 0, eXY = 0, eYX = 0;
+	for (int i = 0; i < N; i++) {
+		eX += pvx[i] * pvx[i];
+		eY += pvy[i] * pvy[i];
+		eXY += pvx[i] * pvy[i];
+		eYX += pvy[i] * pvx[i];
+	}
+	double inv = dtm > 0 ? 1 / (area * dtm) : 0;
+	double pX = -1 * collTermX * inv + eX / area, pY = -1 * collTermY * inv + eY / area;
+	double pXY = -1 * collTermXY * inv + eXY / area, pYX = -1 * collTermYX * inv + eYX / area;
 	double p = dtm > 0 ? (-1 / dtm) * (collTermX + collTermY) / (2 * area) + E / area : E / area;
 	last_pressure = p;
-	collTermX = collTermY = 0;
+	collTermX = collTermY = collTermXY = collTermYX = 0;
 	lastThermoT = t;
-	fprintf(fthermo, "%lf %lu %.10lf %.10lf\n", t, ncol, E / N, p);
-	fflush(fthermo);
+	/* a2 = <dvx^4> / (3 <dvx^2>^2) - 1 */
+	double vav = 0, v2 = 0, v4 = 0;
+	for (int i = 0; i < N; i++) vav += pvx[i];
+	vav /= N;
+	for (int i = 0; i < N; i++) {
+		double d = pvx[i] - vav, d2 = d * d;
+		v2 += d2;
+		v4 += d2 * d2;
+	}
+	v2 /= N; v4 /= N;
+	double a2 = v2 > 0.0 ? v4 / (3.0 * v2 * v2) - 1.0 : 0.0;
+	if (t != 0) {
+		fprintf(fthermo, "%lf %ld %lf %lf %lf %lf %.10lf %.10lf ", t, (long)ncol, E / N, p, pX, pY, pXY, pYX);
+		if (boopThermo) { /* mean q6 of the current configuration, computeBOOPVoronoi / computeBOOPCutoff(2.5) */
+			for (int i = 0; i < N; i++) free_fly(i);
+			gpu_upload();
+			double q6 = 0;
+			int rc = boopThermo == 1 ? edmd_cuda_boop_voronoi(gpu, NULL, NULL, NULL, NULL, NULL, &q6)
+			                         : edmd_cuda_boop_cutoff(gpu, 2.5, NULL, NULL, NULL, NULL, NULL, &q6);
+			if (rc) die_gpu(rc, "edmd_cuda_boop (thermo)");
+			fprintf(fthermo, "%lf ", q6);
+		}
+		fprintf(fthermo, "%lf \n", a2);
+		fflush(fthermo);
+	}
 	if (pcfThermo) {
 		for (int i = 0; i < N; i++) free_fly(i);
 		gpu_upload();
@@ -750,8 +795,9 @@ static void particles_init(void)
 		}
 	}
 	for (int i = 0; i < N; i++) { pvx[i] -= sx / N; pvy[i] -= sy / N; }
-	/* growth runs at E/N = 0.05 (EinitGrow :1692); stopGrow rescales to T */
-	double s = sqrt(kinetic_energy() / N / (init_grow ? 0.05 : T));
+	/* growth runs at E/N = 0.05 (EinitGrow :1692); stopGrow's normalizePhysicalQ rescales to Einit.  A lattice
+	 * start has no stopGrow: it begins at the thermostat's temperature when there is one, else at Einit */
+	double s = sqrt(kinetic_energy() / N / (init_grow ? 0.05 : (noise ? T : Einit)));
 	for (int i = 0; i < N; i++) { pvx[i] /= s; pvy[i] /= s; }
 	growing = init_grow;
 }
@@ -772,9 +818,10 @@ int main(int argc, char **argv)
 		{"boop-voronoi", no_argument, NULL, 1011}, {"area", no_argument, NULL, 1012},
 		{"struc", required_argument, NULL, 1013}, {"qmax", required_argument, NULL, 1014},
 		{"pcfg6", no_argument, NULL, 1015}, {"gamma", required_argument, NULL, 1016},
+		{"initial-energy", required_argument, NULL, 'E'},
 		{NULL, 0, NULL, 0}};
 	int c, device = 0;
-	while ((c = getopt_long(argc, argv, "N:p:x:q:a:t:D:o:T:v:", longopt, NULL)) != -1) {
+	while ((c = getopt_long(argc, argv, "N:p:x:q:a:t:D:o:T:v:E:", longopt, NULL)) != -1) {
 		switch (c) {
 		case 'N': N = atoi(optarg); break;
 		case 'p': phi = atof(optarg); break;
@@ -786,6 +833,7 @@ int main(int argc, char **argv)
 		case 'o': dtimeThermo = atof(optarg); break;
 		case 'T': T = atof(optarg); break;
 		case 'v': seed = atoi(optarg); break;
+		case 'E': Einit = atof(optarg); break;
 		case 1001: noise = atoi(optarg); break;
 		case 1002: dtnoise = atof(optarg); break;
 		case 1003: boopThermo = 2; break;
@@ -802,7 +850,7 @@ int main(int argc, char **argv)
 		case 1014: qmax = atof(optarg); break;
 		case 1015: pcfg6Thermo = 1; break;
 		case 1016: gamm = atof(optarg); break;
-		default: fprintf(stderr, "usage: edmd_host -N n --phi f [-x xs -q ratio -a aspect -t tmax -D dt -o dtThermo -T temp -v seed]\n"
+		default: fprintf(stderr, "usage: edmd_host -N n --phi f [-x xs -q ratio -a aspect -t tmax -D dt -o dtThermo -T temp -v seed -E Einit]\n"
 		                         "       [--init grow|lattice] [--ingest bulk|seq] [--noise 1|2 --dtnoise dt --gamma g] [--boop | --boop-voronoi] [--area] [--pcf] [--pcfg6] [--struc mode --qmax q] [--verify] [--outdir dir] [--quiet]\n");
 			return 2;
 		}
@@ -838,13 +886,29 @@ int main(int argc, char **argv)
 	g_bucket = pinned(sizeof(int32_t) * 2 * N); g_next = pinned(sizeof(int32_t) * 2 * N);
 	g_prev = pinned(sizeof(int32_t) * 2 * N); g_head = pinned(sizeof(int32_t) * ((size_t)paulN + 1));
 
+	/* customName, src/EDMD.c:6015-6116: the reference's file names (under --outdir instead of dump/),
+	 * the first version number that does not exist yet */
 	mkdir(outdir, 0777);
-	char name[512];
-	snprintf(name, sizeof name, "%s/N_%dphi_%.4f.dump", outdir, N, phi); fdump = fopen(name, "w");
-	snprintf(name, sizeof name, "%s/N_%dphi_%.4f.thermo", outdir, N, phi); fthermo = fopen(name, "w");
-	if (pcfThermo) { snprintf(name, sizeof name, "%s/N_%dphi_%.4f.pcf", outdir, N, phi); fpcf = fopen(name, "w"); }
+	char name[768], base[512];
+	{
+		int nsmall = 0;
+		for (int i = 0; i < N; i++) nsmall += ptype[i] == 0;
+		int len = snprintf(base, sizeof base, "%s/N_%dres_%.3lfphi_%.6lfq_%.3lfrat_%.3lfLx_%.3lfLy_%.3lf", outdir, N, 1.0,
+		                   phi, (double)nsmall / N, sizeratio, Lx, Ly);
+		if (noise) len += snprintf(base + len, sizeof base - len, "gamma_%.8lfT_%.3lfdt_%.3lf", gamm, T, dtnoise);
+		len += snprintf(base + len, sizeof base - len, "v_");
+		int version = 0;
+		for (;; version++) {
+			snprintf(name, sizeof name, "%s%d.dump", base, version);
+			if (access(name, F_OK) != 0) break;
+		}
+		snprintf(base + len, sizeof base - len, "%d", version);
+	}
+	snprintf(name, sizeof name, "%s.dump", base); fdump = fopen(name, "w");
+	snprintf(name, sizeof name, "%s.thermo", base); fthermo = fopen(name, "w");
+	if (pcfThermo) { snprintf(name, sizeof name, "%s.pcf", base); fpcf = fopen(name, "w"); }
 	if (strucThermo) {
-		snprintf(name, sizeof name, "%s/N_%dphi_%.4f.struc", outdir, N, phi); fstruc = fopen(name, "w");
+		snprintf(name, sizeof name, "%s.struc", base); fstruc = fopen(name, "w");
 		if (fstruc) { /* header of initStructureFactor, src/struc.c:347-355 */
 			int nqx = 0, nqy = 0;
 			edmd_cuda_structure_factor(gpu, qmax, 0, &nqx, &nqy, NULL, NULL, NULL, NULL, NULL);
@@ -858,9 +922,9 @@ int main(int argc, char **argv)
 			free(qx); free(qy);
 		}
 	}
-	if (pcfg6Thermo) { snprintf(pcfg6Name, sizeof pcfg6Name, "%s/N_%dphi_%.4f.pcfg6", outdir, N, phi); remove(pcfg6Name); }
+	if (pcfg6Thermo) { snprintf(pcfg6Name, sizeof pcfg6Name, "%s.pcfg6", base); remove(pcfg6Name); }
 	if (!fdump || !fthermo || (pcfThermo && !fpcf) || (strucThermo && !fstruc)) { perror("edmd_host: output files"); return 1; }
-	fprintf(fthermo, "t Ncol E p\n");
+	fprintf(fthermo, "t Ncol E p px py pxy pyx %sa2 \n", boopThermo ? "q6 " : "");   /* header, src/EDMD.c:1229-1285 */
 
 	if (!quiet)
 		printf("edmd_host: N = %d  phi = %g  Lx = %.3f  Ly = %.3f  cells = %d x %d  noise = %d\n", N, phi, Lx, Ly, Nx, Ny, noise);

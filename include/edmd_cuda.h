@@ -343,6 +343,21 @@ int edmd_cuda_rescale_velocities(edmd_ctx *ctx, double T, double *E_before, doub
 int edmd_cuda_langevin_kick(edmd_ctx *ctx, double T, double gamma, double dtnoise, uint32_t seed,
                             uint32_t tick);
 
+/* Replaces normalizePhysicalQ (src/EDMD.c:5723-5764, the branch without a circular wall, unit masses;
+ * callers: the initial conditions :1556 and stopGrow :4745) on the RESIDENT state:
+ *   physicalQ();  v -= p/(N*m);  physicalQ();  v /= sqrt(E/N/Einit)
+ * -- the centre-of-mass velocity removed, the kinetic energy per particle set to Einit (the reference's
+ * option of that name, default 1).  The parallel sums agree with the reference's sequential ones to
+ * ~1e-15 relative (inside the 1e-12 bar; reproducible run to run).  Outputs (nullable): the momentum
+ * before, the energy of the shifted velocities, the divisor sqrt(E/N/Einit).  Whole-system contexts. */
+int edmd_cuda_normalize_velocities(edmd_ctx *ctx, double Einit, double *px_before, double *py_before,
+                                   double *E_shifted, double *divisor);
+
+/* v <- (v - (dvx, dvy)) / divisor on the particles the context owns: the two loops of normalizePhysicalQ
+ * / the rescale of addNoise (:4899-4902) with sums the CALLER supplies.  For slab contexts: all-reduce
+ * edmd_cuda_kinetic's (E, px, py) over the ranks, then call this with the whole system's values. */
+int edmd_cuda_shift_scale_velocities(edmd_ctx *ctx, double dvx, double dvy, double divisor);
+
 /* ---- per-frame structure analysis ----------------------------------- */
 
 /* Replaces calculate_pcf (src/pcf.c:16-75; caller save_pcf, src/EDMD.c:

@@ -159,6 +159,20 @@ class Oracle:
         out.update(x=ff["x"], y=ff["y"], vx=vx2, vy=vy2, E_before=E, divisor=float(s))
         return out
 
+    @staticmethod
+    def normalize(vx, vy, e_init=1.0):
+        """normalizePhysicalQ (src/EDMD.c:5723-5764, no circular wall, unit masses): physicalQ's
+        sequential sums, `v -= p/(N*m)`, physicalQ again, `v /= sqrt(E/N/Einit)`."""
+        vx, vy = _f64(vx).copy(), _f64(vy).copy()
+        n = len(vx)
+        px = float(np.cumsum(vx)[-1])            # left-to-right, like the loop
+        py = float(np.cumsum(vy)[-1])
+        vx -= px / (n * 1.0)
+        vy -= py / (n * 1.0)
+        E = float(np.cumsum(0.5 * 1.0 * (vx * vx + vy * vy))[-1])
+        s = np.sqrt(E / n / e_init)
+        return dict(vx=vx / s, vy=vy / s, px_before=px, py_before=py, E_shifted=E, divisor=float(s))
+
     def g6_correlation(self, n, lx, ly, x, y, psi_re, psi_im, dr, max_r):
         """Pair loop of compute_g6_correlation (src/pcf.c:189-228) for a given psi6."""
         b = self.box(n, lx, ly)
@@ -356,6 +370,15 @@ class Reference:
         self.lib.ref_bragg_peak.restype = C.c_double
         sec = self.lib.ref_bragg_peak(C.c_double(expected_bragg), _p(k))
         return dict(k=k, seconds=sec)
+
+    def normalize(self, e_init):
+        """normalizePhysicalQ() of the loaded system."""
+        n = self.n
+        vx, vy = np.empty(n, np.float64), np.empty(n, np.float64)
+        px, py, e = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
+        self.lib.ref_normalize.restype = None
+        self.lib.ref_normalize(C.c_double(e_init), _p(vx), _p(vy), C.byref(px), C.byref(py), C.byref(e))
+        return dict(vx=vx, vy=vy, px_before=px.value, py_before=py.value, E_shifted=e.value)
 
     def tick_rescale(self, t_new, T):
         """physicalQ + addNoise (velocity-rescale branch) at time t_new."""

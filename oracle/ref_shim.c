@@ -491,6 +491,26 @@ double ref_structure_factor(double q_max, int velocity, int *nqx_out, int *nqy_o
 	return t1 - t0;
 }
 
+/* normalizePhysicalQ() (src/EDMD.c:5723-5764) on the loaded system with the reference's option
+ * Einit: centre-of-mass velocity removed, E/N set to Einit.  Outputs the new velocities and the
+ * reference's globals px, py (before) and E (of the shifted velocities, as its second physicalQ left it). */
+void ref_normalize(double e_init, double *vx, double *vy, double *px_before, double *py_before, double *E_shifted)
+{
+	Einit = e_init;
+	physicalQ();
+	if (px_before)
+		*px_before = px;
+	if (py_before)
+		*py_before = py;
+	normalizePhysicalQ();
+	if (E_shifted)
+		*E_shifted = E;
+	for (int i = 0; i < N; i++) {
+		vx[i] = particles[i].vx;
+		vy[i] = particles[i].vy;
+	}
+}
+
 /* A real thermostat tick with the velocity-rescale branch at time t_new:
  * physicalQ() (src/EDMD.c:5968-5997) for E, then addNoise() (:4828-4923): every
  * particle is free-flown to t_new, its velocity divided by sqrt(E/N/T), and the

@@ -173,4 +173,19 @@ if want("tick"):
     tick_case("tick_n2000_phi060", pkg.synth.lattice_config(2000, 0.60, seed=10), 1.25, 1.2625, 0.7)
     tick_case("tick_n1500_phi045_bidisperse",
               pkg.synth.lattice_config(1500, 0.45, seed=11, small_fraction=0.3), 0.0, 0.03125, 1.6)
+def normalize_case(name, cfg, drift, e_init):
+    """normalizePhysicalQ (stopGrow / the initial conditions): a system with a centre-of-mass drift."""
+    n = cfg["n"]
+    vx, vy = cfg["vx"] + drift[0], cfg["vy"] + drift[1]
+    ref.setup(n, cfg["lx"], cfg["ly"], 0.0, cfg["x"], cfg["y"], vx, vy, cfg["rad"])
+    k = ref.normalize(e_init)
+    np.savez_compressed(HERE / f"{name}.npz", n=n, lx=cfg["lx"], ly=cfg["ly"], x=cfg["x"], y=cfg["y"], vx=vx, vy=vy,
+                        rad=cfg["rad"], e_init=e_init, norm_vx=k["vx"], norm_vy=k["vy"], px_before=k["px_before"],
+                        py_before=k["py_before"], E_shifted=k["E_shifted"])
+    print("wrote", name, "n =", n, "p/N before", k["px_before"] / n, k["py_before"] / n)
+
+
+if want("normalize"):
+    normalize_case("normalize_n2000_phi060", pkg.synth.lattice_config(2000, 0.60, seed=12), (0.37, -0.21), 1.0)
+    normalize_case("normalize_n1500_einit", pkg.synth.lattice_config(1500, 0.45, seed=13), (-1.5, 0.02), 2.5)
 ref.teardown()

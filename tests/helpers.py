@@ -89,6 +89,7 @@ def random_points(n, lx, ly, seed, jitter=None):
 
 
 TICK_CASES = ["tick_n2000_phi060", "tick_n1500_phi045_bidisperse"]
+NORMALIZE_CASES = ["normalize_n2000_phi060", "normalize_n1500_einit"]
 TICK_RTOL = 1e-12   # the kinetic-energy sum is order dependent: rescaled velocities and event times to 1e-12
 
 

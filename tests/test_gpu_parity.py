@@ -790,7 +790,7 @@ def test_normal_sweep_after_growth_free_flight(pkg, oracle):
                                                   (200000, 0.70, 243, 0.3, 1.0), (50000, 0.40, 244, 0.0, 300.0),
                                                   (2700, 0.70, 245, 0.3, 1.0), (1000000, 0.70, 246, 0.0, 1.0)])
 def test_tile_sweep_equals_lean_chain_and_full_path(pkg, n, phi, seed, sf, vscale):
-    """The two-kernel tile sweep (tile_sweep.cu), the five-kernel lean chain and the full
+    """The two-kernel cell-slot sweep (cell_sweep.cu), the five-kernel lean chain and the full
     FP64 path produce the same bits (one and two radius classes, tiles narrower than a
     full tile at the grid edge, grids of a single tile)."""
     c = pkg.synth.lattice_config(n, phi, seed, small_fraction=sf, shuffle=True)
@@ -1243,3 +1243,50 @@ def test_slab_decomposition_on_one_gpu_matches_oracle(pkg, oracle, n, phi, seed,
     finally:
         for sr in ranks:
             sr.close()
+
+
+from helpers import GOLDEN, NORMALIZE_CASES  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NORMALIZE_CASES)
+def test_device_normalize_matches_reference_golden(pkg, name):
+    """edmd_cuda_normalize_velocities against the reference's normalizePhysicalQ (src/EDMD.c:5723-5764):
+    velocities within 1e-12 (parallel sums), the sweep on the normalised resident state follows."""
+    g = np.load(GOLDEN / f"{name}.npz")
+    n = int(g["n"])
+    with pkg.EdmdCuda(n, float(g["lx"]), float(g["ly"])) as ctx:
+        ctx.upload(g["x"], g["y"], g["vx"], g["vy"], g["rad"], t=0.0)
+        info = ctx.normalize_velocities(float(g["e_init"]))
+        st = ctx.download_state()
+    for k in ("vx", "vy"):
+        w = g["norm_" + k]
+        assert (np.abs(st[k] - w) <= TICK_RTOL * np.abs(w).max()).all(), k
+    assert abs(info["px_before"] - float(g["px_before"])) <= 1e-12 * abs(float(g["px_before"]))
+    assert abs(info["E_shifted"] - float(g["E_shifted"])) <= 1e-12 * float(g["E_shifted"])
+
+
+@pytest.mark.gpu
+def test_device_normalize_then_sweep_matches_oracle(pkg, oracle):
+    """stopGrow's order on the device: normalise the resident velocities, re-predict -- against the oracle's
+    restatement of both at N = 10^5; shift_scale with caller-supplied sums (the slab form) gives the same state."""
+    c = pkg.synth.lattice_config(100000, 0.70, seed=31, shuffle=True)
+    vx, vy = c["vx"] + 0.25, c["vy"] - 0.4
+    want = oracle.normalize(vx, vy, 1.3)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], vx, vy, c["rad"], t=0.0)
+        ctx.normalize_velocities(1.3)
+        st = ctx.download_state()
+        got = ctx.predict_all()
+        # the slab form: the caller's sums
+        ctx.upload(c["x"], c["y"], vx, vy, c["rad"], t=0.0)
+        E, px, py = ctx.kinetic()
+        ctx.shift_scale_velocities(px / c["n"], py / c["n"], 1.0)
+        E2, _, _ = ctx.kinetic()
+        ctx.shift_scale_velocities(0.0, 0.0, np.sqrt(E2 / c["n"] / 1.3))
+        st2 = ctx.download_state()
+    for k in ("vx", "vy"):
+        assert (np.abs(st[k] - want[k]) <= TICK_RTOL * np.abs(want[k]).max()).all(), k
+        assert (np.abs(st2[k] - want[k]) <= TICK_RTOL * np.abs(want[k]).max()).all(), k
+    ref = oracle.predict_all(c["n"], c["lx"], c["ly"], 0.0, c["x"], c["y"], st["vx"], st["vy"], c["rad"])
+    assert_events_equal(got, ref)

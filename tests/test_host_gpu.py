@@ -127,3 +127,36 @@ def test_host_langevin_thermostat_reaches_the_bath_temperature(tmp_path):
     assert abs(late.mean() - 0.4) < 0.03, late.mean()   # 1/sqrt(N) = 1.8 % per sample
     m = re.search(r"(\d+) collisions", out)
     assert m and int(m.group(1)) > 50000
+
+
+def test_host_writes_the_reference_thermo_columns_and_file_names(tmp_path):
+    """saveThermo's record (src/EDMD.c:1229-1285 header, :5407-5577 line) and customName's file names
+    (:6015-6116): `t Ncol E p px py pxy pyx q6 a2`, the pressure tensor's trace consistent with p,
+    the mean q6 column from the device, versioned names that do not overwrite an earlier run."""
+    args = ("-N", 1500, "--phi", 0.6, "-x", 0, "-t", 20, "-D", 1000, "-o", 2, "--quiet", "--init", "lattice", "--boop")
+    run_host(tmp_path, *args)
+    run_host(tmp_path, *args)
+    names = sorted(p.name for p in tmp_path.glob("*.thermo"))
+    assert len(names) == 2 and names[0].endswith("v_0.thermo") and names[1].endswith("v_1.thermo"), names
+    assert re.match(r"N_1482res_1\.000phi_0\.600000q_0\.000rat_0\.400Lx_\d+\.\d{3}Ly_\d+\.\d{3}v_0\.thermo", names[0]), names[0]
+    lines = (tmp_path / names[0]).read_text().splitlines()
+    assert lines[0] == "t Ncol E p px py pxy pyx q6 a2 "
+    th = np.loadtxt(tmp_path / names[0], skiprows=1)
+    assert th.shape[1] == 10
+    t, ncol, e, p, pxx, pyy, pxy, pyx, q6, a2 = th.T
+    assert (np.diff(ncol) > 0).all() and np.abs(e - 1.0).max() < 1e-6     # `%lf`: six decimals
+    assert np.abs(0.5 * (pxx + pyy) - p).max() < 2e-6                      # p = (px + py)/2 (:5324-5328)
+    assert np.abs(pxy - pyx).max() < 1e-9 and np.abs(pxy).max() < 0.2 * p.mean()
+    assert ((q6 > 0.2) & (q6 < 1.0)).all()                                 # a phi = 0.6 fluid: local sixfold order ~0.4-0.5
+    assert np.abs(a2).max() < 0.2                                          # Maxwellian: a2 ~ 0 +- 1/sqrt(N)
+    # two identical runs are the same trajectory
+    assert (tmp_path / names[0]).read_bytes() == (tmp_path / names[1]).read_bytes()
+
+
+def test_host_growth_stop_normalises_on_the_device(tmp_path):
+    """stopGrow's normalizePhysicalQ runs on the device (edmd_cuda_normalize_velocities) with the
+    reference's --initial-energy: after the growth phase E/N = Einit and stays (no thermostat)."""
+    out = run_host(tmp_path, "-N", 1500, "--phi", 0.6, "-x", 0, "-t", 12, "-D", 1000, "-o", 2, "--quiet", "-E", 1.7)
+    th = np.loadtxt(next(tmp_path.glob("*.thermo")), skiprows=1)
+    assert len(th) >= 4 and np.abs(th[:, 2] - 1.7).max() < 2e-6
+    assert re.search(r"E/N = 1\.70000", out), out

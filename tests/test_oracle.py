@@ -209,3 +209,23 @@ def test_reference_grown_liquid_fixture_and_its_tiling(pkg, oracle):
     pb = oracle.pcf(n0, lx, ly, base["x"], base["y"], 0.1, 8.0)
     pt = oracle.pcf(c["n"], c["lx"], c["ly"], c["x"], c["y"], 0.1, 8.0)
     assert np.array_equal(pt["counts"], 4 * pb["counts"])
+
+
+from helpers import GOLDEN, NORMALIZE_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", NORMALIZE_CASES)
+def test_oracle_normalize_matches_golden(oracle, name):
+    """normalizePhysicalQ (src/EDMD.c:5723-5764): the numpy restatement against the reference's own run
+    (sequential sums in both: bit-exact but for the -ffast-math build's reassociation, <= 1e-15)."""
+    g = np.load(GOLDEN / f"{name}.npz")
+    got = oracle.normalize(g["vx"], g["vy"], float(g["e_init"]))
+    for k in ("vx", "vy"):
+        w = g["norm_" + k]
+        assert (np.abs(got[k] - w) <= 1e-14 * np.abs(w).max()).all(), k
+    assert abs(got["px_before"] - float(g["px_before"])) <= 1e-12 * abs(float(g["px_before"]))
+    assert abs(got["E_shifted"] - float(g["E_shifted"])) <= 1e-13 * float(g["E_shifted"])
+    # what the routine is for: no centre-of-mass motion, E/N = Einit
+    assert abs(got["vx"].sum()) < 1e-9 and abs(got["vy"].sum()) < 1e-9
+    e = 0.5 * (got["vx"] ** 2 + got["vy"] ** 2).sum() / len(got["vx"])
+    assert abs(e - float(g["e_init"])) < 1e-12 * float(g["e_init"])

@@ -14,7 +14,7 @@ TILE_ROWS ?= 8
 NVCCFLAGS  = -DEDMD_TILE_ROWS=$(TILE_ROWS) $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Iinclude -I$(CSRC) \
              -Xcompiler -fPIC,-Wall,-Wno-unused-function
 CU_SRCS    = $(CSRC)/edmd_cuda.cu $(CSRC)/cell_index.cu $(CSRC)/predict.cu $(CSRC)/analysis.cu $(CSRC)/halo.cu \
-             $(CSRC)/lean_index.cu $(CSRC)/predict_lean.cu $(CSRC)/cell_sweep.cu $(CSRC)/calendar.cu $(CSRC)/analysis_weighted.cu $(CSRC)/analysis_pcf_sorted.cu $(CSRC)/analysis_voronoi.cu $(CSRC)/thermostat.cu
+             $(CSRC)/lean_index.cu $(CSRC)/predict_lean.cu $(CSRC)/cell_sweep.cu $(CSRC)/calendar.cu $(CSRC)/analysis_weighted.cu $(CSRC)/analysis_pcf_sorted.cu $(CSRC)/analysis_voronoi.cu $(CSRC)/thermostat.cu $(CSRC)/multi_gpu.cu
 CU_OBJS    = $(CU_SRCS:.cu=.o)
 LIB        = $(PKG)/libedmd_cuda.so
 

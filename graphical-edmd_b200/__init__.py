@@ -10,4 +10,4 @@ The directory name contains a hyphen, so it is loaded by path -- see
 ``__graft_entry__.load_package()``.
 """
 from . import binding, slab, synth  # noqa: F401
-from .binding import EdmdCuda, EdmdError, load_library  # noqa: F401
+from .binding import EdmdCuda, EdmdError, EdmdMg, load_library  # noqa: F401

@@ -53,6 +53,9 @@ SYMBOLS = [
     "edmd_cuda_structure_factor", "edmd_cuda_kinetic", "edmd_cuda_rescale_velocities",
     "edmd_cuda_selftest_rsqrt", "edmd_cuda_langevin_kick",
     "edmd_cuda_normalize_velocities", "edmd_cuda_shift_scale_velocities",
+    "edmd_cuda_create_mg", "edmd_cuda_destroy_mg", "edmd_cuda_mg_last_error", "edmd_cuda_mg_get_box",
+    "edmd_cuda_mg_slab_sizes", "edmd_cuda_mg_upload", "edmd_cuda_mg_predict_all", "edmd_cuda_mg_boop_cutoff",
+    "edmd_cuda_mg_pcf",
 ]
 EVORONOI = 7
 HALO_RECORD_BYTES = 48
@@ -131,6 +134,17 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.edmd_cuda_selftest_rsqrt.argtypes = [vp, C.POINTER(C.c_double)]
     lib.edmd_cuda_langevin_kick.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32]
     lib.edmd_cuda_kinetic.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.edmd_cuda_create_mg.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
+    lib.edmd_cuda_destroy_mg.argtypes = [vp]
+    lib.edmd_cuda_destroy_mg.restype = None
+    lib.edmd_cuda_mg_last_error.argtypes = [vp]
+    lib.edmd_cuda_mg_last_error.restype = C.c_char_p
+    lib.edmd_cuda_mg_get_box.argtypes = [vp, C.POINTER(Box)]
+    lib.edmd_cuda_mg_slab_sizes.argtypes = [vp, C.POINTER(C.c_int)]
+    lib.edmd_cuda_mg_upload.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_double]
+    lib.edmd_cuda_mg_predict_all.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.edmd_cuda_mg_boop_cutoff.argtypes = [vp, C.c_double, vp, vp, vp, vp, vp, C.POINTER(C.c_double)]
+    lib.edmd_cuda_mg_pcf.argtypes = [vp, vp, vp, C.c_double, C.c_double, vp, vp, C.POINTER(C.c_int)]
     lib.edmd_cuda_normalize_velocities.argtypes = [vp, C.c_double] + [C.POINTER(C.c_double)] * 4
     lib.edmd_cuda_shift_scale_velocities.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     lib.edmd_cuda_rescale_velocities.argtypes = [vp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -465,3 +479,82 @@ class EdmdCuda:
         self._check(self.lib.edmd_cuda_bench(self._h, what, mode, dr, max_r, warmup, iters,
                                              flush_bytes, _ptr(tot), _ptr(main) if split else None))
         return tot, main
+
+
+class EdmdMg:
+    """Several GPUs in one process behind the single-GPU interface (edmd_cuda_create_mg): whole-system
+    host arrays in and out; `devices` may list one device several times (several slabs on one GPU)."""
+
+    def __init__(self, n: int, lx: float, ly: float, devices=(0,)):
+        self.lib = load_library()
+        self.n = int(n)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.edmd_cuda_create_mg(len(devices), devs, self.n, lx, ly, C.byref(h))
+        self._h = h if rc == 0 else None
+        self.ndev = len(devices)
+        if rc != 0:
+            raise EdmdError(rc, "edmd_cuda_create_mg failed")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.edmd_cuda_destroy_mg(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, allow=()):
+        if rc != 0 and rc not in allow:
+            raise EdmdError(rc, self.lib.edmd_cuda_mg_last_error(self._h).decode())
+        return rc
+
+    @property
+    def slab_sizes(self):
+        out = (C.c_int * self.ndev)()
+        self._check(self.lib.edmd_cuda_mg_slab_sizes(self._h, out))
+        return list(out)
+
+    def upload(self, x, y, vx, vy, rad, cell_xy=None, t=0.0):
+        n = self.n
+        a = [_f64(v, n) for v in (x, y, vx, vy, rad)]
+        cells = None if cell_xy is None else np.ascontiguousarray(cell_xy, dtype=np.int32)
+        self._check(self.lib.edmd_cuda_mg_upload(self._h, *[_ptr(v) for v in a], _ptr(cells), float(t)))
+
+    def predict_all(self, mode=MODE_NORMAL, allow_overlap=False):
+        n = self.n
+        tc, tl = np.empty(n, np.float64), np.empty(n, np.float64)
+        d, ct = np.empty(n, np.uint8), np.empty(n, np.uint8)
+        p, ov = np.empty(n, np.int32), np.full(2, -7, np.int32)
+        rc = self._check(self.lib.edmd_cuda_mg_predict_all(self._h, mode, _ptr(tc), _ptr(d), _ptr(tl), _ptr(p),
+                                                           _ptr(ct), _ptr(ov)),
+                         allow=(EOVERLAP,) if allow_overlap else ())
+        return dict(t_cross=tc, dir=d, t_coll=tl, partner=p, ctype=ct, overlap=ov, rc=rc)
+
+    def boop_cutoff(self, r_c=2.5):
+        n = self.n
+        q5, q6, q7, arg = (np.empty(n, np.float64) for _ in range(4))
+        nb = np.empty(n, np.int32)
+        mean = C.c_double(0.0)
+        self._check(self.lib.edmd_cuda_mg_boop_cutoff(self._h, r_c, _ptr(q5), _ptr(q6), _ptr(q7), _ptr(arg), _ptr(nb),
+                                                      C.byref(mean)))
+        return dict(q5=q5, q6=q6, q7=q7, q6_arg=arg, neighbors=nb, mean_q6=mean.value)
+
+    def pcf(self, x, y, dr, max_r):
+        nb = C.c_int(0)
+        self._check(self.lib.edmd_cuda_mg_pcf(self._h, None, None, dr, max_r, None, None, C.byref(nb)))
+        counts = np.zeros(max(nb.value, 1), np.uint64)
+        g = np.zeros(max(nb.value, 1), np.float64)
+        xa, ya = _f64(x, self.n), _f64(y, self.n)
+        self._check(self.lib.edmd_cuda_mg_pcf(self._h, _ptr(xa), _ptr(ya), dr, max_r, _ptr(counts), _ptr(g),
+                                              C.byref(nb)))
+        return dict(counts=counts[:nb.value], g_r=g[:nb.value], num_bins=nb.value)

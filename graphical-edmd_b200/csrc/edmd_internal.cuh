@@ -311,6 +311,7 @@ int edmd_launch_halo_pack(edmd_ctx *c, int side, void *out, int cap, int32_t *co
 int edmd_launch_halo_append_row(edmd_ctx *c, const void *in, int count, int row);
 size_t edmd_halo_mem_bytes(int halo_cap);
 int edmd_launch_halo_p2p(edmd_ctx *c);
+int edmd_halo_connect_direct(edmd_ctx *c, edmd_ctx *lower, edmd_ctx *upper);
 int edmd_launch_halo_send(edmd_ctx *c, bool chained);
 int edmd_launch_halo_recv(edmd_ctx *c);
 int edmd_launch_halo_recv_partition(edmd_ctx *c);

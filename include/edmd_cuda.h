@@ -246,6 +246,35 @@ int edmd_cuda_get_counts(const edmd_ctx *ctx, int *n_owned, int *n_total);
 int edmd_cuda_pcf_device(edmd_ctx *ctx, const double *xy_dev, int n_total, double dr, double max_r,
                          int part, int nparts, uint64_t *counts_dev, int *num_bins);
 
+/* ---- several GPUs in ONE process (csrc/multi_gpu.cu) -------------------------------------
+ * The single-GPU interface over `ndev` devices: an edmd_mg owns one slab context per device
+ * (row slabs as above, halo by peer stores over NVLink -- peer access between the devices of the
+ * process, no IPC) and takes / returns WHOLE-SYSTEM host arrays indexed by particle id.  The same
+ * device may be listed more than once (several slabs on one GPU: how the tests run without a second
+ * GPU).  Needs Nycells >= 3 * ndev.  One host thread per edmd_mg, like an edmd_ctx. */
+typedef struct edmd_mg edmd_mg;
+int edmd_cuda_create_mg(int ndev, const int *devices, int n, double lx, double ly, edmd_mg **out);
+void edmd_cuda_destroy_mg(edmd_mg *mg);
+const char *edmd_cuda_mg_last_error(const edmd_mg *mg);
+int edmd_cuda_mg_get_box(const edmd_mg *mg, edmd_box *box);
+/* particles currently owned by every slab, n_owned[ndev] */
+int edmd_cuda_mg_slab_sizes(const edmd_mg *mg, int *n_owned);
+/* As edmd_cuda_upload (cell_xy nullable): the particles are dealt to the slabs by the cell row they
+ * are filed under -- particles migrate between slabs during a run, so every upload carries radii and ids. */
+int edmd_cuda_mg_upload(edmd_mg *mg, const double *x, const double *y, const double *vx, const double *vy,
+                        const double *rad, const int32_t *cell_xy, double t);
+/* As edmd_cuda_predict_all, mode EDMD_MODE_NORMAL: every slab runs the fused halo exchange + sweep, all
+ * devices side by side; the slabs' outputs are disjoint (no collective) and land in the caller's arrays. */
+int edmd_cuda_mg_predict_all(edmd_mg *mg, int mode, double *t_cross, uint8_t *dir, double *t_coll,
+                             int32_t *partner, uint8_t *ctype, int32_t *overlap_pair);
+/* As edmd_cuda_boop_cutoff; mean_q6 = (sum of the slabs' q6 sums) / N, the thermo column (src/EDMD.c:5521-5536). */
+int edmd_cuda_mg_boop_cutoff(edmd_mg *mg, double r_c, double *q5, double *q6, double *q7, double *q6_arg,
+                             int32_t *neighbors, double *mean_q6);
+/* As edmd_cuda_pcf on the positions given (all pairs interact: slabs do not help): every device gets the
+ * positions and bins the tile pairs w = k (mod ndev); the integer histograms are added. */
+int edmd_cuda_mg_pcf(edmd_mg *mg, const double *x, const double *y, double dr, double max_r, uint64_t *counts,
+                     double *g_r, int *num_bins);
+
 /* ---- weighted g(r) family -------------------------------------------------- */
 
 /* Replaces calculate_bond_order_pcf (src/pcf.c:77-167; caller save_pcf_boop

@@ -1280,13 +1280,50 @@ def test_device_normalize_then_sweep_matches_oracle(pkg, oracle):
         got = ctx.predict_all()
         # the slab form: the caller's sums
         ctx.upload(c["x"], c["y"], vx, vy, c["rad"], t=0.0)
-        E, px, py = ctx.kinetic()
-        ctx.shift_scale_velocities(px / c["n"], py / c["n"], 1.0)
-        E2, _, _ = ctx.kinetic()
-        ctx.shift_scale_velocities(0.0, 0.0, np.sqrt(E2 / c["n"] / 1.3))
+        k1 = ctx.kinetic()
+        ctx.shift_scale_velocities(k1["px"] / c["n"], k1["py"] / c["n"], 1.0)
+        k2 = ctx.kinetic()
+        ctx.shift_scale_velocities(0.0, 0.0, np.sqrt(k2["E"] / c["n"] / 1.3))
         st2 = ctx.download_state()
     for k in ("vx", "vy"):
         assert (np.abs(st[k] - want[k]) <= TICK_RTOL * np.abs(want[k]).max()).all(), k
         assert (np.abs(st2[k] - want[k]) <= TICK_RTOL * np.abs(want[k]).max()).all(), k
     ref = oracle.predict_all(c["n"], c["lx"], c["ly"], 0.0, c["x"], c["y"], st["vx"], st["vy"], c["rad"])
     assert_events_equal(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nslabs,n,phi,sf", [(2, 60000, 0.70, 0.0), (3, 150000, 0.72, 0.0), (4, 1000000, 0.70, 0.0),
+                                             (2, 40000, 0.55, 0.3)])
+def test_multi_gpu_c_entry_matches_oracle(pkg, oracle, nslabs, n, phi, sf):
+    """edmd_cuda_create_mg (csrc/multi_gpu.cu): the single-GPU interface over several slab contexts --
+    here several slabs on ONE device, the halo by direct stores between them: sweep bit-exact against the
+    whole-system oracle, psi6 and its mean within 1e-10, g(r) counts exact.  Two ticks: particles that
+    changed rows are dealt to another slab by the second upload."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devices = [k % ndev for k in range(nslabs)]
+    c = pkg.synth.lattice_config(n, phi, seed=41, small_fraction=sf, shuffle=True)
+    with pkg.EdmdMg(c["n"], c["lx"], c["ly"], devices) as mg:
+        mg.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        assert sum(mg.slab_sizes) == c["n"] and min(mg.slab_sizes) > 0
+        got = mg.predict_all()
+        assert_events_equal(got, oracle_sweep(oracle, c, t=0.0))
+        b = mg.boop_cutoff(2.5)
+        want_b = oracle.boop_cutoff(c["n"], c["lx"], c["ly"], c["x"], c["y"], 2.5)
+        assert_boop_close(b, want_b)
+        assert abs(b["mean_q6"] - want_b["q6"].mean()) < 1e-10
+        if c["n"] <= 200000:
+            g = mg.pcf(c["x"], c["y"], 0.1, 12.0)
+            want_g = oracle.pcf(c["n"], c["lx"], c["ly"], c["x"], c["y"], 0.1, 12.0)
+            assert np.array_equal(g["counts"], want_g["counts"])
+            assert np.abs(g["g_r"] - want_g["g_r"]).max() <= 1e-12 * want_g["g_r"].max()
+        # second tick: free flight on the host, new cells
+        dt = 0.05
+        c2 = dict(c)
+        c2["x"] = np.mod(c["x"] + dt * c["vx"], c["lx"])
+        c2["y"] = np.mod(c["y"] + dt * c["vy"], c["ly"])
+        mg.upload(c2["x"], c2["y"], c2["vx"], c2["vy"], c2["rad"], t=dt)
+        got2 = mg.predict_all(allow_overlap=True)
+        want2 = oracle_sweep(oracle, c2, t=dt)
+        assert_events_equal(got2, want2)

@@ -257,11 +257,10 @@ int edmd_launch_boop(edmd_ctx *c, double r_c)
     a.q6arg = c->boop + 3 * N;
     a.nbr = c->boop_nb;
     const int blocks = (a.max_chunks + kStageWarps - 1) / kStageWarps;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;   // devices of this process the attributes are set on
+    if (edmd_first_on_device(&attr)) {
         cudaFuncSetAttribute(k_boop_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem);
         cudaFuncSetAttribute(k_boop_rows, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr = true;
     }
     k_boop_rows<<<min(blocks, edmd_persistent_blocks(c)), kStageThreads, kStageSmem, c->stream>>>(a);
     return 1;
@@ -293,11 +292,10 @@ int edmd_launch_pcf(edmd_ctx *c, double dr, double max_r, int num_bins, const do
     size_t hist_bytes = (size_t)num_bins * sizeof(unsigned int);
     int use_smem = (tile_bytes + hist_bytes) <= 200 * 1024;
     size_t smem = tile_bytes + (use_smem ? hist_bytes : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;   // devices of this process the attributes are set on
+    if (edmd_first_on_device(&attr_set)) {
         cudaFuncSetAttribute(k_pcf, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024);
-        attr_set = true;
     }
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf, kPcfThreads, smem);

@@ -999,12 +999,11 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
         fa.hx32 = 0.5f * fa.lx32;
         fa.hy32 = 0.5f * fa.ly32;
         // groups of 256 threads per CTA (they share the histogram): the G with the most resident warps
-        static bool attr32 = false;
-        if (!attr32) {
+        static unsigned long long attr32 = 0;   // devices of this process the attributes are set on
+        if (edmd_first_on_device(&attr32)) {
             cudaFuncSetAttribute(k_pcf_f32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
             cudaFuncSetAttribute(k_pcf_f32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
             cudaFuncSetAttribute(k_pcf_f32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-            attr32 = true;
         }
         int best_g = 1, best_warps = 0, best_per_sm = 1;
         for (int g = 1; g <= 4; g *= 2) {
@@ -1039,10 +1038,9 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     const size_t hist_bytes = (size_t)num_bins * sizeof(unsigned int);
     a.use_smem = (tile_bytes + hist_bytes) <= 200 * 1024;
     const size_t smem = tile_bytes + (a.use_smem ? hist_bytes : 0);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;   // devices of this process the attributes are set on
+    if (edmd_first_on_device(&attr)) {
         cudaFuncSetAttribute(k_pcf_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-        attr = true;
     }
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcf_sorted, kThreads, smem);

@@ -501,10 +501,9 @@ int edmd_launch_voronoi(edmd_ctx *c, char *scratch, int boop, double *q5, double
         const double sp = sqrt(c->box.lx * c->box.ly / (double)(n > 0 ? n : 1));
         a.near2 = (1.45 * sp) * (1.45 * sp);
     }
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;   // devices of this process the attributes are set on
+    if (edmd_first_on_device(&attr)) {
         cudaFuncSetAttribute(k_voronoi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVorSmem);
-        attr = true;
     }
     if (before_cells) cudaEventRecord(before_cells, c->stream);
     k_voronoi<<<(n + kThreads - 1) / kThreads, kThreads, kVorSmem, c->stream>>>(a);

@@ -260,11 +260,10 @@ int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bin
     const size_t hist_bytes = (size_t)num_bins * (sizeof(unsigned long long) + sizeof(unsigned int));
     a.use_smem = (tile_bytes + hist_bytes) <= 200 * 1024;
     const size_t smem = tile_bytes + (a.use_smem ? hist_bytes : 0);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;   // devices of this process the attributes are set on
+    if (edmd_first_on_device(&attr)) {
         cudaFuncSetAttribute(k_pcf_bond_order<kWeightCos>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(k_pcf_bond_order<kWeightPsi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr = true;
     }
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);

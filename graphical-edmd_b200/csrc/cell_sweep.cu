@@ -1094,6 +1094,18 @@ k_unpack_events(int n, const edmd_ev32 *__restrict__ ev, double *__restrict__ t_
 
 }  // namespace
 
+// see edmd_preload_exchange_kernels (halo.cu)
+void edmd_preload_sweep_kernels()
+{
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_cell_partition);
+    cudaFuncGetAttributes(&fa, k_halo_recv_partition);
+    cudaFuncGetAttributes(&fa, k_cell_sweep);
+    cudaFuncGetAttributes(&fa, k_cell_boop);
+    cudaFuncGetAttributes(&fa, k_unpack_events);
+    cudaFuncGetAttributes(&fa, k_unpack_boop);
+}
+
 bool edmd_tile_eligible(const edmd_ctx *c, int mode)
 {
     return edmd_lean_eligible(c, mode) && !c->tile_off && c->pst != nullptr;
@@ -1240,13 +1252,12 @@ static SweepArgs sweep_args(edmd_ctx *c)
 
 static void tile_attrs()
 {
-    static bool attr = false;
-    if (attr) return;
+    static unsigned long long attr = 0;   // devices of this process the attributes are set on
+    if (!edmd_first_on_device(&attr)) return;
     cudaFuncSetAttribute(k_cell_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_cell_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_cell_boop, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_cell_boop, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    attr = true;
 }
 
 // the sweep kernel over the cell slots (P2): persistent CTAs, kTileCtas per SM

@@ -575,6 +575,7 @@ int edmd_cuda_halo_connect(edmd_ctx *c, const void *lower64, const void *upper64
     if (!c) return EDMD_EINVAL;
     if (!c->slab || !c->halo_mem) return fail(c, EDMD_ESTATE, "halo_export first");
     CU(cudaSetDevice(c->device));
+    edmd_preload_exchange_kernels();
     const void *hs[2] = {lower64, upper64};
     for (int k = 0; k < 2; k++) {
         if (!hs[k]) {               // the neighbour is this very context (single slab)

@@ -311,6 +311,7 @@ int edmd_launch_halo_pack(edmd_ctx *c, int side, void *out, int cap, int32_t *co
 int edmd_launch_halo_append_row(edmd_ctx *c, const void *in, int count, int row);
 size_t edmd_halo_mem_bytes(int halo_cap);
 int edmd_launch_halo_p2p(edmd_ctx *c);
+void edmd_preload_exchange_kernels();
 int edmd_halo_connect_direct(edmd_ctx *c, edmd_ctx *lower, edmd_ctx *upper);
 int edmd_launch_halo_send(edmd_ctx *c, bool chained);
 int edmd_launch_halo_recv(edmd_ctx *c);
@@ -391,6 +392,19 @@ __device__ __forceinline__ void edmd_note_radius(int32_t *flags, double r, doubl
         atomicOr(&flags[kFlagNotMono], level);
 }
 #endif
+
+// Function attributes (dynamic shared memory size, carveout) are PER DEVICE: a launcher sets them the first
+// time it runs on each device of the process (one process may drive several: multi_gpu.cu).
+// `done` = the call site's own static mask, one bit per device ordinal.
+inline bool edmd_first_on_device(unsigned long long *done)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    const unsigned long long bit = 1ull << dev;
+    if (*done & bit) return false;
+    *done |= bit;
+    return true;
+}
 
 // ---- programmatic dependent launch -----------------------------------------------
 // The kernels of a sweep form a dependent chain on one stream.  Each is launched

@@ -191,6 +191,22 @@ size_t edmd_halo_mem_bytes(int halo_cap) { return ack_offset(halo_cap) + 256; }
 // The exchange is two launches on the context's stream: send (peer stores into the neighbours'
 // inboxes; starts a new epoch) and receive (waits for the neighbours' epoch, unpacks, acks).  Work that
 // does not need the halo may be launched between the two (edmd_cuda_exchange_predict_device).
+// The kernels of an exchange WAIT FOR EACH OTHER across streams / devices (receive spins on the neighbour's
+// send).  With CUDA's lazy module loading the first launch of a kernel loads it, and that load may have to
+// wait for the device to go idle -- which a spinning receive kernel of the same process never lets happen
+// (a host thread that drives several slabs hung in its first exchange, measured).  So every kernel of the
+// exchange chain is loaded BEFORE the first exchange: cudaFuncGetAttributes forces the load.
+void edmd_preload_sweep_kernels();   // cell_sweep.cu
+void edmd_preload_exchange_kernels()
+{
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_halo_collect);
+    cudaFuncGetAttributes(&fa, k_halo_send);
+    cudaFuncGetAttributes(&fa, k_halo_recv);
+    edmd_preload_sweep_kernels();
+    cudaGetLastError();
+}
+
 int edmd_launch_halo_send(edmd_ctx *c, bool chained)
 {
     cudaStream_t st = c->stream;

@@ -99,6 +99,8 @@ int edmd_halo_connect_direct(edmd_ctx *c, edmd_ctx *lower, edmd_ctx *upper)
         c->peer_mem[k] = nb[k]->halo_mem;
         c->peer_opened[k] = false;
     }
+    if (cudaSetDevice(c->device) != cudaSuccess) return -1;
+    edmd_preload_exchange_kernels();   // the kernels of an exchange wait for each other: none may load lazily
     return 0;
 }
 

@@ -356,11 +356,10 @@ int edmd_launch_predict(edmd_ctx *c, int mode)
     else if (c->force_generic)
         edmd_launch(k_predict_generic<false>, dim3(blocks), dim3(kStageThreads), 0, c->stream, c->lean_pdl, a);
     else {
-        static bool attr = false;
-        if (!attr) {
+        static unsigned long long attr = 0;   // devices of this process the attributes are set on
+        if (edmd_first_on_device(&attr)) {
             cudaFuncSetAttribute(k_predict_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageSmem);
             cudaFuncSetAttribute(k_predict_rows, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            attr = true;
         }
         edmd_launch(k_predict_rows, dim3(min(blocks, edmd_persistent_blocks(c))), dim3(kStageThreads), kStageSmem,
                     c->stream, c->lean_pdl, a);

@@ -502,11 +502,10 @@ int edmd_launch_predict_lean(edmd_ctx *c)
     sa.max_chunks = c->lean_chunks;
     sa.flags = c->flags;
     sa.res = c->lres;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;   // devices of this process the attributes are set on
+    if (edmd_first_on_device(&attr)) {
         cudaFuncSetAttribute(k_screen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeanSmem);
         cudaFuncSetAttribute(k_screen, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr = true;
     }
     const int blocks = (sa.max_chunks + kLeanWarps - 1) / kLeanWarps;
     const int grid = (c->sm_count > 0 ? c->sm_count : 148) * kLeanCtas;

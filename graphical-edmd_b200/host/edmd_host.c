@@ -350,6 +350,8 @@ static void schedule_special(int slot, int type, double when)
 }
 
 /* ---- the whole-system sweep on the GPU -------------------------------------- */
+static edmd_mg *gpu_mg;   /* --gpus N > 1: the NORMAL-mode re-predict sweeps and the thermo's mean q6 run on N GPUs */
+
 static void gpu_upload(void)
 {
 	int rc = edmd_cuda_upload(gpu, px, py, pvx, pvy, prad, pcell, t);
@@ -418,15 +420,25 @@ static void gpu_predict_all(int remove_first)
 {
 	double t0 = now();
 	int32_t ov[2];
-	gpu_upload();
-	int rc = edmd_cuda_predict_all(gpu, growing ? EDMD_MODE_GROW : EDMD_MODE_NORMAL, growing ? pvr : NULL,
-	                               g_tcross, g_dir, g_tcoll, g_partner, g_type, ov);
-	if (rc == EDMD_EOVERLAP) overlap_abort(ov[0], ov[1]);
-	if (rc) die_gpu(rc, "edmd_cuda_predict_all");
+	int rc;
+	if (gpu_mg && !growing) {
+		/* row slabs over the GPUs (edmd_cuda_create_mg): same arrays in, same arrays out */
+		rc = edmd_cuda_mg_upload(gpu_mg, px, py, pvx, pvy, prad, pcell, t);
+		if (rc) { fprintf(stderr, "edmd_host: edmd_cuda_mg_upload failed (%d): %s\n", rc, edmd_cuda_mg_last_error(gpu_mg)); exit(2); }
+		rc = edmd_cuda_mg_predict_all(gpu_mg, EDMD_MODE_NORMAL, g_tcross, g_dir, g_tcoll, g_partner, g_type, ov);
+		if (rc == EDMD_EOVERLAP) overlap_abort(ov[0], ov[1]);
+		if (rc) { fprintf(stderr, "edmd_host: edmd_cuda_mg_predict_all failed (%d): %s\n", rc, edmd_cuda_mg_last_error(gpu_mg)); exit(2); }
+	} else {
+		gpu_upload();
+		rc = edmd_cuda_predict_all(gpu, growing ? EDMD_MODE_GROW : EDMD_MODE_NORMAL, growing ? pvr : NULL,
+		                           g_tcross, g_dir, g_tcoll, g_partner, g_type, ov);
+		if (rc == EDMD_EOVERLAP) overlap_abort(ov[0], ov[1]);
+		if (rc) die_gpu(rc, "edmd_cuda_predict_all");
+	}
 	gpu_sweep_seconds += now() - t0;
 	gpu_sweeps++;
 	double t1 = now();
-	if (bulk_ingest) {
+	if (bulk_ingest && !(gpu_mg && !growing)) {   /* the ingest plan is made from ONE device's predictions */
 		if (ingest_from_plan()) {
 			ingest_seconds += now() - t1;
 			bulk_sweeps++;
@@ -668,11 +680,18 @@ static void do_thermo(void)
 		fprintf(fthermo, "%lf %ld %lf %lf %lf %lf %.10lf %.10lf ", t, (long)ncol, E / N, p, pX, pY, pXY, pYX);
 		if (boopThermo) { /* mean q6 of the current configuration, computeBOOPVoronoi / computeBOOPCutoff(2.5) */
 			for (int i = 0; i < N; i++) free_fly(i);
-			gpu_upload();
 			double q6 = 0;
-			int rc = boopThermo == 1 ? edmd_cuda_boop_voronoi(gpu, NULL, NULL, NULL, NULL, NULL, &q6)
-			                         : edmd_cuda_boop_cutoff(gpu, 2.5, NULL, NULL, NULL, NULL, NULL, &q6);
-			if (rc) die_gpu(rc, "edmd_cuda_boop (thermo)");
+			int rc;
+			if (gpu_mg && boopThermo == 2) {
+				rc = edmd_cuda_mg_upload(gpu_mg, px, py, pvx, pvy, prad, pcell, t);
+				if (!rc) rc = edmd_cuda_mg_boop_cutoff(gpu_mg, 2.5, NULL, NULL, NULL, NULL, NULL, &q6);
+				if (rc) { fprintf(stderr, "edmd_host: psi6 on the slabs failed (%d): %s\n", rc, edmd_cuda_mg_last_error(gpu_mg)); exit(2); }
+			} else {
+				gpu_upload();
+				rc = boopThermo == 1 ? edmd_cuda_boop_voronoi(gpu, NULL, NULL, NULL, NULL, NULL, &q6)
+				                     : edmd_cuda_boop_cutoff(gpu, 2.5, NULL, NULL, NULL, NULL, NULL, &q6);
+				if (rc) die_gpu(rc, "edmd_cuda_boop (thermo)");
+			}
 			fprintf(fthermo, "%lf ", q6);
 		}
 		fprintf(fthermo, "%lf \n", a2);
@@ -818,9 +837,10 @@ int main(int argc, char **argv)
 		{"boop-voronoi", no_argument, NULL, 1011}, {"area", no_argument, NULL, 1012},
 		{"struc", required_argument, NULL, 1013}, {"qmax", required_argument, NULL, 1014},
 		{"pcfg6", no_argument, NULL, 1015}, {"gamma", required_argument, NULL, 1016},
-		{"initial-energy", required_argument, NULL, 'E'},
+		{"initial-energy", required_argument, NULL, 'E'}, {"gpus", required_argument, NULL, 1017},
+		{"slabs", required_argument, NULL, 1018},
 		{NULL, 0, NULL, 0}};
-	int c, device = 0;
+	int c, device = 0, ngpus = 1, nslabs = 0;
 	while ((c = getopt_long(argc, argv, "N:p:x:q:a:t:D:o:T:v:E:", longopt, NULL)) != -1) {
 		switch (c) {
 		case 'N': N = atoi(optarg); break;
@@ -850,8 +870,10 @@ int main(int argc, char **argv)
 		case 1014: qmax = atof(optarg); break;
 		case 1015: pcfg6Thermo = 1; break;
 		case 1016: gamm = atof(optarg); break;
+		case 1017: ngpus = atoi(optarg); break;
+		case 1018: nslabs = atoi(optarg); break;   /* slabs dealt round-robin to the GPUs (default: one per GPU) */
 		default: fprintf(stderr, "usage: edmd_host -N n --phi f [-x xs -q ratio -a aspect -t tmax -D dt -o dtThermo -T temp -v seed -E Einit]\n"
-		                         "       [--init grow|lattice] [--ingest bulk|seq] [--noise 1|2 --dtnoise dt --gamma g] [--boop | --boop-voronoi] [--area] [--pcf] [--pcfg6] [--struc mode --qmax q] [--verify] [--outdir dir] [--quiet]\n");
+		                         "       [--init grow|lattice] [--ingest bulk|seq] [--noise 1|2 --dtnoise dt --gamma g] [--boop | --boop-voronoi] [--area] [--pcf] [--pcfg6] [--struc mode --qmax q] [--verify] [--outdir dir] [--quiet] [--gpus n [--slabs m]]\n");
 			return 2;
 		}
 	}
@@ -862,6 +884,14 @@ int main(int argc, char **argv)
 	particles_init();
 	int rc = edmd_cuda_create(device, N, Lx, Ly, &gpu);
 	if (rc) die_gpu(rc, "edmd_cuda_create");
+	if (nslabs < ngpus) nslabs = ngpus;
+	if (nslabs > 1) {
+		int devs[64];
+		if (nslabs > 64 || ngpus < 1) { fprintf(stderr, "edmd_host: --gpus / --slabs out of range\n"); return 2; }
+		for (int k = 0; k < nslabs; k++) devs[k] = device + k % ngpus;
+		rc = edmd_cuda_create_mg(nslabs, devs, N, Lx, Ly, &gpu_mg);
+		if (rc) { fprintf(stderr, "edmd_host: edmd_cuda_create_mg(%d slabs on %d GPUs) failed (%d)\n", nslabs, ngpus, rc); return 2; }
+	}
 	edmd_box box;
 	edmd_cuda_get_box(gpu, &box);
 	Nx = box.nxcells; Ny = box.nycells; csx = box.cellx_size; csy = box.celly_size;
@@ -964,6 +994,7 @@ int main(int argc, char **argv)
 	fclose(fdump); fclose(fthermo);
 	if (fpcf) fclose(fpcf);
 	if (fstruc) fclose(fstruc);
+	if (gpu_mg) edmd_cuda_destroy_mg(gpu_mg);
 	edmd_cuda_destroy(gpu);
 	return 0;
 }

@@ -160,3 +160,20 @@ def test_host_growth_stop_normalises_on_the_device(tmp_path):
     th = np.loadtxt(next(tmp_path.glob("*.thermo")), skiprows=1)
     assert len(th) >= 4 and np.abs(th[:, 2] - 1.7).max() < 2e-6
     assert re.search(r"E/N = 1\.70000", out), out
+
+
+def test_host_on_slabs_is_the_same_trajectory(tmp_path):
+    """--gpus / --slabs: the re-predict sweeps and the thermo's mean q6 through edmd_cuda_create_mg (here
+    three slabs dealt to the GPUs present) -- the same events bit for bit, hence the same run byte for byte."""
+    import torch
+    outs = {}
+    for tag, extra in (("one", ()), ("slabs", ("--gpus", min(2, torch.cuda.device_count()), "--slabs", 3))):
+        d = tmp_path / tag
+        d.mkdir()
+        out = run_host(d, "-N", 6000, "--phi", 0.6, "-x", 0, "-t", 12, "-D", 4, "-o", 2, "--quiet", "--init", "lattice",
+                       "--noise", 2, "--dtnoise", 0.5, "--boop", "--ingest", "seq", *extra)
+        outs[tag] = (next(d.glob("*.dump")).read_bytes(), next(d.glob("*.thermo")).read_bytes(),
+                     re.search(r"(\d+) collisions", out).group(1))
+    assert outs["one"][2] == outs["slabs"][2] and int(outs["one"][2]) > 20000
+    assert outs["one"][1] == outs["slabs"][1]
+    assert outs["one"][0] == outs["slabs"][0]

@@ -142,26 +142,33 @@ def cpu_baseline(cfg, repeats=3):
             "seconds_per_sweep": min(secs)}
 
 
-def end_to_end_coll_rate(t_end=150.0):
-    """Third part of BASELINE.json's metric: end-to-end collisions per second of the
-    whole program on configs[0] (`-N 2000 --phi 0.7`, the reference CLI defaults:
-    30 % small disks, growth start).  Ours = graphical-edmd_b200/host/edmd_host
-    (sequential C host + the CUDA library for the whole-system sweeps); reference =
-    the unmodified reference's own main(), called through oracle/_ref.  Both are
-    sequential event loops on one host core; a bounded run of `t_end` time units."""
+def end_to_end_coll_rate(t_short=60.0, t_long=150.0):
+    """Third part of BASELINE.json's metric: end-to-end collisions per second of the whole program on
+    configs[0] (`-N 2000 --phi 0.7`, the reference CLI defaults: 30 % small disks, growth start).
+    Ours = graphical-edmd_b200/host/edmd_host (sequential C host + the CUDA library for the whole-system
+    sweeps); reference = the unmodified reference's own main(), called through oracle/_ref.  Both are
+    sequential event loops on one host core.  LIKE FOR LIKE: each program runs twice (to t_short and to
+    t_long); rate = (collisions(t_long) - collisions(t_short)) / (wall(t_long) - wall(t_short)) -- setup,
+    growth phase and process start cancel -- with EXACT collision counters (ours: the host's own;
+    reference: its global `ncol` read through the shim after main() returns, not a console value)."""
     import re
     import tempfile
-    out = {"config": f"-N 2000 --phi 0.7 -t {t_end:g} (reference CLI defaults, BASELINE configs[0])"}
+    out = {"config": f"-N 2000 --phi 0.7, runs to t = {t_short:g} and t = {t_long:g} (reference CLI defaults, "
+                     f"BASELINE configs[0]); rate = difference of the two runs"}
     host = ROOT / "graphical-edmd_b200" / "host" / "edmd_host"
-    try:
+
+    def ours(t_end):
         with tempfile.TemporaryDirectory() as d:
             r = subprocess.run([str(host), "-N", "2000", "--phi", "0.7", "-t", str(t_end), "-D", "1000",
-                                "-o", "1000", "--quiet", "--outdir", d], capture_output=True, text=True,
-                               timeout=300)
-            m = re.search(r"(\d+) collisions, \d+ crossings in ([\d.]+) s => ([\d.e+]+) coll/s", r.stdout)
-            if m:
-                out["ours"] = {"collisions": int(m.group(1)), "seconds": float(m.group(2)),
-                               "coll_per_s": float(m.group(3)), "cores": 1}
+                                "-o", "1000", "--quiet", "--outdir", d], capture_output=True, text=True, timeout=300)
+        m = re.search(r"(\d+) collisions", r.stdout)
+        w = re.search(r"whole run ([\d.]+) s", r.stdout)
+        return int(m.group(1)), float(w.group(1))
+
+    try:
+        (c1, w1), (c2, w2) = ours(t_short), ours(t_long)
+        out["ours"] = {"collisions": c2 - c1, "seconds": w2 - w1, "coll_per_s": (c2 - c1) / (w2 - w1), "cores": 1,
+                       "runs": [[c1, w1], [c2, w2]]}
     except Exception as e:   # the host program is optional for the headline number
         out["ours_error"] = str(e)[:200]
     ref_so = ROOT / "oracle" / "_ref" / "libedmd_ref.so"
@@ -170,22 +177,53 @@ def end_to_end_coll_rate(t_end=150.0):
                 f"lib = C.CDLL({str(ref_so)!r})\n"
                 "a = [b'a.out', b'-N', b'2000', b'--phi', b'0.7', b'-t', sys.argv[1].encode()]\n"
                 "argv = (C.c_char_p * (len(a) + 1))(*a, None)\n"
-                "t0 = time.time(); lib.edmd_reference_main(len(a), argv)\n"
-                "sys.stdout.flush(); print('\\nWALL', time.time() - t0)\n")
-        try:
+                "t0 = time.time(); lib.edmd_reference_main(len(a), argv); w = time.time() - t0\n"
+                "lib.ref_last_ncol.restype = C.c_ulong\n"
+                "sys.stdout.flush(); print('\\nNCOL', lib.ref_last_ncol(), 'WALL', w)\n")
+
+        def ref(t_end):
             with tempfile.TemporaryDirectory() as d:
                 os.makedirs(os.path.join(d, "dump"), exist_ok=True)
                 r = subprocess.run([sys.executable, "-c", code, str(t_end)], cwd=d, capture_output=True,
                                    text=True, timeout=300)
-                ncoll = re.findall(r"coll = (?:\x1b\[[\d;]*m)?([\d.e+]+)", r.stdout)
-                wall = re.search(r"WALL ([\d.]+)", r.stdout)
-                if ncoll and wall:
-                    out["reference"] = {"collisions": float(ncoll[-1]), "seconds": float(wall.group(1)),
-                                        "coll_per_s": float(ncoll[-1]) / float(wall.group(1)), "cores": 1,
-                                        "note": "whole run incl. its growth phase and console output"}
+            m = re.search(r"NCOL (\d+) WALL ([\d.]+)", r.stdout)
+            return int(m.group(1)), float(m.group(2))
+
+        try:
+            (c1, w1), (c2, w2) = ref(t_short), ref(t_long)
+            out["reference"] = {"collisions": c2 - c1, "seconds": w2 - w1, "coll_per_s": (c2 - c1) / (w2 - w1),
+                                "cores": 1, "runs": [[c1, w1], [c2, w2]]}
         except Exception as e:
             out["reference_error"] = str(e)[:200]
     return out
+
+
+def thermostat_run_1m():
+    """The end-to-end number where the GPU matters: edmd_host at N = 10^6 with the velocity-rescale thermostat
+    (every tick = upload + sweep + download + calendar ingest from the device's plan).  The reference's CLI
+    build has `noise` compiled out (const int noise = 0), so its side is the per-tick cost of its own addNoise()
+    (cpu_baseline.seconds_per_sweep: re-predict incl. calendar remove/insert)."""
+    import re
+    import tempfile
+    host = ROOT / "graphical-edmd_b200" / "host" / "edmd_host"
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            r = subprocess.run([str(host), "-N", "1000000", "--phi", "0.7", "-x", "0", "--init", "lattice", "-t", "0.6",
+                                "-D", "1000", "-o", "1000", "--noise", "2", "--dtnoise", "0.1", "--quiet",
+                                "--outdir", d], capture_output=True, text=True, timeout=600)
+        m = re.search(r"(\d+) collisions, \d+ crossings in ([\d.]+) s => ([\d.e+]+) coll/s.*?(\d+) GPU sweeps, "
+                      r"([\d.]+) ms each.*?calendar ingest ([\d.]+) ms each", r.stdout)
+        if not m:
+            return {"error": (r.stdout + r.stderr)[-300:]}
+        return {"config": "edmd_host -N 1000000 --phi 0.7 -x 0 --init lattice --noise 2 --dtnoise 0.1 -t 0.6",
+                "collisions": int(m.group(1)), "seconds": float(m.group(2)), "coll_per_s": float(m.group(3)),
+                "gpu_sweeps": int(m.group(4)), "ms_per_sweep_upload_k0_k1_download": float(m.group(5)),
+                "ms_calendar_ingest_per_tick": float(m.group(6)),
+                "ms_per_tick": float(m.group(5)) + float(m.group(6)),
+                "note": "per tick: GPU sweep through the C ABI + the host's calendar rebuild from the device's ingest "
+                        "plan; compare cpu_baseline.seconds_per_sweep (the reference's addNoise tick, one core)"}
+    except Exception as e:
+        return {"error": str(e)[:200]}
 
 
 def run_reference(args, cfg):
@@ -723,6 +761,7 @@ def run_ours(args, cfg):
             line["cpu_baseline"] = cpu
         if world == 1 and not args.no_cpu:
             line["end_to_end"] = end_to_end_coll_rate()
+            line["end_to_end"]["thermostat_run_n1e6"] = thermostat_run_1m()
         print(json.dumps(line, default=float))
     if ctx is not None:
         ctx.close()

@@ -985,6 +985,7 @@ int main(int argc, char **argv)
 		}
 	}
 	double wall = now() - wall1;
+	printf("edmd_host: whole run %.3f s (setup + growth phase + event loop)\n", now() - wall0);
 	printf("edmd_host: %lu collisions, %lu crossings in %.3f s => %.4g coll/s ; setup %.3f s ; "
 	       "%d GPU sweeps, %.3f ms each (upload + K0 + K1 + download) ; calendar ingest %.3f ms each "
 	       "(%d from the device plan) ; E/N = %.6f ; p = %.6f\n",

@@ -59,6 +59,11 @@ int ref_run_main(int argc, char **argv)
 	return r;
 }
 
+/* Exact counters of the run edmd_reference_main() / ref_run_main() just finished: the reference's globals
+ * ncol (collisions since stopGrow zeroed it, src/EDMD.c:4746) and t. */
+unsigned long ref_last_ncol(void) { return ncol; }
+double ref_last_time(void) { return t; }
+
 /* State of the run ref_run_main() just finished, every particle brought to the final
  * time by the reference's freeFly (as takeAScreenshot does, src/EDMD.c:4659-4661);
  * box[0..2] = Lx, Ly, t.  Frees the kept array.  Returns N, or < 0. */

@@ -832,7 +832,9 @@ __device__ __forceinline__ void cell_worker(const SweepArgs &a, const SweepSmem 
         if (stamp && it < 6) edmd_stamp(a.ts, 16 + 4 * it);
         // the next tile: asked for now (the round trip hides behind the convert pass), fetched while this
         // one is swept.  ONE tile ahead, not two: what a worker holds when the counter runs out is the tail
-        // of the kernel (two tiles held: workers ended over a span of 25 us, measured).
+        // of the kernel (two tiles held: workers ended over a span of 25 us, measured).  (Also measured: asking
+        // for the next tile only AFTER the sweep in the last gridDim.x tiles -- nobody holds a tile at the end, the
+        // last fetch exposed -- changes nothing: 61.4 against 59.4-61.5 us; the workers' ends still span ~20 us.)
         int next = ntiles;
         if (tid == 0) next = atomicAdd(a.flags + kFlagTileCtr, 1);
         frame_tables(a, s, tp);
@@ -929,46 +931,18 @@ struct BoopTileArgs {
     double rc2;
     double4 *rec;   // two 32-byte sectors per particle id: (q5, q6, q7, q6_arg), (neighbours, 0, 0, 0)
 };
-constexpr int kBoopCtas = 1024 / kTileThreads;   // per SM: 32 warps at 64 registers per thread
-
-__global__ void __launch_bounds__(kTileThreads, kBoopCtas)
-k_cell_boop(const __grid_constant__ BoopTileArgs ba)
+// psi6 of every particle of one tile (frame in shared memory).  The nine plane-0 neighbours sit at fixed
+// offsets of the frame array: nine unrolled visits, then the listed extras of the block.
+template <bool WRAP>
+__device__ __forceinline__ void boop_tile(const BoopTileArgs &ba, const CellSmem &s, const TilePos &tp)
 {
-    extern __shared__ __align__(128) unsigned char cell_smem[];
     const SweepArgs &a = ba.s;
-    const CellSmem s = carve(cell_smem, a.tg.ecap, 0, true);
     const int tid = threadIdx.x;
-    const TilePos tp = tile_pos(a.tg, blockIdx.x);
-    if (tid < kFH) s.bits[tid] = 0ull;
-    if (tid < 2) s.misc[tid] = 0;
-    zero_other_counters(a, tp);
-    edmd_pdl_wait();
-    const bool declined = a.flags[kFlagBoopFail] != 0;
-    __syncthreads();
-    if (declined) return;
-    const bool fits = frame_load<true>(
-        a, s, tp, false,
-        [&](int pos, int, int, const double4 &st, double, int id) {
-            s.xy[pos] = make_double2(st.x, st.y);
-            s.id[pos] = id;
-        },
-        [&](int pos) { s.id[pos] = -1; });
-    if (!fits) {
-        if (tid == 0) atomicOr(&a.flags[kFlagBoopFail], 1);
-        return;
-    }
     const int tw = tp.tw, th = tp.th;
     const int ne = s.misc[0];
     const int nrow_items = th * 32;
     const int nitems = nrow_items + ne;
     const double half_lx = a.b.half_lx, half_ly = a.b.half_ly, lx = a.b.lx, ly = a.b.ly, rc2 = ba.rc2;
-    // a tile away from the edges of the grid never sees the periodic image (every particle lies within
-    // 1.5 cells of the cell it is filed under -- kFlagInsane -- so |d| <= 4 cells < L/2): PBC() is the identity
-    // (frame rows lo .. hi in local rows; in a slab the global row yoff + l wraps somewhere inside the slab)
-    const int fr_lo = tp.y0 - 1, fr_hi = tp.y0 + tp.th;
-    const bool wrap_y = fr_lo < 0 || fr_hi >= a.b.nl || (a.b.yoff + fr_lo < a.b.ny && a.b.yoff + fr_hi >= a.b.ny);
-    const bool wrap = a.flags[kFlagInsane] != 0 || tp.txi == 0 || tp.txi == a.tg.ntx - 1 || wrap_y ||
-                      a.b.nx < 12 || a.b.ny < 12;
 #pragma unroll 1
     for (int w = tid; w < nitems; w += kTileThreads) {
         int p, c, fx, fy;
@@ -995,12 +969,12 @@ k_cell_boop(const __grid_constant__ BoopTileArgs ba)
             const double2 qq = s.xy[q];
             // the reference's own operations decide who is a neighbour (src/boop.c:78-84)
             double dx = __dsub_rn(qq.x, me.x), dy = __dsub_rn(qq.y, me.y);
-            if (wrap) {
+            if (WRAP) {
                 dx = min_image(dx, half_lx, lx);
                 dy = min_image(dy, half_ly, ly);
             }
             const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            if (r2 < rc2) {
+            if (r2 < rc2) {   // (false for the NaN position of an empty cell)
                 nb++;
                 // e^{ik theta} = ((dx + i dy)/r)^k, k = 5, 6, 7, by complex powers (fused multiply-adds:
                 // not parity-critical, gate 1e-10); 1/r from the MUFU seed + two Newton steps
@@ -1026,14 +1000,23 @@ k_cell_boop(const __grid_constant__ BoopTileArgs ba)
                 s7i += __fma_rn(z6r, zi, __dmul_rn(z6i, zr));
             }
         };
+        // scan order: rows, cells, ascending particle id inside a cell (plane 0 holds the smallest id of a cell,
+        // its extras follow in ascending id): the sums run in one fixed order
+        unsigned xm = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) xm |= ((unsigned)(s.bits[fy + j - 1] >> (fx - 1)) & 7u) << (3 * j);
+        if (xm == 0 && p < kFC) {
+            // (nearly always) no extras around and a plane-0 particle: nine fixed offsets, the centre is itself
+#pragma unroll
+            for (int b = 0; b < 9; b++)
+                if (b != 4) visit(c + (b / 3 - 1) * kFW + (b % 3 - 1));
+        } else {
 #pragma unroll 1
-        for (int j = 0; j < 3; j++) {
-            const unsigned rb = (unsigned)(s.bits[fy + j - 1] >> (fx - 1)) & 7u;
-#pragma unroll 1
-            for (int k = 0; k < 3; k++) {
+            for (int b = 0; b < 9; b++) {
+                const int j = (b * 11) >> 5, k = b - 3 * j;
                 const int q = c + (j - 1) * kFW + (k - 1);
-                if (q != p && s.id[q] >= 0) visit(q);   // `p2->num != p1->num`
-                if ((rb >> k) & 1u) {
+                if (q != p) visit(q);   // `p2->num != p1->num`
+                if ((xm >> b) & 1u) {
                     const unsigned info = s.xinfo[q];
                     const int q0 = kFC + (info & 0xfff), qn = info >> 12;
 #pragma unroll 1
@@ -1044,10 +1027,18 @@ k_cell_boop(const __grid_constant__ BoopTileArgs ba)
         }
         double q5 = 0.0, q6 = 0.0, q7 = 0.0, arg = 0.0;
         if (nb > 0) {
-            const double inv_n = 1.0 / (double)nb;
-            auto modulus = [&](double re, double im) {   // |re + i im| / n  (no overflow: |sum| <= n)
+            // 1/n: exact reciprocals are not needed (gate 1e-10); |sum| = m2 * rsqrt(m2) with two Newton steps
+            // instead of an IEEE square root (no overflow: |sum| <= n)
+            const double inv_n = __drcp_rn((double)nb);
+            auto modulus = [&](double re, double im) {
                 const double m2 = __fma_rn(re, re, __dmul_rn(im, im));
-                return __dmul_rn(__dsqrt_rn(m2), inv_n);
+                if (!(m2 > 0)) return 0.0;
+                double y = rsqrt_seed(m2);
+                double e = __fma_rn(-__dmul_rn(m2, y), y, 1.0);
+                y = __fma_rn(__dmul_rn(0.5, y), e, y);
+                e = __fma_rn(-__dmul_rn(m2, y), y, 1.0);
+                y = __fma_rn(__dmul_rn(0.5, y), e, y);
+                return __dmul_rn(__dmul_rn(m2, y), inv_n);
             };
             q5 = modulus(s5r, s5i);
             q6 = modulus(s6r, s6i);
@@ -1060,6 +1051,49 @@ k_cell_boop(const __grid_constant__ BoopTileArgs ba)
         asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(q5), "d"(q6), "d"(q7), "d"(arg) : "memory");
         asm volatile("st.global.v8.b32 [%0], {%1,%2,%2,%2,%2,%2,%2,%2};" ::"l"(dst + 1), "r"(nb), "r"(0) : "memory");
     }
+}
+
+constexpr int kBoopCtas = 1024 / kTileThreads;   // per SM: 32 warps at 64 registers per thread
+
+__global__ void __launch_bounds__(kTileThreads, kBoopCtas)
+k_cell_boop(const __grid_constant__ BoopTileArgs ba)
+{
+    extern __shared__ __align__(128) unsigned char cell_smem[];
+    const SweepArgs &a = ba.s;
+    const CellSmem s = carve(cell_smem, a.tg.ecap, 0, true);
+    const int tid = threadIdx.x;
+    const TilePos tp = tile_pos(a.tg, blockIdx.x);
+    if (tid < kFH) s.bits[tid] = 0ull;
+    if (tid < 2) s.misc[tid] = 0;
+    zero_other_counters(a, tp);
+    edmd_pdl_wait();
+    const bool declined = a.flags[kFlagBoopFail] != 0;
+    __syncthreads();
+    if (declined) return;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    const bool fits = frame_load<true>(
+        a, s, tp, false,
+        [&](int pos, int, int, const double4 &st, double, int id) {
+            s.xy[pos] = make_double2(st.x, st.y);
+            s.id[pos] = id;
+        },
+        [&](int pos) {   // an empty cell is a NaN position: `r2 < rc2` fails by itself
+            s.xy[pos] = make_double2(qnan, qnan);
+            s.id[pos] = -1;
+        });
+    if (!fits) {
+        if (tid == 0) atomicOr(&a.flags[kFlagBoopFail], 1);
+        return;
+    }
+    // a tile away from the edges of the grid never sees the periodic image (every particle lies within
+    // 1.5 cells of the cell it is filed under -- kFlagInsane -- so |d| <= 4 cells < L/2): PBC() is the identity
+    // (frame rows lo .. hi in local rows; in a slab the global row yoff + l wraps somewhere inside the slab)
+    const int fr_lo = tp.y0 - 1, fr_hi = tp.y0 + tp.th;
+    const bool wrap_y = fr_lo < 0 || fr_hi >= a.b.nl || (a.b.yoff + fr_lo < a.b.ny && a.b.yoff + fr_hi >= a.b.ny);
+    const bool wrap = a.flags[kFlagInsane] != 0 || tp.txi == 0 || tp.txi == a.tg.ntx - 1 || wrap_y ||
+                      a.b.nx < 12 || a.b.ny < 12;
+    if (wrap) boop_tile<true>(ba, s, tp);
+    else boop_tile<false>(ba, s, tp);
 }
 
 // the ABI's five psi6 arrays from the records (one coalesced pass)

@@ -1049,8 +1049,15 @@ int edmd_cuda_pcf(edmd_ctx *c, double dr, double max_r, uint64_t *counts, double
     if (!(q < 1e8)) return fail(c, EDMD_EINVAL, "too many bins");
     int nb = (int)q;  // `(int)(max_r / dr)` src/pcf.c:21
     *num_bins = nb;
-    if (!counts) return 0;
+    if (!counts && !g_r) return 0;   // a query for the number of bins
     if (!c->have_state) return fail(c, EDMD_ESTATE, "pcf before upload");
+    // a slab holds copies of its neighbours' boundary rows: all pairs of the WHOLE system are wanted
+    if (c->slab) return fail(c, EDMD_ESTATE, "slab contexts: edmd_cuda_pcf_device on the gathered positions (or edmd_cuda_mg_pcf)");
+    std::vector<uint64_t> own_counts;
+    if (!counts) {   // only g(r) is wanted: the counts go to a buffer of the library's
+        own_counts.resize((size_t)(nb > 0 ? nb : 1));
+        counts = own_counts.data();
+    }
     CU(cudaSetDevice(c->device));
     if (nb > c->pcf_cap) {
         if (c->pcf_counts) CU(cudaFree(c->pcf_counts));
@@ -1616,7 +1623,13 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
         int r = voronoi_scratch(c, &vgrid, &vpsi, &varea, &vperim, &vfail);
         if (r) return r;
     }
-    std::vector<cudaEvent_t> evs(3 * (size_t)iters);
+    // (destroyed on every return path)
+    struct Events {
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+    } guard;
+    guard.v.assign(3 * (size_t)iters, nullptr);
+    std::vector<cudaEvent_t> &evs = guard.v;
     for (auto &e : evs) CU(cudaEventCreate(&e));
     const double t_keep = c->t;
     for (int it = -warmup; it < iters; it++) {
@@ -1726,7 +1739,6 @@ int edmd_cuda_bench(edmd_ctx *c, int what, int mode, double dr, double max_r, in
         if (ms_total) ms_total[it] = a;
         if (ms_main) ms_main[it] = b;
     }
-    for (auto &e : evs) cudaEventDestroy(e);
     return 0;
 }
 

@@ -1327,3 +1327,27 @@ def test_multi_gpu_c_entry_matches_oracle(pkg, oracle, nslabs, n, phi, sf):
         got2 = mg.predict_all(allow_overlap=True)
         want2 = oracle_sweep(oracle, c2, t=dt)
         assert_events_equal(got2, want2)
+
+
+@pytest.mark.gpu
+def test_pcf_g_r_alone_and_slab_rejection(pkg, oracle):
+    """edmd_cuda_pcf with counts == NULL but g_r wanted computes g(r) (it used to return early);
+    a slab context -- which holds copies of its neighbours' rows -- refuses the whole-system call."""
+    import ctypes as C
+    c = pkg.synth.lattice_config(20000, 0.7, seed=5)
+    want = oracle.pcf(c["n"], c["lx"], c["ly"], c["x"], c["y"], 0.1, 9.0)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        nb = C.c_int(0)
+        g = np.zeros(want["num_bins"], np.float64)
+        rc = ctx.lib.edmd_cuda_pcf(ctx._h, 0.1, 9.0, None, g.ctypes.data_as(C.c_void_p), C.byref(nb))
+        assert rc == 0 and nb.value == want["num_bins"]
+        assert np.abs(g - want["g_r"]).max() <= 1e-12 * want["g_r"].max()
+    ny = int(c["ly"] / 2)
+    with pkg.EdmdCuda(c["n"] + 4096, c["lx"], c["ly"], slab_rows=(0, ny // 2)) as sl:
+        cells = oracle.cells(c["n"], c["lx"], c["ly"], c["x"], c["y"]).reshape(-1, 2)
+        own = np.nonzero(cells[:, 1] < ny // 2)[0].astype(np.int32)
+        sl.upload_owned(c["x"][own], c["y"][own], c["vx"][own], c["vy"][own], c["rad"][own], cells[own], own, t=0.0)
+        cnt = np.zeros(want["num_bins"], np.uint64)
+        rc = sl.lib.edmd_cuda_pcf(sl._h, 0.1, 9.0, cnt.ctypes.data_as(C.c_void_p), None, C.byref(nb))
+        assert rc == pkg.binding.ESTATE

@@ -1,6 +1,28 @@
-import sys; sys.path.insert(0,'/root/repo')
-import numpy as np, __graft_entry__ as e
-pkg=e.load_package()
+"""compute-sanitizer target: small sweeps (one class, two classes, slabs on one device), psi6, normalize."""
+import sys
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from __graft_entry__ import load_package  # noqa: E402
+pkg = load_package()
+for sf in (0.0, 0.3):
+    c = pkg.synth.lattice_config(30000, 0.72, seed=3, small_fraction=sf, shuffle=True)
+    with pkg.EdmdCuda(c["n"], c["lx"], c["ly"]) as ctx:
+        ctx.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        a = ctx.predict_all()
+        b = ctx.predict_all()
+        assert np.array_equal(a["t_coll"], b["t_coll"])
+        ctx.boop_cutoff(2.5)
+        ctx.normalize_velocities(1.0)
+        ctx.predict_all()
+    with pkg.EdmdMg(c["n"], c["lx"], c["ly"], [0, 0, 0]) as mg:
+        mg.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.0)
+        g = mg.predict_all()
+        assert np.array_equal(g["t_coll"], a["t_coll"]) and np.array_equal(g["partner"], a["partner"])
+        mg.boop_cutoff(2.5)
+
+# ---- the other paths: growth sweep, free flight, g(r), tiny boxes / overflow -> full path
 for (n,phi,sf) in [(3000,0.7,0.3),(800,0.3,0.0)]:
     c=pkg.synth.lattice_config(n,phi,3,small_fraction=sf)
     with pkg.EdmdCuda(c['n'],c['lx'],c['ly']) as ctx:
@@ -17,3 +39,4 @@ with pkg.EdmdCuda(n,lx,ly) as ctx:
     ctx.upload(x,y,rng.standard_normal(n),rng.standard_normal(n),np.full(n,1e-4),t=0.0)
     ctx.predict_all(); ctx.boop_cutoff(0.5)
 print('ok overflow')
+print("sanitize target done")

@@ -432,7 +432,7 @@ __device__ __forceinline__ bool frame_load(const SweepArgs &a, const CellSmem &s
 //   xst     double4[ecap], xrad double[ecap]   FP64 states / radii of the extras
 //   bits, xinfo, ecell       as CellSmem
 static_assert((kFW * 8) % 16 == 0, "bulk copies move 16-byte granules");
-static_assert(kFW + kFH <= kTileThreads && 32 + kFH <= 62, "frame_tables / the list reset spread their work over the first 64 threads");
+static_assert(kFW + kFH <= kTileThreads && 32 + kFH <= 60, "frame_tables / the list reset spread their work over the first 64 threads");
 static_assert(kFW == 34, "frame_convert divides by 34 with a multiply-shift");
 struct SweepSmem {
     double4 *st;    // buffer b at st + b * kFC
@@ -444,7 +444,8 @@ struct SweepSmem {
     double *xrad;
     unsigned long long *bits;   // [2][kFH]: the set of tile k is cleared while tile k+1 uses the other
     unsigned short *xinfo, *ecell;
-    int *misc;   // per set (4 ints each): [0] extras listed, [1] decline, [2] the tile after the next one
+    unsigned short *items;   // [kTX * kTY + ecap] the particles this tile predicts, compacted: p (see above)
+    int *misc;   // per set (4 ints each): [0] extras listed, [1] decline, [2] the next tile, [3] items listed
     double *ctr; // [kFW] x of the centre of the cell frame column fx is FILED under, [kFH] y of frame row fy's
     int *rowl;   // [kFH] local row of frame row fy, -1: none
     LeanConsts *K;
@@ -466,6 +467,7 @@ __host__ __device__ inline size_t sweep_smem_bytes(int ecap, int rad_smem)
     b += 32;                                               // misc
     b += (sizeof(LeanConsts) + 15) & ~(size_t)15;
     b += sizeof(unsigned short) * (kFC + ecap);            // xinfo, ecell
+    b += sizeof(unsigned short) * (kTX * kTY + ecap);      // items
     return (b + 15) & ~(size_t)15;
 }
 
@@ -505,6 +507,7 @@ __device__ __forceinline__ SweepSmem carve_sweep(unsigned char *base, int ecap, 
     base += (sizeof(LeanConsts) + 15) & ~(size_t)15;
     s.xinfo = reinterpret_cast<unsigned short *>(base);
     s.ecell = s.xinfo + kFC;
+    s.items = s.ecell + ecap;
     return s;
 }
 
@@ -627,6 +630,31 @@ __device__ __forceinline__ bool frame_convert(const SweepArgs &a, const SweepSme
     }
     zero_other_counters(a, tp);
     __syncthreads();
+    // The particles this tile predicts, COMPACTED: 12 % of the cells are empty (and a halo row's disks are never
+    // predicted), so a warp that walks a tile row cell by cell runs at 28 of 32 lanes and the extras take a trip of
+    // their own; from the list every trip is full (-15 % trips).  Order inside the list is irrelevant.
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int r = warp; r < tp.th; r += kTileWarps) {
+            const int c = (r + 1) * kFW + lane + 1;
+            const int id = lane < tp.tw ? s.id[c] : -1;
+            const bool live = id >= 0 && id < a.n_owned;
+            const unsigned m = __ballot_sync(0xffffffffu, live);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&misc[3], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (live) s.items[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)c;
+        }
+        const int ne = min(misc[0], a.tg.ecap);
+        for (int e = tid; e < ne; e += kTileThreads) {
+            const int c = s.ecell[e];
+            const int fy = (c * 241) >> 13, fx = c - fy * kFW;
+            const int id = s.id[kFC + e];
+            if (fx >= 1 && fx <= tp.tw && fy >= 1 && fy <= tp.th && id >= 0 && id < a.n_owned)   // (not an extra of the ring)
+                s.items[atomicAdd(&misc[3], 1)] = (unsigned short)(kFC + e);
+        }
+    }
+    __syncthreads();
     return misc[1] == 0;
 }
 
@@ -637,11 +665,8 @@ __device__ __forceinline__ void cell_tile(const SweepArgs &a, const SweepSmem &s
 {
     const int tid = threadIdx.x;
     const float fnan = __int_as_float(0x7fffffff);
-    const int tw = tp.tw, th = tp.th;
-    const int ne = s.misc[buf * 4];
     const unsigned long long *bits = s.bits + buf * kFH;
-    const int nrow_items = th * 32;
-    const int nitems = (a.dbg & 4) ? 0 : nrow_items + ne;
+    const int nitems = (a.dbg & 4) ? 0 : s.misc[buf * 4 + 3];
     const double4 *st0 = s.st + buf * kFC;
     const double *rad0p = s.rrad + buf * kFC;
     // FP64 state / radius of record p: plane 0 in the copied frame, extras in their list
@@ -650,24 +675,11 @@ __device__ __forceinline__ void cell_tile(const SweepArgs &a, const SweepSmem &s
     auto rad_of = [&](int p) { return radii ? (p < kFC ? rad0p[p] : s.xrad[p - kFC]) : a.rad0; };
 #pragma unroll 1
     for (int w = tid; w < nitems; w += kTileThreads) {
-        // work item: a cell of the tile (its plane-0 disk), then the extras
-        int p, c, fx, fy;
-        if (w < nrow_items) {
-            fy = (w >> 5) + 1;
-            fx = (w & 31) + 1;
-            c = fy * kFW + fx;
-            p = c;
-            if (fx > tw) continue;
-        } else {
-            const int e = w - nrow_items;
-            c = s.ecell[e];
-            fy = c / kFW;
-            fx = c - fy * kFW;
-            p = kFC + e;
-            if (fx < 1 || fx > tw || fy < 1 || fy > th) continue;   // an extra of the ring
-        }
+        // work item: a particle of the tile (plane 0 of a cell, or an extra), from the compacted list
+        const int p = s.items[w];
+        const int c = p < kFC ? p : s.ecell[p - kFC];
+        const int fy = (c * 241) >> 13, fx = c - fy * kFW;
         const int id = s.id[p];
-        if (id < 0 || id >= a.n_owned) continue;   // empty cell; halo copy from a neighbouring slab: never predicted
         const float4 own = s.scr[p];
         // dx = rx_j - (rx_i - k csx), k = column(j) - column(i) in {-1, 0, 1}
         const float pxs[3] = {__fadd_rn(own.x, K.csx), own.x, __fsub_rn(own.x, K.csx)};
@@ -853,7 +865,7 @@ __device__ __forceinline__ void cell_worker(const SweepArgs &a, const SweepSmem 
         if (next < ntiles && tid < 32) frame_issue(a, s, tile_pos(a.tg, next), buf ^ 1, radii);
         // the other set of lists (of the previous tile) goes back to empty for the next one
         if (tid >= 32 && tid < 32 + kFH) s.bits[(buf ^ 1) * kFH + tid - 32] = 0ull;
-        if (tid >= 62 && tid < 64) s.misc[(buf ^ 1) * 4 + tid - 62] = 0;
+        if (tid >= 60 && tid < 64) s.misc[(buf ^ 1) * 4 + tid - 60] = 0;
         cell_tile<TWO>(a, s, tp, buf, radii, K);
         if (stamp && it < 6) edmd_stamp(a.ts, 19 + 4 * it);
         it++;

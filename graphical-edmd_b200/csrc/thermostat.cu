@@ -70,26 +70,7 @@ k_kinetic_final(int n, double T, const double *__restrict__ partial, double *__r
     }
 }
 
-// `p->vx /= sqrt(E/N/T); p->vy /= sqrt(E/N/T);` :4899-4900, and the new largest |component|
-// for the lean sweep's error model
-__global__ void __launch_bounds__(kThreads)
-k_rescale(int n, const double *__restrict__ red, double4 *__restrict__ xv, int32_t *__restrict__ flags)
-{
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    const double s = red[3];
-    float vm = 0.0f;
-    if (i < n && s > 0) {
-        double4 p = xv[i];
-        p.z = __ddiv_rn(p.z, s);
-        p.w = __ddiv_rn(p.w, s);
-        xv[i] = p;
-        vm = __double2float_ru(fmax(fabs(p.z), fabs(p.w)));
-        if (!(vm == vm)) vm = __int_as_float(0x7f800000);
-    }
-    const unsigned vmb = __reduce_max_sync(0xffffffffu, (unsigned)__float_as_int(vm));
-    if ((threadIdx.x & 31) == 0 && vmb) atomicMax(reinterpret_cast<unsigned int *>(&flags[kFlagVmax]), vmb);
-}
-
+// addNoise's rescale (`p->vx /= sqrt(E/N/T)`, src/EDMD.c:4899-4900) and
 // normalizePhysicalQ (src/EDMD.c:5723-5764, the branch without a circular wall; unit masses):
 //   `vx -= px/(N*m); vy -= py/(N*m);`  then, with the E of the shifted velocities,  `vx /= sqrt(E/N/Einit)`.
 // shift = (dvx, dvy) subtracted first, then -- when divisor != 1 -- the division: the reference's two
@@ -111,7 +92,7 @@ k_shift_scale(int n, int n_total, double dvx, double dvy, double divisor, const 
         double4 p = xv[i];
         p.z = __dsub_rn(p.z, dvx);
         p.w = __dsub_rn(p.w, dvy);
-        if (divisor != 1.0) {
+        if (divisor != 1.0 && divisor > 0) {   // (0: a system without kinetic energy / T <= 0: left alone)
             p.z = __ddiv_rn(p.z, divisor);
             p.w = __ddiv_rn(p.w, divisor);
         }
@@ -231,11 +212,10 @@ double *edmd_launch_kinetic_final(edmd_ctx *c, double T, double *scratch, int n_
     return out;
 }
 
+// `p->vx /= sqrt(E/N/T); p->vy /= sqrt(E/N/T);` (addNoise, src/EDMD.c:4899-4900) with the divisor red[3] of the
+// kinetic sums: the shift-and-scale kernel with a zero shift (x - 0.0 is x, bit for bit).  (A thread-per-particle
+// kernel for this took 29.8 us at N = 10^6 against 12.9 us for the grid-stride form: ncu, profiles/r2m_ncu_misc.json.)
 int edmd_launch_rescale(edmd_ctx *c, const double *red)
 {
-    const int n = c->n_owned;
-    if (n == 0) return 0;
-    cudaMemsetAsync(c->flags + kFlagVmax, 0, sizeof(int32_t), c->stream);
-    k_rescale<<<(n + kThreads - 1) / kThreads, kThreads, 0, c->stream>>>(n, red, c->xv, c->flags);
-    return 1;
+    return edmd_launch_shift_scale(c, 0.0, 0.0, 1.0, red, true, c->n_owned, nullptr);
 }

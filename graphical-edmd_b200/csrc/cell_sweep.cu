@@ -1239,13 +1239,15 @@ static PartArgs part_args(edmd_ctx *c, int first, int n)
 // partition begun with edmd_tile_begin_partition
 int edmd_launch_tile_partition_range(edmd_ctx *c, int first, int n, bool beside)
 {
-    if (n <= 0) return 0;
+    // (n == 0, a slab that owns nothing at the moment: the kernel still runs -- one block -- because its first
+    // thread resets the sweep's overlap report and tile counter)
+    if (n < 0) n = 0;
     PartArgs pa = part_args(c, first, n);
     pa.late_wait = beside ? 1 : 0;
     // normally the first kernel of its chain, launched plainly: whatever precedes it on the stream completes
     // first.  `beside`: behind the halo kernels of the fused exchange, with the programmatic attribute
-    edmd_launch(k_cell_partition, dim3((n + kPartThreads - 1) / kPartThreads), dim3(kPartThreads), 0, c->stream,
-                beside, pa);
+    edmd_launch(k_cell_partition, dim3(n > 0 ? (n + kPartThreads - 1) / kPartThreads : 1), dim3(kPartThreads), 0,
+                c->stream, beside, pa);
     return 1;
 }
 

@@ -1351,3 +1351,26 @@ def test_pcf_g_r_alone_and_slab_rejection(pkg, oracle):
         cnt = np.zeros(want["num_bins"], np.uint64)
         rc = sl.lib.edmd_cuda_pcf(sl._h, 0.1, 9.0, cnt.ctypes.data_as(C.c_void_p), None, C.byref(nb))
         assert rc == pkg.binding.ESTATE
+
+
+@pytest.mark.gpu
+def test_multi_gpu_entry_with_an_empty_slab(pkg, oracle):
+    """All particles in one corner of the box: the third of three slabs owns nothing (its sweep still has to
+    keep the cell counters of its rows clean for the tick in which particles arrive there)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    rng = np.random.default_rng(79)
+    lx, ly, n = 400.0, 300.0, 6000
+    side = int(np.ceil(np.sqrt(n)))
+    k = np.arange(n)
+    x = 1.0 + 2.05 * (k % side) + 0.02 * rng.random(n)
+    y = 1.0 + 2.05 * (k // side) + 0.02 * rng.random(n)
+    c = dict(n=n, lx=lx, ly=ly, x=x, y=y, vx=rng.standard_normal(n), vy=rng.standard_normal(n), rad=np.ones(n))
+    with pkg.EdmdMg(n, lx, ly, [j % ndev for j in range(3)]) as mg:
+        for tick in range(3):
+            mg.upload(c["x"], c["y"], c["vx"], c["vy"], c["rad"], t=0.5 * tick)
+            assert mg.slab_sizes[2] == 0 or tick == 2
+            assert_events_equal(mg.predict_all(), oracle_sweep(oracle, c, t=0.5 * tick))
+            if tick == 1:   # for the last tick the blob moves up: the empty slab gets particles
+                c = dict(c, y=np.mod(c["y"] + 130.0, ly))
+        assert mg.slab_sizes[2] > 0

@@ -9,7 +9,14 @@
 //     vr    double [N]   growth rates (GROW mode only)
 //     cid   int32  [N]   PADDED cell id  Y*PS + X + 1,  PS = nx + 3 rounded up to 4
 //
-//   cell index, rebuilt by every sweep (K0).  The reference's intrusive linked
+//   cell index of the DEFAULT sweep (one or two radius classes, cell_sweep.cu): slot planes over the padded
+//   grid, rebuilt by every sweep -- plane s = the s-th arrival of every cell:
+//     pst   double4[kSlotK][ny*PS]   FP64 states        pid  int32[kSlotK][ny*PS]   ids (planes 1.. only)
+//     prad  double [kSlotK][ny*PS]   radii (only when not all equal)
+//     ccnt  uint64 [2][ny*PS]        cell words: count << 32 | sum of ids, double-buffered
+//     evrec edmd_ev32[N]             one 32-byte event record per particle id
+//
+//   cell index of the GENERAL path, rebuilt by every sweep (K0).  The reference's intrusive linked
 //   cell list (src/EDMD.c:1906-1920, 2053-2078) becomes a counting sort over a
 //   PADDED grid: every row of cells carries a left ghost cell (copy of cell
 //   nx-1), the nx real cells, a right ghost cell (copy of cell 0) and 1..4 empty

@@ -44,8 +44,6 @@
 #include "pairmath.cuh"
 #include "halo.cuh"
 #include "rowstage.cuh"
-#include <stdio.h>
-#include <stdlib.h>
 
 namespace {
 
@@ -1207,17 +1205,21 @@ static int sweep_ecap(const edmd_ctx *c)
 // CTAs of the persistent sweep kernel: as many as are resident at once (asked of the runtime: a worker that
 // had to wait for a free slot would begin its first tile when the others are through), at most one per tile
 static void tile_attrs();
-static int sweep_workers(const edmd_ctx *c)
+static int sweep_workers(edmd_ctx *c)
 {
     const int ntiles = c->tgeom.ntiles;
-    const size_t smem = sweep_smem_bytes(sweep_ecap(c), c->lean_two ? 1 : 0);
-    tile_attrs();
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cell_sweep, kTileThreads, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    if (getenv("EDMD_DEBUG_WORKERS")) fprintf(stderr, "k_cell_sweep: %zu bytes of shared memory, %d CTAs per SM\n", smem, per_sm);
+    const int ecap = sweep_ecap(c), rad_smem = c->lean_two ? 1 : 0;
+    if (c->workers_key != ecap * 2 + rad_smem) {   // (asked once per shape: the query costs microseconds of host time)
+        const size_t smem = sweep_smem_bytes(ecap, rad_smem);
+        tile_attrs();
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cell_sweep, kTileThreads, smem) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        c->workers_per_sm = per_sm;
+        c->workers_key = ecap * 2 + rad_smem;
+    }
     const int sms = c->sm_count > 0 ? c->sm_count : 148;
-    return ntiles < sms * per_sm ? ntiles : sms * per_sm;
+    return ntiles < sms * c->workers_per_sm ? ntiles : sms * c->workers_per_sm;
 }
 
 static PartArgs part_args(edmd_ctx *c, int first, int n)

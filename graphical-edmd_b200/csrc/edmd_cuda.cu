@@ -287,6 +287,8 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
         if ((r = dev_alloc(c, &c->evrec, N + 32))) return r;
         CU(cudaMemsetAsync(c->ccnt, 0, (2 * ncp + 32) * sizeof(unsigned long long), c->stream));
         c->cbuf = 0;
+        c->workers_key = -1;
+        c->workers_per_sm = 1;
     }
     if ((r = dev_alloc(c, &c->t_cross, N))) return r;
     if ((r = dev_alloc(c, &c->t_coll, N))) return r;

@@ -239,6 +239,7 @@ struct edmd_ctx {
     double *prad;                    // ... and radii (written only when the radii are not all exactly rad0)
     unsigned long long *ccnt;        // [2][ncp] cell words (count << 32 | sum of ids), double-buffered (consumers zero the other buffer)
     int cbuf;                        // the buffer of the current partition
+    int workers_key, workers_per_sm; // resident CTAs of the sweep kernel per SM for (extras capacity, radii): asked of the runtime once
     bool boop_tile_off;              // EDMD_OPT_NO_TILE_BOOP
     double4 *boop_rec;               // psi6 records of the tile kernel: two sectors per particle id
     edmd_ev32 *evrec;                 // event records of the last tile sweep, by particle id

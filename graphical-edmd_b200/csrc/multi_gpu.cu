@@ -28,7 +28,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "edmd_internal.cuh"
@@ -51,6 +53,7 @@ struct edmd_mg {
     };
     std::vector<Stage> st;
     bool have_state;
+    bool whole;   // ndev == 1: one ordinary whole-system context (a slab needs at least two rows of somebody else)
     double t;
     char err[512];
 };
@@ -68,6 +71,24 @@ template <typename T>
 bool pin(T **p, size_t n)
 {
     return cudaHostAlloc(reinterpret_cast<void **>(p), (n ? n : 1) * sizeof(T), cudaHostAllocPortable) == cudaSuccess;
+}
+
+// f(part, nparts) on `nparts` host threads (the caller's included).  The dealing of the particles to the slabs,
+// the scatter of the slabs' outputs and the per-device uploads / fetches are memory- or PCIe-bound loops over the
+// whole system: one thread would make the multi-GPU tick slower than the single-GPU one.
+template <class F>
+void parallel_parts(int nparts, F f)
+{
+    std::vector<std::thread> th;
+    for (int t = 1; t < nparts; t++) th.emplace_back([&f, t, nparts] { f(t, nparts); });
+    f(0, nparts);
+    for (auto &x : th) x.join();
+}
+
+int host_threads()
+{
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc < 2 ? 1 : (hc > 16 ? 16 : (int)hc);
 }
 
 void free_stage(edmd_mg::Stage &s)
@@ -136,6 +157,18 @@ int edmd_cuda_create_mg(int ndev, const int *devices, int n, double lx, double l
         delete m;
         return EDMD_EINVAL;   // the decomposition needs Nycells >= 3 per slab
     }
+    m->whole = ndev == 1;
+    if (m->whole) {
+        const int rc1 = edmd_cuda_create(devices[0], n, lx, ly, &m->ctx[0]);
+        if (rc1) {
+            edmd_cuda_destroy_mg(m);
+            return rc1;
+        }
+        edmd_cuda_get_box(m->ctx[0], &m->box);
+        m->st[0].n = 0;
+        *out = m;
+        return 0;
+    }
     m->owner_of_row.resize(ny);
     const double per_row = (double)n / ny;
     m->halo_cap = (int)(per_row * 1.5) + 1024;
@@ -189,11 +222,22 @@ int edmd_cuda_mg_upload(edmd_mg *m, const double *x, const double *y, const doub
 {
     if (!m) return EDMD_EINVAL;
     if (m->n > 0 && (!x || !y || !vx || !vy || !rad)) return mg_fail(m, EDMD_EINVAL, "mg_upload: null array");
-    const int ny = m->box.nycells, nx = m->box.nxcells;
-    for (auto &s : m->st) s.n = 0;
-    // deal the particles to the slabs by the row they are filed under
-    for (int i = 0; i < m->n; i++) {
-        int cx, cy;
+    if (m->whole) {
+        const int rc = edmd_cuda_upload(m->ctx[0], x, y, vx, vy, rad, cell_xy, t);
+        if (rc) return mg_fail(m, rc, "mg_upload", m->ctx[0]);
+        m->st[0].n = m->n;
+        m->have_state = true;
+        m->t = t;
+        return 0;
+    }
+    const int ny = m->box.nycells, nx = m->box.nxcells, nd = m->ndev, N = m->n;
+    // Deal the particles to the slabs by the row they are filed under, in ascending particle id inside every
+    // slab, on several host threads: thread p counts its range per slab, a prefix over (thread, slab) gives every
+    // thread its first slot in every slab, then every thread files its range.
+    const int P = host_threads();
+    std::vector<int> cnt((size_t)P * nd, 0);
+    std::atomic<int> bad(0);
+    auto cell_of = [&](int i, int &cx, int &cy) {
         if (cell_xy) {
             cx = cell_xy[2 * i];
             cy = cell_xy[2 * i + 1];
@@ -201,19 +245,50 @@ int edmd_cuda_mg_upload(edmd_mg *m, const double *x, const double *y, const doub
             cx = (int)(x[i] * m->box.cellx_fac);
             cy = (int)(y[i] * m->box.celly_fac);
         }
-        if (cx < 0 || cx >= nx || cy < 0 || cy >= ny) return mg_fail(m, EDMD_ECELL, "mg_upload: a particle's cell lies outside the cell grid");
-        edmd_mg::Stage &s = m->st[m->owner_of_row[cy]];
-        if (s.n >= s.cap - 2 * m->halo_cap) return mg_fail(m, EDMD_EINVAL, "mg_upload: a slab holds more particles than its capacity (very uneven density)");
-        const int k = s.n++;
-        s.x[k] = x[i]; s.y[k] = y[i]; s.vx[k] = vx[i]; s.vy[k] = vy[i]; s.rad[k] = rad[i];
-        s.cells[2 * k] = cx; s.cells[2 * k + 1] = cy;
-        s.gid[k] = i;
+        return cx >= 0 && cx < nx && cy >= 0 && cy < ny;
+    };
+    parallel_parts(P, [&](int p, int np) {
+        const int lo = (int)((long long)N * p / np), hi = (int)((long long)N * (p + 1) / np);
+        std::vector<int> mine(nd, 0);   // (thread-local: neighbouring threads' counters would share cache lines)
+        for (int i = lo; i < hi; i++) {
+            int cx, cy;
+            if (!cell_of(i, cx, cy)) { bad = 1; continue; }
+            mine[m->owner_of_row[cy]]++;
+        }
+        for (int k = 0; k < nd; k++) cnt[(size_t)p * nd + k] = mine[k];
+    });
+    if (bad) return mg_fail(m, EDMD_ECELL, "mg_upload: a particle's cell lies outside the cell grid");
+    std::vector<int> base((size_t)P * nd, 0);
+    for (int k = 0; k < nd; k++) {
+        int run = 0;
+        for (int p = 0; p < P; p++) {
+            base[(size_t)p * nd + k] = run;
+            run += cnt[(size_t)p * nd + k];
+        }
+        if (run > m->st[k].cap - 2 * m->halo_cap) return mg_fail(m, EDMD_EINVAL, "mg_upload: a slab holds more particles than its capacity (very uneven density)");
+        m->st[k].n = run;
     }
-    for (int k = 0; k < m->ndev; k++) {
+    parallel_parts(P, [&](int p, int np) {
+        const int lo = (int)((long long)N * p / np), hi = (int)((long long)N * (p + 1) / np);
+        std::vector<int> pos(base.begin() + (size_t)p * nd, base.begin() + (size_t)(p + 1) * nd);   // thread-local cursors
+        for (int i = lo; i < hi; i++) {
+            int cx, cy;
+            cell_of(i, cx, cy);
+            edmd_mg::Stage &s = m->st[m->owner_of_row[cy]];
+            const int k = pos[m->owner_of_row[cy]]++;
+            s.x[k] = x[i]; s.y[k] = y[i]; s.vx[k] = vx[i]; s.vy[k] = vy[i]; s.rad[k] = rad[i];
+            s.cells[2 * k] = cx; s.cells[2 * k + 1] = cy;
+            s.gid[k] = i;
+        }
+    });
+    // one host thread per device: the copies of the slabs run side by side on the devices' own PCIe links
+    std::vector<int> rcs(nd, 0);
+    parallel_parts(nd, [&](int k, int) {
         const edmd_mg::Stage &s = m->st[k];
-        const int rc = edmd_cuda_upload_owned(m->ctx[k], s.n, s.x, s.y, s.vx, s.vy, s.rad, s.cells, s.gid, t);
-        if (rc) return mg_fail(m, rc, "mg_upload (slab upload)", m->ctx[k]);
-    }
+        rcs[k] = edmd_cuda_upload_owned(m->ctx[k], s.n, s.x, s.y, s.vx, s.vy, s.rad, s.cells, s.gid, t);
+    });
+    for (int k = 0; k < nd; k++)
+        if (rcs[k]) return mg_fail(m, rcs[k], "mg_upload (slab upload)", m->ctx[k]);
     m->have_state = true;
     m->t = t;
     return 0;
@@ -226,19 +301,54 @@ int edmd_cuda_mg_predict_all(edmd_mg *m, int mode, double *t_cross, uint8_t *dir
     if (mode != EDMD_MODE_NORMAL) return mg_fail(m, EDMD_EINVAL, "mg_predict_all: NORMAL mode only (the growth sweep is a single-GPU setup step)");
     if (!m->have_state) return mg_fail(m, EDMD_ESTATE, "mg_predict_all before mg_upload");
     if (overlap_pair) overlap_pair[0] = overlap_pair[1] = -1;
+    if (m->whole) {
+        const int rc = edmd_cuda_predict_all(m->ctx[0], mode, nullptr, t_cross, dir, t_coll, partner, ctype, overlap_pair);
+        if (rc) mg_fail(m, rc, "mg_predict_all", m->ctx[0]);
+        return rc;
+    }
     // every device is launched before any is waited for: the slabs run side by side, their halo
     // kernels meet over NVLink
     for (int k = 0; k < m->ndev; k++) {
         const int rc = edmd_cuda_exchange_predict_device(m->ctx[k], mode);
         if (rc) return mg_fail(m, rc, "mg_predict_all (exchange + sweep)", m->ctx[k]);
     }
+    // one host thread per device fetches its slab's outputs (pinned staging) and scatters them by particle id
+    std::vector<int> rcs(m->ndev, 0);
+    std::vector<int32_t> ovs(2 * (size_t)m->ndev, -1);
+    parallel_parts(m->ndev, [&](int k, int) {
+        edmd_mg::Stage &s = m->st[k];
+        rcs[k] = edmd_cuda_fetch_predictions(m->ctx[k], s.t_cross, s.dir, s.t_coll, s.partner, nullptr, &ovs[2 * k]);
+    });
+    // Scatter by RANGES OF PARTICLE IDS: thread p writes the outputs of ids [lo, hi) from every slab (a slab lists
+    // its ids in ascending order: binary search for lo).  Scattering slab by slab on one thread each had two
+    // threads write neighbouring elements of the same cache lines (ids are dealt to the slabs at random): 7-26 ms
+    // instead of ~1 ms at N = 2*10^6.
+    parallel_parts(host_threads(), [&](int p, int np) {
+        const int lo = (int)((long long)m->n * p / np), hi = (int)((long long)m->n * (p + 1) / np);
+        for (int k = 0; k < m->ndev; k++) {
+            if (rcs[k] && rcs[k] != EDMD_EOVERLAP) continue;
+            const edmd_mg::Stage &s = m->st[k];
+            int a = 0, b = s.n;
+            while (a < b) {   // first j with gid[j] >= lo
+                const int mid = (a + b) / 2;
+                if (s.gid[mid] < lo) a = mid + 1;
+                else b = mid;
+            }
+            for (int j = a; j < s.n && s.gid[j] < hi; j++) {
+                const int i = s.gid[j];
+                if (t_cross) t_cross[i] = s.t_cross[j];
+                if (dir) dir[i] = s.dir[j];
+                if (t_coll) t_coll[i] = s.t_coll[j];
+                if (partner) partner[i] = s.partner[j];
+                if (ctype) ctype[i] = EDMD_EV_COLLISION;
+            }
+        }
+    });
     int result = 0;
     for (int k = 0; k < m->ndev; k++) {
-        edmd_mg::Stage &s = m->st[k];
-        int32_t ov[2] = {-1, -1};
-        const int rc = edmd_cuda_fetch_predictions(m->ctx[k], s.t_cross, s.dir, s.t_coll, s.partner, nullptr, ov);
-        if (rc == EDMD_EOVERLAP) {
+        if (rcs[k] == EDMD_EOVERLAP) {
             // the FIRST overlapping pair in sweep order = the smallest (i, j) over the slabs
+            const int32_t *ov = &ovs[2 * k];
             if (overlap_pair && (result != EDMD_EOVERLAP || ov[0] < overlap_pair[0] ||
                                  (ov[0] == overlap_pair[0] && ov[1] < overlap_pair[1]))) {
                 overlap_pair[0] = ov[0];
@@ -246,16 +356,8 @@ int edmd_cuda_mg_predict_all(edmd_mg *m, int mode, double *t_cross, uint8_t *dir
             }
             result = EDMD_EOVERLAP;
             snprintf(m->err, sizeof(m->err), "mg_predict_all: %s", edmd_cuda_last_error(m->ctx[k]));
-        } else if (rc) {
-            return mg_fail(m, rc, "mg_predict_all (fetch)", m->ctx[k]);
-        }
-        for (int j = 0; j < s.n; j++) {
-            const int i = s.gid[j];
-            if (t_cross) t_cross[i] = s.t_cross[j];
-            if (dir) dir[i] = s.dir[j];
-            if (t_coll) t_coll[i] = s.t_coll[j];
-            if (partner) partner[i] = s.partner[j];
-            if (ctype) ctype[i] = EDMD_EV_COLLISION;
+        } else if (rcs[k]) {
+            return mg_fail(m, rcs[k], "mg_predict_all (fetch)", m->ctx[k]);
         }
     }
     return result;
@@ -266,6 +368,11 @@ int edmd_cuda_mg_boop_cutoff(edmd_mg *m, double r_c, double *q5, double *q6, dou
 {
     if (!m) return EDMD_EINVAL;
     if (!m->have_state) return mg_fail(m, EDMD_ESTATE, "mg_boop_cutoff before mg_upload");
+    if (m->whole) {
+        const int rc = edmd_cuda_boop_cutoff(m->ctx[0], r_c, q5, q6, q7, q6_arg, neighbors, mean_q6);
+        if (rc) mg_fail(m, rc, "mg_boop_cutoff", m->ctx[0]);
+        return rc;
+    }
     // the halo rows must match the resident state: exchange them (peer stores; asynchronous)
     for (int k = 0; k < m->ndev; k++) {
         const int rc = edmd_cuda_halo_exchange(m->ctx[k]);

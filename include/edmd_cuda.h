@@ -251,7 +251,8 @@ int edmd_cuda_pcf_device(edmd_ctx *ctx, const double *xy_dev, int n_total, doubl
  * (row slabs as above, halo by peer stores over NVLink -- peer access between the devices of the
  * process, no IPC) and takes / returns WHOLE-SYSTEM host arrays indexed by particle id.  The same
  * device may be listed more than once (several slabs on one GPU: how the tests run without a second
- * GPU).  Needs Nycells >= 3 * ndev.  One host thread per edmd_mg, like an edmd_ctx. */
+ * GPU).  Needs Nycells >= 3 * ndev; ndev == 1 is an ordinary whole-system context behind the same calls.
+ * One host thread per edmd_mg, like an edmd_ctx. */
 typedef struct edmd_mg edmd_mg;
 int edmd_cuda_create_mg(int ndev, const int *devices, int n, double lx, double ly, edmd_mg **out);
 void edmd_cuda_destroy_mg(edmd_mg *mg);

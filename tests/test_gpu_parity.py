@@ -1293,7 +1293,7 @@ def test_device_normalize_then_sweep_matches_oracle(pkg, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nslabs,n,phi,sf", [(2, 60000, 0.70, 0.0), (3, 150000, 0.72, 0.0), (4, 1000000, 0.70, 0.0),
+@pytest.mark.parametrize("nslabs,n,phi,sf", [(1, 30000, 0.70, 0.0), (2, 60000, 0.70, 0.0), (3, 150000, 0.72, 0.0), (4, 1000000, 0.70, 0.0),
                                              (2, 40000, 0.55, 0.3)])
 def test_multi_gpu_c_entry_matches_oracle(pkg, oracle, nslabs, n, phi, sf):
     """edmd_cuda_create_mg (csrc/multi_gpu.cu): the single-GPU interface over several slab contexts --

@@ -91,6 +91,30 @@ int host_threads()
     return hc < 2 ? 1 : (hc > 16 ? 16 : (int)hc);
 }
 
+// Scatter the slabs' per-particle outputs into whole-system arrays BY RANGES OF PARTICLE IDS: thread p handles
+// the ids [lo, hi) of every slab whose `ok` is set (a slab lists its ids in ascending order: binary search for lo).
+// write(stage, j, i): element j of the slab's staging is particle i.  Scattering slab by slab on one thread each
+// had the threads write neighbouring elements of the same cache lines (ids are dealt to the slabs at random):
+// 7-26 ms instead of ~1 ms at N = 2*10^6.
+template <class W>
+void scatter_by_id_ranges(const edmd_mg *m, const std::vector<char> &ok, W write)
+{
+    parallel_parts(host_threads(), [&](int p, int np) {
+        const int lo = (int)((long long)m->n * p / np), hi = (int)((long long)m->n * (p + 1) / np);
+        for (int k = 0; k < m->ndev; k++) {
+            if (!ok[k]) continue;
+            const edmd_mg::Stage &s = m->st[k];
+            int a = 0, b = s.n;
+            while (a < b) {   // first j with gid[j] >= lo
+                const int mid = (a + b) / 2;
+                if (s.gid[mid] < lo) a = mid + 1;
+                else b = mid;
+            }
+            for (int j = a; j < s.n && s.gid[j] < hi; j++) write(s, j, s.gid[j]);
+        }
+    });
+}
+
 void free_stage(edmd_mg::Stage &s)
 {
     void *ps[] = {s.x, s.y, s.vx, s.vy, s.rad, s.t_cross, s.t_coll, s.q[0], s.q[1], s.q[2], s.q[3],
@@ -319,30 +343,14 @@ int edmd_cuda_mg_predict_all(edmd_mg *m, int mode, double *t_cross, uint8_t *dir
         edmd_mg::Stage &s = m->st[k];
         rcs[k] = edmd_cuda_fetch_predictions(m->ctx[k], s.t_cross, s.dir, s.t_coll, s.partner, nullptr, &ovs[2 * k]);
     });
-    // Scatter by RANGES OF PARTICLE IDS: thread p writes the outputs of ids [lo, hi) from every slab (a slab lists
-    // its ids in ascending order: binary search for lo).  Scattering slab by slab on one thread each had two
-    // threads write neighbouring elements of the same cache lines (ids are dealt to the slabs at random): 7-26 ms
-    // instead of ~1 ms at N = 2*10^6.
-    parallel_parts(host_threads(), [&](int p, int np) {
-        const int lo = (int)((long long)m->n * p / np), hi = (int)((long long)m->n * (p + 1) / np);
-        for (int k = 0; k < m->ndev; k++) {
-            if (rcs[k] && rcs[k] != EDMD_EOVERLAP) continue;
-            const edmd_mg::Stage &s = m->st[k];
-            int a = 0, b = s.n;
-            while (a < b) {   // first j with gid[j] >= lo
-                const int mid = (a + b) / 2;
-                if (s.gid[mid] < lo) a = mid + 1;
-                else b = mid;
-            }
-            for (int j = a; j < s.n && s.gid[j] < hi; j++) {
-                const int i = s.gid[j];
-                if (t_cross) t_cross[i] = s.t_cross[j];
-                if (dir) dir[i] = s.dir[j];
-                if (t_coll) t_coll[i] = s.t_coll[j];
-                if (partner) partner[i] = s.partner[j];
-                if (ctype) ctype[i] = EDMD_EV_COLLISION;
-            }
-        }
+    std::vector<char> ok(m->ndev);
+    for (int k = 0; k < m->ndev; k++) ok[k] = rcs[k] == 0 || rcs[k] == EDMD_EOVERLAP;
+    scatter_by_id_ranges(m, ok, [&](const edmd_mg::Stage &s, int j, int i) {
+        if (t_cross) t_cross[i] = s.t_cross[j];
+        if (dir) dir[i] = s.dir[j];
+        if (t_coll) t_coll[i] = s.t_coll[j];
+        if (partner) partner[i] = s.partner[j];
+        if (ctype) ctype[i] = EDMD_EV_COLLISION;
     });
     int result = 0;
     for (int k = 0; k < m->ndev; k++) {
@@ -378,22 +386,25 @@ int edmd_cuda_mg_boop_cutoff(edmd_mg *m, double r_c, double *q5, double *q6, dou
         const int rc = edmd_cuda_halo_exchange(m->ctx[k]);
         if (rc) return mg_fail(m, rc, "mg_boop_cutoff (halo exchange)", m->ctx[k]);
     }
+    // one host thread per device: the slabs' psi6 kernels run side by side
+    std::vector<int> rcs(m->ndev, 0);
+    std::vector<double> means(m->ndev, 0.0);
+    parallel_parts(m->ndev, [&](int k, int) {
+        edmd_mg::Stage &s = m->st[k];
+        rcs[k] = edmd_cuda_boop_cutoff(m->ctx[k], r_c, s.q[0], s.q[1], s.q[2], s.q[3], s.nb, &means[k]);
+    });
     double sum = 0.0;
     for (int k = 0; k < m->ndev; k++) {
-        edmd_mg::Stage &s = m->st[k];
-        double mean = 0.0;
-        const int rc = edmd_cuda_boop_cutoff(m->ctx[k], r_c, s.q[0], s.q[1], s.q[2], s.q[3], s.nb, &mean);
-        if (rc) return mg_fail(m, rc, "mg_boop_cutoff", m->ctx[k]);
-        sum += mean * s.n;   // the slab's sum of q6 (its mean is sum / n_owned)
-        for (int j = 0; j < s.n; j++) {
-            const int i = s.gid[j];
-            if (q5) q5[i] = s.q[0][j];
-            if (q6) q6[i] = s.q[1][j];
-            if (q7) q7[i] = s.q[2][j];
-            if (q6_arg) q6_arg[i] = s.q[3][j];
-            if (neighbors) neighbors[i] = s.nb[j];
-        }
+        if (rcs[k]) return mg_fail(m, rcs[k], "mg_boop_cutoff", m->ctx[k]);
+        sum += means[k] * m->st[k].n;   // the slab's sum of q6 (its mean is sum / n_owned); added in slab order
     }
+    scatter_by_id_ranges(m, std::vector<char>(m->ndev, 1), [&](const edmd_mg::Stage &s, int j, int i) {
+        if (q5) q5[i] = s.q[0][j];
+        if (q6) q6[i] = s.q[1][j];
+        if (q7) q7[i] = s.q[2][j];
+        if (q6_arg) q6_arg[i] = s.q[3][j];
+        if (neighbors) neighbors[i] = s.nb[j];
+    });
     if (mean_q6) *mean_q6 = m->n > 0 ? sum / m->n : 0.0;
     return 0;
 }

@@ -941,8 +941,55 @@ struct BoopTileArgs {
     double rc2;
     double4 *rec;   // two 32-byte sectors per particle id: (q5, q6, q7, q6_arg), (neighbours, 0, 0, 0)
 };
+// atan2(y, x) to ~1e-14 absolute (the gate on q6_arg is 1e-10; CUDA's atan2 is an IEEE division plus a
+// 20-term polynomial): fold into the first octant, ONE rotation by -pi/4 when the angle is above pi/8
+// (hi + lo, lo - hi: the common factor sqrt(2) drops out of the quotient), the quotient from the MUFU
+// reciprocal seed + two Newton steps, atan(t) = t P(t^2) on |t| <= tan(pi/8) with a degree-8 interpolant
+// at Chebyshev nodes (max error 9.5e-15 in FP64 Horner form, profiles/tools/boop_model.py).
+__constant__ double kAtanC[9] = {0x1.fffffffffff0fp-1, -0x1.55555554e5fc5p-2, 0x1.99999911c1573p-3,
+                                 -0x1.2492291945813p-3, 0x1.c714d3e720df5p-4, -0x1.73d9cba10d56bp-4,
+                                 0x1.35ced8de982a2p-4, -0x1.e13ac280a9accp-5, 0x1.f657ae7e09908p-6};
+__device__ __forceinline__ double atan2_gate(double y, double x)
+{
+    const double ax = fabs(x), ay = fabs(y);
+    const double hi = fmax(ax, ay), lo = fmin(ax, ay);
+    const bool rot = lo > __dmul_rn(0.41421356237309503, hi);   // tan(pi/8)
+    const double h2 = rot ? __dadd_rn(hi, lo) : hi, l2 = rot ? __dsub_rn(lo, hi) : lo;
+    double r = rcp_seed(h2);
+    r = __fma_rn(r, __fma_rn(-h2, r, 1.0), r);
+    r = __fma_rn(r, __fma_rn(-h2, r, 1.0), r);
+    const double t = __dmul_rn(l2, r), u = __dmul_rn(t, t);
+    double p = kAtanC[8];   // (constant-bank operands of the multiply-adds: no registers, no moves per trip)
+#pragma unroll
+    for (int k = 7; k >= 0; k--) p = __fma_rn(p, u, kAtanC[k]);
+    double a = __dmul_rn(t, p);
+    a = rot ? __dadd_rn(a, 0.78539816339744831) : a;
+    a = ay > ax ? __dsub_rn(1.5707963267948966, a) : a;
+    a = x < 0.0 ? __dsub_rn(3.1415926535897931, a) : a;
+    a = h2 > 0.0 ? a : 0.0;   // atan2(0, 0) = 0
+    return copysign(a, y);
+}
+
+// v when mask == -1, +0.0 when mask == 0
+__device__ __forceinline__ double keep_bits(double v, int mask)
+{
+    return __hiloint2double(__double2hiint(v) & mask, __double2loint(v) & mask);
+}
+
+// 1/sqrt(x) for a positive, normal x: MUFU seed (~2^-20) + one third-order step y (1 + e/2 + 3 e^2/8),
+// e = 1 - x y^2: relative error ~ (5/16) e^3, below 2^-52 (five operations against eight for two Newton steps)
+__device__ __forceinline__ double rsqrt_gate(double x)
+{
+    const double y = rsqrt_seed(x);
+    const double e = __fma_rn(-__dmul_rn(x, y), y, 1.0);
+    return __fma_rn(y, __dmul_rn(__fma_rn(0.375, e, 0.5), e), y);
+}
+
 // psi6 of every particle of one tile (frame in shared memory).  The nine plane-0 neighbours sit at fixed
-// offsets of the frame array: nine unrolled visits, then the listed extras of the block.
+// offsets of the frame array: eight unrolled, BRANCH-FREE visits (an empty cell is a position 1e300 away; a
+// candidate beyond r_c contributes z = 0), so that the FP64 chains of different candidates overlap -- with a
+// branch per candidate the kernel waited on one dependent chain at a time (ncu: `wait` 3.3 stalls per issue,
+// FP64 pipe 55 % busy) -- then the listed extras of the block.
 template <bool WRAP>
 __device__ __forceinline__ void boop_tile(const BoopTileArgs &ba, const CellSmem &s, const TilePos &tp)
 {
@@ -973,8 +1020,11 @@ __device__ __forceinline__ void boop_tile(const BoopTileArgs &ba, const CellSmem
         const int id = s.id[p];
         if (id < 0 || id >= a.n_owned) continue;   // empty cell; halo copy from a neighbouring slab
         const double2 me = s.xy[p];
-        double s5r = 0, s5i = 0, s6r = 0, s6i = 0, s7r = 0, s7i = 0;
-        int nb = 0;
+        // sums: z^6, and A = sum Re(z) z^6, B = sum Im(z) z^6 -- with |z| = 1, z^7 + z^5 = 2 Re(z) z^6 and
+        // z^7 - z^5 = 2 i Im(z) z^6: sum7 = A + iB, sum5 = A - iB (four fused multiply-adds instead of two
+        // complex products and four additions)
+        double s6r = 0, s6i = 0, Ar = 0, Ai = 0, Br = 0, Bi = 0;
+        int nb = 0, npos = 0, nvis = 8;
         auto visit = [&](int q) {
             const double2 qq = s.xy[q];
             // the reference's own operations decide who is a neighbour (src/boop.c:78-84)
@@ -984,76 +1034,88 @@ __device__ __forceinline__ void boop_tile(const BoopTileArgs &ba, const CellSmem
                 dy = min_image(dy, half_ly, ly);
             }
             const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            if (r2 < rc2) {   // (false for the NaN position of an empty cell)
-                nb++;
-                // e^{ik theta} = ((dx + i dy)/r)^k, k = 5, 6, 7, by complex powers (fused multiply-adds:
-                // not parity-critical, gate 1e-10); 1/r from the MUFU seed + two Newton steps
-                double zr = 1.0, zi = 0.0;   // atan2(0,0) = 0 in the reference
-                if (r2 > 0) {
-                    double y = rsqrt_seed(r2);
-                    double e = __fma_rn(-__dmul_rn(r2, y), y, 1.0);
-                    y = __fma_rn(__dmul_rn(0.5, y), e, y);
-                    e = __fma_rn(-__dmul_rn(r2, y), y, 1.0);
-                    y = __fma_rn(__dmul_rn(0.5, y), e, y);
-                    zr = __dmul_rn(dx, y);
-                    zi = __dmul_rn(dy, y);
-                }
-                const double z2r = __fma_rn(zr, zr, -__dmul_rn(zi, zi)), z2i = __dmul_rn(__dadd_rn(zr, zr), zi);
-                const double z4r = __fma_rn(z2r, z2r, -__dmul_rn(z2i, z2i)), z4i = __dmul_rn(__dadd_rn(z2r, z2r), z2i);
-                const double z6r = __fma_rn(z4r, z2r, -__dmul_rn(z4i, z2i)), z6i = __fma_rn(z4r, z2i, __dmul_rn(z4i, z2r));
-                // |z| = 1: z^5 = z^6 conj(z), z^7 = z^6 z
-                s5r += __fma_rn(z6r, zr, __dmul_rn(z6i, zi));
-                s5i += __fma_rn(z6i, zr, -__dmul_rn(z6r, zi));
-                s6r += z6r;
-                s6i += z6i;
-                s7r += __fma_rn(z6r, zr, -__dmul_rn(z6i, zi));
-                s7i += __fma_rn(z6r, zi, __dmul_rn(z6i, zr));
+            const bool in = r2 < rc2;          // (false for an empty cell, a NaN coordinate)
+            const bool pos = in && r2 > 0.0;
+            nb += in ? 1 : 0;
+            npos += pos ? 1 : 0;   // (nb - npos coincident disks: atan2(0, 0) = 0 in the reference, z = 1, added at the end)
+            // e^{ik theta} = ((dx + i dy)/r)^k by complex powers (fused multiply-adds: not parity-critical,
+            // gate 1e-10).  Everything is computed for every candidate; one out of range gets 1/r = 0, so z = 0.
+            // (Masks on the bits, not `pos ? y : 0.0`: the compiler turns the latter into a branch around the powers.)
+            const int keep = pos ? -1 : 0;
+            const double y = keep_bits(rsqrt_gate(r2), keep);
+            if (WRAP) {   // (the variant that also takes states with NaN / infinite coordinates: 0 * NaN)
+                dx = keep_bits(dx, keep);
+                dy = keep_bits(dy, keep);
             }
+            const double zr = __dmul_rn(dx, y), zi = __dmul_rn(dy, y);
+            // |z| = 1: z^2 = (2 zr^2 - 1, 2 zr zi), z^4 likewise from z^2 (three operations each instead of four).
+            // For z = 0 this chain gives z^6 = -1: sum6 collects -1 per candidate out of range (put back at the
+            // end, nvis counts the visits), A and B collect 0 * (-1).
+            const double tr = __dadd_rn(zr, zr);
+            const double z2r = __fma_rn(tr, zr, -1.0), z2i = __dmul_rn(tr, zi);
+            const double t2 = __dadd_rn(z2r, z2r);
+            const double z4r = __fma_rn(t2, z2r, -1.0), z4i = __dmul_rn(t2, z2i);
+            const double z6r = __fma_rn(z4r, z2r, -__dmul_rn(z4i, z2i));
+            const double z6i = __fma_rn(z4r, z2i, __dmul_rn(z4i, z2r));
+            s6r = __dadd_rn(s6r, z6r);
+            s6i = __dadd_rn(s6i, z6i);
+            Ar = __fma_rn(zr, z6r, Ar);
+            Ai = __fma_rn(zr, z6i, Ai);
+            Br = __fma_rn(zi, z6r, Br);
+            Bi = __fma_rn(zi, z6i, Bi);
         };
-        // scan order: rows, cells, ascending particle id inside a cell (plane 0 holds the smallest id of a cell,
-        // its extras follow in ascending id): the sums run in one fixed order
+        // Visit order: the eight plane-0 neighbours at their fixed offsets (unrolled, branch-free), the plane-0 disk of
+        // the own cell when the particle is an extra, then the extras of the block by rows and cells in ascending
+        // particle id: one fixed order, so every output bit is reproducible (not the reference's order of
+        // additions: the gate is 1e-10)
         unsigned xm = 0;
 #pragma unroll
         for (int j = 0; j < 3; j++) xm |= ((unsigned)(s.bits[fy + j - 1] >> (fx - 1)) & 7u) << (3 * j);
-        if (xm == 0 && p < kFC) {
-            // (nearly always) no extras around and a plane-0 particle: nine fixed offsets, the centre is itself
 #pragma unroll
-            for (int b = 0; b < 9; b++)
-                if (b != 4) visit(c + (b / 3 - 1) * kFW + (b % 3 - 1));
-        } else {
+        for (int b = 0; b < 9; b++)
+            if (b != 4) visit(c + (b / 3 - 1) * kFW + (b % 3 - 1));
+        if (p >= kFC) {   // `p2->num != p1->num`: an extra sees the plane-0 disk of its own cell
+            visit(c);
+            nvis++;
+        }
 #pragma unroll 1
-            for (int b = 0; b < 9; b++) {
-                const int j = (b * 11) >> 5, k = b - 3 * j;
-                const int q = c + (j - 1) * kFW + (k - 1);
-                if (q != p) visit(q);   // `p2->num != p1->num`
-                if ((xm >> b) & 1u) {
-                    const unsigned info = s.xinfo[q];
-                    const int q0 = kFC + (info & 0xfff), qn = info >> 12;
+        while (xm) {
+            const int b = __ffs(xm) - 1;
+            xm &= xm - 1;
+            const int j = (b * 11) >> 5, k = b - 3 * j;
+            const unsigned info = s.xinfo[c + (j - 1) * kFW + (k - 1)];
+            const int q0 = kFC + (info & 0xfff), qn = info >> 12;
 #pragma unroll 1
-                    for (int e = q0; e < q0 + qn; e++)
-                        if (e != p) visit(e);
+            for (int e = q0; e < q0 + qn; e++)
+                if (e != p) {
+                    visit(e);
+                    nvis++;
                 }
-            }
         }
         double q5 = 0.0, q6 = 0.0, q7 = 0.0, arg = 0.0;
         if (nb > 0) {
-            // 1/n: exact reciprocals are not needed (gate 1e-10); |sum| = m2 * rsqrt(m2) with two Newton steps
-            // instead of an IEEE square root (no overflow: |sum| <= n)
-            const double inv_n = __drcp_rn((double)nb);
+            // coincident disks count as z = 1 in all three sums; sum6 gets back the -1 of every visit that was
+            // not a neighbour at a distance (nvis - (nb - nzero) of them)
+            const int nzero = nb - npos;
+            const double nz = (double)nzero;
+            s6r = __dadd_rn(s6r, (double)(nvis - npos + nzero));
+            const double s5r = __dadd_rn(__dadd_rn(Ar, Bi), nz), s5i = __dsub_rn(Ai, Br);
+            const double s7r = __dadd_rn(__dsub_rn(Ar, Bi), nz), s7i = __dadd_rn(Ai, Br);
+            // 1/n: exact reciprocals are not needed (gate 1e-10); |sum| = m2 * rsqrt(m2) instead of an IEEE
+            // square root (no overflow: |sum| <= n)
+            const double nd = (double)nb;
+            double inv_n = rcp_seed(nd);
+            inv_n = __fma_rn(inv_n, __fma_rn(-nd, inv_n, 1.0), inv_n);
+            inv_n = __fma_rn(inv_n, __fma_rn(-nd, inv_n, 1.0), inv_n);
             auto modulus = [&](double re, double im) {
                 const double m2 = __fma_rn(re, re, __dmul_rn(im, im));
-                if (!(m2 > 0)) return 0.0;
-                double y = rsqrt_seed(m2);
-                double e = __fma_rn(-__dmul_rn(m2, y), y, 1.0);
-                y = __fma_rn(__dmul_rn(0.5, y), e, y);
-                e = __fma_rn(-__dmul_rn(m2, y), y, 1.0);
-                y = __fma_rn(__dmul_rn(0.5, y), e, y);
-                return __dmul_rn(__dmul_rn(m2, y), inv_n);
+                const double m = __dmul_rn(__dmul_rn(m2, rsqrt_gate(m2)), inv_n);
+                return m2 > 0.0 ? m : 0.0;
             };
             q5 = modulus(s5r, s5i);
             q6 = modulus(s6r, s6i);
             q7 = modulus(s7r, s7i);
-            arg = atan2(s6i, s6r);
+            arg = atan2_gate(s6i, s6r);
         }
         // Two FULL-sector stores by particle id.  (Five scattered 8-/4-byte stores cost 60 us at N = 10^6:
         // a partial write to a sector that is not in L2 makes L2 fetch it from DRAM first.)
@@ -1063,7 +1125,10 @@ __device__ __forceinline__ void boop_tile(const BoopTileArgs &ba, const CellSmem
     }
 }
 
-constexpr int kBoopCtas = 1024 / kTileThreads;   // per SM: 32 warps at 64 registers per thread
+#ifndef EDMD_BOOP_CTAS
+#define EDMD_BOOP_CTAS (1024 / kTileThreads)   // per SM: 32 warps at 64 registers per thread
+#endif
+constexpr int kBoopCtas = EDMD_BOOP_CTAS;
 
 __global__ void __launch_bounds__(kTileThreads, kBoopCtas)
 k_cell_boop(const __grid_constant__ BoopTileArgs ba)
@@ -1080,15 +1145,15 @@ k_cell_boop(const __grid_constant__ BoopTileArgs ba)
     const bool declined = a.flags[kFlagBoopFail] != 0;
     __syncthreads();
     if (declined) return;
-    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    const double far = 1e300;
     const bool fits = frame_load<true>(
         a, s, tp, false,
         [&](int pos, int, int, const double4 &st, double, int id) {
             s.xy[pos] = make_double2(st.x, st.y);
             s.id[pos] = id;
         },
-        [&](int pos) {   // an empty cell is a NaN position: `r2 < rc2` fails by itself
-            s.xy[pos] = make_double2(qnan, qnan);
+        [&](int pos) {   // an empty cell is a disk 1e300 away: r2 = inf, `r2 < rc2` fails by itself, no NaN
+            s.xy[pos] = make_double2(far, far);
             s.id[pos] = -1;
         });
     if (!fits) {

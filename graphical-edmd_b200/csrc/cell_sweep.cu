@@ -939,7 +939,7 @@ k_cell_sweep(const __grid_constant__ SweepArgs a)
 struct BoopTileArgs {
     SweepArgs s;
     double rc2;
-    double4 *rec;   // two 32-byte sectors per particle id: (q5, q6, q7, q6_arg), (neighbours, 0, 0, 0)
+    double4 *rec;   // one 32-byte sector per particle id: (q5, q6, q7, q6_arg | neighbours in the 8 low mantissa bits)
 };
 // atan2(y, x) to ~1e-14 absolute (the gate on q6_arg is 1e-10; CUDA's atan2 is an IEEE division plus a
 // 20-term polynomial): fold into the first octant, ONE rotation by -pi/4 when the angle is above pi/8
@@ -1117,11 +1117,13 @@ __device__ __forceinline__ void boop_tile(const BoopTileArgs &ba, const CellSmem
             q7 = modulus(s7r, s7i);
             arg = atan2_gate(s6i, s6r);
         }
-        // Two FULL-sector stores by particle id.  (Five scattered 8-/4-byte stores cost 60 us at N = 10^6:
-        // a partial write to a sector that is not in L2 makes L2 fetch it from DRAM first.)
-        double4 *dst = ba.rec + 2 * (size_t)id;
-        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(q5), "d"(q6), "d"(q7), "d"(arg) : "memory");
-        asm volatile("st.global.v8.b32 [%0], {%1,%2,%2,%2,%2,%2,%2,%2};" ::"l"(dst + 1), "r"(nb), "r"(0) : "memory");
+        // ONE full-sector store by particle id: (q5, q6, q7, q6_arg) with the neighbour count in the eight low
+        // mantissa bits of the argument (at most 9 cells x kSlotK disks; k_unpack_boop clears them again: the argument
+        // moves by less than 2^-44 relative, gate 1e-10).  (Five scattered 8-/4-byte stores cost 60 us at N = 10^6 -- a
+        // partial write to a sector that is not in L2 makes L2 fetch it from DRAM first --, a second sector for the
+        // count 32 more bytes per particle here and in the unpack pass.)
+        const double argn = __hiloint2double(__double2hiint(arg), (__double2loint(arg) & ~0xff) | nb);
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ba.rec + id), "d"(q5), "d"(q6), "d"(q7), "d"(argn) : "memory");
     }
 }
 
@@ -1178,12 +1180,12 @@ k_unpack_boop(int n, const double4 *__restrict__ rec, double *__restrict__ q5, d
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double4 v = ld_sector(rec + 2 * (size_t)i);
-    const int nb = *reinterpret_cast<const int *>(rec + 2 * (size_t)i + 1);
+    const double4 v = ld_sector(rec + i);
+    const int lo = __double2loint(v.w), nb = lo & 0xff;
     q5[i] = v.x;
     q6[i] = v.y;
     q7[i] = v.z;
-    q6arg[i] = v.w;
+    q6arg[i] = __hiloint2double(__double2hiint(v.w), lo & ~0xff);
     nbr[i] = nb;
 }
 

@@ -283,7 +283,7 @@ static int create_impl(int device, int n, double lx, double ly, int slab, int ro
         if ((r = dev_alloc(c, &c->pid, kSlotK * ncp + 32))) return r;
         if ((r = dev_alloc(c, &c->prad, kSlotK * ncp + 32))) return r;
         if ((r = dev_alloc(c, &c->ccnt, 2 * ncp + 32))) return r;
-        if ((r = dev_alloc(c, &c->boop_rec, 2 * N + 8))) return r;
+        if ((r = dev_alloc(c, &c->boop_rec, N + 8))) return r;
         if ((r = dev_alloc(c, &c->evrec, N + 32))) return r;
         CU(cudaMemsetAsync(c->ccnt, 0, (2 * ncp + 32) * sizeof(unsigned long long), c->stream));
         c->cbuf = 0;

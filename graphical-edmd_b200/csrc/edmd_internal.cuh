@@ -241,7 +241,7 @@ struct edmd_ctx {
     int cbuf;                        // the buffer of the current partition
     int workers_key, workers_per_sm; // resident CTAs of the sweep kernel per SM for (extras capacity, radii): asked of the runtime once
     bool boop_tile_off;              // EDMD_OPT_NO_TILE_BOOP
-    double4 *boop_rec;               // psi6 records of the tile kernel: two sectors per particle id
+    double4 *boop_rec;               // psi6 records of the tile kernel: one sector per particle id
     edmd_ev32 *evrec;                 // event records of the last tile sweep, by particle id
     bool pred_packed;                // the predictions of the last sweep are in ev[], not yet in the five arrays
     bool tile_off;                   // EDMD_OPT_NO_TILE

@@ -621,9 +621,11 @@ def run_ours(args, cfg):
             reuse.append(time.perf_counter() - t0)
         analysis["psi6_after_sweep_wall_ms"] = float(np.median(reuse) * 1e3)
         analysis["psi6_roofline"] = {
-            "bound": "fp64 pipe (not HBM: 56 B/particle is 0.06 % of a millisecond of HBM traffic)",
-            "fp64_ops_per_particle": "~6 neighbours x ~40 (distance, 1/r by Newton, z^2 z^4 z^6, z^5 z^7, six sums) "
-                                     "+ ~2.3 rejected candidates x 8 + ~150 (three moduli, atan2)",
+            "bound": "fp64 pipe + instruction issue (not HBM: 56 B/particle is 0.06 % of a millisecond of HBM traffic)",
+            "fp64_ops_per_particle": "8 branch-free plane-0 candidates x 30 (distance, 1/r by one third-order step, "
+                                     "z^2 z^4 by unit-modulus squarings, z^6, sum6 and the A/B sums that give sum5 / sum7) "
+                                     "+ 68 (three moduli, 1/n, atan2 by one rotation + degree-8 polynomial) "
+                                     "+ 30 per extra disk of the 3 x 3 block",
             "hbm_frac": analysis["psi6_hbm_frac"]}
         max_r_cut = 12.0
         if world == 1:

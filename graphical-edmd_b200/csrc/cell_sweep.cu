@@ -945,7 +945,7 @@ struct BoopTileArgs {
 // 20-term polynomial): fold into the first octant, ONE rotation by -pi/4 when the angle is above pi/8
 // (hi + lo, lo - hi: the common factor sqrt(2) drops out of the quotient), the quotient from the MUFU
 // reciprocal seed + two Newton steps, atan(t) = t P(t^2) on |t| <= tan(pi/8) with a degree-8 interpolant
-// at Chebyshev nodes (max error 9.5e-15 in FP64 Horner form, profiles/tools/boop_model.py).
+// at Chebyshev nodes (max error 9.5e-15 in FP64 Horner form, tests/test_boop_model.py).
 __constant__ double kAtanC[9] = {0x1.fffffffffff0fp-1, -0x1.55555554e5fc5p-2, 0x1.99999911c1573p-3,
                                  -0x1.2492291945813p-3, 0x1.c714d3e720df5p-4, -0x1.73d9cba10d56bp-4,
                                  0x1.35ced8de982a2p-4, -0x1.e13ac280a9accp-5, 0x1.f657ae7e09908p-6};

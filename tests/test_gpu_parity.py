@@ -315,6 +315,32 @@ def test_bad_cell_id_is_an_error(pkg):
 
 
 # ------------------------------------------------------------- analysis ----
+def test_boop_ignores_nan_coordinates_and_counts_coincident_disks(pkg, oracle):
+    """The psi6 kernel on the cell slots runs every candidate through the whole chain (no branch): a NaN /
+    infinite coordinate (the reference's `r2 < r_c*r_c` is false for it, src/boop.c:84) must not reach any sum,
+    and two disks at the same point see each other at atan2(0, 0) = 0, i.e. z = 1 (src/boop.c:86-89)."""
+    c = pkg.synth.lattice_config(40000, 0.70, seed=77)
+    n = c["n"]
+    cells = oracle.cells(n, c["lx"], c["ly"], c["x"], c["y"]).reshape(n, 2).copy()
+    x, y = c["x"].copy(), c["y"].copy()
+    x[17], y[4321] = np.nan, np.inf
+    x[1000], y[1000] = x[2000], y[2000]          # coincident pair, filed under the cell of 2000
+    cells[1000] = cells[2000]
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload(x, y, c["vx"], c["vy"], c["rad"], cell_xy=cells, t=0.0)
+        b = ctx.boop_cutoff(2.5)
+    want = oracle.boop_cutoff(n, c["lx"], c["ly"], x, y, 2.5, cell_xy=cells)
+    assert want["neighbors"][17] == 0 and want["neighbors"][4321] == 0
+    assert np.isfinite(b["q6"]).all() and np.isfinite(b["q6_arg"]).all()
+    assert_boop_close(b, want)
+    # the same without the strays (the plain variant of the tile kernel away from the box edges)
+    x[17], y[4321] = c["x"][17], c["y"][4321]
+    with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
+        ctx.upload(x, y, c["vx"], c["vy"], c["rad"], cell_xy=cells, t=0.0)
+        b = ctx.boop_cutoff(2.5)
+    assert_boop_close(b, oracle.boop_cutoff(n, c["lx"], c["ly"], x, y, 2.5, cell_xy=cells))
+
+
 @pytest.mark.parametrize("n,phi,seed,sf", [(100000, 0.72, 2, 0.0), (1000000, 0.70, 3, 0.0),
                                            (1000000, 0.85, 1, 0.3)])
 def test_boop_matches_oracle(pkg, oracle, n, phi, seed, sf):

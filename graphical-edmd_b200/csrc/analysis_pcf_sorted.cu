@@ -898,7 +898,7 @@ int edmd_launch_rsqrt_selftest(edmd_ctx *c, unsigned long long *worst_bits_dev)
 }
 
 // smallest double s with correctly rounded sqrt(s) >= max_r
-static double s_threshold(double max_r)
+double edmd_pcf_s_threshold(double max_r)
 {
     double s = max_r * max_r;
     while (sqrt(s) >= max_r && s > 0) s = nextafter(s, 0.0);
@@ -978,7 +978,7 @@ int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, c
     a.n = n; a.num_bins = num_bins;
     a.b = c->dbox;
     a.dr = dr; a.max_r = max_r;
-    a.s_max = s_threshold(max_r);
+    a.s_max = edmd_pcf_s_threshold(max_r);
     a.dr_lo = dr * (1.0 + 1.7763568394002505e-15);   // 2^-49
     a.dr_hi = dr * (1.0 - 1.7763568394002505e-15);
     a.inv_dr = (float)(1.0 / dr);

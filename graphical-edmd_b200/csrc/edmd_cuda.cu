@@ -1113,6 +1113,8 @@ int edmd_cuda_selftest_rsqrt(edmd_ctx *c, double *max_rel_err)
     return 0;
 }
 
+int voronoi_scratch(edmd_ctx *c, char **grid, double2 **psi, double **area, double **perim, int32_t **failp);
+
 // calculate_bond_order_pcf, src/pcf.c:77-167
 int edmd_cuda_pcf_bond_order(edmd_ctx *c, double dr, double max_r, const double *k_vector,
                              uint64_t *counts, double *g_r, double *g6_r, int *num_bins)
@@ -1145,7 +1147,13 @@ int edmd_cuda_pcf_bond_order(edmd_ctx *c, double dr, double max_r, const double 
     if (nb > 0) {
         CU(cudaMemsetAsync(c->pcf_counts, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
         CU(cudaMemsetAsync(c->pcf_wsum, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
-        c->launches += edmd_launch_pcf_bond_order(c, dr, max_r, nb, k_vector[0], k_vector[1], nullptr,
+        // scratch for e^{i k.r} of every particle (the Voronoi family's psi array)
+        char *grid = nullptr;
+        double2 *psi = nullptr;
+        double *area = nullptr, *perim = nullptr;
+        int32_t *failp = nullptr;
+        if ((r = voronoi_scratch(c, &grid, &psi, &area, &perim, &failp))) return r;
+        c->launches += edmd_launch_pcf_bond_order(c, dr, max_r, nb, k_vector[0], k_vector[1], psi, true,
                                                   c->pcf_counts, c->pcf_wsum);
         CU(cudaGetLastError());
         if ((r = d2h(c, hc.data(), c->pcf_counts, (size_t)nb * sizeof(unsigned long long)))) return r;
@@ -1491,7 +1499,7 @@ int edmd_cuda_g6_correlation(edmd_ctx *c, double dr, double max_r, const double 
     if (nb > 0) {
         CU(cudaMemsetAsync(c->pcf_counts, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
         CU(cudaMemsetAsync(c->pcf_wsum, 0, (size_t)nb * sizeof(unsigned long long), c->stream));
-        c->launches += edmd_launch_pcf_bond_order(c, dr, max_r, nb, 0.0, 0.0, psi, c->pcf_counts, c->pcf_wsum);
+        c->launches += edmd_launch_pcf_bond_order(c, dr, max_r, nb, 0.0, 0.0, psi, false, c->pcf_counts, c->pcf_wsum);
         CU(cudaGetLastError());
         if ((r = d2h(c, hc.data(), c->pcf_counts, (size_t)nb * sizeof(unsigned long long)))) return r;
         if ((r = d2h(c, hw.data(), c->pcf_wsum, (size_t)nb * sizeof(unsigned long long)))) return r;

@@ -345,7 +345,8 @@ int edmd_launch_tile_boop(edmd_ctx *c, double r_c, bool from_keep);
 int edmd_launch_boop(edmd_ctx *c, double r_c);
 int edmd_launch_mean(edmd_ctx *c, const double *v, int n, double *out_dev);
 int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bins, double kx, double ky,
-                               const double2 *psi, unsigned long long *counts, unsigned long long *wsum);
+                               double2 *psi, bool phase, unsigned long long *counts, unsigned long long *wsum);
+double edmd_pcf_s_threshold(double max_r);   // smallest s whose correctly rounded sqrt reaches max_r (analysis_pcf_sorted.cu)
 int edmd_launch_structure_factor(edmd_ctx *c, int velocity, int nqx, int nqy, const double *qx, const double *qy,
                                  double *re, double *im);
 size_t edmd_voronoi_scratch_bytes(const edmd_ctx *c, int *gx_out, int *gy_out);

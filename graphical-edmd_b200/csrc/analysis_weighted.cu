@@ -205,103 +205,108 @@ k_pcf_bond_order(const __grid_constant__ WPcfArgs a)
     }
 }
 
-// ---- Bragg peak: S(k) = |sum_j exp(i k.r_j)|^2 / N over a list of wave vectors ------
-struct BraggArgs {
-    int n, nk, stride, chunk;
-    const double *xy;
-    const double2 *kvec;   // [nk] in the reference's loop order
-    double *re, *im;       // [nk] accumulated with atomics over particle chunks
-};
+// ---- sums over the particles on a GRID of wave vectors ------------------------------------
+//   find_max_structure_factor_bragg   src/pcf.c:405-467   S(k) = |sum_p e^{i k.r_p}|^2 / N, k = (kx_i, ky_j)
+//   computeStructureFactor            src/struc.c:364-384  the same on (qx[i], qy[j])
+//   computeVelocityStructureFactor    src/struc.c:386-408  `re += vx cos + vy sin; im += vx sin - vy cos`
+// The wave vectors are a product grid, so e^{i k.r} = e^{i kx x} e^{i ky y}: per block of 32 x 32 wave vectors and
+// 32 particles, 2 x 32 x 32 FP64 sincos build two tables (the weight (vx - i vy) of the velocity form folded into
+// the y table) and every (wave vector, particle) term is then one complex multiply-add -- four fused
+// multiply-adds -- instead of a sincos (the reference's `phase = kx*x + ky*y; cos(phase); sin(phase)`; the two
+// forms agree to a few 1e-16 per term, gate 1e-10 on S).  A thread holds one column and four rows of the block:
+// the x phasor is read once per particle (a 128-bit load per lane), the y phasors are warp-wide broadcasts.
+constexpr int kGT = 32;    // wave vectors per block side
+constexpr int kGP = 32;    // particles per table
+constexpr int kGR = kGT * kGT / kThreads;   // rows per thread
 
-// blockIdx.x: tile of kThreads wave vectors (one per thread); blockIdx.y: chunk of
-// particles, staged through shared memory and broadcast
-__global__ void __launch_bounds__(kThreads)
-k_bragg_sums(const __grid_constant__ BraggArgs a)
-{
-    __shared__ double2 tile[kTile];
-    const int ik = blockIdx.x * kThreads + threadIdx.x;
-    const double2 kv = ik < a.nk ? a.kvec[ik] : make_double2(0, 0);
-    double re = 0.0, im = 0.0;
-    const int j0 = blockIdx.y * a.chunk, j1 = min(a.n, j0 + a.chunk);
-    for (int base = j0; base < j1; base += kTile) {
-        __syncthreads();
-        const int jj = base + threadIdx.x;
-        if (jj < j1) tile[threadIdx.x] = *reinterpret_cast<const double2 *>(a.xy + (size_t)jj * a.stride);
-        __syncthreads();
-        const int cnt = min(kTile, j1 - base);
-        for (int q = 0; q < cnt; q++) {
-            // `phase = kx * x + ky * y; re += cos(phase); im += sin(phase);` src/pcf.c:442-446
-            const double phase = __dadd_rn(__dmul_rn(kv.x, tile[q].x), __dmul_rn(kv.y, tile[q].y));
-            double s, c;
-            sincos(phase, &s, &c);
-            re += c;
-            im += s;
-        }
-    }
-    if (ik < a.nk) {
-        atomicAdd(&a.re[ik], re);
-        atomicAdd(&a.im[ik], im);
-    }
-}
-
-// Structure factor on the reference's wave-vector grid: the same sums with the
-// weights of computeStructureFactor (1) or computeVelocityStructureFactor
-// (`re += vx cos + vy sin; im += vx sin - vy cos`, src/struc.c:395-396).  Wave
-// vector ik = i * nqy + j  ->  (qx[i], qy[j]).
-struct SqArgs {
-    int n, nqx, nqy, chunk;
+struct GridArgs {
+    int n, ni, nj, chunk;
+    long long si, sj;            // output index of wave vector (i, j) = i * si + j * sj
     const double4 *xv;
-    const double *qx, *qy;
-    double *re, *im;   // [nqx * nqy]
+    const double *qi, *qj;       // the two axes: wave vector (i, j) = (qi[i], qj[j])
+    const unsigned char *mask;   // by output index, nullptr: every wave vector wanted
+    double *re, *im;             // by output index, accumulated with atomics over particle chunks
 };
 
+// blockIdx.x, .y: block of wave vectors; blockIdx.z: chunk of particles
 template <bool VEL>
 __global__ void __launch_bounds__(kThreads)
-k_sq_sums(const __grid_constant__ SqArgs a)
+k_grid_sums(const __grid_constant__ GridArgs a)
 {
-    __shared__ double4 tile[kTile];
-    const int nk = a.nqx * a.nqy;
-    const int ik = blockIdx.x * kThreads + threadIdx.x;
-    const double kx = ik < nk ? a.qx[ik / a.nqy] : 0.0, ky = ik < nk ? a.qy[ik % a.nqy] : 0.0;
-    double re = 0.0, im = 0.0;
-    const int j0 = blockIdx.y * a.chunk, j1 = min(a.n, j0 + a.chunk);
-    for (int base = j0; base < j1; base += kTile) {
+    __shared__ double2 A[kGP][kGT], B[kGP][kGT];
+    __shared__ double4 pos[kGP];
+    const int tid = threadIdx.x, ti = tid & 31, w = tid >> 5;
+    const int i = blockIdx.x * kGT + ti, jb = blockIdx.y * kGT + kGR * w;
+    bool want[kGR];
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < kGR; r++) {
+        const int j = jb + r;
+        want[r] = i < a.ni && j < a.nj && (!a.mask || a.mask[i * a.si + j * a.sj] != 0);
+        any = any || want[r];
+    }
+    if (!__syncthreads_or(any)) return;   // (a block outside the wedge of the Bragg search)
+    // the table entries this thread builds: column `col` of A (tid < 128: wave vectors i) or of B (j), particles
+    // prow, prow + 4, ...
+    const int col = tid & 31, tab = (tid >> 5) & 1, prow = tid >> 6;
+    const int qidx = tab == 0 ? blockIdx.x * kGT + col : blockIdx.y * kGT + col;
+    const double q = tab == 0 ? (qidx < a.ni ? a.qi[qidx] : 0.0) : (qidx < a.nj ? a.qj[qidx] : 0.0);
+    double re[kGR], im[kGR];
+#pragma unroll
+    for (int r = 0; r < kGR; r++) re[r] = im[r] = 0.0;
+    const int p0 = blockIdx.z * a.chunk, p1 = min(a.n, p0 + a.chunk);
+    for (int base = p0; base < p1; base += kGP) {
         __syncthreads();
-        const int jj = base + threadIdx.x;
-        if (jj < j1) tile[threadIdx.x] = a.xv[jj];
+        if (tid < kGP) pos[tid] = base + tid < p1 ? a.xv[base + tid] : make_double4(0, 0, 0, 0);
         __syncthreads();
-        const int cnt = min(kTile, j1 - base);
-        for (int q = 0; q < cnt; q++) {
-            const double4 p = tile[q];
-            // `qr = qx[i]*p->x + qy[j]*p->y` src/struc.c:373
-            const double qr = __dadd_rn(__dmul_rn(kx, p.x), __dmul_rn(ky, p.y));
-            double s, c;
-            sincos(qr, &s, &c);
-            if (VEL) {
-                re += p.z * c + p.w * s;
-                im += p.z * s - p.w * c;
+        const int cnt = min(kGP, p1 - base);
+#pragma unroll
+        for (int m = 0; m < kGP / 4; m++) {
+            const int p = prow + 4 * m;
+            const double4 P = pos[p];
+            double sn, cs;
+            sincos(__dmul_rn(q, tab == 0 ? P.x : P.y), &sn, &cs);
+            if (tab == 0) {
+                A[p][col] = make_double2(cs, sn);
+            } else if (VEL) {   // (vx - i vy) e^{i qy y}
+                B[p][col] = make_double2(__fma_rn(P.z, cs, __dmul_rn(P.w, sn)), __fma_rn(P.z, sn, -__dmul_rn(P.w, cs)));
             } else {
-                re += c;
-                im += s;
+                B[p][col] = make_double2(cs, sn);
+            }
+        }
+        __syncthreads();
+        for (int p = 0; p < cnt; p++) {
+            const double2 x = A[p][ti];
+#pragma unroll
+            for (int r = 0; r < kGR; r++) {
+                const double2 y = B[p][kGR * w + r];
+                re[r] = __fma_rn(x.x, y.x, re[r]);
+                re[r] = __fma_rn(-x.y, y.y, re[r]);
+                im[r] = __fma_rn(x.x, y.y, im[r]);
+                im[r] = __fma_rn(x.y, y.x, im[r]);
             }
         }
     }
-    if (ik < nk) {
-        atomicAdd(&a.re[ik], re);
-        atomicAdd(&a.im[ik], im);
-    }
+#pragma unroll
+    for (int r = 0; r < kGR; r++)
+        if (want[r]) {
+            const long long idx = i * a.si + (jb + r) * a.sj;
+            atomicAdd(&a.re[idx], re[r]);
+            atomicAdd(&a.im[idx], im[r]);
+        }
 }
 
-// one block: S per wave vector, the first maximum in list order wins
+// one block: S per wave vector (mask: only the marked ones), the first maximum in index order wins
 __global__ void __launch_bounds__(1024)
-k_bragg_argmax(int n, int nk, const double *__restrict__ re, const double *__restrict__ im,
-               double *__restrict__ best_s, int *__restrict__ best_i)
+k_bragg_argmax(int n, long long nk, const double *__restrict__ re, const double *__restrict__ im,
+               const unsigned char *__restrict__ mask, double *__restrict__ best_s, long long *__restrict__ best_i)
 {
     __shared__ double ss[1024];
-    __shared__ int si[1024];
+    __shared__ long long si[1024];
     double bs = -1.0;
-    int bi = -1;
-    for (int k = threadIdx.x; k < nk; k += 1024) {
+    long long bi = -1;
+    for (long long k = threadIdx.x; k < nk; k += 1024) {
+        if (mask && !mask[k]) continue;
         const double S = (re[k] * re[k] + im[k] * im[k]) / (double)n;
         if (S > bs) {   // ascending k within a thread: the earlier index stays on ties
             bs = S;
@@ -314,7 +319,7 @@ k_bragg_argmax(int n, int nk, const double *__restrict__ re, const double *__res
     for (int d = 512; d > 0; d >>= 1) {
         if (threadIdx.x < d) {
             const double os = ss[threadIdx.x + d];
-            const int oi = si[threadIdx.x + d];
+            const long long oi = si[threadIdx.x + d];
             if (oi >= 0 && (os > ss[threadIdx.x] || (os == ss[threadIdx.x] && (si[threadIdx.x] < 0 || oi < si[threadIdx.x])))) {
                 ss[threadIdx.x] = os;
                 si[threadIdx.x] = oi;
@@ -381,26 +386,39 @@ int edmd_launch_pcf_bond_order(edmd_ctx *c, double dr, double max_r, int num_bin
     return launches + 1;
 }
 
-// kvec / re / im / out live in caller-provided device scratch
-int edmd_launch_bragg(edmd_ctx *c, int nk, const double2 *kvec, double *re, double *im, double *best_s,
-                      int *best_i)
+// sums on the grid (qi[i], qj[j]) (device arrays); re / im by output index i * si + j * sj, zeroed by the caller
+static int launch_grid_sums(edmd_ctx *c, bool velocity, int ni, int nj, long long si, long long sj, const double *qi,
+                            const double *qj, const unsigned char *mask, double *re, double *im)
 {
     const int n = c->n;
-    if (n < 1 || nk < 1) return 0;
-    BraggArgs a;
-    a.n = n; a.nk = nk; a.stride = 4;
-    a.xy = reinterpret_cast<const double *>(c->xv);
-    a.kvec = kvec; a.re = re; a.im = im;
-    const int kb = (nk + kThreads - 1) / kThreads;
+    GridArgs a;
+    a.n = n; a.ni = ni; a.nj = nj; a.si = si; a.sj = sj;
+    a.xv = c->xv; a.qi = qi; a.qj = qj; a.mask = mask; a.re = re; a.im = im;
+    const int bi = (ni + kGT - 1) / kGT, bj = (nj + kGT - 1) / kGT;
     // enough CTAs to fill the GPU: split the particles when there are few wave vectors
-    int parts = (2 * (c->sm_count > 0 ? c->sm_count : 148) + kb - 1) / kb;
-    const int max_parts = (n + kTile - 1) / kTile;
+    const long long blocks = (long long)bi * bj;
+    long long parts = (8LL * (c->sm_count > 0 ? c->sm_count : 148) + blocks - 1) / blocks;
+    const long long max_parts = (n + kGP - 1) / kGP;
     if (parts > max_parts) parts = max_parts;
+    if (parts > 65535) parts = 65535;
     if (parts < 1) parts = 1;
-    a.chunk = (((n + parts - 1) / parts) + kTile - 1) / kTile * kTile;
+    a.chunk = (int)((((n + parts - 1) / parts) + kGP - 1) / kGP * kGP);
     parts = (n + a.chunk - 1) / a.chunk;
-    k_bragg_sums<<<dim3(kb, parts), kThreads, 0, c->stream>>>(a);
-    k_bragg_argmax<<<1, 1024, 0, c->stream>>>(n, nk, re, im, best_s, best_i);
+    const dim3 grid(bi, bj, (unsigned)parts);
+    if (velocity) k_grid_sums<true><<<grid, kThreads, 0, c->stream>>>(a);
+    else k_grid_sums<false><<<grid, kThreads, 0, c->stream>>>(a);
+    return 1;
+}
+
+// Bragg search on the grid (kx[ikx], ky[iky]); wave vector (ikx, iky) has index iky * nkx + ikx (the reference's
+// loop order), mask marks the ones inside its wedge; re / im zeroed by the caller
+int edmd_launch_bragg(edmd_ctx *c, int nkx, int nky, const double *kx, const double *ky, const unsigned char *mask,
+                      double *re, double *im, double *best_s, long long *best_i)
+{
+    const int n = c->n;
+    if (n < 1 || nkx < 1 || nky < 1) return 0;
+    launch_grid_sums(c, false, nkx, nky, 1, nkx, kx, ky, mask, re, im);
+    k_bragg_argmax<<<1, 1024, 0, c->stream>>>(n, (long long)nkx * nky, re, im, mask, best_s, best_i);
     return 2;
 }
 
@@ -408,19 +426,6 @@ int edmd_launch_bragg(edmd_ctx *c, int nk, const double2 *kvec, double *re, doub
 int edmd_launch_structure_factor(edmd_ctx *c, int velocity, int nqx, int nqy, const double *qx, const double *qy,
                                  double *re, double *im)
 {
-    const int n = c->n, nk = nqx * nqy;
-    if (n < 1 || nk < 1) return 0;
-    SqArgs a;
-    a.n = n; a.nqx = nqx; a.nqy = nqy;
-    a.xv = c->xv; a.qx = qx; a.qy = qy; a.re = re; a.im = im;
-    const int kb = (nk + kThreads - 1) / kThreads;
-    int parts = (2 * (c->sm_count > 0 ? c->sm_count : 148) + kb - 1) / kb;
-    const int max_parts = (n + kTile - 1) / kTile;
-    if (parts > max_parts) parts = max_parts;
-    if (parts < 1) parts = 1;
-    a.chunk = (((n + parts - 1) / parts) + kTile - 1) / kTile * kTile;
-    parts = (n + a.chunk - 1) / a.chunk;
-    if (velocity) k_sq_sums<true><<<dim3(kb, parts), kThreads, 0, c->stream>>>(a);
-    else k_sq_sums<false><<<dim3(kb, parts), kThreads, 0, c->stream>>>(a);
-    return 1;
+    if (c->n < 1 || nqx * nqy < 1) return 0;
+    return launch_grid_sums(c, velocity != 0, nqx, nqy, nqy, 1, qx, qy, nullptr, re, im);
 }

@@ -1190,47 +1190,59 @@ int edmd_cuda_bragg_peak(edmd_ctx *c, double expected_bragg, double *k_out, doub
     const double kx_max = ceil((expected_bragg + 0.8) / dkx) * dkx;
     const double ky_min = floor((-expected_bragg - 0.8) / dky) * dky;
     const double ky_max = ceil((expected_bragg + 0.8) / dky) * dky;
-    std::vector<double2> ks;
+    // wave vector (ikx, iky) = (kx_min + ikx dkx, ky_max - iky dky); index iky * nkx + ikx = the reference's loop
+    // order; the wedge test with the host's libm, like the reference's
+    const int nky = (int)((ky_max - ky_min) / dky) + 1, nkx = (int)((kx_max - kx_min) / dkx) + 1;
+    if (!((double)nkx * (double)nky < 2e8)) return fail(c, EDMD_EINVAL, "too many wave vectors");
+    std::vector<double> axes;
+    std::vector<unsigned char> mask;
+    size_t nvalid = 0;
     try {
-        for (int iky = 0; iky <= (int)((ky_max - ky_min) / dky); iky++) {
-            for (int ikx = 0; ikx <= (int)((kx_max - kx_min) / dkx); ikx++) {
-                const double kx = kx_min + ikx * dkx;
-                const double ky = ky_max - iky * dky;
-                const double k_abs = sqrt(kx * kx + ky * ky);
-                const double theta = atan2(ky, kx);
-                if (k_abs < 1.5 || theta < M_PI / 2 - M_PI / 5 || theta > M_PI / 2 + M_PI / 5) continue;
-                ks.push_back(make_double2(kx, ky));
-            }
-        }
+        axes.resize((size_t)nkx + nky);
+        mask.assign((size_t)nkx * nky, 0);
     } catch (...) {
         return fail(c, EDMD_ENOMEM, "host staging allocation failed");
     }
+    for (int ikx = 0; ikx < nkx; ikx++) axes[ikx] = kx_min + ikx * dkx;
+    for (int iky = 0; iky < nky; iky++) axes[(size_t)nkx + iky] = ky_max - iky * dky;
+    for (int iky = 0; iky < nky; iky++) {
+        for (int ikx = 0; ikx < nkx; ikx++) {
+            const double kx = axes[ikx];
+            const double ky = axes[(size_t)nkx + iky];
+            const double k_abs = sqrt(kx * kx + ky * ky);
+            const double theta = atan2(ky, kx);
+            if (k_abs < 1.5 || theta < M_PI / 2 - M_PI / 5 || theta > M_PI / 2 + M_PI / 5) continue;
+            mask[(size_t)iky * nkx + ikx] = 1;
+            nvalid++;
+        }
+    }
     k_out[0] = k_out[1] = 0.0;   // `best_k = {0, 0}` when nothing qualifies
     if (s_max) *s_max = -1.0;
-    const int nk = (int)ks.size();
-    if (nk == 0 || c->n == 0) return 0;
+    const size_t nk = (size_t)nkx * nky;
+    if (nvalid == 0 || c->n == 0) return 0;
     double *scratch = nullptr;
-    const size_t doubles = 4 * (size_t)nk + 4;
-    CU(cudaMalloc((void **)&scratch, doubles * sizeof(double)));
-    double2 *d_k = reinterpret_cast<double2 *>(scratch);
-    double *d_re = scratch + 2 * (size_t)nk, *d_im = d_re + nk, *d_s = d_im + nk;
-    int *d_i = reinterpret_cast<int *>(d_s + 1);
-    cudaError_t e = cudaMemcpyAsync(d_k, ks.data(), (size_t)nk * sizeof(double2), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_re, 0, 2 * (size_t)nk * sizeof(double), c->stream);
+    const size_t doubles = 2 * nk + (size_t)nkx + nky + 4;
+    CU(cudaMalloc((void **)&scratch, doubles * sizeof(double) + nk));
+    double *d_re = scratch, *d_im = d_re + nk, *d_ax = d_im + nk, *d_s = d_ax + nkx + nky;
+    long long *d_i = reinterpret_cast<long long *>(d_s + 1);
+    unsigned char *d_mask = reinterpret_cast<unsigned char *>(scratch + doubles);
+    cudaError_t e = cudaMemcpyAsync(d_ax, axes.data(), axes.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_mask, mask.data(), nk, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_re, 0, 2 * nk * sizeof(double), c->stream);
     if (e == cudaSuccess) {
-        c->launches += edmd_launch_bragg(c, nk, d_k, d_re, d_im, d_s, d_i);
+        c->launches += edmd_launch_bragg(c, nkx, nky, d_ax, d_ax + nkx, d_mask, d_re, d_im, d_s, d_i);
         e = cudaGetLastError();
     }
     double best = -1.0;
-    int bi = -1;
+    long long bi = -1;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&best, d_s, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&bi, d_i, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bi, d_i, sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(scratch);
     if (e != cudaSuccess) return fail_cuda(c, e, "bragg_peak");
     if (bi >= 0) {
-        k_out[0] = ks[(size_t)bi].x;
-        k_out[1] = ks[(size_t)bi].y;
+        k_out[0] = axes[(size_t)(bi % nkx)];
+        k_out[1] = axes[(size_t)nkx + (size_t)(bi / nkx)];
     }
     if (s_max) *s_max = best;
     return 0;

@@ -360,8 +360,8 @@ int edmd_launch_shift_scale(edmd_ctx *c, double dvx, double dvy, double divisor,
                             int n_total, double *sums);
 double *edmd_launch_kinetic_final(edmd_ctx *c, double T, double *scratch, int n_total);
 int edmd_launch_langevin(edmd_ctx *c, double T, double gamma, double dtnoise, unsigned int seed, unsigned int tick);
-int edmd_launch_bragg(edmd_ctx *c, int nk, const double2 *kvec, double *re, double *im, double *best_s,
-                      int *best_i);
+int edmd_launch_bragg(edmd_ctx *c, int nkx, int nky, const double *kx, const double *ky, const unsigned char *mask,
+                      double *re, double *im, double *best_s, long long *best_i);
 int edmd_launch_rsqrt_selftest(edmd_ctx *c, unsigned long long *worst_bits_dev);
 int edmd_launch_pcf_sorted(edmd_ctx *c, double dr, double max_r, int num_bins, const double *xy, int stride,
                            int n, int part, int nparts, unsigned long long *counts);

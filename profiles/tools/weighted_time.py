@@ -23,6 +23,12 @@ for n in [int(a) for a in sys.argv[1:]] or [100000, 1000000]:
         g6 = ctx.g6_correlation(0.1, max_r, np.cos(th), np.sin(th))
         t2 = time.perf_counter()
         plain = ctx.pcf(0.1, max_r)
+        t3 = time.perf_counter()
+        peak = ctx.bragg_peak(float(np.sqrt(8 * np.pi * 0.70 / np.sqrt(3))))
+        t4 = time.perf_counter()
+        sq = ctx.structure_factor(1.0)
+        t5 = time.perf_counter()
     assert np.array_equal(bo["counts"], plain["counts"]) and np.array_equal(g6["counts"], plain["counts"])
     print(f"N={c['n']}: cos-weighted g(r) {t1 - t0:.3f} s, g6 correlation (given psi) {t2 - t1:.3f} s, "
-          f"{int(plain['counts'].sum())} pairs in range, counts equal the plain g(r)'s", flush=True)
+          f"{int(plain['counts'].sum())} pairs in range, counts equal the plain g(r)'s; Bragg search {t4 - t3:.3f} s "
+          f"(k = {peak['k']}, S = {peak['s_max']:.1f}); S(q), q_max = 1: {t5 - t4:.3f} s ({sq['s'].size} wave vectors)", flush=True)

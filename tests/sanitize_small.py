@@ -31,6 +31,17 @@ for (n,phi,sf) in [(3000,0.7,0.3),(800,0.3,0.0)]:
         ctx.free_fly(1.5); s=ctx.download_state()
         ctx.set_growth(np.full(c['n'],0.01)); ctx.predict_all(mode=1, vr=np.full(c['n'],0.01))
     print('ok',c['n'])
+# the weighted g(r) family and the sums on grids of wave vectors
+c = pkg.synth.lattice_config(900, 0.70, 5)   # (small: the pair and grid kernels are O(N^2) under the sanitizer)
+with pkg.EdmdCuda(c['n'], c['lx'], c['ly']) as ctx:
+    ctx.upload(c['x'], c['y'], c['vx'], c['vy'], c['rad'], t=0.0)
+    pk = ctx.bragg_peak(3.2)
+    bo = ctx.pcf_bond_order(0.1, min(c['lx'], c['ly']) / 2, pk['k'])
+    g6 = ctx.g6_correlation(0.25, 20.0, np.cos(c['x']), np.sin(c['x']))
+    ctx.structure_factor(1.0)
+    ctx.structure_factor(1.0, velocity=True)
+    assert np.array_equal(bo['counts'], ctx.pcf(0.1, min(c['lx'], c['ly']) / 2)['counts'])
+print('ok weighted')
 # tiny boxes / overflow path
 rng=np.random.default_rng(1)
 n=4000; lx,ly=20.0,16.0

@@ -2,7 +2,8 @@
 slab ownership, the one-cell-row halo exchange and result reassembly.  The
 per-rank compute is done by the oracle here (no GPU in this suite); the check
 is that "owned + halo" is enough to reproduce the whole-system sweep bit for
-bit on every owned particle, for 2 and 3 ranks, including the periodic wrap."""
+bit on every owned particle, for 2 and 3 ranks, including the periodic wrap; and that psi6 of the owned
+particles plus the all-reduce of the slabs' q6 sums give the whole system's values and mean."""
 import os
 import socket
 import sys
@@ -65,6 +66,13 @@ def _worker(rank, world, port, n, phi, seed, out_dir):
     partner = np.where(has, lgid[res["partner"][:no]], 0)
     np.savez(Path(out_dir) / f"rank{rank}.npz", gid=gid, t_cross=res["t_cross"][:no], dir=res["dir"][:no],
              t_coll=res["t_coll"][:no], partner=partner)
+    # psi6 (computeBOOPCutoff, src/boop.c:61-107): owned + halo rows hold every neighbour of an owned particle;
+    # the mean q6 of the thermo column (src/EDMD.c:5521-5536) is the all-reduced sum of the slabs' sums over N
+    bo = orc.boop_cutoff(len(lgid), lx, ly, loc["x"], loc["y"], 2.5, cell_xy=lcells)
+    sums = torch.tensor([float(bo["q6"][:no].sum()), float(no)], dtype=torch.float64)
+    dist.all_reduce(sums)
+    np.savez(Path(out_dir) / f"boop{rank}.npz", gid=gid, q6=bo["q6"][:no], q6_arg=bo["q6_arg"][:no],
+             neighbors=bo["neighbors"][:no], mean_q6=float(sums[0] / sums[1]), n_total=float(sums[1]))
     # g(r): every rank bins its share of the pairs, counts are summed
     counts = torch.zeros(40, dtype=torch.int64)
     dist.all_reduce(counts)
@@ -95,6 +103,15 @@ def test_slab_partition_and_halo_reproduce_the_global_sweep(tmp_path, world):
         for k in ("t_cross", "dir", "t_coll", "partner"):
             assert np.array_equal(z[k], want[k][g]), (r, k)
     assert seen.all()
+    # psi6 per slab + the all-reduced mean
+    wb = orc.boop_cutoff(cfg["n"], cfg["lx"], cfg["ly"], cfg["x"], cfg["y"], 2.5)
+    for r in range(world):
+        z = np.load(tmp_path / f"boop{r}.npz")
+        g = z["gid"]
+        assert np.array_equal(z["neighbors"], wb["neighbors"][g])
+        assert np.abs(z["q6"] - wb["q6"][g]).max() <= 1e-10
+        assert z["n_total"] == cfg["n"]
+        assert abs(float(z["mean_q6"]) - wb["q6"].mean()) <= 1e-10
 
 
 def test_slab_rows_are_balanced_and_cover_the_grid():

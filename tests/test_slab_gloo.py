@@ -73,9 +73,35 @@ def _worker(rank, world, port, n, phi, seed, out_dir):
     dist.all_reduce(sums)
     np.savez(Path(out_dir) / f"boop{rank}.npz", gid=gid, q6=bo["q6"][:no], q6_arg=bo["q6_arg"][:no],
              neighbors=bo["neighbors"][:no], mean_q6=float(sums[0] / sums[1]), n_total=float(sums[1]))
-    # g(r): every rank bins its share of the pairs, counts are summed
-    counts = torch.zeros(40, dtype=torch.int64)
+    # g(r) (calculate_pcf, src/pcf.c:34-54): the positions go to every rank, rank k bins the pairs of the tile
+    # pairs w = k (mod world) -- tiles of 256 particles, the upper triangle walked row by row, as the library
+    # deals them (edmd_cuda_pcf_device) --, the integer histograms are all-reduced
+    dr, max_r = 0.1, min(lx, ly) / 2
+    nb = int(max_r / dr)
+    tile = 256
+    nt = (N + tile - 1) // tile
+    counts = torch.zeros(nb, dtype=torch.int64)
+    w = 0
+    for ta in range(nt):
+        for tb in range(ta, nt):
+            if w % world == rank:
+                ia = np.arange(ta * tile, min(N, (ta + 1) * tile))
+                ib = np.arange(tb * tile, min(N, (tb + 1) * tile))
+                ii, jj = np.meshgrid(ia, ib, indexing="ij")
+                keep = ii < jj
+                ii, jj = ii[keep], jj[keep]
+                dx, dy = cfg["x"][jj] - cfg["x"][ii], cfg["y"][jj] - cfg["y"][ii]
+                dx = np.where(dx >= lx / 2, dx - lx, np.where(dx < -lx / 2, dx + lx, dx))
+                dy = np.where(dy >= ly / 2, dy - ly, np.where(dy < -ly / 2, dy + ly, dy))
+                r = np.sqrt(dx * dx + dy * dy)
+                b = (r / dr).astype(np.int64)
+                ok = (r < max_r) & (b < nb)
+                counts += torch.from_numpy(np.bincount(b[ok], minlength=nb))
+            w += 1
+    mine = int(counts.sum())
     dist.all_reduce(counts)
+    if rank == 0:
+        np.savez(Path(out_dir) / "pcf.npz", counts=counts.numpy(), share0=mine)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -103,6 +129,11 @@ def test_slab_partition_and_halo_reproduce_the_global_sweep(tmp_path, world):
         for k in ("t_cross", "dir", "t_coll", "partner"):
             assert np.array_equal(z[k], want[k][g]), (r, k)
     assert seen.all()
+    # g(r): the all-reduced histogram of the ranks' shares is calculate_pcf's
+    z = np.load(tmp_path / "pcf.npz")
+    wg = orc.pcf(cfg["n"], cfg["lx"], cfg["ly"], cfg["x"], cfg["y"], 0.1, min(cfg["lx"], cfg["ly"]) / 2)
+    assert np.array_equal(z["counts"].astype(np.uint64), wg["counts"])
+    assert 0 < int(z["share0"]) < int(wg["counts"].sum())
     # psi6 per slab + the all-reduced mean
     wb = orc.boop_cutoff(cfg["n"], cfg["lx"], cfg["ly"], cfg["x"], cfg["y"], 2.5)
     for r in range(world):

@@ -333,6 +333,16 @@ def test_boop_ignores_nan_coordinates_and_counts_coincident_disks(pkg, oracle):
     assert want["neighbors"][17] == 0 and want["neighbors"][4321] == 0
     assert np.isfinite(b["q6"]).all() and np.isfinite(b["q6_arg"]).all()
     assert_boop_close(b, want)
+    # ... and against the unmodified reference itself where oracle/_ref exists (the same state through its own
+    # computeBOOPCutoff; tests/test_reference_edges.py pins the restatement on it in the CPU suite)
+    from oracle.oracle_py import Reference
+    if Reference.available():
+        ref = Reference()
+        ref.setup(n, c["lx"], c["ly"], 0.0, x, y, c["vx"], c["vy"], c["rad"], cell_xy=cells)
+        try:
+            assert_boop_close(b, ref.boop_cutoff(2.5))
+        finally:
+            ref.teardown()
     # the same without the strays (the plain variant of the tile kernel away from the box edges)
     x[17], y[4321] = c["x"][17], c["y"][4321]
     with pkg.EdmdCuda(n, c["lx"], c["ly"]) as ctx:
